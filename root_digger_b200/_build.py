@@ -1,0 +1,147 @@
+"""Build recipes (nvcc / g++) for the native libraries, all in-tree.
+
+  lib/librdk_b200.so   CUDA kernels + C ABI (include/rdk.h), sm_100a only
+  lib/librd_host.so    C++ host: traversal scheduler + model_t mirror, linked
+                       against librdk_b200.so
+  lib/liblbfgsb.so     the reference's vendored L-BFGS-B 3.0 (lib/lbfgsb/*.c),
+                       compiled from where it lies under /root/reference when
+                       that tree is present; never copied into this repo
+
+The oracle (test infrastructure) has its own recipe in oracle/Makefile and is
+built by build_oracle(); nothing in the product links it.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+PKG = ROOT / "root_digger_b200"
+LIBDIR = PKG / "lib"
+CSRC = PKG / "csrc"
+HOST = PKG / "host"
+INCLUDE = ROOT / "include"
+ORACLE = ROOT / "oracle"
+REFERENCE = Path("/root/reference")
+
+NVCC_ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+
+
+def _cxx() -> str:
+    return "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+
+
+def _cc() -> str:
+    return "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+
+
+def _nvcc() -> str:
+    for cand in ("/usr/local/cuda/bin/nvcc", shutil.which("nvcc")):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found: the CUDA engine cannot be built (there is no CPU fallback)")
+
+
+def _newer(target: Path, sources) -> bool:
+    if not target.exists():
+        return False
+    t = target.stat().st_mtime
+    return all(Path(s).stat().st_mtime <= t for s in sources)
+
+
+def _run(cmd, **kw):
+    res = subprocess.run([str(c) for c in cmd], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, **kw)
+    if res.returncode != 0:
+        raise RuntimeError("build failed: %s\n%s" % (" ".join(str(c) for c in cmd), res.stdout))
+    return res.stdout
+
+
+def build_engine(force: bool = False, verbose: bool = False) -> Path:
+    """nvcc -> lib/librdk_b200.so (sm_100a, -lineinfo)."""
+    LIBDIR.mkdir(exist_ok=True)
+    out = LIBDIR / "librdk_b200.so"
+    srcs = [CSRC / "rdk_abi.cu", CSRC / "rdk_host_math.cpp"]
+    deps = srcs + [CSRC / "rdk_kernels.cuh", INCLUDE / "rdk.h"]
+    if not force and _newer(out, deps):
+        return out
+    cmd = [_nvcc(), *NVCC_ARCH, "-lineinfo", "-O3", "-std=c++17", "--fmad=false",
+           "-ccbin", _cxx(),
+           "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall", "-shared", "-o", out, *srcs, "-ldl"]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    log = _run(cmd)
+    if verbose:
+        print(log)
+    return out
+
+
+def build_lbfgsb(force: bool = False) -> Path | None:
+    """Compile the reference's vendored L-BFGS-B from /root/reference (if present)."""
+    LIBDIR.mkdir(exist_ok=True)
+    out = LIBDIR / "liblbfgsb.so"
+    src_dir = REFERENCE / "lib" / "lbfgsb"
+    if not src_dir.is_dir():
+        return out if out.exists() else None
+    srcs = sorted(src_dir.glob("*.c"))
+    if not force and _newer(out, srcs):
+        return out
+    _run([_cc(), "-O2", "-fPIC", "-shared", "-w", "-I", src_dir, "-o", out, *srcs, "-lm"])
+    return out
+
+
+def host_sources():
+    return [HOST / "tree.cpp", HOST / "tree_capi.cpp", HOST / "msa.cpp", HOST / "model.cpp",
+            HOST / "lbfgsb_driver.cpp", HOST / "model_capi.cpp"]
+
+
+def build_host(force: bool = False) -> Path:
+    """g++ -> lib/librd_host.so (scheduler + model_t mirror on the CUDA engine)."""
+    engine = build_engine()
+    build_lbfgsb()
+    out = LIBDIR / "librd_host.so"
+    srcs = [s for s in host_sources() if s.exists()]
+    deps = srcs + list(HOST.glob("*.hpp")) + [INCLUDE / "rdk.h", engine]
+    if not force and _newer(out, deps):
+        return out
+    _run([_cxx(), "-std=c++17", "-O2", "-fPIC", "-fopenmp", "-Wall", "-ffp-contract=off", "-I", INCLUDE, "-shared",
+          "-o", out, *srcs, "-L", LIBDIR, "-lrdk_b200", "-ldl", "-Wl,-rpath,$ORIGIN"])
+    return out
+
+
+def build_oracle(force: bool = False) -> Path:
+    """TEST INFRASTRUCTURE: oracle/librd_oracle.so via oracle/Makefile."""
+    out = ORACLE / "librd_oracle.so"
+    deps = [ORACLE / "rd_oracle.c", ORACLE / "rd_oracle.h", ORACLE / "Makefile"]
+    if not force and _newer(out, deps):
+        return out
+    _run(["make", "-C", ORACLE, "-B" if force else "-s"])
+    return out
+
+
+def build_host_on_oracle(force: bool = False) -> Path:
+    """TEST INFRASTRUCTURE: the same host sources compiled against the oracle
+    through tests/oracle_shim/rdk.h -> tests/_build/librd_host_oracle.so."""
+    oracle = build_oracle()
+    build_lbfgsb()
+    outdir = ROOT / "tests" / "_build"
+    outdir.mkdir(exist_ok=True)
+    out = outdir / "librd_host_oracle.so"
+    srcs = [s for s in host_sources() if s.exists()]
+    shim = ROOT / "tests" / "oracle_shim"
+    deps = srcs + list(HOST.glob("*.hpp")) + [shim / "rdk.h", oracle]
+    if not force and _newer(out, deps):
+        return out
+    _run([_cxx(), "-std=c++17", "-O2", "-fPIC", "-fopenmp", "-Wall", "-ffp-contract=off", "-DRD_BACKEND_ORACLE",
+          "-I", shim, "-I", ORACLE, "-shared", "-o", out, *srcs, "-L", ORACLE, "-lrd_oracle", "-ldl",
+          "-Wl,-rpath," + str(ORACLE)])
+    return out
+
+
+def build_all(verbose: bool = False):
+    build_engine(verbose=verbose)
+    build_lbfgsb()
+    build_host()
+    build_oracle()
+    build_host_on_oracle()

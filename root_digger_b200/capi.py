@@ -1,0 +1,525 @@
+"""ctypes binding of the C ABI (include/rdk.h) and of the host scheduler.
+
+This is plumbing for tests, bench.py and Python callers; the product is the
+shared library.  Loading fails loudly when the CUDA library has not been built:
+there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+from . import _build
+
+RDK_SUCCESS = 1
+RDK_SCALE_BUFFER_NONE = -1
+RDK_ATTRIB_SITE_REPEATS = 1 << 10
+RDK_ATTRIB_NONREV = 1 << 11
+RDK_GAMMA_RATES_MEAN = 0
+RDK_GAMMA_RATES_MEDIAN = 1
+RDK_SHARD_ALIGN = 1024
+
+
+class Operation(C.Structure):
+    """rdk_operation_t / corax_operation_t"""
+    _fields_ = [
+        ("parent_clv_index", C.c_uint),
+        ("parent_scaler_index", C.c_int),
+        ("child1_clv_index", C.c_uint),
+        ("child1_matrix_index", C.c_uint),
+        ("child1_scaler_index", C.c_int),
+        ("child2_clv_index", C.c_uint),
+        ("child2_matrix_index", C.c_uint),
+        ("child2_scaler_index", C.c_int),
+    ]
+
+    def astuple(self):
+        return tuple(getattr(self, f[0]) for f in self._fields_)
+
+
+class PartitionStruct(C.Structure):
+    """public prefix of rdk_partition_t"""
+    _fields_ = [
+        ("tips", C.c_uint), ("clv_buffers", C.c_uint), ("states", C.c_uint), ("sites", C.c_uint),
+        ("rate_matrices", C.c_uint), ("prob_matrices", C.c_uint), ("rate_cats", C.c_uint),
+        ("scale_buffers", C.c_uint), ("attributes", C.c_uint),
+        ("subst_params", C.POINTER(C.POINTER(C.c_double))),
+        ("frequencies", C.POINTER(C.POINTER(C.c_double))),
+        ("rates", C.POINTER(C.c_double)),
+        ("rate_weights", C.POINTER(C.c_double)),
+        ("prop_invar", C.POINTER(C.c_double)),
+        ("pattern_weights", C.POINTER(C.c_uint)),
+        ("engine", C.c_void_p),
+    ]
+
+
+class Stats(C.Structure):
+    _fields_ = [(n, C.c_ulonglong) for n in (
+        "kernel_launches", "program_launches", "pmatrix_launches", "reduce_launches", "clv_ops",
+        "root_evals", "pmatrices", "algorithmic_bytes", "h2d_bytes", "d2h_bytes", "device_bytes")]
+
+    def asdict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+_dp = C.POINTER(C.c_double)
+_up = C.POINTER(C.c_uint)
+_pp = C.POINTER(PartitionStruct)
+
+_engine_lib = None
+_host_lib = None
+
+
+def _ptr(a, t):
+    return a.ctypes.data_as(t)
+
+
+def engine_lib_path() -> Path:
+    return _build.LIBDIR / "librdk_b200.so"
+
+
+def load_engine() -> C.CDLL:
+    """dlopen lib/librdk_b200.so (building it when nvcc is available)."""
+    global _engine_lib
+    if _engine_lib is not None:
+        return _engine_lib
+    path = engine_lib_path()
+    if not path.exists():
+        _build.build_engine()
+    if not path.exists():
+        raise RuntimeError(f"{path} is missing: build the CUDA engine first (no CPU fallback exists)")
+    L = C.CDLL(str(path), mode=C.RTLD_GLOBAL)
+    L.rdk_errno_location.restype = C.POINTER(C.c_int)
+    L.rdk_errmsg_location.restype = C.c_char_p
+    L.rdk_version.restype = C.c_char_p
+    L.rdk_partition_create.restype = _pp
+    L.rdk_partition_create.argtypes = [C.c_uint] * 9
+    L.rdk_partition_destroy.argtypes = [_pp]
+    L.rdk_partition_destroy.restype = None
+    L.rdk_set_tip_states.argtypes = [_pp, C.c_uint, C.c_void_p, C.c_char_p]
+    L.rdk_set_pattern_weights.argtypes = [_pp, _up]
+    L.rdk_set_pattern_weights.restype = None
+    L.rdk_set_subst_params.argtypes = [_pp, C.c_uint, _dp]
+    L.rdk_set_subst_params.restype = None
+    L.rdk_set_frequencies.argtypes = [_pp, C.c_uint, _dp]
+    L.rdk_set_frequencies.restype = None
+    L.rdk_set_category_rates.argtypes = [_pp, _dp]
+    L.rdk_set_category_rates.restype = None
+    L.rdk_set_category_weights.argtypes = [_pp, _dp]
+    L.rdk_set_category_weights.restype = None
+    L.rdk_update_invariant_sites.argtypes = [_pp]
+    L.rdk_update_invariant_sites_proportion.argtypes = [_pp, C.c_uint, C.c_double]
+    L.rdk_update_prob_matrices.argtypes = [_pp, _up, _up, _dp, C.c_uint]
+    L.rdk_update_clvs.argtypes = [_pp, C.POINTER(Operation), C.c_uint]
+    L.rdk_update_clvs.restype = None
+    L.rdk_compute_root_loglikelihood.argtypes = [_pp, C.c_uint, C.c_int, _up, _dp]
+    L.rdk_compute_root_loglikelihood.restype = C.c_double
+    L.rdk_compute_gamma_cats.argtypes = [C.c_double, C.c_uint, _dp, C.c_int]
+    L.rdk_msa_empirical_frequencies.argtypes = [_pp]
+    L.rdk_msa_empirical_frequencies.restype = C.c_void_p
+    L.rdk_root_loglikelihood_multi.argtypes = [_pp, C.POINTER(Operation), _up, _up, _dp, C.c_uint, _dp]
+    L.rdk_sweep_root_placements.argtypes = [_pp, C.c_uint, _up, _up, _up, _up, _dp, _up,
+                                            C.POINTER(Operation), C.c_uint, C.c_int, _dp]
+    L.rdk_partition_set_shard.argtypes = [_pp, C.c_ulonglong, C.c_ulonglong]
+    L.rdk_comm_unique_id.argtypes = [C.c_void_p]
+    L.rdk_partition_attach_comm.argtypes = [_pp, C.c_int, C.c_int, C.c_void_p]
+    L.rdk_partition_flush.argtypes = [_pp]
+    L.rdk_partition_sync.argtypes = [_pp]
+    L.rdk_partition_set_stream.argtypes = [_pp, C.c_void_p]
+    L.rdk_partition_stream.argtypes = [_pp]
+    L.rdk_partition_stream.restype = C.c_void_p
+    L.rdk_get_clv.argtypes = [_pp, C.c_uint, _dp]
+    L.rdk_get_scale_buffer.argtypes = [_pp, C.c_int, _up]
+    L.rdk_get_pmatrix.argtypes = [_pp, C.c_uint, _dp]
+    L.rdk_partition_stats.argtypes = [_pp, C.POINTER(Stats)]
+    L.rdk_partition_stats.restype = None
+    L.rdk_partition_reset_stats.argtypes = [_pp]
+    L.rdk_partition_reset_stats.restype = None
+    L.rdk_partition_set_launch_config.argtypes = [_pp, C.c_int, C.c_int, C.c_int]
+    L.rdk_set_device.argtypes = [C.c_int]
+    _engine_lib = L
+    return L
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def _err(L) -> str:
+    return L.rdk_errmsg_location().decode(errors="replace")
+
+
+def ops_array(ops) -> C.Array:
+    """list of 8-tuples / Operation -> ctypes array"""
+    arr = (Operation * max(1, len(ops)))()
+    for i, o in enumerate(ops):
+        if isinstance(o, Operation):
+            arr[i] = o
+        else:
+            arr[i] = Operation(*o)
+    return arr
+
+
+def gamma_cats(alpha: float, k: int, mode: int = RDK_GAMMA_RATES_MEAN) -> np.ndarray:
+    L = load_engine()
+    out = np.zeros(k)
+    if L.rdk_compute_gamma_cats(alpha, k, _ptr(out, _dp), mode) != RDK_SUCCESS:
+        raise EngineError(_err(L))
+    return out
+
+
+class Partition:
+    """One rdk_partition_t (a site shard resident on one GPU)."""
+
+    def __init__(self, tips: int, sites: int, rate_cats: int = 4, *, clv_buffers: int | None = None,
+                 prob_matrices: int | None = None, scale_buffers: int | None = None,
+                 attributes: int = RDK_ATTRIB_NONREV | RDK_ATTRIB_SITE_REPEATS, device: int | None = None):
+        self.L = load_engine()
+        if device is not None:
+            if self.L.rdk_set_device(device) != RDK_SUCCESS:
+                raise EngineError(_err(self.L))
+        branches = 2 * tips - 2
+        self.tips, self.sites, self.K = tips, sites, rate_cats
+        self.clv_buffers = branches if clv_buffers is None else clv_buffers
+        self.prob_matrices = branches if prob_matrices is None else prob_matrices
+        self.scale_buffers = branches if scale_buffers is None else scale_buffers
+        self.p = self.L.rdk_partition_create(tips, self.clv_buffers, 4, sites, 1, self.prob_matrices,
+                                             rate_cats, self.scale_buffers, attributes)
+        if not self.p:
+            raise EngineError("rdk_partition_create failed: " + _err(self.L))
+        self._zeros = (C.c_uint * max(1, rate_cats))()
+
+    def close(self):
+        if getattr(self, "p", None):
+            self.L.rdk_partition_destroy(self.p)
+            self.p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- inputs
+    def set_tip_states(self, tip: int, seq: bytes):
+        assert len(seq) >= self.sites
+        rc = self.L.rdk_set_tip_states(self.p, tip, C.addressof(C.c_ulonglong.in_dll(self.L, "rdk_map_nt")), seq)
+        if rc != RDK_SUCCESS:
+            raise EngineError(_err(self.L))
+
+    def set_pattern_weights(self, w):
+        w = np.ascontiguousarray(w, dtype=np.uint32)
+        self.L.rdk_set_pattern_weights(self.p, _ptr(w, _up))
+
+    def set_subst_params(self, r):
+        r = np.ascontiguousarray(r, dtype=np.float64)
+        self.L.rdk_set_subst_params(self.p, 0, _ptr(r, _dp))
+
+    def set_frequencies(self, f):
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        self.L.rdk_set_frequencies(self.p, 0, _ptr(f, _dp))
+
+    def set_category_rates(self, r):
+        r = np.ascontiguousarray(r, dtype=np.float64)
+        self.L.rdk_set_category_rates(self.p, _ptr(r, _dp))
+
+    def set_category_weights(self, w):
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        self.L.rdk_set_category_weights(self.p, _ptr(w, _dp))
+
+    # ---- hot path
+    def update_prob_matrices(self, matrix_indices, branch_lengths):
+        mi = np.ascontiguousarray(matrix_indices, dtype=np.uint32)
+        bl = np.ascontiguousarray(branch_lengths, dtype=np.float64)
+        rc = self.L.rdk_update_prob_matrices(self.p, self._zeros, _ptr(mi, _up), _ptr(bl, _dp), len(mi))
+        if rc != RDK_SUCCESS:
+            raise EngineError(_err(self.L))
+
+    def update_clvs(self, ops):
+        arr = ops if isinstance(ops, C.Array) else ops_array(ops)
+        n = len(ops)
+        self.L.rdk_errno_location()[0] = 0
+        self.L.rdk_update_clvs(self.p, arr, n)
+        if self.L.rdk_errno_location()[0] != 0:
+            raise EngineError(_err(self.L))
+
+    def root_loglikelihood(self, clv_index: int, scaler_index: int, persite: bool = False):
+        ps = np.zeros(self.sites) if persite else None
+        v = self.L.rdk_compute_root_loglikelihood(self.p, clv_index, scaler_index, self._zeros,
+                                                  _ptr(ps, _dp) if persite else None)
+        if persite:
+            return v, ps
+        return v
+
+    def root_loglikelihood_multi(self, root_op, branch_length_pairs):
+        bl = np.ascontiguousarray(branch_length_pairs, dtype=np.float64).reshape(-1)
+        n = len(bl) // 2
+        out = np.zeros(n)
+        op = root_op if isinstance(root_op, Operation) else Operation(*root_op)
+        rc = self.L.rdk_root_loglikelihood_multi(self.p, C.byref(op), self._zeros, self._zeros, _ptr(bl, _dp), n,
+                                                 _ptr(out, _dp))
+        if rc != RDK_SUCCESS:
+            raise EngineError(_err(self.L))
+        return out
+
+    def sweep_root_placements(self, pm_offsets, matrix_indices, branch_lengths, op_offsets, ops,
+                              root_clv_index: int, root_scaler_index: int):
+        pmo = np.ascontiguousarray(pm_offsets, dtype=np.uint32)
+        mi = np.ascontiguousarray(matrix_indices, dtype=np.uint32)
+        bl = np.ascontiguousarray(branch_lengths, dtype=np.float64)
+        opo = np.ascontiguousarray(op_offsets, dtype=np.uint32)
+        arr = ops if isinstance(ops, C.Array) else ops_array(ops)
+        n = len(pmo) - 1
+        out = np.zeros(n)
+        rc = self.L.rdk_sweep_root_placements(self.p, n, self._zeros, self._zeros, _ptr(pmo, _up), _ptr(mi, _up),
+                                              _ptr(bl, _dp), _ptr(opo, _up), arr, root_clv_index,
+                                              root_scaler_index, _ptr(out, _dp))
+        if rc != RDK_SUCCESS:
+            raise EngineError(_err(self.L))
+        return out
+
+    def empirical_frequencies(self) -> np.ndarray:
+        ptr = self.L.rdk_msa_empirical_frequencies(self.p)
+        if not ptr:
+            raise EngineError(_err(self.L))
+        out = np.array(C.cast(ptr, _dp)[0:4])
+        libc = C.CDLL(None)
+        libc.free.argtypes = [C.c_void_p]
+        libc.free(ptr)
+        return out
+
+    # ---- sharding
+    def set_shard(self, site_offset: int, global_sites: int):
+        if self.L.rdk_partition_set_shard(self.p, site_offset, global_sites) != RDK_SUCCESS:
+            raise EngineError(_err(self.L))
+
+    def attach_comm(self, nranks: int, rank: int, unique_id: bytes):
+        buf = C.create_string_buffer(unique_id, 128)
+        if self.L.rdk_partition_attach_comm(self.p, nranks, rank, buf) != RDK_SUCCESS:
+            raise EngineError(_err(self.L))
+
+    # ---- plumbing
+    def flush(self):
+        if self.L.rdk_partition_flush(self.p) != RDK_SUCCESS:
+            raise EngineError(_err(self.L))
+
+    def sync(self):
+        if self.L.rdk_partition_sync(self.p) != RDK_SUCCESS:
+            raise EngineError(_err(self.L))
+
+    def set_stream(self, cuda_stream: int):
+        if self.L.rdk_partition_set_stream(self.p, C.c_void_p(cuda_stream)) != RDK_SUCCESS:
+            raise EngineError(_err(self.L))
+
+    def set_launch_config(self, ctas_per_sm=0, threads=0, elems=0):
+        if self.L.rdk_partition_set_launch_config(self.p, ctas_per_sm, threads, elems) != RDK_SUCCESS:
+            raise EngineError(_err(self.L))
+
+    def get_clv(self, idx: int) -> np.ndarray:
+        out = np.zeros(self.sites * self.K * 4)
+        if self.L.rdk_get_clv(self.p, idx, _ptr(out, _dp)) != RDK_SUCCESS:
+            raise EngineError(_err(self.L))
+        return out.reshape(self.sites, self.K, 4)
+
+    def get_scaler(self, idx: int) -> np.ndarray:
+        out = np.zeros(self.sites, dtype=np.uint32)
+        if self.L.rdk_get_scale_buffer(self.p, idx, _ptr(out, _up)) != RDK_SUCCESS:
+            raise EngineError(_err(self.L))
+        return out
+
+    def get_pmatrix(self, idx: int) -> np.ndarray:
+        out = np.zeros(self.K * 16)
+        if self.L.rdk_get_pmatrix(self.p, idx, _ptr(out, _dp)) != RDK_SUCCESS:
+            raise EngineError(_err(self.L))
+        return out.reshape(self.K, 4, 4)
+
+    def stats(self) -> dict:
+        s = Stats()
+        self.L.rdk_partition_stats(self.p, C.byref(s))
+        return s.asdict()
+
+    def reset_stats(self):
+        self.L.rdk_partition_reset_stats(self.p)
+
+
+def comm_unique_id() -> bytes:
+    L = load_engine()
+    buf = C.create_string_buffer(128)
+    if L.rdk_comm_unique_id(buf) != RDK_SUCCESS:
+        raise EngineError(_err(L))
+    return buf.raw
+
+
+# ---------------------------------------------------------------------------
+# host traversal scheduler (rooted_tree_t mirror)
+# ---------------------------------------------------------------------------
+def load_tree_lib(path: Path | None = None) -> C.CDLL:
+    global _host_lib
+    if path is None and _host_lib is not None:
+        return _host_lib
+    if path is None:
+        path = _build.LIBDIR / "librd_host.so"
+        if not path.exists():
+            _build.build_host()
+    L = C.CDLL(str(path))
+    vp = C.c_void_p
+    L.rdh_last_error.restype = C.c_char_p
+    L.rdh_tree_from_newick.restype = vp
+    L.rdh_tree_from_newick.argtypes = [C.c_char_p]
+    L.rdh_tree_from_file.restype = vp
+    L.rdh_tree_from_file.argtypes = [C.c_char_p]
+    L.rdh_tree_copy.restype = vp
+    L.rdh_tree_copy.argtypes = [vp]
+    L.rdh_tree_destroy.argtypes = [vp]
+    L.rdh_tree_destroy.restype = None
+    for f in ("tip_count", "inner_count", "branch_count", "root_count", "root_clv_index"):
+        getattr(L, "rdh_tree_" + f).argtypes = [vp]
+        getattr(L, "rdh_tree_" + f).restype = C.c_uint
+    for f in ("root_scaler_index", "rooted", "sanity_check", "unroot"):
+        getattr(L, "rdh_tree_" + f).argtypes = [vp]
+        getattr(L, "rdh_tree_" + f).restype = C.c_int
+    L.rdh_tree_root_info.argtypes = [vp, C.c_uint, _dp, C.POINTER(C.c_int), C.c_char_p, C.c_uint]
+    L.rdh_tree_root_id_by_label.argtypes = [vp, C.c_char_p]
+    L.rdh_tree_tip_index.argtypes = [vp, C.c_char_p]
+    L.rdh_tree_tip_label.argtypes = [vp, C.c_uint, C.c_char_p, C.c_uint]
+    sig = [vp, C.c_uint, C.c_double, C.POINTER(Operation), C.c_uint, _up, _up, _dp, C.c_uint, _up]
+    L.rdh_tree_generate_operations.argtypes = sig
+    L.rdh_tree_generate_root_update_operations.argtypes = sig
+    L.rdh_tree_generate_derivative_operations.argtypes = [vp, C.c_uint, C.c_double, C.POINTER(Operation), _up, _dp]
+    L.rdh_tree_root_by.argtypes = [vp, C.c_uint, C.c_double]
+    L.rdh_tree_newick.argtypes = [vp, C.c_int]
+    L.rdh_tree_newick.restype = vp
+    L.rdh_free.argtypes = [vp]
+    L.rdh_free.restype = None
+    L.rdh_tree_annotate_branch.argtypes = [vp, C.c_uint, C.c_char_p, C.c_char_p]
+    L.rdh_tree_annotate_lwr.argtypes = [vp, C.c_uint, C.c_double, C.c_double, C.c_double]
+    L.rdh_tree_rank_roots.argtypes = [vp, C.c_int, _up, C.c_uint]
+    if path == _build.LIBDIR / "librd_host.so":
+        _host_lib = L
+    return L
+
+
+class RootedTree:
+    """rooted_tree_t through the C wrappers (reference src/tree.hpp:54-201)."""
+
+    def __init__(self, newick: str | None = None, *, path: str | None = None, lib: C.CDLL | None = None, _h=None):
+        self.L = lib or load_tree_lib()
+        if _h is not None:
+            self.h = _h
+        elif newick is not None:
+            self.h = self.L.rdh_tree_from_newick(newick.encode())
+        else:
+            self.h = self.L.rdh_tree_from_file(str(path).encode())
+        if not self.h:
+            raise ValueError("tree could not be parsed: " + self.L.rdh_last_error().decode())
+        self.h = C.c_void_p(self.h)
+        n = self.tip_count
+        self._cap = 2 * n + 2
+        self._ops = (Operation * self._cap)()
+        self._pm = (C.c_uint * self._cap)()
+        self._br = (C.c_double * self._cap)()
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.rdh_tree_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def copy(self) -> "RootedTree":
+        h = self.L.rdh_tree_copy(self.h)
+        if not h:
+            raise RuntimeError(self.L.rdh_last_error().decode())
+        return RootedTree(lib=self.L, _h=h)
+
+    tip_count = property(lambda s: s.L.rdh_tree_tip_count(s.h))
+    inner_count = property(lambda s: s.L.rdh_tree_inner_count(s.h))
+    branch_count = property(lambda s: s.L.rdh_tree_branch_count(s.h))
+    root_count = property(lambda s: s.L.rdh_tree_root_count(s.h))
+    root_clv_index = property(lambda s: s.L.rdh_tree_root_clv_index(s.h))
+    root_scaler_index = property(lambda s: s.L.rdh_tree_root_scaler_index(s.h))
+    rooted = property(lambda s: bool(s.L.rdh_tree_rooted(s.h)))
+
+    def sanity_check(self) -> bool:
+        return bool(self.L.rdh_tree_sanity_check(self.h))
+
+    def root_info(self, rid: int):
+        br = C.c_double()
+        internal = C.c_int()
+        label = C.create_string_buffer(256)
+        if not self.L.rdh_tree_root_info(self.h, rid, C.byref(br), C.byref(internal), label, 256):
+            raise IndexError(self.L.rdh_last_error().decode())
+        return br.value, bool(internal.value), label.value.decode()
+
+    def root_id(self, label: str) -> int:
+        r = self.L.rdh_tree_root_id_by_label(self.h, label.encode())
+        if r < 0:
+            raise KeyError(label)
+        return r
+
+    def tip_index(self, label: str) -> int:
+        return self.L.rdh_tree_tip_index(self.h, label.encode())
+
+    def tip_label(self, index: int) -> str:
+        buf = C.create_string_buffer(256)
+        if not self.L.rdh_tree_tip_label(self.h, index, buf, 256):
+            raise IndexError(index)
+        return buf.value.decode()
+
+    def _bundle(self, fn, rid, ratio):
+        no, npm = C.c_uint(), C.c_uint()
+        if not fn(self.h, rid, ratio, self._ops, self._cap, C.byref(no), self._pm, self._br, self._cap, C.byref(npm)):
+            raise RuntimeError(self.L.rdh_last_error().decode())
+        ops = [Operation(*self._ops[i].astuple()) for i in range(no.value)]
+        pm = np.array(self._pm[: npm.value], dtype=np.uint32)
+        br = np.array(self._br[: npm.value], dtype=np.float64)
+        return ops, pm, br
+
+    def generate_operations(self, rid: int, ratio: float = 0.5):
+        return self._bundle(self.L.rdh_tree_generate_operations, rid, ratio)
+
+    def generate_root_update_operations(self, rid: int, ratio: float = 0.5):
+        return self._bundle(self.L.rdh_tree_generate_root_update_operations, rid, ratio)
+
+    def generate_derivative_operations(self, rid: int, ratio: float = 0.5):
+        op = Operation()
+        pm = (C.c_uint * 2)()
+        br = (C.c_double * 2)()
+        if not self.L.rdh_tree_generate_derivative_operations(self.h, rid, ratio, C.byref(op), pm, br):
+            raise RuntimeError(self.L.rdh_last_error().decode())
+        return op, np.array(pm[:], dtype=np.uint32), np.array(br[:], dtype=np.float64)
+
+    def root_by(self, rid: int, ratio: float = 0.5):
+        if not self.L.rdh_tree_root_by(self.h, rid, ratio):
+            raise RuntimeError(self.L.rdh_last_error().decode())
+
+    def unroot(self):
+        if not self.L.rdh_tree_unroot(self.h):
+            raise RuntimeError(self.L.rdh_last_error().decode())
+
+    def newick(self, annotations: bool = True) -> str:
+        p = self.L.rdh_tree_newick(self.h, 1 if annotations else 0)
+        if not p:
+            raise RuntimeError(self.L.rdh_last_error().decode())
+        s = C.string_at(p).decode()
+        self.L.rdh_free(p)
+        return s
+
+    def annotate_branch(self, rid: int, key: str, value: str):
+        self.L.rdh_tree_annotate_branch(self.h, rid, key.encode(), value.encode())
+
+    def annotate_lwr(self, rid: int, ratio: float, lwr: float, llh: float):
+        self.L.rdh_tree_annotate_lwr(self.h, rid, ratio, lwr, llh)
+
+    def rank_roots(self, which: str = "modified_mad"):
+        n = self.root_count
+        ids = (C.c_uint * n)()
+        if not self.L.rdh_tree_rank_roots(self.h, 0 if which == "midpoint" else 1, ids, n):
+            raise RuntimeError(self.L.rdh_last_error().decode())
+        return list(ids)

@@ -1,0 +1,1232 @@
+// rdk_abi.cu -- the C ABI of include/rdk.h on top of the sm_100a kernels.
+//
+// Host-side responsibilities: partition memory in HBM, the P-matrix pool with
+// slot renaming, recording of P-matrix updates / CLV operations into a program,
+// launch of the three kernels (pmat_expm_nonrev, clv_program, tree_reduce),
+// NCCL exchange of the per-shard tree nodes, and the error channel.
+//
+// There is deliberately no CPU implementation of the path in this file: if a
+// CUDA call fails the entry point fails (RDK_FAILURE / NaN).
+#include "../../include/rdk.h"
+#include "rdk_kernels.cuh"
+
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <mutex>
+#include <vector>
+
+using namespace rdk;
+
+// ---------------------------------------------------------------------------
+// error channel (replaces corax_errno / corax_errmsg)
+// ---------------------------------------------------------------------------
+static thread_local int  tl_errno = 0;
+static thread_local char tl_errmsg[256] = {0};
+static thread_local int  tl_device = -1;
+
+extern "C" int  *rdk_errno_location(void) { return &tl_errno; }
+extern "C" char *rdk_errmsg_location(void) { return tl_errmsg; }
+
+static int fail(int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(tl_errmsg, sizeof(tl_errmsg), fmt, ap);
+  va_end(ap);
+  tl_errno = code;
+  return RDK_FAILURE;
+}
+
+#define CUDA_TRY(expr)                                                              \
+  do {                                                                              \
+    cudaError_t _e = (expr);                                                        \
+    if (_e != cudaSuccess)                                                          \
+      return fail(RDK_ERROR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                  __FILE__, __LINE__);                                              \
+  } while (0)
+
+extern "C" const rdk_state_t rdk_map_nt[256] = {
+    0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,   // 0
+    0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,   // 16
+    0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  15, 0,  0,   // 32  '-'=45
+    0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  15,  // 48  '?'=63
+    0,  1,  14, 2,  13, 0,  0,  4,  11, 0,  0,  12, 0,  3,  15, 15,  // 64  @ABCDEFGHIJKLMNO
+    0,  0,  5,  6,  8,  8,  7,  9,  15, 10, 0,  0,  0,  0,  0,  0,   // 80  PQRSTUVWXYZ
+    0,  1,  14, 2,  13, 0,  0,  4,  11, 0,  0,  12, 0,  3,  15, 15,  // 96  `abcdefghijklmno
+    0,  0,  5,  6,  8,  8,  7,  9,  15, 10, 0,  0,  0,  0,  0,  0,   // 112 pqrstuvwxyz
+};
+
+// ---------------------------------------------------------------------------
+// NCCL, resolved lazily with dlopen so that the library has no link-time
+// dependency on it (single-GPU use never touches NCCL)
+// ---------------------------------------------------------------------------
+struct Id128 {  // ncclUniqueId: 128 opaque bytes, passed by value
+  char b[128];
+};
+namespace {
+struct NcclApi {
+  void *handle = nullptr;
+  int (*GetUniqueId)(void *) = nullptr;
+  int (*CommInitRank)(void **, int, Id128, int) = nullptr;
+  int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void *) = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+};
+}  // namespace
+static NcclApi    g_nccl;
+static std::mutex g_nccl_mu;
+
+static int load_nccl() {
+  std::lock_guard<std::mutex> lk(g_nccl_mu);
+  if (g_nccl.handle) return RDK_SUCCESS;
+  const char *names[] = {"libnccl.so.2", "libnccl.so"};
+  void       *h = nullptr;
+  for (const char *n : names) {
+    h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (h) break;
+  }
+  if (!h) return fail(RDK_ERROR_COMM, "cannot dlopen libnccl.so.2: %s", dlerror());
+  g_nccl.GetUniqueId = (int (*)(void *))dlsym(h, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (int (*)(void **, int, Id128, int))dlsym(h, "ncclCommInitRank");
+  g_nccl.AllReduce =
+      (int (*)(const void *, void *, size_t, int, int, void *, cudaStream_t))dlsym(h, "ncclAllReduce");
+  g_nccl.CommDestroy = (int (*)(void *))dlsym(h, "ncclCommDestroy");
+  g_nccl.GetErrorString = (const char *(*)(int))dlsym(h, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy)
+    return fail(RDK_ERROR_COMM, "libnccl is missing required symbols");
+  g_nccl.handle = h;
+  return RDK_SUCCESS;
+}
+// ncclDataType_t / ncclRedOp_t values (stable across NCCL 2.x)
+static const int kNcclFloat64 = 8, kNcclUint64 = 5, kNcclSum = 0;
+
+// ---------------------------------------------------------------------------
+// engine state
+// ---------------------------------------------------------------------------
+namespace {
+
+struct Ring {  // pinned host ring + device ring of equal size, bump-allocated
+  char  *h = nullptr, *d = nullptr;
+  size_t cap = 0, head = 0;
+};
+
+struct Engine {
+  int          device = 0;
+  cudaStream_t stream = nullptr;
+  bool         own_stream = true;
+  int          sm_count = 148;
+
+  unsigned tips = 0, clv_buffers = 0, S = 0, K = 0, prob_matrices = 0, scale_buffers = 0;
+  size_t   clv_elems = 0;   // S*K*4 doubles per CLV
+  size_t   tip_stride = 0;  // bytes per tip row
+
+  unsigned char          *d_tips = nullptr;
+  std::vector<double *>   clv_ptr;   // per inner CLV buffer, lazily allocated
+  std::vector<void *>     slabs;     // cudaMalloc'd slabs backing clv_ptr
+  double                 *slab_cur = nullptr;
+  unsigned                slab_left = 0;
+  unsigned               *d_scalers = nullptr;  // [scale_buffers][S]
+  unsigned               *d_weights = nullptr;  // [S]
+  unsigned long long     *d_hist = nullptr;     // [16]
+
+  // P-matrix pool with slot renaming
+  double               *d_pool = nullptr;
+  unsigned              pool_slots = 0;
+  std::vector<unsigned> pm_map;      // matrix index -> physical slot
+  std::vector<unsigned> pm_free;     // free physical slots
+  std::vector<unsigned> pm_retired;  // freed at the next flush
+
+  // recorded work
+  std::vector<PmatEntry> pend_pm;
+  std::vector<Instr>     pend_prog;
+  unsigned               pend_slots = 0;  // eval slots used by pend_prog
+  unsigned long long     pend_bytes = 0;  // algorithmic bytes of pend_prog
+  unsigned               pend_ops = 0, pend_evals = 0;
+  bool                   want_persite = false;
+
+  Ring    ring;
+  double *d_partials = nullptr;
+  size_t  partials_cap = 0;  // doubles
+  double *d_nodes = nullptr; // sharded: [slots][global_blocks]
+  size_t  nodes_cap = 0;
+  double *d_persite = nullptr;
+  double *h_results = nullptr;  // pinned, device-visible
+  size_t  results_cap = 0;      // doubles
+
+  // shard / comm
+  unsigned long long site_offset = 0, global_sites = 0;
+  void              *comm = nullptr;
+  int                nranks = 1, rank = 0;
+
+  // launch config
+  int ctas_per_sm = 0, threads = 0, elems = 0;
+
+  rdk_stats_t stats{};
+  std::mutex  mu;
+};
+
+Engine *eng(rdk_partition_t *p) { return reinterpret_cast<Engine *>(p->engine); }
+
+unsigned next_pow2(unsigned long long n) {
+  unsigned long long v = 1;
+  while (v < n) v <<= 1;
+  return (unsigned)v;
+}
+
+int dev_alloc(Engine *e, void **ptr, size_t bytes) {
+  if (bytes == 0) bytes = 16;
+  cudaError_t err = cudaMalloc(ptr, bytes);
+  if (err != cudaSuccess)
+    return fail(RDK_ERROR_MEM, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(err));
+  e->stats.device_bytes += bytes;
+  return RDK_SUCCESS;
+}
+
+int ring_alloc(Engine *e, size_t bytes, char **h, char **d) {
+  bytes = (bytes + 255) & ~size_t(255);
+  if (bytes > e->ring.cap) {
+    // grow: drain the stream, then replace both rings
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    size_t ncap = std::max(bytes * 2, e->ring.cap * 2);
+    if (e->ring.h) cudaFreeHost(e->ring.h);
+    if (e->ring.d) {
+      cudaFree(e->ring.d);
+      e->stats.device_bytes -= e->ring.cap;
+    }
+    e->ring.h = e->ring.d = nullptr;
+    CUDA_TRY(cudaMallocHost((void **)&e->ring.h, ncap));
+    if (!dev_alloc(e, (void **)&e->ring.d, ncap)) return RDK_FAILURE;
+    e->ring.cap = ncap;
+    e->ring.head = 0;
+  }
+  if (e->ring.head + bytes > e->ring.cap) {
+    // wrap: everything enqueued so far must have consumed its staging data
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    e->ring.head = 0;
+  }
+  *h = e->ring.h + e->ring.head;
+  *d = e->ring.d + e->ring.head;
+  e->ring.head += bytes;
+  return RDK_SUCCESS;
+}
+
+int ensure_clv(Engine *e, unsigned buf) {
+  if (e->clv_ptr[buf]) return RDK_SUCCESS;
+  if (e->slab_left == 0) {
+    // slabs of up to 64 CLVs or ~1 GiB, whichever is smaller
+    size_t   bytes_one = e->clv_elems * sizeof(double);
+    if (bytes_one == 0) bytes_one = 32;
+    unsigned n = (unsigned)std::max<size_t>(1, std::min<size_t>(64, (size_t(1) << 30) / bytes_one));
+    unsigned missing = 0;
+    for (double *q : e->clv_ptr)
+      if (!q) ++missing;
+    n = std::min(n, std::max(1u, missing));
+    void *slab = nullptr;
+    if (!dev_alloc(e, &slab, bytes_one * n)) return RDK_FAILURE;
+    e->slabs.push_back(slab);
+    e->slab_cur = reinterpret_cast<double *>(slab);
+    e->slab_left = n;
+  }
+  e->clv_ptr[buf] = e->slab_cur;
+  e->slab_cur += e->clv_elems ? e->clv_elems : 4;
+  e->slab_left -= 1;
+  return RDK_SUCCESS;
+}
+
+// ---- launches --------------------------------------------------------------
+int launch_pmatrices(rdk_partition_t *p) {
+  Engine *e = eng(p);
+  if (e->pend_pm.empty()) return RDK_SUCCESS;
+  PmatArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n = (int)e->pend_pm.size();
+  a.K = (int)e->K;
+  for (int i = 0; i < 12; ++i) a.r[i] = p->subst_params[0][i];
+  for (int i = 0; i < 4; ++i) a.pi[i] = p->frequencies[0][i];
+  a.pinv = p->prop_invar[0];
+  for (unsigned k = 0; k < e->K; ++k) a.rates[k] = p->rates[k];
+  a.pool = e->d_pool;
+  if (a.n <= kPmatInline) {
+    for (int i = 0; i < a.n; ++i) a.inl[i] = e->pend_pm[i];
+  } else {
+    char  *h, *d;
+    size_t bytes = sizeof(PmatEntry) * e->pend_pm.size();
+    if (!ring_alloc(e, bytes, &h, &d)) return RDK_FAILURE;
+    memcpy(h, e->pend_pm.data(), bytes);
+    CUDA_TRY(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, e->stream));
+    e->stats.h2d_bytes += bytes;
+    a.entries = reinterpret_cast<const PmatEntry *>(d);
+  }
+  int total = a.n * a.K;
+  int block = 64, grid = (total + block - 1) / block;
+  pmat_expm_nonrev_kernel<<<grid, block, 0, e->stream>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  e->stats.kernel_launches++;
+  e->stats.pmatrix_launches++;
+  e->stats.pmatrices += e->pend_pm.size();
+  e->pend_pm.clear();
+  return RDK_SUCCESS;
+}
+
+template <int K>
+void launch_program_E(const ProgArgs &a, int grid, int threads, int E, cudaStream_t st) {
+  switch (E) {
+    case 1: clv_program_kernel<K, 1><<<grid, threads, 0, st>>>(a); break;
+    case 4: clv_program_kernel<K, 4><<<grid, threads, 0, st>>>(a); break;
+    default: clv_program_kernel<K, 2><<<grid, threads, 0, st>>>(a); break;
+  }
+}
+
+int ensure_partials(Engine *e, unsigned slots, unsigned stride) {
+  size_t need = (size_t)slots * stride;
+  if (need > e->partials_cap) {
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    if (e->d_partials) {
+      cudaFree(e->d_partials);
+      e->stats.device_bytes -= e->partials_cap * sizeof(double);
+    }
+    size_t ncap = std::max(need, e->partials_cap * 2);
+    if (!dev_alloc(e, (void **)&e->d_partials, ncap * sizeof(double))) return RDK_FAILURE;
+    e->partials_cap = ncap;
+  }
+  if (slots > e->results_cap) {
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    if (e->h_results) cudaFreeHost(e->h_results);
+    size_t ncap = std::max<size_t>(slots, std::max<size_t>(64, e->results_cap * 2));
+    CUDA_TRY(cudaHostAlloc((void **)&e->h_results, ncap * sizeof(double), cudaHostAllocMapped));
+    e->results_cap = ncap;
+  }
+  return RDK_SUCCESS;
+}
+
+// launch recorded P-matrix work and the recorded program (no host sync)
+int flush(rdk_partition_t *p) {
+  Engine *e = eng(p);
+  if (!launch_pmatrices(p)) return RDK_FAILURE;
+  if (e->pend_prog.empty()) {
+    for (unsigned s : e->pm_retired) e->pm_free.push_back(s);
+    e->pm_retired.clear();
+    return RDK_SUCCESS;
+  }
+  const unsigned nelem = e->S * e->K;
+  const unsigned n_witer = (nelem + 31) / 32;
+  ProgArgs       a;
+  memset(&a, 0, sizeof(a));
+  a.n_instr = (int)e->pend_prog.size();
+  a.nelem = nelem;
+  a.n_witer = n_witer;
+  a.weights = e->d_weights;
+  a.partial_stride = n_witer ? n_witer : 1;
+  for (int i = 0; i < 4; ++i) a.pi[i] = p->frequencies[0][i];
+  for (unsigned k = 0; k < e->K; ++k) a.w[k] = p->rate_weights[k];
+  if (e->pend_slots) {
+    if (!ensure_partials(e, e->pend_slots, a.partial_stride)) return RDK_FAILURE;
+    a.partials = e->d_partials;
+  }
+  a.persite = e->want_persite ? e->d_persite : nullptr;
+  if (a.n_instr <= kProgInline) {
+    for (int i = 0; i < a.n_instr; ++i) a.inl[i] = e->pend_prog[i];
+  } else {
+    char  *h, *d;
+    size_t bytes = sizeof(Instr) * e->pend_prog.size();
+    if (!ring_alloc(e, bytes, &h, &d)) return RDK_FAILURE;
+    memcpy(h, e->pend_prog.data(), bytes);
+    CUDA_TRY(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, e->stream));
+    e->stats.h2d_bytes += bytes;
+    a.prog = reinterpret_cast<const Instr *>(d);
+  }
+  if (nelem > 0) {
+    int threads = e->threads ? e->threads : 256;
+    int per_sm = e->ctas_per_sm ? e->ctas_per_sm : 2;
+    int E = e->elems ? e->elems : 2;
+    int grid = e->sm_count * per_sm;
+    // never launch more warps than warp iterations
+    int max_grid = (int)((n_witer + (threads / 32) - 1) / (threads / 32));
+    grid = std::max(1, std::min(grid, max_grid));
+    switch (e->K) {
+      case 1: launch_program_E<1>(a, grid, threads, E, e->stream); break;
+      case 2: launch_program_E<2>(a, grid, threads, E, e->stream); break;
+      case 4: launch_program_E<4>(a, grid, threads, E, e->stream); break;
+      case 8: launch_program_E<8>(a, grid, threads, E, e->stream); break;
+      case 16: launch_program_E<16>(a, grid, threads, E, e->stream); break;
+      case 32: launch_program_E<32>(a, grid, threads, E, e->stream); break;
+      default: return fail(RDK_ERROR_PARAM, "rate_cats must divide 32");
+    }
+    CUDA_TRY(cudaGetLastError());
+    e->stats.kernel_launches++;
+    e->stats.program_launches++;
+  }
+  e->stats.clv_ops += e->pend_ops;
+  e->stats.root_evals += e->pend_evals;
+  e->stats.algorithmic_bytes += e->pend_bytes;
+  e->pend_prog.clear();
+  e->pend_ops = e->pend_evals = 0;
+  e->pend_bytes = 0;
+  for (unsigned s : e->pm_retired) e->pm_free.push_back(s);
+  e->pm_retired.clear();
+  return RDK_SUCCESS;
+}
+
+// reduce the partials of `slots` eval slots to h_results[0..slots) (+ sync)
+int finish_evals(rdk_partition_t *p, unsigned slots) {
+  Engine        *e = eng(p);
+  const unsigned nelem = e->S * e->K;
+  const unsigned n_witer = (nelem + 31) / 32;
+  const unsigned stride = n_witer ? n_witer : 1;
+  double        *d_out = nullptr;
+  CUDA_TRY(cudaHostGetDevicePointer((void **)&d_out, e->h_results, 0));
+  const bool sharded = e->global_sites != 0 && (e->comm != nullptr || e->global_sites != e->S);
+  if (!sharded) {
+    unsigned span = next_pow2(std::max(1u, n_witer));
+    tree_reduce_kernel<<<dim3(1, slots), 256, 0, e->stream>>>(e->d_partials, stride, n_witer, span,
+                                                             d_out, 1, 0);
+    CUDA_TRY(cudaGetLastError());
+    e->stats.kernel_launches++;
+    e->stats.reduce_launches++;
+  } else {
+    // nodes of the global tree that cover RDK_SHARD_ALIGN sites each
+    const unsigned span1 = RDK_SHARD_ALIGN * e->K / 32;
+    const unsigned gblocks =
+        (unsigned)((e->global_sites + RDK_SHARD_ALIGN - 1) / RDK_SHARD_ALIGN);
+    const unsigned lblocks = (n_witer + span1 - 1) / span1;
+    const unsigned boff = (unsigned)(e->site_offset / RDK_SHARD_ALIGN);
+    size_t         need = (size_t)slots * gblocks;
+    if (need > e->nodes_cap) {
+      CUDA_TRY(cudaStreamSynchronize(e->stream));
+      if (e->d_nodes) {
+        cudaFree(e->d_nodes);
+        e->stats.device_bytes -= e->nodes_cap * sizeof(double);
+      }
+      if (!dev_alloc(e, (void **)&e->d_nodes, need * sizeof(double))) return RDK_FAILURE;
+      e->nodes_cap = need;
+    }
+    CUDA_TRY(cudaMemsetAsync(e->d_nodes, 0, need * sizeof(double), e->stream));
+    if (lblocks) {
+      tree_reduce_kernel<<<dim3(lblocks, slots), 256, 0, e->stream>>>(
+          e->d_partials, stride, n_witer, span1, e->d_nodes, gblocks, boff);
+      CUDA_TRY(cudaGetLastError());
+      e->stats.kernel_launches++;
+      e->stats.reduce_launches++;
+    }
+    if (e->comm) {
+      // every other shard contributes +0.0 to a node, so the sum is exact and
+      // the result is independent of the number of shards
+      int rc = g_nccl.AllReduce(e->d_nodes, e->d_nodes, need, kNcclFloat64, kNcclSum, e->comm,
+                                e->stream);
+      if (rc != 0)
+        return fail(RDK_ERROR_COMM, "ncclAllReduce failed: %s",
+                    g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+    }
+    tree_reduce_kernel<<<dim3(1, slots), 256, 0, e->stream>>>(e->d_nodes, gblocks, gblocks,
+                                                             next_pow2(gblocks), d_out, 1, 0);
+    CUDA_TRY(cudaGetLastError());
+    e->stats.kernel_launches++;
+    e->stats.reduce_launches++;
+  }
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  e->stats.d2h_bytes += sizeof(double) * slots;
+  return RDK_SUCCESS;
+}
+
+// translate a corax-shaped operation into a program instruction
+int make_instr(rdk_partition_t *p, const rdk_operation_t &op, unsigned flags, Instr *out) {
+  Engine *e = eng(p);
+  const unsigned nclv = e->tips + e->clv_buffers;
+  if (op.parent_clv_index < e->tips || op.parent_clv_index >= nclv)
+    return fail(RDK_ERROR_PARAM, "parent_clv_index %u out of range", op.parent_clv_index);
+  if (op.child1_clv_index >= nclv || op.child2_clv_index >= nclv)
+    return fail(RDK_ERROR_PARAM, "child clv index out of range");
+  if (op.child1_matrix_index >= e->prob_matrices || op.child2_matrix_index >= e->prob_matrices)
+    return fail(RDK_ERROR_PARAM, "matrix index out of range");
+  auto bad_scaler = [&](int s) { return s != RDK_SCALE_BUFFER_NONE && (s < 0 || (unsigned)s >= e->scale_buffers); };
+  if (bad_scaler(op.parent_scaler_index) || bad_scaler(op.child1_scaler_index) ||
+      bad_scaler(op.child2_scaler_index))
+    return fail(RDK_ERROR_PARAM, "scaler index out of range");
+  Instr in;
+  memset(&in, 0, sizeof(in));
+  in.flags = flags;
+  if (flags & kWrite) {
+    if (!ensure_clv(e, op.parent_clv_index - e->tips)) return RDK_FAILURE;
+    in.parent = e->clv_ptr[op.parent_clv_index - e->tips];
+  }
+  auto child = [&](unsigned idx, unsigned tipflag, const void **ptr) -> int {
+    if (idx < e->tips) {
+      in.flags |= tipflag;
+      *ptr = e->d_tips + (size_t)idx * e->tip_stride;
+    } else {
+      if (!ensure_clv(e, idx - e->tips)) return RDK_FAILURE;  // reading an unwritten CLV: zeros
+      *ptr = e->clv_ptr[idx - e->tips];
+    }
+    return RDK_SUCCESS;
+  };
+  if (!child(op.child1_clv_index, kTip1, &in.c1)) return RDK_FAILURE;
+  if (!child(op.child2_clv_index, kTip2, &in.c2)) return RDK_FAILURE;
+  if (op.parent_scaler_index != RDK_SCALE_BUFFER_NONE) {
+    in.flags |= kScale;
+    in.pscale = e->d_scalers + (size_t)op.parent_scaler_index * e->S;
+    if (op.child1_scaler_index != RDK_SCALE_BUFFER_NONE)
+      in.c1scale = e->d_scalers + (size_t)op.child1_scaler_index * e->S;
+    if (op.child2_scaler_index != RDK_SCALE_BUFFER_NONE)
+      in.c2scale = e->d_scalers + (size_t)op.child2_scaler_index * e->S;
+  }
+  in.P1 = e->d_pool + (size_t)e->pm_map[op.child1_matrix_index] * e->K * 16;
+  in.P2 = e->d_pool + (size_t)e->pm_map[op.child2_matrix_index] * e->K * 16;
+  *out = in;
+  return RDK_SUCCESS;
+}
+
+// SURVEY 8d accounting for one CLV operation on this shard
+unsigned long long op_bytes(const Engine *e, const Instr &in) {
+  unsigned long long S = e->S, clv = 32ull * e->K * S, b = 0;
+  b += (in.flags & kTip1) ? S : clv;
+  b += (in.flags & kTip2) ? S : clv;
+  if (in.flags & kWrite) b += clv;
+  if (in.c1scale) b += 4 * S;
+  if (in.c2scale) b += 4 * S;
+  if ((in.flags & kWrite) && in.pscale) b += 4 * S;
+  if (in.flags & kEval) b += 4 * S;  // pattern weights
+  return b;
+}
+
+// record a P-matrix update with slot renaming; caller holds the mutex
+int record_pmatrix(rdk_partition_t *p, unsigned matrix_index, double t) {
+  Engine *e = eng(p);
+  if (e->pm_free.empty()) {
+    // recycle: launch what is recorded so that retired slots become free
+    if (!flush(p)) return RDK_FAILURE;
+    if (e->pm_free.empty()) return fail(RDK_ERROR_MEM, "P-matrix pool exhausted");
+  }
+  unsigned slot = e->pm_free.back();
+  e->pm_free.pop_back();
+  e->pm_retired.push_back(e->pm_map[matrix_index]);
+  e->pm_map[matrix_index] = slot;
+  PmatEntry ent;
+  ent.slot = slot;
+  ent.pad = 0;
+  ent.t = t;
+  e->pend_pm.push_back(ent);
+  return RDK_SUCCESS;
+}
+
+// P entries recorded so far were computed against the current parameters;
+// launch them before a parameter changes
+int params_about_to_change(rdk_partition_t *p) { return launch_pmatrices(p); }
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// device selection
+// ---------------------------------------------------------------------------
+extern "C" int rdk_device_count(void) {
+  int         n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    fail(RDK_ERROR_CUDA, "cudaGetDeviceCount failed: %s", cudaGetErrorString(e));
+    return 0;
+  }
+  return n;
+}
+
+extern "C" int rdk_set_device(int device) {
+  CUDA_TRY(cudaSetDevice(device));
+  tl_device = device;
+  return RDK_SUCCESS;
+}
+
+extern "C" const char *rdk_version(void) { return "rdk-b200 0.1 (sm_100a)"; }
+
+// ---------------------------------------------------------------------------
+// partition life cycle
+// ---------------------------------------------------------------------------
+static int engine_init(rdk_partition_t *p, Engine *e) {
+  if (tl_device >= 0) CUDA_TRY(cudaSetDevice(tl_device));
+  CUDA_TRY(cudaGetDevice(&e->device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, e->device));
+  e->sm_count = prop.multiProcessorCount;
+  CUDA_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  e->tips = p->tips;
+  e->clv_buffers = p->clv_buffers;
+  e->S = p->sites;
+  e->K = p->rate_cats;
+  e->prob_matrices = p->prob_matrices;
+  e->scale_buffers = p->scale_buffers;
+  e->clv_elems = (size_t)e->S * e->K * 4;
+  e->tip_stride = ((size_t)e->S + 127) & ~size_t(127);
+  e->global_sites = 0;
+  e->clv_ptr.assign(e->clv_buffers, nullptr);
+
+  if (!dev_alloc(e, (void **)&e->d_tips, e->tip_stride * std::max(1u, e->tips))) return RDK_FAILURE;
+  CUDA_TRY(cudaMemsetAsync(e->d_tips, 0, e->tip_stride * std::max(1u, e->tips), e->stream));
+  size_t sc_bytes = sizeof(unsigned) * (size_t)e->S * std::max(1u, e->scale_buffers);
+  if (!dev_alloc(e, (void **)&e->d_scalers, sc_bytes)) return RDK_FAILURE;
+  CUDA_TRY(cudaMemsetAsync(e->d_scalers, 0, sc_bytes, e->stream));
+  if (!dev_alloc(e, (void **)&e->d_weights, sizeof(unsigned) * std::max(1u, e->S))) return RDK_FAILURE;
+  if (!dev_alloc(e, (void **)&e->d_hist, sizeof(unsigned long long) * 16)) return RDK_FAILURE;
+  if (!dev_alloc(e, (void **)&e->d_persite, sizeof(double) * std::max(1u, e->S))) return RDK_FAILURE;
+  std::vector<unsigned> ones(std::max(1u, e->S), 1u);
+  CUDA_TRY(cudaMemcpyAsync(e->d_weights, ones.data(), sizeof(unsigned) * ones.size(),
+                           cudaMemcpyHostToDevice, e->stream));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+
+  // P-matrix pool: every index has a slot, plus spare slots for renaming
+  e->pool_slots = e->prob_matrices * 2 + 4096;
+  size_t pool_bytes = sizeof(double) * 16 * e->K * (size_t)e->pool_slots;
+  if (!dev_alloc(e, (void **)&e->d_pool, pool_bytes)) return RDK_FAILURE;
+  CUDA_TRY(cudaMemsetAsync(e->d_pool, 0, pool_bytes, e->stream));
+  e->pm_map.resize(e->prob_matrices);
+  for (unsigned i = 0; i < e->prob_matrices; ++i) e->pm_map[i] = i;
+  for (unsigned s = e->pool_slots; s-- > e->prob_matrices;) e->pm_free.push_back(s);
+
+  e->ring.cap = 0;
+  char *h, *d;
+  if (!ring_alloc(e, size_t(1) << 20, &h, &d)) return RDK_FAILURE;
+  e->ring.head = 0;
+  if (!ensure_partials(e, 1, std::max(1u, (e->S * e->K + 31) / 32))) return RDK_FAILURE;
+  return RDK_SUCCESS;
+}
+
+extern "C" rdk_partition_t *rdk_partition_create(unsigned int tips, unsigned int clv_buffers,
+                                                 unsigned int states, unsigned int sites,
+                                                 unsigned int rate_matrices,
+                                                 unsigned int prob_matrices,
+                                                 unsigned int rate_cats,
+                                                 unsigned int scale_buffers,
+                                                 unsigned int attributes) {
+  tl_errno = 0;
+  if (states != 4) {
+    fail(RDK_ERROR_PARAM, "only 4-state (DNA) partitions are supported, got %u states", states);
+    return nullptr;
+  }
+  if (!(attributes & RDK_ATTRIB_NONREV)) {
+    fail(RDK_ERROR_PARAM, "RDK_ATTRIB_NONREV is required (non-reversible engine)");
+    return nullptr;
+  }
+  if (rate_matrices != 1) {
+    fail(RDK_ERROR_PARAM, "exactly one rate matrix per partition is supported (model_t::_submodels)");
+    return nullptr;
+  }
+  if (rate_cats == 0 || rate_cats > (unsigned)kMaxCats || (32 % rate_cats) != 0) {
+    fail(RDK_ERROR_PARAM, "rate_cats must be one of 1,2,4,8,16,32 (got %u)", rate_cats);
+    return nullptr;
+  }
+  if ((unsigned long long)sites * rate_cats >= (1ull << 31)) {
+    fail(RDK_ERROR_PARAM, "sites * rate_cats must be < 2^31 per shard");
+    return nullptr;
+  }
+  rdk_partition_t *p = (rdk_partition_t *)calloc(1, sizeof(rdk_partition_t));
+  if (!p) {
+    fail(RDK_ERROR_MEM, "out of host memory");
+    return nullptr;
+  }
+  p->tips = tips;
+  p->clv_buffers = clv_buffers;
+  p->states = states;
+  p->sites = sites;
+  p->rate_matrices = rate_matrices;
+  p->prob_matrices = prob_matrices;
+  p->rate_cats = rate_cats;
+  p->scale_buffers = scale_buffers;
+  p->attributes = attributes;
+  p->subst_params = (double **)calloc(rate_matrices, sizeof(double *));
+  p->frequencies = (double **)calloc(rate_matrices, sizeof(double *));
+  for (unsigned i = 0; i < rate_matrices; ++i) {
+    p->subst_params[i] = (double *)calloc(12, sizeof(double));
+    p->frequencies[i] = (double *)calloc(4, sizeof(double));
+    for (int j = 0; j < 12; ++j) p->subst_params[i][j] = 1.0;
+    for (int j = 0; j < 4; ++j) p->frequencies[i][j] = 0.25;
+  }
+  p->rates = (double *)calloc(rate_cats, sizeof(double));
+  p->rate_weights = (double *)calloc(rate_cats, sizeof(double));
+  for (unsigned k = 0; k < rate_cats; ++k) {
+    p->rates[k] = 1.0;
+    p->rate_weights[k] = 1.0 / rate_cats;
+  }
+  p->prop_invar = (double *)calloc(rate_matrices, sizeof(double));
+  p->pattern_weights = (unsigned *)calloc(sites ? sites : 1, sizeof(unsigned));
+  for (unsigned s = 0; s < sites; ++s) p->pattern_weights[s] = 1;
+  Engine *e = new Engine();
+  p->engine = e;
+  if (!engine_init(p, e)) {
+    rdk_partition_destroy(p);
+    return nullptr;
+  }
+  return p;
+}
+
+extern "C" void rdk_partition_destroy(rdk_partition_t *p) {
+  if (!p) return;
+  Engine *e = eng(p);
+  if (e) {
+    cudaSetDevice(e->device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
+    cudaFree(e->d_tips);
+    for (void *s : e->slabs) cudaFree(s);
+    cudaFree(e->d_scalers);
+    cudaFree(e->d_weights);
+    cudaFree(e->d_hist);
+    cudaFree(e->d_persite);
+    cudaFree(e->d_pool);
+    cudaFree(e->d_partials);
+    cudaFree(e->d_nodes);
+    cudaFree(e->ring.d);
+    if (e->ring.h) cudaFreeHost(e->ring.h);
+    if (e->h_results) cudaFreeHost(e->h_results);
+    if (e->stream && e->own_stream) cudaStreamDestroy(e->stream);
+    delete e;
+  }
+  for (unsigned i = 0; i < p->rate_matrices; ++i) {
+    free(p->subst_params[i]);
+    free(p->frequencies[i]);
+  }
+  free(p->subst_params);
+  free(p->frequencies);
+  free(p->rates);
+  free(p->rate_weights);
+  free(p->prop_invar);
+  free(p->pattern_weights);
+  free(p);
+}
+
+// ---------------------------------------------------------------------------
+// inputs
+// ---------------------------------------------------------------------------
+extern "C" int rdk_set_tip_states(rdk_partition_t *p, unsigned int tip_index, const rdk_state_t *map,
+                                  const char *sequence) {
+  Engine *e = eng(p);
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (tip_index >= e->tips) return fail(RDK_ERROR_PARAM, "tip index %u out of range", tip_index);
+  CUDA_TRY(cudaSetDevice(e->device));
+  if (!flush(p)) return RDK_FAILURE;
+  char *h, *d;
+  if (!ring_alloc(e, e->S ? e->S : 1, &h, &d)) return RDK_FAILURE;
+  for (unsigned s = 0; s < e->S; ++s) {
+    rdk_state_t st = map[(unsigned char)sequence[s]];
+    if (!st) {
+      tl_errno = RDK_ERROR_TIP_DATA;
+      snprintf(tl_errmsg, sizeof(tl_errmsg), "Illegal state code in tip \"%c\"", sequence[s]);
+      return RDK_FAILURE;
+    }
+    h[s] = (char)(st & 15ull);
+  }
+  CUDA_TRY(cudaMemcpyAsync(e->d_tips + (size_t)tip_index * e->tip_stride, h, e->S,
+                           cudaMemcpyHostToDevice, e->stream));
+  e->stats.h2d_bytes += e->S;
+  return RDK_SUCCESS;
+}
+
+extern "C" void rdk_set_pattern_weights(rdk_partition_t *p, const unsigned int *w) {
+  Engine *e = eng(p);
+  std::lock_guard<std::mutex> lk(e->mu);
+  cudaSetDevice(e->device);
+  flush(p);
+  memcpy(p->pattern_weights, w, sizeof(unsigned) * e->S);
+  char *h, *d;
+  if (!ring_alloc(e, sizeof(unsigned) * (e->S ? e->S : 1), &h, &d)) return;
+  memcpy(h, w, sizeof(unsigned) * e->S);
+  cudaMemcpyAsync(e->d_weights, h, sizeof(unsigned) * e->S, cudaMemcpyHostToDevice, e->stream);
+  e->stats.h2d_bytes += sizeof(unsigned) * e->S;
+}
+
+extern "C" void rdk_set_subst_params(rdk_partition_t *p, unsigned int idx, const double *params) {
+  Engine *e = eng(p);
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (idx >= p->rate_matrices) return;
+  cudaSetDevice(e->device);
+  params_about_to_change(p);
+  memcpy(p->subst_params[idx], params, sizeof(double) * 12);
+}
+
+extern "C" void rdk_set_frequencies(rdk_partition_t *p, unsigned int idx, const double *f) {
+  Engine *e = eng(p);
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (idx >= p->rate_matrices) return;
+  cudaSetDevice(e->device);
+  flush(p);  // frequencies also enter recorded evaluations
+  memcpy(p->frequencies[idx], f, sizeof(double) * 4);
+}
+
+extern "C" void rdk_set_category_rates(rdk_partition_t *p, const double *rates) {
+  Engine *e = eng(p);
+  std::lock_guard<std::mutex> lk(e->mu);
+  cudaSetDevice(e->device);
+  params_about_to_change(p);
+  memcpy(p->rates, rates, sizeof(double) * e->K);
+}
+
+extern "C" void rdk_set_category_weights(rdk_partition_t *p, const double *w) {
+  Engine *e = eng(p);
+  std::lock_guard<std::mutex> lk(e->mu);
+  cudaSetDevice(e->device);
+  flush(p);
+  memcpy(p->rate_weights, w, sizeof(double) * e->K);
+}
+
+extern "C" int rdk_update_invariant_sites(rdk_partition_t *p) {
+  // Marks invariant columns for the +I likelihood term.  RootDigger never sets
+  // a non-zero proportion (reference src/model.cpp:292-300, SURVEY B-5), and the
+  // engine rejects a non-zero proportion below, so the marks are never read.
+  (void)p;
+  return RDK_SUCCESS;
+}
+
+extern "C" int rdk_update_invariant_sites_proportion(rdk_partition_t *p, unsigned int idx,
+                                                     double prop_invar) {
+  if (idx >= p->rate_matrices) return fail(RDK_ERROR_PARAM, "params index out of range");
+  if (prop_invar != 0.0)
+    return fail(RDK_ERROR_PARAM,
+                "a non-zero proportion of invariant sites is not supported (RootDigger always "
+                "passes 0.0)");
+  Engine *e = eng(p);
+  std::lock_guard<std::mutex> lk(e->mu);
+  params_about_to_change(p);
+  p->prop_invar[idx] = prop_invar;
+  return RDK_SUCCESS;
+}
+
+// ---------------------------------------------------------------------------
+// the hot path
+// ---------------------------------------------------------------------------
+extern "C" int rdk_update_prob_matrices(rdk_partition_t *p, const unsigned int *params_indices,
+                                        const unsigned int *matrix_indices,
+                                        const double *branch_lengths, unsigned int count) {
+  Engine *e = eng(p);
+  if (params_indices)
+    for (unsigned k = 0; k < e->K; ++k)
+      if (params_indices[k] != 0) return fail(RDK_ERROR_PARAM, "params_indices must be all 0");
+  for (unsigned i = 0; i < count; ++i) {
+    if (matrix_indices[i] >= e->prob_matrices)
+      return fail(RDK_ERROR_PARAM, "matrix index %u out of range", matrix_indices[i]);
+    if (!(branch_lengths[i] >= 0.0) || !std::isfinite(branch_lengths[i]))
+      return fail(RDK_ERROR_PARAM, "branch length must be finite and non-negative");
+  }
+  std::lock_guard<std::mutex> lk(e->mu);
+  CUDA_TRY(cudaSetDevice(e->device));
+  for (unsigned i = 0; i < count; ++i)
+    if (!record_pmatrix(p, matrix_indices[i], branch_lengths[i])) return RDK_FAILURE;
+  return RDK_SUCCESS;
+}
+
+extern "C" void rdk_update_clvs(rdk_partition_t *p, const rdk_operation_t *ops, unsigned int count) {
+  Engine *e = eng(p);
+  std::lock_guard<std::mutex> lk(e->mu);
+  cudaSetDevice(e->device);
+  for (unsigned i = 0; i < count; ++i) {
+    Instr in;
+    if (!make_instr(p, ops[i], kWrite, &in)) return;  // error left in rdk_errno
+    e->pend_bytes += op_bytes(e, in);
+    e->pend_prog.push_back(in);
+    e->pend_ops++;
+  }
+}
+
+extern "C" double rdk_compute_root_loglikelihood(rdk_partition_t *p, unsigned int clv_index,
+                                                 int scaler_index, const unsigned int *freqs_indices,
+                                                 double *persite_lnl) {
+  (void)freqs_indices;
+  Engine *e = eng(p);
+  const double nan = std::numeric_limits<double>::quiet_NaN();
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (cudaSetDevice(e->device) != cudaSuccess) return nan;
+  if (clv_index >= e->tips + e->clv_buffers || clv_index < e->tips) {
+    fail(RDK_ERROR_PARAM, "root clv index %u out of range", clv_index);
+    return nan;
+  }
+  if (scaler_index != RDK_SCALE_BUFFER_NONE && (scaler_index < 0 || (unsigned)scaler_index >= e->scale_buffers)) {
+    fail(RDK_ERROR_PARAM, "root scaler index out of range");
+    return nan;
+  }
+  if (!ensure_clv(e, clv_index - e->tips)) return nan;
+  double        *root = e->clv_ptr[clv_index - e->tips];
+  const unsigned *rs = scaler_index == RDK_SCALE_BUFFER_NONE ? nullptr : e->d_scalers + (size_t)scaler_index * e->S;
+  // fuse with the recorded operation that produces this CLV, if it is the last one
+  bool fused = false;
+  if (!e->pend_prog.empty()) {
+    Instr &last = e->pend_prog.back();
+    if ((last.flags & kWrite) && !(last.flags & kEval) && last.parent == root &&
+        last.pscale == rs) {
+      last.flags |= kEval;
+      last.slot = 0;
+      e->pend_bytes += 4ull * e->S;
+      fused = true;
+    }
+  }
+  if (!fused) {
+    Instr in;
+    memset(&in, 0, sizeof(in));
+    in.flags = kLoadOnly | kEval;
+    in.c1 = root;
+    in.c1scale = rs;
+    in.slot = 0;
+    e->pend_bytes += 32ull * e->K * e->S + (rs ? 4ull * e->S : 0) + 4ull * e->S;
+    e->pend_prog.push_back(in);
+  }
+  e->pend_evals++;
+  e->pend_slots = 1;
+  e->want_persite = persite_lnl != nullptr;
+  int ok = flush(p);
+  e->pend_slots = 0;
+  e->want_persite = false;
+  if (!ok) return nan;
+  if (e->S == 0 && e->global_sites == 0) return 0.0;
+  if (!finish_evals(p, 1)) return nan;
+  if (persite_lnl) {
+    if (cudaMemcpy(persite_lnl, e->d_persite, sizeof(double) * e->S, cudaMemcpyDeviceToHost) !=
+        cudaSuccess) {
+      fail(RDK_ERROR_CUDA, "persite copy failed");
+      return nan;
+    }
+    e->stats.d2h_bytes += sizeof(double) * e->S;
+  }
+  return e->h_results[0];
+}
+
+// ---------------------------------------------------------------------------
+// fused extensions
+// ---------------------------------------------------------------------------
+extern "C" int rdk_root_loglikelihood_multi(rdk_partition_t *p, const rdk_operation_t *root_op,
+                                            const unsigned int *params_indices,
+                                            const unsigned int *freqs_indices,
+                                            const double *branch_lengths, unsigned int count,
+                                            double *out_lnl) {
+  (void)params_indices;
+  (void)freqs_indices;
+  Engine *e = eng(p);
+  if (count == 0) return RDK_SUCCESS;
+  for (unsigned i = 0; i < 2 * count; ++i)
+    if (!(branch_lengths[i] >= 0.0) || !std::isfinite(branch_lengths[i]))
+      return fail(RDK_ERROR_PARAM, "branch length must be finite and non-negative");
+  std::lock_guard<std::mutex> lk(e->mu);
+  CUDA_TRY(cudaSetDevice(e->device));
+  if (!flush(p)) return RDK_FAILURE;
+  if (e->pm_free.size() < 2 * (size_t)count)
+    return fail(RDK_ERROR_PARAM, "too many candidates in one call (max %zu)", e->pm_free.size() / 2);
+  Instr base;
+  if (!make_instr(p, *root_op, 0, &base)) return RDK_FAILURE;
+  std::vector<unsigned> used;
+  for (unsigned b = 0; b < count; ++b) {
+    unsigned s1 = e->pm_free.back();
+    e->pm_free.pop_back();
+    unsigned s2 = e->pm_free.back();
+    e->pm_free.pop_back();
+    used.push_back(s1);
+    used.push_back(s2);
+    PmatEntry e1{s1, 0, branch_lengths[2 * b]}, e2{s2, 0, branch_lengths[2 * b + 1]};
+    e->pend_pm.push_back(e1);
+    e->pend_pm.push_back(e2);
+    Instr in = base;
+    in.flags |= kEval;  // no kWrite: partition state is left untouched
+    in.parent = nullptr;
+    in.pscale = nullptr;
+    in.P1 = e->d_pool + (size_t)s1 * e->K * 16;
+    in.P2 = e->d_pool + (size_t)s2 * e->K * 16;
+    in.slot = b;
+    e->pend_bytes += op_bytes(e, in);
+    e->pend_prog.push_back(in);
+    e->pend_evals++;
+  }
+  e->pend_slots = count;
+  int ok = flush(p);
+  e->pend_slots = 0;
+  for (unsigned s : used) e->pm_free.push_back(s);
+  if (!ok) return RDK_FAILURE;
+  if (!finish_evals(p, count)) return RDK_FAILURE;
+  for (unsigned b = 0; b < count; ++b) out_lnl[b] = e->h_results[b];
+  return RDK_SUCCESS;
+}
+
+extern "C" int rdk_sweep_root_placements(rdk_partition_t *p, unsigned int placements,
+                                         const unsigned int *params_indices,
+                                         const unsigned int *freqs_indices,
+                                         const unsigned int *pm_offsets,
+                                         const unsigned int *matrix_indices,
+                                         const double *branch_lengths,
+                                         const unsigned int *op_offsets,
+                                         const rdk_operation_t *operations,
+                                         unsigned int root_clv_index, int root_scaler_index,
+                                         double *out_lnl) {
+  (void)params_indices;
+  (void)freqs_indices;
+  Engine *e = eng(p);
+  if (placements == 0) return RDK_SUCCESS;
+  if (root_clv_index < e->tips || root_clv_index >= e->tips + e->clv_buffers)
+    return fail(RDK_ERROR_PARAM, "root clv index out of range");
+  for (unsigned i = 0; i < pm_offsets[placements]; ++i) {
+    if (matrix_indices[i] >= e->prob_matrices) return fail(RDK_ERROR_PARAM, "matrix index out of range");
+    if (!(branch_lengths[i] >= 0.0) || !std::isfinite(branch_lengths[i]))
+      return fail(RDK_ERROR_PARAM, "branch length must be finite and non-negative");
+  }
+  std::lock_guard<std::mutex> lk(e->mu);
+  CUDA_TRY(cudaSetDevice(e->device));
+  if (!flush(p)) return RDK_FAILURE;
+  if (!ensure_clv(e, root_clv_index - e->tips)) return RDK_FAILURE;
+  double         *root = e->clv_ptr[root_clv_index - e->tips];
+  const unsigned *rs = root_scaler_index == RDK_SCALE_BUFFER_NONE
+                           ? nullptr
+                           : e->d_scalers + (size_t)root_scaler_index * e->S;
+  // batches bounded by the spare P-matrix slots and the partial-sum buffer
+  const size_t   stride = std::max(1u, (e->S * e->K + 31) / 32);
+  const unsigned max_slots = (unsigned)std::max<size_t>(1, std::min<size_t>(4096, (size_t(256) << 20) / (stride * 8)));
+  unsigned       done = 0;
+  while (done < placements) {
+    unsigned b = 0;
+    size_t   pm_budget = e->pm_free.size();
+    while (done + b < placements && b < max_slots) {
+      unsigned q = done + b;
+      size_t   need = pm_offsets[q + 1] - pm_offsets[q];
+      if (need > pm_budget) break;
+      pm_budget -= need;
+      for (unsigned i = pm_offsets[q]; i < pm_offsets[q + 1]; ++i)
+        if (!record_pmatrix(p, matrix_indices[i], branch_lengths[i])) return RDK_FAILURE;
+      bool fused = false;
+      for (unsigned i = op_offsets[q]; i < op_offsets[q + 1]; ++i) {
+        Instr in;
+        if (!make_instr(p, operations[i], kWrite, &in)) return RDK_FAILURE;
+        if (i + 1 == op_offsets[q + 1] && in.parent == root && in.pscale == rs) {
+          in.flags |= kEval;
+          in.slot = b;
+          fused = true;
+        }
+        e->pend_bytes += op_bytes(e, in);
+        e->pend_prog.push_back(in);
+        e->pend_ops++;
+      }
+      if (!fused) {
+        Instr in;
+        memset(&in, 0, sizeof(in));
+        in.flags = kLoadOnly | kEval;
+        in.c1 = root;
+        in.c1scale = rs;
+        in.slot = b;
+        e->pend_bytes += 32ull * e->K * e->S + (rs ? 4ull * e->S : 0) + 4ull * e->S;
+        e->pend_prog.push_back(in);
+      }
+      e->pend_evals++;
+      ++b;
+    }
+    if (b == 0) return fail(RDK_ERROR_PARAM, "a placement needs more P-matrices than the pool holds");
+    e->pend_slots = b;
+    int ok = flush(p);
+    e->pend_slots = 0;
+    if (!ok) return RDK_FAILURE;
+    if (!finish_evals(p, b)) return RDK_FAILURE;
+    for (unsigned i = 0; i < b; ++i) out_lnl[done + i] = e->h_results[i];
+    done += b;
+  }
+  return RDK_SUCCESS;
+}
+
+// ---------------------------------------------------------------------------
+// empirical frequencies (device histogram, exact integers)
+// ---------------------------------------------------------------------------
+extern "C" double *rdk_msa_empirical_frequencies(rdk_partition_t *p) {
+  Engine *e = eng(p);
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (cudaSetDevice(e->device) != cudaSuccess) return nullptr;
+  if (!flush(p)) return nullptr;
+  unsigned long long hist[16];
+  cudaMemsetAsync(e->d_hist, 0, sizeof(hist), e->stream);
+  if (e->S > 0 && e->tips > 0) {
+    size_t total = (size_t)e->tips * e->S;
+    int    grid = (int)std::min<size_t>((total + 255) / 256, (size_t)e->sm_count * 8);
+    tip_hist_kernel<<<grid, 256, 0, e->stream>>>(e->d_tips, e->tip_stride, e->tips, e->S, e->d_weights,
+                                                 e->d_hist);
+    e->stats.kernel_launches++;
+  }
+  if (e->comm) {
+    int rc = g_nccl.AllReduce(e->d_hist, e->d_hist, 16, kNcclUint64, kNcclSum, e->comm, e->stream);
+    if (rc != 0) {
+      fail(RDK_ERROR_COMM, "ncclAllReduce failed");
+      return nullptr;
+    }
+  }
+  if (cudaMemcpyAsync(hist, e->d_hist, sizeof(hist), cudaMemcpyDeviceToHost, e->stream) != cudaSuccess ||
+      cudaStreamSynchronize(e->stream) != cudaSuccess) {
+    fail(RDK_ERROR_CUDA, "histogram read-back failed");
+    return nullptr;
+  }
+  // f_j = sum over masks m containing j of H[m] / popcount(m), ascending m;
+  // normalised by (total pattern weight) * tips = sum of all H[m]
+  double *f = (double *)calloc(4, sizeof(double));
+  double  total = 0.0;
+  for (int m = 1; m < 16; ++m) total += (double)hist[m];
+  for (int j = 0; j < 4; ++j) {
+    double s = 0.0;
+    for (int m = 1; m < 16; ++m)
+      if (m & (1 << j)) s += (double)hist[m] / (double)__builtin_popcount(m);
+    f[j] = s / total;
+  }
+  return f;
+}
+
+// ---------------------------------------------------------------------------
+// sharding
+// ---------------------------------------------------------------------------
+extern "C" int rdk_partition_set_shard(rdk_partition_t *p, unsigned long long site_offset,
+                                       unsigned long long global_sites) {
+  Engine *e = eng(p);
+  if (site_offset % RDK_SHARD_ALIGN != 0)
+    return fail(RDK_ERROR_PARAM, "site_offset must be a multiple of %u", RDK_SHARD_ALIGN);
+  if (site_offset + e->S > global_sites)
+    return fail(RDK_ERROR_PARAM, "shard [%llu, %llu) exceeds global_sites %llu", site_offset,
+                site_offset + e->S, global_sites);
+  if ((RDK_SHARD_ALIGN * e->K) % 32 != 0) return fail(RDK_ERROR_PARAM, "unsupported rate_cats for sharding");
+  std::lock_guard<std::mutex> lk(e->mu);
+  e->site_offset = site_offset;
+  e->global_sites = global_sites;
+  return RDK_SUCCESS;
+}
+
+extern "C" int rdk_comm_unique_id(void *id_out) {
+  if (!load_nccl()) return RDK_FAILURE;
+  Id128 id;
+  memset(&id, 0, sizeof(id));
+  int rc = g_nccl.GetUniqueId(&id);
+  if (rc != 0) return fail(RDK_ERROR_COMM, "ncclGetUniqueId failed (%d)", rc);
+  memcpy(id_out, &id, sizeof(id));
+  return RDK_SUCCESS;
+}
+
+extern "C" int rdk_partition_attach_comm(rdk_partition_t *p, int nranks, int rank, const void *id) {
+  Engine *e = eng(p);
+  if (!load_nccl()) return RDK_FAILURE;
+  if (e->global_sites == 0)
+    return fail(RDK_ERROR_PARAM, "call rdk_partition_set_shard before attaching a communicator");
+  std::lock_guard<std::mutex> lk(e->mu);
+  CUDA_TRY(cudaSetDevice(e->device));
+  Id128 uid;
+  memcpy(&uid, id, sizeof(uid));
+  void *comm = nullptr;
+  int   rc = g_nccl.CommInitRank(&comm, nranks, uid, rank);
+  if (rc != 0)
+    return fail(RDK_ERROR_COMM, "ncclCommInitRank failed: %s",
+                g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+  e->comm = comm;
+  e->nranks = nranks;
+  e->rank = rank;
+  return RDK_SUCCESS;
+}
+
+// ---------------------------------------------------------------------------
+// plumbing / introspection
+// ---------------------------------------------------------------------------
+extern "C" int rdk_partition_flush(rdk_partition_t *p) {
+  Engine *e = eng(p);
+  std::lock_guard<std::mutex> lk(e->mu);
+  CUDA_TRY(cudaSetDevice(e->device));
+  return flush(p);
+}
+
+extern "C" int rdk_partition_sync(rdk_partition_t *p) {
+  Engine *e = eng(p);
+  std::lock_guard<std::mutex> lk(e->mu);
+  CUDA_TRY(cudaSetDevice(e->device));
+  if (!flush(p)) return RDK_FAILURE;
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  return RDK_SUCCESS;
+}
+
+extern "C" int rdk_partition_set_stream(rdk_partition_t *p, void *cuda_stream) {
+  Engine *e = eng(p);
+  std::lock_guard<std::mutex> lk(e->mu);
+  CUDA_TRY(cudaSetDevice(e->device));
+  if (!flush(p)) return RDK_FAILURE;
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
+  e->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+  e->own_stream = false;
+  return RDK_SUCCESS;
+}
+
+extern "C" void *rdk_partition_stream(rdk_partition_t *p) { return eng(p)->stream; }
+
+extern "C" int rdk_get_clv(rdk_partition_t *p, unsigned int clv_index, double *out) {
+  Engine *e = eng(p);
+  std::lock_guard<std::mutex> lk(e->mu);
+  CUDA_TRY(cudaSetDevice(e->device));
+  if (clv_index >= e->tips + e->clv_buffers) return fail(RDK_ERROR_PARAM, "clv index out of range");
+  if (!flush(p)) return RDK_FAILURE;
+  size_t bytes = e->clv_elems * sizeof(double);
+  if (clv_index < e->tips) {
+    double *tmp = nullptr;
+    CUDA_TRY(cudaMalloc((void **)&tmp, bytes ? bytes : 32));
+    size_t n = (size_t)e->S * e->K;
+    if (n) {
+      tip_expand_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(
+          e->d_tips + (size_t)clv_index * e->tip_stride, e->S, (int)e->K, tmp);
+      e->stats.kernel_launches++;
+    }
+    cudaError_t err = cudaMemcpyAsync(out, tmp, bytes, cudaMemcpyDeviceToHost, e->stream);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+    cudaFree(tmp);
+    CUDA_TRY(err);
+  } else {
+    if (!ensure_clv(e, clv_index - e->tips)) return RDK_FAILURE;
+    CUDA_TRY(cudaMemcpyAsync(out, e->clv_ptr[clv_index - e->tips], bytes, cudaMemcpyDeviceToHost,
+                             e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+  }
+  e->stats.d2h_bytes += bytes;
+  return RDK_SUCCESS;
+}
+
+extern "C" int rdk_get_scale_buffer(rdk_partition_t *p, int scaler_index, unsigned int *out) {
+  Engine *e = eng(p);
+  std::lock_guard<std::mutex> lk(e->mu);
+  CUDA_TRY(cudaSetDevice(e->device));
+  if (scaler_index < 0 || (unsigned)scaler_index >= e->scale_buffers)
+    return fail(RDK_ERROR_PARAM, "scaler index out of range");
+  if (!flush(p)) return RDK_FAILURE;
+  CUDA_TRY(cudaMemcpyAsync(out, e->d_scalers + (size_t)scaler_index * e->S, sizeof(unsigned) * e->S,
+                           cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  return RDK_SUCCESS;
+}
+
+extern "C" int rdk_get_pmatrix(rdk_partition_t *p, unsigned int matrix_index, double *out) {
+  Engine *e = eng(p);
+  std::lock_guard<std::mutex> lk(e->mu);
+  CUDA_TRY(cudaSetDevice(e->device));
+  if (matrix_index >= e->prob_matrices) return fail(RDK_ERROR_PARAM, "matrix index out of range");
+  if (!flush(p)) return RDK_FAILURE;
+  CUDA_TRY(cudaMemcpyAsync(out, e->d_pool + (size_t)e->pm_map[matrix_index] * e->K * 16,
+                           sizeof(double) * 16 * e->K, cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  return RDK_SUCCESS;
+}
+
+extern "C" void rdk_partition_stats(rdk_partition_t *p, rdk_stats_t *out) {
+  Engine *e = eng(p);
+  std::lock_guard<std::mutex> lk(e->mu);
+  *out = e->stats;
+}
+
+extern "C" void rdk_partition_reset_stats(rdk_partition_t *p) {
+  Engine *e = eng(p);
+  std::lock_guard<std::mutex> lk(e->mu);
+  unsigned long long dev = e->stats.device_bytes;
+  memset(&e->stats, 0, sizeof(e->stats));
+  e->stats.device_bytes = dev;
+}
+
+extern "C" int rdk_partition_set_launch_config(rdk_partition_t *p, int ctas_per_sm,
+                                               int threads_per_cta, int elems_per_thread) {
+  Engine *e = eng(p);
+  if (threads_per_cta != 0 && (threads_per_cta < 32 || threads_per_cta > 256 || threads_per_cta % 32))
+    return fail(RDK_ERROR_PARAM, "threads_per_cta must be a multiple of 32 in [32,256]");
+  if (elems_per_thread != 0 && elems_per_thread != 1 && elems_per_thread != 2 && elems_per_thread != 4)
+    return fail(RDK_ERROR_PARAM, "elems_per_thread must be 1, 2 or 4");
+  if (ctas_per_sm < 0 || ctas_per_sm > 32) return fail(RDK_ERROR_PARAM, "ctas_per_sm out of range");
+  std::lock_guard<std::mutex> lk(e->mu);
+  e->ctas_per_sm = ctas_per_sm;
+  e->threads = threads_per_cta;
+  e->elems = elems_per_thread;
+  return RDK_SUCCESS;
+}

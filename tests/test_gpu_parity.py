@@ -1,0 +1,201 @@
+"""GPU parity tests: the CUDA engine (through the C ABI of include/rdk.h) against
+the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.md section 5 / north_star):
+  * fp64 log-likelihoods, per site and total: <= 1e-9 relative against the
+    oracle in REFERENCE arithmetic (libm log, serial site sum);
+  * stronger, by construction: bit-for-bit equality of P-matrices, CLVs,
+    scalers, per-site and total log-likelihood against the oracle in ENGINE
+    arithmetic (spec'd software log + canonical pairwise tree), which is what
+    makes the chosen root / LWR ranking / optimised alpha identical.
+"""
+import numpy as np
+import pytest
+
+import cases
+from cases import Case, bits, compute_lh, compute_lh_root, move_root, rel_err, same_bits
+from oracle_capi import MODE_ENGINE, MODE_REFERENCE, OraclePartition
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9  # north_star tolerance for fp64 log-likelihoods
+
+
+def make(case):
+    from root_digger_b200.capi import Partition
+    g = Partition(case.n, case.S, case.K)
+    o = OraclePartition(case.n, case.S, case.K)
+    case.setup(g)
+    case.setup(o)
+    return g, o
+
+
+CASES = [
+    # n_taxa, sites, K, data, weights
+    (4, 1, 1, "evolved", "ones"),
+    (5, 7, 4, "evolved", "random"),
+    (10, 1000, 1, "evolved", "ones"),
+    (10, 991, 4, "evolved", "random"),
+    (33, 2049, 2, "ambiguous", "random"),
+    (64, 4097, 8, "evolved", "ones"),
+    (101, 1630, 4, "ambiguous", "random"),
+    (300, 523, 4, "iid", "ones"),      # deep underflow: scalers fire
+    (40, 300, 16, "evolved", "ones"),
+    (24, 100, 32, "evolved", "ones"),
+]
+
+
+@pytest.mark.parametrize("n,S,K,data,weights", CASES)
+def test_full_evaluation_matches_oracle(n, S, K, data, weights):
+    case = Case(n, S, K, seed=1000 + n + S, data=data, weights=weights)
+    g, o = make(case)
+    sched = case.full_schedule(0, 0.5)
+    lg, pg = compute_lh(g, sched, case.root_clv, case.root_scaler, persite=True)
+    lo_ref, po_ref = compute_lh(o, sched, case.root_clv, case.root_scaler, persite=True, mode=MODE_REFERENCE)
+    lo_eng, po_eng = o.root_loglikelihood(case.root_clv, case.root_scaler, persite=True, mode=MODE_ENGINE)
+    assert np.isfinite(lg) and lg < 0
+    # contractual tolerance
+    assert abs(lg - lo_ref) <= RTOL * abs(lo_ref)
+    assert rel_err(pg, po_ref) <= RTOL
+    # bit-for-bit against the oracle in engine arithmetic
+    ops, pm, br = sched
+    for mi in pm:
+        assert same_bits(g.get_pmatrix(int(mi)), o.get_pmatrix(int(mi))), f"P-matrix {mi}"
+    for op in ops:
+        assert same_bits(g.get_clv(op.parent_clv_index), o.get_clv(op.parent_clv_index)), "CLV"
+        assert np.array_equal(g.get_scaler(op.parent_scaler_index), o.get_scaler(op.parent_scaler_index))
+    assert same_bits(pg, po_eng)
+    assert same_bits([lg], [lo_eng])
+    if data == "iid" and n >= 300:
+        assert g.get_scaler(case.root_scaler).max() >= 1, "the underflow case must exercise the scalers"
+    # reference invariant: bit-identical on a second call (test/src/model.cpp:59-75)
+    lg2 = compute_lh(g, sched, case.root_clv, case.root_scaler)
+    assert same_bits([lg], [lg2])
+
+
+def test_tip_clv_readback_and_frequencies():
+    case = Case(12, 333, 4, seed=7, data="ambiguous", weights="random")
+    g, o = make(case)
+    for t in range(case.n):
+        assert same_bits(g.get_clv(t), o.get_clv(t))
+    fg, fo = g.empirical_frequencies(), o.empirical_frequencies()
+    assert abs(fg.sum() - 1) < 1e-12
+    assert np.allclose(fg, fo, rtol=1e-13, atol=0)
+
+
+@pytest.mark.parametrize("n,S,K", [(10, 991, 4), (50, 3001, 4), (17, 64, 1)])
+def test_root_only_and_full_paths_agree(n, S, K):
+    """test/src/model.cpp:271-288: compute_lh == compute_lh_root (zero tolerance)"""
+    case = Case(n, S, K, seed=n * S)
+    g, o = make(case)
+    for rid in range(case.tree.root_count):
+        full = compute_lh(g, case.full_schedule(rid, 0.5), case.root_clv, case.root_scaler)
+        root = compute_lh_root(g, case.derivative_schedule(rid, 0.5), case.root_clv, case.root_scaler)
+        assert same_bits([full], [root])
+        if rid % 7 == 0:
+            oo = compute_lh(o, case.full_schedule(rid, 0.5), case.root_clv, case.root_scaler, mode=MODE_ENGINE)
+            assert same_bits([full], [oo])
+
+
+@pytest.mark.parametrize("n,S,K,data", [(10, 991, 4, "evolved"), (60, 2000, 4, "ambiguous"), (300, 257, 4, "iid")])
+def test_move_root_sequence_matches_oracle(n, S, K, data):
+    """suggest_roots_lh (src/model.cpp:865-889): move_root + compute_lh_root per root"""
+    case = Case(n, S, K, seed=31 * n, data=data)
+    g, o = make(case)
+    s0 = case.full_schedule(0, 0.5)
+    compute_lh(g, s0, case.root_clv, case.root_scaler)
+    compute_lh(o, s0, case.root_clv, case.root_scaler)
+    rng = np.random.default_rng(5)
+    order = list(range(case.tree.root_count))
+    rng.shuffle(order)
+    for rid in order[:40]:
+        ms = case.move_schedule(rid, 0.5)
+        ds = case.derivative_schedule(rid, 0.37)
+        move_root(g, ms)
+        move_root(o, ms)
+        a = compute_lh_root(g, ds, case.root_clv, case.root_scaler)
+        b_ref = compute_lh_root(o, ds, case.root_clv, case.root_scaler, mode=MODE_REFERENCE)
+        b_eng = o.root_loglikelihood(case.root_clv, case.root_scaler, mode=MODE_ENGINE)
+        assert abs(a - b_ref) <= RTOL * abs(b_ref)
+        assert same_bits([a], [b_eng])
+
+
+def test_root_invariance_under_reversible_model():
+    """test/src/model.cpp:367-387: all-ones rates + uniform pi => every root gives the same logL"""
+    case = Case(30, 800, 4, seed=99, data="ambiguous")
+    case.rates = np.ones(12)
+    case.freqs = np.full(4, 0.25)
+    g, o = make(case)
+    vals = [compute_lh(g, case.full_schedule(r, 0.5), case.root_clv, case.root_scaler)
+            for r in range(case.tree.root_count)]
+    assert np.ptp(vals) <= 1.2e-5 * abs(vals[0])
+
+
+def test_multi_candidate_root_evaluation():
+    """rdk_root_loglikelihood_multi == repeated compute_lh_root, state untouched"""
+    case = Case(40, 1500, 4, seed=3)
+    g, o = make(case)
+    s0 = case.full_schedule(5, 0.5)
+    compute_lh(g, s0, case.root_clv, case.root_scaler)
+    compute_lh(o, s0, case.root_clv, case.root_scaler)
+    op, pm, br = case.derivative_schedule(5, 0.5)
+    total = br.sum()
+    ratios = np.array([0.0, 1e-8, 0.25, 0.5, 0.5 + 1e-8, 0.75, 1.0 - 1e-8, 1.0])
+    pairs = np.stack([total * ratios, total * (1 - ratios)], axis=1)
+    before = g.get_clv(op.parent_clv_index).copy()
+    got = g.root_loglikelihood_multi(op, pairs)
+    want = o.root_loglikelihood_multi(op, pairs, mode=MODE_ENGINE)
+    assert same_bits(got, want)
+    assert same_bits(before, g.get_clv(op.parent_clv_index))
+    # zero-length root branch: P(0) must be exactly the identity (SURVEY B-15)
+    g.update_prob_matrices([int(pm[0])], [0.0])
+    assert np.array_equal(g.get_pmatrix(int(pm[0])), np.tile(np.eye(4), (case.K, 1, 1)))
+
+
+@pytest.mark.parametrize("n,S,K,data", [(12, 500, 4, "evolved"), (80, 1200, 4, "ambiguous"), (300, 129, 2, "iid")])
+def test_sweep_equals_sequential_calls(n, S, K, data):
+    case = Case(n, S, K, seed=17 + n, data=data)
+    g, o = make(case)
+    s0 = case.full_schedule(0, 0.5)
+    compute_lh(g, s0, case.root_clv, case.root_scaler)
+    compute_lh(o, s0, case.root_clv, case.root_scaler)
+    roots = list(range(case.tree.root_count))
+    sw = case.sweep_schedule(roots, 0.5)
+    got = g.sweep_root_placements(*sw, case.root_clv, case.root_scaler)
+    want = o.sweep_root_placements(*sw, case.root_clv, case.root_scaler, mode=MODE_ENGINE)
+    want_ref = o.sweep_root_placements(*case.sweep_schedule(roots, 0.5), case.root_clv, case.root_scaler,
+                                       mode=MODE_REFERENCE)
+    assert same_bits(got, want)
+    assert rel_err(got, want_ref) <= RTOL
+    # ranking of candidate roots identical
+    assert np.array_equal(np.argsort(-got, kind="stable"), np.argsort(-want, kind="stable"))
+    # state afterwards = state after the last placement
+    for idx in (case.root_clv,):
+        assert same_bits(g.get_clv(idx), o.get_clv(idx))
+
+
+def test_launch_configs_do_not_change_results():
+    case = Case(25, 5000, 4, seed=11, data="ambiguous", weights="random")
+    g, o = make(case)
+    sched = case.full_schedule(3, 0.4)
+    want = compute_lh(o, sched, case.root_clv, case.root_scaler, mode=MODE_ENGINE)
+    for ctas, threads, elems in [(1, 32, 1), (2, 256, 2), (4, 128, 4), (8, 64, 1), (3, 96, 2)]:
+        g.set_launch_config(ctas, threads, elems)
+        got = compute_lh(g, sched, case.root_clv, case.root_scaler)
+        assert same_bits([got], [want]), (ctas, threads, elems)
+
+
+def test_error_paths():
+    from root_digger_b200.capi import EngineError, Partition
+    with pytest.raises(EngineError):
+        Partition(4, 10, 3)  # rate_cats must divide 32
+    p = Partition(4, 10, 4)
+    with pytest.raises(EngineError):
+        p.set_tip_states(0, b"ACGTACGT!J")  # illegal state code
+    with pytest.raises(EngineError):
+        p.update_prob_matrices([99], [0.1])
+    with pytest.raises(EngineError):
+        p.update_prob_matrices([0], [-1.0])
+    # empty partition
+    e = Partition(4, 0, 4)
+    assert e.root_loglikelihood(6, 2) == 0.0
