@@ -274,12 +274,29 @@ int launch_pmatrices(rdk_partition_t *p) {
   return RDK_SUCCESS;
 }
 
+template <int K, int E, int MAXT, int MINB>
+int launch_program_inst(const ProgArgs &a, int grid, int threads, cudaStream_t st) {
+  // shared memory: program window + double-buffered P / tip tables of both children
+  const size_t smem = sizeof(Instr) * kProgWindow + sizeof(double) * 2 * 2 * 64 * K;
+  static bool  configured = false;  // per template instantiation
+  if (!configured) {
+    cudaError_t err = cudaFuncSetAttribute(clv_program_kernel<K, E, MAXT, MINB>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return fail(RDK_ERROR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(err));
+    configured = true;
+  }
+  clv_program_kernel<K, E, MAXT, MINB><<<grid, threads, smem, st>>>(a);
+  return RDK_SUCCESS;
+}
+
 template <int K>
-void launch_program_E(const ProgArgs &a, int grid, int threads, int E, cudaStream_t st) {
+int launch_program(const ProgArgs &a, int grid, int threads, int E, cudaStream_t st) {
+  // elements per thread E trades registers (occupancy) for fewer shared-memory
+  // table reads per element
   switch (E) {
-    case 1: clv_program_kernel<K, 1><<<grid, threads, 0, st>>>(a); break;
-    case 4: clv_program_kernel<K, 4><<<grid, threads, 0, st>>>(a); break;
-    default: clv_program_kernel<K, 2><<<grid, threads, 0, st>>>(a); break;
+    case 1: return launch_program_inst<K, 1, 256, 3>(a, grid, threads, st);
+    case 4: return launch_program_inst<K, 4, 128, 2>(a, grid, std::min(threads, 128), st);
+    default: return launch_program_inst<K, 2, 128, 3>(a, grid, std::min(threads, 128), st);
   }
 }
 
@@ -342,20 +359,22 @@ int flush(rdk_partition_t *p) {
     a.prog = reinterpret_cast<const Instr *>(d);
   }
   if (nelem > 0) {
-    int threads = e->threads ? e->threads : 256;
-    int per_sm = e->ctas_per_sm ? e->ctas_per_sm : 2;
+    int threads = e->threads ? e->threads : 96;
+    int per_sm = e->ctas_per_sm ? e->ctas_per_sm : 4;
     int E = e->elems ? e->elems : 2;
     int grid = e->sm_count * per_sm;
     // never launch more warps than warp iterations
+    if (E >= 2) threads = std::min(threads, 128);
+    if (E == 3) E = 2;
     int max_grid = (int)((n_witer + (threads / 32) - 1) / (threads / 32));
     grid = std::max(1, std::min(grid, max_grid));
     switch (e->K) {
-      case 1: launch_program_E<1>(a, grid, threads, E, e->stream); break;
-      case 2: launch_program_E<2>(a, grid, threads, E, e->stream); break;
-      case 4: launch_program_E<4>(a, grid, threads, E, e->stream); break;
-      case 8: launch_program_E<8>(a, grid, threads, E, e->stream); break;
-      case 16: launch_program_E<16>(a, grid, threads, E, e->stream); break;
-      case 32: launch_program_E<32>(a, grid, threads, E, e->stream); break;
+      case 1: if (!launch_program<1>(a, grid, threads, E, e->stream)) return RDK_FAILURE; break;
+      case 2: if (!launch_program<2>(a, grid, threads, E, e->stream)) return RDK_FAILURE; break;
+      case 4: if (!launch_program<4>(a, grid, threads, E, e->stream)) return RDK_FAILURE; break;
+      case 8: if (!launch_program<8>(a, grid, threads, E, e->stream)) return RDK_FAILURE; break;
+      case 16: if (!launch_program<16>(a, grid, threads, E, e->stream)) return RDK_FAILURE; break;
+      case 32: if (!launch_program<32>(a, grid, threads, E, e->stream)) return RDK_FAILURE; break;
       default: return fail(RDK_ERROR_PARAM, "rate_cats must divide 32");
     }
     CUDA_TRY(cudaGetLastError());
@@ -475,8 +494,8 @@ int make_instr(rdk_partition_t *p, const rdk_operation_t &op, unsigned flags, In
     if (op.child2_scaler_index != RDK_SCALE_BUFFER_NONE)
       in.c2scale = e->d_scalers + (size_t)op.child2_scaler_index * e->S;
   }
-  in.P1 = e->d_pool + (size_t)e->pm_map[op.child1_matrix_index] * e->K * 16;
-  in.P2 = e->d_pool + (size_t)e->pm_map[op.child2_matrix_index] * e->K * 16;
+  in.P1 = e->d_pool + (size_t)e->pm_map[op.child1_matrix_index] * e->K * kSlotDoubles;
+  in.P2 = e->d_pool + (size_t)e->pm_map[op.child2_matrix_index] * e->K * kSlotDoubles;
   *out = in;
   return RDK_SUCCESS;
 }
@@ -577,7 +596,7 @@ static int engine_init(rdk_partition_t *p, Engine *e) {
 
   // P-matrix pool: every index has a slot, plus spare slots for renaming
   e->pool_slots = e->prob_matrices * 2 + 4096;
-  size_t pool_bytes = sizeof(double) * 16 * e->K * (size_t)e->pool_slots;
+  size_t pool_bytes = sizeof(double) * kSlotDoubles * e->K * (size_t)e->pool_slots;
   if (!dev_alloc(e, (void **)&e->d_pool, pool_bytes)) return RDK_FAILURE;
   CUDA_TRY(cudaMemsetAsync(e->d_pool, 0, pool_bytes, e->stream));
   e->pm_map.resize(e->prob_matrices);
@@ -714,7 +733,7 @@ extern "C" int rdk_set_tip_states(rdk_partition_t *p, unsigned int tip_index, co
       snprintf(tl_errmsg, sizeof(tl_errmsg), "Illegal state code in tip \"%c\"", sequence[s]);
       return RDK_FAILURE;
     }
-    h[s] = (char)(st & 15ull);
+    h[s] = (char)tip_code_of_mask((unsigned)(st & 15ull));
   }
   CUDA_TRY(cudaMemcpyAsync(e->d_tips + (size_t)tip_index * e->tip_stride, h, e->S,
                            cudaMemcpyHostToDevice, e->stream));
@@ -925,8 +944,8 @@ extern "C" int rdk_root_loglikelihood_multi(rdk_partition_t *p, const rdk_operat
     in.flags |= kEval;  // no kWrite: partition state is left untouched
     in.parent = nullptr;
     in.pscale = nullptr;
-    in.P1 = e->d_pool + (size_t)s1 * e->K * 16;
-    in.P2 = e->d_pool + (size_t)s2 * e->K * 16;
+    in.P1 = e->d_pool + (size_t)s1 * e->K * kSlotDoubles;
+    in.P2 = e->d_pool + (size_t)s2 * e->K * kSlotDoubles;
     in.slot = b;
     e->pend_bytes += op_bytes(e, in);
     e->pend_prog.push_back(in);
@@ -1196,9 +1215,13 @@ extern "C" int rdk_get_pmatrix(rdk_partition_t *p, unsigned int matrix_index, do
   CUDA_TRY(cudaSetDevice(e->device));
   if (matrix_index >= e->prob_matrices) return fail(RDK_ERROR_PARAM, "matrix index out of range");
   if (!flush(p)) return RDK_FAILURE;
-  CUDA_TRY(cudaMemcpyAsync(out, e->d_pool + (size_t)e->pm_map[matrix_index] * e->K * 16,
+  std::vector<double> tmp((size_t)16 * e->K);
+  CUDA_TRY(cudaMemcpyAsync(tmp.data(), e->d_pool + (size_t)e->pm_map[matrix_index] * e->K * kSlotDoubles,
                            sizeof(double) * 16 * e->K, cudaMemcpyDeviceToHost, e->stream));
   CUDA_TRY(cudaStreamSynchronize(e->stream));
+  // device layout [i*4+j][cat] -> corax layout [cat][i][j]
+  for (unsigned k = 0; k < e->K; ++k)
+    for (int ij = 0; ij < 16; ++ij) out[(size_t)k * 16 + ij] = tmp[(size_t)ij * e->K + k];
   return RDK_SUCCESS;
 }
 
@@ -1221,8 +1244,8 @@ extern "C" int rdk_partition_set_launch_config(rdk_partition_t *p, int ctas_per_
   Engine *e = eng(p);
   if (threads_per_cta != 0 && (threads_per_cta < 32 || threads_per_cta > 256 || threads_per_cta % 32))
     return fail(RDK_ERROR_PARAM, "threads_per_cta must be a multiple of 32 in [32,256]");
-  if (elems_per_thread != 0 && elems_per_thread != 1 && elems_per_thread != 2 && elems_per_thread != 4)
-    return fail(RDK_ERROR_PARAM, "elems_per_thread must be 1, 2 or 4");
+  if (elems_per_thread < 0 || elems_per_thread > 4)
+    return fail(RDK_ERROR_PARAM, "elems_per_thread must be in [0,4]");
   if (ctas_per_sm < 0 || ctas_per_sm > 32) return fail(RDK_ERROR_PARAM, "ctas_per_sm out of range");
   std::lock_guard<std::mutex> lk(e->mu);
   e->ctas_per_sm = ctas_per_sm;

@@ -310,9 +310,32 @@ __device__ inline void build_q_nonrev(const double* r, const double* pi, double*
 }
 
 // ---------------------------------------------------------------------------
-// pmat_expm_nonrev: one thread per (branch entry, rate category).
-// Replaces corax_update_prob_matrices.  Output layout [slot][cat][i][j].
+// Tip states are stored on the device as 4-bit CODES, a permutation of the
+// 4-bit state masks chosen so that the unambiguous states A,C,G,T get codes
+// 0..3 (they then hit distinct shared-memory banks in the tip tables).
 // ---------------------------------------------------------------------------
+__host__ __device__ __forceinline__ unsigned tip_mask_of_code(unsigned code) {
+  // code: 0  1  2  3  4  5  6  7  8  9  10 11 12 13 14 15
+  // mask: 1  2  4  8  3  5  6  7  9  10 11 12 13 14 15 0
+  return (unsigned)((0x0FEDCBA976538421ULL >> (4 * code)) & 15ULL);
+}
+__host__ __device__ __forceinline__ unsigned tip_code_of_mask(unsigned mask) {
+  // mask: 0  1  2  3  4  5  6  7  8  9  10 11 12 13 14 15
+  // code: 15 0  1  4  2  5  6  7  3  8  9  10 11 12 13 14
+  return (unsigned)((0xEDCBA9837652410FULL >> (4 * mask)) & 15ULL);
+}
+
+// ---------------------------------------------------------------------------
+// pmat_expm_nonrev: one thread per (branch entry, rate category).
+// Replaces corax_update_prob_matrices.  A pool slot holds, for one branch,
+//   P : [i*4+j][cat]            16*K doubles  (the transition matrices)
+//   T : [i][tip code][cat]      64*K doubles  (tip lookup table)
+// T[i][code][k] = ((P_i0 c_0 + P_i1 c_1) + P_i2 c_2) + P_i3 c_3 with c the 0/1
+// vector of the tip state: exactly the expression a tip child contributes to a
+// CLV update, evaluated once per branch instead of once per site.
+// ---------------------------------------------------------------------------
+constexpr int kSlotDoubles = 80;  // per category
+
 struct PmatEntry {
   unsigned slot;  // physical slot in the P-matrix pool
   unsigned pad;
@@ -345,8 +368,18 @@ __global__ void __launch_bounds__(64) pmat_expm_nonrev_kernel(const __grid_const
   double c = ddiv(dmul(a.rates[k], ent.t), dsub(1.0, a.pinv));
   for (int i = 0; i < 16; ++i) A[i] = dmul(Q[i], c);
   expm4(A, E);
-  double* out = a.pool + ((size_t)ent.slot * a.K + k) * 16;
-  for (int i = 0; i < 16; ++i) out[i] = E[i];
+  double* out = a.pool + (size_t)ent.slot * a.K * kSlotDoubles + k;
+  for (int i = 0; i < 16; ++i) out[(size_t)i * a.K] = E[i];
+  double* tab = out + (size_t)16 * a.K;
+  for (int i = 0; i < 4; ++i)
+    for (unsigned code = 0; code < 16; ++code) {
+      unsigned m = tip_mask_of_code(code);
+      double   x = dmul(E[i * 4 + 0], (m & 1u) ? 1.0 : 0.0);
+      x = dadd(x, dmul(E[i * 4 + 1], (m & 2u) ? 1.0 : 0.0));
+      x = dadd(x, dmul(E[i * 4 + 2], (m & 4u) ? 1.0 : 0.0));
+      x = dadd(x, dmul(E[i * 4 + 3], (m & 8u) ? 1.0 : 0.0));
+      tab[(size_t)(i * 16 + code) * a.K] = x;
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -368,7 +401,7 @@ __global__ void __launch_bounds__(64) pmat_expm_nonrev_kernel(const __grid_const
 // the thread's two 4x4 P-matrices live in registers for E iterations.
 // ---------------------------------------------------------------------------
 enum : unsigned {
-  kTip1 = 1u,      // child1 is a tip: 1 byte per site (4-bit state mask)
+  kTip1 = 1u,      // child1 is a tip: 1 byte per site (4-bit state code)
   kTip2 = 2u,      // child2 is a tip
   kWrite = 4u,     // store the parent CLV (and parent scaler if present)
   kEval = 8u,      // evaluate the root log-likelihood of the parent values
@@ -393,6 +426,7 @@ struct alignas(16) Instr {
 static_assert(sizeof(Instr) == 80, "Instr layout");
 
 constexpr int kProgInline = 8;
+constexpr int kProgWindow = 256;  // instructions staged in shared memory at a time
 struct ProgArgs {
   const Instr*    prog;  // used when n_instr > kProgInline
   int             n_instr;
@@ -412,10 +446,11 @@ struct d4 {
 };
 
 __device__ __forceinline__ d4 ld_clv(const double* p) {
-  // 32 B per thread as 2 x 128-bit loads; plain (coherent) loads because CLVs
-  // are read and written within one launch.
+  // 32 B per thread as 2 x 128-bit loads, L2-coherent (ld.global.cg): CLVs are
+  // read and written within one launch and never re-read by the same SM soon
+  // enough for L1 to help.
   const double2* q = reinterpret_cast<const double2*>(p);
-  double2        a = q[0], b = q[1];
+  double2        a = __ldcg(q), b = __ldcg(q + 1);
   d4             r;
   r.v[0] = a.x;
   r.v[1] = a.y;
@@ -425,124 +460,263 @@ __device__ __forceinline__ d4 ld_clv(const double* p) {
 }
 __device__ __forceinline__ void st_clv(double* p, const d4& x) {
   double2* q = reinterpret_cast<double2*>(p);
-  q[0] = make_double2(x.v[0], x.v[1]);
-  q[1] = make_double2(x.v[2], x.v[3]);
-}
-__device__ __forceinline__ d4 tip_vec(unsigned m) {
-  d4 r;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) r.v[j] = ((m >> j) & 1u) ? 1.0 : 0.0;
-  return r;
-}
-__device__ __forceinline__ void ld_p(const double* P, double* out) {
-  const double2* q = reinterpret_cast<const double2*>(P);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    double2 t = __ldg(q + i);
-    out[2 * i] = t.x;
-    out[2 * i + 1] = t.y;
-  }
-}
-__device__ __forceinline__ d4 matvec(const double* P, const d4& c) {
-  d4 r;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    double s = dmul(P[i * 4 + 0], c.v[0]);
-    s = dadd(s, dmul(P[i * 4 + 1], c.v[1]));
-    s = dadd(s, dmul(P[i * 4 + 2], c.v[2]));
-    s = dadd(s, dmul(P[i * 4 + 3], c.v[3]));
-    r.v[i] = s;
-  }
-  return r;
+  __stcg(q, make_double2(x.v[0], x.v[1]));
+  __stcg(q + 1, make_double2(x.v[2], x.v[3]));
 }
 
-template <int K, int E>
-__global__ void __launch_bounds__(256) clv_program_kernel(const __grid_constant__ ProgArgs a) {
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+// operands of one instruction for the E elements of a thread
+template <int E>
+struct Operands {
+  d4       c1[E], c2[E];  // inner children: the 4 state likelihoods
+  unsigned m1[E], m2[E];  // tip children: the state code
+  unsigned cnt[E];        // sum of the children's scaler counts (k == 0 lanes)
+};
+
+// Each CTA owns a contiguous range of warp iterations and walks the whole
+// program over it, one "pass" of (warps per CTA x E) iterations at a time.
+//  * the program is staged in shared memory in windows;
+//  * per instruction and child, either the transition matrices P (inner child,
+//    16K doubles) or the tip table T (tip child, 64K doubles) of the child's
+//    branch is prefetched into a shared double buffer with cp.async while the
+//    previous instruction computes; one __syncthreads per instruction keeps the
+//    CTA's warps on the same instruction (needed for this buffer only -- CLV
+//    dependencies are per element and therefore per thread);
+//  * the global operands of instruction i+1 are loaded into registers BEFORE
+//    the arithmetic of instruction i (software pipelining, two register sets
+//    used in ping-pong), and when a child of i+1 is the CLV instruction i is
+//    producing -- the normal case in a post-order schedule -- it is forwarded in
+//    registers and never re-read.
+template <int K, int E, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) clv_program_kernel(const __grid_constant__ ProgArgs a) {
   static_assert(32 % K == 0, "K must divide the warp size");
-  const unsigned lane = threadIdx.x & 31u;
-  const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const unsigned nwarps = (gridDim.x * blockDim.x) >> 5;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Instr*  s_prog = reinterpret_cast<Instr*>(smem_raw);
+  double* s_tab = reinterpret_cast<double*>(smem_raw + sizeof(Instr) * kProgWindow);
+  // s_tab[buf][child][64*K]
+  constexpr unsigned kTabDoubles = 64 * K;
+
+  const unsigned tid = threadIdx.x;
+  const unsigned lane = tid & 31u;
+  const unsigned wib = tid >> 5;
+  const unsigned wpb = blockDim.x >> 5;
   const unsigned k = lane % K;
   const bool     k0 = (k == 0);
-  // the K lanes of this thread's site
   const unsigned gmask = (K == 32) ? 0xffffffffu : (((1u << K) - 1u) << (lane - k));
 
-  const unsigned it_begin = (unsigned)(((unsigned long long)a.n_witer * warp) / nwarps);
-  const unsigned it_end = (unsigned)(((unsigned long long)a.n_witer * (warp + 1)) / nwarps);
-  const bool     inl = a.n_instr <= kProgInline;
+  const unsigned it_begin = (unsigned)(((unsigned long long)a.n_witer * blockIdx.x) / gridDim.x);
+  const unsigned it_end = (unsigned)(((unsigned long long)a.n_witer * (blockIdx.x + 1)) / gridDim.x);
+  const unsigned per_pass = wpb * E;
+  const unsigned passes = (it_end - it_begin + per_pass - 1) / per_pass;
+  const bool     single_window = a.n_instr <= kProgWindow;
 
-  for (unsigned it0 = it_begin; it0 < it_end; it0 += E) {
-    for (int ii = 0; ii < a.n_instr; ++ii) {
-      const Instr in = inl ? a.inl[ii] : a.prog[ii];
+  // stage P or T of both children of `in` into buffer `buf`
+  auto prefetch_tables = [&](const Instr& in, unsigned buf) {
+    const unsigned fl = in.flags;
+    if (!(fl & kLoadOnly)) {
+      double* dst = s_tab + (size_t)buf * 2 * kTabDoubles;
+      {
+        const double*  src = (fl & kTip1) ? in.P1 + 16 * K : in.P1;
+        const unsigned chunks = (fl & kTip1) ? 32 * K : 8 * K;
+        for (unsigned c = tid; c < chunks; c += blockDim.x) cp_async16(dst + c * 2, src + c * 2);
+      }
+      {
+        const double*  src = (fl & kTip2) ? in.P2 + 16 * K : in.P2;
+        const unsigned chunks = (fl & kTip2) ? 32 * K : 8 * K;
+        for (unsigned c = tid; c < chunks; c += blockDim.x)
+          cp_async16(dst + kTabDoubles + c * 2, src + c * 2);
+      }
+    }
+    cp_async_commit();
+  };
+
+  for (unsigned pass = 0; pass < passes; ++pass) {
+    unsigned it[E], site[E];
+    size_t   off[E];  // element offset in doubles
+    bool     valid[E];
+#pragma unroll
+    for (int u = 0; u < E; ++u) {
+      it[u] = it_begin + (pass * E + u) * wpb + wib;
+      unsigned e = it[u] * 32u + lane;
+      valid[u] = (it[u] < it_end) && (e < a.nelem);
+      // lanes without an element read element `lane` (always in bounds when the
+      // partition is non-empty; the kernel is not launched otherwise) and never store
+      if (!valid[u]) e = lane < a.nelem ? lane : 0u;
+      site[u] = e / K;
+      off[u] = (size_t)e * 4;
+    }
+
+    // issue the global loads of one instruction's operands; an operand equal to
+    // fwd_clv / fwd_scale (what the previous instruction is writing) is skipped
+    // here and forwarded from registers by the caller
+    auto load_operands = [&](const Instr& in, Operands<E>& o, const void* fwd_clv,
+                             const unsigned* fwd_scale) {
       const unsigned fl = in.flags;
-      double         P1[16], P2[16];
+      if (fl & kTip1) {
+        const unsigned char* t = reinterpret_cast<const unsigned char*>(in.c1);
+#pragma unroll
+        for (int u = 0; u < E; ++u) o.m1[u] = __ldg(t + site[u]);
+      } else if (in.c1 != fwd_clv) {
+        const double* g = reinterpret_cast<const double*>(in.c1);
+#pragma unroll
+        for (int u = 0; u < E; ++u) o.c1[u] = ld_clv(g + off[u]);
+      }
       if (!(fl & kLoadOnly)) {
-        ld_p(in.P1 + k * 16, P1);
-        ld_p(in.P2 + k * 16, P2);
-      }
-      d4       c1[E], c2[E];
-      unsigned cnt[E];
-      bool     valid[E];
-      // phase 1: issue every load of this instruction
+        if (fl & kTip2) {
+          const unsigned char* t = reinterpret_cast<const unsigned char*>(in.c2);
 #pragma unroll
-      for (int u = 0; u < E; ++u) {
-        const unsigned it = it0 + u;
-        const unsigned e = it * 32u + lane;
-        valid[u] = (it < it_end) && (e < a.nelem);
-        cnt[u] = 0;
-        if (valid[u]) {
-          const unsigned site = e / K;
-          if (fl & kTip1)
-            c1[u] = tip_vec(__ldg(reinterpret_cast<const unsigned char*>(in.c1) + site));
-          else
-            c1[u] = ld_clv(reinterpret_cast<const double*>(in.c1) + (size_t)e * 4);
-          if (!(fl & kLoadOnly)) {
-            if (fl & kTip2)
-              c2[u] = tip_vec(__ldg(reinterpret_cast<const unsigned char*>(in.c2) + site));
-            else
-              c2[u] = ld_clv(reinterpret_cast<const double*>(in.c2) + (size_t)e * 4);
-          }
-          if (k0) {
-            if (in.c1scale) cnt[u] = in.c1scale[site];
-            if (in.c2scale) cnt[u] += in.c2scale[site];
-          }
+          for (int u = 0; u < E; ++u) o.m2[u] = __ldg(t + site[u]);
+        } else if (in.c2 != fwd_clv) {
+          const double* g = reinterpret_cast<const double*>(in.c2);
+#pragma unroll
+          for (int u = 0; u < E; ++u) o.c2[u] = ld_clv(g + off[u]);
         }
       }
-      // phase 2: arithmetic, rescaling, stores, log-likelihood
 #pragma unroll
-      for (int u = 0; u < E; ++u) {
-        const unsigned it = it0 + u;
-        if (it >= it_end) break;  // warp-uniform
-        const unsigned e = it * 32u + lane;
-        const unsigned site = e / K;
-        d4             v;
-        if (fl & kLoadOnly) {
-          v = c1[u];
+      for (int u = 0; u < E; ++u) o.cnt[u] = 0;
+      const unsigned* s1 = in.c1scale;
+      const unsigned* s2 = in.c2scale;
+      if (k0) {
+        if (s1 && s1 != fwd_scale) {
+#pragma unroll
+          for (int u = 0; u < E; ++u) o.cnt[u] = __ldcg(s1 + site[u]);
+        }
+        if (s2 && s2 != fwd_scale) {
+#pragma unroll
+          for (int u = 0; u < E; ++u) o.cnt[u] += __ldcg(s2 + site[u]);
+        }
+      }
+    };
+
+    // one instruction: `cur` holds its operands, the operands of the next
+    // instruction are loaded into `nxt`
+    auto step = [&](int ii, int wn, Operands<E>& cur, Operands<E>& nxt) {
+      cp_async_wait_all();
+      __syncthreads();  // tables(ii) visible; every warp has finished instruction ii-1
+      const bool more = ii + 1 < wn;
+      if (more) prefetch_tables(s_prog[ii + 1], (unsigned)(ii + 1) & 1u);
+      const Instr&   in = s_prog[ii];
+      const unsigned fl = in.flags;
+      const double*  tab = s_tab + (size_t)((unsigned)ii & 1u) * 2 * kTabDoubles;
+
+      const void*     fwd_clv = (fl & kWrite) ? (const void*)in.parent : nullptr;
+      const unsigned* fwd_scale = (fl & kWrite) ? in.pscale : nullptr;
+      bool            f1 = false, f2 = false, fs1 = false, fs2 = false;
+      if (more) {
+        const Instr& nx = s_prog[ii + 1];
+        f1 = fwd_clv && nx.c1 == fwd_clv;
+        f2 = fwd_clv && !(nx.flags & kLoadOnly) && nx.c2 == fwd_clv;
+        fs1 = fwd_scale && nx.c1scale == fwd_scale;
+        fs2 = fwd_scale && nx.c2scale == fwd_scale;
+        load_operands(nx, nxt, fwd_clv, fwd_scale);
+      }
+
+      d4 v[E];
+      if (fl & kLoadOnly) {
+#pragma unroll
+        for (int u = 0; u < E; ++u) v[u] = cur.c1[u];
+      } else {
+        // child 1
+        if (fl & kTip1) {
+#pragma unroll
+          for (int u = 0; u < E; ++u)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[u].v[i] = tab[(i * 16 + cur.m1[u]) * K + k];
         } else {
-          d4 x = matvec(P1, c1[u]);
-          d4 y = matvec(P2, c2[u]);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) v.v[i] = dmul(x.v[i], y.v[i]);
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const double p = tab[(i * 4 + j) * K + k];
+#pragma unroll
+              for (int u = 0; u < E; ++u) {
+                const double t = dmul(p, cur.c1[u].v[j]);
+                v[u].v[i] = (j == 0) ? t : dadd(v[u].v[i], t);
+              }
+            }
         }
-        if (fl & kScale) {
-          bool small = valid[u] && (v.v[0] < RDK_SCALE_THRESHOLD) && (v.v[1] < RDK_SCALE_THRESHOLD) &&
-                       (v.v[2] < RDK_SCALE_THRESHOLD) && (v.v[3] < RDK_SCALE_THRESHOLD);
+        // child 2
+        const double* tab2 = tab + kTabDoubles;
+        if (fl & kTip2) {
+#pragma unroll
+          for (int u = 0; u < E; ++u)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[u].v[i] = dmul(v[u].v[i], tab2[(i * 16 + cur.m2[u]) * K + k]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            double y[E];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const double p = tab2[(i * 4 + j) * K + k];
+#pragma unroll
+              for (int u = 0; u < E; ++u) {
+                const double t = dmul(p, cur.c2[u].v[j]);
+                y[u] = (j == 0) ? t : dadd(y[u], t);
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < E; ++u) v[u].v[i] = dmul(v[u].v[i], y[u]);
+          }
+        }
+      }
+      if (fl & kScale) {
+#pragma unroll
+        for (int u = 0; u < E; ++u) {
+          bool small = valid[u] && (v[u].v[0] < RDK_SCALE_THRESHOLD) && (v[u].v[1] < RDK_SCALE_THRESHOLD) &&
+                       (v[u].v[2] < RDK_SCALE_THRESHOLD) && (v[u].v[3] < RDK_SCALE_THRESHOLD);
           unsigned m = __ballot_sync(0xffffffffu, small);
           if ((m & gmask) == gmask) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) v.v[i] = dmul(v.v[i], RDK_SCALE_FACTOR);
-            cnt[u] += 1;
+            for (int i = 0; i < 4; ++i) v[u].v[i] = dmul(v[u].v[i], RDK_SCALE_FACTOR);
+            cur.cnt[u] += 1;
           }
         }
-        if ((fl & kWrite) && valid[u]) {
-          st_clv(in.parent + (size_t)e * 4, v);
-          if (k0 && in.pscale) in.pscale[site] = cnt[u];
+      }
+      if (fl & kWrite) {
+        double*   par = in.parent;
+        unsigned* ps = in.pscale;
+#pragma unroll
+        for (int u = 0; u < E; ++u)
+          if (valid[u]) st_clv(par + off[u], v[u]);
+        if (k0 && ps) {
+#pragma unroll
+          for (int u = 0; u < E; ++u)
+            if (valid[u]) __stcg(ps + site[u], cur.cnt[u]);
         }
-        if (fl & kEval) {
-          double t = dmul(a.pi[0], v.v[0]);
-          t = dadd(t, dmul(a.pi[1], v.v[1]));
-          t = dadd(t, dmul(a.pi[2], v.v[2]));
-          t = dadd(t, dmul(a.pi[3], v.v[3]));
+      }
+      // register forwarding into the operands of instruction ii+1
+      if (f1) {
+#pragma unroll
+        for (int u = 0; u < E; ++u) nxt.c1[u] = v[u];
+      }
+      if (f2) {
+#pragma unroll
+        for (int u = 0; u < E; ++u) nxt.c2[u] = v[u];
+      }
+      if (fs1) {
+#pragma unroll
+        for (int u = 0; u < E; ++u) nxt.cnt[u] += cur.cnt[u];
+      }
+      if (fs2) {
+#pragma unroll
+        for (int u = 0; u < E; ++u) nxt.cnt[u] += cur.cnt[u];
+      }
+      if (fl & kEval) {
+        // scaler term only when a scale buffer is attached to the root
+        const bool has_scaler = (fl & kLoadOnly) ? (in.c1scale != nullptr) : ((fl & kScale) != 0);
+#pragma unroll
+        for (int u = 0; u < E; ++u) {
+          double t = dmul(a.pi[0], v[u].v[0]);
+          t = dadd(t, dmul(a.pi[1], v[u].v[1]));
+          t = dadd(t, dmul(a.pi[2], v[u].v[2]));
+          t = dadd(t, dmul(a.pi[3], v[u].v[3]));
           double term = dmul(a.w[0], t);
 #pragma unroll
           for (int kk = 1; kk < K; ++kk) {
@@ -552,18 +726,43 @@ __global__ void __launch_bounds__(256) clv_program_kernel(const __grid_constant_
           double l = 0.0;
           if (valid[u] && k0) {
             l = rd_log(term);
-            // scaler term only when a scale buffer is attached to the root
-            const bool has_scaler = (fl & kLoadOnly) ? (in.c1scale != nullptr) : ((fl & kScale) != 0);
-            if (has_scaler) l = dadd(l, dmul((double)cnt[u], RDK_LOG_SCALE_THRESHOLD));
-            l = dmul(l, (double)__ldg(a.weights + site));
-            if (a.persite && in.slot == 0) a.persite[site] = l;
+            if (has_scaler) l = dadd(l, dmul((double)cur.cnt[u], RDK_LOG_SCALE_THRESHOLD));
+            l = dmul(l, (double)__ldg(a.weights + site[u]));
+            if (a.persite && in.slot == 0) a.persite[site[u]] = l;
           }
           // canonical tree over the 32/K sites of this warp iteration
 #pragma unroll
-          for (int off = K; off < 32; off <<= 1) l = dadd(l, __shfl_xor_sync(0xffffffffu, l, off));
-          if (lane == 0) a.partials[(size_t)in.slot * a.partial_stride + it] = l;
+          for (int off2 = K; off2 < 32; off2 <<= 1) l = dadd(l, __shfl_xor_sync(0xffffffffu, l, off2));
+          if (lane == 0 && it[u] < it_end) a.partials[(size_t)in.slot * a.partial_stride + it[u]] = l;
         }
       }
+    };
+
+    for (int w0 = 0; w0 < a.n_instr; w0 += kProgWindow) {
+      const int wn = min(kProgWindow, a.n_instr - w0);
+      if (!(single_window && pass > 0)) {
+        __syncthreads();  // everyone is done with the previous window
+        const int4* src = reinterpret_cast<const int4*>(a.n_instr <= kProgInline ? a.inl : a.prog + w0);
+        int4*       dst = reinterpret_cast<int4*>(s_prog);
+        for (unsigned c = tid; c < (unsigned)wn * (sizeof(Instr) / 16); c += blockDim.x) dst[c] = src[c];
+        __syncthreads();
+      }
+      prefetch_tables(s_prog[0], 0);
+      Operands<E> opA, opB;
+#pragma unroll
+      for (int u = 0; u < E; ++u) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) opA.c1[u].v[i] = opA.c2[u].v[i] = opB.c1[u].v[i] = opB.c2[u].v[i] = 0.0;
+        opA.m1[u] = opA.m2[u] = opB.m1[u] = opB.m2[u] = 15u;  // code 15: all-zero table row
+        opA.cnt[u] = opB.cnt[u] = 0;
+      }
+      load_operands(s_prog[0], opA, nullptr, nullptr);
+      int ii = 0;
+      for (; ii + 1 < wn; ii += 2) {
+        step(ii, wn, opA, opB);
+        step(ii + 1, wn, opB, opA);
+      }
+      if (ii < wn) step(ii, wn, opA, opB);
     }
   }
 }
@@ -631,7 +830,7 @@ __global__ void __launch_bounds__(256) tip_hist_kernel(const unsigned char* __re
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (size_t)gridDim.x * blockDim.x) {
     unsigned tip = (unsigned)(idx / sites), s = (unsigned)(idx - (size_t)tip * sites);
-    unsigned m = tips[(size_t)tip * tip_stride + s] & 15u;
+    unsigned m = tip_mask_of_code(tips[(size_t)tip * tip_stride + s] & 15u);
     unsigned w = weights[s];
 #pragma unroll
     for (int i = 0; i < 16; ++i)
@@ -649,7 +848,7 @@ __global__ void tip_expand_kernel(const unsigned char* __restrict__ tip, unsigne
                                   double* __restrict__ out) {
   size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= (size_t)sites * K) return;
-  unsigned m = tip[e / K];
+  unsigned m = tip_mask_of_code(tip[e / K] & 15u);
   for (int j = 0; j < 4; ++j) out[e * 4 + j] = ((m >> j) & 1u) ? 1.0 : 0.0;
 }
 

@@ -24,7 +24,7 @@ def timed(fn, reps=5):
         a.record(); fn(); b.record(); torch.cuda.synchronize(); ts.append(a.elapsed_time(b))
     return min(ts), float(np.median(ts))
 res = []
-for ctas, threads, elems in [(2,256,2),(1,256,2),(1,256,4),(2,256,1),(4,128,1),(3,128,2),(4,128,2),(2,128,4),(6,64,2),(8,64,1),(4,64,4),(8,32,2)]:
+for ctas, threads, elems in [(6,128,1),(4,192,1),(3,256,1),(5,160,1),(3,128,2),(4,96,2),(6,64,2),(2,128,4),(4,64,4),(3,96,4)]:
     g.set_launch_config(ctas, threads, elems)
     g.reset_stats()
     lh = compute_lh(g, sched, case.root_clv, case.root_scaler)
