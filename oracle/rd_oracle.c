@@ -729,6 +729,30 @@ double rdo_compute_root_loglikelihood_mt(rdo_partition_t *p,
 double *rdo_msa_empirical_frequencies(rdo_partition_t *p) {
   double  *f = (double *)calloc(4, sizeof(double));
   unsigned K = p->rate_cats;
+  if (g_default_mode == RDO_MODE_ENGINE) {
+    /* ENGINE arithmetic: exact integer histogram of the weighted state masks,
+     * f_j = sum over masks m containing j (ascending m) of H[m]/popcount(m),
+     * divided by the total count -- order independent, hence identical on any
+     * number of shards */
+    unsigned long long hist[16] = {0};
+    for (unsigned t = 0; t < p->tips; ++t)
+      for (unsigned s = 0; s < p->sites; ++s) {
+        const double *c = p->clv[t] + ((size_t)s * K) * 4;
+        unsigned      m = 0;
+        for (int j = 0; j < 4; ++j)
+          if (c[j] != 0.0) m |= 1u << j;
+        hist[m] += p->pattern_weights[s];
+      }
+    double total = 0.0;
+    for (int m = 1; m < 16; ++m) total += (double)hist[m];
+    for (int j = 0; j < 4; ++j) {
+      double s = 0.0;
+      for (int m = 1; m < 16; ++m)
+        if (m & (1 << j)) s += (double)hist[m] / (double)__builtin_popcount(m);
+      f[j] = s / total;
+    }
+    return f;
+  }
   double   wsum = 0.0;
   for (unsigned s = 0; s < p->sites; ++s) wsum += (double)p->pattern_weights[s];
   for (unsigned t = 0; t < p->tips; ++t)

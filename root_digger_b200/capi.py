@@ -523,3 +523,184 @@ class RootedTree:
         if not self.L.rdh_tree_rank_roots(self.h, 0 if which == "midpoint" else 1, ids, n):
             raise RuntimeError(self.L.rdh_last_error().decode())
         return list(ids)
+
+
+# ---------------------------------------------------------------------------
+# model_t mirror (host C++) through the C wrappers
+# ---------------------------------------------------------------------------
+def _bind_model(L: C.CDLL):
+    if getattr(L, "_rdh_model_bound", False):
+        return
+    vp = C.c_void_p
+    ull = C.c_ulonglong
+    L.rdh_model_create.restype = vp
+    L.rdh_model_create.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_int, C.c_uint,
+                                   C.c_int, ull, C.c_int, C.c_int, C.POINTER(ull), C.POINTER(ull), ull, ull,
+                                   C.c_int, C.c_int, vp]
+    L.rdh_model_destroy.argtypes = [vp]
+    L.rdh_model_destroy.restype = None
+    L.rdh_model_sites.argtypes = [vp, C.c_uint]
+    L.rdh_model_sites.restype = C.c_uint
+    L.rdh_model_root_count.argtypes = [vp]
+    L.rdh_model_root_count.restype = C.c_uint
+    L.rdh_model_initialize_partitions.argtypes = [vp, C.c_int]
+    L.rdh_model_set_fused.argtypes = [vp, C.c_int]
+    L.rdh_model_set_params.argtypes = [vp, C.c_uint, _dp, _dp, _dp]
+    L.rdh_model_compute_lh.argtypes = [vp, C.c_uint, C.c_double, _dp]
+    L.rdh_model_compute_lh_root.argtypes = [vp, C.c_uint, C.c_double, _dp]
+    L.rdh_model_compute_dlh.argtypes = [vp, C.c_uint, C.c_double, _dp, _dp]
+    L.rdh_model_move_root.argtypes = [vp, C.c_uint, C.c_double]
+    L.rdh_model_optimize_alpha.argtypes = [vp, C.c_uint, C.c_double, C.c_double, _dp]
+    L.rdh_model_optimize_root_location.argtypes = [vp, C.c_uint, C.c_double, _up, _dp, _dp]
+    L.rdh_model_sweep_root_lh.argtypes = [vp, _dp]
+    L.rdh_model_compute_all_root_lh.argtypes = [vp, _dp]
+    L.rdh_model_search.argtypes = [vp, C.c_uint, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
+                                   C.c_int, C.c_uint, C.c_uint, _up, _dp, _dp]
+    L.rdh_model_exhaustive_search.argtypes = [vp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_uint,
+                                              C.c_uint, _up, _dp, _dp, C.c_uint, _up]
+    L.rdh_model_lwr.argtypes = [_dp, C.c_uint, _dp]
+    L.rdh_model_newick.argtypes = [vp, C.c_int]
+    L.rdh_model_newick.restype = vp
+    L.rdh_model_get_params.argtypes = [vp, C.c_uint, _dp, _dp, _dp]
+    L.rdh_model_partition.argtypes = [vp, C.c_uint]
+    L.rdh_model_partition.restype = vp
+    L._rdh_model_bound = True
+
+
+class Model:
+    """model_t (reference src/model.hpp:46-277) on the engine the host library was linked against."""
+
+    STRATEGY = {"random": 0, "midpoint": 1, "modified_mad": 2}
+
+    def __init__(self, tree: RootedTree, alignment: dict, rate_cats: int = 4, *, compress: bool = False,
+                 invariant_sites: bool = False, seed: int = 1, early_stop: bool = False, partitions=None,
+                 site_offset: int = 0, global_sites: int = 0, nranks: int = 1, rank: int = 0,
+                 comm_id: bytes | None = None):
+        self.L = tree.L
+        _bind_model(self.L)
+        labels = list(alignment)
+        n = len(labels)
+        la = (C.c_char_p * n)(*[l.encode() for l in labels])
+        sa = (C.c_char_p * n)(*[alignment[l] if isinstance(alignment[l], bytes) else alignment[l].encode()
+                                for l in labels])
+        nparts = 0 if not partitions else len(partitions)
+        pb = (C.c_ulonglong * max(1, nparts))(*([p[0] for p in partitions] if partitions else [0]))
+        pe = (C.c_ulonglong * max(1, nparts))(*([p[1] for p in partitions] if partitions else [0]))
+        cid = C.create_string_buffer(comm_id, 128) if comm_id else None
+        self.h = self.L.rdh_model_create(tree.h, n, la, sa, 1 if compress else 0, rate_cats,
+                                         1 if invariant_sites else 0, seed, 1 if early_stop else 0, nparts, pb, pe,
+                                         site_offset, global_sites, nranks, rank, cid)
+        if not self.h:
+            raise RuntimeError("model_t could not be created: " + self.L.rdh_last_error().decode())
+        self.h = C.c_void_p(self.h)
+        self.K = rate_cats
+        self.root_count = self.L.rdh_model_root_count(self.h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.rdh_model_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if not rc:
+            raise RuntimeError(self.L.rdh_last_error().decode())
+
+    def sites(self, part: int = 0) -> int:
+        return self.L.rdh_model_sites(self.h, part)
+
+    def initialize_partitions(self, uniform_freqs: bool = False):
+        self._check(self.L.rdh_model_initialize_partitions(self.h, 1 if uniform_freqs else 0))
+
+    def set_fused(self, on: bool):
+        self.L.rdh_model_set_fused(self.h, 1 if on else 0)
+
+    def set_params(self, rates=None, freqs=None, alpha=None, part: int = 0):
+        r = np.ascontiguousarray(rates, dtype=np.float64) if rates is not None else None
+        f = np.ascontiguousarray(freqs, dtype=np.float64) if freqs is not None else None
+        a = np.array([alpha], dtype=np.float64) if alpha is not None else None
+        self._check(self.L.rdh_model_set_params(self.h, part, _ptr(r, _dp) if r is not None else None,
+                                                _ptr(f, _dp) if f is not None else None,
+                                                _ptr(a, _dp) if a is not None else None))
+
+    def get_params(self, part: int = 0):
+        r, f, c = np.zeros(12), np.zeros(4), np.zeros(self.K)
+        self.L.rdh_model_get_params(self.h, part, _ptr(r, _dp), _ptr(f, _dp), _ptr(c, _dp))
+        return r, f, c
+
+    def compute_lh(self, rid: int, ratio: float = 0.5) -> float:
+        out = C.c_double()
+        self._check(self.L.rdh_model_compute_lh(self.h, rid, ratio, C.byref(out)))
+        return out.value
+
+    def compute_lh_root(self, rid: int, ratio: float = 0.5) -> float:
+        out = C.c_double()
+        self._check(self.L.rdh_model_compute_lh_root(self.h, rid, ratio, C.byref(out)))
+        return out.value
+
+    def compute_dlh(self, rid: int, ratio: float = 0.5):
+        lh, dlh = C.c_double(), C.c_double()
+        self._check(self.L.rdh_model_compute_dlh(self.h, rid, ratio, C.byref(lh), C.byref(dlh)))
+        return lh.value, dlh.value
+
+    def move_root(self, rid: int, ratio: float = 0.5):
+        self._check(self.L.rdh_model_move_root(self.h, rid, ratio))
+
+    def optimize_alpha(self, rid: int, ratio: float = 0.5, atol: float = 1e-7) -> float:
+        out = C.c_double()
+        self._check(self.L.rdh_model_optimize_alpha(self.h, rid, ratio, atol, C.byref(out)))
+        return out.value
+
+    def optimize_root_location(self, min_roots: int = 1, root_ratio: float = 0.05):
+        rid, alpha, lh = C.c_uint(), C.c_double(), C.c_double()
+        self._check(self.L.rdh_model_optimize_root_location(self.h, min_roots, root_ratio, C.byref(rid),
+                                                            C.byref(alpha), C.byref(lh)))
+        return rid.value, alpha.value, lh.value
+
+    def sweep_root_lh(self) -> np.ndarray:
+        out = np.zeros(self.root_count)
+        self._check(self.L.rdh_model_sweep_root_lh(self.h, _ptr(out, _dp)))
+        return out
+
+    def compute_all_root_lh(self) -> np.ndarray:
+        out = np.zeros(self.root_count)
+        self._check(self.L.rdh_model_compute_all_root_lh(self.h, _ptr(out, _dp)))
+        return out
+
+    def search(self, min_roots=1, root_ratio=0.01, atol=1e-7, pgtol=1e-7, brtol=1e-12, factor=1e4,
+               strategy="modified_mad", rank=0, num_tasks=1):
+        rid, alpha, lh = C.c_uint(), C.c_double(), C.c_double()
+        self._check(self.L.rdh_model_search(self.h, min_roots, root_ratio, atol, pgtol, brtol, factor,
+                                            self.STRATEGY[strategy], rank, num_tasks, C.byref(rid), C.byref(alpha),
+                                            C.byref(lh)))
+        return rid.value, alpha.value, lh.value
+
+    def exhaustive_search(self, atol=1e-7, pgtol=1e-7, brtol=1e-12, factor=1e4, rank=0, num_tasks=1):
+        n = self.root_count
+        ids = np.zeros(n, dtype=np.uint32)
+        llh, alpha = np.zeros(n), np.zeros(n)
+        got = C.c_uint()
+        self._check(self.L.rdh_model_exhaustive_search(self.h, atol, pgtol, brtol, factor, rank, num_tasks,
+                                                       _ptr(ids, _up), _ptr(llh, _dp), _ptr(alpha, _dp), n,
+                                                       C.byref(got)))
+        k = got.value
+        return ids[:k].copy(), llh[:k].copy(), alpha[:k].copy()
+
+    def lwr(self, llh) -> np.ndarray:
+        llh = np.ascontiguousarray(llh, dtype=np.float64)
+        out = np.zeros(len(llh))
+        self.L.rdh_model_lwr(_ptr(llh, _dp), len(llh), _ptr(out, _dp))
+        return out
+
+    def newick(self, annotations: bool = True) -> str:
+        p = self.L.rdh_model_newick(self.h, 1 if annotations else 0)
+        if not p:
+            raise RuntimeError(self.L.rdh_last_error().decode())
+        s = C.string_at(p).decode()
+        self.L.rdh_free(p)
+        return s

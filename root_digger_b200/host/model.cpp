@@ -1,0 +1,1052 @@
+// model.cpp -- see model.hpp.  Every member cites the reference code it mirrors
+// (RootDigger src/model.cpp); quirks that change results are kept on purpose
+// (SURVEY.md Appendix B).
+#include "model.hpp"
+
+#include "lbfgsb_driver.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <limits>
+#include <numeric>
+#include <sstream>
+
+// src/model.cpp:87-93
+model_params_t random_params(size_t size, uint64_t seed) {
+  model_params_t                   mp(size);
+  std::minstd_rand                 engine(seed);
+  std::uniform_real_distribution<> dist(1e-4, 1.0);
+  for (auto &f : mp) f = dist(engine);
+  return mp;
+}
+
+static inline size_t compute_final_size(size_t vector_size, double ratio, size_t min) {
+  return std::max(static_cast<size_t>(vector_size * ratio), min);
+}
+
+static std::string engine_error() { return std::string(rdk_errmsg); }
+
+// ---------------------------------------------------------------------------
+// construction (src/model.cpp:99-182)
+// ---------------------------------------------------------------------------
+model_t::model_t(rooted_tree_t tree, const std::vector<msa_t> &msas,
+                 const std::vector<ratehet_opts_t> &rate_cats, bool invariant_sites, uint64_t seed,
+                 bool early_stop, const shard_spec_t &shard)
+    : _invariant_sites{invariant_sites}, _seed{seed}, _early_stop{early_stop} {
+  _random_engine = std::minstd_rand(_seed);
+  _tree = std::move(tree);
+  if (rate_cats.size() < msas.size())
+    throw std::invalid_argument("one rate heterogeneity option per partition is required");
+  for (auto rc : rate_cats) {
+    _rate_rates.emplace_back(rc.rate_cats, rc.alpha);
+    _rate_weights.emplace_back(rc.rate_cats, 1.0 / rc.rate_cats);
+    _rate_category_types.emplace_back(rc.rate_category_type);
+    _rate_user_init.emplace_back(rc.alpha_init);
+    _param_indicies.emplace_back(rc.rate_cats, 0);
+  }
+  for (auto &msa : msas)
+    if (!msa.constiency_check(_tree.label_set()))
+      throw std::invalid_argument("Taxa on the tree and in the MSA are inconsistient");
+
+  for (size_t pi = 0; pi < msas.size(); ++pi) {
+    auto &msa = msas[pi];
+    if (msa.length() > static_cast<size_t>(std::numeric_limits<int>::max()))
+      throw std::runtime_error("The length of the MSA is too large to safely cast");
+    // the ARCH_* attributes of the reference select coraxlib CPU kernels; the
+    // engine accepts and ignores them
+    unsigned int attributes = RDK_ATTRIB_SITE_REPEATS | RDK_ATTRIB_NONREV;
+    rdk_partition_t *p = rdk_partition_create(
+        _tree.tip_count(), _tree.branch_count(), msa.states(), msa.length(), _submodels,
+        _tree.branch_count(), static_cast<unsigned int>(_rate_rates[pi].size()), _tree.branch_count(),
+        attributes);
+    if (!p) throw std::runtime_error("partition could not be created: " + engine_error());
+    _partitions.push_back(p);
+#ifndef RD_BACKEND_ORACLE
+    if (shard.global_sites) {
+      if (msas.size() != 1) throw std::invalid_argument("site sharding supports a single MSA partition");
+      if (rdk_partition_set_shard(p, shard.site_offset, shard.global_sites) != RDK_SUCCESS)
+        throw std::runtime_error(engine_error());
+      if (shard.comm_id && shard.nranks > 1 &&
+          rdk_partition_attach_comm(p, shard.nranks, shard.rank, shard.comm_id) != RDK_SUCCESS)
+        throw std::runtime_error(engine_error());
+    }
+#else
+    (void)shard;
+#endif
+    _partition_weights.push_back(msa.total_weight());
+    set_gamma_rates(pi);
+  }
+  assign_indicies();
+}
+
+model_t::~model_t() {
+  for (auto p : _partitions)
+    if (p) rdk_partition_destroy(p);
+}
+
+// ---------------------------------------------------------------------------
+// parameter setters (src/model.cpp:184-355)
+// ---------------------------------------------------------------------------
+void model_t::set_subst_rates(size_t p, const model_params_t &mp) {
+  rdk_set_subst_params(_partitions[p], 0, mp.data());
+}
+
+void model_t::set_subst_rates_random(size_t p, const msa_t &msa) {
+  set_subst_rates(p, random_params(msa.states() * msa.states() - msa.states(), _random_engine()));
+}
+
+void model_t::set_gamma_weights(size_t p, model_params_t w) {
+  double sum = 0.0;
+  for (auto &f : w) sum += f;
+  for (auto &f : w) f /= sum;
+  rdk_set_category_weights(_partitions[p], w.data());
+}
+
+void model_t::set_gamma_rates(size_t p) {
+  rdk_set_category_weights(_partitions[p], _rate_weights[p].data());
+  switch (_rate_category_types[p]) {
+  case rate_category::MEAN: set_gamma_rates_mean(p); break;
+  case rate_category::MEDIAN: set_gamma_rates_median(p); break;
+  default: set_gamma_rates_free(p); break;
+  }
+}
+
+void model_t::set_gamma_rates(size_t p, const model_params_t &alpha) {
+  switch (_rate_category_types[p]) {
+  case rate_category::MEAN: set_gamma_rates_mean(p, alpha[0]); break;
+  case rate_category::MEDIAN: set_gamma_rates_median(p, alpha[0]); break;
+  default: set_gamma_rates_free(p, alpha); break;
+  }
+}
+
+// Appendix B-1: the no-argument variants use alpha = 1 in MEAN mode, the
+// variants taking alpha use MEDIAN mode, for both category types
+// (src/model.cpp:238-272)
+void model_t::set_gamma_rates_mean(size_t p) {
+  rdk_compute_gamma_cats(1.0, (unsigned)_rate_rates[p].size(), _rate_rates[p].data(),
+                         RDK_GAMMA_RATES_MEAN);
+  rdk_set_category_rates(_partitions[p], _rate_rates[p].data());
+}
+void model_t::set_gamma_rates_mean(size_t p, double alpha) {
+  rdk_compute_gamma_cats(alpha, (unsigned)_rate_rates[p].size(), _rate_rates[p].data(),
+                         RDK_GAMMA_RATES_MEDIAN);
+  rdk_set_category_rates(_partitions[p], _rate_rates[p].data());
+}
+void model_t::set_gamma_rates_median(size_t p) {
+  rdk_compute_gamma_cats(1.0, (unsigned)_rate_rates[p].size(), _rate_rates[p].data(),
+                         RDK_GAMMA_RATES_MEAN);
+  rdk_set_category_rates(_partitions[p], _rate_rates[p].data());
+}
+void model_t::set_gamma_rates_median(size_t p, double alpha) {
+  rdk_compute_gamma_cats(alpha, (unsigned)_rate_rates[p].size(), _rate_rates[p].data(),
+                         RDK_GAMMA_RATES_MEDIAN);
+  rdk_set_category_rates(_partitions[p], _rate_rates[p].data());
+}
+void model_t::set_gamma_rates_free(size_t p) {
+  for (auto &r : _rate_rates[p]) r = 1.0;
+  rdk_set_category_rates(_partitions[p], _rate_rates[p].data());
+}
+// Appendix B-2: the normalised copy is discarded, the stored rates are installed
+// (src/model.cpp:279-290)
+void model_t::set_gamma_rates_free(size_t p, model_params_t free_rates) {
+  double sum = 0.0;
+  for (size_t i = 0; i < free_rates.size(); ++i) sum += free_rates[i] * _rate_weights[p][i];
+  for (auto &f : free_rates) f /= sum;
+  rdk_set_category_rates(_partitions[p], _rate_rates[p].data());
+}
+
+void model_t::update_invariant_sites(size_t p) {
+  if (_invariant_sites) {
+    rdk_update_invariant_sites(_partitions[p]);
+  } else {
+    for (unsigned int i = 0; i < _submodels; ++i)
+      rdk_update_invariant_sites_proportion(_partitions[p], i, 0.0);
+  }
+}
+
+// src/model.cpp:302-325
+void model_t::set_tip_states(size_t p, const msa_t &msa) {
+  auto label_map = _tree.label_map();
+  for (int i = 0; i < msa.count(); ++i) {
+    auto it = label_map.find(msa.label(i));
+    if (it == label_map.end())
+      throw std::runtime_error(std::string("Could not find taxa ") + msa.label(i) + " in tree");
+    if (rdk_set_tip_states(_partitions[p], it->second, msa.map(), msa.sequence(i)) == RDK_FAILURE)
+      throw std::runtime_error("failed to set tip " + std::to_string(i) + ": " + engine_error());
+  }
+  rdk_set_pattern_weights(_partitions[p], msa.weights());
+}
+
+// src/model.cpp:327-339
+void model_t::set_empirical_freqs(size_t p) {
+  rdk_partition_t *partition = _partitions[p];
+  double          *emp = rdk_msa_empirical_frequencies(partition);
+  if (!emp) throw std::runtime_error("empirical frequencies failed: " + engine_error());
+  for (size_t i = 0; i < partition->states; ++i) {
+    if (emp[i] <= 0) {
+      free(emp);
+      throw invalid_empirical_frequencies_exception(
+          "One of the state frequenices is zero while using emperical frequencies");
+    }
+  }
+  rdk_set_frequencies(partition, 0, emp);
+  free(emp);
+}
+
+void model_t::set_empirical_freqs() {
+  for (size_t i = 0; i < _partitions.size(); ++i) set_empirical_freqs(i);
+}
+
+void model_t::set_freqs(size_t p, const model_params_t &freqs) {
+  for (auto f : freqs)
+    if (f <= 0.0) throw std::runtime_error("Frequencies with 0 entries are not allowed");
+  rdk_set_frequencies(_partitions[p], 0, freqs.data());
+}
+
+// Appendix B-4 (src/model.cpp:350-355)
+void model_t::set_freqs_all_free(size_t p, model_params_t freqs) {
+  double sum = 0.0;
+  for (auto v : freqs) sum += v;
+  for (auto &f : freqs) f /= sum;
+  set_freqs(p, freqs);
+}
+
+void model_t::set_subst_rates_uniform() {
+  for (size_t i = 0; i < _partitions.size(); ++i) {
+    unsigned int   states = _partitions[i]->states;
+    unsigned int   params = states * states - states;
+    model_params_t mp(params, 1.0 / params);
+    set_subst_rates(i, mp);
+  }
+}
+
+void model_t::set_model_params(const std::vector<partition_parameters_t> &params) {
+  for (size_t i = 0; i < params.size(); ++i) {
+    set_subst_rates(i, params[i].subst_rates);
+    set_freqs(i, params[i].freqs);
+    set_gamma_rates(i, params[i].gamma_alpha);
+    if (_rate_category_types[i] == rate_category::FREE) set_gamma_weights(i, params[i].gamma_weights);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// likelihood facade
+// ---------------------------------------------------------------------------
+// src/model.cpp:357-370: the reference issues one corax_update_prob_matrices
+// call per branch from an OpenMP loop; one call with all branches is the same
+// thing for the engine (it batches them into a single kernel anyway)
+void model_t::update_pmatrix_partition(size_t pi, const std::vector<unsigned int> &pmatrix_indices,
+                                       const std::vector<double> &branch_lengths) {
+  if (pmatrix_indices.empty()) return;
+  int rc = rdk_update_prob_matrices(_partitions[pi], _param_indicies[pi].data(), pmatrix_indices.data(),
+                                    branch_lengths.data(), (unsigned)pmatrix_indices.size());
+  if (rc == RDK_FAILURE) throw std::runtime_error(engine_error());
+}
+
+// src/model.cpp:372-382 (Appendix B-3: always "updated")
+std::vector<bool> model_t::update_pmatrices(const std::vector<unsigned int> &pmatrix_indices,
+                                            const std::vector<double>       &branch_lengths) {
+  std::vector<bool> updated(_partitions.size(), true);
+  for (size_t i = 0; i < _partitions.size(); ++i)
+    update_pmatrix_partition(i, pmatrix_indices, branch_lengths);
+  return updated;
+}
+
+// src/model.cpp:384-413
+double model_t::compute_lh(const root_location_t &root_location) {
+  std::vector<rdk_operation_t> ops;
+  std::vector<unsigned int>    pmatrix_indices;
+  std::vector<double>          branch_lengths;
+  bool new_root = root_location != _tree.root_location();
+  GENERATE_AND_UNPACK_OPS(_tree, root_location, ops, pmatrix_indices, branch_lengths);
+  auto   updated = update_pmatrices(pmatrix_indices, branch_lengths);
+  double lh = 0.0;
+#pragma omp parallel for reduction(+ : lh)
+  for (size_t i = 0; i < _partitions.size(); ++i) {
+    if (new_root || updated[i]) rdk_update_clvs(_partitions[i], ops.data(), (unsigned)ops.size());
+    lh += rdk_compute_root_loglikelihood(_partitions[i], _tree.root_clv_index(),
+                                         _tree.root_scaler_index(), _param_indicies[i].data(), nullptr);
+  }
+  return lh;
+}
+
+// src/model.cpp:415-452
+double model_t::compute_lh_root(const root_location_t &root) {
+  auto                      result = _tree.generate_derivative_operations(root);
+  rdk_operation_t           op = std::get<0>(result);
+  std::vector<unsigned int> matrix_indices = std::move(std::get<1>(result));
+  std::vector<double>       branch_lengths = std::move(std::get<2>(result));
+  double                    lh = 0.0;
+  bool                      failed = false;
+#pragma omp parallel for reduction(+ : lh)
+  for (size_t i = 0; i < _partitions.size(); ++i) {
+    int rc = rdk_update_prob_matrices(_partitions[i], _param_indicies[i].data(), matrix_indices.data(),
+                                      branch_lengths.data(), (unsigned)matrix_indices.size());
+    if (rc == RDK_FAILURE) {
+      failed = true;
+      continue;
+    }
+    rdk_update_clvs(_partitions[i], &op, 1);
+    lh += rdk_compute_root_loglikelihood(_partitions[i], _tree.root_clv_index(),
+                                         _tree.root_scaler_index(), _param_indicies[i].data(), nullptr);
+  }
+  if (failed) throw std::runtime_error(engine_error());
+  if (std::isnan(lh)) throw std::runtime_error("lh at root is not a number: " + std::to_string(lh));
+  return lh;
+}
+
+// src/model.cpp:454-476
+double model_t::compute_lh_partition(size_t pi, const std::vector<rdk_operation_t> &ops,
+                                     const std::vector<unsigned int> &pmatrix_indices,
+                                     const std::vector<double>       &branch_lengths) {
+  update_pmatrix_partition(pi, pmatrix_indices, branch_lengths);
+  rdk_update_clvs(_partitions[pi], ops.data(), (unsigned)ops.size());
+  double lh = rdk_compute_root_loglikelihood(_partitions[pi], _tree.root_clv_index(),
+                                             _tree.root_scaler_index(), _param_indicies[pi].data(),
+                                             nullptr);
+  if (std::isnan(lh)) throw std::runtime_error("lh at root is not a number: " + std::to_string(lh));
+  return lh;
+}
+
+// src/model.cpp:481-519: forward difference with h = 1e-8 in the branch ratio,
+// taken backwards at the upper end (Appendix B-15)
+dlh_t model_t::compute_dlh(const root_location_t &root) {
+  constexpr double EPSILON = 1e-8;
+  root_location_t  root_prime{root};
+  root_prime.brlen_ratio += EPSILON;
+  double sign = 1.0;
+  if (root_prime.brlen_ratio >= 1.0) {
+    root_prime.brlen_ratio = root.brlen_ratio - EPSILON;
+    sign = -1.0;
+  }
+  dlh_t  ret;
+  double fx = compute_lh_root(root);
+  ret.lh = fx;
+  if (std::isnan(fx))
+    throw std::runtime_error("fx is not finite when computing derivative: " +
+                             std::to_string(root.edge->length));
+  double fxh = compute_lh_root(root_prime);
+  if (std::isnan(fxh))
+    throw std::runtime_error("fxh is not finite when computing derivative: " +
+                             std::to_string(root_prime.edge->length));
+  if (std::isinf(fxh) && std::isinf(fx)) return {fx, 0};
+  double dlh = (fxh - fx) / EPSILON;
+  ret.dlh = dlh * sign;
+  return ret;
+}
+
+// src/model.cpp:606-676
+std::pair<root_location_t, double> model_t::brents(root_location_t beg, dlh_t d_beg, root_location_t end,
+                                                   dlh_t d_end, double atol) {
+  if (!(d_beg.dlh * d_end.dlh < 0))
+    throw std::runtime_error("Brents called with endpoints which don't bracket");
+  root_location_t midpoint{end};
+  auto            d_midpoint = d_end;
+  double          e, d;
+  d = e = end.brlen_ratio - beg.brlen_ratio;
+
+  for (size_t i = 0; i < 64; ++i) {
+    if (d_end.dlh * d_midpoint.dlh > 0.0) {
+      midpoint = beg;
+      d_midpoint = d_beg;
+      d = e = end.brlen_ratio - beg.brlen_ratio;
+    }
+    if (fabs(d_end.dlh) < fabs(d_midpoint.dlh)) {
+      beg = end;
+      end = midpoint;
+      midpoint = beg;
+      d_beg = d_end;
+      d_end = d_midpoint;
+      d_midpoint = d_beg;
+    }
+    double tol = 2.0 * fabs(end.brlen_ratio) * std::numeric_limits<double>::epsilon() + 0.5 * atol;
+    double e_tol = 0.5 * (midpoint.brlen_ratio - end.brlen_ratio);
+    if (fabs(e_tol) <= tol || fabs(d_end.dlh) <= 1e-12) return {end, d_end.lh};
+    if (fabs(e) >= tol && fabs(d_beg.dlh) > fabs(d_end.dlh)) {
+      double s = d_end.dlh / d_beg.dlh;
+      double p, q;
+      if (fabs(beg.brlen_ratio - midpoint.brlen_ratio) < 1e-12) {
+        p = 2.0 * e_tol * s;
+        q = 1.0 - s;
+      } else {
+        q = d_beg.dlh / d_midpoint.dlh;
+        double r = d_end.dlh / d_midpoint.dlh;
+        p = s * (2.0 * e_tol * q * (q - r) - (end.brlen_ratio - beg.brlen_ratio) * (r - 1.0));
+        q = (q - 1.0) * (r - 1.0) * (s - 1.0);
+      }
+      if (p > 0.0) q = -q;
+      p = fabs(p);
+      double min1 = 3.0 * e_tol * q - fabs(e_tol * q);
+      double min2 = fabs(e * q);
+      if (2.0 * p < (min1 < min2 ? min1 : min2)) {
+        e = d;
+        d = p / q;
+      } else {
+        d = e_tol;
+        e = d;
+      }
+    } else {
+      d = e_tol;
+      e = d;
+    }
+    beg = end;
+    d_beg = d_end;
+    if (fabs(d) > tol)
+      end.brlen_ratio += d;
+    else
+      end.brlen_ratio += e_tol >= 0.0 ? tol : -tol;
+    d_end = compute_dlh(end);
+  }
+  throw std::runtime_error("Brents method failed to converge");
+}
+
+// src/model.cpp:679-794
+root_location_t model_t::optimize_alpha(const root_location_t &root, double atol) {
+  double lh = compute_lh_root(root);
+  if (std::isnan(lh)) throw std::runtime_error("initial likelihood calculation is not finite");
+  root_location_t beg{root};
+  beg.brlen_ratio = 0.0;
+  root_location_t end{root};
+  end.brlen_ratio = 1.0;
+  auto d_beg = compute_dlh(beg);
+  auto d_end = compute_dlh(end);
+  if (std::isnan(d_beg.dlh) || std::isnan(d_end.dlh))
+    throw std::runtime_error("Initial derivatives failed when optimizing alpha: " +
+                             std::to_string(root.edge->length));
+
+  root_location_t best_endpoint = d_beg.lh >= d_end.lh ? beg : end;
+  auto            lh_best_endpoint = d_beg.lh >= d_end.lh ? d_beg : d_end;
+
+  if (fabs(d_beg.dlh) < atol || fabs(d_end.dlh) < atol) return best_endpoint;
+
+  if ((d_beg.dlh < 0.0 && d_end.dlh > 0.0) || (d_beg.dlh > 0.0 && d_end.dlh < 0.0)) {
+    auto mid = brents(beg, d_beg, end, d_end, atol);
+    return lh_best_endpoint.lh > mid.second ? best_endpoint : mid.first;
+  }
+
+  // same sign at both ends: dyadic grid search for a sign change
+  bool            beg_end_pos = d_beg.dlh > 0.0 && d_end.dlh > 0.0;
+  dlh_t           best_midpoint_lh = {-std::numeric_limits<double>::infinity(), 0};
+  root_location_t best_midpoint;
+  bool            found_midpoint = false;
+
+  for (size_t midpoints = 2; midpoints <= 32; midpoints *= 2) {
+    for (size_t midpoint = 1; midpoint <= midpoints; ++midpoint) {
+      if (midpoint % 2 == 0) continue;
+      double          alpha = 1.0 / (double)midpoints * midpoint;
+      root_location_t midpoint_root{beg};
+      midpoint_root.brlen_ratio = alpha;
+      auto d_midpoint = compute_dlh(midpoint_root);
+      if (fabs(d_midpoint.dlh) < atol) {
+        if (best_midpoint_lh.lh < d_midpoint.lh) {
+          best_midpoint_lh = d_midpoint;
+          best_midpoint = midpoint_root;
+          found_midpoint = true;
+        }
+      }
+      if ((beg_end_pos && d_midpoint.dlh < 0.0) || (!beg_end_pos && d_midpoint.dlh > 0.0)) {
+        auto r1 = brents(beg, d_beg, midpoint_root, d_midpoint, atol);
+        auto r2 = brents(midpoint_root, d_midpoint, end, d_end, atol);
+        if (lh_best_endpoint.lh < best_midpoint_lh.lh) {
+          lh_best_endpoint = best_midpoint_lh;
+          best_endpoint = best_midpoint;
+        }
+        if (r1.second < r2.second) return lh_best_endpoint.lh >= r2.second ? best_endpoint : r2.first;
+        return lh_best_endpoint.lh >= r1.second ? best_endpoint : r1.first;
+      }
+    }
+  }
+  if (found_midpoint) return best_midpoint;
+  return beg_end_pos ? end : beg;
+}
+
+// src/model.cpp:796-821 (Appendix B-6: atol of the ratio search is hard-coded)
+std::pair<root_location_t, double> model_t::optimize_root_location(size_t min_roots, double root_ratio) {
+  std::pair<root_location_t, double> best;
+  best.second = -std::numeric_limits<double>::infinity();
+  auto sorted_roots = suggest_roots_lh(min_roots, root_ratio);
+  for (auto &rl : sorted_roots) {
+    move_root(rl);
+    rl = optimize_alpha(rl, 1e-14);
+    double rl_lh = compute_lh_root(rl);
+    if (rl_lh > best.second) {
+      best.first = rl;
+      best.second = rl_lh;
+    }
+  }
+  return best;
+}
+
+// src/model.cpp:823-854
+void model_t::move_root(const root_location_t &new_root) {
+  auto                         results = _tree.generate_root_update_operations(new_root);
+  std::vector<rdk_operation_t> ops = std::move(std::get<0>(results));
+  std::vector<unsigned int>    pmatrix_indices = std::move(std::get<1>(results));
+  std::vector<double>          branch_lengths = std::move(std::get<2>(results));
+  for (size_t i = 0; i < _partitions.size(); ++i) {
+    int rc = rdk_update_prob_matrices(_partitions[i], _param_indicies[i].data(), pmatrix_indices.data(),
+                                      branch_lengths.data(), (unsigned)pmatrix_indices.size());
+    if (rc == RDK_FAILURE) throw std::runtime_error(engine_error());
+    rdk_update_clvs(_partitions[i], ops.data(), (unsigned)ops.size());
+  }
+}
+
+std::vector<root_location_t> model_t::suggest_roots_random(size_t min, double ratio) {
+  auto roots = _tree.roots();
+  std::shuffle(roots.begin(), roots.end(), _random_engine);
+  roots.resize(compute_final_size(roots.size(), ratio, min));
+  return roots;
+}
+
+// log-likelihood of every root placement at its stored ratio, in root-id order:
+// what the loop at src/model.cpp:871-874 computes (move_root + compute_lh_root
+// per root).  With the fused path the whole sweep is ONE engine call.
+std::vector<double> model_t::sweep_root_lh() {
+  const auto         &roots = _tree.roots();
+  std::vector<double> lh(roots.size(), 0.0);
+  if (!_fused) {
+    for (size_t r = 0; r < roots.size(); ++r) {
+      move_root(roots[r]);
+      lh[r] = compute_lh_root(roots[r]);
+    }
+    return lh;
+  }
+  std::vector<unsigned int>    pm_off{0}, op_off{0}, mi;
+  std::vector<double>          bl;
+  std::vector<rdk_operation_t> ops;
+  for (const auto &rl : roots) {
+    auto mv = _tree.generate_root_update_operations(rl);
+    mi.insert(mi.end(), std::get<1>(mv).begin(), std::get<1>(mv).end());
+    bl.insert(bl.end(), std::get<2>(mv).begin(), std::get<2>(mv).end());
+    ops.insert(ops.end(), std::get<0>(mv).begin(), std::get<0>(mv).end());
+    auto dv = _tree.generate_derivative_operations(rl);
+    mi.insert(mi.end(), std::get<1>(dv).begin(), std::get<1>(dv).end());
+    bl.insert(bl.end(), std::get<2>(dv).begin(), std::get<2>(dv).end());
+    ops.push_back(std::get<0>(dv));
+    pm_off.push_back((unsigned)mi.size());
+    op_off.push_back((unsigned)ops.size());
+  }
+  std::vector<double> part(roots.size());
+  for (size_t i = 0; i < _partitions.size(); ++i) {
+    int rc = rdk_sweep_root_placements(_partitions[i], (unsigned)roots.size(), _param_indicies[i].data(),
+                                       _param_indicies[i].data(), pm_off.data(), mi.data(), bl.data(),
+                                       op_off.data(), ops.data(), _tree.root_clv_index(),
+                                       _tree.root_scaler_index(), part.data());
+    if (rc == RDK_FAILURE) throw std::runtime_error(engine_error());
+    for (size_t r = 0; r < roots.size(); ++r) lh[r] += part[r];
+  }
+  for (double v : lh)
+    if (std::isnan(v)) throw std::runtime_error("lh at root is not a number: " + std::to_string(v));
+  return lh;
+}
+
+// src/model.cpp:865-889
+std::vector<root_location_t> model_t::suggest_roots_lh(size_t min, double ratio) {
+  std::vector<std::pair<root_location_t, double>> rl_lhs;
+  auto                                            lh = sweep_root_lh();
+  const auto                                     &roots = _tree.roots();
+  rl_lhs.reserve(roots.size());
+  for (size_t r = 0; r < roots.size(); ++r) rl_lhs.push_back(std::make_pair(roots[r], lh[r]));
+  auto final_size = std::min(compute_final_size(rl_lhs.size(), ratio, min), rl_lhs.size());
+  std::partial_sort(rl_lhs.begin(), rl_lhs.begin() + (std::ptrdiff_t)final_size, rl_lhs.end(),
+                    [](const std::pair<root_location_t, double> &a,
+                       const std::pair<root_location_t, double> &b) { return a.second > b.second; });
+  rl_lhs.resize(final_size);
+  std::vector<root_location_t> ret;
+  ret.reserve(final_size);
+  for (size_t i = 0; i < final_size; i++) ret.push_back(rl_lhs[i].first);
+  return ret;
+}
+
+std::vector<root_location_t> model_t::suggest_roots_midpoint(size_t min, double ratio) {
+  auto midpoints = _tree.rank_midpoints();
+  midpoints.resize(std::min(compute_final_size(midpoints.size(), ratio, min), midpoints.size()));
+  return midpoints;
+}
+
+std::vector<root_location_t> model_t::suggest_roots_modified_mad(size_t min, double ratio) {
+  auto madpoints = _tree.rank_modified_mad();
+  madpoints.resize(std::min(compute_final_size(madpoints.size(), ratio, min), madpoints.size()));
+  return madpoints;
+}
+
+std::vector<size_t> model_t::shuffle_root_indicies() {
+  std::vector<size_t> idx(_tree.root_count());
+  std::iota(idx.begin(), idx.end(), 0);
+  std::shuffle(idx.begin(), idx.end(), _random_engine);
+  return idx;
+}
+
+std::vector<size_t> model_t::suggest_root_indicies_midpoint() {
+  std::vector<size_t> ret;
+  for (auto &rl : suggest_roots_midpoint(1, 1.0)) ret.push_back(rl.id);
+  return ret;
+}
+
+std::vector<size_t> model_t::suggest_root_indicies_modified_mad() {
+  std::vector<size_t> ret;
+  for (auto &rl : suggest_roots_modified_mad(1, 1.0)) ret.push_back(rl.id);
+  return ret;
+}
+
+// src/model.cpp:979-1005
+partition_parameters_t model_t::make_partition_parameters(size_t states, rate_category rc,
+                                                          size_t rate_cat_count) {
+  partition_parameters_t pp;
+  size_t                 subst_size = states * states - states;
+  pp.subst_rates.assign(subst_size, 1.0 / subst_size);
+  pp.freqs.assign(states, 1.0 / states);
+  switch (rc) {
+  case rate_category::MEAN:
+  case rate_category::MEDIAN:
+    pp.gamma_alpha.assign(1, 1.0);
+    break;
+  case rate_category::FREE: {
+    pp.gamma_alpha.assign(rate_cat_count, 1.0);
+    pp.gamma_weights.resize(rate_cat_count);
+    std::uniform_real_distribution<> dis(0.0, 1.0);
+    for (auto &v : pp.gamma_weights) v = dis(_random_engine);
+  }
+  }
+  return pp;
+}
+
+// ---------------------------------------------------------------------------
+// search drivers
+// ---------------------------------------------------------------------------
+// src/model.cpp:1008-1137
+std::pair<root_location_t, double> model_t::search(size_t min_roots, double root_ratio, double atol,
+                                                   double pgtol, double brtol, double factor,
+                                                   checkpoint_t &checkpoint) {
+  double          best_llh = -std::numeric_limits<double>::infinity();
+  root_location_t best_rl;
+  set_subst_rates_uniform();
+  set_empirical_freqs();
+
+  for (auto rl_index : _assigned_idx) {
+    auto rl = _tree.root_location(rl_index);
+    set_subst_rates_uniform();  // Appendix B-9
+    set_empirical_freqs();
+
+    std::vector<partition_parameters_t> params, saved_params;
+    for (size_t p = 0; p < _partitions.size(); ++p)
+      params.push_back(make_partition_parameters(_partitions[p]->states, _rate_category_types[p],
+                                                 _partitions[p]->rate_cats));
+    auto   cur_best_rl = rl;
+    double cur_best_lh = -std::numeric_limits<double>::infinity();
+
+    for (size_t iter = 0; iter < 1e3; ++iter) {
+      saved_params = params;
+      optimize_params(params, rl, pgtol, factor, true);
+      auto cur = optimize_root_location(min_roots, root_ratio);
+
+      if (cur.second < cur_best_lh) {
+        // no progress: restore the parameters of the previous iteration
+        for (size_t i = 0; i < _partitions.size(); ++i) {
+          set_subst_rates(i, saved_params[i].subst_rates);
+          set_freqs(i, saved_params[i].freqs);
+          set_gamma_rates(i, saved_params[i].gamma_alpha);
+          if (_rate_category_types[i] == rate_category::FREE)
+            set_gamma_weights(i, saved_params[i].gamma_weights);
+        }
+        params = saved_params;
+        break;
+      }
+      if (_early_stop) {
+        if (rl.edge == cur.first.edge && fabs(rl.brlen_ratio - cur.first.brlen_ratio) < brtol) {
+          cur_best_rl = cur.first;
+          cur_best_lh = cur.second;
+          break;
+        }
+      }
+      if (fabs(cur.second - cur_best_lh) < atol) {
+        cur_best_rl = cur.first;
+        cur_best_lh = cur.second;
+        break;
+      }
+      cur_best_rl = cur.first;
+      cur_best_lh = cur.second;
+      rl = cur_best_rl;
+    }
+    checkpoint.write({cur_best_rl.id, cur_best_lh, cur_best_rl.brlen_ratio}, params);
+  }
+
+  // what rank 0 does after the barrier (src/model.cpp:1119-1133)
+  auto total = checkpoint.read_results();
+  if (!total.empty()) {
+    auto best = *std::max_element(total.begin(), total.end(),
+                                  [](const checkpoint_t::record_t &a, const checkpoint_t::record_t &b) {
+                                    return a.first.llh < b.first.llh;
+                                  });
+    best_rl = _tree.root_location(best.first.root_id);
+    best_rl.brlen_ratio = best.first.alpha;
+    best_llh = best.first.llh;
+    set_model_params(best.second);
+  }
+  if (!_assigned_idx.empty()) move_root(best_rl);
+  return {best_rl, best_llh};
+}
+
+// src/model.cpp:1139-1272
+std::pair<root_location_t, double> model_t::exhaustive_search(double atol, double pgtol, double brtol,
+                                                              double factor, checkpoint_t &checkpoint) {
+  root_location_t best_rl;
+  double          best_llh = -std::numeric_limits<double>::infinity();
+
+  for (auto rl_index : _assigned_idx) {
+    auto rl = _tree.root_location(rl_index);
+    set_subst_rates_uniform();
+    set_empirical_freqs();
+    _tree.root_by(rl);
+    compute_lh(rl);
+    std::vector<partition_parameters_t> params;
+    for (size_t p = 0; p < _partitions.size(); ++p)
+      params.push_back(make_partition_parameters(_partitions[p]->states, _rate_category_types[p],
+                                                 _partitions[p]->rate_cats));
+    root_location_t cur_best_rl = rl;
+    double          cur_best_llh = -std::numeric_limits<double>::infinity();
+
+    for (size_t iter = 0; iter < 1e3; ++iter) {
+      optimize_params(params, rl, pgtol, factor, (iter % 10 == 0));  // Appendix B-7
+      if (fabs(compute_lh(rl) - cur_best_llh) < atol) break;
+      auto   cur_rl = optimize_alpha(rl, brtol);
+      double cur_llh = compute_lh_root(cur_rl);
+      if (_early_stop) {
+        if (fabs(rl.brlen_ratio - cur_rl.brlen_ratio) < brtol) {
+          cur_best_rl = cur_rl;
+          cur_best_llh = cur_llh;
+          break;
+        }
+      }
+      if ((cur_llh - cur_best_llh) < atol) {
+        if (cur_llh > cur_best_llh) {
+          cur_best_rl = cur_rl;
+          cur_best_llh = cur_llh;
+        }
+        break;
+      }
+      if (cur_llh > cur_best_llh) {
+        cur_best_rl = cur_rl;
+        cur_best_llh = cur_llh;
+      }
+      rl = cur_rl;
+    }
+    checkpoint.write({cur_best_rl.id, cur_best_llh, cur_best_rl.brlen_ratio}, params);
+    if (cur_best_llh > best_llh) {
+      best_rl = cur_best_rl;
+      best_llh = cur_best_llh;
+    }
+  }
+
+  // LWR annotation (src/model.cpp:1237-1269)
+  auto total = checkpoint.read_results();
+  if (!total.empty()) {
+    std::vector<double> llh;
+    for (auto &r : total) llh.push_back(r.first.llh);
+    auto w = lwr(llh);
+    for (size_t i = 0; i < total.size(); ++i) {
+      auto rl = _tree.root_location(total[i].first.root_id);
+      rl.brlen_ratio = total[i].first.alpha;
+      _tree.annotate_branch(rl, "LWR", std::to_string(w[i]));
+      _tree.annotate_lh(rl, total[i].first.llh);
+      _tree.annotate_ratio(rl, total[i].first.alpha);
+    }
+    auto best = *std::max_element(total.begin(), total.end(),
+                                  [](const checkpoint_t::record_t &a, const checkpoint_t::record_t &b) {
+                                    return a.first.llh < b.first.llh;
+                                  });
+    best_rl = _tree.root_location(best.first.root_id);
+    best_rl.brlen_ratio = best.first.alpha;
+    best_llh = best.first.llh;
+  }
+  return {best_rl, best_llh};
+}
+
+// LWR_i = exp(llh_i - max) / sum_j exp(llh_j - max) (src/model.cpp:1238-1253)
+std::vector<double> model_t::lwr(const std::vector<double> &llh) {
+  double max_llh = -std::numeric_limits<double>::infinity();
+  for (double v : llh) max_llh = std::max(v, max_llh);
+  double total = 0;
+  for (double v : llh) total += exp(v - max_llh);
+  std::vector<double> out;
+  for (double v : llh) out.push_back(exp(v - max_llh) / total);
+  return out;
+}
+
+void model_t::initialize() { compute_lh(_tree.root_location(0)); }
+void model_t::finalize() { _tree.unroot(); }
+
+rooted_tree_t model_t::rooted_tree(const root_location_t &root) const {
+  rooted_tree_t t(_tree);
+  t.root_by((unsigned)root.id);
+  return t;
+}
+rooted_tree_t model_t::virtual_rooted_tree(const root_location_t &root) const {
+  rooted_tree_t t(_tree);
+  t.root_by((unsigned)root.id);
+  t.unroot();
+  return t;
+}
+rooted_tree_t model_t::unrooted_tree() const {
+  rooted_tree_t t(_tree);
+  t.unroot();
+  return t;
+}
+
+// src/model.cpp:1297-1321
+void model_t::initialize_partitions(const std::vector<msa_t> &msa) {
+  for (size_t p = 0; p < _partitions.size(); ++p) {
+    set_tip_states(p, msa[p]);
+    update_invariant_sites(p);
+    set_empirical_freqs(p);
+    set_subst_rates_random(p, msa[p]);  // Appendix B-10
+  }
+}
+
+void model_t::initialize_partitions_uniform_freqs(const std::vector<msa_t> &msa) {
+  for (size_t p = 0; p < _partitions.size(); ++p) {
+    set_tip_states(p, msa[p]);
+    update_invariant_sites(p);
+    std::vector<double> uni(_partitions[p]->states, 1.0 / (double)_partitions[p]->states);
+    set_freqs(p, uni);
+    set_subst_rates_random(p, msa[p]);
+    set_gamma_rates(p);
+  }
+}
+
+std::string model_t::subst_string() const {
+  std::ostringstream oss;
+  oss << "{";
+  for (size_t p = 0; p < _partitions.size(); ++p) {
+    auto   part = _partitions[p];
+    size_t n = part->states * part->states - part->states;
+    oss << "{";
+    for (size_t i = 0; i < n; ++i) {
+      oss << std::to_string(part->subst_params[0][i]);
+      if (i != n - 1) oss << ",";
+    }
+    oss << "}";
+    if (p != _partitions.size() - 1) oss << ",";
+  }
+  oss << "}";
+  return oss.str();
+}
+
+// ---------------------------------------------------------------------------
+// L-BFGS-B parameter optimisation (src/model.cpp:1430-1522; Appendix B-8,B-14)
+// ---------------------------------------------------------------------------
+static double bfgs_params(model_params_t &initial_params, size_t partition_index, double p_min,
+                          double p_max, double epsilon, double pgtol, double factor,
+                          std::function<double()>                             compute_lh,
+                          std::function<void(size_t, const model_params_t &)> set_func) {
+  rd::setulb_fn setulb = rd::load_setulb();
+  int           task = rd::LBFGSB_START;
+  int           n_params = static_cast<int>(initial_params.size());
+  set_func(partition_index, initial_params);
+  double              score = compute_lh();
+  double              initial_score = score;
+  int                 csave = 0;
+  std::vector<double> gradient(static_cast<size_t>(n_params), 0.0);
+  int                 max_corrections = 20;
+  std::vector<double> wa((2 * (size_t)max_corrections + 5) * static_cast<size_t>(n_params) +
+                             12 * (size_t)max_corrections * ((size_t)max_corrections + 1),
+                         0.0);
+  std::vector<int>    iwa(3 * static_cast<size_t>(n_params), 0);
+  std::vector<double> parameters(initial_params);
+  std::vector<double> param_min(static_cast<size_t>(n_params), p_min);
+  std::vector<double> param_max(static_cast<size_t>(n_params), p_max);
+  int                 lsave[4] = {0, 0, 0, 0};
+  int                 isave[44] = {0};
+  double              dsave[29] = {0};
+  std::vector<int>    bound_type(static_cast<size_t>(n_params), 2);
+  int                 iprint = -1;
+  size_t              iters = 0;
+
+  while (iters < 500) {
+    setulb(&n_params, &max_corrections, parameters.data(), param_min.data(), param_max.data(),
+           bound_type.data(), &score, gradient.data(), &factor, &pgtol, wa.data(), iwa.data(), &task,
+           &iprint, &csave, lsave, isave, dsave);
+    // f is evaluated after every return, whatever the task (Appendix B-8)
+    set_func(partition_index, parameters);
+    score = compute_lh();
+    if (rd::lbfgsb_is_fg(task)) {
+      for (size_t i = 0; i < static_cast<size_t>(n_params); ++i) {
+        double h = epsilon * fabs(parameters[i]);
+        if (h < epsilon) h = epsilon;
+        double temp = parameters[i];
+        parameters[i] += h;
+        set_func(partition_index, parameters);
+        double dlh = compute_lh();
+        if (!std::isfinite(dlh)) throw std::runtime_error("dlh is not finite");
+        gradient[i] = (dlh - score) / h;
+        if (!std::isfinite(gradient[i])) throw std::runtime_error("gradient is not finite");
+        parameters[i] = temp;
+      }
+    } else if (task != rd::LBFGSB_NEW_X) {
+      break;
+    }
+    iters++;
+  }
+  set_func(partition_index, parameters);
+  score = compute_lh();
+  // accepted only if not worse; the partition keeps the last tried values either
+  // way (Appendix B-14)
+  if (initial_score >= score) std::swap(parameters, initial_params);
+  return score;
+}
+
+double model_t::bfgs_rates(model_params_t &initial_rates, const std::vector<rdk_operation_t> &ops,
+                           const std::vector<unsigned int> &pmatrix_indices,
+                           const std::vector<double> &branch_lengths, size_t pi, double pgtol,
+                           double factor) {
+  return bfgs_params(
+      initial_rates, pi, 1e-4, 1e4, 1e-4, pgtol, factor,
+      [&, this]() -> double { return -this->compute_lh_partition(pi, ops, pmatrix_indices, branch_lengths); },
+      [&, this](size_t p, const model_params_t &mp) { this->set_subst_rates(p, mp); });
+}
+
+double model_t::bfgs_freqs(model_params_t &initial_freqs, const std::vector<rdk_operation_t> &ops,
+                           const std::vector<unsigned int> &pmatrix_indices,
+                           const std::vector<double> &branch_lengths, size_t pi, double pgtol,
+                           double factor) {
+  return bfgs_params(
+      initial_freqs, pi, 1e-4, 1.0 - 1e-4 * 3, 1e-4, pgtol, factor,
+      [&, this]() -> double { return -this->compute_lh_partition(pi, ops, pmatrix_indices, branch_lengths); },
+      [&, this](size_t p, const model_params_t &mp) { this->set_freqs_all_free(p, mp); });
+}
+
+double model_t::bfgs_gamma_rates(model_params_t &alpha, const std::vector<rdk_operation_t> &ops,
+                                 const std::vector<unsigned int> &pmatrix_indices,
+                                 const std::vector<double> &branch_lengths, size_t pi, double pgtol,
+                                 double factor) {
+  return bfgs_params(
+      alpha, pi, 0.2, 10000.0, 1e-4, pgtol, factor,
+      [&, this]() -> double { return -this->compute_lh_partition(pi, ops, pmatrix_indices, branch_lengths); },
+      [&, this](size_t p, const model_params_t &mp) { this->set_gamma_rates(p, mp); });
+}
+
+double model_t::bfgs_gamma_weights(model_params_t &w, const std::vector<rdk_operation_t> &ops,
+                                   const std::vector<unsigned int> &pmatrix_indices,
+                                   const std::vector<double> &branch_lengths, size_t pi, double pgtol,
+                                   double factor) {
+  return bfgs_params(
+      w, pi, 1e-4, 1.0, 1e-4, pgtol, factor,
+      [&, this]() -> double { return -this->compute_lh_partition(pi, ops, pmatrix_indices, branch_lengths); },
+      [&, this](size_t p, const model_params_t &mp) { this->set_gamma_weights(p, mp); });
+}
+
+// src/model.cpp:1925-1984
+void model_t::optimize_params(std::vector<partition_parameters_t> &params, const root_location_t &rl,
+                              double pgtol, double factor, bool optimize_gamma) {
+  std::vector<rdk_operation_t> ops;
+  std::vector<unsigned int>    pmatrix_indices;
+  std::vector<double>          branch_lengths;
+  GENERATE_AND_UNPACK_OPS(_tree, rl, ops, pmatrix_indices, branch_lengths);
+#pragma omp parallel for schedule(dynamic)
+  for (size_t i = 0; i < _partitions.size(); ++i) {
+    set_subst_rates(i, params[i].subst_rates);
+    set_freqs_all_free(i, params[i].freqs);
+    set_gamma_rates(i, params[i].gamma_alpha);
+    if (_rate_category_types[i] == rate_category::FREE) set_gamma_weights(i, params[i].gamma_weights);
+
+    bfgs_rates(params[i].subst_rates, ops, pmatrix_indices, branch_lengths, i, pgtol, factor);
+    bfgs_freqs(params[i].freqs, ops, pmatrix_indices, branch_lengths, i, pgtol, factor);
+    if (optimize_gamma && !_rate_user_init[i]) {
+      bfgs_gamma_rates(params[i].gamma_alpha, ops, pmatrix_indices, branch_lengths, i, pgtol, factor);
+      if (_rate_category_types[i] == rate_category::FREE)
+        bfgs_gamma_weights(params[i].gamma_weights, ops, pmatrix_indices, branch_lengths, i, pgtol,
+                           factor);
+    }
+  }
+}
+
+// src/model.cpp:1737-1746
+std::vector<double> model_t::compute_all_root_lh() {
+  compute_lh(_tree.roots()[0]);
+  std::vector<double> root_lh;
+  for (auto rl : _tree.roots()) {
+    move_root(rl);
+    root_lh.push_back(compute_lh(rl));
+  }
+  return root_lh;
+}
+
+// ---------------------------------------------------------------------------
+// work assignment (src/model.cpp:1761-1911)
+// ---------------------------------------------------------------------------
+void model_t::assign_indicies(const std::vector<size_t> &idx) { _assigned_idx = idx; }
+
+void model_t::assign_indicies(size_t begin, size_t end) {
+  _assigned_idx.resize(end - begin);
+  std::iota(_assigned_idx.begin(), _assigned_idx.end(), begin);
+}
+
+void model_t::assign_indicies() {
+  _assigned_idx.resize(_tree.root_count());
+  std::iota(_assigned_idx.begin(), _assigned_idx.end(), 0);
+}
+
+void model_t::assign_indicies(size_t beg, size_t end, std::vector<size_t> idx) {
+  _assigned_idx.clear();
+  for (size_t i = beg; i < end; ++i) _assigned_idx.push_back(idx[i]);
+}
+
+void model_t::assign_indicies_by_rank_search(size_t min_roots, double root_ratio, size_t rank,
+                                             size_t num_tasks, checkpoint_t &checkpoint) {
+  assign_indicies_by_rank_search(min_roots, root_ratio, rank, num_tasks, initial_root_strategy_t::random,
+                                 checkpoint);
+}
+
+void model_t::assign_indicies_by_rank_search(size_t min_roots, double root_ratio, size_t rank,
+                                             size_t num_tasks, initial_root_strategy_t init_root,
+                                             checkpoint_t &checkpoint) {
+  auto                completed = checkpoint.completed_indicies();
+  std::vector<size_t> order;
+  if (init_root == initial_root_strategy_t::random)
+    order = shuffle_root_indicies();
+  else if (init_root == initial_root_strategy_t::midpoint)
+    order = suggest_root_indicies_midpoint();
+  else if (init_root == initial_root_strategy_t::modified_mad)
+    order = suggest_root_indicies_modified_mad();
+  else
+    throw std::runtime_error{"The initial root strategy was not recognized"};
+
+  size_t root_count = std::min(
+      std::max(static_cast<size_t>(_tree.root_count() * root_ratio), min_roots), _tree.root_count());
+  if (root_count < completed.size())
+    throw std::runtime_error{"There are too many results in the checkpoint for this search. Is the "
+                             "checkpoint corrupted?"};
+  std::sort(completed.begin(), completed.end());
+  size_t              work_left = root_count - completed.size();
+  std::vector<size_t> trimmed;
+  for (auto i : order)
+    if (!std::binary_search(completed.begin(), completed.end(), i)) trimmed.push_back(i);
+  size_t chunk = work_left / num_tasks, mod = work_left % num_tasks;
+  size_t beg = chunk * rank + std::min(mod, rank);
+  size_t end = chunk * (rank + 1) + std::min(mod, (rank + 1));
+  assign_indicies(beg, end, trimmed);
+}
+
+void model_t::assign_indicies_by_rank_exhaustive(size_t rank, size_t num_tasks,
+                                                 checkpoint_t &checkpoint) {
+  auto completed = checkpoint.current_progress();
+  if (_tree.root_count() < completed.size())
+    throw std::runtime_error{"There are too many results in the checkpoint for this tree, are you "
+                             "sure the checkpoint matches?"};
+  size_t work_left = _tree.root_count() - completed.size();
+  std::sort(completed.begin(), completed.end(),
+            [](rd_result_t a, rd_result_t b) { return a.root_id < b.root_id; });
+  std::vector<size_t> todo;
+  size_t              c = 0;
+  for (size_t i = 0; i < _tree.root_count(); ++i) {
+    if (c < completed.size() && completed[c].root_id == i)
+      ++c;
+    else
+      todo.push_back(i);
+  }
+  size_t chunk = work_left / num_tasks, mod = work_left % num_tasks;
+  size_t beg = chunk * rank + std::min(mod, rank);
+  size_t end = chunk * (rank + 1) + std::min(mod, (rank + 1));
+  assign_indicies(beg, end, todo);
+}

@@ -1,0 +1,185 @@
+// model.hpp -- model_t: the likelihood facade, root-location and parameter
+// optimisers and the two search drivers of RootDigger, on the B200 engine.
+//
+// Same class surface as the reference's model_t (src/model.hpp:46-277): a user
+// of the reference finds compute_lh, compute_lh_root, compute_dlh,
+// optimize_alpha, optimize_root_location, search, exhaustive_search,
+// initialize_partitions*, assign_indicies*, suggest_roots_*, with the same
+// argument meaning and the same exceptions.  Underneath, every corax_* call of
+// the reference is the rdk_* call of include/rdk.h, and the placement sweep /
+// derivative evaluations may use the fused rdk entry points (same values).
+#ifndef RD_HOST_MODEL_HPP_
+#define RD_HOST_MODEL_HPP_
+
+#include <rdk.h>
+
+#include "checkpoint.hpp"
+#include "msa.hpp"
+#include "tree.hpp"
+#include "util.hpp"
+
+#include <functional>
+#include <random>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+struct invalid_empirical_frequencies_exception : public std::runtime_error {
+  invalid_empirical_frequencies_exception(const char *m) : std::runtime_error(m) {}
+};
+
+model_params_t random_params(size_t size, uint64_t seed);
+
+// how model_t's partitions are laid out over GPUs (new).  The
+// default is one unsharded partition per MSA partition on the current device.
+struct shard_spec_t {
+  unsigned long long site_offset = 0;  // first global site pattern held by this process
+  unsigned long long global_sites = 0; // 0 = unsharded
+  int                nranks = 1, rank = 0;
+  const void        *comm_id = nullptr; // 128-byte id from rdk_comm_unique_id (rank 0), or nullptr
+};
+
+class model_t {
+public:
+  model_t(rooted_tree_t t, const std::vector<msa_t> &msa, const std::vector<ratehet_opts_t> &rate_cats,
+          bool invariant_sites, uint64_t seed, bool early_stop, const shard_spec_t &shard = shard_spec_t());
+  model_t(rooted_tree_t t, const std::vector<msa_t> &msa, size_t rate_cats, bool invariant_sites,
+          uint64_t seed, bool early_stop)
+      : model_t(std::move(t), msa, std::vector<ratehet_opts_t>(msa.size(), ratehet_opts_t{rate_cats}),
+                invariant_sites, seed, early_stop) {}
+  model_t(const model_t &) = delete;
+  ~model_t();
+
+  double compute_lh(const root_location_t &root_location);
+  double compute_lh_root(const root_location_t &root);
+  dlh_t  compute_dlh(const root_location_t &root_location);
+
+  root_location_t                    optimize_alpha(const root_location_t &root, double atol);
+  std::pair<root_location_t, double> optimize_root_location(size_t min_roots, double root_ratio);
+
+  std::pair<root_location_t, double> search(size_t min_roots, double root_ratio, double atol, double pgtol,
+                                            double brtol, double factor, checkpoint_t &);
+  std::pair<root_location_t, double> exhaustive_search(double atol, double pgtol, double brtol,
+                                                       double factor, checkpoint_t &);
+
+  void initialize();
+  void finalize();
+
+  rooted_tree_t rooted_tree(const root_location_t &root) const;
+  rooted_tree_t virtual_rooted_tree(const root_location_t &root) const;
+  rooted_tree_t unrooted_tree() const;
+  rooted_tree_t &tree() { return _tree; }
+
+  void initialize_partitions(const std::vector<msa_t> &);
+  void initialize_partitions_uniform_freqs(const std::vector<msa_t> &);
+
+  std::string subst_string() const;
+
+  std::vector<root_location_t> suggest_roots_random(size_t min, double ratio);
+  std::vector<root_location_t> suggest_roots_lh(size_t min, double ratio);
+  std::vector<root_location_t> suggest_roots_midpoint(size_t min, double ratio);
+  std::vector<root_location_t> suggest_roots_modified_mad(size_t min, double ratio);
+
+  std::vector<size_t> shuffle_root_indicies();
+  std::vector<size_t> suggest_root_indicies_midpoint();
+  std::vector<size_t> suggest_root_indicies_modified_mad();
+
+  std::vector<double> compute_all_root_lh();
+  // log-likelihood of every root placement at ratio 0.5 (the values
+  // suggest_roots_lh ranks), and LWR = softmax of a log-likelihood vector
+  // (exhaustive mode, src/model.cpp:1238-1258)
+  std::vector<double>        sweep_root_lh();
+  static std::vector<double> lwr(const std::vector<double> &llh);
+
+  void set_subst_rates(size_t, const model_params_t &);
+  void set_freqs(size_t, const model_params_t &);
+  void set_gamma_rates(size_t, const model_params_t &);
+  void set_gamma_weights(size_t, model_params_t);
+
+  void assign_indicies(const std::vector<size_t> &);
+  void assign_indicies(size_t, size_t);
+  void assign_indicies(size_t beg, size_t end, std::vector<size_t> idx);
+  void assign_indicies();
+  void assign_indicies_by_rank_search(size_t min_roots, double root_ratio, size_t rank, size_t num_tasks,
+                                      checkpoint_t &checkpoint);
+  void assign_indicies_by_rank_search(size_t min_roots, double root_ratio, size_t rank, size_t num_tasks,
+                                      initial_root_strategy_t init_root, checkpoint_t &);
+  void assign_indicies_by_rank_exhaustive(size_t rank, size_t num_tasks, checkpoint_t &);
+  std::vector<size_t> assigned_indicies() const { return _assigned_idx; }
+
+  void move_root(const root_location_t &new_root);
+  // use the fused engine entry points (rdk_sweep_root_placements) where the
+  // reference loops over move_root + compute_lh_root; results are identical
+  void set_fused(bool on) { _fused = on; }
+
+  rdk_partition_t *partition(size_t i) { return _partitions[i]; }
+  size_t           partition_count() const { return _partitions.size(); }
+
+private:
+  std::pair<root_location_t, double> brents(root_location_t beg, dlh_t d_beg, root_location_t end,
+                                            dlh_t d_end, double atol);
+
+  void set_subst_rates_random(size_t, const msa_t &);
+  void set_subst_rates_uniform();
+  void set_gamma_rates(size_t);
+  void set_gamma_rates_mean(size_t);
+  void set_gamma_rates_mean(size_t, double);
+  void set_gamma_rates_median(size_t);
+  void set_gamma_rates_median(size_t, double);
+  void set_gamma_rates_free(size_t);
+  void set_gamma_rates_free(size_t, model_params_t);
+  void update_invariant_sites(size_t);
+  void set_tip_states(size_t, const msa_t &);
+  void set_empirical_freqs(size_t);
+  void set_empirical_freqs();
+  void set_freqs_all_free(size_t, model_params_t);
+  void set_model_params(const std::vector<partition_parameters_t> &);
+
+  void update_pmatrix_partition(size_t partition_index, const std::vector<unsigned int> &pmatrix_indices,
+                                const std::vector<double> &branch_lengths);
+  std::vector<bool> update_pmatrices(const std::vector<unsigned int> &pmatrix_indices,
+                                     const std::vector<double>       &branch_lengths);
+  double compute_lh_partition(size_t partition_index, const std::vector<rdk_operation_t> &ops,
+                              const std::vector<unsigned int> &pmatrix_indices,
+                              const std::vector<double>       &branch_lengths);
+
+  double bfgs_rates(model_params_t &initial_rates, const std::vector<rdk_operation_t> &ops,
+                    const std::vector<unsigned int> &pmatrix_indices,
+                    const std::vector<double> &branch_lengths, size_t partition_index, double pgtol,
+                    double factor);
+  double bfgs_freqs(model_params_t &initial_freqs, const std::vector<rdk_operation_t> &ops,
+                    const std::vector<unsigned int> &pmatrix_indices,
+                    const std::vector<double> &branch_lengths, size_t partition_index, double pgtol,
+                    double factor);
+  double bfgs_gamma_rates(model_params_t &alpha, const std::vector<rdk_operation_t> &ops,
+                          const std::vector<unsigned int> &pmatrix_indices,
+                          const std::vector<double> &branch_lengths, size_t partition_index, double pgtol,
+                          double factor);
+  double bfgs_gamma_weights(model_params_t &w, const std::vector<rdk_operation_t> &ops,
+                            const std::vector<unsigned int> &pmatrix_indices,
+                            const std::vector<double> &branch_lengths, size_t partition_index,
+                            double pgtol, double factor);
+  void   optimize_params(std::vector<partition_parameters_t> &params, const root_location_t &rl,
+                         double pgtol, double factor, bool optimize_gamma);
+
+  partition_parameters_t make_partition_parameters(size_t states, rate_category rc, size_t rate_cat_count);
+
+  rooted_tree_t                          _tree;
+  std::vector<rdk_partition_t *>         _partitions;
+  std::vector<rate_category>             _rate_category_types;
+  std::vector<double>                    _partition_weights;
+  std::vector<model_params_t>            _rate_rates;
+  std::vector<model_params_t>            _rate_weights;
+  std::vector<bool>                      _rate_user_init;
+  std::vector<std::vector<unsigned int>> _param_indicies;
+  std::vector<size_t>                    _assigned_idx;
+  std::minstd_rand                       _random_engine;
+  bool                                   _invariant_sites;
+  uint64_t                               _seed;
+  bool                                   _early_stop;
+  bool                                   _fused = true;
+  static constexpr unsigned int          _submodels = 1;
+};
+
+#endif

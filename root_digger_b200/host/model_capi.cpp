@@ -1,0 +1,231 @@
+// model_capi.cpp -- C wrappers around model_t for ctypes (tests, bench, the
+// Python multi-GPU launcher).  Return 1 on success, 0 on failure with the
+// message available from rdh_last_error() (exceptions never cross the boundary).
+#include "model.hpp"
+
+#include <cstring>
+#include <memory>
+#include <string>
+
+extern "C" const char *rdh_last_error(void);
+void                   rdh_set_error(const std::string &s);
+
+namespace {
+struct holder_t {
+  std::vector<msa_t>       msa;
+  std::unique_ptr<model_t> model;
+  checkpoint_t             checkpoint;
+};
+holder_t &H(void *h) { return *reinterpret_cast<holder_t *>(h); }
+}  // namespace
+
+#define RDH_TRY(body)                                                                              \
+  try {                                                                                            \
+    body                                                                                           \
+  } catch (const std::exception &e) {                                                              \
+    rdh_set_error(e.what());                                                                       \
+    return 0;                                                                                      \
+  }
+
+// partitions: `n_parts` column ranges [part_begin[i], part_end[i]) of the given
+// alignment (n_parts == 0: one partition with every column).  Sharding: this
+// process holds global site patterns [site_offset, site_offset + local) of
+// `global_sites` (0 = unsharded); comm_id = 128-byte NCCL id or NULL.
+extern "C" void *rdh_model_create(void *tree, int n_taxa, const char **labels, const char **seqs,
+                                  int compress, unsigned rate_cats, int invariant_sites,
+                                  unsigned long long seed, int early_stop, int n_parts,
+                                  const unsigned long long *part_begin,
+                                  const unsigned long long *part_end,
+                                  unsigned long long site_offset, unsigned long long global_sites,
+                                  int nranks, int rank, const void *comm_id) {
+  try {
+    auto                     h = std::make_unique<holder_t>();
+    std::vector<std::string> l(labels, labels + n_taxa), s(seqs, seqs + n_taxa);
+    if (n_parts <= 0) {
+      h->msa.emplace_back(l, s, rdk_map_nt, 4u, compress != 0);
+    } else {
+      msa_t whole(l, s, rdk_map_nt, 4u, false);
+      for (int i = 0; i < n_parts; ++i) {
+        h->msa.emplace_back(whole, (size_t)part_begin[i], (size_t)part_end[i]);
+        if (compress) h->msa.back().compress();
+      }
+    }
+    shard_spec_t shard;
+    shard.site_offset = site_offset;
+    shard.global_sites = global_sites;
+    shard.nranks = nranks;
+    shard.rank = rank;
+    shard.comm_id = comm_id;
+    rooted_tree_t t(*reinterpret_cast<rooted_tree_t *>(tree));
+    h->model = std::make_unique<model_t>(std::move(t), h->msa,
+                                         std::vector<ratehet_opts_t>(h->msa.size(), ratehet_opts_t{rate_cats}),
+                                         invariant_sites != 0, (uint64_t)seed, early_stop != 0, shard);
+    return h.release();
+  } catch (const std::exception &e) {
+    rdh_set_error(e.what());
+    return nullptr;
+  }
+}
+
+extern "C" void rdh_model_destroy(void *h) { delete reinterpret_cast<holder_t *>(h); }
+
+extern "C" unsigned rdh_model_sites(void *h, unsigned part) { return H(h).msa[part].length(); }
+extern "C" unsigned rdh_model_root_count(void *h) { return (unsigned)H(h).model->tree().root_count(); }
+
+extern "C" int rdh_model_initialize_partitions(void *h, int uniform_freqs) {
+  RDH_TRY({
+    if (uniform_freqs)
+      H(h).model->initialize_partitions_uniform_freqs(H(h).msa);
+    else
+      H(h).model->initialize_partitions(H(h).msa);
+    return 1;
+  })
+}
+
+extern "C" int rdh_model_set_fused(void *h, int on) {
+  H(h).model->set_fused(on != 0);
+  return 1;
+}
+
+extern "C" int rdh_model_set_params(void *h, unsigned part, const double *rates12, const double *freqs4,
+                                    const double *alpha) {
+  RDH_TRY({
+    if (rates12) H(h).model->set_subst_rates(part, model_params_t(rates12, rates12 + 12));
+    if (freqs4) H(h).model->set_freqs(part, model_params_t(freqs4, freqs4 + 4));
+    if (alpha) H(h).model->set_gamma_rates(part, model_params_t(alpha, alpha + 1));
+    return 1;
+  })
+}
+
+static root_location_t RL(void *h, unsigned id, double ratio) {
+  auto rl = H(h).model->tree().root_location((size_t)id);
+  rl.brlen_ratio = ratio;
+  return rl;
+}
+
+extern "C" int rdh_model_compute_lh(void *h, unsigned id, double ratio, double *out) {
+  RDH_TRY({
+    *out = H(h).model->compute_lh(RL(h, id, ratio));
+    return 1;
+  })
+}
+extern "C" int rdh_model_compute_lh_root(void *h, unsigned id, double ratio, double *out) {
+  RDH_TRY({
+    *out = H(h).model->compute_lh_root(RL(h, id, ratio));
+    return 1;
+  })
+}
+extern "C" int rdh_model_compute_dlh(void *h, unsigned id, double ratio, double *lh, double *dlh) {
+  RDH_TRY({
+    auto d = H(h).model->compute_dlh(RL(h, id, ratio));
+    *lh = d.lh;
+    *dlh = d.dlh;
+    return 1;
+  })
+}
+extern "C" int rdh_model_move_root(void *h, unsigned id, double ratio) {
+  RDH_TRY({
+    H(h).model->move_root(RL(h, id, ratio));
+    return 1;
+  })
+}
+extern "C" int rdh_model_optimize_alpha(void *h, unsigned id, double ratio, double atol, double *out) {
+  RDH_TRY({
+    *out = H(h).model->optimize_alpha(RL(h, id, ratio), atol).brlen_ratio;
+    return 1;
+  })
+}
+extern "C" int rdh_model_optimize_root_location(void *h, unsigned min_roots, double root_ratio,
+                                                unsigned *id, double *alpha, double *lh) {
+  RDH_TRY({
+    auto r = H(h).model->optimize_root_location(min_roots, root_ratio);
+    *id = (unsigned)r.first.id;
+    *alpha = r.first.brlen_ratio;
+    *lh = r.second;
+    return 1;
+  })
+}
+extern "C" int rdh_model_sweep_root_lh(void *h, double *out) {
+  RDH_TRY({
+    auto v = H(h).model->sweep_root_lh();
+    for (size_t i = 0; i < v.size(); ++i) out[i] = v[i];
+    return 1;
+  })
+}
+extern "C" int rdh_model_compute_all_root_lh(void *h, double *out) {
+  RDH_TRY({
+    auto v = H(h).model->compute_all_root_lh();
+    for (size_t i = 0; i < v.size(); ++i) out[i] = v[i];
+    return 1;
+  })
+}
+
+// init_strategy: 0 random, 1 midpoint, 2 modified MAD
+extern "C" int rdh_model_search(void *h, unsigned min_roots, double root_ratio, double atol, double pgtol,
+                                double brtol, double factor, int init_strategy, unsigned rank,
+                                unsigned num_tasks, unsigned *id, double *alpha, double *lh) {
+  RDH_TRY({
+    auto &m = *H(h).model;
+    H(h).checkpoint.clear();
+    auto strat = init_strategy == 0   ? initial_root_strategy_t::random
+                 : init_strategy == 1 ? initial_root_strategy_t::midpoint
+                                      : initial_root_strategy_t::modified_mad;
+    m.assign_indicies_by_rank_search(min_roots, root_ratio, rank, num_tasks, strat, H(h).checkpoint);
+    auto r = m.search(min_roots, root_ratio, atol, pgtol, brtol, factor, H(h).checkpoint);
+    *id = (unsigned)r.first.id;
+    *alpha = r.first.brlen_ratio;
+    *lh = r.second;
+    return 1;
+  })
+}
+
+// exhaustive mode over this rank's slice of the root ids; per-root results are
+// written to ids/llh/alpha (capacity `cap`), n_out receives their number
+extern "C" int rdh_model_exhaustive_search(void *h, double atol, double pgtol, double brtol, double factor,
+                                           unsigned rank, unsigned num_tasks, unsigned *ids, double *llh,
+                                           double *alpha, unsigned cap, unsigned *n_out) {
+  RDH_TRY({
+    auto &m = *H(h).model;
+    H(h).checkpoint.clear();
+    m.assign_indicies_by_rank_exhaustive(rank, num_tasks, H(h).checkpoint);
+    m.exhaustive_search(atol, pgtol, brtol, factor, H(h).checkpoint);
+    auto res = H(h).checkpoint.current_progress();
+    if (res.size() > cap) throw std::runtime_error("output buffers too small");
+    for (size_t i = 0; i < res.size(); ++i) {
+      ids[i] = (unsigned)res[i].root_id;
+      llh[i] = res[i].llh;
+      alpha[i] = res[i].alpha;
+    }
+    *n_out = (unsigned)res.size();
+    return 1;
+  })
+}
+
+extern "C" int rdh_model_lwr(const double *llh, unsigned n, double *out) {
+  auto w = model_t::lwr(std::vector<double>(llh, llh + n));
+  for (unsigned i = 0; i < n; ++i) out[i] = w[i];
+  return 1;
+}
+
+extern "C" char *rdh_model_newick(void *h, int annotations) {
+  try {
+    std::string s = H(h).model->tree().newick(annotations != 0);
+    char       *out = (char *)malloc(s.size() + 1);
+    std::memcpy(out, s.c_str(), s.size() + 1);
+    return out;
+  } catch (const std::exception &e) {
+    rdh_set_error(e.what());
+    return nullptr;
+  }
+}
+
+extern "C" int rdh_model_get_params(void *h, unsigned part, double *rates12, double *freqs4,
+                                    double *cat_rates) {
+  auto p = H(h).model->partition(part);
+  for (int i = 0; i < 12; ++i) rates12[i] = p->subst_params[0][i];
+  for (int i = 0; i < 4; ++i) freqs4[i] = p->frequencies[0][i];
+  for (unsigned k = 0; k < p->rate_cats; ++k) cat_rates[k] = p->rates[k];
+  return 1;
+}
+
+extern "C" void *rdh_model_partition(void *h, unsigned part) { return H(h).model->partition(part); }

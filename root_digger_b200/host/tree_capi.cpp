@@ -9,6 +9,7 @@
 static thread_local std::string g_err;
 
 extern "C" const char *rdh_last_error(void) { return g_err.c_str(); }
+void                   rdh_set_error(const std::string &s) { g_err = s; }
 extern "C" void        rdh_free(void *p) { free(p); }
 
 #define RDH_GUARD(body)                                                                            \
