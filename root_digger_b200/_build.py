@@ -106,7 +106,7 @@ def build_host(force: bool = False) -> Path:
     if not force and _newer(out, deps):
         return out
     _run([_cxx(), "-std=c++17", "-O2", "-fPIC", "-fopenmp", "-Wall", "-ffp-contract=off", "-I", INCLUDE, "-shared",
-          "-o", out, *srcs, "-L", LIBDIR, "-lrdk_b200", "-ldl", "-Wl,-rpath,$ORIGIN"])
+          "-o", out, *srcs, "-L", LIBDIR, "-lrdk_b200", "-ldl", "-Wl,-rpath,$ORIGIN", "-Wl,-Bsymbolic"])
     return out
 
 
@@ -135,7 +135,7 @@ def build_host_on_oracle(force: bool = False) -> Path:
         return out
     _run([_cxx(), "-std=c++17", "-O2", "-fPIC", "-fopenmp", "-Wall", "-ffp-contract=off", "-DRD_BACKEND_ORACLE",
           "-I", shim, "-I", ORACLE, "-shared", "-o", out, *srcs, "-L", ORACLE, "-lrd_oracle", "-ldl",
-          "-Wl,-rpath," + str(ORACLE)])
+          "-Wl,-rpath," + str(ORACLE), "-Wl,-Bsymbolic"])
     return out
 
 

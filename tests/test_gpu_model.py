@@ -1,0 +1,135 @@
+"""GPU parity at the model_t level: the host C++ (search, Brent, L-BFGS-B drivers)
+compiled against the CUDA engine vs. the same sources compiled against the CPU
+oracle in ENGINE arithmetic.  Because every likelihood evaluation is bit-identical,
+the whole optimiser trajectory is: chosen root branch, optimised alpha, LWR
+ranking and final log-likelihood must be IDENTICAL (north_star)."""
+import numpy as np
+import pytest
+
+import fixtures
+import oracle_capi
+from root_digger_b200 import _build, capi, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def libs():
+    oracle_capi.load_oracle().rdo_set_default_mode(oracle_capi.MODE_ENGINE)
+    return capi.load_tree_lib(), capi.load_tree_lib(_build.build_host_on_oracle())
+
+
+def pair(libs, name="10.fasta", K=4, uniform=True, seed=4242):
+    fx = fixtures.load(name)
+    out = []
+    for lib in libs:
+        tree = capi.RootedTree(path=str(fx["tree_path"]), lib=lib)
+        m = capi.Model(tree, fx["alignment"], rate_cats=K, compress=True, invariant_sites=True, seed=seed)
+        m.initialize_partitions(uniform_freqs=uniform)
+        out.append(m)
+    return out
+
+
+def synthetic_pair(libs, n=24, S=3000, K=4, seed=9):
+    top = synth.random_tree(n, seed)
+    rates, freqs = synth.random_params(seed + 1)
+    aln = synth.simulate_alignment(top, S, seed + 2, rates, freqs, capi.gamma_cats(0.8, K))
+    out = []
+    for lib in libs:
+        tree = capi.RootedTree(synth.to_newick(top), lib=lib)
+        m = capi.Model(tree, aln, rate_cats=K, compress=True, seed=seed)
+        m.initialize_partitions(uniform_freqs=False)
+        out.append(m)
+    return out
+
+
+def bits(x):
+    return np.asarray(x, dtype=np.float64).view(np.uint64)
+
+
+@pytest.mark.parametrize("K", [1, 4])
+def test_likelihood_facade_is_bit_identical(libs, K):
+    g, o = pair(libs, K=K)
+    assert g.sites() == o.sites() == 991
+    for rid in range(g.root_count):
+        a, b = g.compute_lh(rid, 0.3), o.compute_lh(rid, 0.3)
+        assert a.hex() == b.hex()
+        assert g.compute_lh_root(rid, 0.8).hex() == o.compute_lh_root(rid, 0.8).hex()
+        assert [v.hex() for v in g.compute_dlh(rid, 0.5)] == [v.hex() for v in o.compute_dlh(rid, 0.5)]
+    # reference invariants on the GPU-backed model (test/src/model.cpp:59-75, :271-288)
+    for rid in range(g.root_count):
+        a, b, c = g.compute_lh(rid), g.compute_lh(rid), g.compute_lh_root(rid)
+        assert np.isfinite(a) and a < 0 and a == b and a == c
+
+
+def test_empirical_frequencies_and_random_rates_identical(libs):
+    g, o = pair(libs, "101.phy", K=4, uniform=False)
+    for a, b in zip(g.get_params(), o.get_params()):
+        assert np.array_equal(bits(a), bits(b))
+
+
+def test_sweep_and_root_ranking_identical(libs):
+    g, o = pair(libs, "101.phy", K=4, uniform=False)
+    g.compute_lh(0)
+    o.compute_lh(0)
+    a, b = g.sweep_root_lh(), o.sweep_root_lh()
+    assert np.array_equal(bits(a), bits(b))
+    g.compute_lh(0)
+    g.set_fused(False)           # the reference's own loop: move_root + compute_lh_root per root
+    c = g.sweep_root_lh()
+    assert np.array_equal(bits(a), bits(c))
+    assert np.array_equal(np.argsort(-a, kind="stable"), np.argsort(-b, kind="stable"))
+
+
+def test_optimize_alpha_identical(libs):
+    g, o = pair(libs, K=4)
+    for rid in range(g.root_count):
+        g.compute_lh(rid)
+        o.compute_lh(rid)
+        for atol in (1e-7, 1e-14):
+            assert g.optimize_alpha(rid, 0.5, atol).hex() == o.optimize_alpha(rid, 0.5, atol).hex()
+    assert g.optimize_root_location(2, 0.1) == o.optimize_root_location(2, 0.1)
+
+
+def test_search_chooses_identical_root_alpha_and_likelihood(libs):
+    for (g, o) in (pair(libs, K=1), synthetic_pair(libs)):
+        g.compute_lh(0)
+        o.compute_lh(0)
+        rg = g.search(2, 0.0, 1e-3, 1e-3, 1e-3, 1e12, strategy="modified_mad")
+        ro = o.search(2, 0.0, 1e-3, 1e-3, 1e-3, 1e12, strategy="modified_mad")
+        assert rg[0] == ro[0]                       # chosen root branch
+        assert rg[1].hex() == ro[1].hex()           # optimised alpha
+        assert rg[2].hex() == ro[2].hex()           # final log-likelihood
+        for a, b in zip(g.get_params(), o.get_params()):
+            assert np.array_equal(bits(a), bits(b))  # optimised rates / frequencies / category rates
+
+
+def test_exhaustive_mode_lwr_identical(libs):
+    g, o = synthetic_pair(libs, n=8, S=1500, K=4, seed=21)
+    g.compute_lh(0)
+    o.compute_lh(0)
+    ig, lg, ag = g.exhaustive_search(1e-3, 1e-3, 1e-3, 1e12)
+    io, lo, ao = o.exhaustive_search(1e-3, 1e-3, 1e-3, 1e12)
+    assert np.array_equal(ig, io) and np.array_equal(bits(lg), bits(lo)) and np.array_equal(bits(ag), bits(ao))
+    wg, wo = g.lwr(lg), o.lwr(lo)
+    assert np.array_equal(bits(wg), bits(wo))
+    assert np.array_equal(np.argsort(-wg, kind="stable"), np.argsort(-wo, kind="stable"))   # LWR ranking
+    assert g.newick() == o.newick()                                                        # annotated output tree
+
+
+def test_multi_partition_model(libs):
+    """config 4 shape in miniature: independent parameters per partition, summed log-likelihood"""
+    top = synth.random_tree(16, 5)
+    rates, freqs = synth.random_params(6)
+    aln = synth.simulate_alignment(top, 4000, 7, rates, freqs, capi.gamma_cats(1.0, 4))
+    parts = [(0, 1000), (1000, 2500), (2500, 4000)]
+    ms = []
+    for lib in libs:
+        tree = capi.RootedTree(synth.to_newick(top), lib=lib)
+        m = capi.Model(tree, aln, rate_cats=4, compress=True, seed=3, partitions=parts)
+        m.initialize_partitions(uniform_freqs=False)
+        ms.append(m)
+    g, o = ms
+    for rid in (0, 5, 11):
+        assert g.compute_lh(rid).hex() == o.compute_lh(rid).hex()
+        assert g.compute_lh_root(rid, 0.25).hex() == o.compute_lh_root(rid, 0.25).hex()

@@ -1,0 +1,126 @@
+"""model_t mirror (host C++) on the ORACLE backend: the reference's own model_t
+tests (test/src/model.cpp) restated.  The same host sources compiled against the
+CUDA engine are compared with this build in test_gpu_model.py."""
+import math
+
+import numpy as np
+import pytest
+
+import fixtures
+import oracle_capi
+from root_digger_b200 import _build, capi
+
+
+@pytest.fixture(scope="module")
+def lib():
+    oracle_capi.load_oracle().rdo_set_default_mode(oracle_capi.MODE_ENGINE)
+    return capi.load_tree_lib(_build.build_host_on_oracle())
+
+
+def make_model(lib, name="10.fasta", K=1, seed=12345, uniform=True, **kw):
+    fx = fixtures.load(name)
+    tree = capi.RootedTree(path=str(fx["tree_path"]), lib=lib)
+    m = capi.Model(tree, fx["alignment"], rate_cats=K, compress=True, invariant_sites=True, seed=seed, **kw)
+    m.initialize_partitions(uniform_freqs=uniform)
+    return m
+
+
+def test_pattern_compression_matches_reference_counts(lib):
+    assert make_model(lib, "10.fasta").sites() == 991
+    assert make_model(lib, "101.phy").sites() == 1630
+
+
+def test_compute_lh_invariants(lib):
+    """test/src/model.cpp:59-75, :271-288"""
+    m = make_model(lib)
+    assert m.root_count == 17
+    for rid in range(m.root_count):
+        a, b, c = m.compute_lh(rid), m.compute_lh(rid), m.compute_lh_root(rid)
+        assert math.isfinite(a) and a < 0 and a == b and a == c
+
+
+def test_compute_dlh_and_optimize_alpha(lib):
+    """test/src/model.cpp:95-110, :132-238"""
+    m = make_model(lib)
+    for rid in range(m.root_count):
+        m.compute_lh(rid)
+        lh, dlh = m.compute_dlh(rid)
+        assert math.isfinite(lh) and math.isfinite(dlh)
+        for start in (0.5, 0.0, 1.0):
+            m.compute_lh(rid, start)
+            r = m.optimize_alpha(rid, start, 1e-7)
+            assert 0.0 <= r <= 1.0
+
+
+def test_optimize_root_location(lib):
+    """test/src/model.cpp:240-252"""
+    m = make_model(lib)
+    m.compute_lh(0)
+    rid, alpha, lh = m.optimize_root_location(1, .05)
+    assert 0.0 <= alpha <= 1.0 and math.isfinite(lh)
+
+
+def test_fused_sweep_equals_reference_loop(lib):
+    m = make_model(lib, K=4)
+    m.compute_lh(0)
+    m.set_fused(True)
+    a = m.sweep_root_lh()
+    m.compute_lh(0)
+    m.set_fused(False)
+    b = m.sweep_root_lh()
+    assert np.array_equal(a.view(np.uint64), b.view(np.uint64))
+
+
+def test_move_root_invariance_under_jc(lib):
+    """test/src/model.cpp:367-387"""
+    m = make_model(lib, "101.phy", uniform=False)
+    m.set_params(rates=np.ones(12), freqs=np.full(4, .25))
+    m.compute_lh(0)
+    v = m.sweep_root_lh()
+    assert np.ptp(v) <= 1.19e-5 * abs(v[0])
+
+
+def test_search_returns_consistent_likelihood(lib):
+    """test/src/model.cpp:310-346: compute_lh(final_rl) == Approx(final_lh).
+
+    Quirk kept from the reference ("B-17"): set_model_params (src/model.cpp:1913-1923)
+    re-installs the optimiser's RAW frequency vector with set_freqs, while every likelihood during the search
+    was computed with set_freqs_all_free (:350-355), i.e. the vector divided by its sum.  The recorded
+    likelihood is therefore reproduced after normalising the installed frequencies."""
+    m = make_model(lib)
+    m.compute_lh(0)
+    initial = m.compute_lh(4)
+    rid, alpha, lh = m.search(3, 0.0, 1e-3, 1e-3, 1e-3, 1e12, strategy="random")
+    assert lh >= initial
+    rates, freqs, _ = m.get_params()
+    m.set_params(freqs=freqs / freqs.sum())
+    assert m.compute_lh(rid, alpha) == pytest.approx(lh, rel=1.2e-5)
+    assert m.compute_lh_root(rid, alpha) == pytest.approx(lh, rel=1.2e-5)
+
+
+def test_lwr_is_a_softmax(lib):
+    m = make_model(lib)
+    llh = np.array([-100.0, -101.0, -130.0, -100.5])
+    w = m.lwr(llh)
+    assert abs(w.sum() - 1) < 1e-15 and np.argmax(w) == 0
+    assert np.allclose(w, np.exp(llh + 100) / np.exp(llh + 100).sum())
+
+
+def test_taxa_mismatch_is_rejected(lib):
+    fx = fixtures.load("10.fasta")
+    tree = capi.RootedTree(path=str(fx["tree_path"]), lib=lib)
+    aln = dict(fx["alignment"])
+    aln["zzz"] = aln.pop("a")
+    with pytest.raises(RuntimeError, match="inconsistient"):
+        capi.Model(tree, aln, rate_cats=1)
+
+
+@pytest.mark.slow
+def test_exhaustive_search_runs(lib):
+    """test/src/model.cpp:389-401"""
+    m = make_model(lib, uniform=False)
+    m.compute_lh(0)
+    ids, llh, alpha = m.exhaustive_search(1e-3, 1e-3, 1e-3, 1e12)
+    assert sorted(ids.tolist()) == list(range(17)) and np.isfinite(llh).all()
+    assert ((alpha >= 0) & (alpha <= 1)).all()
+    assert "LWR=" in m.newick()

@@ -1,0 +1,94 @@
+"""N > 1 host logic on CPU: shard planners and a world_size-2 gloo run in which
+every rank evaluates its site shard with the oracle and the per-shard tree nodes
+are all-reduced exactly as the CUDA engine does over NCCL (zeros elsewhere, so
+the sum is exact and independent of the number of shards)."""
+import os
+import socket
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from root_digger_b200 import sharding
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_site_shard_plan():
+    for S in (0, 1, 1023, 1024, 1025, 100_000, 1_000_000):
+        for G in (1, 2, 3, 8):
+            plan = sharding.plan_site_shards(S, G)
+            assert len(plan) == G and sum(c for _, c in plan) == S
+            pos = 0
+            for off, cnt in plan:
+                assert off == pos and (off % 1024 == 0 or cnt == 0)
+                pos += cnt
+    counts = [c for _, c in sharding.plan_site_shards(1_000_000, 8)]
+    assert max(counts) - min(counts) <= 1024 + 576   # balanced to one alignment block (last one ragged)
+
+
+def test_root_shard_plan_matches_reference_rule():
+    """src/model.cpp:1899-1907: chunk*rank + min(mod, rank)"""
+    assert sharding.plan_root_shards(range(17), 4) == [[0, 1, 2, 3, 4], [5, 6, 7, 8], [9, 10, 11, 12], [13, 14, 15, 16]]
+    assert sharding.plan_root_shards(range(3), 8)[3:] == [[]] * 5
+    assert sum(sharding.plan_root_shards(range(19997), 8), []) == list(range(19997))
+    assert sharding.plan_partition_shards(8, 8) == [[i] for i in range(8)]
+
+
+def _worker(rank, world, port, S, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, str(ROOT))
+    sys.path.insert(0, str(ROOT / "tests"))
+    import torch
+    import torch.distributed as dist
+    from cases import Case, compute_lh
+    from oracle_capi import MODE_ENGINE, OraclePartition, load_oracle
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    case = Case(12, S, 4, seed=77, data="ambiguous", weights="random")
+    off, cnt = sharding.plan_site_shards(S, world)[rank]
+    sl = slice(off, off + cnt)
+    part = OraclePartition(case.n, cnt, 4)
+    case.setup(part, site_slice=sl)
+    sched = case.full_schedule(2, 0.4)
+    _, persite = compute_lh(part, sched, case.root_clv, case.root_scaler, persite=True, mode=MODE_ENGINE)
+    # per-shard nodes of the canonical tree (one per 1024-site block), zeros elsewhere
+    L = load_oracle()
+    import ctypes as C
+    nblocks = (S + 1023) // 1024
+    nodes = np.zeros(nblocks)
+    for b in range((cnt + 1023) // 1024):
+        seg = np.ascontiguousarray(persite[b * 1024:(b + 1) * 1024])
+        pad = np.zeros(1024)
+        pad[:len(seg)] = seg
+        nodes[off // 1024 + b] = L.rdo_pairwise_sum(pad.ctypes.data_as(C.POINTER(C.c_double)), 1024)
+    t = torch.from_numpy(nodes)
+    dist.all_reduce(t)
+    total = L.rdo_pairwise_sum(t.numpy().ctypes.data_as(C.POINTER(C.c_double)), nblocks)
+    if rank == 0:
+        q.put(total)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("S", [5000, 2048])
+def test_two_rank_gloo_site_sharding_matches_single_shard(S):
+    import torch.multiprocessing as mp
+    from cases import Case, compute_lh
+    from oracle_capi import MODE_ENGINE, OraclePartition
+    case = Case(12, S, 4, seed=77, data="ambiguous", weights="random")
+    full = OraclePartition(case.n, S, 4)
+    case.setup(full)
+    want = compute_lh(full, case.full_schedule(2, 0.4), case.root_clv, case.root_scaler, mode=MODE_ENGINE)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, S, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got.hex() == want.hex()   # bit-identical whatever the number of shards
