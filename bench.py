@@ -1,0 +1,441 @@
+#!/usr/bin/env python
+"""bench.py -- root placements evaluated per second + CLV-update GB/s (BASELINE.json metric).
+
+Workload (BASELINE.json configs[1]): synthetic 500-taxon x 100 000-site DNA alignment, UNREST
+model, 4 Gamma categories, search mode.  One STEP is what one outer iteration of
+model_t::search needs from the likelihood engine to score every candidate root
+(reference src/model.cpp:1051-1057 -> optimize_root_location :796 -> suggest_roots_lh :865-889):
+
+    1 full evaluation           model_t::compute_lh        (n-1 CLV operations + root logL)
+  + 1 placement sweep           model_t::suggest_roots_lh  (for each of the 2n-3 candidate
+                                root branches: move_root + compute_lh_root)
+
+value   = (2n-3) placements x K steps / device time, schedules and alignment already
+          resident (host arrays pre-built, tips in HBM); CUDA events on the engine's stream.
+e2e     = the same step through the host model_t mirror (librd_host.so: C++ traversal
+          scheduler generates the op lists each step, programs go host->device, the 2n-3
+          log-likelihoods come back device->host), wall clock around the public calls.
+roofline= the dominant kernel (clv_program_kernel): algorithmic bytes (counted
+          per launch by the engine) / its device time (CUDA events bracketing each launch).
+
+N > 1: the alignment's sites are sharded across the GPUs (strong scaling: the global problem
+is fixed), one process per GPU, one NCCL all-reduce of tree nodes per evaluation batch.
+
+--impl reference: the CPU oracle restatement of the same step (the reference's coraxlib is an
+absent submodule: it cannot be built), all host threads, on a bounded site sample.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+import numpy as np  # noqa: E402
+
+METRIC = "root_placements_per_sec"
+UNIT = "placements/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--taxa", type=int, default=500)
+    ap.add_argument("--sites", type=int, default=100000)
+    ap.add_argument("--cats", type=int, default=4)
+    ap.add_argument("--data", default="evolved", choices=["evolved", "iid"])
+    ap.add_argument("--seed", type=int, default=0x5EED0002)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--launch-config", default="", help="ctas_per_sm,threads,elems (0 = engine default)")
+    return ap.parse_args()
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpus):
+        self.gpus = gpus
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", ",".join(str(g) for g in self.gpus)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_case(args):
+    from cases import Case
+    from root_digger_b200.capi import gamma_cats
+    return Case(args.taxa, args.sites, args.cats, seed=args.seed, data=args.data, alpha=1.0, gamma_cats=gamma_cats)
+
+
+def step_bytes_formula(n, S, K):
+    """bytes of one full evaluation, per site count S (unfused accounting)"""
+    return S * ((n - 1) * (64 * K + 8) + n)
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm: CPU oracle, all host threads, bounded site sample
+# ---------------------------------------------------------------------------------------------
+def oracle_step(o, case, full_arr, full_pm, full_br, sw, sw_ops_arrs, threads):
+    """one step on the oracle: compute_lh(root 0) + the sweep, as the three reference calls"""
+    o.update_prob_matrices(full_pm, full_br)
+    o.L.rdo_update_clvs_mt(o.p, full_arr, len(full_arr), threads)
+    lh0 = o.root_loglikelihood_mt(case.root_clv, case.root_scaler, threads)
+    pm_off, mi, bl, op_off, _ = sw
+    out = np.zeros(len(pm_off) - 1)
+    for q in range(len(pm_off) - 1):
+        a, b = pm_off[q], pm_off[q + 1]
+        if b > a:
+            o.update_prob_matrices(mi[a:b], bl[a:b])
+        arr, cnt = sw_ops_arrs[q]
+        if cnt:
+            o.L.rdo_update_clvs_mt(o.p, arr, cnt, threads)
+        out[q] = o.root_loglikelihood_mt(case.root_clv, case.root_scaler, threads)
+    return lh0, out
+
+
+def cpu_reference_run(args, case, steps, warmup, threads, target_step_s=1.5, quiet=False):
+    """times the oracle on a site sample; returns (placements/s scaled to the full site count, info)"""
+    from oracle_capi import OraclePartition
+    from root_digger_b200.capi import ops_array
+    n, S, K = case.n, case.S, case.K
+    full_ops, full_pm, full_br = case.full_schedule(0, 0.5)
+    full_arr = ops_array(full_ops)
+    roots = list(range(case.tree.root_count))
+    sw = case.sweep_schedule(roots, 0.5)
+    pm_off, mi, bl, op_off, ops = sw
+    sw_ops_arrs = []
+    for q in range(len(roots)):
+        sub = ops[op_off[q]:op_off[q + 1]]
+        sw_ops_arrs.append((ops_array(sub), len(sub)))
+
+    def make(sample):
+        o = OraclePartition(n, sample, K)
+        case.setup(o, slice(0, sample))
+        return o
+
+    # calibrate the sample so that one step costs about target_step_s
+    probe = min(S, 1024)
+    o = make(probe)
+    oracle_step(o, case, full_arr, full_pm, full_br, sw, sw_ops_arrs, threads)  # first touch, thread start-up
+    t0 = time.perf_counter()
+    oracle_step(o, case, full_arr, full_pm, full_br, sw, sw_ops_arrs, threads)
+    t_probe = time.perf_counter() - t0
+    o.close()
+    sample = int(min(S, max(probe, probe * target_step_s / max(t_probe, 1e-6))))
+    sample = max(256, (sample // 256) * 256) if sample < S else S
+    o = make(sample)
+    for _ in range(warmup):
+        oracle_step(o, case, full_arr, full_pm, full_br, sw, sw_ops_arrs, threads)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        oracle_step(o, case, full_arr, full_pm, full_br, sw, sw_ops_arrs, threads)
+    dt = time.perf_counter() - t0
+    o.close()
+    ms_step_sample = dt / steps * 1e3
+    ms_step_full = ms_step_sample * S / sample
+    value = len(roots) / (ms_step_full * 1e-3)
+    info = {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": "oracle/rd_oracle.c (CPU restatement; coraxlib is an absent submodule), OpenMP site-parallel, "
+                      "%d of %d sites of the same alignment, all %d placements, %d steps; scaled by sites"
+                      % (sample, S, len(roots), steps),
+            "ms_per_step_full_size": ms_step_full}
+    return value, info, ms_step_full
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    case = build_case_cpu(args)
+    value, info, ms_full = cpu_reference_run(args, case, args.steps, args.warmup, threads)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_full, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, case.tree.root_count),
+        "cpu_baseline": info,
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def build_case_cpu(args):
+    """the reference arm must not need the CUDA library: gamma categories from the oracle"""
+    from cases import Case
+    return Case(args.taxa, args.sites, args.cats, seed=args.seed, data=args.data, alpha=1.0)
+
+
+def workload_config(args, placements):
+    return {"workload": "cfg2: synthetic %d-taxon x %d-site DNA, UNREST+G%d, search-mode step = 1 full "
+                        "evaluation (compute_lh) + 1 sweep of all %d candidate root placements "
+                        "(suggest_roots_lh: move_root + compute_lh_root each)"
+                        % (args.taxa, args.sites, args.cats, placements),
+            "taxa": args.taxa, "sites": args.sites, "rate_cats": args.cats, "placements_per_step": placements,
+            "alignment": args.data, "sharding": "sites/%d" % args.gpus,
+            "l2_policy": "inputs larger than L2 (inner CLVs %.1f GB per GPU vs 126 MB L2)"
+                         % ((args.taxa - 1) * 32.0 * args.cats * args.sites / args.gpus / 1e9)}
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n_gpus = world
+
+    from cases import compute_lh
+    from root_digger_b200 import capi
+    from root_digger_b200.capi import Model, Partition, RootedTree, ops_array
+    from root_digger_b200.sharding import plan_site_shards
+
+    case = build_case(args)
+    n, S, K = case.n, case.S, case.K
+    shards = plan_site_shards(S, n_gpus)
+    off, cnt = shards[rank]
+    sl = slice(off, off + cnt)
+
+    comm_id = None
+    if world > 1:
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt = torch.tensor(list(capi.comm_unique_id()), dtype=torch.uint8, device="cuda")
+        dist.broadcast(idt, 0)
+        comm_id = bytes(idt.cpu().tolist())
+
+    g = Partition(n, cnt, K, device=local)
+    g.set_stream(torch.cuda.current_stream().cuda_stream)
+    case.setup(g, sl)
+    if world > 1:
+        g.set_shard(off, S)
+        g.attach_comm(world, rank, comm_id)
+    if args.launch_config:
+        g.set_launch_config(*[int(x) for x in args.launch_config.split(",")])
+
+    full_ops, full_pm, full_br = case.full_schedule(0, 0.5)
+    full_arr = ops_array(full_ops)
+    roots = list(range(case.tree.root_count))
+    sw = case.sweep_schedule(roots, 0.5)
+    pm_off, mi, bl, op_off, ops = sw
+    sw_arr = ops_array(ops)
+    placements = len(roots)
+
+    def step():
+        g.update_prob_matrices(full_pm, full_br)
+        g.L.rdk_update_clvs(g.p, full_arr, len(full_ops))
+        lh0 = g.root_loglikelihood(case.root_clv, case.root_scaler)
+        out = g.sweep_root_placements(pm_off, mi, bl, op_off, sw_arr, case.root_clv, case.root_scaler)
+        return lh0, out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        lh0, sweep_lh = step()
+    g.set_timing(True)
+    g.reset_stats()
+    sampler = ClockSampler(list(range(n_gpus))) if rank == 0 else None
+    barrier()
+    if sampler:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        lh0, sweep_lh = step()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    st = g.stats()
+    g.set_timing(False)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    agg = torch.tensor([float(st["algorithmic_bytes"]), float(st["kernel_launches"])], dtype=torch.float64,
+                       device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(agg, op=dist.ReduceOp.SUM)
+    ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = placements * args.steps / (ms * 1e-3)
+    total_alg_bytes = float(agg[0].item())
+    clv_gbs = total_alg_bytes / (ms * 1e-3) / 1e9
+
+    # roofline of the dominant kernel on this rank (rank 0 reports)
+    peak, peak_src = peaks()
+    prog_s = st["program_time_ns"] * 1e-9
+    achieved = st["algorithmic_bytes"] / prog_s / 1e9 if prog_s > 0 else 0.0
+    per_launch = st["algorithmic_bytes"] / max(1, st["program_timed"])
+    roofline = {"bound": "hbm", "kernel": "clv_program_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": dram_traffic_from_profiles(),
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": per_launch,
+                "avg_launch_ms": prog_s * 1e3 / max(1, st["program_timed"]),
+                "launches_timed": st["program_timed"],
+                "kernel_share_of_step": prog_s * 1e3 / ms if ms > 0 else None}
+
+    # ---- e2e: the same step through the host model_t mirror (public API, host buffers)
+    e2e = None
+    if not args.no_e2e:
+        tree = RootedTree(case.newick)
+        aln = {l: s[sl] for l, s in case.aln.items()}
+        m = Model(tree, aln, K, site_offset=off if world > 1 else 0, global_sites=S if world > 1 else 0,
+                  nranks=world, rank=rank, comm_id=comm_id if world > 1 else None)
+        m.initialize_partitions()
+        m.set_params(rates=case.rates, freqs=case.freqs)
+        part = C.cast(m.L.rdh_model_partition(m.h, 0), C.POINTER(capi.PartitionStruct))
+        L = capi.load_engine()
+
+        def mstats():
+            s = capi.Stats()
+            L.rdk_partition_stats(part, C.byref(s))
+            return s.asdict()
+
+        def mstep():
+            a = m.compute_lh(0, 0.5)
+            b = m.sweep_root_lh()
+            return a, b
+
+        for _ in range(max(3, args.warmup)):
+            a, b = mstep()
+        L.rdk_partition_reset_stats(part)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            a, b = mstep()
+        barrier()
+        dt = time.perf_counter() - t0
+        ms2 = torch.tensor([dt * 1e3], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+        s2 = mstats()
+        e2e = {"value": placements * args.steps / (float(ms2.item()) * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": s2["h2d_bytes"] / args.steps, "d2h_bytes_per_step": s2["d2h_bytes"] / args.steps,
+               "ms_per_step": float(ms2.item()) / args.steps,
+               "api": "librd_host.so model_t::compute_lh + model_t::suggest_roots_lh sweep (host scheduler, "
+                      "programs H2D, log-likelihoods D2H; alignment resident as in the reference partition)",
+               "logl_root0": a, "matches_device_arm": bool(a == lh0 and np.array_equal(b, sweep_lh))}
+        m.close()
+    clocks = sampler.stop() if sampler else None
+
+    cpu = None
+    if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        _, cpu, _ = cpu_reference_run(args, case, steps=3, warmup=1, threads=threads, target_step_s=3.0)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, placements),
+            "clv_update_gbs": clv_gbs, "clv_update_gbs_per_gpu": clv_gbs / n_gpus,
+            "algorithmic_bytes_per_step": total_alg_bytes / args.steps,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": int(agg[1].item()), "clocks": clocks,
+            "logl_root0": lh0, "best_placement": int(np.argmax(sweep_lh)),
+        }
+        print(json.dumps(line), flush=True)
+    g.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def dram_traffic_from_profiles():
+    """dram bytes per launch of clv_program_kernel from the committed ncu --set full summary, if any"""
+    p = ROOT / "profiles" / "clv_program_traffic.json"
+    if p.exists():
+        try:
+            return json.loads(p.read_text()).get("dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -256,9 +256,16 @@ typedef struct rdk_stats {
   unsigned long long h2d_bytes;
   unsigned long long d2h_bytes;
   unsigned long long device_bytes;      /* currently allocated                */
+  unsigned long long program_time_ns;   /* device time of the program kernels,
+                                           CUDA events on the partition's
+                                           stream; 0 unless timing is enabled */
+  unsigned long long program_timed;     /* launches included in program_time_ns */
 } rdk_stats_t;
 void rdk_partition_stats(rdk_partition_t *partition, rdk_stats_t *out);
 void rdk_partition_reset_stats(rdk_partition_t *partition);
+/* Bracket every program-kernel launch with CUDA events on the partition's
+ * stream; rdk_partition_stats then reports their summed device time. */
+int rdk_partition_set_timing(rdk_partition_t *partition, int enabled);
 /* tuning knobs (0 = engine default): program-kernel CTAs per SM, threads */
 int rdk_partition_set_launch_config(rdk_partition_t *partition,
                                     int ctas_per_sm, int threads_per_cta,

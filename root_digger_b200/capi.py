@@ -58,7 +58,8 @@ class PartitionStruct(C.Structure):
 class Stats(C.Structure):
     _fields_ = [(n, C.c_ulonglong) for n in (
         "kernel_launches", "program_launches", "pmatrix_launches", "reduce_launches", "clv_ops",
-        "root_evals", "pmatrices", "algorithmic_bytes", "h2d_bytes", "d2h_bytes", "device_bytes")]
+        "root_evals", "pmatrices", "algorithmic_bytes", "h2d_bytes", "d2h_bytes", "device_bytes",
+        "program_time_ns", "program_timed")]
 
     def asdict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
@@ -138,6 +139,7 @@ def load_engine() -> C.CDLL:
     L.rdk_partition_reset_stats.argtypes = [_pp]
     L.rdk_partition_reset_stats.restype = None
     L.rdk_partition_set_launch_config.argtypes = [_pp, C.c_int, C.c_int, C.c_int]
+    L.rdk_partition_set_timing.argtypes = [_pp, C.c_int]
     L.rdk_set_device.argtypes = [C.c_int]
     _engine_lib = L
     return L
@@ -315,6 +317,10 @@ class Partition:
 
     def set_launch_config(self, ctas_per_sm=0, threads=0, elems=0):
         if self.L.rdk_partition_set_launch_config(self.p, ctas_per_sm, threads, elems) != RDK_SUCCESS:
+            raise EngineError(_err(self.L))
+
+    def set_timing(self, on: bool = True):
+        if self.L.rdk_partition_set_timing(self.p, 1 if on else 0) != RDK_SUCCESS:
             raise EngineError(_err(self.L))
 
     def get_clv(self, idx: int) -> np.ndarray:

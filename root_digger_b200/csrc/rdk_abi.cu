@@ -167,6 +167,11 @@ struct Engine {
   // launch config
   int ctas_per_sm = 0, threads = 0, elems = 0;
 
+  // optional per-launch timing of the program kernel (bench / profiling)
+  bool                                            timing = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
+  size_t                                          ev_used = 0;
+
   rdk_stats_t stats{};
   std::mutex  mu;
 };
@@ -237,6 +242,32 @@ int ensure_clv(Engine *e, unsigned buf) {
   e->slab_cur += e->clv_elems ? e->clv_elems : 4;
   e->slab_left -= 1;
   return RDK_SUCCESS;
+}
+
+// ---- program-kernel timing ----------------------------------------------------
+// fold the recorded event pairs into the stats (waits for them to complete)
+void harvest_events(Engine *e) {
+  for (size_t i = 0; i < e->ev_used; ++i) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(e->ev_pool[i].second) == cudaSuccess &&
+        cudaEventElapsedTime(&ms, e->ev_pool[i].first, e->ev_pool[i].second) == cudaSuccess) {
+      e->stats.program_time_ns += (unsigned long long)((double)ms * 1e6 + 0.5);
+      e->stats.program_timed++;
+    }
+  }
+  e->ev_used = 0;
+}
+
+std::pair<cudaEvent_t, cudaEvent_t> *next_event_pair(Engine *e) {
+  if (e->ev_used == e->ev_pool.size()) {
+    if (e->ev_pool.size() >= 256) harvest_events(e);
+    else {
+      cudaEvent_t a = nullptr, b = nullptr;
+      if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return nullptr;
+      e->ev_pool.emplace_back(a, b);
+    }
+  }
+  return &e->ev_pool[e->ev_used++];
 }
 
 // ---- launches --------------------------------------------------------------
@@ -368,6 +399,8 @@ int flush(rdk_partition_t *p) {
     if (E == 3) E = 2;
     int max_grid = (int)((n_witer + (threads / 32) - 1) / (threads / 32));
     grid = std::max(1, std::min(grid, max_grid));
+    std::pair<cudaEvent_t, cudaEvent_t> *ev = e->timing ? next_event_pair(e) : nullptr;
+    if (ev) CUDA_TRY(cudaEventRecord(ev->first, e->stream));
     switch (e->K) {
       case 1: if (!launch_program<1>(a, grid, threads, E, e->stream)) return RDK_FAILURE; break;
       case 2: if (!launch_program<2>(a, grid, threads, E, e->stream)) return RDK_FAILURE; break;
@@ -378,6 +411,7 @@ int flush(rdk_partition_t *p) {
       default: return fail(RDK_ERROR_PARAM, "rate_cats must divide 32");
     }
     CUDA_TRY(cudaGetLastError());
+    if (ev) CUDA_TRY(cudaEventRecord(ev->second, e->stream));
     e->stats.kernel_launches++;
     e->stats.program_launches++;
   }
@@ -698,6 +732,10 @@ extern "C" void rdk_partition_destroy(rdk_partition_t *p) {
     cudaFree(e->ring.d);
     if (e->ring.h) cudaFreeHost(e->ring.h);
     if (e->h_results) cudaFreeHost(e->h_results);
+    for (auto &pr : e->ev_pool) {
+      cudaEventDestroy(pr.first);
+      cudaEventDestroy(pr.second);
+    }
     if (e->stream && e->own_stream) cudaStreamDestroy(e->stream);
     delete e;
   }
@@ -1228,6 +1266,8 @@ extern "C" int rdk_get_pmatrix(rdk_partition_t *p, unsigned int matrix_index, do
 extern "C" void rdk_partition_stats(rdk_partition_t *p, rdk_stats_t *out) {
   Engine *e = eng(p);
   std::lock_guard<std::mutex> lk(e->mu);
+  cudaSetDevice(e->device);
+  harvest_events(e);
   *out = e->stats;
 }
 
@@ -1235,8 +1275,19 @@ extern "C" void rdk_partition_reset_stats(rdk_partition_t *p) {
   Engine *e = eng(p);
   std::lock_guard<std::mutex> lk(e->mu);
   unsigned long long dev = e->stats.device_bytes;
+  cudaSetDevice(e->device);
+  harvest_events(e);
   memset(&e->stats, 0, sizeof(e->stats));
   e->stats.device_bytes = dev;
+}
+
+extern "C" int rdk_partition_set_timing(rdk_partition_t *p, int enabled) {
+  Engine *e = eng(p);
+  std::lock_guard<std::mutex> lk(e->mu);
+  CUDA_TRY(cudaSetDevice(e->device));
+  harvest_events(e);
+  e->timing = enabled != 0;
+  return RDK_SUCCESS;
 }
 
 extern "C" int rdk_partition_set_launch_config(rdk_partition_t *p, int ctas_per_sm,

@@ -715,6 +715,11 @@ bool rooted_tree_t::find_path_recurse(unode_t *n1, unode_t *n2) {
 // src/tree.cpp:572-657: re-orient only the CLVs between the old and new root
 rooted_tree_t::op_bundle_t
 rooted_tree_t::generate_root_update_operations(const root_location_t &new_root) {
+  // the reference dereferences the current root edge unconditionally (UB on a tree that
+  // was never rooted); here that is an error the caller can see
+  if (!rooted() || _current_rl.edge == nullptr)
+    throw std::runtime_error("generate_root_update_operations: the tree has no current root "
+                             "(call generate_operations / root_by first)");
   if (new_root.edge == _current_rl.edge || new_root.edge == _current_rl.edge->back) return {};
 
   auto old_root = _current_rl;
