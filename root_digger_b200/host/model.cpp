@@ -261,13 +261,18 @@ double model_t::compute_lh(const root_location_t &root_location) {
   bool new_root = root_location != _tree.root_location();
   GENERATE_AND_UNPACK_OPS(_tree, root_location, ops, pmatrix_indices, branch_lengths);
   auto   updated = update_pmatrices(pmatrix_indices, branch_lengths);
-  double lh = 0.0;
-#pragma omp parallel for reduction(+ : lh)
+  // The reference sums the partitions with an OpenMP reduction (src/model.cpp:397), whose
+  // association order depends on the thread count; here the per-partition terms are added
+  // in partition order so that the result is reproducible on any host.
+  std::vector<double> part_lh(_partitions.size(), 0.0);
+#pragma omp parallel for
   for (size_t i = 0; i < _partitions.size(); ++i) {
     if (new_root || updated[i]) rdk_update_clvs(_partitions[i], ops.data(), (unsigned)ops.size());
-    lh += rdk_compute_root_loglikelihood(_partitions[i], _tree.root_clv_index(),
-                                         _tree.root_scaler_index(), _param_indicies[i].data(), nullptr);
+    part_lh[i] = rdk_compute_root_loglikelihood(_partitions[i], _tree.root_clv_index(),
+                                                _tree.root_scaler_index(), _param_indicies[i].data(), nullptr);
   }
+  double lh = 0.0;
+  for (double v : part_lh) lh += v;
   return lh;
 }
 
@@ -277,21 +282,24 @@ double model_t::compute_lh_root(const root_location_t &root) {
   rdk_operation_t           op = std::get<0>(result);
   std::vector<unsigned int> matrix_indices = std::move(std::get<1>(result));
   std::vector<double>       branch_lengths = std::move(std::get<2>(result));
-  double                    lh = 0.0;
   bool                      failed = false;
-#pragma omp parallel for reduction(+ : lh)
+  std::vector<double>       part_lh(_partitions.size(), 0.0);  // summed in partition order (see compute_lh)
+#pragma omp parallel for
   for (size_t i = 0; i < _partitions.size(); ++i) {
     int rc = rdk_update_prob_matrices(_partitions[i], _param_indicies[i].data(), matrix_indices.data(),
                                       branch_lengths.data(), (unsigned)matrix_indices.size());
     if (rc == RDK_FAILURE) {
+#pragma omp atomic write
       failed = true;
       continue;
     }
     rdk_update_clvs(_partitions[i], &op, 1);
-    lh += rdk_compute_root_loglikelihood(_partitions[i], _tree.root_clv_index(),
-                                         _tree.root_scaler_index(), _param_indicies[i].data(), nullptr);
+    part_lh[i] = rdk_compute_root_loglikelihood(_partitions[i], _tree.root_clv_index(),
+                                                _tree.root_scaler_index(), _param_indicies[i].data(), nullptr);
   }
   if (failed) throw std::runtime_error(engine_error());
+  double lh = 0.0;
+  for (double v : part_lh) lh += v;
   if (std::isnan(lh)) throw std::runtime_error("lh at root is not a number: " + std::to_string(lh));
   return lh;
 }
