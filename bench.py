@@ -273,13 +273,17 @@ def run_ours(args):
     off, cnt = shards[rank]
     sl = slice(off, off + cnt)
 
-    comm_id = None
-    if world > 1:
+    def fresh_comm_id():
+        """a new 128-byte NCCL unique id from rank 0 (one per communicator), shipped with torch.distributed"""
+        if world == 1:
+            return None
         idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
             idt = torch.tensor(list(capi.comm_unique_id()), dtype=torch.uint8, device="cuda")
         dist.broadcast(idt, 0)
-        comm_id = bytes(idt.cpu().tolist())
+        return bytes(idt.cpu().tolist())
+
+    comm_id = fresh_comm_id()
 
     g = Partition(n, cnt, K, device=local)
     g.set_stream(torch.cuda.current_stream().cuda_stream)
@@ -357,7 +361,7 @@ def run_ours(args):
         tree = RootedTree(case.newick)
         aln = {l: s[sl] for l, s in case.aln.items()}
         m = Model(tree, aln, K, site_offset=off if world > 1 else 0, global_sites=S if world > 1 else 0,
-                  nranks=world, rank=rank, comm_id=comm_id if world > 1 else None)
+                  nranks=world, rank=rank, comm_id=fresh_comm_id())
         m.initialize_partitions()
         m.set_params(rates=case.rates, freqs=case.freqs)
         part = C.cast(m.L.rdh_model_partition(m.h, 0), C.POINTER(capi.PartitionStruct))
