@@ -308,7 +308,7 @@ int launch_pmatrices(rdk_partition_t *p) {
 template <int K, int E, int MAXT, int MINB>
 int launch_program_inst(const ProgArgs &a, int grid, int threads, cudaStream_t st) {
   // shared memory: program window + double-buffered P / tip tables of both children
-  const size_t smem = sizeof(Instr) * kProgWindow + sizeof(double) * 2 * 2 * 64 * K;
+  const size_t smem = sizeof(Instr) * kProgWindow + sizeof(double) * 2 * 2 * kTabDoubles * K + 16;
   static bool  configured = false;  // per template instantiation
   if (!configured) {
     cudaError_t err = cudaFuncSetAttribute(clv_program_kernel<K, E, MAXT, MINB>,
@@ -353,6 +353,31 @@ int ensure_partials(Engine *e, unsigned slots, unsigned stride) {
   return RDK_SUCCESS;
 }
 
+// pre-decode, per instruction, what the kernel would otherwise find out by comparing
+// pointers at run time: which operands are forwarded in registers from the previous
+// instruction and which scaler counts have to be loaded.  The first instruction of a
+// shared-memory window never forwards (its operands are loaded from memory).
+void finalize_program(std::vector<Instr> &prog) {
+  const unsigned decoded = kFwd1 | kFwd2 | kLdS1 | kLdS2 | kFwdS1 | kFwdS2 | kEvalScaler;
+  for (size_t i = 0; i < prog.size(); ++i) {
+    Instr &in = prog[i];
+    in.flags &= ~decoded;
+    const bool   first = (i % kProgWindow) == 0;
+    const Instr *pv = first ? nullptr : &prog[i - 1];
+    const double   *fwd_clv = (pv && (pv->flags & kWrite)) ? pv->parent : nullptr;
+    const unsigned *fwd_scale = (pv && (pv->flags & kWrite)) ? pv->pscale : nullptr;
+    const bool load_only = (in.flags & kLoadOnly) != 0;
+    if (!(in.flags & kTip1) && fwd_clv && in.c1 == fwd_clv) in.flags |= kFwd1;
+    if (!load_only && !(in.flags & kTip2) && fwd_clv && in.c2 == fwd_clv) in.flags |= kFwd2;
+    if (in.c1scale) in.flags |= (fwd_scale && in.c1scale == fwd_scale) ? kFwdS1 : kLdS1;
+    if (!load_only && in.c2scale) in.flags |= (fwd_scale && in.c2scale == fwd_scale) ? kFwdS2 : kLdS2;
+    if (in.flags & kEval) {
+      const bool has_scaler = load_only ? (in.c1scale != nullptr) : ((in.flags & kScale) != 0);
+      if (has_scaler) in.flags |= kEvalScaler;
+    }
+  }
+}
+
 // launch recorded P-matrix work and the recorded program (no host sync)
 int flush(rdk_partition_t *p) {
   Engine *e = eng(p);
@@ -378,6 +403,7 @@ int flush(rdk_partition_t *p) {
     a.partials = e->d_partials;
   }
   a.persite = e->want_persite ? e->d_persite : nullptr;
+  finalize_program(e->pend_prog);
   if (a.n_instr <= kProgInline) {
     for (int i = 0; i < a.n_instr; ++i) a.inl[i] = e->pend_prog[i];
   } else {
@@ -1253,13 +1279,13 @@ extern "C" int rdk_get_pmatrix(rdk_partition_t *p, unsigned int matrix_index, do
   CUDA_TRY(cudaSetDevice(e->device));
   if (matrix_index >= e->prob_matrices) return fail(RDK_ERROR_PARAM, "matrix index out of range");
   if (!flush(p)) return RDK_FAILURE;
-  std::vector<double> tmp((size_t)16 * e->K);
+  std::vector<double> tmp((size_t)kPTabDoubles * e->K);
   CUDA_TRY(cudaMemcpyAsync(tmp.data(), e->d_pool + (size_t)e->pm_map[matrix_index] * e->K * kSlotDoubles,
-                           sizeof(double) * 16 * e->K, cudaMemcpyDeviceToHost, e->stream));
+                           sizeof(double) * kPTabDoubles * e->K, cudaMemcpyDeviceToHost, e->stream));
   CUDA_TRY(cudaStreamSynchronize(e->stream));
-  // device layout [i*4+j][cat] -> corax layout [cat][i][j]
+  // device layout [cat][18 (16 used)] -> corax layout [cat][i][j]
   for (unsigned k = 0; k < e->K; ++k)
-    for (int ij = 0; ij < 16; ++ij) out[(size_t)k * 16 + ij] = tmp[(size_t)ij * e->K + k];
+    for (int ij = 0; ij < 16; ++ij) out[(size_t)k * 16 + ij] = tmp[(size_t)k * kPTabDoubles + ij];
   return RDK_SUCCESS;
 }
 

@@ -328,13 +328,21 @@ __host__ __device__ __forceinline__ unsigned tip_code_of_mask(unsigned mask) {
 // ---------------------------------------------------------------------------
 // pmat_expm_nonrev: one thread per (branch entry, rate category).
 // Replaces corax_update_prob_matrices.  A pool slot holds, for one branch,
-//   P : [i*4+j][cat]            16*K doubles  (the transition matrices)
-//   T : [i][tip code][cat]      64*K doubles  (tip lookup table)
-// T[i][code][k] = ((P_i0 c_0 + P_i1 c_1) + P_i2 c_2) + P_i3 c_3 with c the 0/1
+//   P : [cat][i*4+j (+2 pad)]   18*K doubles  (the transition matrices; the pad
+//                               makes a category's row start 144 B apart so that the
+//                               128-bit shared-memory reads of a warp's K categories
+//                               fall into distinct banks)
+//   T : [tip code][cat][i]      64*K doubles  (tip lookup table)
+// T[code][k][i] = ((P_i0 c_0 + P_i1 c_1) + P_i2 c_2) + P_i3 c_3 with c the 0/1
 // vector of the tip state: exactly the expression a tip child contributes to a
 // CLV update, evaluated once per branch instead of once per site.
+// The slot layout IS the shared-memory layout: the program kernel moves P or T
+// with one bulk async copy.
 // ---------------------------------------------------------------------------
-constexpr int kSlotDoubles = 80;  // per category
+constexpr int kPTabDoubles = 18;    // per category
+constexpr int kTipTabDoubles = 64;  // per category
+constexpr int kTabDoubles = 64;     // per category: the larger of the two
+constexpr int kSlotDoubles = kPTabDoubles + kTipTabDoubles;  // per category
 
 struct PmatEntry {
   unsigned slot;  // physical slot in the P-matrix pool
@@ -368,9 +376,11 @@ __global__ void __launch_bounds__(64) pmat_expm_nonrev_kernel(const __grid_const
   double c = ddiv(dmul(a.rates[k], ent.t), dsub(1.0, a.pinv));
   for (int i = 0; i < 16; ++i) A[i] = dmul(Q[i], c);
   expm4(A, E);
-  double* out = a.pool + (size_t)ent.slot * a.K * kSlotDoubles + k;
-  for (int i = 0; i < 16; ++i) out[(size_t)i * a.K] = E[i];
-  double* tab = out + (size_t)16 * a.K;
+  double* slot = a.pool + (size_t)ent.slot * a.K * kSlotDoubles;
+  double* out = slot + (size_t)k * kPTabDoubles;
+  for (int i = 0; i < 16; ++i) out[i] = E[i];
+  out[16] = out[17] = 0.0;
+  double* tab = slot + (size_t)a.K * kPTabDoubles;
   for (int i = 0; i < 4; ++i)
     for (unsigned code = 0; code < 16; ++code) {
       unsigned m = tip_mask_of_code(code);
@@ -378,7 +388,7 @@ __global__ void __launch_bounds__(64) pmat_expm_nonrev_kernel(const __grid_const
       x = dadd(x, dmul(E[i * 4 + 1], (m & 2u) ? 1.0 : 0.0));
       x = dadd(x, dmul(E[i * 4 + 2], (m & 4u) ? 1.0 : 0.0));
       x = dadd(x, dmul(E[i * 4 + 3], (m & 8u) ? 1.0 : 0.0));
-      tab[(size_t)(i * 16 + code) * a.K] = x;
+      tab[((size_t)code * a.K + k) * 4 + i] = x;
     }
 }
 
@@ -389,16 +399,15 @@ __global__ void __launch_bounds__(64) pmat_expm_nonrev_kernel(const __grid_const
 // (site, category) element.  Elements are independent of each other (the
 // dependency between a parent CLV and its children is per site), so each warp
 // owns a contiguous range of elements and walks the WHOLE program on it with
-// no block or grid synchronisation: a full post-order traversal (n-1 CLV
+// no grid synchronisation: a full post-order traversal (n-1 CLV
 // operations + the root log-likelihood), a root move, or an entire placement
 // sweep is ONE launch.  Child CLVs produced a few instructions earlier by the
-// same warp are still in L2, so HBM sees each CLV written once and mostly not
-// read back.
+// same warp are still in L2 (or in registers), so HBM sees each CLV written
+// once and mostly not read back.
 //
 // Thread mapping: element e = site*K + k.  Lane l of a warp iteration `it`
 // handles e = 32*it + l, i.e. 32 consecutive 32-byte (4 x fp64) vectors = 1 KiB
-// contiguous per CLV per warp access; k = l % K is fixed per thread (K | 32), so
-// the thread's two 4x4 P-matrices live in registers for E iterations.
+// contiguous per CLV per warp access; k = l % K is fixed per thread (K | 32).
 // ---------------------------------------------------------------------------
 enum : unsigned {
   kTip1 = 1u,      // child1 is a tip: 1 byte per site (4-bit state code)
@@ -408,6 +417,14 @@ enum : unsigned {
   kLoadOnly = 16u, // no CLV arithmetic: parent values := CLV at c1 (root logL of
                    // a stored CLV, corax_compute_root_loglikelihood)
   kScale = 32u,    // parent has a scale buffer: apply 2^256 rescaling
+  // pre-decoded by the host when the program is finalised (finalize_program):
+  kFwd1 = 64u,     // c1 is the CLV the previous instruction produced: take it from registers
+  kFwd2 = 128u,    // same for c2
+  kLdS1 = 256u,    // load child1's scaler counts from memory
+  kLdS2 = 512u,    // load child2's scaler counts from memory
+  kFwdS1 = 1024u,  // child1's scaler is the one the previous instruction produced
+  kFwdS2 = 2048u,  // same for child2
+  kEvalScaler = 4096u,  // the evaluated root has a scale buffer (adds cnt * ln 2^-256)
 };
 
 struct alignas(16) Instr {
@@ -417,7 +434,7 @@ struct alignas(16) Instr {
   unsigned*       pscale;
   const unsigned* c1scale;
   const unsigned* c2scale;
-  const double*   P1;
+  const double*   P1;  // pool slot of child1's branch
   const double*   P2;
   unsigned        flags;
   unsigned        slot;  // eval slot (row of the partial-sum buffer)
@@ -445,11 +462,11 @@ struct d4 {
   double v[4];
 };
 
-__device__ __forceinline__ d4 ld_clv(const double* p) {
+__device__ __forceinline__ d4 ld_clv(const double* base, unsigned e) {
   // 32 B per thread as 2 x 128-bit loads, L2-coherent (ld.global.cg): CLVs are
   // read and written within one launch and never re-read by the same SM soon
   // enough for L1 to help.
-  const double2* q = reinterpret_cast<const double2*>(p);
+  const double2* q = reinterpret_cast<const double2*>(reinterpret_cast<const char*>(base) + (size_t)e * 32u);
   double2        a = __ldcg(q), b = __ldcg(q + 1);
   d4             r;
   r.v[0] = a.x;
@@ -458,164 +475,188 @@ __device__ __forceinline__ d4 ld_clv(const double* p) {
   r.v[3] = b.y;
   return r;
 }
-__device__ __forceinline__ void st_clv(double* p, const d4& x) {
-  double2* q = reinterpret_cast<double2*>(p);
+__device__ __forceinline__ void st_clv(double* base, unsigned e, const d4& x) {
+  double2* q = reinterpret_cast<double2*>(reinterpret_cast<char*>(base) + (size_t)e * 32u);
   __stcg(q, make_double2(x.v[0], x.v[1]));
   __stcg(q + 1, make_double2(x.v[2], x.v[3]));
 }
 
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-  unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem) : "memory");
+// ---- mbarrier + bulk async copy (one elected thread moves a whole table) ----
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
 
 // operands of one instruction for the E elements of a thread
 template <int E>
 struct Operands {
   d4       c1[E], c2[E];  // inner children: the 4 state likelihoods
   unsigned m1[E], m2[E];  // tip children: the state code
-  unsigned cnt[E];        // sum of the children's scaler counts (k == 0 lanes)
+  unsigned cnt[E];        // sum of the children's scaler counts
 };
 
 // Each CTA owns a contiguous range of warp iterations and walks the whole
 // program over it, one "pass" of (warps per CTA x E) iterations at a time.
 //  * the program is staged in shared memory in windows;
-//  * per instruction and child, either the transition matrices P (inner child,
-//    16K doubles) or the tip table T (tip child, 64K doubles) of the child's
-//    branch is prefetched into a shared double buffer with cp.async while the
-//    previous instruction computes; one __syncthreads per instruction keeps the
-//    CTA's warps on the same instruction (needed for this buffer only -- CLV
-//    dependencies are per element and therefore per thread);
+//  * per instruction and child, either the transition matrices P (inner child)
+//    or the tip table T (tip child) of the child's branch is moved into a shared
+//    double buffer by ONE thread with a bulk async copy (cp.async.bulk +
+//    mbarrier) while the previous instruction computes; one __syncthreads per
+//    instruction keeps the CTA's warps on the same instruction (needed for this
+//    buffer and for the duplicate-work tails below -- CLV dependencies are per
+//    element and therefore per thread);
 //  * the global operands of instruction i+1 are loaded into registers BEFORE
 //    the arithmetic of instruction i (software pipelining, two register sets
 //    used in ping-pong), and when a child of i+1 is the CLV instruction i is
 //    producing -- the normal case in a post-order schedule -- it is forwarded in
-//    registers and never re-read.
+//    registers and never re-read (the host pre-decodes this into kFwd*);
+//  * there are no per-element validity predicates: a thread without an element
+//    of its own (tail of the CTA's range, tail of the partition) redundantly
+//    recomputes the last element of the range / the last site and stores the
+//    identical values; only the log-likelihood reduction masks it out.
 template <int K, int E, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) clv_program_kernel(const __grid_constant__ ProgArgs a) {
   static_assert(32 % K == 0, "K must divide the warp size");
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  Instr*  s_prog = reinterpret_cast<Instr*>(smem_raw);
-  double* s_tab = reinterpret_cast<double*>(smem_raw + sizeof(Instr) * kProgWindow);
-  // s_tab[buf][child][64*K]
-  constexpr unsigned kTabDoubles = 64 * K;
+  constexpr unsigned kTabBytes = kTabDoubles * K * 8;  // one child's slice of a table buffer
+  Instr*              s_prog = reinterpret_cast<Instr*>(smem_raw);
+  unsigned char*      s_tab = smem_raw + sizeof(Instr) * kProgWindow;  // [buf][child][kTabBytes]
+  unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_tab + 4 * kTabBytes);  // [buf]
 
   const unsigned tid = threadIdx.x;
   const unsigned lane = tid & 31u;
   const unsigned wib = tid >> 5;
   const unsigned wpb = blockDim.x >> 5;
   const unsigned k = lane % K;
-  const bool     k0 = (k == 0);
   const unsigned gmask = (K == 32) ? 0xffffffffu : (((1u << K) - 1u) << (lane - k));
 
   const unsigned it_begin = (unsigned)(((unsigned long long)a.n_witer * blockIdx.x) / gridDim.x);
   const unsigned it_end = (unsigned)(((unsigned long long)a.n_witer * (blockIdx.x + 1)) / gridDim.x);
+  if (it_end == it_begin) return;  // whole CTA
   const unsigned per_pass = wpb * E;
   const unsigned passes = (it_end - it_begin + per_pass - 1) / per_pass;
-  const bool     single_window = a.n_instr <= kProgWindow;
+  const unsigned last_site = a.nelem / K - 1;
 
-  // stage P or T of both children of `in` into buffer `buf`
+  if (tid == 0) {
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  unsigned phase = 0;  // bit b: parity of the next completion of s_bar[b]
+
+  // one thread: move P or T of both children of `in` into buffer `buf`
   auto prefetch_tables = [&](const Instr& in, unsigned buf) {
     const unsigned fl = in.flags;
-    if (!(fl & kLoadOnly)) {
-      double* dst = s_tab + (size_t)buf * 2 * kTabDoubles;
-      {
-        const double*  src = (fl & kTip1) ? in.P1 + 16 * K : in.P1;
-        const unsigned chunks = (fl & kTip1) ? 32 * K : 8 * K;
-        for (unsigned c = tid; c < chunks; c += blockDim.x) cp_async16(dst + c * 2, src + c * 2);
-      }
-      {
-        const double*  src = (fl & kTip2) ? in.P2 + 16 * K : in.P2;
-        const unsigned chunks = (fl & kTip2) ? 32 * K : 8 * K;
-        for (unsigned c = tid; c < chunks; c += blockDim.x)
-          cp_async16(dst + kTabDoubles + c * 2, src + c * 2);
-      }
+    unsigned long long* bar = &s_bar[buf];
+    if (fl & kLoadOnly) {
+      mbar_arrive(bar);
+      return;
     }
-    cp_async_commit();
+    const unsigned b1 = (fl & kTip1) ? kTipTabDoubles * K * 8 : kPTabDoubles * K * 8;
+    const unsigned b2 = (fl & kTip2) ? kTipTabDoubles * K * 8 : kPTabDoubles * K * 8;
+    mbar_expect_tx(bar, b1 + b2);
+    unsigned char* dst = s_tab + (size_t)buf * 2 * kTabBytes;
+    bulk_g2s(dst, (fl & kTip1) ? in.P1 + kPTabDoubles * K : in.P1, b1, bar);
+    bulk_g2s(dst + kTabBytes, (fl & kTip2) ? in.P2 + kPTabDoubles * K : in.P2, b2, bar);
   };
 
   for (unsigned pass = 0; pass < passes; ++pass) {
-    unsigned it[E], site[E];
-    size_t   off[E];  // element offset in doubles
-    bool     valid[E];
+    unsigned it[E], e[E], site[E];
+    bool     own[E];  // this thread's element is its own (not a duplicate)
 #pragma unroll
     for (int u = 0; u < E; ++u) {
-      it[u] = it_begin + (pass * E + u) * wpb + wib;
-      unsigned e = it[u] * 32u + lane;
-      valid[u] = (it[u] < it_end) && (e < a.nelem);
-      // lanes without an element read element `lane` (always in bounds when the
-      // partition is non-empty; the kernel is not launched otherwise) and never store
-      if (!valid[u]) e = lane < a.nelem ? lane : 0u;
-      site[u] = e / K;
-      off[u] = (size_t)e * 4;
+      unsigned i0 = it_begin + (pass * E + u) * wpb + wib;
+      own[u] = i0 < it_end;
+      it[u] = own[u] ? i0 : it_end - 1;
+      unsigned ee = it[u] * 32u + lane;
+      if (ee >= a.nelem) {
+        own[u] = false;
+        ee = last_site * K + k;
+      }
+      e[u] = ee;
+      site[u] = ee / K;
     }
 
-    // issue the global loads of one instruction's operands; an operand equal to
-    // fwd_clv / fwd_scale (what the previous instruction is writing) is skipped
-    // here and forwarded from registers by the caller
-    auto load_operands = [&](const Instr& in, Operands<E>& o, const void* fwd_clv,
-                             const unsigned* fwd_scale) {
-      const unsigned fl = in.flags;
+    // issue the global loads of one instruction's operands
+    auto load_operands = [&](const Instr& in, unsigned fl, Operands<E>& o) {
       if (fl & kTip1) {
         const unsigned char* t = reinterpret_cast<const unsigned char*>(in.c1);
 #pragma unroll
         for (int u = 0; u < E; ++u) o.m1[u] = __ldg(t + site[u]);
-      } else if (in.c1 != fwd_clv) {
+      } else if (!(fl & kFwd1)) {
         const double* g = reinterpret_cast<const double*>(in.c1);
 #pragma unroll
-        for (int u = 0; u < E; ++u) o.c1[u] = ld_clv(g + off[u]);
+        for (int u = 0; u < E; ++u) o.c1[u] = ld_clv(g, e[u]);
       }
-      if (!(fl & kLoadOnly)) {
-        if (fl & kTip2) {
-          const unsigned char* t = reinterpret_cast<const unsigned char*>(in.c2);
+      if (fl & kTip2) {
+        const unsigned char* t = reinterpret_cast<const unsigned char*>(in.c2);
 #pragma unroll
-          for (int u = 0; u < E; ++u) o.m2[u] = __ldg(t + site[u]);
-        } else if (in.c2 != fwd_clv) {
-          const double* g = reinterpret_cast<const double*>(in.c2);
+        for (int u = 0; u < E; ++u) o.m2[u] = __ldg(t + site[u]);
+      } else if (!(fl & (kFwd2 | kLoadOnly))) {
+        const double* g = reinterpret_cast<const double*>(in.c2);
 #pragma unroll
-          for (int u = 0; u < E; ++u) o.c2[u] = ld_clv(g + off[u]);
-        }
+        for (int u = 0; u < E; ++u) o.c2[u] = ld_clv(g, e[u]);
       }
 #pragma unroll
       for (int u = 0; u < E; ++u) o.cnt[u] = 0;
-      const unsigned* s1 = in.c1scale;
-      const unsigned* s2 = in.c2scale;
-      if (k0) {
-        if (s1 && s1 != fwd_scale) {
+      if (fl & kLdS1) {
+        const unsigned* s1 = in.c1scale;
 #pragma unroll
-          for (int u = 0; u < E; ++u) o.cnt[u] = __ldcg(s1 + site[u]);
-        }
-        if (s2 && s2 != fwd_scale) {
+        for (int u = 0; u < E; ++u) o.cnt[u] = __ldcg(s1 + site[u]);
+      }
+      if (fl & kLdS2) {
+        const unsigned* s2 = in.c2scale;
 #pragma unroll
-          for (int u = 0; u < E; ++u) o.cnt[u] += __ldcg(s2 + site[u]);
-        }
+        for (int u = 0; u < E; ++u) o.cnt[u] += __ldcg(s2 + site[u]);
       }
     };
 
     // one instruction: `cur` holds its operands, the operands of the next
-    // instruction are loaded into `nxt`
+    // instruction are loaded into `nxt`.  first == first instruction of a window
+    // (its operands were loaded without forwarding).
     auto step = [&](int ii, int wn, Operands<E>& cur, Operands<E>& nxt) {
-      cp_async_wait_all();
-      __syncthreads();  // tables(ii) visible; every warp has finished instruction ii-1
+      __syncthreads();  // every warp has finished instruction ii-1
       const bool more = ii + 1 < wn;
-      if (more) prefetch_tables(s_prog[ii + 1], (unsigned)(ii + 1) & 1u);
+      const unsigned buf = (unsigned)ii & 1u;
+      if (more && tid == 0) prefetch_tables(s_prog[ii + 1], buf ^ 1u);
       const Instr&   in = s_prog[ii];
       const unsigned fl = in.flags;
-      const double*  tab = s_tab + (size_t)((unsigned)ii & 1u) * 2 * kTabDoubles;
-
-      const void*     fwd_clv = (fl & kWrite) ? (const void*)in.parent : nullptr;
-      const unsigned* fwd_scale = (fl & kWrite) ? in.pscale : nullptr;
-      bool            f1 = false, f2 = false, fs1 = false, fs2 = false;
+      unsigned       nfl = 0;
       if (more) {
         const Instr& nx = s_prog[ii + 1];
-        f1 = fwd_clv && nx.c1 == fwd_clv;
-        f2 = fwd_clv && !(nx.flags & kLoadOnly) && nx.c2 == fwd_clv;
-        fs1 = fwd_scale && nx.c1scale == fwd_scale;
-        fs2 = fwd_scale && nx.c2scale == fwd_scale;
-        load_operands(nx, nxt, fwd_clv, fwd_scale);
+        nfl = nx.flags;
+        load_operands(nx, nfl, nxt);
       }
+      mbar_wait(&s_bar[buf], (phase >> buf) & 1u);  // tables(ii) have landed
+      phase ^= 1u << buf;
+      const unsigned char* tab1 = s_tab + (size_t)buf * 2 * kTabBytes;
+      const unsigned char* tab2 = tab1 + kTabBytes;
 
       d4 v[E];
       if (fl & kLoadOnly) {
@@ -625,53 +666,62 @@ __global__ void __launch_bounds__(MAXT, MINB) clv_program_kernel(const __grid_co
         // child 1
         if (fl & kTip1) {
 #pragma unroll
-          for (int u = 0; u < E; ++u)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) v[u].v[i] = tab[(i * 16 + cur.m1[u]) * K + k];
+          for (int u = 0; u < E; ++u) {
+            const double2* t = reinterpret_cast<const double2*>(tab1 + (cur.m1[u] * K + k) * 32u);
+            const double2  lo = t[0], hi = t[1];
+            v[u].v[0] = lo.x;
+            v[u].v[1] = lo.y;
+            v[u].v[2] = hi.x;
+            v[u].v[3] = hi.y;
+          }
         } else {
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const double p = tab[(i * 4 + j) * K + k];
-#pragma unroll
-              for (int u = 0; u < E; ++u) {
-                const double t = dmul(p, cur.c1[u].v[j]);
-                v[u].v[i] = (j == 0) ? t : dadd(v[u].v[i], t);
-              }
-            }
-        }
-        // child 2
-        const double* tab2 = tab + kTabDoubles;
-        if (fl & kTip2) {
-#pragma unroll
-          for (int u = 0; u < E; ++u)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) v[u].v[i] = dmul(v[u].v[i], tab2[(i * 16 + cur.m2[u]) * K + k]);
-        } else {
+          const double2* p = reinterpret_cast<const double2*>(tab1 + k * (kPTabDoubles * 8));
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            double y[E];
+            const double2 p01 = p[i * 2], p23 = p[i * 2 + 1];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const double p = tab2[(i * 4 + j) * K + k];
-#pragma unroll
-              for (int u = 0; u < E; ++u) {
-                const double t = dmul(p, cur.c2[u].v[j]);
-                y[u] = (j == 0) ? t : dadd(y[u], t);
-              }
+            for (int u = 0; u < E; ++u) {
+              double s = dmul(p01.x, cur.c1[u].v[0]);
+              s = dadd(s, dmul(p01.y, cur.c1[u].v[1]));
+              s = dadd(s, dmul(p23.x, cur.c1[u].v[2]));
+              s = dadd(s, dmul(p23.y, cur.c1[u].v[3]));
+              v[u].v[i] = s;
             }
+          }
+        }
+        // child 2
+        if (fl & kTip2) {
 #pragma unroll
-            for (int u = 0; u < E; ++u) v[u].v[i] = dmul(v[u].v[i], y[u]);
+          for (int u = 0; u < E; ++u) {
+            const double2* t = reinterpret_cast<const double2*>(tab2 + (cur.m2[u] * K + k) * 32u);
+            const double2  lo = t[0], hi = t[1];
+            v[u].v[0] = dmul(v[u].v[0], lo.x);
+            v[u].v[1] = dmul(v[u].v[1], lo.y);
+            v[u].v[2] = dmul(v[u].v[2], hi.x);
+            v[u].v[3] = dmul(v[u].v[3], hi.y);
+          }
+        } else {
+          const double2* p = reinterpret_cast<const double2*>(tab2 + k * (kPTabDoubles * 8));
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const double2 p01 = p[i * 2], p23 = p[i * 2 + 1];
+#pragma unroll
+            for (int u = 0; u < E; ++u) {
+              double s = dmul(p01.x, cur.c2[u].v[0]);
+              s = dadd(s, dmul(p01.y, cur.c2[u].v[1]));
+              s = dadd(s, dmul(p23.x, cur.c2[u].v[2]));
+              s = dadd(s, dmul(p23.y, cur.c2[u].v[3]));
+              v[u].v[i] = dmul(v[u].v[i], s);
+            }
           }
         }
       }
       if (fl & kScale) {
 #pragma unroll
         for (int u = 0; u < E; ++u) {
-          bool small = valid[u] && (v[u].v[0] < RDK_SCALE_THRESHOLD) && (v[u].v[1] < RDK_SCALE_THRESHOLD) &&
-                       (v[u].v[2] < RDK_SCALE_THRESHOLD) && (v[u].v[3] < RDK_SCALE_THRESHOLD);
-          unsigned m = __ballot_sync(0xffffffffu, small);
+          const bool small = (v[u].v[0] < RDK_SCALE_THRESHOLD) && (v[u].v[1] < RDK_SCALE_THRESHOLD) &&
+                             (v[u].v[2] < RDK_SCALE_THRESHOLD) && (v[u].v[3] < RDK_SCALE_THRESHOLD);
+          const unsigned m = __ballot_sync(0xffffffffu, small);
           if ((m & gmask) == gmask) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) v[u].v[i] = dmul(v[u].v[i], RDK_SCALE_FACTOR);
@@ -680,37 +730,33 @@ __global__ void __launch_bounds__(MAXT, MINB) clv_program_kernel(const __grid_co
         }
       }
       if (fl & kWrite) {
-        double*   par = in.parent;
+        double* par = in.parent;
+#pragma unroll
+        for (int u = 0; u < E; ++u) st_clv(par, e[u], v[u]);
         unsigned* ps = in.pscale;
+        if (ps && k == 0) {
 #pragma unroll
-        for (int u = 0; u < E; ++u)
-          if (valid[u]) st_clv(par + off[u], v[u]);
-        if (k0 && ps) {
-#pragma unroll
-          for (int u = 0; u < E; ++u)
-            if (valid[u]) __stcg(ps + site[u], cur.cnt[u]);
+          for (int u = 0; u < E; ++u) __stcg(ps + site[u], cur.cnt[u]);
         }
       }
       // register forwarding into the operands of instruction ii+1
-      if (f1) {
+      if (nfl & kFwd1) {
 #pragma unroll
         for (int u = 0; u < E; ++u) nxt.c1[u] = v[u];
       }
-      if (f2) {
+      if (nfl & kFwd2) {
 #pragma unroll
         for (int u = 0; u < E; ++u) nxt.c2[u] = v[u];
       }
-      if (fs1) {
+      if (nfl & kFwdS1) {
 #pragma unroll
         for (int u = 0; u < E; ++u) nxt.cnt[u] += cur.cnt[u];
       }
-      if (fs2) {
+      if (nfl & kFwdS2) {
 #pragma unroll
         for (int u = 0; u < E; ++u) nxt.cnt[u] += cur.cnt[u];
       }
       if (fl & kEval) {
-        // scaler term only when a scale buffer is attached to the root
-        const bool has_scaler = (fl & kLoadOnly) ? (in.c1scale != nullptr) : ((fl & kScale) != 0);
 #pragma unroll
         for (int u = 0; u < E; ++u) {
           double t = dmul(a.pi[0], v[u].v[0]);
@@ -724,30 +770,30 @@ __global__ void __launch_bounds__(MAXT, MINB) clv_program_kernel(const __grid_co
             term = dadd(term, dmul(a.w[kk], tk));
           }
           double l = 0.0;
-          if (valid[u] && k0) {
+          if (k == 0 && it[u] * 32u + lane < a.nelem) {
             l = rd_log(term);
-            if (has_scaler) l = dadd(l, dmul((double)cur.cnt[u], RDK_LOG_SCALE_THRESHOLD));
+            if (fl & kEvalScaler) l = dadd(l, dmul((double)cur.cnt[u], RDK_LOG_SCALE_THRESHOLD));
             l = dmul(l, (double)__ldg(a.weights + site[u]));
             if (a.persite && in.slot == 0) a.persite[site[u]] = l;
           }
           // canonical tree over the 32/K sites of this warp iteration
 #pragma unroll
           for (int off2 = K; off2 < 32; off2 <<= 1) l = dadd(l, __shfl_xor_sync(0xffffffffu, l, off2));
-          if (lane == 0 && it[u] < it_end) a.partials[(size_t)in.slot * a.partial_stride + it[u]] = l;
+          if (lane == 0) a.partials[(size_t)in.slot * a.partial_stride + it[u]] = l;
         }
       }
     };
 
     for (int w0 = 0; w0 < a.n_instr; w0 += kProgWindow) {
       const int wn = min(kProgWindow, a.n_instr - w0);
-      if (!(single_window && pass > 0)) {
-        __syncthreads();  // everyone is done with the previous window
+      __syncthreads();  // everyone is done with the previous window / pass (program and tables)
+      if (a.n_instr > kProgWindow || pass == 0) {
         const int4* src = reinterpret_cast<const int4*>(a.n_instr <= kProgInline ? a.inl : a.prog + w0);
         int4*       dst = reinterpret_cast<int4*>(s_prog);
         for (unsigned c = tid; c < (unsigned)wn * (sizeof(Instr) / 16); c += blockDim.x) dst[c] = src[c];
         __syncthreads();
       }
-      prefetch_tables(s_prog[0], 0);
+      if (tid == 0) prefetch_tables(s_prog[0], 0);
       Operands<E> opA, opB;
 #pragma unroll
       for (int u = 0; u < E; ++u) {
@@ -756,7 +802,8 @@ __global__ void __launch_bounds__(MAXT, MINB) clv_program_kernel(const __grid_co
         opA.m1[u] = opA.m2[u] = opB.m1[u] = opB.m2[u] = 15u;  // code 15: all-zero table row
         opA.cnt[u] = opB.cnt[u] = 0;
       }
-      load_operands(s_prog[0], opA, nullptr, nullptr);
+      // the first instruction of a window never carries kFwd* (finalize_program)
+      load_operands(s_prog[0], s_prog[0].flags, opA);
       int ii = 0;
       for (; ii + 1 < wn; ii += 2) {
         step(ii, wn, opA, opB);
