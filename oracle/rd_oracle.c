@@ -5,11 +5,14 @@
  * restatement of the libpll-2/coraxlib algorithm as documented in SURVEY.md
  * Appendix A, anchored on RootDigger's call sites (cited per function).
  *
- * Build: gcc -O2 -ffp-contract=off -fno-fast-math (see oracle/Makefile).
- * -ffp-contract=off is part of the arithmetic specification: every +,-,*,/ is
- * individually rounded (no FMA), in the order written here.  The CUDA engine
- * follows the same order with __dmul_rn/__dadd_rn so that ENGINE mode results
- * can be compared bit for bit.
+ * Build: gcc -O3 -march=x86-64-v3 -ffp-contract=off -fno-fast-math (see
+ * oracle/Makefile).  Arithmetic specification v2: the 4x4 mat-vec of the CLV
+ * update and the dot products of the root log-likelihood are explicit fma()
+ * chains (coraxlib's AVX2 kernels are FMA kernels too); every other +,-,*,/ is
+ * individually rounded (-ffp-contract=off: no implicit contraction), in the
+ * order written here.  The CUDA engine follows the same order with
+ * __fma_rn/__dmul_rn/__dadd_rn so that ENGINE mode results can be compared bit
+ * for bit.
  */
 #include "rd_oracle.h"
 
@@ -491,14 +494,17 @@ static inline void clv_site(const double *P1, const double *P2,
     const double *p1 = P1 + k * 16, *p2 = P2 + k * 16;
     const double *a = c1 + k * 4, *b = c2 + k * 4;
     for (int i = 0; i < 4; ++i) {
+      /* fused multiply-add chain, j ascending (arithmetic spec v2: the 4x4
+       * mat-vec and the root dot products are FMA chains, as in coraxlib's
+       * AVX2/FMA kernels; everything else is individually rounded) */
       double x = p1[i * 4 + 0] * a[0];
-      x = x + p1[i * 4 + 1] * a[1];
-      x = x + p1[i * 4 + 2] * a[2];
-      x = x + p1[i * 4 + 3] * a[3];
+      x = fma(p1[i * 4 + 1], a[1], x);
+      x = fma(p1[i * 4 + 2], a[2], x);
+      x = fma(p1[i * 4 + 3], a[3], x);
       double y = p2[i * 4 + 0] * b[0];
-      y = y + p2[i * 4 + 1] * b[1];
-      y = y + p2[i * 4 + 2] * b[2];
-      y = y + p2[i * 4 + 3] * b[3];
+      y = fma(p2[i * 4 + 1], b[1], y);
+      y = fma(p2[i * 4 + 2], b[2], y);
+      y = fma(p2[i * 4 + 3], b[3], y);
       double v = x * y;
       out[k * 4 + i] = v;
       if (!(v < RDO_SCALE_THRESHOLD)) small = 0;
@@ -650,13 +656,13 @@ static inline double site_term(const rdo_partition_t *p, const double *clv,
   for (unsigned k = 0; k < K; ++k) {
     const double *c = clv + ((size_t)s * K + k) * 4;
     double        t = pi[0] * c[0];
-    t = t + pi[1] * c[1];
-    t = t + pi[2] * c[2];
-    t = t + pi[3] * c[3];
+    t = fma(pi[1], c[1], t);
+    t = fma(pi[2], c[2], t);
+    t = fma(pi[3], c[3], t);
     if (k == 0)
       term = p->rate_weights[0] * t;
     else
-      term = term + p->rate_weights[k] * t;
+      term = fma(p->rate_weights[k], t, term);
   }
   return term;
 }

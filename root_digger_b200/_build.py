@@ -69,6 +69,8 @@ def build_engine(force: bool = False, verbose: bool = False) -> Path:
     cmd = [_nvcc(), *NVCC_ARCH, "-lineinfo", "-O3", "-std=c++17", "--fmad=false",
            "-ccbin", _cxx(),
            "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall", "-shared", "-o", out, *srcs, "-ldl"]
+    for d in os.environ.get("RDK_NVCC_DEFINES", "").split():
+        cmd.insert(1, "-D" + d)  # experiment switches (RDK_KSLOW=0 ...)
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     log = _run(cmd)

@@ -78,7 +78,9 @@ def _ptr(a, t):
 
 
 def engine_lib_path() -> Path:
-    return _build.LIBDIR / "librdk_b200.so"
+    import os
+    override = os.environ.get("RDK_ENGINE_LIB")  # kernel experiments: a variant build of the same ABI
+    return Path(override) if override else _build.LIBDIR / "librdk_b200.so"
 
 
 def load_engine() -> C.CDLL:

@@ -307,14 +307,16 @@ int launch_pmatrices(rdk_partition_t *p) {
 
 template <int K, int E, int MAXT, int MINB>
 int launch_program_inst(const ProgArgs &a, int grid, int threads, cudaStream_t st) {
-  // shared memory: program window + double-buffered P / tip tables of both children
-  const size_t smem = sizeof(Instr) * kProgWindow + sizeof(double) * 2 * 2 * kTabDoubles * K + 16;
-  static bool  configured = false;  // per template instantiation
-  if (!configured) {
+  // shared memory: program window + per warp: double-buffered P / tip tables of both
+  // children and two mbarriers
+  const int    warps = threads / 32;
+  const size_t smem = sizeof(Instr) * kProgWindow + (size_t)warps * (sizeof(double) * 2 * 2 * kTabDoubles * K + 16);
+  static size_t configured = 0;  // per template instantiation
+  if (smem > configured) {
     cudaError_t err = cudaFuncSetAttribute(clv_program_kernel<K, E, MAXT, MINB>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return fail(RDK_ERROR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(err));
-    configured = true;
+    configured = smem;
   }
   clv_program_kernel<K, E, MAXT, MINB><<<grid, threads, smem, st>>>(a);
   return RDK_SUCCESS;
@@ -327,7 +329,7 @@ int launch_program(const ProgArgs &a, int grid, int threads, int E, cudaStream_t
   switch (E) {
     case 1: return launch_program_inst<K, 1, 256, 3>(a, grid, threads, st);
     case 4: return launch_program_inst<K, 4, 128, 2>(a, grid, std::min(threads, 128), st);
-    default: return launch_program_inst<K, 2, 128, 3>(a, grid, std::min(threads, 128), st);
+    default: return launch_program_inst<K, 2, 128, RDK_MINB2>(a, grid, std::min(threads, 128), st);
   }
 }
 
@@ -416,13 +418,21 @@ int flush(rdk_partition_t *p) {
     a.prog = reinterpret_cast<const Instr *>(d);
   }
   if (nelem > 0) {
-    int threads = e->threads ? e->threads : 96;
+    int threads = e->threads ? e->threads : 128;
     int per_sm = e->ctas_per_sm ? e->ctas_per_sm : 4;
     int E = e->elems ? e->elems : 2;
-    int grid = e->sm_count * per_sm;
-    // never launch more warps than warp iterations
     if (E >= 2) threads = std::min(threads, 128);
     if (E == 3) E = 2;
+    // every warp owns a table buffer of 2 KiB * K: keep a CTA's shared memory near 64 KiB
+    // (K = 4: 4 warps; K = 16: 1-2 warps; K = 32: 1 warp)
+    {
+      const size_t per_warp = sizeof(double) * 2 * 2 * kTabDoubles * e->K + 16;
+      const size_t budget = (size_t)64 << 10;
+      int max_warps = (int)std::max<size_t>(1, (budget - std::min(budget, sizeof(Instr) * kProgWindow)) / per_warp);
+      threads = std::min(threads, 32 * max_warps);
+    }
+    int grid = e->sm_count * per_sm;
+    // never launch more warps than warp iterations
     int max_grid = (int)((n_witer + (threads / 32) - 1) / (threads / 32));
     grid = std::max(1, std::min(grid, max_grid));
     std::pair<cudaEvent_t, cudaEvent_t> *ev = e->timing ? next_event_pair(e) : nullptr;
@@ -636,7 +646,12 @@ static int engine_init(rdk_partition_t *p, Engine *e) {
   e->K = p->rate_cats;
   e->prob_matrices = p->prob_matrices;
   e->scale_buffers = p->scale_buffers;
+#if RDK_KSLOW
+  // whole blocks of 32 elements (32/K sites): the blocked layout of rdk_kernels.cuh
+  e->clv_elems = (size_t)((e->S + 32 / e->K - 1) / (32 / e->K)) * 32 * 4;
+#else
   e->clv_elems = (size_t)e->S * e->K * 4;
+#endif
   e->tip_stride = ((size_t)e->S + 127) & ~size_t(127);
   e->global_sites = 0;
   e->clv_ptr.assign(e->clv_buffers, nullptr);
@@ -1236,8 +1251,9 @@ extern "C" int rdk_get_clv(rdk_partition_t *p, unsigned int clv_index, double *o
   CUDA_TRY(cudaSetDevice(e->device));
   if (clv_index >= e->tips + e->clv_buffers) return fail(RDK_ERROR_PARAM, "clv index out of range");
   if (!flush(p)) return RDK_FAILURE;
-  size_t bytes = e->clv_elems * sizeof(double);
+  size_t bytes = e->clv_elems * sizeof(double);  // device size (whole blocks)
   if (clv_index < e->tips) {
+    bytes = (size_t)e->S * e->K * 4 * sizeof(double);  // natural size
     double *tmp = nullptr;
     CUDA_TRY(cudaMalloc((void **)&tmp, bytes ? bytes : 32));
     size_t n = (size_t)e->S * e->K;
@@ -1252,9 +1268,23 @@ extern "C" int rdk_get_clv(rdk_partition_t *p, unsigned int clv_index, double *o
     CUDA_TRY(err);
   } else {
     if (!ensure_clv(e, clv_index - e->tips)) return RDK_FAILURE;
+#if RDK_KSLOW
+    // device layout [block][cat][site in block][state] -> corax layout [site][cat][state]
+    std::vector<double> tmp(e->clv_elems);
+    CUDA_TRY(cudaMemcpyAsync(tmp.data(), e->clv_ptr[clv_index - e->tips], bytes, cudaMemcpyDeviceToHost,
+                             e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    const unsigned spw = 32 / e->K;
+    for (unsigned s = 0; s < e->S; ++s)
+      for (unsigned k = 0; k < e->K; ++k) {
+        const size_t src = ((size_t)(s / spw) * 32 + k * spw + (s % spw)) * 4;
+        for (int j = 0; j < 4; ++j) out[((size_t)s * e->K + k) * 4 + j] = tmp[src + j];
+      }
+#else
     CUDA_TRY(cudaMemcpyAsync(out, e->clv_ptr[clv_index - e->tips], bytes, cudaMemcpyDeviceToHost,
                              e->stream));
     CUDA_TRY(cudaStreamSynchronize(e->stream));
+#endif
   }
   e->stats.d2h_bytes += bytes;
   return RDK_SUCCESS;

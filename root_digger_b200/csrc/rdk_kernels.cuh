@@ -4,9 +4,11 @@
 // corax_update_clvs and corax_compute_root_loglikelihood (call sites:
 // reference src/model.cpp:367,432,842 / :402,440,461,851 / :406,441,466).
 //
-// Arithmetic contract (DESIGN.md "Arithmetic specification"): fp64, every
-// +,-,*,/ individually rounded (round-to-nearest-even, no FMA contraction), in
-// the order written.  All arithmetic goes through the __d*_rn intrinsics so the
+// Arithmetic contract (DESIGN.md "Arithmetic specification", v2): fp64; the 4x4
+// mat-vec of the CLV update and the dot products of the root log-likelihood are
+// explicit FMA chains (__fma_rn, j ascending); every other +,-,*,/ is
+// individually rounded (round-to-nearest-even, no contraction), in the order
+// written.  All arithmetic goes through the __d*_rn / __fma_rn intrinsics so the
 // contract holds whatever -fmad says.
 //
 // Memory-bound by design: 0.61 flop/B, no tensor cores (a 4x4 mat-vec is not a
@@ -14,6 +16,19 @@
 // accesses, enough bytes in flight, and never re-reading a CLV from HBM.
 #pragma once
 #include <cuda_runtime.h>
+#ifndef RDK_KSLOW
+// 1: CLVs are stored in blocks of 32 elements (= 32/K sites) laid out [cat][site in block][state]
+//    and lane l of a warp holds category l / (32/K): global accesses stay 1 KiB-contiguous per warp
+//    while the lanes of a quarter warp share their category (one shared-memory address per
+//    quarter warp when reading P).  0: natural [site][cat][state] layout, category = l % K.
+#define RDK_KSLOW 0  // measured on B200: no gain from the blocked layout (the LSU pipe is not the limiter)
+#endif
+#ifndef RDK_MINB2
+#define RDK_MINB2 4  // resident CTAs of 128 threads the E = 2 program kernel is compiled for
+#endif
+#ifndef RDK_LD256
+#define RDK_LD256 1  // 256-bit global loads/stores of CLV elements
+#endif
 #include <stdint.h>
 
 namespace rdk {
@@ -27,6 +42,9 @@ __device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a,
 __device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
 __device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
 __device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a, b); }
+// the 4x4 mat-vec of the CLV update and the root dot products are explicit FMA chains
+// (arithmetic spec v2); everything else stays individually rounded
+__device__ __forceinline__ double dfma(double a, double b, double c) { return __fma_rn(a, b, c); }
 
 // 2^-256 underflow threshold, 2^256 rescale factor, ln(2^-256)
 #define RDK_SCALE_THRESHOLD 0x1p-256
@@ -405,9 +423,12 @@ __global__ void __launch_bounds__(64) pmat_expm_nonrev_kernel(const __grid_const
 // same warp are still in L2 (or in registers), so HBM sees each CLV written
 // once and mostly not read back.
 //
-// Thread mapping: element e = site*K + k.  Lane l of a warp iteration `it`
-// handles e = 32*it + l, i.e. 32 consecutive 32-byte (4 x fp64) vectors = 1 KiB
-// contiguous per CLV per warp access; k = l % K is fixed per thread (K | 32).
+// Thread mapping: element e = site*K + k.  A warp iteration `it` covers the 32/K
+// sites [it*32/K, (it+1)*32/K) = 32 consecutive 32-byte (4 x fp64) vectors = 1 KiB
+// contiguous per CLV per warp access.  Lane l handles site it*32/K + l % (32/K),
+// category k = l / (32/K): the lanes of a quarter warp share k, so their 128-bit
+// shared-memory reads of P hit ONE address per quarter warp (measured on B200:
+// 2 LSU cycles per read instead of 4 for the interleaved k = l % K mapping).
 // ---------------------------------------------------------------------------
 enum : unsigned {
   kTip1 = 1u,      // child1 is a tip: 1 byte per site (4-bit state code)
@@ -443,7 +464,10 @@ struct alignas(16) Instr {
 static_assert(sizeof(Instr) == 80, "Instr layout");
 
 constexpr int kProgInline = 8;
-constexpr int kProgWindow = 256;  // instructions staged in shared memory at a time
+#ifndef RDK_PROG_WINDOW
+#define RDK_PROG_WINDOW 256
+#endif
+constexpr int kProgWindow = RDK_PROG_WINDOW;  // instructions staged in shared memory at a time
 struct ProgArgs {
   const Instr*    prog;  // used when n_instr > kProgInline
   int             n_instr;
@@ -463,22 +487,37 @@ struct d4 {
 };
 
 __device__ __forceinline__ d4 ld_clv(const double* base, unsigned e) {
-  // 32 B per thread as 2 x 128-bit loads, L2-coherent (ld.global.cg): CLVs are
-  // read and written within one launch and never re-read by the same SM soon
-  // enough for L1 to help.
-  const double2* q = reinterpret_cast<const double2*>(reinterpret_cast<const char*>(base) + (size_t)e * 32u);
-  double2        a = __ldcg(q), b = __ldcg(q + 1);
-  d4             r;
+  // one 256-bit load per element (sm_100 LDG.E.256): a warp access covers 1 KiB
+  // contiguous with every 32-byte sector used by exactly one lane.  L2-coherent
+  // (.cg): CLVs are read and written within one launch and never re-read by the
+  // same SM soon enough for L1 to help.
+  const char* q = reinterpret_cast<const char*>(base) + (size_t)e * 32u;
+  d4          r;
+#if RDK_LD256
+  asm volatile("ld.global.cg.v4.f64 {%0,%1,%2,%3}, [%4];\n"
+               : "=d"(r.v[0]), "=d"(r.v[1]), "=d"(r.v[2]), "=d"(r.v[3])
+               : "l"(q));
+#else
+  const double2* q2 = reinterpret_cast<const double2*>(q);
+  double2        a = __ldcg(q2), b = __ldcg(q2 + 1);
   r.v[0] = a.x;
   r.v[1] = a.y;
   r.v[2] = b.x;
   r.v[3] = b.y;
+#endif
   return r;
 }
 __device__ __forceinline__ void st_clv(double* base, unsigned e, const d4& x) {
-  double2* q = reinterpret_cast<double2*>(reinterpret_cast<char*>(base) + (size_t)e * 32u);
-  __stcg(q, make_double2(x.v[0], x.v[1]));
-  __stcg(q + 1, make_double2(x.v[2], x.v[3]));
+  char* q = reinterpret_cast<char*>(base) + (size_t)e * 32u;
+#if RDK_LD256
+  asm volatile("st.global.cg.v4.f64 [%0], {%1,%2,%3,%4};\n" ::"l"(q), "d"(x.v[0]), "d"(x.v[1]), "d"(x.v[2]),
+               "d"(x.v[3])
+               : "memory");
+#else
+  double2* q2 = reinterpret_cast<double2*>(q);
+  __stcg(q2, make_double2(x.v[0], x.v[1]));
+  __stcg(q2 + 1, make_double2(x.v[2], x.v[3]));
+#endif
 }
 
 // ---- mbarrier + bulk async copy (one elected thread moves a whole table) ----
@@ -518,56 +557,76 @@ template <int E>
 struct Operands {
   d4       c1[E], c2[E];  // inner children: the 4 state likelihoods
   unsigned m1[E], m2[E];  // tip children: the state code
-  unsigned cnt[E];        // sum of the children's scaler counts
+  unsigned cnt1[E], cnt2[E];  // the children's scaler counts (kept apart so that nothing
+                              // waits on the loads before the instruction that needs them)
 };
 
-// Each CTA owns a contiguous range of warp iterations and walks the whole
-// program over it, one "pass" of (warps per CTA x E) iterations at a time.
-//  * the program is staged in shared memory in windows;
+// Each WARP owns a contiguous range of warp iterations and walks the whole
+// program over it, one "pass" of E iterations at a time, independently of every
+// other warp (no CTA barrier per instruction).
+//  * the program is staged in shared memory in windows (the only CTA-level
+//    synchronisation: once per kProgWindow instructions, and only when the
+//    program does not fit one window);
 //  * per instruction and child, either the transition matrices P (inner child)
-//    or the tip table T (tip child) of the child's branch is moved into a shared
-//    double buffer by ONE thread with a bulk async copy (cp.async.bulk +
-//    mbarrier) while the previous instruction computes; one __syncthreads per
-//    instruction keeps the CTA's warps on the same instruction (needed for this
-//    buffer and for the duplicate-work tails below -- CLV dependencies are per
-//    element and therefore per thread);
+//    or the tip table T (tip child) of the child's branch is moved into the
+//    warp's own shared double buffer by lane 0 with a bulk async copy
+//    (cp.async.bulk + mbarrier) while the previous instruction computes;
 //  * the global operands of instruction i+1 are loaded into registers BEFORE
 //    the arithmetic of instruction i (software pipelining, two register sets
 //    used in ping-pong), and when a child of i+1 is the CLV instruction i is
 //    producing -- the normal case in a post-order schedule -- it is forwarded in
 //    registers and never re-read (the host pre-decodes this into kFwd*);
-//  * there are no per-element validity predicates: a thread without an element
-//    of its own (tail of the CTA's range, tail of the partition) redundantly
-//    recomputes the last element of the range / the last site and stores the
-//    identical values; only the log-likelihood reduction masks it out.
+//  * there are no per-element validity predicates: a slot without an element
+//    of its own (tail of the warp's range, tail of the partition) redundantly
+//    recomputes the last iteration of the range / the last site and stores the
+//    identical values (same warp, same instruction: no race); only the
+//    log-likelihood reduction masks it out.
 template <int K, int E, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) clv_program_kernel(const __grid_constant__ ProgArgs a) {
   static_assert(32 % K == 0, "K must divide the warp size");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr unsigned kTabBytes = kTabDoubles * K * 8;  // one child's slice of a table buffer
   Instr*              s_prog = reinterpret_cast<Instr*>(smem_raw);
-  unsigned char*      s_tab = smem_raw + sizeof(Instr) * kProgWindow;  // [buf][child][kTabBytes]
-  unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_tab + 4 * kTabBytes);  // [buf]
+  const unsigned      wib = threadIdx.x >> 5;
+  const unsigned      wpb = blockDim.x >> 5;
+  // per warp: [buf][child][kTabBytes] tables, then (after all warps' tables) [warp][buf] barriers
+  unsigned char*      s_tab = smem_raw + sizeof(Instr) * kProgWindow + (size_t)wib * 4 * kTabBytes;
+  unsigned long long* s_bar =
+      reinterpret_cast<unsigned long long*>(smem_raw + sizeof(Instr) * kProgWindow + (size_t)wpb * 4 * kTabBytes) +
+      2 * wib;
 
   const unsigned tid = threadIdx.x;
   const unsigned lane = tid & 31u;
-  const unsigned wib = tid >> 5;
-  const unsigned wpb = blockDim.x >> 5;
-  const unsigned k = lane % K;
-  const unsigned gmask = (K == 32) ? 0xffffffffu : (((1u << K) - 1u) << (lane - k));
+  constexpr unsigned SPW = 32 / K;  // sites per warp iteration
+#if RDK_KSLOW
+  constexpr unsigned KSTRIDE = SPW;  // lane distance between two categories of a site
+  const unsigned     k = lane / SPW;
+  const unsigned     sl = lane % SPW;  // site within the warp iteration
+#else
+  constexpr unsigned KSTRIDE = 1;
+  const unsigned     k = lane % K;
+  const unsigned     sl = lane / K;
+#endif
+  const unsigned lane0 = lane - k * KSTRIDE;  // the k == 0 lane of this lane's site
+  unsigned       gmask = 0;                   // the K lanes that hold this lane's site
+#pragma unroll
+  for (int j = 0; j < K; ++j) gmask |= 1u << (j * KSTRIDE + lane0);
 
-  const unsigned it_begin = (unsigned)(((unsigned long long)a.n_witer * blockIdx.x) / gridDim.x);
-  const unsigned it_end = (unsigned)(((unsigned long long)a.n_witer * (blockIdx.x + 1)) / gridDim.x);
-  if (it_end == it_begin) return;  // whole CTA
-  const unsigned per_pass = wpb * E;
-  const unsigned passes = (it_end - it_begin + per_pass - 1) / per_pass;
+  const unsigned gw = blockIdx.x * wpb + wib, nw = gridDim.x * wpb;
+  const unsigned it_begin = (unsigned)(((unsigned long long)a.n_witer * gw) / nw);
+  const unsigned it_end = (unsigned)(((unsigned long long)a.n_witer * (gw + 1)) / nw);
+  // every warp of the grid runs the same number of passes (the window barriers below are
+  // CTA-wide); a warp whose range is exhausted idles through the remaining ones
+  const unsigned passes = ((a.n_witer + nw - 1) / nw + E - 1) / E;
   const unsigned last_site = a.nelem / K - 1;
+  const bool     multi_window = a.n_instr > kProgWindow;
 
-  if (tid == 0) {
+  if (lane == 0) {
     mbar_init(&s_bar[0], 1);
     mbar_init(&s_bar[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
+  __syncwarp();
   unsigned phase = 0;  // bit b: parity of the next completion of s_bar[b]
 
   // one thread: move P or T of both children of `in` into buffer `buf`
@@ -587,20 +646,20 @@ __global__ void __launch_bounds__(MAXT, MINB) clv_program_kernel(const __grid_co
   };
 
   for (unsigned pass = 0; pass < passes; ++pass) {
-    unsigned it[E], e[E], site[E];
-    bool     own[E];  // this thread's element is its own (not a duplicate)
+    const bool active = it_begin + pass * E < it_end;  // warp-uniform
+    unsigned   it[E], e[E], site[E];
 #pragma unroll
     for (int u = 0; u < E; ++u) {
-      unsigned i0 = it_begin + (pass * E + u) * wpb + wib;
-      own[u] = i0 < it_end;
-      it[u] = own[u] ? i0 : it_end - 1;
-      unsigned ee = it[u] * 32u + lane;
-      if (ee >= a.nelem) {
-        own[u] = false;
-        ee = last_site * K + k;
-      }
-      e[u] = ee;
-      site[u] = ee / K;
+      const unsigned i0 = it_begin + pass * E + u;
+      it[u] = (i0 < it_end || !active) ? i0 : it_end - 1;
+      unsigned st = it[u] * SPW + sl;
+      if (st > last_site) st = last_site;
+      site[u] = st;
+#if RDK_KSLOW
+      e[u] = (st / SPW) * 32u + k * SPW + (st % SPW);  // blocked CLV layout [block][cat][site in block]
+#else
+      e[u] = st * K + k;
+#endif
     }
 
     // issue the global loads of one instruction's operands
@@ -624,16 +683,16 @@ __global__ void __launch_bounds__(MAXT, MINB) clv_program_kernel(const __grid_co
         for (int u = 0; u < E; ++u) o.c2[u] = ld_clv(g, e[u]);
       }
 #pragma unroll
-      for (int u = 0; u < E; ++u) o.cnt[u] = 0;
+      for (int u = 0; u < E; ++u) o.cnt1[u] = o.cnt2[u] = 0;
       if (fl & kLdS1) {
         const unsigned* s1 = in.c1scale;
 #pragma unroll
-        for (int u = 0; u < E; ++u) o.cnt[u] = __ldcg(s1 + site[u]);
+        for (int u = 0; u < E; ++u) o.cnt1[u] = __ldcg(s1 + site[u]);
       }
       if (fl & kLdS2) {
         const unsigned* s2 = in.c2scale;
 #pragma unroll
-        for (int u = 0; u < E; ++u) o.cnt[u] += __ldcg(s2 + site[u]);
+        for (int u = 0; u < E; ++u) o.cnt2[u] = __ldcg(s2 + site[u]);
       }
     };
 
@@ -641,10 +700,10 @@ __global__ void __launch_bounds__(MAXT, MINB) clv_program_kernel(const __grid_co
     // instruction are loaded into `nxt`.  first == first instruction of a window
     // (its operands were loaded without forwarding).
     auto step = [&](int ii, int wn, Operands<E>& cur, Operands<E>& nxt) {
-      __syncthreads();  // every warp has finished instruction ii-1
+      __syncwarp();  // every lane has finished instruction ii-1 (frees the other table buffer)
       const bool more = ii + 1 < wn;
       const unsigned buf = (unsigned)ii & 1u;
-      if (more && tid == 0) prefetch_tables(s_prog[ii + 1], buf ^ 1u);
+      if (more && lane == 0) prefetch_tables(s_prog[ii + 1], buf ^ 1u);
       const Instr&   in = s_prog[ii];
       const unsigned fl = in.flags;
       unsigned       nfl = 0;
@@ -658,7 +717,10 @@ __global__ void __launch_bounds__(MAXT, MINB) clv_program_kernel(const __grid_co
       const unsigned char* tab1 = s_tab + (size_t)buf * 2 * kTabBytes;
       const unsigned char* tab2 = tab1 + kTabBytes;
 
-      d4 v[E];
+      d4       v[E];
+      unsigned cnt[E];
+#pragma unroll
+      for (int u = 0; u < E; ++u) cnt[u] = cur.cnt1[u] + cur.cnt2[u];
       if (fl & kLoadOnly) {
 #pragma unroll
         for (int u = 0; u < E; ++u) v[u] = cur.c1[u];
@@ -682,9 +744,9 @@ __global__ void __launch_bounds__(MAXT, MINB) clv_program_kernel(const __grid_co
 #pragma unroll
             for (int u = 0; u < E; ++u) {
               double s = dmul(p01.x, cur.c1[u].v[0]);
-              s = dadd(s, dmul(p01.y, cur.c1[u].v[1]));
-              s = dadd(s, dmul(p23.x, cur.c1[u].v[2]));
-              s = dadd(s, dmul(p23.y, cur.c1[u].v[3]));
+              s = dfma(p01.y, cur.c1[u].v[1], s);
+              s = dfma(p23.x, cur.c1[u].v[2], s);
+              s = dfma(p23.y, cur.c1[u].v[3], s);
               v[u].v[i] = s;
             }
           }
@@ -708,9 +770,9 @@ __global__ void __launch_bounds__(MAXT, MINB) clv_program_kernel(const __grid_co
 #pragma unroll
             for (int u = 0; u < E; ++u) {
               double s = dmul(p01.x, cur.c2[u].v[0]);
-              s = dadd(s, dmul(p01.y, cur.c2[u].v[1]));
-              s = dadd(s, dmul(p23.x, cur.c2[u].v[2]));
-              s = dadd(s, dmul(p23.y, cur.c2[u].v[3]));
+              s = dfma(p01.y, cur.c2[u].v[1], s);
+              s = dfma(p23.x, cur.c2[u].v[2], s);
+              s = dfma(p23.y, cur.c2[u].v[3], s);
               v[u].v[i] = dmul(v[u].v[i], s);
             }
           }
@@ -725,7 +787,7 @@ __global__ void __launch_bounds__(MAXT, MINB) clv_program_kernel(const __grid_co
           if ((m & gmask) == gmask) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) v[u].v[i] = dmul(v[u].v[i], RDK_SCALE_FACTOR);
-            cur.cnt[u] += 1;
+            cnt[u] += 1;
           }
         }
       }
@@ -736,7 +798,7 @@ __global__ void __launch_bounds__(MAXT, MINB) clv_program_kernel(const __grid_co
         unsigned* ps = in.pscale;
         if (ps && k == 0) {
 #pragma unroll
-          for (int u = 0; u < E; ++u) __stcg(ps + site[u], cur.cnt[u]);
+          for (int u = 0; u < E; ++u) __stcg(ps + site[u], cnt[u]);
         }
       }
       // register forwarding into the operands of instruction ii+1
@@ -750,35 +812,37 @@ __global__ void __launch_bounds__(MAXT, MINB) clv_program_kernel(const __grid_co
       }
       if (nfl & kFwdS1) {
 #pragma unroll
-        for (int u = 0; u < E; ++u) nxt.cnt[u] += cur.cnt[u];
+        for (int u = 0; u < E; ++u) nxt.cnt1[u] = cnt[u];
       }
       if (nfl & kFwdS2) {
 #pragma unroll
-        for (int u = 0; u < E; ++u) nxt.cnt[u] += cur.cnt[u];
+        for (int u = 0; u < E; ++u) nxt.cnt2[u] = cnt[u];
       }
       if (fl & kEval) {
 #pragma unroll
         for (int u = 0; u < E; ++u) {
           double t = dmul(a.pi[0], v[u].v[0]);
-          t = dadd(t, dmul(a.pi[1], v[u].v[1]));
-          t = dadd(t, dmul(a.pi[2], v[u].v[2]));
-          t = dadd(t, dmul(a.pi[3], v[u].v[3]));
-          double term = dmul(a.w[0], t);
+          t = dfma(a.pi[1], v[u].v[1], t);
+          t = dfma(a.pi[2], v[u].v[2], t);
+          t = dfma(a.pi[3], v[u].v[3], t);
+          // every lane of a site gathers the K category terms in category order
+          double term = dmul(a.w[0], __shfl_sync(0xffffffffu, t, lane0));
 #pragma unroll
           for (int kk = 1; kk < K; ++kk) {
-            double tk = __shfl_down_sync(0xffffffffu, t, kk);
-            term = dadd(term, dmul(a.w[kk], tk));
+            double tk = __shfl_sync(0xffffffffu, t, lane0 + kk * KSTRIDE);
+            term = dfma(a.w[kk], tk, term);
           }
           double l = 0.0;
-          if (k == 0 && it[u] * 32u + lane < a.nelem) {
+          if (k == 0 && it[u] * SPW + sl <= last_site) {
             l = rd_log(term);
-            if (fl & kEvalScaler) l = dadd(l, dmul((double)cur.cnt[u], RDK_LOG_SCALE_THRESHOLD));
+            if (fl & kEvalScaler) l = dadd(l, dmul((double)cnt[u], RDK_LOG_SCALE_THRESHOLD));
             l = dmul(l, (double)__ldg(a.weights + site[u]));
             if (a.persite && in.slot == 0) a.persite[site[u]] = l;
           }
-          // canonical tree over the 32/K sites of this warp iteration
+          // canonical tree over the 32/K sites of this warp iteration (the k == 0 lanes)
 #pragma unroll
-          for (int off2 = K; off2 < 32; off2 <<= 1) l = dadd(l, __shfl_xor_sync(0xffffffffu, l, off2));
+          for (int off2 = 1; off2 < (int)SPW; off2 <<= 1)
+            l = dadd(l, __shfl_xor_sync(0xffffffffu, l, off2 * (KSTRIDE == 1 ? K : 1)));
           if (lane == 0) a.partials[(size_t)in.slot * a.partial_stride + it[u]] = l;
         }
       }
@@ -786,21 +850,23 @@ __global__ void __launch_bounds__(MAXT, MINB) clv_program_kernel(const __grid_co
 
     for (int w0 = 0; w0 < a.n_instr; w0 += kProgWindow) {
       const int wn = min(kProgWindow, a.n_instr - w0);
-      __syncthreads();  // everyone is done with the previous window / pass (program and tables)
-      if (a.n_instr > kProgWindow || pass == 0) {
+      if (multi_window || pass == 0) {
+        if (multi_window) __syncthreads();  // every warp is done with the previous window
         const int4* src = reinterpret_cast<const int4*>(a.n_instr <= kProgInline ? a.inl : a.prog + w0);
         int4*       dst = reinterpret_cast<int4*>(s_prog);
         for (unsigned c = tid; c < (unsigned)wn * (sizeof(Instr) / 16); c += blockDim.x) dst[c] = src[c];
         __syncthreads();
       }
-      if (tid == 0) prefetch_tables(s_prog[0], 0);
+      if (!active) continue;
+      __syncwarp();
+      if (lane == 0) prefetch_tables(s_prog[0], 0);
       Operands<E> opA, opB;
 #pragma unroll
       for (int u = 0; u < E; ++u) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) opA.c1[u].v[i] = opA.c2[u].v[i] = opB.c1[u].v[i] = opB.c2[u].v[i] = 0.0;
         opA.m1[u] = opA.m2[u] = opB.m1[u] = opB.m2[u] = 15u;  // code 15: all-zero table row
-        opA.cnt[u] = opB.cnt[u] = 0;
+        opA.cnt1[u] = opA.cnt2[u] = opB.cnt1[u] = opB.cnt2[u] = 0;
       }
       // the first instruction of a window never carries kFwd* (finalize_program)
       load_operands(s_prog[0], s_prog[0].flags, opA);
