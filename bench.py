@@ -18,8 +18,14 @@ e2e     = the same step through the host model_t mirror (librd_host.so: C++ trav
 roofline= the dominant kernel (clv_program_kernel): algorithmic bytes (counted
           per launch by the engine) / its device time (CUDA events bracketing each launch).
 
-N > 1: the alignment's sites are sharded across the GPUs (strong scaling: the global problem
-is fixed), one process per GPU, one NCCL all-reduce of tree nodes per evaluation batch.
+N > 1 (strong scaling: the global problem is fixed), one process per GPU, N = G_s x G_r
+(root_digger_b200.sharding.plan_grid): the alignment's sites are split into G_s
+shards -- as few as HBM allows, one NCCL all-reduce of tree nodes per evaluation batch inside
+a site group -- and the 2n-3 candidate placements of the sweep into G_r contiguous chunks
+(the rule exhaustive mode uses for ranks, reference src/model.cpp:1899-1907; no data-path
+collective, one all-gather of the 2n-3 log-likelihoods per step).  cfg2 fits a replica per
+GPU, so the default is G_s = 1, G_r = N; --shard sites forces G_s = N (measured in
+profiles/ for comparison: a 12.5k-site shard is latency-bound).
 
 --impl reference: the CPU oracle restatement of the same step (the reference's coraxlib is an
 absent submodule: it cannot be built), all host threads, on a bounded site sample.
@@ -61,6 +67,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--launch-config", default="", help="ctas_per_sm,threads,elems (0 = engine default)")
+    ap.add_argument("--tail-mode", type=int, default=0, help="0 engine rule, 1 always skip idle slots, 2 never")
+    ap.add_argument("--shard", default="auto", choices=["auto", "sites", "roots"],
+                    help="N > 1: auto = fewest site shards that fit HBM, rest over root placements")
     return ap.parse_args()
 
 
@@ -213,6 +222,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    from root_digger_b200.sharding import plan_grid
     threads = os.cpu_count() or 1
     case = build_case_cpu(args)
     value, info, ms_full = cpu_reference_run(args, case, args.steps, args.warmup, threads)
@@ -220,7 +230,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_full, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, case.tree.root_count),
+        "config": workload_config(args, case.tree.root_count,
+                                  plan_grid(args.gpus, case.n, case.S, case.K, force=args.shard)),
         "cpu_baseline": info,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -234,15 +245,16 @@ def build_case_cpu(args):
     return Case(args.taxa, args.sites, args.cats, seed=args.seed, data=args.data, alpha=1.0)
 
 
-def workload_config(args, placements):
+def workload_config(args, placements, grid=None):
     return {"workload": "cfg2: synthetic %d-taxon x %d-site DNA, UNREST+G%d, search-mode step = 1 full "
                         "evaluation (compute_lh) + 1 sweep of all %d candidate root placements "
                         "(suggest_roots_lh: move_root + compute_lh_root each)"
                         % (args.taxa, args.sites, args.cats, placements),
             "taxa": args.taxa, "sites": args.sites, "rate_cats": args.cats, "placements_per_step": placements,
-            "alignment": args.data, "sharding": "sites/%d" % args.gpus,
+            "alignment": args.data,
+            "sharding": "sites/%d x root-placements/%d" % (grid if grid else (args.gpus, 1)),
             "l2_policy": "inputs larger than L2 (inner CLVs %.1f GB per GPU vs 126 MB L2)"
-                         % ((args.taxa - 1) * 32.0 * args.cats * args.sites / args.gpus / 1e9)}
+                         % ((args.taxa - 1) * 32.0 * args.cats * args.sites / (grid[0] if grid else args.gpus) / 1e9)}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -265,49 +277,72 @@ def run_ours(args):
     from cases import compute_lh
     from root_digger_b200 import capi
     from root_digger_b200.capi import Model, Partition, RootedTree, ops_array
-    from root_digger_b200.sharding import plan_site_shards
+    from root_digger_b200.sharding import plan_grid, plan_root_shards, plan_site_shards
 
     case = build_case(args)
     n, S, K = case.n, case.S, case.K
-    shards = plan_site_shards(S, n_gpus)
-    off, cnt = shards[rank]
+    # N = G_s site shards x G_r root-placement chunks; rank r: site shard r % G_s, chunk r // G_s
+    G_s, G_r = plan_grid(world, n, S, K, force=args.shard)
+    site_rank, root_group = rank % G_s, rank // G_s
+    shards = plan_site_shards(S, G_s)
+    off, cnt = shards[site_rank]
     sl = slice(off, off + cnt)
 
     def fresh_comm_id():
-        """a new 128-byte NCCL unique id from rank 0 (one per communicator), shipped with torch.distributed"""
-        if world == 1:
+        """a new 128-byte NCCL unique id per site group (one per communicator), made by the group's
+        first rank and shipped with torch.distributed"""
+        if G_s == 1:
             return None
-        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            idt = torch.tensor(list(capi.comm_unique_id()), dtype=torch.uint8, device="cuda")
-        dist.broadcast(idt, 0)
-        return bytes(idt.cpu().tolist())
+        mine = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if site_rank == 0:
+            mine = torch.tensor(list(capi.comm_unique_id()), dtype=torch.uint8, device="cuda")
+        ids = torch.zeros(world * 128, dtype=torch.uint8, device="cuda")
+        dist.all_gather_into_tensor(ids, mine)
+        leader = root_group * G_s
+        return bytes(ids[leader * 128:(leader + 1) * 128].cpu().tolist())
 
     comm_id = fresh_comm_id()
 
     g = Partition(n, cnt, K, device=local)
     g.set_stream(torch.cuda.current_stream().cuda_stream)
     case.setup(g, sl)
-    if world > 1:
+    if G_s > 1:
         g.set_shard(off, S)
-        g.attach_comm(world, rank, comm_id)
+        g.attach_comm(G_s, site_rank, comm_id)
     if args.launch_config:
         g.set_launch_config(*[int(x) for x in args.launch_config.split(",")])
+    if args.tail_mode:
+        g.set_tail_mode(args.tail_mode)
 
     full_ops, full_pm, full_br = case.full_schedule(0, 0.5)
     full_arr = ops_array(full_ops)
-    roots = list(range(case.tree.root_count))
+    placements = case.tree.root_count
+    chunks = plan_root_shards(range(placements), G_r)
+    roots = chunks[root_group]  # this rank's contiguous chunk of root ids
     sw = case.sweep_schedule(roots, 0.5)
     pm_off, mi, bl, op_off, ops = sw
     sw_arr = ops_array(ops)
-    placements = len(roots)
+    chunk_max = max(len(c) for c in chunks)
+    gather_in = torch.zeros(chunk_max, dtype=torch.float64, device="cuda")
+    gather_out = torch.zeros(world * chunk_max, dtype=torch.float64, device="cuda")
+    pinned = torch.zeros(chunk_max, dtype=torch.float64).pin_memory()
+
+    def gather_placements(mine):
+        """every rank ends with all 2n-3 log-likelihoods (exhaustive mode's final gather)"""
+        if G_r == 1:
+            return mine
+        pinned[:len(mine)] = torch.from_numpy(mine)
+        gather_in.copy_(pinned, non_blocking=True)
+        dist.all_gather_into_tensor(gather_out, gather_in)
+        allv = gather_out.cpu().numpy().reshape(world, chunk_max)
+        return np.concatenate([allv[q * G_s, :len(chunks[q])] for q in range(G_r)])
 
     def step():
         g.update_prob_matrices(full_pm, full_br)
         g.L.rdk_update_clvs(g.p, full_arr, len(full_ops))
         lh0 = g.root_loglikelihood(case.root_clv, case.root_scaler)
         out = g.sweep_root_placements(pm_off, mi, bl, op_off, sw_arr, case.root_clv, case.root_scaler)
-        return lh0, out
+        return lh0, gather_placements(out)
 
     def barrier():
         if world > 1:
@@ -360,8 +395,8 @@ def run_ours(args):
     if not args.no_e2e:
         tree = RootedTree(case.newick)
         aln = {l: s[sl] for l, s in case.aln.items()}
-        m = Model(tree, aln, K, site_offset=off if world > 1 else 0, global_sites=S if world > 1 else 0,
-                  nranks=world, rank=rank, comm_id=fresh_comm_id())
+        m = Model(tree, aln, K, site_offset=off if G_s > 1 else 0, global_sites=S if G_s > 1 else 0,
+                  nranks=G_s, rank=site_rank, comm_id=fresh_comm_id())
         m.initialize_partitions()
         m.set_params(rates=case.rates, freqs=case.freqs)
         part = C.cast(m.L.rdh_model_partition(m.h, 0), C.POINTER(capi.PartitionStruct))
@@ -374,8 +409,8 @@ def run_ours(args):
 
         def mstep():
             a = m.compute_lh(0, 0.5)
-            b = m.sweep_root_lh()
-            return a, b
+            b = m.sweep_root_lh(roots[0], roots[-1] + 1) if G_r > 1 else m.sweep_root_lh()
+            return a, gather_placements(b)
 
         for _ in range(max(3, args.warmup)):
             a, b = mstep()
@@ -394,7 +429,8 @@ def run_ours(args):
                "h2d_bytes_per_step": s2["h2d_bytes"] / args.steps, "d2h_bytes_per_step": s2["d2h_bytes"] / args.steps,
                "ms_per_step": float(ms2.item()) / args.steps,
                "api": "librd_host.so model_t::compute_lh + model_t::suggest_roots_lh sweep (host scheduler, "
-                      "programs H2D, log-likelihoods D2H; alignment resident as in the reference partition)",
+                      "programs H2D, log-likelihoods D2H; alignment resident as in the reference partition"
+                      + ("; + all-gather of the placement log-likelihoods)" if G_r > 1 else ")"),
                "logl_root0": a, "matches_device_arm": bool(a == lh0 and np.array_equal(b, sweep_lh))}
         m.close()
     clocks = sampler.stop() if sampler else None
@@ -409,7 +445,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args, placements),
+            "config": workload_config(args, placements, (G_s, G_r)),
             "clv_update_gbs": clv_gbs, "clv_update_gbs_per_gpu": clv_gbs / n_gpus,
             "algorithmic_bytes_per_step": total_alg_bytes / args.steps,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,

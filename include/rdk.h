@@ -270,6 +270,10 @@ int rdk_partition_set_timing(rdk_partition_t *partition, int enabled);
 int rdk_partition_set_launch_config(rdk_partition_t *partition,
                                     int ctas_per_sm, int threads_per_cta,
                                     int elems_per_thread);
+/* program-kernel tail handling when a warp's site range is not a multiple of
+ * its elements per thread: 0 = engine's rule, 1 = always skip the idle slots,
+ * 2 = never (recompute).  Results are identical in every mode. */
+int rdk_partition_set_tail_mode(rdk_partition_t *partition, int mode);
 const char *rdk_version(void);
 
 #ifdef __cplusplus

@@ -142,6 +142,7 @@ def load_engine() -> C.CDLL:
     L.rdk_partition_reset_stats.restype = None
     L.rdk_partition_set_launch_config.argtypes = [_pp, C.c_int, C.c_int, C.c_int]
     L.rdk_partition_set_timing.argtypes = [_pp, C.c_int]
+    L.rdk_partition_set_tail_mode.argtypes = [_pp, C.c_int]
     L.rdk_set_device.argtypes = [C.c_int]
     _engine_lib = L
     return L
@@ -319,6 +320,10 @@ class Partition:
 
     def set_launch_config(self, ctas_per_sm=0, threads=0, elems=0):
         if self.L.rdk_partition_set_launch_config(self.p, ctas_per_sm, threads, elems) != RDK_SUCCESS:
+            raise EngineError(_err(self.L))
+
+    def set_tail_mode(self, mode: int = 0):
+        if self.L.rdk_partition_set_tail_mode(self.p, mode) != RDK_SUCCESS:
             raise EngineError(_err(self.L))
 
     def set_timing(self, on: bool = True):
@@ -561,6 +566,7 @@ def _bind_model(L: C.CDLL):
     L.rdh_model_optimize_alpha.argtypes = [vp, C.c_uint, C.c_double, C.c_double, _dp]
     L.rdh_model_optimize_root_location.argtypes = [vp, C.c_uint, C.c_double, _up, _dp, _dp]
     L.rdh_model_sweep_root_lh.argtypes = [vp, _dp]
+    L.rdh_model_sweep_root_lh_range.argtypes = [vp, C.c_uint, C.c_uint, _dp]
     L.rdh_model_compute_all_root_lh.argtypes = [vp, _dp]
     L.rdh_model_search.argtypes = [vp, C.c_uint, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
                                    C.c_int, C.c_uint, C.c_uint, _up, _dp, _dp]
@@ -670,9 +676,17 @@ class Model:
                                                             C.byref(alpha), C.byref(lh)))
         return rid.value, alpha.value, lh.value
 
-    def sweep_root_lh(self) -> np.ndarray:
-        out = np.zeros(self.root_count)
-        self._check(self.L.rdh_model_sweep_root_lh(self.h, _ptr(out, _dp)))
+    def sweep_root_lh(self, begin: int | None = None, end: int | None = None) -> np.ndarray:
+        """log-likelihood of every root placement (root-id order); with begin/end only of the
+        root ids [begin, end) -- one rank's share when the roots are distributed over GPUs"""
+        if begin is None and end is None:
+            out = np.zeros(self.root_count)
+            self._check(self.L.rdh_model_sweep_root_lh(self.h, _ptr(out, _dp)))
+            return out
+        begin = 0 if begin is None else begin
+        end = self.root_count if end is None else end
+        out = np.zeros(max(0, end - begin))
+        self._check(self.L.rdh_model_sweep_root_lh_range(self.h, begin, end, _ptr(out, _dp)))
         return out
 
     def compute_all_root_lh(self) -> np.ndarray:

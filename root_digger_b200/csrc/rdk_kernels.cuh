@@ -30,6 +30,7 @@
 #define RDK_LD256 1  // 256-bit global loads/stores of CLV elements
 #endif
 #include <stdint.h>
+#include <type_traits>
 
 namespace rdk {
 
@@ -576,12 +577,18 @@ struct Operands {
 //    used in ping-pong), and when a child of i+1 is the CLV instruction i is
 //    producing -- the normal case in a post-order schedule -- it is forwarded in
 //    registers and never re-read (the host pre-decodes this into kFwd*);
-//  * there are no per-element validity predicates: a slot without an element
-//    of its own (tail of the warp's range, tail of the partition) redundantly
-//    recomputes the last iteration of the range / the last site and stores the
-//    identical values (same warp, same instruction: no race); only the
-//    log-likelihood reduction masks it out.
-template <int K, int E, int MAXT, int MINB>
+//  * there are no per-lane validity predicates: a lane without a site of its
+//    own (tail of the partition) redundantly recomputes the last site and
+//    stores the identical values (same warp, same instruction: no race); only
+//    the log-likelihood reduction masks it out.  The last pass of a warp whose
+//    range is not a multiple of E runs the instruction loop instantiated for
+//    the number of iterations it has left (NV < E) when the kernel is
+//    instantiated with TS (tail skip); without TS the slots without an iteration
+//    of their own redundantly recompute the last iteration of the range.  The
+//    host picks TS when no warp has a full last pass (choose_tail_skip): there
+//    the short loop pays; otherwise the slowest warps run full passes anyway and
+//    the second copy of the loop only costs instruction-cache misses (measured).
+template <int K, int E, int MAXT, int MINB, bool TS>
 __global__ void __launch_bounds__(MAXT, MINB) clv_program_kernel(const __grid_constant__ ProgArgs a) {
   static_assert(32 % K == 0, "K must divide the warp size");
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -663,43 +670,45 @@ __global__ void __launch_bounds__(MAXT, MINB) clv_program_kernel(const __grid_co
     }
 
     // issue the global loads of one instruction's operands
-    auto load_operands = [&](const Instr& in, unsigned fl, Operands<E>& o) {
+    auto load_operands = [&](auto nvc, const Instr& in, unsigned fl, Operands<E>& o) {
+      constexpr int NV = decltype(nvc)::value;  // slots with an iteration of their own
       if (fl & kTip1) {
         const unsigned char* t = reinterpret_cast<const unsigned char*>(in.c1);
 #pragma unroll
-        for (int u = 0; u < E; ++u) o.m1[u] = __ldg(t + site[u]);
+        for (int u = 0; u < NV; ++u) o.m1[u] = __ldg(t + site[u]);
       } else if (!(fl & kFwd1)) {
         const double* g = reinterpret_cast<const double*>(in.c1);
 #pragma unroll
-        for (int u = 0; u < E; ++u) o.c1[u] = ld_clv(g, e[u]);
+        for (int u = 0; u < NV; ++u) o.c1[u] = ld_clv(g, e[u]);
       }
       if (fl & kTip2) {
         const unsigned char* t = reinterpret_cast<const unsigned char*>(in.c2);
 #pragma unroll
-        for (int u = 0; u < E; ++u) o.m2[u] = __ldg(t + site[u]);
+        for (int u = 0; u < NV; ++u) o.m2[u] = __ldg(t + site[u]);
       } else if (!(fl & (kFwd2 | kLoadOnly))) {
         const double* g = reinterpret_cast<const double*>(in.c2);
 #pragma unroll
-        for (int u = 0; u < E; ++u) o.c2[u] = ld_clv(g, e[u]);
+        for (int u = 0; u < NV; ++u) o.c2[u] = ld_clv(g, e[u]);
       }
 #pragma unroll
-      for (int u = 0; u < E; ++u) o.cnt1[u] = o.cnt2[u] = 0;
+      for (int u = 0; u < NV; ++u) o.cnt1[u] = o.cnt2[u] = 0;
       if (fl & kLdS1) {
         const unsigned* s1 = in.c1scale;
 #pragma unroll
-        for (int u = 0; u < E; ++u) o.cnt1[u] = __ldcg(s1 + site[u]);
+        for (int u = 0; u < NV; ++u) o.cnt1[u] = __ldcg(s1 + site[u]);
       }
       if (fl & kLdS2) {
         const unsigned* s2 = in.c2scale;
 #pragma unroll
-        for (int u = 0; u < E; ++u) o.cnt2[u] = __ldcg(s2 + site[u]);
+        for (int u = 0; u < NV; ++u) o.cnt2[u] = __ldcg(s2 + site[u]);
       }
     };
 
     // one instruction: `cur` holds its operands, the operands of the next
     // instruction are loaded into `nxt`.  first == first instruction of a window
     // (its operands were loaded without forwarding).
-    auto step = [&](int ii, int wn, Operands<E>& cur, Operands<E>& nxt) {
+    auto step = [&](auto nvc, int ii, int wn, Operands<E>& cur, Operands<E>& nxt) {
+      constexpr int NV = decltype(nvc)::value;
       __syncwarp();  // every lane has finished instruction ii-1 (frees the other table buffer)
       const bool more = ii + 1 < wn;
       const unsigned buf = (unsigned)ii & 1u;
@@ -710,7 +719,7 @@ __global__ void __launch_bounds__(MAXT, MINB) clv_program_kernel(const __grid_co
       if (more) {
         const Instr& nx = s_prog[ii + 1];
         nfl = nx.flags;
-        load_operands(nx, nfl, nxt);
+        load_operands(nvc, nx, nfl, nxt);
       }
       mbar_wait(&s_bar[buf], (phase >> buf) & 1u);  // tables(ii) have landed
       phase ^= 1u << buf;
@@ -720,15 +729,15 @@ __global__ void __launch_bounds__(MAXT, MINB) clv_program_kernel(const __grid_co
       d4       v[E];
       unsigned cnt[E];
 #pragma unroll
-      for (int u = 0; u < E; ++u) cnt[u] = cur.cnt1[u] + cur.cnt2[u];
+      for (int u = 0; u < NV; ++u) cnt[u] = cur.cnt1[u] + cur.cnt2[u];
       if (fl & kLoadOnly) {
 #pragma unroll
-        for (int u = 0; u < E; ++u) v[u] = cur.c1[u];
+        for (int u = 0; u < NV; ++u) v[u] = cur.c1[u];
       } else {
         // child 1
         if (fl & kTip1) {
 #pragma unroll
-          for (int u = 0; u < E; ++u) {
+          for (int u = 0; u < NV; ++u) {
             const double2* t = reinterpret_cast<const double2*>(tab1 + (cur.m1[u] * K + k) * 32u);
             const double2  lo = t[0], hi = t[1];
             v[u].v[0] = lo.x;
@@ -742,7 +751,7 @@ __global__ void __launch_bounds__(MAXT, MINB) clv_program_kernel(const __grid_co
           for (int i = 0; i < 4; ++i) {
             const double2 p01 = p[i * 2], p23 = p[i * 2 + 1];
 #pragma unroll
-            for (int u = 0; u < E; ++u) {
+            for (int u = 0; u < NV; ++u) {
               double s = dmul(p01.x, cur.c1[u].v[0]);
               s = dfma(p01.y, cur.c1[u].v[1], s);
               s = dfma(p23.x, cur.c1[u].v[2], s);
@@ -754,7 +763,7 @@ __global__ void __launch_bounds__(MAXT, MINB) clv_program_kernel(const __grid_co
         // child 2
         if (fl & kTip2) {
 #pragma unroll
-          for (int u = 0; u < E; ++u) {
+          for (int u = 0; u < NV; ++u) {
             const double2* t = reinterpret_cast<const double2*>(tab2 + (cur.m2[u] * K + k) * 32u);
             const double2  lo = t[0], hi = t[1];
             v[u].v[0] = dmul(v[u].v[0], lo.x);
@@ -768,7 +777,7 @@ __global__ void __launch_bounds__(MAXT, MINB) clv_program_kernel(const __grid_co
           for (int i = 0; i < 4; ++i) {
             const double2 p01 = p[i * 2], p23 = p[i * 2 + 1];
 #pragma unroll
-            for (int u = 0; u < E; ++u) {
+            for (int u = 0; u < NV; ++u) {
               double s = dmul(p01.x, cur.c2[u].v[0]);
               s = dfma(p01.y, cur.c2[u].v[1], s);
               s = dfma(p23.x, cur.c2[u].v[2], s);
@@ -780,7 +789,7 @@ __global__ void __launch_bounds__(MAXT, MINB) clv_program_kernel(const __grid_co
       }
       if (fl & kScale) {
 #pragma unroll
-        for (int u = 0; u < E; ++u) {
+        for (int u = 0; u < NV; ++u) {
           const bool small = (v[u].v[0] < RDK_SCALE_THRESHOLD) && (v[u].v[1] < RDK_SCALE_THRESHOLD) &&
                              (v[u].v[2] < RDK_SCALE_THRESHOLD) && (v[u].v[3] < RDK_SCALE_THRESHOLD);
           const unsigned m = __ballot_sync(0xffffffffu, small);
@@ -794,33 +803,33 @@ __global__ void __launch_bounds__(MAXT, MINB) clv_program_kernel(const __grid_co
       if (fl & kWrite) {
         double* par = in.parent;
 #pragma unroll
-        for (int u = 0; u < E; ++u) st_clv(par, e[u], v[u]);
+        for (int u = 0; u < NV; ++u) st_clv(par, e[u], v[u]);
         unsigned* ps = in.pscale;
         if (ps && k == 0) {
 #pragma unroll
-          for (int u = 0; u < E; ++u) __stcg(ps + site[u], cnt[u]);
+          for (int u = 0; u < NV; ++u) __stcg(ps + site[u], cnt[u]);
         }
       }
       // register forwarding into the operands of instruction ii+1
       if (nfl & kFwd1) {
 #pragma unroll
-        for (int u = 0; u < E; ++u) nxt.c1[u] = v[u];
+        for (int u = 0; u < NV; ++u) nxt.c1[u] = v[u];
       }
       if (nfl & kFwd2) {
 #pragma unroll
-        for (int u = 0; u < E; ++u) nxt.c2[u] = v[u];
+        for (int u = 0; u < NV; ++u) nxt.c2[u] = v[u];
       }
       if (nfl & kFwdS1) {
 #pragma unroll
-        for (int u = 0; u < E; ++u) nxt.cnt1[u] = cnt[u];
+        for (int u = 0; u < NV; ++u) nxt.cnt1[u] = cnt[u];
       }
       if (nfl & kFwdS2) {
 #pragma unroll
-        for (int u = 0; u < E; ++u) nxt.cnt2[u] = cnt[u];
+        for (int u = 0; u < NV; ++u) nxt.cnt2[u] = cnt[u];
       }
       if (fl & kEval) {
 #pragma unroll
-        for (int u = 0; u < E; ++u) {
+        for (int u = 0; u < NV; ++u) {
           double t = dmul(a.pi[0], v[u].v[0]);
           t = dfma(a.pi[1], v[u].v[1], t);
           t = dfma(a.pi[2], v[u].v[2], t);
@@ -848,16 +857,8 @@ __global__ void __launch_bounds__(MAXT, MINB) clv_program_kernel(const __grid_co
       }
     };
 
-    for (int w0 = 0; w0 < a.n_instr; w0 += kProgWindow) {
-      const int wn = min(kProgWindow, a.n_instr - w0);
-      if (multi_window || pass == 0) {
-        if (multi_window) __syncthreads();  // every warp is done with the previous window
-        const int4* src = reinterpret_cast<const int4*>(a.n_instr <= kProgInline ? a.inl : a.prog + w0);
-        int4*       dst = reinterpret_cast<int4*>(s_prog);
-        for (unsigned c = tid; c < (unsigned)wn * (sizeof(Instr) / 16); c += blockDim.x) dst[c] = src[c];
-        __syncthreads();
-      }
-      if (!active) continue;
+    // the instruction loop over one staged window, for NV slots
+    auto run_window = [&](auto nvc, int wn) {
       __syncwarp();
       if (lane == 0) prefetch_tables(s_prog[0], 0);
       Operands<E> opA, opB;
@@ -869,13 +870,33 @@ __global__ void __launch_bounds__(MAXT, MINB) clv_program_kernel(const __grid_co
         opA.cnt1[u] = opA.cnt2[u] = opB.cnt1[u] = opB.cnt2[u] = 0;
       }
       // the first instruction of a window never carries kFwd* (finalize_program)
-      load_operands(s_prog[0], s_prog[0].flags, opA);
+      load_operands(nvc, s_prog[0], s_prog[0].flags, opA);
       int ii = 0;
       for (; ii + 1 < wn; ii += 2) {
-        step(ii, wn, opA, opB);
-        step(ii + 1, wn, opB, opA);
+        step(nvc, ii, wn, opA, opB);
+        step(nvc, ii + 1, wn, opB, opA);
       }
-      if (ii < wn) step(ii, wn, opA, opB);
+      if (ii < wn) step(nvc, ii, wn, opA, opB);
+    };
+
+    for (int w0 = 0; w0 < a.n_instr; w0 += kProgWindow) {
+      const int wn = min(kProgWindow, a.n_instr - w0);
+      if (multi_window || pass == 0) {
+        if (multi_window) __syncthreads();  // every warp is done with the previous window
+        const int4* src = reinterpret_cast<const int4*>(a.n_instr <= kProgInline ? a.inl : a.prog + w0);
+        int4*       dst = reinterpret_cast<int4*>(s_prog);
+        for (unsigned c = tid; c < (unsigned)wn * (sizeof(Instr) / 16); c += blockDim.x) dst[c] = src[c];
+        __syncthreads();
+      }
+      if (!active) continue;
+      // iterations of its own this warp has in this pass (warp-uniform)
+      const unsigned nvalid = min((unsigned)E, it_end - (it_begin + pass * E));
+      if (TS && E >= 2 && nvalid == 1)
+        run_window(std::integral_constant<int, 1>{}, wn);
+      else if (TS && E >= 4 && nvalid == 2)
+        run_window(std::integral_constant<int, (TS && E >= 4 ? 2 : E)>{}, wn);
+      else
+        run_window(std::integral_constant<int, E>{}, wn);
     }
   }
 }

@@ -510,9 +510,19 @@ std::vector<root_location_t> model_t::suggest_roots_random(size_t min, double ra
 // log-likelihood of every root placement at its stored ratio, in root-id order:
 // what the loop at src/model.cpp:871-874 computes (move_root + compute_lh_root
 // per root).  With the fused path the whole sweep is ONE engine call.
-std::vector<double> model_t::sweep_root_lh() {
-  const auto         &roots = _tree.roots();
+std::vector<double> model_t::sweep_root_lh() { return sweep_root_lh(0, _tree.roots().size()); }
+
+// The same sweep restricted to the root ids [begin, end): the unit of work of one rank when
+// the candidate roots are distributed over ranks the way exhaustive mode distributes them
+// (src/model.cpp:1899-1907).  The CLVs must be valid for the current root (compute_lh); the
+// first placement re-orients them along the path from there.
+std::vector<double> model_t::sweep_root_lh(size_t begin, size_t end) {
+  const auto &all_roots = _tree.roots();
+  if (begin > end || end > all_roots.size()) throw std::invalid_argument("sweep_root_lh: bad root range");
+  const std::vector<root_location_t> roots(all_roots.begin() + (std::ptrdiff_t)begin,
+                                           all_roots.begin() + (std::ptrdiff_t)end);
   std::vector<double> lh(roots.size(), 0.0);
+  if (roots.empty()) return lh;
   if (!_fused) {
     for (size_t r = 0; r < roots.size(); ++r) {
       move_root(roots[r]);

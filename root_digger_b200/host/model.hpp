@@ -90,6 +90,7 @@ public:
   // suggest_roots_lh ranks), and LWR = softmax of a log-likelihood vector
   // (exhaustive mode, src/model.cpp:1238-1258)
   std::vector<double>        sweep_root_lh();
+  std::vector<double>        sweep_root_lh(size_t begin, size_t end);  // root ids [begin, end)
   static std::vector<double> lwr(const std::vector<double> &llh);
 
   void set_subst_rates(size_t, const model_params_t &);

@@ -152,6 +152,13 @@ extern "C" int rdh_model_sweep_root_lh(void *h, double *out) {
     return 1;
   })
 }
+extern "C" int rdh_model_sweep_root_lh_range(void *h, unsigned begin, unsigned end, double *out) {
+  RDH_TRY({
+    auto v = H(h).model->sweep_root_lh(begin, end);
+    for (size_t i = 0; i < v.size(); ++i) out[i] = v[i];
+    return 1;
+  })
+}
 extern "C" int rdh_model_compute_all_root_lh(void *h, double *out) {
   RDH_TRY({
     auto v = H(h).model->compute_all_root_lh();

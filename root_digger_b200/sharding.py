@@ -44,3 +44,36 @@ def plan_root_shards(root_ids, nranks: int):
 
 def plan_partition_shards(n_partitions: int, nranks: int):
     return [[p for p in range(n_partitions) if p % nranks == r] for r in range(nranks)]
+
+
+def replica_bytes(n_taxa: int, sites: int, rate_cats: int = 4) -> int:
+    """device bytes of one partition holding `sites` patterns:
+    n-1 inner CLVs of 32*K B per site, 2n-2 uint32 scale buffers, 1-byte tips, weights"""
+    return sites * ((n_taxa - 1) * 32 * rate_cats + (2 * n_taxa - 2) * 4 + n_taxa + 4)
+
+
+def plan_grid(nranks: int, n_taxa: int, sites: int, rate_cats: int = 4, budget_bytes: float = 150e9,
+              force: str = "auto"):
+    """2-D decomposition: nranks = site_groups x root_groups.
+
+    Root placements shard with no data-path collective but need a replica of all the
+    sites they score; sites shard with one all-reduce per evaluation.  So: as few site
+    shards as HBM allows (the smallest divisor G_s of nranks whose shard fits
+    `budget_bytes`), and the remaining factor distributes the root placements
+    (exhaustive mode, src/model.cpp:1899-1907).  cfg2 (6.4 GB) and cfg3 (137 GB) fit a
+    replica -> (1, N); cfg5 (1.35 TB) -> (8, 1).
+    force = "sites" -> (N, 1); "roots" -> (1, N).
+    Rank r works on site shard r % G_s for root chunk r // G_s."""
+    if nranks < 1:
+        raise ValueError("nranks must be positive")
+    if force == "sites":
+        return nranks, 1
+    if force == "roots":
+        return 1, nranks
+    for gs in range(1, nranks + 1):
+        if nranks % gs:
+            continue
+        shard_sites = max(c for _, c in plan_site_shards(sites, gs))
+        if replica_bytes(n_taxa, shard_sites, rate_cats) <= budget_bytes:
+            return gs, nranks // gs
+    return nranks, 1

@@ -181,8 +181,11 @@ def test_launch_configs_do_not_change_results():
     want = compute_lh(o, sched, case.root_clv, case.root_scaler, mode=MODE_ENGINE)
     for ctas, threads, elems in [(1, 32, 1), (2, 256, 2), (4, 128, 4), (8, 64, 1), (3, 96, 2)]:
         g.set_launch_config(ctas, threads, elems)
-        got = compute_lh(g, sched, case.root_clv, case.root_scaler)
-        assert same_bits([got], [want]), (ctas, threads, elems)
+        for tail in (1, 2, 0):
+            g.set_tail_mode(tail)
+            got = compute_lh(g, sched, case.root_clv, case.root_scaler)
+            assert same_bits([got], [want]), (ctas, threads, elems, tail)
+            assert same_bits(g.get_clv(case.root_clv), o.get_clv(case.root_clv)), (ctas, threads, elems, tail)
 
 
 def test_error_paths():

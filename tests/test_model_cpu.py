@@ -71,6 +71,26 @@ def test_fused_sweep_equals_reference_loop(lib):
     assert np.array_equal(a.view(np.uint64), b.view(np.uint64))
 
 
+def test_root_sharded_sweep_equals_full_sweep(lib):
+    """root placements distributed over ranks (src/model.cpp:1899-1907 rule): every rank
+    starts from the CLVs of root 0 and sweeps its own chunk; the chunks concatenate to
+    the single-rank sweep bit for bit"""
+    from root_digger_b200.sharding import plan_root_shards
+    m = make_model(lib, K=4)
+    m.compute_lh(0)
+    full = m.sweep_root_lh()
+    for nranks in (2, 3, 8):
+        parts = []
+        for chunk in plan_root_shards(range(m.root_count), nranks):
+            m.compute_lh(0)
+            parts.append(m.sweep_root_lh(chunk[0], chunk[-1] + 1) if chunk else np.zeros(0))
+        got = np.concatenate(parts)
+        assert np.array_equal(got.view(np.uint64), full.view(np.uint64)), nranks
+    assert len(m.sweep_root_lh(5, 5)) == 0
+    with pytest.raises(Exception):
+        m.sweep_root_lh(3, m.root_count + 1)
+
+
 def test_move_root_invariance_under_jc(lib):
     """test/src/model.cpp:367-387"""
     m = make_model(lib, "101.phy", uniform=False)

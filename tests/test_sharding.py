@@ -28,6 +28,20 @@ def test_site_shard_plan():
     assert max(counts) - min(counts) <= 1024 + 576   # balanced to one alignment block (last one ragged)
 
 
+def test_grid_plan_prefers_replicas_that_fit():
+    """cfg2 / cfg3 fit a full-site replica per GPU (roots distribute), cfg5 does not"""
+    assert sharding.plan_grid(8, 500, 100_000) == (1, 8)
+    assert sharding.plan_grid(8, 2000, 500_000) == (1, 8)
+    assert sharding.plan_grid(8, 10_000, 1_000_000) == (8, 1)
+    assert sharding.plan_grid(8, 5_000, 500_000) == (4, 2)
+    assert sharding.plan_grid(8, 500, 100_000, force="sites") == (8, 1)
+    assert sharding.plan_grid(1, 10_000, 1_000_000) == (1, 1)
+    assert abs(sharding.replica_bytes(10_000, 125_000) - 171.2e9) < 0.1e9
+    for n in (1, 2, 4, 8):
+        gs, gr = sharding.plan_grid(n, 2000, 500_000, budget_bytes=40e9)
+        assert gs * gr == n
+
+
 def test_root_shard_plan_matches_reference_rule():
     """src/model.cpp:1899-1907: chunk*rank + min(mod, rank)"""
     assert sharding.plan_root_shards(range(17), 4) == [[0, 1, 2, 3, 4], [5, 6, 7, 8], [9, 10, 11, 12], [13, 14, 15, 16]]
