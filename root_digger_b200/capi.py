@@ -552,6 +552,13 @@ def _bind_model(L: C.CDLL):
                                    C.c_int, C.c_int, vp]
     L.rdh_model_destroy.argtypes = [vp]
     L.rdh_model_destroy.restype = None
+    L.rdh_model_create_from_files.restype = vp
+    L.rdh_model_create_from_files.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_uint, C.c_int, ull, C.c_int]
+    L.rdh_model_partition_count.argtypes = [vp]
+    L.rdh_model_partition_count.restype = C.c_uint
+    L.rdh_partition_describe.argtypes = [C.c_char_p]
+    L.rdh_partition_describe.restype = vp
+    L.rdh_msa_partition_lengths.argtypes = [C.c_char_p, C.c_char_p, C.c_int, _up, C.c_uint]
     L.rdh_model_sites.argtypes = [vp, C.c_uint]
     L.rdh_model_sites.restype = C.c_uint
     L.rdh_model_root_count.argtypes = [vp]
@@ -579,6 +586,42 @@ def _bind_model(L: C.CDLL):
     L.rdh_model_partition.argtypes = [vp, C.c_uint]
     L.rdh_model_partition.restype = vp
     L._rdh_model_bound = True
+
+
+def parse_partitions(text: str, lib: C.CDLL | None = None) -> list:
+    """RAxML-NG partition-file text -> list of dicts (host/partition_file.cpp; reference
+    parse_partition_info / parse_model_info, src/msa.cpp:364-493).  Raises ValueError when the
+    text does not parse."""
+    L = lib or load_tree_lib()
+    _bind_model(L)
+    r = L.rdh_partition_describe(text.encode())
+    if not r:
+        raise ValueError(L.rdh_last_error().decode())
+    out = []
+    try:
+        for line in C.string_at(r).decode().splitlines():
+            f = line.split("|")
+            out.append({"model_name": f[0], "partition_name": f[1],
+                        "parts": [tuple(int(x) for x in rg.split("-")) for rg in f[2].split(",")],
+                        "subst": f[3], "freq": f[4], "invar_present": f[5] == "1", "invar": f[6],
+                        "invar_prop": float(f[7]), "ratehet": f[8], "cat_type": f[9], "rate_cats": int(f[10]),
+                        "alpha_init": f[11] == "1", "alpha": float(f[12]), "asc": f[13]})
+    finally:
+        L.rdh_free(C.c_void_p(r))
+    return out
+
+
+def msa_partition_lengths(msa_path: str, partition_text: str, compress_first: bool = True,
+                          lib: C.CDLL | None = None) -> list:
+    """pattern counts of msa_t::partition() on an alignment file (reference test/src/msa.cpp:236-283)"""
+    L = lib or load_tree_lib()
+    _bind_model(L)
+    out = (C.c_uint * 64)()
+    rc = L.rdh_msa_partition_lengths(str(msa_path).encode(), partition_text.encode(), 1 if compress_first else 0,
+                                     out, 64)
+    if not rc:
+        raise ValueError(L.rdh_last_error().decode())
+    return [int(out[i]) for i in range(rc - 1)]
 
 
 class Model:
@@ -609,6 +652,28 @@ class Model:
         self.h = C.c_void_p(self.h)
         self.K = rate_cats
         self.root_count = self.L.rdh_model_root_count(self.h)
+
+    @classmethod
+    def from_files(cls, tree: RootedTree, msa_path, partition_path=None, rate_cats: int = 4, *,
+                   invariant_sites: bool = False, seed: int = 1, early_stop: bool = False) -> "Model":
+        """the reference's ingest path (src/main.cpp:513-560): PHYLIP/FASTA alignment + optional
+        RAxML-NG partition file (rate categories then come from the partition file)"""
+        self = cls.__new__(cls)
+        self.L = tree.L
+        _bind_model(self.L)
+        h = self.L.rdh_model_create_from_files(tree.h, str(msa_path).encode(),
+                                               str(partition_path).encode() if partition_path else None,
+                                               rate_cats, 1 if invariant_sites else 0, seed, 1 if early_stop else 0)
+        if not h:
+            raise RuntimeError("model_t could not be created: " + self.L.rdh_last_error().decode())
+        self.h = C.c_void_p(h)
+        self.K = rate_cats
+        self.root_count = self.L.rdh_model_root_count(self.h)
+        return self
+
+    @property
+    def partition_count(self) -> int:
+        return int(self.L.rdh_model_partition_count(self.h))
 
     def close(self):
         if getattr(self, "h", None):

@@ -3,6 +3,8 @@
 // message available from rdh_last_error() (exceptions never cross the boundary).
 #include "model.hpp"
 
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -65,6 +67,100 @@ extern "C" void *rdh_model_create(void *tree, int n_taxa, const char **labels, c
     rdh_set_error(e.what());
     return nullptr;
   }
+}
+
+// The ingest path of the reference's main (src/main.cpp:513-560): alignment file
+// (PHYLIP or FASTA), optional RAxML-NG partition file; with a partition file the
+// alignment is loaded uncompressed, split, every partition compressed on its own,
+// and the rate categories come from the partition file's model strings (0 -> 1).
+extern "C" void *rdh_model_create_from_files(void *tree, const char *msa_path, const char *partition_path,
+                                             unsigned rate_cats, int invariant_sites,
+                                             unsigned long long seed, int early_stop) {
+  try {
+    auto                        h = std::make_unique<holder_t>();
+    std::vector<ratehet_opts_t> cats;
+    if (!partition_path || !*partition_path) {
+      h->msa.emplace_back(std::string(msa_path), rdk_map_nt, 4u, true);
+      cats.emplace_back(ratehet_opts_t{rate_cats});
+    } else {
+      msa_t whole(std::string(msa_path), rdk_map_nt, 4u, false);
+      auto  infos = parse_partition_file(partition_path);
+      if (infos.empty()) throw std::runtime_error("the partition file names no partition");
+      h->msa = whole.partition(infos);
+      for (auto &p : infos) {
+        ratehet_opts_t r = p.model.ratehet_opts;
+        if (r.rate_cats == 0) r.rate_cats = 1;
+        cats.push_back(r);
+      }
+    }
+    for (auto &m : h->msa) m.valid_data();
+    rooted_tree_t t(*reinterpret_cast<rooted_tree_t *>(tree));
+    h->model = std::make_unique<model_t>(std::move(t), h->msa, cats, invariant_sites != 0, (uint64_t)seed,
+                                         early_stop != 0, shard_spec_t{});
+    return h.release();
+  } catch (const std::exception &e) {
+    rdh_set_error(e.what());
+    return nullptr;
+  }
+}
+
+extern "C" unsigned rdh_model_partition_count(void *h) { return (unsigned)H(h).msa.size(); }
+
+namespace {
+const char *ptype(param_type t) {
+  switch (t) {
+    case param_type::emperical: return "emperical";
+    case param_type::estimate: return "estimate";
+    case param_type::equal: return "equal";
+    default: return "user";
+  }
+}
+}  // namespace
+
+// parse partition-file text; one line per partition:
+//   model_name|partition_name|b-e,b-e|subst|freq|invar_present|invar|invar_prop|ratehet|cat_type|rate_cats|alpha_init|alpha|asc
+// malloc'd (free with rdh_free); NULL + rdh_last_error() when the text does not parse
+extern "C" char *rdh_partition_describe(const char *text) {
+  try {
+    std::string out;
+    for (auto &p : parse_partition_text(text)) {
+      char buf[256];
+      out += p.model_name + "|" + p.partition_name + "|";
+      for (size_t i = 0; i < p.parts.size(); ++i)
+        out += (i ? "," : "") + std::to_string(p.parts[i].first) + "-" + std::to_string(p.parts[i].second);
+      const auto &m = p.model;
+      const char *cat = m.ratehet_opts.rate_category_type == rate_category::MEDIAN ? "median"
+                        : m.ratehet_opts.rate_category_type == rate_category::FREE ? "free"
+                                                                                    : "mean";
+      const char *asc = m.asc_opts.type == asc_bias_type::lewis  ? "lewis"
+                        : m.asc_opts.type == asc_bias_type::fels ? "fels"
+                        : m.asc_opts.type == asc_bias_type::stam ? "stam"
+                                                                  : "none";
+      snprintf(buf, sizeof(buf), "|%s|%s|%d|%s|%.17g|%s|%s|%zu|%d|%.17g|%s\n", m.subst_str.c_str(),
+               ptype(m.freq_opts.type), m.invar_opts.present ? 1 : 0, ptype(m.invar_opts.type),
+               m.invar_opts.user_prop, ptype(m.ratehet_opts.type), cat, m.ratehet_opts.rate_cats,
+               m.ratehet_opts.alpha_init ? 1 : 0, m.ratehet_opts.alpha, asc);
+      out += buf;
+    }
+    char *r = (char *)malloc(out.size() + 1);
+    memcpy(r, out.c_str(), out.size() + 1);
+    return r;
+  } catch (const std::exception &e) {
+    rdh_set_error(e.what());
+    return nullptr;
+  }
+}
+
+// pattern counts of the partitions of an alignment file (test/src/msa.cpp:236-283)
+extern "C" int rdh_msa_partition_lengths(const char *msa_path, const char *partition_text, int compress_first,
+                                         unsigned *out, unsigned cap) {
+  RDH_TRY({
+    msa_t whole(std::string(msa_path), rdk_map_nt, 4u, compress_first != 0);
+    auto  parts = whole.partition(parse_partition_text(partition_text));
+    if (parts.size() > cap) throw std::runtime_error("output buffer too small");
+    for (size_t i = 0; i < parts.size(); ++i) out[i] = parts[i].length();
+    return (int)parts.size() + 1;
+  })
 }
 
 extern "C" void rdh_model_destroy(void *h) { delete reinterpret_cast<holder_t *>(h); }

@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cctype>
 #include <fstream>
+#include <limits>
 #include <numeric>
 #include <sstream>
 #include <stdexcept>
@@ -122,6 +123,35 @@ msa_t::msa_t(const msa_t &o, size_t begin, size_t end) : _labels(o._labels), _ma
   if (begin > end || end > o.length()) throw std::out_of_range("column slice out of range");
   for (auto &s : o._sequences) _sequences.push_back(s.substr(begin, end - begin));
   _weights.assign(o._weights.begin() + (long)begin, o._weights.begin() + (long)end);
+}
+
+msa_t::msa_t(const msa_t &o, const partition_info_t &part) : _labels(o._labels), _map(o._map), _states(o._states) {
+  size_t total = 0;
+  for (auto &r : part.parts) {
+    if (r.first == 0) throw std::runtime_error("Partition ranges start at 1, but we encountered a 0");
+    if (r.second < r.first || r.second > o.length())
+      throw std::runtime_error("Partition range " + std::to_string(r.first) + "-" + std::to_string(r.second) +
+                               " of '" + part.partition_name + "' is outside the alignment (" +
+                               std::to_string(o.length()) + " columns)");
+    total += r.second - r.first + 1;
+  }
+  if (total > (size_t)std::numeric_limits<int>::max()) throw std::runtime_error("Partition range is too large");
+  _sequences.reserve(o._sequences.size());
+  for (auto &s : o._sequences) {
+    std::string t;
+    t.reserve(total);
+    for (auto &r : part.parts) t.append(s, r.first - 1, r.second - r.first + 1);
+    _sequences.push_back(std::move(t));
+  }
+  _weights.assign(total, 1u);
+  compress();
+}
+
+std::vector<msa_t> msa_t::partition(const msa_partitions_t &parts) const {
+  std::vector<msa_t> out;
+  out.reserve(parts.size());
+  for (auto &p : parts) out.emplace_back(*this, p);
+  return out;
 }
 
 const char *msa_t::sequence(int i) const {

@@ -2,11 +2,13 @@
 // reference's msa_t, src/msa.hpp:21-68: sequence/label/weights/map/states/
 // count/length/total_weight, pattern compression, taxa consistency check).
 // PHYLIP (sequential or interleaved) and FASTA are read; partition files and
-// model strings are outside the hot path.
+// model strings are parsed by partition_file.hpp.
 #ifndef RD_HOST_MSA_HPP_
 #define RD_HOST_MSA_HPP_
 
 #include <rdk.h>
+
+#include "partition_file.hpp"
 
 #include <string>
 #include <unordered_set>
@@ -21,6 +23,10 @@ public:
         const rdk_state_t *map = rdk_map_nt, unsigned int states = 4, bool compress = true);
   // contiguous column slice [begin, end) of another alignment, weights carried over
   msa_t(const msa_t &other, size_t begin, size_t end);
+  // the columns named by a partition's 1-based inclusive ranges, in range order,
+  // weights reset and patterns re-compressed (src/msa.cpp:505-587)
+  msa_t(const msa_t &other, const partition_info_t &partition);
+  std::vector<msa_t> partition(const msa_partitions_t &parts) const;
   msa_t(const msa_t &) = delete;
   msa_t(msa_t &&) = default;
 
