@@ -68,6 +68,9 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--launch-config", default="", help="ctas_per_sm,threads,elems (0 = engine default)")
     ap.add_argument("--tail-mode", type=int, default=0, help="0 engine rule, 1 always skip idle slots, 2 never")
+    ap.add_argument("--sweep", default="directed", choices=["directed", "path"],
+                    help="how our arm scores the 2n-3 placements: one pre-order pass over directed CLVs "
+                         "(default) or the reference-shaped move_root path per placement; identical values")
     ap.add_argument("--shard", default="auto", choices=["auto", "sites", "roots"],
                     help="N > 1: auto = fewest site shards that fit HBM, rest over root placements")
     return ap.parse_args()
@@ -303,7 +306,9 @@ def run_ours(args):
 
     comm_id = fresh_comm_id()
 
-    g = Partition(n, cnt, K, device=local)
+    lay = case.tree.sweep_layout()  # reference buffer counts + the spare buffers of the directed sweep
+    g = Partition(n, cnt, K, device=local, clv_buffers=lay["clv_buffers"], scale_buffers=lay["scale_buffers"],
+                  prob_matrices=lay["prob_matrices"])
     g.set_stream(torch.cuda.current_stream().cuda_stream)
     case.setup(g, sl)
     if G_s > 1:
@@ -319,8 +324,15 @@ def run_ours(args):
     placements = case.tree.root_count
     chunks = plan_root_shards(range(placements), G_r)
     roots = chunks[root_group]  # this rank's contiguous chunk of root ids
-    sw = case.sweep_schedule(roots, 0.5)
-    pm_off, mi, bl, op_off, ops = sw
+    if args.sweep == "directed":
+        # the tree is rooted at root 0 (full_schedule above): directed-CLV pass over this rank's chunk
+        pm_off, mi, bl, op_off, ops, pos = case.tree.generate_sweep_operations(roots[0], roots[-1] + 1, layout=lay)
+        pos = pos - roots[0]
+        sweep_flags = capi.RDK_SWEEP_KEEP_ROOT
+    else:
+        pm_off, mi, bl, op_off, ops = case.sweep_schedule(roots, 0.5)
+        pos = np.arange(len(roots))
+        sweep_flags = 0
     sw_arr = ops_array(ops)
     chunk_max = max(len(c) for c in chunks)
     gather_in = torch.zeros(chunk_max, dtype=torch.float64, device="cuda")
@@ -341,7 +353,9 @@ def run_ours(args):
         g.update_prob_matrices(full_pm, full_br)
         g.L.rdk_update_clvs(g.p, full_arr, len(full_ops))
         lh0 = g.root_loglikelihood(case.root_clv, case.root_scaler)
-        out = g.sweep_root_placements(pm_off, mi, bl, op_off, sw_arr, case.root_clv, case.root_scaler)
+        out = np.empty(len(pos))
+        out[pos] = g.sweep_root_placements(pm_off, mi, bl, op_off, sw_arr, case.root_clv, case.root_scaler,
+                                           flags=sweep_flags)
         return lh0, gather_placements(out)
 
     def barrier():
@@ -399,6 +413,7 @@ def run_ours(args):
                   nranks=G_s, rank=site_rank, comm_id=fresh_comm_id())
         m.initialize_partitions()
         m.set_params(rates=case.rates, freqs=case.freqs)
+        m.set_sweep_mode(m.SWEEP_DIRECTED if args.sweep == "directed" else m.SWEEP_PATH)
         part = C.cast(m.L.rdh_model_partition(m.h, 0), C.POINTER(capi.PartitionStruct))
         L = capi.load_engine()
 
@@ -445,7 +460,11 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args, placements, (G_s, G_r)),
+            "config": dict(workload_config(args, placements, (G_s, G_r)), sweep=(
+                "directed-CLV pre-order pass (1 CLV op + 1 root evaluation per placement; same bits as the "
+                "reference's loop)" if args.sweep == "directed" else
+                "reference-shaped: move_root path ops + root op per placement, one engine call"),
+                clv_ops_per_step=st["clv_ops"] / args.steps, root_evals_per_step=st["root_evals"] / args.steps),
             "clv_update_gbs": clv_gbs, "clv_update_gbs_per_gpu": clv_gbs / n_gpus,
             "algorithmic_bytes_per_step": total_alg_bytes / args.steps,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,

@@ -213,6 +213,29 @@ int rdk_sweep_root_placements(rdk_partition_t *partition,
                               unsigned int root_clv_index,
                               int root_scaler_index, double *out_lnl);
 
+/* The same sweep with options.  RDK_SWEEP_KEEP_ROOT: the LAST operation of a
+ * placement, when its parent is (root_clv_index, root_scaler_index), is only
+ * evaluated -- the root CLV and root scale buffer are not stored, so partition
+ * state seen through them is what it was before the call (log-likelihoods are
+ * unchanged: the root CLV is consumed in registers).  This is what the
+ * directed-CLV sweep (rooted_tree_t::generate_sweep_operations in the host
+ * mirror) uses: one pre-order pass over spare CLV buffers scores all 2n-3
+ * placements with ~1 CLV operation + 1 root evaluation each instead of a
+ * re-orientation path per placement. */
+#define RDK_SWEEP_KEEP_ROOT 1u
+int rdk_sweep_root_placements_ex(rdk_partition_t *partition,
+                                 unsigned int placements,
+                                 const unsigned int *params_indices,
+                                 const unsigned int *freqs_indices,
+                                 const unsigned int *pm_offsets,
+                                 const unsigned int *matrix_indices,
+                                 const double *branch_lengths,
+                                 const unsigned int *op_offsets,
+                                 const rdk_operation_t *operations,
+                                 unsigned int root_clv_index,
+                                 int root_scaler_index, unsigned int flags,
+                                 double *out_lnl);
+
 /* ---- site sharding across GPUs (new) --------------------------- */
 /* A partition holds a contiguous range of the alignment's site patterns.
  * site_offset must be a multiple of RDK_SHARD_ALIGN unless it is 0; the

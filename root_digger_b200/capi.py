@@ -20,6 +20,7 @@ RDK_ATTRIB_NONREV = 1 << 11
 RDK_GAMMA_RATES_MEAN = 0
 RDK_GAMMA_RATES_MEDIAN = 1
 RDK_SHARD_ALIGN = 1024
+RDK_SWEEP_KEEP_ROOT = 1
 
 
 class Operation(C.Structure):
@@ -125,6 +126,8 @@ def load_engine() -> C.CDLL:
     L.rdk_root_loglikelihood_multi.argtypes = [_pp, C.POINTER(Operation), _up, _up, _dp, C.c_uint, _dp]
     L.rdk_sweep_root_placements.argtypes = [_pp, C.c_uint, _up, _up, _up, _up, _dp, _up,
                                             C.POINTER(Operation), C.c_uint, C.c_int, _dp]
+    L.rdk_sweep_root_placements_ex.argtypes = [_pp, C.c_uint, _up, _up, _up, _up, _dp, _up,
+                                               C.POINTER(Operation), C.c_uint, C.c_int, C.c_uint, _dp]
     L.rdk_partition_set_shard.argtypes = [_pp, C.c_ulonglong, C.c_ulonglong]
     L.rdk_comm_unique_id.argtypes = [C.c_void_p]
     L.rdk_partition_attach_comm.argtypes = [_pp, C.c_int, C.c_int, C.c_void_p]
@@ -270,7 +273,7 @@ class Partition:
         return out
 
     def sweep_root_placements(self, pm_offsets, matrix_indices, branch_lengths, op_offsets, ops,
-                              root_clv_index: int, root_scaler_index: int):
+                              root_clv_index: int, root_scaler_index: int, flags: int = 0):
         pmo = np.ascontiguousarray(pm_offsets, dtype=np.uint32)
         mi = np.ascontiguousarray(matrix_indices, dtype=np.uint32)
         bl = np.ascontiguousarray(branch_lengths, dtype=np.float64)
@@ -278,9 +281,9 @@ class Partition:
         arr = ops if isinstance(ops, C.Array) else ops_array(ops)
         n = len(pmo) - 1
         out = np.zeros(n)
-        rc = self.L.rdk_sweep_root_placements(self.p, n, self._zeros, self._zeros, _ptr(pmo, _up), _ptr(mi, _up),
-                                              _ptr(bl, _dp), _ptr(opo, _up), arr, root_clv_index,
-                                              root_scaler_index, _ptr(out, _dp))
+        rc = self.L.rdk_sweep_root_placements_ex(self.p, n, self._zeros, self._zeros, _ptr(pmo, _up), _ptr(mi, _up),
+                                                 _ptr(bl, _dp), _ptr(opo, _up), arr, root_clv_index,
+                                                 root_scaler_index, flags, _ptr(out, _dp))
         if rc != RDK_SUCCESS:
             raise EngineError(_err(self.L))
         return out
@@ -402,6 +405,11 @@ def load_tree_lib(path: Path | None = None) -> C.CDLL:
     L.rdh_tree_generate_root_update_operations.argtypes = sig
     L.rdh_tree_generate_derivative_operations.argtypes = [vp, C.c_uint, C.c_double, C.POINTER(Operation), _up, _dp]
     L.rdh_tree_root_by.argtypes = [vp, C.c_uint, C.c_double]
+    L.rdh_tree_sweep_depth_bound.argtypes = [vp]
+    L.rdh_tree_sweep_depth_bound.restype = C.c_uint
+    L.rdh_tree_generate_sweep_operations.argtypes = [vp, C.c_uint, C.c_uint, C.c_uint, C.c_int, C.c_uint, C.c_uint,
+                                                     _up, _up, _up, _up, C.c_uint, _up, _dp, C.c_uint,
+                                                     C.POINTER(Operation), C.c_uint]
     L.rdh_tree_newick.argtypes = [vp, C.c_int]
     L.rdh_tree_newick.restype = vp
     L.rdh_free.argtypes = [vp]
@@ -508,6 +516,38 @@ class RootedTree:
             raise RuntimeError(self.L.rdh_last_error().decode())
         return op, np.array(pm[:], dtype=np.uint32), np.array(br[:], dtype=np.float64)
 
+    sweep_depth_bound = property(lambda s: s.L.rdh_tree_sweep_depth_bound(s.h))
+
+    def sweep_layout(self):
+        """buffer counts and first spare indices of a partition that can run the directed sweep:
+        dict(clv_buffers, scale_buffers, prob_matrices, clv0, scaler0, pm0, extra)"""
+        n, br, extra = self.tip_count, self.branch_count, self.sweep_depth_bound
+        return dict(clv_buffers=br + extra, scale_buffers=br + extra, prob_matrices=br + 3, clv0=n + br,
+                    scaler0=br, pm0=br, extra=extra)
+
+    def generate_sweep_operations(self, begin: int | None = None, end: int | None = None, layout=None):
+        """rooted_tree_t::generate_sweep_operations from the CURRENT root: the directed-CLV sweep of
+        root positions [begin, end).  Returns (pm_off, mi, bl, op_off, ops, root_pos): the arguments of
+        Partition.sweep_root_placements + the root position each placement scores."""
+        lay = layout or self.sweep_layout()
+        nroots = self.root_count
+        begin = 0 if begin is None else begin
+        end = nroots if end is None else end
+        pcap = nroots + 1
+        cap = 8 * self.tip_count + 16
+        pm_off, op_off, pos = (C.c_uint * pcap)(), (C.c_uint * pcap)(), (C.c_uint * pcap)()
+        pm, br, ops = (C.c_uint * cap)(), (C.c_double * cap)(), (Operation * cap)()
+        npl = C.c_uint()
+        if not self.L.rdh_tree_generate_sweep_operations(self.h, begin, end, lay["clv0"], lay["scaler0"], lay["pm0"],
+                                                         lay["extra"], C.byref(npl), pm_off, op_off, pos, nroots,
+                                                         pm, br, cap, ops, cap):
+            raise RuntimeError(self.L.rdh_last_error().decode())
+        q = npl.value
+        npm, nops = pm_off[q], op_off[q]
+        return (np.array(pm_off[: q + 1], dtype=np.uint32), np.array(pm[:npm], dtype=np.uint32),
+                np.array(br[:npm], dtype=np.float64), np.array(op_off[: q + 1], dtype=np.uint32),
+                [Operation(*ops[i].astuple()) for i in range(nops)], np.array(pos[:q], dtype=np.int64))
+
     def root_by(self, rid: int, ratio: float = 0.5):
         if not self.L.rdh_tree_root_by(self.h, rid, ratio):
             raise RuntimeError(self.L.rdh_last_error().decode())
@@ -565,6 +605,7 @@ def _bind_model(L: C.CDLL):
     L.rdh_model_root_count.restype = C.c_uint
     L.rdh_model_initialize_partitions.argtypes = [vp, C.c_int]
     L.rdh_model_set_fused.argtypes = [vp, C.c_int]
+    L.rdh_model_set_sweep_mode.argtypes = [vp, C.c_int]
     L.rdh_model_set_params.argtypes = [vp, C.c_uint, _dp, _dp, _dp]
     L.rdh_model_compute_lh.argtypes = [vp, C.c_uint, C.c_double, _dp]
     L.rdh_model_compute_lh_root.argtypes = [vp, C.c_uint, C.c_double, _dp]
@@ -698,6 +739,14 @@ class Model:
 
     def set_fused(self, on: bool):
         self.L.rdh_model_set_fused(self.h, 1 if on else 0)
+
+    SWEEP_SEQUENTIAL, SWEEP_PATH, SWEEP_DIRECTED = 0, 1, 2
+
+    def set_sweep_mode(self, mode: int):
+        """how sweep_root_lh scores the placements (identical values): 0 the reference's
+        move_root + compute_lh_root loop, 1 the same operations in one engine call, 2 (default)
+        one pre-order pass over directed CLVs"""
+        self._check(self.L.rdh_model_set_sweep_mode(self.h, mode))
 
     def set_params(self, rates=None, freqs=None, alpha=None, part: int = 0):
         r = np.ascontiguousarray(rates, dtype=np.float64) if rates is not None else None

@@ -1070,6 +1070,21 @@ extern "C" int rdk_sweep_root_placements(rdk_partition_t *p, unsigned int placem
                                          const rdk_operation_t *operations,
                                          unsigned int root_clv_index, int root_scaler_index,
                                          double *out_lnl) {
+  return rdk_sweep_root_placements_ex(p, placements, params_indices, freqs_indices, pm_offsets, matrix_indices,
+                                      branch_lengths, op_offsets, operations, root_clv_index,
+                                      root_scaler_index, 0u, out_lnl);
+}
+
+extern "C" int rdk_sweep_root_placements_ex(rdk_partition_t *p, unsigned int placements,
+                                            const unsigned int *params_indices,
+                                            const unsigned int *freqs_indices,
+                                            const unsigned int *pm_offsets,
+                                            const unsigned int *matrix_indices,
+                                            const double *branch_lengths,
+                                            const unsigned int *op_offsets,
+                                            const rdk_operation_t *operations,
+                                            unsigned int root_clv_index, int root_scaler_index,
+                                            unsigned int flags, double *out_lnl) {
   (void)params_indices;
   (void)freqs_indices;
   Engine *e = eng(p);
@@ -1111,6 +1126,11 @@ extern "C" int rdk_sweep_root_placements(rdk_partition_t *p, unsigned int placem
           in.flags |= kEval;
           in.slot = b;
           fused = true;
+          if (flags & RDK_SWEEP_KEEP_ROOT) {  // evaluate in registers, store nothing
+            in.flags &= ~kWrite;
+            in.parent = nullptr;
+            in.pscale = nullptr;
+          }
         }
         e->pend_bytes += op_bytes(e, in);
         e->pend_prog.push_back(in);

@@ -56,10 +56,15 @@ model_t::model_t(rooted_tree_t tree, const std::vector<msa_t> &msas,
     // the ARCH_* attributes of the reference select coraxlib CPU kernels; the
     // engine accepts and ignores them
     unsigned int attributes = RDK_ATTRIB_SITE_REPEATS | RDK_ATTRIB_NONREV;
+    // on top of what the reference asks for (src/model.cpp:159-168): spare CLV / scale
+    // buffers for the directed CLVs of the placement sweep (one per depth level) and three
+    // spare P-matrices (rooted_tree_t::generate_sweep_operations); the engine allocates a
+    // CLV on first use, so unused spares cost only their scale buffer
+    _sweep_extra = _tree.sweep_depth_bound();
     rdk_partition_t *p = rdk_partition_create(
-        _tree.tip_count(), _tree.branch_count(), msa.states(), msa.length(), _submodels,
-        _tree.branch_count(), static_cast<unsigned int>(_rate_rates[pi].size()), _tree.branch_count(),
-        attributes);
+        _tree.tip_count(), _tree.branch_count() + _sweep_extra, msa.states(), msa.length(), _submodels,
+        _tree.branch_count() + 3, static_cast<unsigned int>(_rate_rates[pi].size()),
+        _tree.branch_count() + _sweep_extra, attributes);
     if (!p) throw std::runtime_error("partition could not be created: " + engine_error());
     _partitions.push_back(p);
 #ifndef RD_BACKEND_ORACLE
@@ -523,11 +528,30 @@ std::vector<double> model_t::sweep_root_lh(size_t begin, size_t end) {
                                            all_roots.begin() + (std::ptrdiff_t)end);
   std::vector<double> lh(roots.size(), 0.0);
   if (roots.empty()) return lh;
-  if (!_fused) {
+  if (_sweep_mode == sweep_mode_t::sequential) {
     for (size_t r = 0; r < roots.size(); ++r) {
       move_root(roots[r]);
       lh[r] = compute_lh_root(roots[r]);
     }
+    return lh;
+  }
+  if (_sweep_mode == sweep_mode_t::directed) {
+    // one pre-order pass over directed CLVs from the current root; same bits as the loop
+    // above (tree.hpp), ~1 CLV operation + 1 root evaluation per placement
+    auto sw = _tree.generate_sweep_operations(begin, end, _tree.tip_count() + _tree.branch_count(),
+                                              (int)_tree.branch_count(), _tree.branch_count(), _sweep_extra);
+    std::vector<double> part(sw.root_pos.size());
+    for (size_t i = 0; i < _partitions.size(); ++i) {
+      int rc = rdk_sweep_root_placements_ex(_partitions[i], (unsigned)sw.root_pos.size(),
+                                            _param_indicies[i].data(), _param_indicies[i].data(),
+                                            sw.pm_off.data(), sw.mi.data(), sw.bl.data(), sw.op_off.data(),
+                                            sw.ops.data(), _tree.root_clv_index(), _tree.root_scaler_index(),
+                                            RDK_SWEEP_KEEP_ROOT, part.data());
+      if (rc == RDK_FAILURE) throw std::runtime_error(engine_error());
+      for (size_t q = 0; q < part.size(); ++q) lh[sw.root_pos[q] - begin] += part[q];
+    }
+    for (double v : lh)
+      if (std::isnan(v)) throw std::runtime_error("lh at root is not a number: " + std::to_string(v));
     return lh;
   }
   std::vector<unsigned int>    pm_off{0}, op_off{0}, mi;

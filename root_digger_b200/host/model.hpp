@@ -112,7 +112,15 @@ public:
   void move_root(const root_location_t &new_root);
   // use the fused engine entry points (rdk_sweep_root_placements) where the
   // reference loops over move_root + compute_lh_root; results are identical
-  void set_fused(bool on) { _fused = on; }
+  void set_fused(bool on) { _sweep_mode = on ? sweep_mode_t::directed : sweep_mode_t::sequential; }
+  // how sweep_root_lh / suggest_roots_lh score the 2n-3 placements (identical values):
+  //   sequential  the reference's loop, move_root + compute_lh_root per root (src/model.cpp:871-874)
+  //   path        the same operations recorded into ONE rdk_sweep_root_placements call
+  //   directed    one pre-order pass over directed CLVs (rooted_tree_t::generate_sweep_operations);
+  //               leaves the tree rooted where it was
+  enum class sweep_mode_t { sequential = 0, path = 1, directed = 2 };
+  void         set_sweep_mode(sweep_mode_t m) { _sweep_mode = m; }
+  sweep_mode_t sweep_mode() const { return _sweep_mode; }
 
   rdk_partition_t *partition(size_t i) { return _partitions[i]; }
   size_t           partition_count() const { return _partitions.size(); }
@@ -179,7 +187,8 @@ private:
   bool                                   _invariant_sites;
   uint64_t                               _seed;
   bool                                   _early_stop;
-  bool                                   _fused = true;
+  sweep_mode_t                           _sweep_mode = sweep_mode_t::directed;
+  unsigned int                           _sweep_extra = 0;
   static constexpr unsigned int          _submodels = 1;
 };
 

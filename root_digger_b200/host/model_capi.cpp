@@ -183,6 +183,16 @@ extern "C" int rdh_model_set_fused(void *h, int on) {
   return 1;
 }
 
+// 0 = sequential (the reference's loop), 1 = path (same operations, one engine call),
+// 2 = directed (one pre-order pass over directed CLVs); identical values
+extern "C" int rdh_model_set_sweep_mode(void *h, int mode) {
+  RDH_TRY({
+    if (mode < 0 || mode > 2) throw std::invalid_argument("sweep mode must be 0, 1 or 2");
+    H(h).model->set_sweep_mode(static_cast<model_t::sweep_mode_t>(mode));
+    return 1;
+  })
+}
+
 extern "C" int rdh_model_set_params(void *h, unsigned part, const double *rates12, const double *freqs4,
                                     const double *alpha) {
   RDH_TRY({

@@ -751,6 +751,149 @@ rooted_tree_t::generate_root_update_operations(const root_location_t &new_root) 
   return std::make_tuple(ops, pm, br);
 }
 
+// ---- the directed-CLV placement sweep (see tree.hpp) --------------------------
+namespace {
+// height in edges of the subtree hanging below c (c faces up); diam = longest path seen
+unsigned height_below(const unode_t *c, unsigned &diam) {
+  if (!c->next) return 0;
+  unsigned h1 = height_below(c->next->back, diam) + 1, h2 = height_below(c->next->next->back, diam) + 1;
+  diam = std::max(diam, h1 + h2);
+  return std::max(h1, h2);
+}
+}  // namespace
+
+unsigned int rooted_tree_t::sweep_depth_bound() const {
+  // the depth of any edge below any root edge is at most the diameter of the tree
+  unsigned              diam = 0;
+  std::vector<unsigned> tops;
+  const unode_t        *v = _tree->vroot;
+  const unode_t        *s = v;
+  do {
+    tops.push_back(height_below(s->back, diam) + 1);
+    s = s->next;
+  } while (s && s != v);
+  std::sort(tops.rbegin(), tops.rend());
+  if (tops.size() >= 2) diam = std::max(diam, tops[0] + tops[1]);
+  return diam + 1;
+}
+
+rooted_tree_t::sweep_schedule_t rooted_tree_t::generate_sweep_operations(size_t begin, size_t end,
+                                                                         unsigned int clv0, int scaler0,
+                                                                         unsigned int pm0,
+                                                                         unsigned int extra) const {
+  if (!rooted() || _current_rl.edge == nullptr)
+    throw std::runtime_error("generate_sweep_operations: the tree has no current root "
+                             "(call generate_operations / root_by first)");
+  if (begin > end || end > _roots.size()) throw std::invalid_argument("generate_sweep_operations: bad root range");
+  sweep_schedule_t out;
+  if (begin == end) return out;
+
+  const unode_t     *lchild = _tree->vroot->back, *rchild = _tree->vroot->next->back;
+  const unsigned int ML = pm0, MR = pm0 + 1, MC = pm0 + 2;
+  const double       L0 = _current_rl.saved_brlen;
+
+  // position in roots() of the edge behind each unode (both end points)
+  std::unordered_map<const unode_t *, size_t> pos_of;
+  for (size_t i = 0; i < _roots.size(); ++i) {
+    const unode_t *a = _roots[i].edge;
+    const unode_t *b = a == lchild ? rchild : (a == rchild ? lchild : a->back);
+    pos_of[a] = i;
+    pos_of[b] = i;
+  }
+  auto requested = [&](const unode_t *c) {
+    size_t i = pos_of.at(c);
+    return i >= begin && i < end;
+  };
+  // does the subtree below c, the edge above c included, hold a requested placement?
+  std::unordered_map<const unode_t *, bool>  needed;
+  std::function<bool(const unode_t *)> mark = [&](const unode_t *c) {
+    bool need = requested(c);
+    if (c->next) {
+      bool a = mark(c->next->back), b = mark(c->next->next->back);
+      need = need || a || b;
+    }
+    needed[c] = need;
+    return need;
+  };
+  mark(lchild);
+  mark(rchild);
+
+  struct ref_t {
+    unsigned int clv;
+    int          scaler;
+  };
+  std::vector<char> pm_seen((size_t)pm0 + 3, 0);
+  auto use_pm = [&](unsigned int idx, double len) {
+    if (idx < pm_seen.size() && pm_seen[idx]) return;
+    if (idx < pm_seen.size()) pm_seen[idx] = 1;
+    out.mi.push_back(idx);
+    out.bl.push_back(len);
+  };
+  // close a placement: the two root half-branches and the root operation; child1 is the
+  // end point root_by would make the left child (src/tree.cpp:273-320)
+  auto emit_placement = [&](const unode_t *c, ref_t below, ref_t above) {
+    const size_t           i = pos_of.at(c);
+    const root_location_t &rl = _roots[i];
+    out.mi.push_back(ML);
+    out.bl.push_back(rl.brlen());
+    out.mi.push_back(MR);
+    out.bl.push_back(rl.brlen_compliment());
+    const bool      c_is_left = rl.edge == c;
+    const ref_t     l = c_is_left ? below : above, r = c_is_left ? above : below;
+    rdk_operation_t op;
+    op.parent_clv_index = root_clv_index();
+    op.parent_scaler_index = root_scaler_index();
+    op.child1_clv_index = l.clv;
+    op.child1_scaler_index = l.scaler;
+    op.child1_matrix_index = ML;
+    op.child2_clv_index = r.clv;
+    op.child2_scaler_index = r.scaler;
+    op.child2_matrix_index = MR;
+    out.ops.push_back(op);
+    out.pm_off.push_back((unsigned)out.mi.size());
+    out.op_off.push_back((unsigned)out.ops.size());
+    out.root_pos.push_back(i);
+  };
+
+  std::function<void(const unode_t *, ref_t, unsigned int, double, unsigned int)> descend;
+  // c faces up; `up` is the CLV on the far side of the edge above c, directed towards c
+  auto handle_edge = [&](const unode_t *c, ref_t up, unsigned int depth) {
+    if (requested(c)) emit_placement(c, ref_t{c->clv_index, c->scaler_index}, up);
+    descend(c, up, c->pmatrix_index, c->length, depth + 1);
+  };
+  descend = [&](const unode_t *c, ref_t up, unsigned int edge_pm, double edge_len, unsigned int depth) {
+    if (!c->next) return;
+    const unode_t *k[2] = {c->next->back, c->next->next->back};
+    for (int i = 0; i < 2; ++i) {
+      const unode_t *child = k[i], *sib = k[1 - i];
+      if (!needed.at(child)) continue;
+      if (depth >= extra)
+        throw std::runtime_error("generate_sweep_operations: the sweep needs more directed-CLV buffers "
+                                 "than were set aside (sweep_depth_bound)");
+      const ref_t U{clv0 + depth, scaler0 + (int)depth};
+      use_pm(edge_pm, edge_len);
+      use_pm(sib->pmatrix_index, sib->length);
+      rdk_operation_t op;
+      op.parent_clv_index = U.clv;
+      op.parent_scaler_index = U.scaler;
+      op.child1_clv_index = up.clv;
+      op.child1_scaler_index = up.scaler;
+      op.child1_matrix_index = edge_pm;
+      op.child2_clv_index = sib->clv_index;
+      op.child2_scaler_index = sib->scaler_index;
+      op.child2_matrix_index = sib->pmatrix_index;
+      out.ops.push_back(op);
+      handle_edge(child, U, depth);
+    }
+  };
+
+  const ref_t L{lchild->clv_index, lchild->scaler_index}, R{rchild->clv_index, rchild->scaler_index};
+  if (requested(lchild)) emit_placement(lchild, L, R);
+  descend(lchild, R, MC, L0, 0);
+  descend(rchild, L, MC, L0, 0);
+  return out;
+}
+
 void rooted_tree_t::clear_traversal_data() {
   for (auto &u : _tree->arena) u.mark = 0;
 }

@@ -148,6 +148,35 @@ public:
               generate_derivative_operations(const root_location_t &root);
   op_bundle_t generate_root_update_operations(const root_location_t &new_root);
 
+  // ---- B200-first addition (no counterpart in src/tree.hpp) -------------------
+  // The placement sweep of suggest_roots_lh (src/model.cpp:865-889) as ONE pre-order
+  // pass over DIRECTED CLVs instead of 2n-3 move_root + compute_lh_root rounds.
+  // Precondition: the tree is rooted and every inner CLV is valid for the current
+  // root (compute_lh).  For the edge (v, a), a below v seen from the current root,
+  //   U(a) = (P(parent edge of v) U(v)) o (P(sibling edge) D(sibling))
+  // is the CLV at v directed towards a; it is exactly the CLV move_root would leave
+  // in v's buffer after re-rooting on (v, a) -- same two children, same P-matrices,
+  // a commutative product -- so the root log-likelihood of every placement has the
+  // same bits as the reference's loop.  The U's live in `extra` spare CLV / scale
+  // buffers (one per depth level: the DFS only needs the current root-to-edge
+  // stack) starting at clv0 / scaler0; three spare P-matrix indices starting at
+  // pm0 hold the two root half-branches and the full length of the current root
+  // edge, so NOTHING the reference-shaped calls rely on is modified: the tree
+  // stays rooted where it was and its CLVs, scalers and P-matrices keep their
+  // values.  The output has the shape rdk_sweep_root_placements takes; the last
+  // operation of each placement is the root operation.  placement q scores the
+  // root at position root_pos[q] of roots().
+  struct sweep_schedule_t {
+    std::vector<unsigned int>    pm_off{0}, op_off{0}, mi;
+    std::vector<double>          bl;
+    std::vector<rdk_operation_t> ops;
+    std::vector<size_t>          root_pos;
+  };
+  // spare CLV / scale buffers generate_sweep_operations can need for ANY current root
+  unsigned int     sweep_depth_bound() const;
+  sweep_schedule_t generate_sweep_operations(size_t begin, size_t end, unsigned int clv0, int scaler0,
+                                             unsigned int pm0, unsigned int extra) const;
+
   void root_by(unsigned int root_id) { root_by(_roots[root_id]); }
   void root_by(const root_location_t &);
   void update_root(root_location_t);

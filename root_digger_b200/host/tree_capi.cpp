@@ -163,6 +163,37 @@ extern "C" int rdh_tree_generate_root_update_operations(void *t, unsigned root_i
   })
 }
 
+extern "C" unsigned rdh_tree_sweep_depth_bound(void *t) { return T(t).sweep_depth_bound(); }
+
+// the directed-CLV placement sweep of root positions [begin, end) from the CURRENT root
+// (rooted_tree_t::generate_sweep_operations); flat outputs in the shape
+// rdk_sweep_root_placements takes.  pm_off / op_off / root_pos hold placements (+1) entries.
+extern "C" int rdh_tree_generate_sweep_operations(void *t, unsigned begin, unsigned end, unsigned clv0,
+                                                  int scaler0, unsigned pm0, unsigned extra,
+                                                  unsigned *n_placements, unsigned *pm_off,
+                                                  unsigned *op_off, unsigned *root_pos,
+                                                  unsigned placements_cap, unsigned *pm, double *br,
+                                                  unsigned pm_cap, rdk_operation_t *ops,
+                                                  unsigned ops_cap) {
+  RDH_GUARD({
+    auto s = T(t).generate_sweep_operations(begin, end, clv0, scaler0, pm0, extra);
+    if (s.root_pos.size() > placements_cap || s.mi.size() > pm_cap || s.ops.size() > ops_cap) {
+      g_err = "output buffers too small";
+      return 0;
+    }
+    *n_placements = (unsigned)s.root_pos.size();
+    for (size_t i = 0; i < s.pm_off.size(); ++i) pm_off[i] = s.pm_off[i];
+    for (size_t i = 0; i < s.op_off.size(); ++i) op_off[i] = s.op_off[i];
+    for (size_t i = 0; i < s.root_pos.size(); ++i) root_pos[i] = (unsigned)s.root_pos[i];
+    for (size_t i = 0; i < s.mi.size(); ++i) {
+      pm[i] = s.mi[i];
+      br[i] = s.bl[i];
+    }
+    for (size_t i = 0; i < s.ops.size(); ++i) ops[i] = s.ops[i];
+    return 1;
+  })
+}
+
 extern "C" int rdh_tree_root_by(void *t, unsigned root_id, double ratio) {
   RDH_GUARD({
     auto rl = T(t).root_location((size_t)root_id);

@@ -61,4 +61,19 @@ static inline int rdk_sweep_root_placements(rdo_partition_t *p, unsigned int pla
   }
   return RDO_SUCCESS;
 }
+/* the flags only concern what is stored, never the values returned */
+#define RDK_SWEEP_KEEP_ROOT 1u
+static inline int rdk_sweep_root_placements_ex(rdo_partition_t *p, unsigned int placements,
+                                               const unsigned int *params_indices,
+                                               const unsigned int *freqs_indices,
+                                               const unsigned int *pm_offsets,
+                                               const unsigned int *matrix_indices,
+                                               const double *branch_lengths, const unsigned int *op_offsets,
+                                               const rdo_operation_t *operations, unsigned int root_clv_index,
+                                               int root_scaler_index, unsigned int flags, double *out_lnl) {
+  (void)flags;
+  return rdk_sweep_root_placements(p, placements, params_indices, freqs_indices, pm_offsets, matrix_indices,
+                                   branch_lengths, op_offsets, operations, root_clv_index, root_scaler_index,
+                                   out_lnl);
+}
 #endif

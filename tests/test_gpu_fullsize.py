@@ -41,7 +41,9 @@ def canonical_tree_sum(x):
 def cfg2():
     from root_digger_b200.capi import Partition, gamma_cats
     case = Case(500, 100000, 4, seed=0x5EED0002, data="iid", alpha=1.0, gamma_cats=gamma_cats)
-    g = Partition(case.n, case.S, case.K)
+    lay = case.tree.sweep_layout()
+    g = Partition(case.n, case.S, case.K, clv_buffers=lay["clv_buffers"], scale_buffers=lay["scale_buffers"],
+                  prob_matrices=lay["prob_matrices"])
     case.setup(g)
     yield case, g
     g.close()
@@ -99,6 +101,36 @@ def test_cfg2_sweep_is_path_independent(cfg2):
     rev = list(range(nroots - 1, -1, -1))
     out_rev = g.sweep_root_placements(*case.sweep_schedule(rev, 0.5), case.root_clv, case.root_scaler)
     assert same_bits(out_rev[::-1], out[:nroots])
+
+
+def test_cfg2_directed_sweep_equals_path_sweep(cfg2):
+    """at full size: the directed-CLV pre-order pass == the reference-shaped sweep, bit for bit, from
+    two different current roots; its chunks concatenate to the whole; nothing it does is visible in
+    the partition afterwards"""
+    from root_digger_b200.capi import RDK_SWEEP_KEEP_ROOT
+    case, g = cfg2
+    lay = case.tree.sweep_layout()
+    nroots = case.tree.root_count
+    compute_lh(g, case.full_schedule(0, 0.5), case.root_clv, case.root_scaler)
+    want = g.sweep_root_placements(*case.sweep_schedule(list(range(nroots)), 0.5), case.root_clv, case.root_scaler)
+    for start in (0, nroots // 2):
+        lh0 = compute_lh(g, case.full_schedule(start, 0.5), case.root_clv, case.root_scaler)
+        *sw, pos = case.tree.generate_sweep_operations(layout=lay)
+        assert len(pos) == nroots and len(sw[4]) == 2 * nroots - 1
+        got = np.empty(nroots)
+        got[pos] = g.sweep_root_placements(*sw, case.root_clv, case.root_scaler, flags=RDK_SWEEP_KEEP_ROOT)
+        assert same_bits(got, want), start
+        assert same_bits([lh0], [compute_lh_root(g, case.derivative_schedule(start, 0.5), case.root_clv,
+                                                 case.root_scaler)])
+    # root-placement chunks (exhaustive mode's distribution over ranks)
+    compute_lh(g, case.full_schedule(0, 0.5), case.root_clv, case.root_scaler)
+    parts = []
+    for lo, hi in ((0, 250), (250, 251), (251, nroots)):
+        *sw, pos = case.tree.generate_sweep_operations(lo, hi, layout=lay)
+        out = np.empty(hi - lo)
+        out[pos - lo] = g.sweep_root_placements(*sw, case.root_clv, case.root_scaler, flags=RDK_SWEEP_KEEP_ROOT)
+        parts.append(out)
+    assert same_bits(np.concatenate(parts), want)
 
 
 def test_cfg2_site_shards_are_independent(cfg2):

@@ -74,10 +74,13 @@ def test_sweep_and_root_ranking_identical(libs):
     o.compute_lh(0)
     a, b = g.sweep_root_lh(), o.sweep_root_lh()
     assert np.array_equal(bits(a), bits(b))
-    g.compute_lh(0)
-    g.set_fused(False)           # the reference's own loop: move_root + compute_lh_root per root
-    c = g.sweep_root_lh()
-    assert np.array_equal(bits(a), bits(c))
+    for mode in (g.SWEEP_SEQUENTIAL, g.SWEEP_PATH, g.SWEEP_DIRECTED):
+        # the reference's own loop (move_root + compute_lh_root per root), the same operations in one
+        # engine call, the directed-CLV pass: same bits, from a different current root too
+        g.compute_lh(7, 0.2)
+        g.set_sweep_mode(mode)
+        c = g.sweep_root_lh()
+        assert np.array_equal(bits(a), bits(c)), mode
     assert np.array_equal(np.argsort(-a, kind="stable"), np.argsort(-b, kind="stable"))
 
 

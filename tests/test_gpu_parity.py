@@ -174,6 +174,49 @@ def test_sweep_equals_sequential_calls(n, S, K, data):
         assert same_bits(g.get_clv(idx), o.get_clv(idx))
 
 
+@pytest.mark.parametrize("n,S,K,data", [(12, 500, 4, "evolved"), (80, 1200, 4, "ambiguous"), (300, 129, 2, "iid"),
+                                        (150, 700, 4, "iid")])
+def test_directed_sweep_equals_the_reference_loop(n, S, K, data):
+    """the directed-CLV sweep (rooted_tree_t::generate_sweep_operations + RDK_SWEEP_KEEP_ROOT) on the
+    engine == the reference's move_root + compute_lh_root loop on the oracle, bit for bit, from a
+    non-trivial current root; scalers fire in the iid cases; partition state is left untouched"""
+    from root_digger_b200.capi import RDK_SWEEP_KEEP_ROOT, Partition
+    case = Case(n, S, K, seed=23 + n, data=data, weights="random")
+    lay = case.tree.sweep_layout()
+    kw = dict(clv_buffers=lay["clv_buffers"], scale_buffers=lay["scale_buffers"], prob_matrices=lay["prob_matrices"])
+    g, o = Partition(case.n, case.S, case.K, **kw), OraclePartition(case.n, case.S, case.K, **kw)
+    case.setup(g)
+    case.setup(o)
+    start = case.tree.root_count // 3
+    s0 = case.full_schedule(start, 0.4)
+    lh0 = compute_lh(g, s0, case.root_clv, case.root_scaler)
+    compute_lh(o, s0, case.root_clv, case.root_scaler)
+    *sw, pos = case.tree.generate_sweep_operations(layout=lay)
+    assert sorted(pos.tolist()) == list(range(case.tree.root_count))
+    # ~1 CLV operation + 1 root evaluation per placement
+    assert len(sw[4]) <= 2 * case.tree.root_count
+    root_before = g.get_clv(case.root_clv).copy()
+    got = np.empty(len(pos))
+    got[pos] = g.sweep_root_placements(*sw, case.root_clv, case.root_scaler, flags=RDK_SWEEP_KEEP_ROOT)
+    same = np.empty(len(pos))
+    same[pos] = o.sweep_root_placements(*sw, case.root_clv, case.root_scaler, mode=MODE_ENGINE)
+    assert same_bits(got, same)                       # same schedule on the oracle
+    assert same_bits(root_before, g.get_clv(case.root_clv))
+    assert case.tree.rooted and compute_lh_root(g, case.derivative_schedule(start, 0.4), case.root_clv,
+                                                case.root_scaler) == lh0
+    # the reference's loop on the oracle, in root-id order
+    compute_lh(o, case.full_schedule(start, 0.4), case.root_clv, case.root_scaler)
+    roots = list(range(case.tree.root_count))
+    want = o.sweep_root_placements(*case.sweep_schedule(roots, 0.5), case.root_clv, case.root_scaler, mode=MODE_ENGINE)
+    assert same_bits(got, want)
+    compute_lh(o, case.full_schedule(start, 0.4), case.root_clv, case.root_scaler)
+    want_ref = o.sweep_root_placements(*case.sweep_schedule(roots, 0.5), case.root_clv, case.root_scaler,
+                                       mode=MODE_REFERENCE)
+    assert rel_err(got, want_ref) <= RTOL
+    if data == "iid":
+        assert max(int(g.get_scaler(lay["scaler0"]).max()), int(g.get_scaler(case.root_scaler).max())) > 0
+
+
 def test_launch_configs_do_not_change_results():
     case = Case(25, 5000, 4, seed=11, data="ambiguous", weights="random")
     g, o = make(case)

@@ -71,6 +71,30 @@ def test_fused_sweep_equals_reference_loop(lib):
     assert np.array_equal(a.view(np.uint64), b.view(np.uint64))
 
 
+@pytest.mark.parametrize("name,K", [("10.fasta", 1), ("10.fasta", 4), ("101.phy", 4)])
+def test_directed_sweep_has_the_bits_of_the_reference_loop(lib, name, K):
+    """the three sweep modes -- the reference's move_root + compute_lh_root loop
+    (src/model.cpp:871-874), the same operations as one engine call, and the directed-CLV
+    pre-order pass -- give bit-identical log-likelihoods from ANY current root, and the
+    directed pass leaves the model where it was (same root, same compute_lh_root)"""
+    m = make_model(lib, name, K=K, uniform=(name != "101.phy"))
+    nroots = m.root_count
+    for start in sorted({0, 3, nroots // 2, nroots - 1}):
+        out = []
+        for mode in (m.SWEEP_SEQUENTIAL, m.SWEEP_PATH, m.SWEEP_DIRECTED):
+            lh0 = m.compute_lh(start, 0.3)
+            m.set_sweep_mode(mode)
+            out.append(m.sweep_root_lh())
+        assert np.array_equal(out[0].view(np.uint64), out[1].view(np.uint64)), start
+        assert np.array_equal(out[0].view(np.uint64), out[2].view(np.uint64)), start
+        assert m.compute_lh_root(start, 0.3) == lh0           # directed: state untouched
+        # two directed sweeps in a row, and a directed chunk
+        again = m.sweep_root_lh()
+        assert np.array_equal(again.view(np.uint64), out[2].view(np.uint64))
+        part = m.sweep_root_lh(2, 7)
+        assert np.array_equal(part.view(np.uint64), out[2][2:7].view(np.uint64))
+
+
 def test_root_sharded_sweep_equals_full_sweep(lib):
     """root placements distributed over ranks (src/model.cpp:1899-1907 rule): every rank
     starts from the CLVs of root 0 and sweeps its own chunk; the chunks concatenate to
