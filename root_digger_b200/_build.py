@@ -94,7 +94,8 @@ def build_lbfgsb(force: bool = False) -> Path | None:
 
 
 def host_sources():
-    return [HOST / "tree.cpp", HOST / "tree_capi.cpp", HOST / "msa.cpp", HOST / "partition_file.cpp", HOST / "model.cpp",
+    return [HOST / "tree.cpp", HOST / "tree_capi.cpp", HOST / "msa.cpp", HOST / "partition_file.cpp", HOST / "checkpoint.cpp",
+            HOST / "checkpoint_capi.cpp", HOST / "model.cpp",
             HOST / "lbfgsb_driver.cpp", HOST / "model_capi.cpp"]
 
 

@@ -626,7 +626,146 @@ def _bind_model(L: C.CDLL):
     L.rdh_model_get_params.argtypes = [vp, C.c_uint, _dp, _dp, _dp]
     L.rdh_model_partition.argtypes = [vp, C.c_uint]
     L.rdh_model_partition.restype = vp
+    L.rdh_model_set_checkpoint.argtypes = [vp, C.c_char_p]
     L._rdh_model_bound = True
+
+
+def _bind_checkpoint(L: C.CDLL):
+    if getattr(L, "_rdh_ckp_bound", False):
+        return
+    vp, ull = C.c_void_p, C.c_ulonglong
+    ullp = C.POINTER(ull)
+    opts = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, ullp, C.c_uint, ull, ull, ull, C.c_int, C.c_int, C.c_int]
+    L.rdh_ckp_open.restype = vp
+    L.rdh_ckp_open.argtypes = [C.c_char_p]
+    L.rdh_ckp_close.argtypes = [vp]
+    L.rdh_ckp_close.restype = None
+    L.rdh_ckp_existing.argtypes = [vp]
+    L.rdh_ckp_filename.argtypes = [vp, C.c_char_p, C.c_uint]
+    L.rdh_ckp_save_options.argtypes = [vp] + opts
+    L.rdh_ckp_load_options.argtypes = [vp] + opts + [C.c_char_p, C.c_uint, ullp, _up]
+    L.rdh_ckp_write.argtypes = [vp, ull, C.c_double, C.c_double, C.c_uint, _dp, _dp, _dp, _dp, C.c_uint]
+    L.rdh_ckp_read.argtypes = [vp, C.c_uint, ullp, _dp, _dp, _up, _up]
+    L.rdh_ckp_read_params.argtypes = [vp, C.c_uint, C.c_uint, _dp, _dp, _dp, _dp, C.c_uint]
+    L.rdh_ckp_completed.argtypes = [vp, C.c_uint, ullp, _up]
+    L.rdh_ckp_needs_cleaning.argtypes = [vp]
+    L.rdh_ckp_clean.argtypes = [vp]
+    L.rdh_ckp_checksum_result.argtypes = [ull, C.c_double, C.c_double]
+    L.rdh_ckp_checksum_result.restype = C.c_uint
+    L.rdh_ckp_checksum_params.argtypes = [C.c_uint, _dp, _dp, _dp, _dp, C.c_uint]
+    L.rdh_ckp_checksum_params.restype = C.c_uint
+    L._rdh_ckp_bound = True
+
+
+class Checkpoint:
+    """checkpoint_t (reference src/checkpoint.hpp:251-301): the "<prefix>.ckp" result log in the
+    reference's on-disk format (prefix=None: the in-memory log)."""
+
+    OPTION_DEFAULTS = dict(msa="", tree="", prefix="", model_string="", rate_cats=(1,), seed=0, min_roots=1,
+                           threads=0, exhaustive=False, early_stop=0, strategy=2)
+
+    def __init__(self, prefix: str | None, lib: C.CDLL | None = None):
+        self.L = lib or load_tree_lib()
+        _bind_checkpoint(self.L)
+        self.h = self.L.rdh_ckp_open(prefix.encode() if prefix is not None else None)
+        if not self.h:
+            raise RuntimeError("checkpoint_t could not be opened: " + self.L.rdh_last_error().decode())
+        self.h = C.c_void_p(self.h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.rdh_ckp_close(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def _check(self, rc):
+        if rc == 0:
+            raise RuntimeError(self.L.rdh_last_error().decode())
+        return rc
+
+    @property
+    def existing(self) -> bool:
+        return bool(self.L.rdh_ckp_existing(self.h))
+
+    @property
+    def filename(self) -> str:
+        buf = C.create_string_buffer(4096)
+        self._check(self.L.rdh_ckp_filename(self.h, buf, 4096))
+        return buf.value.decode()
+
+    def _opts(self, kw):
+        o = dict(self.OPTION_DEFAULTS)
+        o.update(kw)
+        rc = (C.c_ulonglong * max(1, len(o["rate_cats"])))(*o["rate_cats"])
+        return [o["msa"].encode(), o["tree"].encode(), o["prefix"].encode(), o["model_string"].encode(), rc,
+                len(o["rate_cats"]), o["seed"], o["min_roots"], o["threads"], int(o["exhaustive"]),
+                int(o["early_stop"]), int(o["strategy"])]
+
+    def save_options(self, **kw):
+        self._check(self.L.rdh_ckp_save_options(self.h, *self._opts(kw)))
+
+    def load_options(self, **kw) -> dict:
+        """stored options vs the given ones: {"equal": bool, "msa": str, "seed": int, "n_rate_cats": int}"""
+        buf = C.create_string_buffer(4096)
+        seed, nrc = C.c_ulonglong(), C.c_uint()
+        rc = self._check(self.L.rdh_ckp_load_options(self.h, *self._opts(kw), buf, 4096, C.byref(seed), C.byref(nrc)))
+        return {"equal": rc == 2, "msa": buf.value.decode(), "seed": seed.value, "n_rate_cats": nrc.value}
+
+    @staticmethod
+    def _flat(params, K):
+        n = len(params)
+        rates = np.ascontiguousarray([p["rates"] for p in params], dtype=np.float64).reshape(n, 12) if n else np.zeros((0, 12))
+        freqs = np.ascontiguousarray([p["freqs"] for p in params], dtype=np.float64).reshape(n, 4) if n else np.zeros((0, 4))
+        alpha = np.ascontiguousarray([p["alpha"] for p in params], dtype=np.float64).reshape(n) if n else np.zeros(0)
+        w = np.ascontiguousarray([p["weights"] for p in params], dtype=np.float64).reshape(n, K) if n else np.zeros((0, K))
+        return n, rates, freqs, alpha, w
+
+    def write(self, root_id: int, llh: float, alpha: float, params=(), K: int = 4):
+        n, r, f, a, w = self._flat(list(params), K)
+        self._check(self.L.rdh_ckp_write(self.h, root_id, llh, alpha, n, _ptr(r, _dp), _ptr(f, _dp), _ptr(a, _dp),
+                                         _ptr(w, _dp), K))
+
+    def read_results(self):
+        cap = 1 << 16
+        ids = np.zeros(cap, dtype=np.uint64)
+        llh, alpha = np.zeros(cap), np.zeros(cap)
+        nparts = np.zeros(cap, dtype=np.uint32)
+        got = C.c_uint()
+        self._check(self.L.rdh_ckp_read(self.h, cap, _ptr(ids, C.POINTER(C.c_ulonglong)), _ptr(llh, _dp),
+                                        _ptr(alpha, _dp), _ptr(nparts, _up), C.byref(got)))
+        k = min(got.value, cap)
+        return [(int(ids[i]), float(llh[i]), float(alpha[i]), int(nparts[i])) for i in range(k)]
+
+    def read_params(self, index: int, part: int = 0, K: int = 4) -> dict:
+        r, f, w = np.zeros(12), np.zeros(4), np.zeros(K)
+        a = C.c_double()
+        self._check(self.L.rdh_ckp_read_params(self.h, index, part, _ptr(r, _dp), _ptr(f, _dp), C.byref(a),
+                                               _ptr(w, _dp), K))
+        return {"rates": r, "freqs": f, "alpha": a.value, "weights": w}
+
+    def completed_indicies(self):
+        cap = 1 << 16
+        ids = np.zeros(cap, dtype=np.uint64)
+        got = C.c_uint()
+        self._check(self.L.rdh_ckp_completed(self.h, cap, _ptr(ids, C.POINTER(C.c_ulonglong)), C.byref(got)))
+        return [int(x) for x in ids[:min(got.value, cap)]]
+
+    def needs_cleaning(self) -> bool:
+        rc = self.L.rdh_ckp_needs_cleaning(self.h)
+        if rc < 0:
+            raise RuntimeError(self.L.rdh_last_error().decode())
+        return rc == 1
+
+    def clean(self):
+        self._check(self.L.rdh_ckp_clean(self.h))
+
+    def checksum_result(self, root_id, llh, alpha) -> int:
+        return self.L.rdh_ckp_checksum_result(root_id, llh, alpha)
+
+    def checksum_params(self, params, K: int = 4) -> int:
+        n, r, f, a, w = self._flat(list(params), K)
+        return self.L.rdh_ckp_checksum_params(n, _ptr(r, _dp), _ptr(f, _dp), _ptr(a, _dp), _ptr(w, _dp), K)
 
 
 def parse_partitions(text: str, lib: C.CDLL | None = None) -> list:
@@ -826,6 +965,11 @@ class Model:
                                                        C.byref(got)))
         k = got.value
         return ids[:k].copy(), llh[:k].copy(), alpha[:k].copy()
+
+    def set_checkpoint(self, prefix: str | None):
+        """log search / exhaustive_search results to "<prefix>.ckp" (the reference's on-disk format);
+        a file that already holds results makes the next run resume from it"""
+        self._check(self.L.rdh_model_set_checkpoint(self.h, prefix.encode() if prefix is not None else None))
 
     def lwr(self, llh) -> np.ndarray:
         llh = np.ascontiguousarray(llh, dtype=np.float64)

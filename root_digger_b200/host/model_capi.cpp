@@ -273,6 +273,22 @@ extern "C" int rdh_model_compute_all_root_lh(void *h, double *out) {
   })
 }
 
+// Back the model's result log by the reference's on-disk checkpoint "<prefix>.ckp"
+// (NULL: back to the in-memory log).  A file that already holds results makes the next
+// search / exhaustive_search RESUME: root ids found in it are skipped
+// (assign_indicies_by_rank_*, reference src/model.cpp:1899-1960).
+extern "C" int rdh_model_set_checkpoint(void *h, const char *prefix) {
+  RDH_TRY({
+    H(h).checkpoint = prefix ? checkpoint_t(std::string(prefix)) : checkpoint_t();
+    if (prefix && !H(h).checkpoint.existing_checkpoint()) {
+      cli_options_t o;
+      o.prefix = prefix;
+      H(h).checkpoint.save_options(o);
+    }
+    return 1;
+  })
+}
+
 // init_strategy: 0 random, 1 midpoint, 2 modified MAD
 extern "C" int rdh_model_search(void *h, unsigned min_roots, double root_ratio, double atol, double pgtol,
                                 double brtol, double factor, int init_strategy, unsigned rank,
