@@ -311,7 +311,12 @@ int launch_program_inst(const ProgArgs &a, int grid, int threads, cudaStream_t s
   // shared memory: program window + per warp: double-buffered P / tip tables of both
   // children and two mbarriers
   const int    warps = threads / 32;
+#if RDK_TABLES_L1
+  (void)warps;
+  const size_t smem = sizeof(Instr) * kProgWindow;  // the tables are read through L1
+#else
   const size_t smem = sizeof(Instr) * kProgWindow + (size_t)warps * (sizeof(double) * 2 * 2 * kTabDoubles * K + 16);
+#endif
   static size_t configured = 0;  // per template instantiation
   if (smem > configured) {
     cudaError_t err = cudaFuncSetAttribute(clv_program_kernel<K, E, MAXT, MINB, TS>,
@@ -391,12 +396,37 @@ void finalize_program(std::vector<Instr> &prog) {
     const bool load_only = (in.flags & kLoadOnly) != 0;
     if (!(in.flags & kTip1) && fwd_clv && in.c1 == fwd_clv) in.flags |= kFwd1;
     if (!load_only && !(in.flags & kTip2) && fwd_clv && in.c2 == fwd_clv) in.flags |= kFwd2;
+    // canonical child order (the product of the two children's terms is commutative, so the
+    // result keeps its bits): a tip first, a forwarded CLV last -- fewer kinds to compile
+    if (load_only) {
+      // the stored CLV to evaluate is the one just produced: it arrives where a forwarded
+      // child always does, in the child-2 registers
+      if (in.flags & kFwd1) in.flags = (in.flags & ~kFwd1) | kFwd2;
+    } else {
+      const unsigned f = in.flags;
+      const bool     swap = ((f & kTip2) && !(f & kTip1)) || ((f & kFwd1) && !(f & (kFwd2 | kTip2)));
+      if (swap) {
+        std::swap(in.c1, in.c2);
+        std::swap(in.c1scale, in.c2scale);
+        std::swap(in.P1, in.P2);
+        unsigned g = f & ~(kTip1 | kTip2 | kFwd1 | kFwd2);
+        if (f & kTip1) g |= kTip2;
+        if (f & kTip2) g |= kTip1;
+        if (f & kFwd1) g |= kFwd2;
+        if (f & kFwd2) g |= kFwd1;
+        in.flags = g;
+      }
+    }
     if (in.c1scale) in.flags |= (fwd_scale && in.c1scale == fwd_scale) ? kFwdS1 : kLdS1;
     if (!load_only && in.c2scale) in.flags |= (fwd_scale && in.c2scale == fwd_scale) ? kFwdS2 : kLdS2;
     if (in.flags & kEval) {
       const bool has_scaler = load_only ? (in.c1scale != nullptr) : ((in.flags & kScale) != 0);
       if (has_scaler) in.flags |= kEvalScaler;
     }
+    in.kind = 2u * ((in.flags & kFwd1) ? 0u : fast_kind_of(in.flags));
+    in.pad = 0;
+    // the previous instruction produces its values directly in this one's child-2 registers
+    if (in.flags & kFwd2) prog[i - 1].kind |= 1u;
   }
 }
 
@@ -439,18 +469,26 @@ int flush(rdk_partition_t *p) {
   }
   if (nelem > 0) {
     int threads = e->threads ? e->threads : 128;
-    int per_sm = e->ctas_per_sm ? e->ctas_per_sm : 4;
-    int E = e->elems ? e->elems : 2;
+    // elements per thread: every program instruction costs a warp a fixed preamble (table
+    // staging, flag decode, barrier wait) whatever E is, so large shards run E = 4 on 2 CTAs
+    // per SM (255 registers; measured on B200, cfg2 step: 82.0 k placements/s against 66.2 k
+    // for E = 2 on 4 CTAs per SM); shards too small to give every warp >= 6 iterations keep
+    // E = 2, where the shorter passes waste less of the last one
+    int E = e->elems;
+    if (E == 0) E = (n_witer >= 6u * (unsigned)(e->sm_count * 2 * 4)) ? 4 : 2;
+    int per_sm = e->ctas_per_sm ? e->ctas_per_sm : (E == 4 ? 2 : 4);
     if (E >= 2) threads = std::min(threads, 128);
     if (E == 3) E = 2;
     // every warp owns a table buffer of 2 KiB * K: keep a CTA's shared memory near 64 KiB
     // (K = 4: 4 warps; K = 16: 1-2 warps; K = 32: 1 warp)
+#if !RDK_TABLES_L1
     {
       const size_t per_warp = sizeof(double) * 2 * 2 * kTabDoubles * e->K + 16;
       const size_t budget = (size_t)64 << 10;
       int max_warps = (int)std::max<size_t>(1, (budget - std::min(budget, sizeof(Instr) * kProgWindow)) / per_warp);
       threads = std::min(threads, 32 * max_warps);
     }
+#endif
     int grid = e->sm_count * per_sm;
     // never launch more warps than warp iterations
     int max_grid = (int)((n_witer + (threads / 32) - 1) / (threads / 32));
@@ -458,12 +496,16 @@ int flush(rdk_partition_t *p) {
     std::pair<cudaEvent_t, cudaEvent_t> *ev = e->timing ? next_event_pair(e) : nullptr;
     if (ev) CUDA_TRY(cudaEventRecord(ev->first, e->stream));
     switch (e->K) {
+#ifndef RDK_ONLY_K4  // (kernel experiments build the DNA + Gamma4 instantiation only)
       case 1: if (!launch_program<1>(a, grid, threads, E, e->tail_skip, e->stream)) return RDK_FAILURE; break;
       case 2: if (!launch_program<2>(a, grid, threads, E, e->tail_skip, e->stream)) return RDK_FAILURE; break;
+#endif
       case 4: if (!launch_program<4>(a, grid, threads, E, e->tail_skip, e->stream)) return RDK_FAILURE; break;
+#ifndef RDK_ONLY_K4
       case 8: if (!launch_program<8>(a, grid, threads, E, e->tail_skip, e->stream)) return RDK_FAILURE; break;
       case 16: if (!launch_program<16>(a, grid, threads, E, e->tail_skip, e->stream)) return RDK_FAILURE; break;
       case 32: if (!launch_program<32>(a, grid, threads, E, e->tail_skip, e->stream)) return RDK_FAILURE; break;
+#endif
       default: return fail(RDK_ERROR_PARAM, "rate_cats must divide 32");
     }
     CUDA_TRY(cudaGetLastError());

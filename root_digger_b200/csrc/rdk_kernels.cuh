@@ -26,6 +26,23 @@
 #ifndef RDK_MINB2
 #define RDK_MINB2 4  // resident CTAs of 128 threads the E = 2 program kernel is compiled for
 #endif
+#ifndef RDK_FAST_KINDS
+// 1: per-kind compile-time copies of the instruction body (K = 4; E = 2, 4).  Measured on B200
+// (cfg2 step): 24 % fewer warp instructions, but the same time at E = 4 (80.4 k vs 81-82 k
+// placements/s) and +4 % at E = 2 (66.4 k vs 63.8 k): the walk is bound by the latency of each
+// warp's dependent chain, not by issue slots, and the copies cost instruction-cache misses and
+// 2 more minutes of compile time.  Off by default.
+#define RDK_FAST_KINDS 0
+#endif
+#ifndef RDK_TABLES_L1
+// 1: the P / tip tables of an instruction are read straight from global memory through L1
+//    (ld.global.nc; the lines are prefetched into L1 one instruction ahead) -- no shared-memory
+//    staging, no mbarrier wait, no per-warp copy issue per instruction.
+// 0: every warp stages them in its own shared-memory double buffer with cp.async.bulk + mbarrier.
+// Measured on B200 (cfg2 step, E = 4): 63.7 k placements/s through L1 against 81-82 k with the
+// shared-memory staging -- the L1 hit latency sits on every instruction's critical path.
+#define RDK_TABLES_L1 0
+#endif
 #ifndef RDK_LD256
 #define RDK_LD256 1  // 256-bit global loads/stores of CLV elements
 #endif
@@ -449,6 +466,31 @@ enum : unsigned {
   kEvalScaler = 4096u,  // the evaluated root has a scale buffer (adds cnt * ln 2^-256)
 };
 
+// The flags that select code in the arithmetic of an instruction (the rest only steer the
+// operand loads).  For the combinations below -- the ones a post-order traversal and the
+// directed placement sweep are made of -- the K = 4, E = 2 kernel carries copies of the
+// instruction body compiled with the flags as CONSTANTS (no flag tests), once for "the next
+// instruction takes my result as its child 2" (the values are then produced directly in the
+// registers of the next instruction's operand: forwarding costs no register move) and once
+// for "it does not".  The host stores 2 * (index + 1) + forwards-out in Instr::kind
+// (finalize_program; 0 / 1 = flags decoded at run time), after ordering the two children
+// canonically -- a tip first, a forwarded CLV last -- which the commutative product
+// (P1 c1) o (P2 c2) allows without changing a bit of the result.
+constexpr unsigned kKindMask = kTip1 | kTip2 | kWrite | kEval | kLoadOnly | kScale | kFwd1 | kEvalScaler;
+constexpr unsigned kFastKinds[] = {
+    kWrite | kScale,                         // inner x inner
+    kWrite | kScale | kTip1,                 // tip x inner
+    kWrite | kScale | kTip1 | kTip2,         // tip x tip
+    kEval | kEvalScaler | kScale,            // sweep placement: evaluated in registers, nothing stored
+    kEval | kEvalScaler | kScale | kTip1,    // sweep placement on a tip branch
+};
+constexpr int kNumFastKinds = (int)(sizeof(kFastKinds) / sizeof(kFastKinds[0]));
+inline constexpr unsigned fast_kind_of(unsigned flags) {
+  for (int i = 0; i < kNumFastKinds; ++i)
+    if ((flags & kKindMask) == kFastKinds[i]) return (unsigned)i + 1u;
+  return 0u;
+}
+
 struct alignas(16) Instr {
   double*         parent;
   const void*     c1;
@@ -460,7 +502,8 @@ struct alignas(16) Instr {
   const double*   P2;
   unsigned        flags;
   unsigned        slot;  // eval slot (row of the partial-sum buffer)
-  unsigned long long pad;
+  unsigned        kind;  // 2 * (index into kFastKinds + 1, or 0) + (the next instruction forwards my result)
+  unsigned        pad;
 };
 static_assert(sizeof(Instr) == 80, "Instr layout");
 
@@ -519,6 +562,18 @@ __device__ __forceinline__ void st_clv(double* base, unsigned e, const d4& x) {
   __stcg(q2, make_double2(x.v[0], x.v[1]));
   __stcg(q2 + 1, make_double2(x.v[2], x.v[3]));
 #endif
+}
+
+// a 16-byte read of a P / tip table entry
+__device__ __forceinline__ double2 ld_tab(const double2* p) {
+#if RDK_TABLES_L1
+  return __ldg(p);
+#else
+  return *p;
+#endif
+}
+__device__ __forceinline__ void prefetch_l1(const void* p) {
+  asm volatile("prefetch.global.L1 [%0];\n" ::"l"(p));
 }
 
 // ---- mbarrier + bulk async copy (one elected thread moves a whole table) ----
@@ -591,6 +646,9 @@ struct Operands {
 template <int K, int E, int MAXT, int MINB, bool TS>
 __global__ void __launch_bounds__(MAXT, MINB) clv_program_kernel(const __grid_constant__ ProgArgs a) {
   static_assert(32 % K == 0, "K must divide the warp size");
+  // the configuration RootDigger runs DNA data in (4 Gamma categories) carries the
+  // per-kind copies of the instruction body; the others decode the flags at run time
+  constexpr bool FAST = (K == 4 && (E == 2 || E == 4)) && RDK_FAST_KINDS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr unsigned kTabBytes = kTabDoubles * K * 8;  // one child's slice of a table buffer
   Instr*              s_prog = reinterpret_cast<Instr*>(smem_raw);
@@ -628,14 +686,30 @@ __global__ void __launch_bounds__(MAXT, MINB) clv_program_kernel(const __grid_co
   const unsigned last_site = a.nelem / K - 1;
   const bool     multi_window = a.n_instr > kProgWindow;
 
+#if !RDK_TABLES_L1
   if (lane == 0) {
     mbar_init(&s_bar[0], 1);
     mbar_init(&s_bar[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncwarp();
+#endif
   unsigned phase = 0;  // bit b: parity of the next completion of s_bar[b]
 
+#if RDK_TABLES_L1
+  // the whole warp: pull the lines of P or T of both children of `in` into L1 (lane l
+  // takes the l-th 128-byte line of each table; a tip table is 16 lines at K = 4)
+  auto prefetch_tables = [&](const Instr& in, unsigned) {
+    const unsigned fl = in.flags;
+    if (fl & kLoadOnly) return;
+    const unsigned       b1 = (fl & kTip1) ? kTipTabDoubles * K * 8 : kPTabDoubles * K * 8;
+    const unsigned       b2 = (fl & kTip2) ? kTipTabDoubles * K * 8 : kPTabDoubles * K * 8;
+    const unsigned char* s1 = reinterpret_cast<const unsigned char*>((fl & kTip1) ? in.P1 + kPTabDoubles * K : in.P1);
+    const unsigned char* s2 = reinterpret_cast<const unsigned char*>((fl & kTip2) ? in.P2 + kPTabDoubles * K : in.P2);
+    for (unsigned off = lane * 128u; off < b1 + 127u; off += 32u * 128u) prefetch_l1(s1 + min(off, b1 - 1u));
+    for (unsigned off = lane * 128u; off < b2 + 127u; off += 32u * 128u) prefetch_l1(s2 + min(off, b2 - 1u));
+  };
+#else
   // one thread: move P or T of both children of `in` into buffer `buf`
   auto prefetch_tables = [&](const Instr& in, unsigned buf) {
     const unsigned fl = in.flags;
@@ -651,6 +725,7 @@ __global__ void __launch_bounds__(MAXT, MINB) clv_program_kernel(const __grid_co
     bulk_g2s(dst, (fl & kTip1) ? in.P1 + kPTabDoubles * K : in.P1, b1, bar);
     bulk_g2s(dst + kTabBytes, (fl & kTip2) ? in.P2 + kPTabDoubles * K : in.P2, b2, bar);
   };
+#endif
 
   for (unsigned pass = 0; pass < passes; ++pass) {
     const bool active = it_begin + pass * E < it_end;  // warp-uniform
@@ -670,13 +745,13 @@ __global__ void __launch_bounds__(MAXT, MINB) clv_program_kernel(const __grid_co
     }
 
     // issue the global loads of one instruction's operands
-    auto load_operands = [&](auto nvc, const Instr& in, unsigned fl, Operands<E>& o) {
+    auto load_operands = [&](auto nvc, const Instr& in, unsigned fl, Operands<E>& o) __attribute__((always_inline)) {
       constexpr int NV = decltype(nvc)::value;  // slots with an iteration of their own
       if (fl & kTip1) {
         const unsigned char* t = reinterpret_cast<const unsigned char*>(in.c1);
 #pragma unroll
         for (int u = 0; u < NV; ++u) o.m1[u] = __ldg(t + site[u]);
-      } else if (!(fl & kFwd1)) {
+      } else if (!(fl & kFwd1) && (fl & (kLoadOnly | kFwd2)) != (kLoadOnly | kFwd2)) {
         const double* g = reinterpret_cast<const double*>(in.c1);
 #pragma unroll
         for (int u = 0; u < NV; ++u) o.c1[u] = ld_clv(g, e[u]);
@@ -704,42 +779,69 @@ __global__ void __launch_bounds__(MAXT, MINB) clv_program_kernel(const __grid_co
       }
     };
 
-    // one instruction: `cur` holds its operands, the operands of the next
-    // instruction are loaded into `nxt`.  first == first instruction of a window
-    // (its operands were loaded without forwarding).
-    auto step = [&](auto nvc, int ii, int wn, Operands<E>& cur, Operands<E>& nxt) {
-      constexpr int NV = decltype(nvc)::value;
-      __syncwarp();  // every lane has finished instruction ii-1 (frees the other table buffer)
+    // pattern weights of this pass's sites (the same for every instruction of the program)
+    unsigned wgt[E];
+#pragma unroll
+    for (int u = 0; u < E; ++u) wgt[u] = __ldg(a.weights + site[u]);
+
+    // one instruction: `cur` holds its operands, the operands of the next instruction are
+    // loaded into `nxt`.  A child forwarded from the previous instruction is always child 2
+    // (canonical order) and is already in cur.c2: the previous instruction produced its
+    // values there.  flc: the instruction's kKindMask flags as a compile-time constant (a
+    // fast kind), or < 0: read at run time.  fwdc: the next instruction takes this one's
+    // values as its child 2; `v` is then nxt.c2, otherwise a scratch array.  bufc: the
+    // parity of the instruction's position in the window = its table buffer.
+    auto step = [&](auto nvc, auto flc, auto fwdc, auto bufc, int ii, int wn, Operands<E>& cur, Operands<E>& nxt,
+                    d4(&v)[E]) __attribute__((always_inline)) {
+      constexpr int      NV = decltype(nvc)::value;
+      constexpr int      F = decltype(flc)::value;
+      constexpr bool     FWDOUT = decltype(fwdc)::value;
+      constexpr unsigned buf = decltype(bufc)::value;
       const bool more = ii + 1 < wn;
-      const unsigned buf = (unsigned)ii & 1u;
+#if RDK_TABLES_L1
+      if (more) prefetch_tables(s_prog[ii + 1], 0);
+#else
+      __syncwarp();  // every lane has finished instruction ii-1 (frees the other table buffer)
       if (more && lane == 0) prefetch_tables(s_prog[ii + 1], buf ^ 1u);
+#endif
       const Instr&   in = s_prog[ii];
-      const unsigned fl = in.flags;
+      const unsigned fl = F < 0 ? in.flags : (unsigned)F;
       unsigned       nfl = 0;
-      if (more) {
+      if (FWDOUT || more) {  // FWDOUT implies a next instruction
         const Instr& nx = s_prog[ii + 1];
-        nfl = nx.flags;
+        nfl = FWDOUT ? (nx.flags | kFwd2) : (nx.flags & ~kFwd2);
         load_operands(nvc, nx, nfl, nxt);
       }
+#if RDK_TABLES_L1
+      const unsigned char* tab1 = reinterpret_cast<const unsigned char*>((fl & kTip1) ? in.P1 + kPTabDoubles * K : in.P1);
+      const unsigned char* tab2 = reinterpret_cast<const unsigned char*>((fl & kTip2) ? in.P2 + kPTabDoubles * K : in.P2);
+#else
       mbar_wait(&s_bar[buf], (phase >> buf) & 1u);  // tables(ii) have landed
       phase ^= 1u << buf;
       const unsigned char* tab1 = s_tab + (size_t)buf * 2 * kTabBytes;
       const unsigned char* tab2 = tab1 + kTabBytes;
+#endif
 
-      d4       v[E];
+      d4 a1[E], a2[E];
+#pragma unroll
+      for (int u = 0; u < NV; ++u) {
+        a2[u] = cur.c2[u];
+        a1[u] = cur.c1[u];
+        if (F < 0 && (fl & kFwd1)) a1[u] = cur.c2[u];  // both children are the forwarded CLV
+      }
       unsigned cnt[E];
 #pragma unroll
       for (int u = 0; u < NV; ++u) cnt[u] = cur.cnt1[u] + cur.cnt2[u];
       if (fl & kLoadOnly) {
 #pragma unroll
-        for (int u = 0; u < NV; ++u) v[u] = cur.c1[u];
+        for (int u = 0; u < NV; ++u) v[u] = (fl & kFwd2) ? a2[u] : a1[u];  // kFwd2: the CLV just produced
       } else {
         // child 1
         if (fl & kTip1) {
 #pragma unroll
           for (int u = 0; u < NV; ++u) {
             const double2* t = reinterpret_cast<const double2*>(tab1 + (cur.m1[u] * K + k) * 32u);
-            const double2  lo = t[0], hi = t[1];
+            const double2  lo = ld_tab(t), hi = ld_tab(t + 1);
             v[u].v[0] = lo.x;
             v[u].v[1] = lo.y;
             v[u].v[2] = hi.x;
@@ -749,13 +851,13 @@ __global__ void __launch_bounds__(MAXT, MINB) clv_program_kernel(const __grid_co
           const double2* p = reinterpret_cast<const double2*>(tab1 + k * (kPTabDoubles * 8));
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const double2 p01 = p[i * 2], p23 = p[i * 2 + 1];
+            const double2 p01 = ld_tab(p + i * 2), p23 = ld_tab(p + i * 2 + 1);
 #pragma unroll
             for (int u = 0; u < NV; ++u) {
-              double s = dmul(p01.x, cur.c1[u].v[0]);
-              s = dfma(p01.y, cur.c1[u].v[1], s);
-              s = dfma(p23.x, cur.c1[u].v[2], s);
-              s = dfma(p23.y, cur.c1[u].v[3], s);
+              double s = dmul(p01.x, a1[u].v[0]);
+              s = dfma(p01.y, a1[u].v[1], s);
+              s = dfma(p23.x, a1[u].v[2], s);
+              s = dfma(p23.y, a1[u].v[3], s);
               v[u].v[i] = s;
             }
           }
@@ -765,7 +867,7 @@ __global__ void __launch_bounds__(MAXT, MINB) clv_program_kernel(const __grid_co
 #pragma unroll
           for (int u = 0; u < NV; ++u) {
             const double2* t = reinterpret_cast<const double2*>(tab2 + (cur.m2[u] * K + k) * 32u);
-            const double2  lo = t[0], hi = t[1];
+            const double2  lo = ld_tab(t), hi = ld_tab(t + 1);
             v[u].v[0] = dmul(v[u].v[0], lo.x);
             v[u].v[1] = dmul(v[u].v[1], lo.y);
             v[u].v[2] = dmul(v[u].v[2], hi.x);
@@ -775,13 +877,13 @@ __global__ void __launch_bounds__(MAXT, MINB) clv_program_kernel(const __grid_co
           const double2* p = reinterpret_cast<const double2*>(tab2 + k * (kPTabDoubles * 8));
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const double2 p01 = p[i * 2], p23 = p[i * 2 + 1];
+            const double2 p01 = ld_tab(p + i * 2), p23 = ld_tab(p + i * 2 + 1);
 #pragma unroll
             for (int u = 0; u < NV; ++u) {
-              double s = dmul(p01.x, cur.c2[u].v[0]);
-              s = dfma(p01.y, cur.c2[u].v[1], s);
-              s = dfma(p23.x, cur.c2[u].v[2], s);
-              s = dfma(p23.y, cur.c2[u].v[3], s);
+              double s = dmul(p01.x, a2[u].v[0]);
+              s = dfma(p01.y, a2[u].v[1], s);
+              s = dfma(p23.x, a2[u].v[2], s);
+              s = dfma(p23.y, a2[u].v[3], s);
               v[u].v[i] = dmul(v[u].v[i], s);
             }
           }
@@ -810,15 +912,7 @@ __global__ void __launch_bounds__(MAXT, MINB) clv_program_kernel(const __grid_co
           for (int u = 0; u < NV; ++u) __stcg(ps + site[u], cnt[u]);
         }
       }
-      // register forwarding into the operands of instruction ii+1
-      if (nfl & kFwd1) {
-#pragma unroll
-        for (int u = 0; u < NV; ++u) nxt.c1[u] = v[u];
-      }
-      if (nfl & kFwd2) {
-#pragma unroll
-        for (int u = 0; u < NV; ++u) nxt.c2[u] = v[u];
-      }
+      // the scaler counts of a forwarded child of instruction ii+1 (its values are `v`)
       if (nfl & kFwdS1) {
 #pragma unroll
         for (int u = 0; u < NV; ++u) nxt.cnt1[u] = cnt[u];
@@ -828,39 +922,107 @@ __global__ void __launch_bounds__(MAXT, MINB) clv_program_kernel(const __grid_co
         for (int u = 0; u < NV; ++u) nxt.cnt2[u] = cnt[u];
       }
       if (fl & kEval) {
+        // every lane of a site gathers the K category terms in category order
+        double term[E];
 #pragma unroll
         for (int u = 0; u < NV; ++u) {
           double t = dmul(a.pi[0], v[u].v[0]);
           t = dfma(a.pi[1], v[u].v[1], t);
           t = dfma(a.pi[2], v[u].v[2], t);
           t = dfma(a.pi[3], v[u].v[3], t);
-          // every lane of a site gathers the K category terms in category order
-          double term = dmul(a.w[0], __shfl_sync(0xffffffffu, t, lane0));
+          double tm = dmul(a.w[0], __shfl_sync(0xffffffffu, t, lane0));
 #pragma unroll
           for (int kk = 1; kk < K; ++kk) {
             double tk = __shfl_sync(0xffffffffu, t, lane0 + kk * KSTRIDE);
-            term = dfma(a.w[kk], tk, term);
+            tm = dfma(a.w[kk], tk, tm);
           }
+          term[u] = tm;
+        }
+        if constexpr (NV <= K) {
+          // the K lanes of a site hold the same term: lane k takes the logarithm of the
+          // site of slot u = k, so that ONE pass through rd_log serves all NV slots
+          double   x = term[0];
+          unsigned cn = cnt[0], st = site[0], iw = it[0], wg = wgt[0];
+#pragma unroll
+          for (int u = 1; u < NV; ++u)
+            if (k == (unsigned)u) {
+              x = term[u];
+              cn = cnt[u];
+              st = site[u];
+              iw = it[u];
+              wg = wgt[u];
+            }
           double l = 0.0;
-          if (k == 0 && it[u] * SPW + sl <= last_site) {
-            l = rd_log(term);
-            if (fl & kEvalScaler) l = dadd(l, dmul((double)cnt[u], RDK_LOG_SCALE_THRESHOLD));
-            l = dmul(l, (double)__ldg(a.weights + site[u]));
-            if (a.persite && in.slot == 0) a.persite[site[u]] = l;
+          if (k < (unsigned)NV && iw * SPW + sl <= last_site) {
+            l = rd_log(x);
+            if (fl & kEvalScaler) l = dadd(l, dmul((double)cn, RDK_LOG_SCALE_THRESHOLD));
+            l = dmul(l, (double)wg);
+            if (a.persite && in.slot == 0) a.persite[st] = l;
           }
-          // canonical tree over the 32/K sites of this warp iteration (the k == 0 lanes)
+          // canonical tree over the 32/K sites of a warp iteration (the lanes of equal k)
 #pragma unroll
           for (int off2 = 1; off2 < (int)SPW; off2 <<= 1)
             l = dadd(l, __shfl_xor_sync(0xffffffffu, l, off2 * (KSTRIDE == 1 ? K : 1)));
-          if (lane == 0) a.partials[(size_t)in.slot * a.partial_stride + it[u]] = l;
+          if (sl == 0 && k < (unsigned)NV) a.partials[(size_t)in.slot * a.partial_stride + iw] = l;
+        } else {
+#pragma unroll
+          for (int u = 0; u < NV; ++u) {
+            double l = 0.0;
+            if (k == 0 && it[u] * SPW + sl <= last_site) {
+              l = rd_log(term[u]);
+              if (fl & kEvalScaler) l = dadd(l, dmul((double)cnt[u], RDK_LOG_SCALE_THRESHOLD));
+              l = dmul(l, (double)wgt[u]);
+              if (a.persite && in.slot == 0) a.persite[site[u]] = l;
+            }
+#pragma unroll
+            for (int off2 = 1; off2 < (int)SPW; off2 <<= 1)
+              l = dadd(l, __shfl_xor_sync(0xffffffffu, l, off2 * (KSTRIDE == 1 ? K : 1)));
+            if (lane == 0) a.partials[(size_t)in.slot * a.partial_stride + it[u]] = l;
+          }
         }
       }
     };
 
+    // run instruction ii through the copy of the body compiled for its kind
+    auto dispatch = [&](auto nvc, auto bufc, int ii, int wn, Operands<E>& cur, Operands<E>& nxt)
+                        __attribute__((always_inline)) {
+      using IC = std::integral_constant<int, -1>;
+      using std::integral_constant;
+      using std::false_type;
+      using std::true_type;
+      d4             scratch[E];
+      const unsigned kind = s_prog[ii].kind;
+      // (short tail passes, NV < E, run the run-time decoded body: they are rare)
+      if constexpr (FAST && decltype(nvc)::value == E) {
+        switch (kind) {
+          case 2: step(nvc, integral_constant<int, (int)kFastKinds[0]>{}, false_type{}, bufc, ii, wn, cur, nxt, scratch); break;
+          case 3: step(nvc, integral_constant<int, (int)kFastKinds[0]>{}, true_type{}, bufc, ii, wn, cur, nxt, nxt.c2); break;
+          case 4: step(nvc, integral_constant<int, (int)kFastKinds[1]>{}, false_type{}, bufc, ii, wn, cur, nxt, scratch); break;
+          case 5: step(nvc, integral_constant<int, (int)kFastKinds[1]>{}, true_type{}, bufc, ii, wn, cur, nxt, nxt.c2); break;
+          case 6: step(nvc, integral_constant<int, (int)kFastKinds[2]>{}, false_type{}, bufc, ii, wn, cur, nxt, scratch); break;
+          case 7: step(nvc, integral_constant<int, (int)kFastKinds[2]>{}, true_type{}, bufc, ii, wn, cur, nxt, nxt.c2); break;
+          case 8: step(nvc, integral_constant<int, (int)kFastKinds[3]>{}, false_type{}, bufc, ii, wn, cur, nxt, scratch); break;
+          case 10: step(nvc, integral_constant<int, (int)kFastKinds[4]>{}, false_type{}, bufc, ii, wn, cur, nxt, scratch); break;
+          case 1: step(nvc, IC{}, true_type{}, bufc, ii, wn, cur, nxt, nxt.c2); break;
+          default: step(nvc, IC{}, false_type{}, bufc, ii, wn, cur, nxt, scratch); break;
+        }
+      } else {
+        if (kind & 1u)
+          step(nvc, IC{}, true_type{}, bufc, ii, wn, cur, nxt, nxt.c2);
+        else
+          step(nvc, IC{}, false_type{}, bufc, ii, wn, cur, nxt, scratch);
+      }
+    };
+
     // the instruction loop over one staged window, for NV slots
-    auto run_window = [&](auto nvc, int wn) {
+    auto run_window = [&](auto nvc, int wn) __attribute__((always_inline)) {
+      using std::integral_constant;
+#if RDK_TABLES_L1
+      prefetch_tables(s_prog[0], 0);
+#else
       __syncwarp();
       if (lane == 0) prefetch_tables(s_prog[0], 0);
+#endif
       Operands<E> opA, opB;
 #pragma unroll
       for (int u = 0; u < E; ++u) {
@@ -873,10 +1035,10 @@ __global__ void __launch_bounds__(MAXT, MINB) clv_program_kernel(const __grid_co
       load_operands(nvc, s_prog[0], s_prog[0].flags, opA);
       int ii = 0;
       for (; ii + 1 < wn; ii += 2) {
-        step(nvc, ii, wn, opA, opB);
-        step(nvc, ii + 1, wn, opB, opA);
+        dispatch(nvc, integral_constant<unsigned, 0>{}, ii, wn, opA, opB);
+        dispatch(nvc, integral_constant<unsigned, 1>{}, ii + 1, wn, opB, opA);
       }
-      if (ii < wn) step(nvc, ii, wn, opA, opB);
+      if (ii < wn) dispatch(nvc, integral_constant<unsigned, 0>{}, ii, wn, opA, opB);
     };
 
     for (int w0 = 0; w0 < a.n_instr; w0 += kProgWindow) {
