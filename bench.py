@@ -19,13 +19,14 @@ roofline= the dominant kernel (clv_program_kernel): algorithmic bytes (SURVEY 8d
           per launch by the engine) / its device time (CUDA events bracketing each launch).
 
 N > 1 (strong scaling: the global problem is fixed), one process per GPU, N = G_s x G_r
-(root_digger_b200.sharding.plan_grid): the alignment's sites are split into G_s
-shards -- as few as HBM allows, one NCCL all-reduce of tree nodes per evaluation batch inside
-a site group -- and the 2n-3 candidate placements of the sweep into G_r contiguous chunks
+(root_digger_b200.sharding.plan_grid).  Default G_s = N: the alignment's sites are
+split into N contiguous, 1024-aligned shards, CLVs resident per GPU, ONE NCCL all-reduce of the
+per-shard tree nodes per evaluation batch (the north-star layout).  --shard roots keeps a replica
+per GPU and splits the 2n-3 candidate placements of the sweep into N contiguous chunks instead
 (the rule exhaustive mode uses for ranks, reference src/model.cpp:1899-1907; no data-path
-collective, one all-gather of the 2n-3 log-likelihoods per step).  cfg2 fits a replica per
-GPU, so the default is G_s = 1, G_r = N; --shard sites forces G_s = N (measured in
-profiles/ for comparison: a 12.5k-site shard is latency-bound).
+collective, one all-gather of the log-likelihoods per step) -- but every rank then repeats the
+full evaluation, and measured on B200 (profiles/r01_bench_e4_n{4,8}_{sites,roots}.json) the site
+shards win from N = 4 up: 296.5 k vs 228.2 k placements/s at N = 8, 187.8 k vs 183.9 k at N = 4.
 
 --impl reference: the CPU oracle restatement of the same step (the reference's coraxlib is an
 absent submodule: it cannot be built), all host threads, on a bounded site sample.
@@ -71,8 +72,10 @@ def parse_args():
     ap.add_argument("--sweep", default="directed", choices=["directed", "path"],
                     help="how our arm scores the 2n-3 placements: one pre-order pass over directed CLVs "
                          "(default) or the reference-shaped move_root path per placement; identical values")
-    ap.add_argument("--shard", default="auto", choices=["auto", "sites", "roots"],
-                    help="N > 1: auto = fewest site shards that fit HBM, rest over root placements")
+    ap.add_argument("--shard", default="sites", choices=["auto", "sites", "roots"],
+                    help="N > 1: sites = one site shard per GPU (the north-star layout: one all-reduce per "
+                         "evaluation batch); roots = a replica per GPU, root placements in chunks; auto = fewest "
+                         "site shards that fit HBM, rest over root placements (exhaustive mode's rule)")
     return ap.parse_args()
 
 
@@ -404,6 +407,32 @@ def run_ours(args):
                 "launches_timed": st["program_timed"],
                 "kernel_share_of_step": prog_s * 1e3 / ms if ms > 0 else None}
 
+    # ---- the unit of exhaustive mode / BFGS: one full evaluation (compute_lh), timed alone
+    g.set_timing(True)
+    g.reset_stats()
+    barrier()
+    fe0, fe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    fe0.record()
+    for _ in range(args.steps):
+        g.update_prob_matrices(full_pm, full_br)
+        g.L.rdk_update_clvs(g.p, full_arr, len(full_ops))
+        lh_full = g.root_loglikelihood(case.root_clv, case.root_scaler)
+    fe1.record()
+    barrier()
+    fst = g.stats()
+    g.set_timing(False)
+    fe_ms = torch.tensor([fe0.elapsed_time(fe1) / args.steps], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(fe_ms, op=dist.ReduceOp.MAX)
+    fe_ms = float(fe_ms.item())
+    fe_kernel_s = fst["program_time_ns"] * 1e-9 / max(1, fst["program_timed"])
+    fe_bytes = fst["algorithmic_bytes"] / args.steps
+    full_eval = {"evaluations_per_sec": 1e3 / fe_ms, "ms": fe_ms, "kernel_ms": fe_kernel_s * 1e3,
+                 "algorithmic_bytes_per_gpu": fe_bytes,
+                 "kernel_gbs_per_gpu": fe_bytes / fe_kernel_s / 1e9 if fe_kernel_s > 0 else None,
+                 "frac_of_hbm_peak": fe_bytes / fe_kernel_s / 1e9 / peak if fe_kernel_s > 0 else None,
+                 "logl_matches_step": bool(lh_full == lh0)}
+
     # ---- e2e: the same step through the host model_t mirror (public API, host buffers)
     e2e = None
     if not args.no_e2e:
@@ -467,7 +496,7 @@ def run_ours(args):
                 clv_ops_per_step=st["clv_ops"] / args.steps, root_evals_per_step=st["root_evals"] / args.steps),
             "clv_update_gbs": clv_gbs, "clv_update_gbs_per_gpu": clv_gbs / n_gpus,
             "algorithmic_bytes_per_step": total_alg_bytes / args.steps,
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "roofline": roofline, "full_evaluation": full_eval, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(agg[1].item()), "clocks": clocks,
             "logl_root0": lh0, "best_placement": int(np.argmax(sweep_lh)),
         }

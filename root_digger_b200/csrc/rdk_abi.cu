@@ -384,7 +384,7 @@ int ensure_partials(Engine *e, unsigned slots, unsigned stride) {
 // pointers at run time: which operands are forwarded in registers from the previous
 // instruction and which scaler counts have to be loaded.  The first instruction of a
 // shared-memory window never forwards (its operands are loaded from memory).
-void finalize_program(std::vector<Instr> &prog) {
+void finalize_program(std::vector<Instr> &prog, int table_K) {
   const unsigned decoded = kFwd1 | kFwd2 | kLdS1 | kLdS2 | kFwdS1 | kFwdS2 | kEvalScaler;
   for (size_t i = 0; i < prog.size(); ++i) {
     Instr &in = prog[i];
@@ -424,7 +424,16 @@ void finalize_program(std::vector<Instr> &prog) {
       if (has_scaler) in.flags |= kEvalScaler;
     }
     in.kind = 2u * ((in.flags & kFwd1) ? 0u : fast_kind_of(in.flags));
-    in.pad = 0;
+    // the table each child reads (P of an inner child, T of a tip child) and their sizes,
+    // so that the kernel's staging has nothing to decide
+    if (in.tx == 0 && !load_only) {
+      const unsigned K = (unsigned)table_K;
+      const unsigned b1 = ((in.flags & kTip1) ? kTipTabDoubles : kPTabDoubles) * K * 8u;
+      const unsigned b2 = ((in.flags & kTip2) ? kTipTabDoubles : kPTabDoubles) * K * 8u;
+      if (in.flags & kTip1) in.P1 += (size_t)kPTabDoubles * K;
+      if (in.flags & kTip2) in.P2 += (size_t)kPTabDoubles * K;
+      in.tx = b1 | (b2 << 16);
+    }
     // the previous instruction produces its values directly in this one's child-2 registers
     if (in.flags & kFwd2) prog[i - 1].kind |= 1u;
   }
@@ -455,7 +464,7 @@ int flush(rdk_partition_t *p) {
     a.partials = e->d_partials;
   }
   a.persite = e->want_persite ? e->d_persite : nullptr;
-  finalize_program(e->pend_prog);
+  finalize_program(e->pend_prog, (int)e->K);
   if (a.n_instr <= kProgInline) {
     for (int i = 0; i < a.n_instr; ++i) a.inl[i] = e->pend_prog[i];
   } else {
@@ -470,12 +479,12 @@ int flush(rdk_partition_t *p) {
   if (nelem > 0) {
     int threads = e->threads ? e->threads : 128;
     // elements per thread: every program instruction costs a warp a fixed preamble (table
-    // staging, flag decode, barrier wait) whatever E is, so large shards run E = 4 on 2 CTAs
-    // per SM (255 registers; measured on B200, cfg2 step: 82.0 k placements/s against 66.2 k
-    // for E = 2 on 4 CTAs per SM); shards too small to give every warp >= 6 iterations keep
-    // E = 2, where the shorter passes waste less of the last one
+    // staging, flag decode, barrier wait) whatever E is, so shards that give every warp of the
+    // E = 4 grid (2 CTAs per SM, 255 registers) at least 2 iterations run E = 4.  Measured on
+    // B200, ms per cfg2 step, E = 4 / E = 2 (4 CTAs per SM): 100 k sites 12.1 / 15.0, 50 k
+    // 7.0 / 8.3, 25 k 4.2 / 5.2, 12.5 k 3.07 / 3.08 (one iteration per warp either way).
     int E = e->elems;
-    if (E == 0) E = (n_witer >= 6u * (unsigned)(e->sm_count * 2 * 4)) ? 4 : 2;
+    if (E == 0) E = (n_witer >= 2u * (unsigned)(e->sm_count * 2 * 4)) ? 4 : 2;
     int per_sm = e->ctas_per_sm ? e->ctas_per_sm : (E == 4 ? 2 : 4);
     if (E >= 2) threads = std::min(threads, 128);
     if (E == 3) E = 2;

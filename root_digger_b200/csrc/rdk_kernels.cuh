@@ -43,6 +43,27 @@
 // shared-memory staging -- the L1 hit latency sits on every instruction's critical path.
 #define RDK_TABLES_L1 0
 #endif
+#ifndef RDK_L2_PREFETCH_DIST
+// > 0: while instruction i computes, the CLV operands of instruction i + DIST are pulled into
+// L2 (prefetch.global.L2, no registers), so that the register loads issued one instruction
+// ahead find them there instead of paying the DRAM latency.  Measured on B200 (cfg2 step and
+// its 12.5 k-site shard, distances 2 / 3 / 5): no change -- the walk is not waiting on DRAM.
+#define RDK_L2_PREFETCH_DIST 0
+#endif
+// timing experiments only (tools/build_variant.sh): each removes one piece of the instruction
+// body -- the results are WRONG when any is set
+#ifndef RDK_X_NOEVAL
+#define RDK_X_NOEVAL 0
+#endif
+#ifndef RDK_X_NOWAIT
+#define RDK_X_NOWAIT 0
+#endif
+#ifndef RDK_X_NOLOAD
+#define RDK_X_NOLOAD 0
+#endif
+#ifndef RDK_X_NOSTORE
+#define RDK_X_NOSTORE 0
+#endif
 #ifndef RDK_LD256
 #define RDK_LD256 1  // 256-bit global loads/stores of CLV elements
 #endif
@@ -498,12 +519,12 @@ struct alignas(16) Instr {
   unsigned*       pscale;
   const unsigned* c1scale;
   const unsigned* c2scale;
-  const double*   P1;  // pool slot of child1's branch
+  const double*   P1;  // child1's table in its branch's pool slot: P (inner child) or T (tip child)
   const double*   P2;
   unsigned        flags;
   unsigned        slot;  // eval slot (row of the partial-sum buffer)
   unsigned        kind;  // 2 * (index into kFastKinds + 1, or 0) + (the next instruction forwards my result)
-  unsigned        pad;
+  unsigned        tx;    // bytes of the two tables: b1 | b2 << 16 (0: no tables, kLoadOnly)
 };
 static_assert(sizeof(Instr) == 80, "Instr layout");
 
@@ -571,6 +592,9 @@ __device__ __forceinline__ double2 ld_tab(const double2* p) {
 #else
   return *p;
 #endif
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p));
 }
 __device__ __forceinline__ void prefetch_l1(const void* p) {
   asm volatile("prefetch.global.L1 [%0];\n" ::"l"(p));
@@ -700,30 +724,28 @@ __global__ void __launch_bounds__(MAXT, MINB) clv_program_kernel(const __grid_co
   // the whole warp: pull the lines of P or T of both children of `in` into L1 (lane l
   // takes the l-th 128-byte line of each table; a tip table is 16 lines at K = 4)
   auto prefetch_tables = [&](const Instr& in, unsigned) {
-    const unsigned fl = in.flags;
-    if (fl & kLoadOnly) return;
-    const unsigned       b1 = (fl & kTip1) ? kTipTabDoubles * K * 8 : kPTabDoubles * K * 8;
-    const unsigned       b2 = (fl & kTip2) ? kTipTabDoubles * K * 8 : kPTabDoubles * K * 8;
-    const unsigned char* s1 = reinterpret_cast<const unsigned char*>((fl & kTip1) ? in.P1 + kPTabDoubles * K : in.P1);
-    const unsigned char* s2 = reinterpret_cast<const unsigned char*>((fl & kTip2) ? in.P2 + kPTabDoubles * K : in.P2);
+    const unsigned tx = in.tx;
+    if (tx == 0) return;
+    const unsigned       b1 = tx & 0xffffu, b2 = tx >> 16;
+    const unsigned char* s1 = reinterpret_cast<const unsigned char*>(in.P1);
+    const unsigned char* s2 = reinterpret_cast<const unsigned char*>(in.P2);
     for (unsigned off = lane * 128u; off < b1 + 127u; off += 32u * 128u) prefetch_l1(s1 + min(off, b1 - 1u));
     for (unsigned off = lane * 128u; off < b2 + 127u; off += 32u * 128u) prefetch_l1(s2 + min(off, b2 - 1u));
   };
 #else
   // one thread: move P or T of both children of `in` into buffer `buf`
   auto prefetch_tables = [&](const Instr& in, unsigned buf) {
-    const unsigned fl = in.flags;
     unsigned long long* bar = &s_bar[buf];
-    if (fl & kLoadOnly) {
+    const unsigned      tx = in.tx;  // sizes and table addresses are pre-computed by the host
+    if (tx == 0) {
       mbar_arrive(bar);
       return;
     }
-    const unsigned b1 = (fl & kTip1) ? kTipTabDoubles * K * 8 : kPTabDoubles * K * 8;
-    const unsigned b2 = (fl & kTip2) ? kTipTabDoubles * K * 8 : kPTabDoubles * K * 8;
+    const unsigned b1 = tx & 0xffffu, b2 = tx >> 16;
     mbar_expect_tx(bar, b1 + b2);
     unsigned char* dst = s_tab + (size_t)buf * 2 * kTabBytes;
-    bulk_g2s(dst, (fl & kTip1) ? in.P1 + kPTabDoubles * K : in.P1, b1, bar);
-    bulk_g2s(dst + kTabBytes, (fl & kTip2) ? in.P2 + kPTabDoubles * K : in.P2, b2, bar);
+    bulk_g2s(dst, in.P1, b1, bar);
+    bulk_g2s(dst + kTabBytes, in.P2, b2, bar);
   };
 #endif
 
@@ -810,13 +832,31 @@ __global__ void __launch_bounds__(MAXT, MINB) clv_program_kernel(const __grid_co
       if (FWDOUT || more) {  // FWDOUT implies a next instruction
         const Instr& nx = s_prog[ii + 1];
         nfl = FWDOUT ? (nx.flags | kFwd2) : (nx.flags & ~kFwd2);
-        load_operands(nvc, nx, nfl, nxt);
+        if (!RDK_X_NOLOAD) load_operands(nvc, nx, nfl, nxt);
       }
+#if RDK_L2_PREFETCH_DIST > 0
+      if (ii + RDK_L2_PREFETCH_DIST < wn) {
+        const Instr&   fx = s_prog[ii + RDK_L2_PREFETCH_DIST];
+        const unsigned ffl = fx.flags;
+        if (!(ffl & (kTip1 | kFwd1)) && (ffl & (kLoadOnly | kFwd2)) != (kLoadOnly | kFwd2)) {
+          const char* g = reinterpret_cast<const char*>(fx.c1);
+#pragma unroll
+          for (int u = 0; u < NV; ++u) prefetch_l2(g + (size_t)e[u] * 32u);
+        }
+        if (!(ffl & (kTip2 | kFwd2 | kLoadOnly))) {
+          const char* g = reinterpret_cast<const char*>(fx.c2);
+#pragma unroll
+          for (int u = 0; u < NV; ++u) prefetch_l2(g + (size_t)e[u] * 32u);
+        }
+      }
+#endif
 #if RDK_TABLES_L1
-      const unsigned char* tab1 = reinterpret_cast<const unsigned char*>((fl & kTip1) ? in.P1 + kPTabDoubles * K : in.P1);
-      const unsigned char* tab2 = reinterpret_cast<const unsigned char*>((fl & kTip2) ? in.P2 + kPTabDoubles * K : in.P2);
+      const unsigned char* tab1 = reinterpret_cast<const unsigned char*>(in.P1);
+      const unsigned char* tab2 = reinterpret_cast<const unsigned char*>(in.P2);
 #else
+#if !RDK_X_NOWAIT
       mbar_wait(&s_bar[buf], (phase >> buf) & 1u);  // tables(ii) have landed
+#endif
       phase ^= 1u << buf;
       const unsigned char* tab1 = s_tab + (size_t)buf * 2 * kTabBytes;
       const unsigned char* tab2 = tab1 + kTabBytes;
@@ -890,19 +930,25 @@ __global__ void __launch_bounds__(MAXT, MINB) clv_program_kernel(const __grid_co
         }
       }
       if (fl & kScale) {
+        // branch-free: all E ballots first, then a multiplication by 2^256 or by 1.0 (exact),
+        // so that the E slots' chains interleave instead of running one after the other
+        unsigned m[E];
 #pragma unroll
         for (int u = 0; u < NV; ++u) {
-          const bool small = (v[u].v[0] < RDK_SCALE_THRESHOLD) && (v[u].v[1] < RDK_SCALE_THRESHOLD) &&
-                             (v[u].v[2] < RDK_SCALE_THRESHOLD) && (v[u].v[3] < RDK_SCALE_THRESHOLD);
-          const unsigned m = __ballot_sync(0xffffffffu, small);
-          if ((m & gmask) == gmask) {
+          const bool small = (v[u].v[0] < RDK_SCALE_THRESHOLD) & (v[u].v[1] < RDK_SCALE_THRESHOLD) &
+                             (v[u].v[2] < RDK_SCALE_THRESHOLD) & (v[u].v[3] < RDK_SCALE_THRESHOLD);
+          m[u] = __ballot_sync(0xffffffffu, small);
+        }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) v[u].v[i] = dmul(v[u].v[i], RDK_SCALE_FACTOR);
-            cnt[u] += 1;
-          }
+        for (int u = 0; u < NV; ++u) {
+          const bool   all = (m[u] & gmask) == gmask;
+          const double f = all ? RDK_SCALE_FACTOR : 1.0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) v[u].v[i] = dmul(v[u].v[i], f);
+          cnt[u] += all ? 1u : 0u;
         }
       }
-      if (fl & kWrite) {
+      if ((fl & kWrite) && !RDK_X_NOSTORE) {
         double* par = in.parent;
 #pragma unroll
         for (int u = 0; u < NV; ++u) st_clv(par, e[u], v[u]);
@@ -921,7 +967,7 @@ __global__ void __launch_bounds__(MAXT, MINB) clv_program_kernel(const __grid_co
 #pragma unroll
         for (int u = 0; u < NV; ++u) nxt.cnt2[u] = cnt[u];
       }
-      if (fl & kEval) {
+      if ((fl & kEval) && !RDK_X_NOEVAL) {
         // every lane of a site gathers the K category terms in category order
         double term[E];
 #pragma unroll
