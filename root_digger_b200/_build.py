@@ -58,24 +58,41 @@ def _run(cmd, **kw):
     return res.stdout
 
 
-def build_engine(force: bool = False, verbose: bool = False) -> Path:
-    """nvcc -> lib/librdk_b200.so (sm_100a, -lineinfo)."""
+PROGRAM_KS = (1, 2, 4, 8, 16, 32)  # rate-category counts the program kernel is instantiated for
+
+
+def build_engine(force: bool = False, verbose: bool = False, out: Path | None = None, defines=()) -> Path:
+    """nvcc -> lib/librdk_b200.so (sm_100a, -lineinfo).  The ABI, the host math and one
+    translation unit per rate-category count (rdk_program_inst.cu, -DRDK_INST_K=K) are compiled
+    in parallel and linked into one shared library."""
+    from concurrent.futures import ThreadPoolExecutor
+
     LIBDIR.mkdir(exist_ok=True)
-    out = LIBDIR / "librdk_b200.so"
-    srcs = [CSRC / "rdk_abi.cu", CSRC / "rdk_host_math.cpp"]
+    out = Path(out) if out else LIBDIR / "librdk_b200.so"
+    out.parent.mkdir(parents=True, exist_ok=True)
+    srcs = [CSRC / "rdk_abi.cu", CSRC / "rdk_host_math.cpp", CSRC / "rdk_program_inst.cu"]
     deps = srcs + [CSRC / "rdk_kernels.cuh", INCLUDE / "rdk.h"]
     if not force and _newer(out, deps):
         return out
-    cmd = [_nvcc(), *NVCC_ARCH, "-lineinfo", "-O3", "-std=c++17", "--fmad=false",
-           "-ccbin", _cxx(),
-           "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall", "-shared", "-o", out, *srcs, "-ldl"]
-    for d in os.environ.get("RDK_NVCC_DEFINES", "").split():
-        cmd.insert(1, "-D" + d)  # experiment switches (RDK_KSLOW=0 ...)
+    objdir = out.parent / ("obj_" + out.stem)
+    objdir.mkdir(exist_ok=True)
+    defs = ["-D" + d for d in list(defines) + os.environ.get("RDK_NVCC_DEFINES", "").split()]  # experiment switches
+    base = [_nvcc(), *defs, *NVCC_ARCH, "-lineinfo", "-O3", "-std=c++17", "--fmad=false", "-ccbin", _cxx(),
+            "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall", "-I", INCLUDE]
     if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    log = _run(cmd)
+        base.insert(1, "-Xptxas=-v")
+    jobs = [(base + ["-c", CSRC / "rdk_abi.cu", "-o", objdir / "rdk_abi.o"]),
+            (base + ["-c", CSRC / "rdk_host_math.cpp", "-o", objdir / "rdk_host_math.o"])]
+    for k in PROGRAM_KS:
+        jobs.append(base + ["-DRDK_INST_K=%d" % k, "-c", CSRC / "rdk_program_inst.cu", "-o", objdir / ("rdk_program_k%d.o" % k)])
+    # heaviest translation units first (K = 4 carries the optional per-kind copies)
+    jobs.sort(key=lambda c: 0 if any(str(x) == "-DRDK_INST_K=4" for x in c) else 1)
+    with ThreadPoolExecutor(max_workers=max(1, min(len(jobs), os.cpu_count() or 1))) as pool:
+        logs = list(pool.map(_run, jobs))
+    objs = [j[-1] for j in jobs]
+    logs.append(_run([_nvcc(), *NVCC_ARCH, "-shared", "-o", out, *objs, "-ldl"]))
     if verbose:
-        print(log)
+        print("\n".join(logs))
     return out
 
 

@@ -306,28 +306,6 @@ int launch_pmatrices(rdk_partition_t *p) {
   return RDK_SUCCESS;
 }
 
-template <int K, int E, int MAXT, int MINB, bool TS>
-int launch_program_inst(const ProgArgs &a, int grid, int threads, cudaStream_t st) {
-  // shared memory: program window + per warp: double-buffered P / tip tables of both
-  // children and two mbarriers
-  const int    warps = threads / 32;
-#if RDK_TABLES_L1
-  (void)warps;
-  const size_t smem = sizeof(Instr) * kProgWindow;  // the tables are read through L1
-#else
-  const size_t smem = sizeof(Instr) * kProgWindow + (size_t)warps * (sizeof(double) * 2 * 2 * kTabDoubles * K + 16);
-#endif
-  static size_t configured = 0;  // per template instantiation
-  if (smem > configured) {
-    cudaError_t err = cudaFuncSetAttribute(clv_program_kernel<K, E, MAXT, MINB, TS>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (err != cudaSuccess) return fail(RDK_ERROR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(err));
-    configured = smem;
-  }
-  clv_program_kernel<K, E, MAXT, MINB, TS><<<grid, threads, smem, st>>>(a);
-  return RDK_SUCCESS;
-}
-
 // Tail skip pays when NO warp has a full last pass: the warps' ranges differ by at most
 // one iteration, so that is when the largest range is not a multiple of E.  (Measured on
 // B200, 500 taxa, E = 2, ms per search step with / without: 12.5k sites 5.5 / 7.7,
@@ -339,23 +317,6 @@ bool choose_tail_skip(unsigned n_witer, int grid, int threads, int E, int mode) 
   const unsigned long long nw = (unsigned long long)grid * (unsigned)(threads / 32);
   const unsigned long long q_hi = (n_witer + nw - 1) / nw;
   return q_hi % (unsigned)E != 0;
-}
-
-template <int K>
-int launch_program(const ProgArgs &a, int grid, int threads, int E, int tail_mode, cudaStream_t st) {
-  // elements per thread E trades registers (occupancy) for fewer shared-memory
-  // table reads per element
-  if (E != 1) threads = std::min(threads, 128);
-  const bool ts = choose_tail_skip(a.n_witer, grid, threads, E, tail_mode);
-  switch (E) {
-    case 1: return launch_program_inst<K, 1, 256, 3, false>(a, grid, threads, st);
-    case 4:
-      return ts ? launch_program_inst<K, 4, 128, 2, true>(a, grid, threads, st)
-                : launch_program_inst<K, 4, 128, 2, false>(a, grid, threads, st);
-    default:
-      return ts ? launch_program_inst<K, 2, 128, RDK_MINB2, true>(a, grid, threads, st)
-                : launch_program_inst<K, 2, 128, RDK_MINB2, false>(a, grid, threads, st);
-  }
 }
 
 int ensure_partials(Engine *e, unsigned slots, unsigned stride) {
@@ -504,19 +465,19 @@ int flush(rdk_partition_t *p) {
     grid = std::max(1, std::min(grid, max_grid));
     std::pair<cudaEvent_t, cudaEvent_t> *ev = e->timing ? next_event_pair(e) : nullptr;
     if (ev) CUDA_TRY(cudaEventRecord(ev->first, e->stream));
+    if (E != 1) threads = std::min(threads, 128);
+    const bool  ts = choose_tail_skip(n_witer, grid, threads, E, e->tail_skip);
+    cudaError_t lerr;
     switch (e->K) {
-#ifndef RDK_ONLY_K4  // (kernel experiments build the DNA + Gamma4 instantiation only)
-      case 1: if (!launch_program<1>(a, grid, threads, E, e->tail_skip, e->stream)) return RDK_FAILURE; break;
-      case 2: if (!launch_program<2>(a, grid, threads, E, e->tail_skip, e->stream)) return RDK_FAILURE; break;
-#endif
-      case 4: if (!launch_program<4>(a, grid, threads, E, e->tail_skip, e->stream)) return RDK_FAILURE; break;
-#ifndef RDK_ONLY_K4
-      case 8: if (!launch_program<8>(a, grid, threads, E, e->tail_skip, e->stream)) return RDK_FAILURE; break;
-      case 16: if (!launch_program<16>(a, grid, threads, E, e->tail_skip, e->stream)) return RDK_FAILURE; break;
-      case 32: if (!launch_program<32>(a, grid, threads, E, e->tail_skip, e->stream)) return RDK_FAILURE; break;
-#endif
+      case 1: lerr = launch_program<1>(a, grid, threads, E, ts, e->stream); break;
+      case 2: lerr = launch_program<2>(a, grid, threads, E, ts, e->stream); break;
+      case 4: lerr = launch_program<4>(a, grid, threads, E, ts, e->stream); break;
+      case 8: lerr = launch_program<8>(a, grid, threads, E, ts, e->stream); break;
+      case 16: lerr = launch_program<16>(a, grid, threads, E, ts, e->stream); break;
+      case 32: lerr = launch_program<32>(a, grid, threads, E, ts, e->stream); break;
       default: return fail(RDK_ERROR_PARAM, "rate_cats must divide 32");
     }
+    if (lerr != cudaSuccess) return fail(RDK_ERROR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(lerr));
     CUDA_TRY(cudaGetLastError());
     if (ev) CUDA_TRY(cudaEventRecord(ev->second, e->stream));
     e->stats.kernel_launches++;

@@ -1,9 +1,11 @@
 #!/bin/bash
 # usage: tools/build_variant.sh NAME "DEFINES"   -> root_digger_b200/lib/variants/NAME/librdk_b200.so
+# (kernel experiments: run bench.py with RDK_ENGINE_LIB pointing at the variant)
 set -e
 cd "$(dirname "$0")/.."
-mkdir -p root_digger_b200/lib/variants/$1
-DEFS=""; for d in $2; do DEFS="$DEFS -D$d"; done
-/usr/local/cuda/bin/nvcc $DEFS -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --fmad=false -ccbin /usr/bin/g++ \
-  -Xcompiler -fPIC,-ffp-contract=off,-Wall -shared -o root_digger_b200/lib/variants/$1/librdk_b200.so \
-  root_digger_b200/csrc/rdk_abi.cu root_digger_b200/csrc/rdk_host_math.cpp -ldl
+python - "$1" "$2" <<'PY'
+import sys
+from root_digger_b200 import _build
+out = _build.LIBDIR / "variants" / sys.argv[1] / "librdk_b200.so"
+print(_build.build_engine(force=True, out=out, defines=sys.argv[2].split()))
+PY
