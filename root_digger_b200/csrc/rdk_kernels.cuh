@@ -43,6 +43,13 @@
 // shared-memory staging -- the L1 hit latency sits on every instruction's critical path.
 #define RDK_TABLES_L1 0
 #endif
+#ifndef RDK_FWD_STATIC
+// 1: the instruction body is compiled twice, for "the next instruction forwards my values" (they
+//    are produced directly in its child-2 operand registers) and for "it does not".
+// 0: one copy; forwarded values are moved into the next instruction's operand registers under a
+//    run-time test (8 E register moves), which halves the code the warps of an SM walk through.
+#define RDK_FWD_STATIC 1
+#endif
 #ifndef RDK_L2_PREFETCH_DIST
 // > 0: while instruction i computes, the CLV operands of instruction i + DIST are pulled into
 // L2 (prefetch.global.L2, no registers), so that the register loads issued one instruction
@@ -820,7 +827,8 @@ __global__ void __launch_bounds__(MAXT, MINB) clv_program_kernel(const __grid_co
                     d4(&v)[E]) __attribute__((always_inline)) {
       constexpr int      NV = decltype(nvc)::value;
       constexpr int      F = decltype(flc)::value;
-      constexpr bool     FWDOUT = decltype(fwdc)::value;
+      constexpr int      FWDMODE = decltype(fwdc)::value;  // 0: not forwarded, 1: forwarded (v is nxt.c2), 2: run time
+      constexpr bool     FWDOUT = FWDMODE == 1;
       constexpr unsigned buf = decltype(bufc)::value;
       const bool more = ii + 1 < wn;
 #if RDK_TABLES_L1
@@ -834,7 +842,7 @@ __global__ void __launch_bounds__(MAXT, MINB) clv_program_kernel(const __grid_co
       unsigned       nfl = 0;
       if (FWDOUT || more) {  // FWDOUT implies a next instruction
         const Instr& nx = s_prog[ii + 1];
-        nfl = FWDOUT ? (nx.flags | kFwd2) : (nx.flags & ~kFwd2);
+        nfl = FWDMODE == 2 ? nx.flags : (FWDOUT ? (nx.flags | kFwd2) : (nx.flags & ~kFwd2));
         if (!RDK_X_NOLOAD) load_operands(nvc, nx, nfl, nxt);
       }
 #if RDK_L2_PREFETCH_DIST > 0
@@ -957,6 +965,10 @@ __global__ void __launch_bounds__(MAXT, MINB) clv_program_kernel(const __grid_co
           for (int u = 0; u < NV; ++u) __stcg(ps + site[u], cnt[u]);
         }
       }
+      if (FWDMODE == 2 && (nfl & kFwd2)) {
+#pragma unroll
+        for (int u = 0; u < NV; ++u) nxt.c2[u] = v[u];
+      }
       // the scaler counts of a forwarded child of instruction ii+1 (its values are `v`)
       if (nfl & kFwdS1) {
 #pragma unroll
@@ -1033,29 +1045,31 @@ __global__ void __launch_bounds__(MAXT, MINB) clv_program_kernel(const __grid_co
                         __attribute__((always_inline)) {
       using IC = std::integral_constant<int, -1>;
       using std::integral_constant;
-      using std::false_type;
-      using std::true_type;
+      using no_fwd = integral_constant<int, 0>;
+      using fwd = integral_constant<int, 1>;
       d4             scratch[E];
       const unsigned kind = s_prog[ii].kind;
       // (short tail passes, NV < E, run the run-time decoded body: they are rare)
       if constexpr (FAST && decltype(nvc)::value == E) {
         switch (kind) {
-          case 2: step(nvc, integral_constant<int, (int)kFastKinds[0]>{}, false_type{}, bufc, ii, wn, cur, nxt, scratch); break;
-          case 3: step(nvc, integral_constant<int, (int)kFastKinds[0]>{}, true_type{}, bufc, ii, wn, cur, nxt, nxt.c2); break;
-          case 4: step(nvc, integral_constant<int, (int)kFastKinds[1]>{}, false_type{}, bufc, ii, wn, cur, nxt, scratch); break;
-          case 5: step(nvc, integral_constant<int, (int)kFastKinds[1]>{}, true_type{}, bufc, ii, wn, cur, nxt, nxt.c2); break;
-          case 6: step(nvc, integral_constant<int, (int)kFastKinds[2]>{}, false_type{}, bufc, ii, wn, cur, nxt, scratch); break;
-          case 7: step(nvc, integral_constant<int, (int)kFastKinds[2]>{}, true_type{}, bufc, ii, wn, cur, nxt, nxt.c2); break;
-          case 8: step(nvc, integral_constant<int, (int)kFastKinds[3]>{}, false_type{}, bufc, ii, wn, cur, nxt, scratch); break;
-          case 10: step(nvc, integral_constant<int, (int)kFastKinds[4]>{}, false_type{}, bufc, ii, wn, cur, nxt, scratch); break;
-          case 1: step(nvc, IC{}, true_type{}, bufc, ii, wn, cur, nxt, nxt.c2); break;
-          default: step(nvc, IC{}, false_type{}, bufc, ii, wn, cur, nxt, scratch); break;
+          case 2: step(nvc, integral_constant<int, (int)kFastKinds[0]>{}, no_fwd{}, bufc, ii, wn, cur, nxt, scratch); break;
+          case 3: step(nvc, integral_constant<int, (int)kFastKinds[0]>{}, fwd{}, bufc, ii, wn, cur, nxt, nxt.c2); break;
+          case 4: step(nvc, integral_constant<int, (int)kFastKinds[1]>{}, no_fwd{}, bufc, ii, wn, cur, nxt, scratch); break;
+          case 5: step(nvc, integral_constant<int, (int)kFastKinds[1]>{}, fwd{}, bufc, ii, wn, cur, nxt, nxt.c2); break;
+          case 6: step(nvc, integral_constant<int, (int)kFastKinds[2]>{}, no_fwd{}, bufc, ii, wn, cur, nxt, scratch); break;
+          case 7: step(nvc, integral_constant<int, (int)kFastKinds[2]>{}, fwd{}, bufc, ii, wn, cur, nxt, nxt.c2); break;
+          case 8: step(nvc, integral_constant<int, (int)kFastKinds[3]>{}, no_fwd{}, bufc, ii, wn, cur, nxt, scratch); break;
+          case 10: step(nvc, integral_constant<int, (int)kFastKinds[4]>{}, no_fwd{}, bufc, ii, wn, cur, nxt, scratch); break;
+          case 1: step(nvc, IC{}, fwd{}, bufc, ii, wn, cur, nxt, nxt.c2); break;
+          default: step(nvc, IC{}, no_fwd{}, bufc, ii, wn, cur, nxt, scratch); break;
         }
-      } else {
+      } else if constexpr (RDK_FWD_STATIC) {
         if (kind & 1u)
-          step(nvc, IC{}, true_type{}, bufc, ii, wn, cur, nxt, nxt.c2);
+          step(nvc, IC{}, fwd{}, bufc, ii, wn, cur, nxt, nxt.c2);
         else
-          step(nvc, IC{}, false_type{}, bufc, ii, wn, cur, nxt, scratch);
+          step(nvc, IC{}, no_fwd{}, bufc, ii, wn, cur, nxt, scratch);
+      } else {
+        step(nvc, IC{}, integral_constant<int, 2>{}, bufc, ii, wn, cur, nxt, scratch);
       }
     };
 
