@@ -72,6 +72,8 @@ def parse_args():
     ap.add_argument("--sweep", default="directed", choices=["directed", "path"],
                     help="how our arm scores the 2n-3 placements: one pre-order pass over directed CLVs "
                          "(default) or the reference-shaped move_root path per placement; identical values")
+    ap.add_argument("--chunks", type=int, default=0,
+                    help="independent chunks of the directed sweep (0 = the engine's hint for the shard size)")
     ap.add_argument("--shard", default="sites", choices=["auto", "sites", "roots"],
                     help="N > 1: sites = one site shard per GPU (the north-star layout: one all-reduce per "
                          "evaluation batch); roots = a replica per GPU, root placements in chunks; auto = fewest "
@@ -309,7 +311,10 @@ def run_ours(args):
 
     comm_id = fresh_comm_id()
 
-    lay = case.tree.sweep_layout()  # reference buffer counts + the spare buffers of the directed sweep
+    # reference buffer counts + the spare buffers of the directed sweep, once per independent chunk of
+    # placements (a small shard fills the device only when several chunks are walked side by side)
+    n_chunks = args.chunks if args.chunks > 0 else capi.sweep_chunk_hint(cnt, K)
+    lay = case.tree.sweep_layout(n_chunks)
     g = Partition(n, cnt, K, device=local, clv_buffers=lay["clv_buffers"], scale_buffers=lay["scale_buffers"],
                   prob_matrices=lay["prob_matrices"])
     g.set_stream(torch.cuda.current_stream().cuda_stream)
@@ -329,13 +334,15 @@ def run_ours(args):
     roots = chunks[root_group]  # this rank's contiguous chunk of root ids
     if args.sweep == "directed":
         # the tree is rooted at root 0 (full_schedule above): directed-CLV pass over this rank's chunk
-        pm_off, mi, bl, op_off, ops, pos = case.tree.generate_sweep_operations(roots[0], roots[-1] + 1, layout=lay)
+        pm_off, mi, bl, op_off, ops, pos, chunk_off = case.tree.generate_chunked_sweep_operations(
+            roots[0], roots[-1] + 1, layout=lay)
         pos = pos - roots[0]
         sweep_flags = capi.RDK_SWEEP_KEEP_ROOT
     else:
         pm_off, mi, bl, op_off, ops = case.sweep_schedule(roots, 0.5)
         pos = np.arange(len(roots))
         sweep_flags = 0
+        chunk_off = None
     sw_arr = ops_array(ops)
     chunk_max = max(len(c) for c in chunks)
     gather_in = torch.zeros(chunk_max, dtype=torch.float64, device="cuda")
@@ -358,7 +365,7 @@ def run_ours(args):
         lh0 = g.root_loglikelihood(case.root_clv, case.root_scaler)
         out = np.empty(len(pos))
         out[pos] = g.sweep_root_placements(pm_off, mi, bl, op_off, sw_arr, case.root_clv, case.root_scaler,
-                                           flags=sweep_flags)
+                                           flags=sweep_flags, chunk_offsets=chunk_off)
         return lh0, gather_placements(out)
 
     def barrier():
@@ -493,6 +500,7 @@ def run_ours(args):
                 "directed-CLV pre-order pass (1 CLV op + 1 root evaluation per placement; same bits as the "
                 "reference's loop)" if args.sweep == "directed" else
                 "reference-shaped: move_root path ops + root op per placement, one engine call"),
+                sweep_chunks=n_chunks,
                 clv_ops_per_step=st["clv_ops"] / args.steps, root_evals_per_step=st["root_evals"] / args.steps),
             "clv_update_gbs": clv_gbs, "clv_update_gbs_per_gpu": clv_gbs / n_gpus,
             "algorithmic_bytes_per_step": total_alg_bytes / args.steps,

@@ -236,6 +236,37 @@ int rdk_sweep_root_placements_ex(rdk_partition_t *partition,
                                  int root_scaler_index, unsigned int flags,
                                  double *out_lnl);
 
+/* The same sweep cut into n_chunks INDEPENDENT chunks of consecutive placements
+ * (chunk c = placements [chunk_offsets[c], chunk_offsets[c+1]), chunk_offsets[0] = 0,
+ * chunk_offsets[n_chunks] = placements).  Contract: no chunk reads a CLV or scale
+ * buffer that another chunk writes (rooted_tree_t::generate_sweep_operations gives
+ * every chunk its own spare buffers and re-derives the directed CLVs on the path to
+ * its first placement); with RDK_SWEEP_KEEP_ROOT the root buffers are not written
+ * either.  The engine may then walk the chunks SIDE BY SIDE -- (site range) x (chunk)
+ * warps in one launch -- which is what fills the device when the shard is small (a
+ * 12.5k-site shard has one warp iteration per warp: one long latency-bound chain);
+ * otherwise it runs them in order.  Results are those of rdk_sweep_root_placements_ex
+ * on the same arrays, bit for bit. */
+int rdk_sweep_root_placements_chunks(rdk_partition_t *partition,
+                                     unsigned int placements,
+                                     const unsigned int *params_indices,
+                                     const unsigned int *freqs_indices,
+                                     const unsigned int *pm_offsets,
+                                     const unsigned int *matrix_indices,
+                                     const double *branch_lengths,
+                                     const unsigned int *op_offsets,
+                                     const rdk_operation_t *operations,
+                                     unsigned int root_clv_index,
+                                     int root_scaler_index, unsigned int flags,
+                                     unsigned int n_chunks,
+                                     const unsigned int *chunk_offsets,
+                                     double *out_lnl);
+/* how many chunks a sweep over a shard of `sites` patterns x `rate_cats` categories
+ * should be cut into to fill the current device (1: the shard fills it alone);
+ * at most RDK_SWEEP_MAX_CHUNKS */
+#define RDK_SWEEP_MAX_CHUNKS 16u
+unsigned int rdk_sweep_chunk_hint(unsigned int sites, unsigned int rate_cats);
+
 /* ---- site sharding across GPUs (new) --------------------------- */
 /* A partition holds a contiguous range of the alignment's site patterns.
  * site_offset must be a multiple of RDK_SHARD_ALIGN unless it is 0; the

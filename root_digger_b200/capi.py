@@ -128,6 +128,11 @@ def load_engine() -> C.CDLL:
                                             C.POINTER(Operation), C.c_uint, C.c_int, _dp]
     L.rdk_sweep_root_placements_ex.argtypes = [_pp, C.c_uint, _up, _up, _up, _up, _dp, _up,
                                                C.POINTER(Operation), C.c_uint, C.c_int, C.c_uint, _dp]
+    L.rdk_sweep_root_placements_chunks.argtypes = [_pp, C.c_uint, _up, _up, _up, _up, _dp, _up,
+                                                   C.POINTER(Operation), C.c_uint, C.c_int, C.c_uint, C.c_uint, _up,
+                                                   _dp]
+    L.rdk_sweep_chunk_hint.argtypes = [C.c_uint, C.c_uint]
+    L.rdk_sweep_chunk_hint.restype = C.c_uint
     L.rdk_partition_set_shard.argtypes = [_pp, C.c_ulonglong, C.c_ulonglong]
     L.rdk_comm_unique_id.argtypes = [C.c_void_p]
     L.rdk_partition_attach_comm.argtypes = [_pp, C.c_int, C.c_int, C.c_void_p]
@@ -273,7 +278,7 @@ class Partition:
         return out
 
     def sweep_root_placements(self, pm_offsets, matrix_indices, branch_lengths, op_offsets, ops,
-                              root_clv_index: int, root_scaler_index: int, flags: int = 0):
+                              root_clv_index: int, root_scaler_index: int, flags: int = 0, chunk_offsets=None):
         pmo = np.ascontiguousarray(pm_offsets, dtype=np.uint32)
         mi = np.ascontiguousarray(matrix_indices, dtype=np.uint32)
         bl = np.ascontiguousarray(branch_lengths, dtype=np.float64)
@@ -281,9 +286,16 @@ class Partition:
         arr = ops if isinstance(ops, C.Array) else ops_array(ops)
         n = len(pmo) - 1
         out = np.zeros(n)
-        rc = self.L.rdk_sweep_root_placements_ex(self.p, n, self._zeros, self._zeros, _ptr(pmo, _up), _ptr(mi, _up),
-                                                 _ptr(bl, _dp), _ptr(opo, _up), arr, root_clv_index,
-                                                 root_scaler_index, flags, _ptr(out, _dp))
+        if chunk_offsets is None:
+            rc = self.L.rdk_sweep_root_placements_ex(self.p, n, self._zeros, self._zeros, _ptr(pmo, _up),
+                                                     _ptr(mi, _up), _ptr(bl, _dp), _ptr(opo, _up), arr,
+                                                     root_clv_index, root_scaler_index, flags, _ptr(out, _dp))
+        else:  # independent chunks of consecutive placements (rdk.h): the engine may walk them side by side
+            co = np.ascontiguousarray(chunk_offsets, dtype=np.uint32)
+            rc = self.L.rdk_sweep_root_placements_chunks(self.p, n, self._zeros, self._zeros, _ptr(pmo, _up),
+                                                         _ptr(mi, _up), _ptr(bl, _dp), _ptr(opo, _up), arr,
+                                                         root_clv_index, root_scaler_index, flags, len(co) - 1,
+                                                         _ptr(co, _up), _ptr(out, _dp))
         if rc != RDK_SUCCESS:
             raise EngineError(_err(self.L))
         return out
@@ -358,6 +370,11 @@ class Partition:
 
     def reset_stats(self):
         self.L.rdk_partition_reset_stats(self.p)
+
+
+def sweep_chunk_hint(sites: int, rate_cats: int) -> int:
+    """rdk_sweep_chunk_hint: independent chunks a directed sweep over such a shard should be cut into"""
+    return int(load_engine().rdk_sweep_chunk_hint(sites, rate_cats))
 
 
 def comm_unique_id() -> bytes:
@@ -518,12 +535,38 @@ class RootedTree:
 
     sweep_depth_bound = property(lambda s: s.L.rdh_tree_sweep_depth_bound(s.h))
 
-    def sweep_layout(self):
-        """buffer counts and first spare indices of a partition that can run the directed sweep:
-        dict(clv_buffers, scale_buffers, prob_matrices, clv0, scaler0, pm0, extra)"""
+    def sweep_layout(self, chunks: int = 1):
+        """buffer counts and first spare indices of a partition that can run the directed sweep in
+        `chunks` independent chunks: dict(clv_buffers, scale_buffers, prob_matrices, clv0, scaler0, pm0,
+        extra, chunks)"""
         n, br, extra = self.tip_count, self.branch_count, self.sweep_depth_bound
-        return dict(clv_buffers=br + extra, scale_buffers=br + extra, prob_matrices=br + 3, clv0=n + br,
-                    scaler0=br, pm0=br, extra=extra)
+        return dict(clv_buffers=br + chunks * extra, scale_buffers=br + chunks * extra, prob_matrices=br + 3,
+                    clv0=n + br, scaler0=br, pm0=br, extra=extra, chunks=chunks)
+
+    def generate_chunked_sweep_operations(self, begin: int | None = None, end: int | None = None, layout=None):
+        """the directed sweep of root positions [begin, end) cut into layout["chunks"] independent chunks,
+        each on its own spare buffers (model_t::sweep_root_lh does the same).  Returns
+        (pm_off, mi, bl, op_off, ops, root_pos, chunk_offsets): the arguments of
+        Partition.sweep_root_placements(..., chunk_offsets=...)."""
+        lay = layout or self.sweep_layout()
+        begin = 0 if begin is None else begin
+        end = self.root_count if end is None else end
+        total = end - begin
+        chunks = max(1, min(lay.get("chunks", 1), total // 8))
+        pm_off, op_off, mi, bl, ops, pos, coff = [0], [0], [], [], [], [], [0]
+        for c in range(chunks):
+            b0, b1 = begin + total * c // chunks, begin + total * (c + 1) // chunks
+            sub = dict(lay, clv0=lay["clv0"] + c * lay["extra"], scaler0=lay["scaler0"] + c * lay["extra"])
+            p_off, p_mi, p_bl, o_off, p_ops, p_pos = self.generate_sweep_operations(b0, b1, layout=sub)
+            pm_off += [len(mi) + int(x) for x in p_off[1:]]
+            op_off += [len(ops) + int(x) for x in o_off[1:]]
+            mi += p_mi.tolist()
+            bl += p_bl.tolist()
+            ops += p_ops
+            pos += p_pos.tolist()
+            coff.append(len(pos))
+        return (np.array(pm_off, dtype=np.uint32), np.array(mi, dtype=np.uint32), np.array(bl, dtype=np.float64),
+                np.array(op_off, dtype=np.uint32), ops, np.array(pos, dtype=np.int64), np.array(coff, dtype=np.uint32))
 
     def generate_sweep_operations(self, begin: int | None = None, end: int | None = None, layout=None):
         """rooted_tree_t::generate_sweep_operations from the CURRENT root: the directed-CLV sweep of

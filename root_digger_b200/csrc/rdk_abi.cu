@@ -148,6 +148,7 @@ struct Engine {
   unsigned               pend_slots = 0;  // eval slots used by pend_prog
   unsigned long long     pend_bytes = 0;  // algorithmic bytes of pend_prog
   unsigned               pend_ops = 0, pend_evals = 0;
+  std::vector<unsigned>  pend_chunk_off;  // > 2 entries: pend_prog is that many - 1 independent chunks
   bool                   want_persite = false;
 
   Ring    ring;
@@ -345,12 +346,15 @@ int ensure_partials(Engine *e, unsigned slots, unsigned stride) {
 // pointers at run time: which operands are forwarded in registers from the previous
 // instruction and which scaler counts have to be loaded.  The first instruction of a
 // shared-memory window never forwards (its operands are loaded from memory).
-void finalize_program(std::vector<Instr> &prog, int table_K) {
+void finalize_program(std::vector<Instr> &prog, int table_K, const std::vector<unsigned> &chunk_off) {
+  size_t chunk = 0, chunk_begin = 0;
   const unsigned decoded = kFwd1 | kFwd2 | kLdS1 | kLdS2 | kFwdS1 | kFwdS2 | kEvalScaler;
   for (size_t i = 0; i < prog.size(); ++i) {
     Instr &in = prog[i];
     in.flags &= ~decoded;
-    const bool   first = (i % kProgWindow) == 0;
+    // shared-memory windows restart at every chunk of a chunked program
+    while (chunk + 1 < chunk_off.size() && i >= chunk_off[chunk + 1]) chunk_begin = chunk_off[++chunk];
+    const bool   first = ((i - chunk_begin) % kProgWindow) == 0;
     const Instr *pv = first ? nullptr : &prog[i - 1];
     const double   *fwd_clv = (pv && (pv->flags & kWrite)) ? pv->parent : nullptr;
     const unsigned *fwd_scale = (pv && (pv->flags & kWrite)) ? pv->pscale : nullptr;
@@ -425,7 +429,12 @@ int flush(rdk_partition_t *p) {
     a.partials = e->d_partials;
   }
   a.persite = e->want_persite ? e->d_persite : nullptr;
-  finalize_program(e->pend_prog, (int)e->K);
+  const bool chunked = e->pend_chunk_off.size() > 2 && e->pend_prog.size() > (size_t)kProgInline;
+  if (chunked) {
+    a.n_chunks = (unsigned)e->pend_chunk_off.size() - 1;
+    for (size_t c = 0; c < e->pend_chunk_off.size(); ++c) a.chunk_off[c] = e->pend_chunk_off[c];
+  }
+  finalize_program(e->pend_prog, (int)e->K, chunked ? e->pend_chunk_off : std::vector<unsigned>());
   if (a.n_instr <= kProgInline) {
     for (int i = 0; i < a.n_instr; ++i) a.inl[i] = e->pend_prog[i];
   } else {
@@ -487,6 +496,7 @@ int flush(rdk_partition_t *p) {
   e->stats.root_evals += e->pend_evals;
   e->stats.algorithmic_bytes += e->pend_bytes;
   e->pend_prog.clear();
+  e->pend_chunk_off.clear();
   e->pend_ops = e->pend_evals = 0;
   e->pend_bytes = 0;
   for (unsigned s : e->pm_retired) e->pm_free.push_back(s);
@@ -702,7 +712,9 @@ static int engine_init(rdk_partition_t *p, Engine *e) {
   CUDA_TRY(cudaStreamSynchronize(e->stream));
 
   // P-matrix pool: every index has a slot, plus spare slots for renaming
-  e->pool_slots = e->prob_matrices * 2 + 4096;
+  // two generations of every matrix, 4096 for the per-placement root branches of a sweep, and
+  // room for the chunks of a chunked sweep to re-record the branches they walk
+  e->pool_slots = e->prob_matrices * 2 + 4096 + std::min<unsigned>(e->prob_matrices * (unsigned)kMaxChunks, 32768u);
   size_t pool_bytes = sizeof(double) * kSlotDoubles * e->K * (size_t)e->pool_slots;
   if (!dev_alloc(e, (void **)&e->d_pool, pool_bytes)) return RDK_FAILURE;
   CUDA_TRY(cudaMemsetAsync(e->d_pool, 0, pool_bytes, e->stream));
@@ -1097,6 +1109,38 @@ extern "C" int rdk_sweep_root_placements_ex(rdk_partition_t *p, unsigned int pla
                                             const rdk_operation_t *operations,
                                             unsigned int root_clv_index, int root_scaler_index,
                                             unsigned int flags, double *out_lnl) {
+  const unsigned int one[2] = {0u, placements};
+  return rdk_sweep_root_placements_chunks(p, placements, params_indices, freqs_indices, pm_offsets,
+                                          matrix_indices, branch_lengths, op_offsets, operations,
+                                          root_clv_index, root_scaler_index, flags, 1u, one, out_lnl);
+}
+
+extern "C" unsigned int rdk_sweep_chunk_hint(unsigned int sites, unsigned int rate_cats) {
+  if (const char *env = getenv("RDK_SWEEP_CHUNKS")) {  // kernel experiments
+    int v = atoi(env);
+    if (v >= 1) return (unsigned)std::min(v, kMaxChunks);
+  }
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  // warps one walk of the shard occupies (one warp iteration = 32 elements each, at least)
+  // against the warps the device holds in the E = 2 configuration (4 CTAs x 4 warps per SM)
+  const unsigned long long n_witer = ((unsigned long long)sites * rate_cats + 31) / 32;
+  const unsigned long long capacity = (unsigned long long)sms * 16;
+  if (n_witer == 0 || n_witer >= capacity) return 1;
+  return (unsigned)std::min<unsigned long long>(kMaxChunks, (2 * capacity + n_witer / 2) / n_witer);
+}
+
+extern "C" int rdk_sweep_root_placements_chunks(rdk_partition_t *p, unsigned int placements,
+                                                const unsigned int *params_indices,
+                                                const unsigned int *freqs_indices,
+                                                const unsigned int *pm_offsets,
+                                                const unsigned int *matrix_indices,
+                                                const double *branch_lengths,
+                                                const unsigned int *op_offsets,
+                                                const rdk_operation_t *operations,
+                                                unsigned int root_clv_index, int root_scaler_index,
+                                                unsigned int flags, unsigned int n_chunks,
+                                                const unsigned int *chunk_offsets, double *out_lnl) {
   (void)params_indices;
   (void)freqs_indices;
   Engine *e = eng(p);
@@ -1119,14 +1163,41 @@ extern "C" int rdk_sweep_root_placements_ex(rdk_partition_t *p, unsigned int pla
   // batches bounded by the spare P-matrix slots and the partial-sum buffer
   const size_t   stride = std::max(1u, (e->S * e->K + 31) / 32);
   const unsigned max_slots = (unsigned)std::max<size_t>(1, std::min<size_t>(4096, (size_t(256) << 20) / (stride * 8)));
+  // the chunks run side by side only when nothing they share is written (the root CLV is:
+  // RDK_SWEEP_KEEP_ROOT must be set) and the whole sweep is one launch; otherwise they run
+  // in order, which the contract always allows
+  bool concurrent = n_chunks > 1 && n_chunks <= (unsigned)kMaxChunks && (flags & RDK_SWEEP_KEEP_ROOT) &&
+                    placements <= max_slots && pm_offsets[placements] <= e->pm_free.size();
+  if (concurrent) {
+    if (chunk_offsets[0] != 0 || chunk_offsets[n_chunks] != placements)
+      return fail(RDK_ERROR_PARAM, "chunk_offsets must run from 0 to the number of placements");
+    for (unsigned c = 0; c < n_chunks; ++c)
+      if (chunk_offsets[c] >= chunk_offsets[c + 1]) concurrent = false;  // an empty chunk: run in order
+    // every placement must end in the root operation that is evaluated in registers
+    for (unsigned q = 0; q < placements && concurrent; ++q) {
+      if (op_offsets[q + 1] == op_offsets[q]) {
+        concurrent = false;
+        break;
+      }
+      const rdk_operation_t &last = operations[op_offsets[q + 1] - 1];
+      if (last.parent_clv_index != root_clv_index || last.parent_scaler_index != root_scaler_index)
+        concurrent = false;
+    }
+  }
   unsigned       done = 0;
   while (done < placements) {
     unsigned b = 0;
     size_t   pm_budget = e->pm_free.size();
+    unsigned next_chunk = 0;
+    if (concurrent) e->pend_chunk_off.clear();
     while (done + b < placements && b < max_slots) {
       unsigned q = done + b;
       size_t   need = pm_offsets[q + 1] - pm_offsets[q];
       if (need > pm_budget) break;
+      if (concurrent && next_chunk < n_chunks && q == chunk_offsets[next_chunk]) {
+        e->pend_chunk_off.push_back((unsigned)e->pend_prog.size());
+        ++next_chunk;
+      }
       pm_budget -= need;
       for (unsigned i = pm_offsets[q]; i < pm_offsets[q + 1]; ++i)
         if (!record_pmatrix(p, matrix_indices[i], branch_lengths[i])) return RDK_FAILURE;
@@ -1162,6 +1233,7 @@ extern "C" int rdk_sweep_root_placements_ex(rdk_partition_t *p, unsigned int pla
       ++b;
     }
     if (b == 0) return fail(RDK_ERROR_PARAM, "a placement needs more P-matrices than the pool holds");
+    if (concurrent) e->pend_chunk_off.push_back((unsigned)e->pend_prog.size());
     e->pend_slots = b;
     int ok = flush(p);
     e->pend_slots = 0;

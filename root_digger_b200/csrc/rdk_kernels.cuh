@@ -543,6 +543,7 @@ constexpr int kProgInline = 8;
 #define RDK_PROG_WINDOW 256
 #endif
 constexpr int kProgWindow = RDK_PROG_WINDOW;  // instructions staged in shared memory at a time
+constexpr int kMaxChunks = 16;  // independent sub-programs one launch can run side by side
 struct ProgArgs {
   const Instr*    prog;  // used when n_instr > kProgInline
   int             n_instr;
@@ -554,6 +555,12 @@ struct ProgArgs {
   double*         persite;  // optional, eval slot 0 only
   double          pi[4];
   double          w[kMaxCats];
+  // n_chunks > 1: the program is n_chunks INDEPENDENT sub-programs (chunk c = instructions
+  // [chunk_off[c], chunk_off[c+1]) of prog); blockIdx.y selects the one a CTA walks, so a
+  // small shard fills the device with (site range) x (chunk) warps instead of leaving a
+  // handful of warps per SM to walk one long chain
+  unsigned        n_chunks;
+  unsigned        chunk_off[kMaxChunks + 1];
   Instr           inl[kProgInline];
 };
 
@@ -718,7 +725,13 @@ __global__ void __launch_bounds__(MAXT, MINB) clv_program_kernel(const __grid_co
   // CTA-wide); a warp whose range is exhausted idles through the remaining ones
   const unsigned passes = ((a.n_witer + nw - 1) / nw + E - 1) / E;
   const unsigned last_site = a.nelem / K - 1;
-  const bool     multi_window = a.n_instr > kProgWindow;
+  const Instr*   prog = a.prog;
+  int            n_instr = a.n_instr;
+  if (a.n_chunks > 1) {
+    prog += a.chunk_off[blockIdx.y];
+    n_instr = (int)(a.chunk_off[blockIdx.y + 1] - a.chunk_off[blockIdx.y]);
+  }
+  const bool     multi_window = n_instr > kProgWindow;
 
 #if !RDK_TABLES_L1
   if (lane == 0) {
@@ -1100,11 +1113,11 @@ __global__ void __launch_bounds__(MAXT, MINB) clv_program_kernel(const __grid_co
       if (ii < wn) dispatch(nvc, integral_constant<unsigned, 0>{}, ii, wn, opA, opB);
     };
 
-    for (int w0 = 0; w0 < a.n_instr; w0 += kProgWindow) {
-      const int wn = min(kProgWindow, a.n_instr - w0);
+    for (int w0 = 0; w0 < n_instr; w0 += kProgWindow) {
+      const int wn = min(kProgWindow, n_instr - w0);
       if (multi_window || pass == 0) {
         if (multi_window) __syncthreads();  // every warp is done with the previous window
-        const int4* src = reinterpret_cast<const int4*>(a.n_instr <= kProgInline ? a.inl : a.prog + w0);
+        const int4* src = reinterpret_cast<const int4*>(a.n_instr <= kProgInline ? a.inl : prog + w0);
         int4*       dst = reinterpret_cast<int4*>(s_prog);
         for (unsigned c = tid; c < (unsigned)wn * (sizeof(Instr) / 16); c += blockDim.x) dst[c] = src[c];
         __syncthreads();

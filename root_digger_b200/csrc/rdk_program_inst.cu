@@ -29,7 +29,7 @@ cudaError_t launch_inst(const ProgArgs &a, int grid, int threads, cudaStream_t s
     if (err != cudaSuccess) return err;
     configured = smem;
   }
-  clv_program_kernel<K, E, MAXT, MINB, TS><<<grid, threads, smem, st>>>(a);
+  clv_program_kernel<K, E, MAXT, MINB, TS><<<dim3((unsigned)grid, a.n_chunks > 1 ? a.n_chunks : 1u), threads, smem, st>>>(a);
   return cudaSuccess;
 }
 

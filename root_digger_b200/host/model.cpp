@@ -60,11 +60,20 @@ model_t::model_t(rooted_tree_t tree, const std::vector<msa_t> &msas,
     // buffers for the directed CLVs of the placement sweep (one per depth level) and three
     // spare P-matrices (rooted_tree_t::generate_sweep_operations); the engine allocates a
     // CLV on first use, so unused spares cost only their scale buffer
+    // -- once per independent CHUNK of the sweep: a small partition fills the device only
+    // when several chunks of placements are walked side by side (rdk_sweep_root_placements_chunks)
     _sweep_extra = _tree.sweep_depth_bound();
+    if (pi == 0) {
+      _sweep_chunks = 1;
+      for (size_t q = 0; q < msas.size(); ++q)
+        _sweep_chunks = std::max(_sweep_chunks, rdk_sweep_chunk_hint((unsigned int)msas[q].length(),
+                                                                     (unsigned int)_rate_rates[q].size()));
+      _sweep_chunks = std::min<unsigned int>(_sweep_chunks, RDK_SWEEP_MAX_CHUNKS);
+    }
     rdk_partition_t *p = rdk_partition_create(
-        _tree.tip_count(), _tree.branch_count() + _sweep_extra, msa.states(), msa.length(), _submodels,
-        _tree.branch_count() + 3, static_cast<unsigned int>(_rate_rates[pi].size()),
-        _tree.branch_count() + _sweep_extra, attributes);
+        _tree.tip_count(), _tree.branch_count() + _sweep_chunks * _sweep_extra, msa.states(), msa.length(),
+        _submodels, _tree.branch_count() + 3, static_cast<unsigned int>(_rate_rates[pi].size()),
+        _tree.branch_count() + _sweep_chunks * _sweep_extra, attributes);
     if (!p) throw std::runtime_error("partition could not be created: " + engine_error());
     _partitions.push_back(p);
 #ifndef RD_BACKEND_ORACLE
@@ -538,15 +547,34 @@ std::vector<double> model_t::sweep_root_lh(size_t begin, size_t end) {
   if (_sweep_mode == sweep_mode_t::directed) {
     // one pre-order pass over directed CLVs from the current root; same bits as the loop
     // above (tree.hpp), ~1 CLV operation + 1 root evaluation per placement
-    auto sw = _tree.generate_sweep_operations(begin, end, _tree.tip_count() + _tree.branch_count(),
-                                              (int)_tree.branch_count(), _tree.branch_count(), _sweep_extra);
+    // cut into _sweep_chunks ranges of consecutive root ids, each with its own spare buffers
+    // (and its own copy of the directed CLVs on the path to its first placement): independent
+    // programs the engine may walk side by side
+    const size_t                 total = end - begin;
+    const unsigned int           chunks = (unsigned int)std::max<size_t>(1, std::min<size_t>(_sweep_chunks, total / 8));
+    rooted_tree_t::sweep_schedule_t sw;
+    std::vector<unsigned int>    chunk_off{0};
+    for (unsigned int c = 0; c < chunks; ++c) {
+      const size_t b0 = begin + total * c / chunks, b1 = begin + total * (c + 1) / chunks;
+      auto part = _tree.generate_sweep_operations(b0, b1, _tree.tip_count() + _tree.branch_count() + c * _sweep_extra,
+                                                  (int)(_tree.branch_count() + c * _sweep_extra),
+                                                  _tree.branch_count(), _sweep_extra);
+      const unsigned int pm_base = (unsigned int)sw.mi.size(), op_base = (unsigned int)sw.ops.size();
+      sw.mi.insert(sw.mi.end(), part.mi.begin(), part.mi.end());
+      sw.bl.insert(sw.bl.end(), part.bl.begin(), part.bl.end());
+      sw.ops.insert(sw.ops.end(), part.ops.begin(), part.ops.end());
+      for (size_t q = 1; q < part.pm_off.size(); ++q) sw.pm_off.push_back(pm_base + part.pm_off[q]);
+      for (size_t q = 1; q < part.op_off.size(); ++q) sw.op_off.push_back(op_base + part.op_off[q]);
+      sw.root_pos.insert(sw.root_pos.end(), part.root_pos.begin(), part.root_pos.end());
+      chunk_off.push_back((unsigned int)sw.root_pos.size());
+    }
     std::vector<double> part(sw.root_pos.size());
     for (size_t i = 0; i < _partitions.size(); ++i) {
-      int rc = rdk_sweep_root_placements_ex(_partitions[i], (unsigned)sw.root_pos.size(),
-                                            _param_indicies[i].data(), _param_indicies[i].data(),
-                                            sw.pm_off.data(), sw.mi.data(), sw.bl.data(), sw.op_off.data(),
-                                            sw.ops.data(), _tree.root_clv_index(), _tree.root_scaler_index(),
-                                            RDK_SWEEP_KEEP_ROOT, part.data());
+      int rc = rdk_sweep_root_placements_chunks(_partitions[i], (unsigned)sw.root_pos.size(),
+                                                _param_indicies[i].data(), _param_indicies[i].data(),
+                                                sw.pm_off.data(), sw.mi.data(), sw.bl.data(), sw.op_off.data(),
+                                                sw.ops.data(), _tree.root_clv_index(), _tree.root_scaler_index(),
+                                                RDK_SWEEP_KEEP_ROOT, chunks, chunk_off.data(), part.data());
       if (rc == RDK_FAILURE) throw std::runtime_error(engine_error());
       for (size_t q = 0; q < part.size(); ++q) lh[sw.root_pos[q] - begin] += part[q];
     }

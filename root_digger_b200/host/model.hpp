@@ -188,7 +188,8 @@ private:
   uint64_t                               _seed;
   bool                                   _early_stop;
   sweep_mode_t                           _sweep_mode = sweep_mode_t::directed;
-  unsigned int                           _sweep_extra = 0;
+  unsigned int                           _sweep_extra = 0;   // spare directed-CLV buffers per sweep chunk
+  unsigned int                           _sweep_chunks = 1;  // independent chunks of a directed sweep
   static constexpr unsigned int          _submodels = 1;
 };
 

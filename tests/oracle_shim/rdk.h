@@ -76,4 +76,29 @@ static inline int rdk_sweep_root_placements_ex(rdo_partition_t *p, unsigned int 
                                    branch_lengths, op_offsets, operations, root_clv_index, root_scaler_index,
                                    out_lnl);
 }
+/* chunks may always run in order; the hint is > 1 for small alignments so that the CPU
+ * tests walk the chunked schedules of the host mirror too */
+#define RDK_SWEEP_MAX_CHUNKS 16u
+static inline unsigned int rdk_sweep_chunk_hint(unsigned int sites, unsigned int rate_cats) {
+  (void)rate_cats;
+  return sites < 4096u ? 3u : 1u;
+}
+static inline int rdk_sweep_root_placements_chunks(rdo_partition_t *p, unsigned int placements,
+                                                   const unsigned int *params_indices,
+                                                   const unsigned int *freqs_indices,
+                                                   const unsigned int *pm_offsets,
+                                                   const unsigned int *matrix_indices,
+                                                   const double *branch_lengths,
+                                                   const unsigned int *op_offsets,
+                                                   const rdo_operation_t *operations,
+                                                   unsigned int root_clv_index, int root_scaler_index,
+                                                   unsigned int flags, unsigned int n_chunks,
+                                                   const unsigned int *chunk_offsets, double *out_lnl) {
+  (void)flags;
+  (void)n_chunks;
+  (void)chunk_offsets;
+  return rdk_sweep_root_placements(p, placements, params_indices, freqs_indices, pm_offsets, matrix_indices,
+                                   branch_lengths, op_offsets, operations, root_clv_index, root_scaler_index,
+                                   out_lnl);
+}
 #endif

@@ -217,6 +217,48 @@ def test_directed_sweep_equals_the_reference_loop(n, S, K, data):
         assert max(int(g.get_scaler(lay["scaler0"]).max()), int(g.get_scaler(case.root_scaler).max())) > 0
 
 
+@pytest.mark.parametrize("n,S,K,data,chunks", [(40, 700, 4, "evolved", 2), (150, 700, 4, "iid", 5),
+                                               (300, 129, 2, "iid", 16), (64, 3000, 4, "ambiguous", 3)])
+def test_chunked_sweep_equals_the_unchunked_sweep(n, S, K, data, chunks):
+    """rdk_sweep_root_placements_chunks: the directed sweep cut into independent chunks of placements,
+    walked side by side in ONE launch (gridDim.y = chunks), returns the bits of the unchunked directed
+    sweep -- hence of the reference's move_root + compute_lh_root loop -- and leaves the partition's own
+    CLVs untouched; the launch count shows the chunks really shared a launch"""
+    from root_digger_b200.capi import RDK_SWEEP_KEEP_ROOT, Partition
+    case = Case(n, S, K, seed=5 + n, data=data, weights="random")
+    lay = case.tree.sweep_layout(chunks)
+    kw = dict(clv_buffers=lay["clv_buffers"], scale_buffers=lay["scale_buffers"], prob_matrices=lay["prob_matrices"])
+    g, o = Partition(case.n, case.S, case.K, **kw), OraclePartition(case.n, case.S, case.K, **kw)
+    case.setup(g)
+    case.setup(o)
+    start = case.tree.root_count // 2
+    s0 = case.full_schedule(start, 0.3)
+    lh0 = compute_lh(g, s0, case.root_clv, case.root_scaler)
+    compute_lh(o, s0, case.root_clv, case.root_scaler)
+    *sw, pos = case.tree.generate_sweep_operations(layout=lay)
+    want = np.empty(len(pos))
+    want[pos] = g.sweep_root_placements(*sw, case.root_clv, case.root_scaler, flags=RDK_SWEEP_KEEP_ROOT)
+    *csw, cpos, coff = case.tree.generate_chunked_sweep_operations(layout=lay)
+    assert len(coff) - 1 == min(chunks, case.tree.root_count // 8) and sorted(cpos.tolist()) == sorted(pos.tolist())
+    before = g.stats()["program_launches"]
+    root_before = g.get_clv(case.root_clv).copy()
+    got = np.empty(len(cpos))
+    got[cpos] = g.sweep_root_placements(*csw, case.root_clv, case.root_scaler, flags=RDK_SWEEP_KEEP_ROOT,
+                                        chunk_offsets=coff)
+    assert g.stats()["program_launches"] == before + 1
+    assert same_bits(got, want)
+    assert same_bits(root_before, g.get_clv(case.root_clv))
+    assert compute_lh_root(g, case.derivative_schedule(start, 0.3), case.root_clv, case.root_scaler) == lh0
+    # the same chunked schedule run in order on the oracle, and the reference's loop
+    ora = np.empty(len(cpos))
+    ora[cpos] = o.sweep_root_placements(*csw, case.root_clv, case.root_scaler, mode=MODE_ENGINE)
+    assert same_bits(got, ora)
+    # without RDK_SWEEP_KEEP_ROOT the chunks share the root buffers: the engine runs them in order
+    got2 = np.empty(len(cpos))
+    got2[cpos] = g.sweep_root_placements(*csw, case.root_clv, case.root_scaler, flags=0, chunk_offsets=coff)
+    assert same_bits(got2, want)
+
+
 def test_launch_configs_do_not_change_results():
     case = Case(25, 5000, 4, seed=11, data="ambiguous", weights="random")
     g, o = make(case)
