@@ -31,7 +31,8 @@
 // (cfg2 step): 24 % fewer warp instructions, but the same time at E = 4 (80.4 k vs 81-82 k
 // placements/s) and +4 % at E = 2 (66.4 k vs 63.8 k): the walk is bound by the latency of each
 // warp's dependent chain, not by issue slots, and the copies cost instruction-cache misses and
-// 2 more minutes of compile time.  Off by default.
+// 2 more minutes of compile time.  (2: also for the short tail passes -- 64.7 k at 100 k sites,
+// no gain on a 12.5 k-site shard.)  Off by default.
 #define RDK_FAST_KINDS 0
 #endif
 #ifndef RDK_TABLES_L1
@@ -1063,7 +1064,7 @@ __global__ void __launch_bounds__(MAXT, MINB) clv_program_kernel(const __grid_co
       d4             scratch[E];
       const unsigned kind = s_prog[ii].kind;
       // (short tail passes, NV < E, run the run-time decoded body: they are rare)
-      if constexpr (FAST && decltype(nvc)::value == E) {
+      if constexpr (FAST && (decltype(nvc)::value == E || RDK_FAST_KINDS >= 2)) {
         switch (kind) {
           case 2: step(nvc, integral_constant<int, (int)kFastKinds[0]>{}, no_fwd{}, bufc, ii, wn, cur, nxt, scratch); break;
           case 3: step(nvc, integral_constant<int, (int)kFastKinds[0]>{}, fwd{}, bufc, ii, wn, cur, nxt, nxt.c2); break;
