@@ -472,6 +472,9 @@ int flush(rdk_partition_t *p) {
     // never launch more warps than warp iterations
     int max_grid = (int)((n_witer + (threads / 32) - 1) / (threads / 32));
     grid = std::max(1, std::min(grid, max_grid));
+    // a chunked program launches grid x chunks CTAs: keep them all resident at once (one wave) --
+    // a partial extra wave costs as much as a full one, so the warps take more iterations instead
+    if (chunked) grid = std::max(1, std::min(grid, (e->sm_count * per_sm) / (int)a.n_chunks));
     std::pair<cudaEvent_t, cudaEvent_t> *ev = e->timing ? next_event_pair(e) : nullptr;
     if (ev) CUDA_TRY(cudaEventRecord(ev->first, e->stream));
     if (E != 1) threads = std::min(threads, 128);
@@ -1127,7 +1130,10 @@ extern "C" unsigned int rdk_sweep_chunk_hint(unsigned int sites, unsigned int ra
   const unsigned long long n_witer = ((unsigned long long)sites * rate_cats + 31) / 32;
   const unsigned long long capacity = (unsigned long long)sms * 16;
   if (n_witer == 0 || n_witer >= capacity) return 1;
-  return (unsigned)std::min<unsigned long long>(kMaxChunks, (2 * capacity + n_witer / 2) / n_witer);
+  // the largest count that still gives every warp of a one-wave launch at most E = 2 iterations
+  // (one pass): rounding UP instead costs a second pass -- measured on B200, 13 312-site shard,
+  // 3 chunks: 2.95 ms per cfg2 step against 2.16 ms for 12 500 sites
+  return (unsigned)std::max<unsigned long long>(1, std::min<unsigned long long>(kMaxChunks, 2 * capacity / n_witer));
 }
 
 extern "C" int rdk_sweep_root_placements_chunks(rdk_partition_t *p, unsigned int placements,
