@@ -197,6 +197,34 @@ def test_reads_a_file_written_by_the_restated_format(lib, tmp_path):
             assert q["alpha"] == r[3][part]["alpha"] and q["weights"].tolist() == r[3][part]["weights"]
 
 
+def test_golden_checkpoint_file(lib, tmp_path, golden_dir):
+    """tests/golden/checkpoint_v1.ckp (written by tests/golden/make_checkpoint_golden.py): read back by
+    the C++, and reproduced byte for byte when the C++ writes the same options and records"""
+    import importlib.util
+    import shutil
+    spec = importlib.util.spec_from_file_location("make_checkpoint_golden", golden_dir / "make_checkpoint_golden.py")
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    blob = (golden_dir / "checkpoint_v1.ckp").read_bytes()
+    assert blob == mk.golden_bytes()                       # the committed file is what the script writes
+    p = new_prefix(tmp_path, "golden")
+    shutil.copy(golden_dir / "checkpoint_v1.ckp", p + ".ckp")
+    c = capi.Checkpoint(p, lib)
+    assert c.existing and not c.needs_cleaning()
+    assert c.load_options(**mk.OPTIONS)["equal"]
+    recs = mk.records()
+    assert c.read_results() == [(r[0], r[1], r[2], 1) for r in recs]
+    assert c.completed_indicies() == [0, 7, 42, 198]
+    for i, r in enumerate(recs):
+        q = c.read_params(i, 0)
+        assert q["rates"].tolist() == r[3][0]["rates"] and q["alpha"] == r[3][0]["alpha"]
+    w = capi.Checkpoint(new_prefix(tmp_path, "rewrite"), lib)
+    w.save_options(**mk.OPTIONS)
+    for r in recs:
+        w.write(*r)
+    assert open(w.filename, "rb").read() == blob
+
+
 @pytest.mark.parametrize("damage", ["truncate", "flip"])
 def test_damaged_tail_is_dropped_and_cleaned(lib, tmp_path, damage):
     """src/checkpoint.cpp:318-324 ("resume with what we can"), needs_cleaning :329-362, clean :165-190"""
