@@ -226,6 +226,13 @@ def cpu_reference_run(args, case, steps, warmup, threads, target_step_s=1.5, qui
     return value, info, ms_step_full
 
 
+def cpu_single_thread(args, case):
+    """what the reference itself would do on this single-partition workload: it threads over
+    partitions only, i.e. ONE thread; short bounded sample, scaled by sites"""
+    v, info, ms = cpu_reference_run(args, case, steps=1, warmup=0, threads=1, target_step_s=1.0)
+    return {"value": v, "unit": UNIT, "cores": 1, "ms_per_step_full_size": ms, "sample": info["sample"]}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -234,6 +241,7 @@ def run_reference(args):
     threads = os.cpu_count() or 1
     case = build_case_cpu(args)
     value, info, ms_full = cpu_reference_run(args, case, args.steps, args.warmup, threads)
+    info["single_thread"] = cpu_single_thread(args, case)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_full, "higher_is_better": True,
@@ -490,6 +498,7 @@ def run_ours(args):
     if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         _, cpu, _ = cpu_reference_run(args, case, steps=3, warmup=1, threads=threads, target_step_s=3.0)
+        cpu["single_thread"] = cpu_single_thread(args, case)
 
     if rank == 0:
         line = {
