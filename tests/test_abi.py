@@ -55,6 +55,22 @@ def test_host_math_matches_oracle_bit_for_bit():
         capi.gamma_cats(0.001, 4)
 
 
+def test_sweep_chunk_hint_rule(monkeypatch):
+    """rdk_sweep_chunk_hint is host arithmetic (148 SMs assumed without a device): the largest chunk count
+    that leaves every warp of a one-wave launch at most 2 iterations; 1 once the shard fills the device"""
+    import torch
+    if torch.cuda.is_available() and torch.cuda.get_device_properties(0).multi_processor_count != 148:
+        pytest.skip("rule values below are for 148 SMs")
+    monkeypatch.delenv("RDK_SWEEP_CHUNKS", raising=False)
+    h = capi.sweep_chunk_hint
+    assert h(100000, 4) == 1 and h(25000, 4) == 1 and h(18944, 4) == 1   # >= 2368 warp iterations
+    assert h(12500, 4) == 3 and h(13312, 4) == 2 and h(6250, 4) == 6
+    assert h(1630, 4) == 16 and h(10, 1) == 16 and h(0, 4) == 1          # capped at RDK_SWEEP_MAX_CHUNKS
+    assert h(50000, 1) == 3                                               # 1 category: a quarter of the elements
+    monkeypatch.setenv("RDK_SWEEP_CHUNKS", "5")
+    assert h(100000, 4) == 5
+
+
 def test_no_gpu_means_loud_failure_not_fallback():
     import torch
     if torch.cuda.is_available():

@@ -131,3 +131,38 @@ def test_schedule_invariants_on_random_trees(n):
     t.unroot()
     c = t.copy()
     assert [c.root_info(i)[0] for i in range(c.root_count)] == [t.root_info(i)[0] for i in range(t.root_count)]
+
+
+@pytest.mark.parametrize("chunks,begin,end", [(3, None, None), (16, None, None), (4, 10, 61), (5, 0, 7)])
+def test_chunked_sweep_schedule_on_the_oracle(chunks, begin, end):
+    """RootedTree.generate_chunked_sweep_operations (what bench.py feeds
+    rdk_sweep_root_placements_chunks): chunks use disjoint spare buffers, cover the requested
+    root positions once, and -- run in order on the oracle -- give the bits of the unchunked sweep"""
+    import numpy as np
+    from cases import Case, compute_lh, same_bits
+    from oracle_capi import MODE_ENGINE, OraclePartition
+    case = Case(40, 300, 4, seed=31, data="ambiguous", weights="random")
+    lay = case.tree.sweep_layout(chunks)
+    o = OraclePartition(case.n, case.S, case.K, clv_buffers=lay["clv_buffers"], scale_buffers=lay["scale_buffers"],
+                        prob_matrices=lay["prob_matrices"])
+    case.setup(o)
+    compute_lh(o, case.full_schedule(5, 0.4), case.root_clv, case.root_scaler)
+    *sw, pos = case.tree.generate_sweep_operations(begin, end, layout=lay)
+    want = np.empty(case.tree.root_count)
+    want[pos] = o.sweep_root_placements(*sw, case.root_clv, case.root_scaler, mode=MODE_ENGINE)
+    compute_lh(o, case.full_schedule(5, 0.4), case.root_clv, case.root_scaler)
+    *csw, cpos, coff = case.tree.generate_chunked_sweep_operations(begin, end, layout=lay)
+    b, e = (0 if begin is None else begin), (case.tree.root_count if end is None else end)
+    assert sorted(cpos.tolist()) == list(range(b, e)) and coff[0] == 0 and coff[-1] == len(cpos)
+    assert len(coff) - 1 == max(1, min(chunks, (e - b) // 8))
+    # spare buffers written by different chunks are disjoint
+    op_off, ops = csw[3], csw[4]
+    written = []
+    for c in range(len(coff) - 1):
+        w = {ops[i].parent_clv_index for i in range(op_off[coff[c]], op_off[coff[c + 1]])} - {case.root_clv}
+        assert all(lay["clv0"] + c * lay["extra"] <= x < lay["clv0"] + (c + 1) * lay["extra"] for x in w)
+        written.append(w)
+    assert all(written[i].isdisjoint(written[j]) for i in range(len(written)) for j in range(i))
+    got = np.empty(case.tree.root_count)
+    got[cpos] = o.sweep_root_placements(*csw, case.root_clv, case.root_scaler, mode=MODE_ENGINE)
+    assert same_bits(got[b:e], want[b:e])
