@@ -670,6 +670,8 @@ def _bind_model(L: C.CDLL):
     L.rdh_model_partition.argtypes = [vp, C.c_uint]
     L.rdh_model_partition.restype = vp
     L.rdh_model_set_checkpoint.argtypes = [vp, C.c_char_p]
+    L.rdh_model_assign_indicies.argtypes = [vp, C.c_int, C.c_uint, C.c_double, C.c_uint, C.c_uint, C.c_int, _up,
+                                            C.c_uint, _up]
     L._rdh_model_bound = True
 
 
@@ -1013,6 +1015,17 @@ class Model:
         """log search / exhaustive_search results to "<prefix>.ckp" (the reference's on-disk format);
         a file that already holds results makes the next run resume from it"""
         self._check(self.L.rdh_model_set_checkpoint(self.h, prefix.encode() if prefix is not None else None))
+
+    def assign_indicies(self, mode: str = "exhaustive", min_roots: int = 1, root_ratio: float = 0.0, rank: int = 0,
+                        num_tasks: int = 1, strategy: str = "modified_mad"):
+        """assign_indicies_by_rank_search / _exhaustive against the model's result log
+        (reference src/model.cpp:1899-1960): the root ids this rank still has to do"""
+        out = np.zeros(self.root_count, dtype=np.uint32)
+        got = C.c_uint()
+        self._check(self.L.rdh_model_assign_indicies(self.h, 0 if mode == "search" else 1, min_roots, root_ratio,
+                                                     rank, num_tasks, self.STRATEGY[strategy], _ptr(out, _up),
+                                                     len(out), C.byref(got)))
+        return out[:got.value].tolist()
 
     def lwr(self, llh) -> np.ndarray:
         llh = np.ascontiguousarray(llh, dtype=np.float64)

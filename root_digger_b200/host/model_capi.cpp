@@ -289,6 +289,30 @@ extern "C" int rdh_model_set_checkpoint(void *h, const char *prefix) {
   })
 }
 
+// Work assignment against the model's result log (reference src/model.cpp:1899-1960): the root
+// ids this rank still has to do.  mode 0: search (min_roots / root_ratio / init_strategy as in
+// rdh_model_search), mode 1: exhaustive.  The ids are copied to out (capacity cap).
+extern "C" int rdh_model_assign_indicies(void *h, int mode, unsigned min_roots, double root_ratio, unsigned rank,
+                                         unsigned num_tasks, int init_strategy, unsigned *out, unsigned cap,
+                                         unsigned *n_out) {
+  RDH_TRY({
+    auto &m = *H(h).model;
+    if (mode == 0) {
+      auto strat = init_strategy == 0   ? initial_root_strategy_t::random
+                   : init_strategy == 1 ? initial_root_strategy_t::midpoint
+                                        : initial_root_strategy_t::modified_mad;
+      m.assign_indicies_by_rank_search(min_roots, root_ratio, rank, num_tasks, strat, H(h).checkpoint);
+    } else {
+      m.assign_indicies_by_rank_exhaustive(rank, num_tasks, H(h).checkpoint);
+    }
+    auto idx = m.assigned_indicies();
+    if (idx.size() > cap) throw std::runtime_error("output buffer too small");
+    for (size_t i = 0; i < idx.size(); ++i) out[i] = (unsigned)idx[i];
+    *n_out = (unsigned)idx.size();
+    return 1;
+  })
+}
+
 // init_strategy: 0 random, 1 midpoint, 2 modified MAD
 extern "C" int rdh_model_search(void *h, unsigned min_roots, double root_ratio, double atol, double pgtol,
                                 double brtol, double factor, int init_strategy, unsigned rank,

@@ -299,3 +299,38 @@ def test_exhaustive_search_resumes_from_its_checkpoint(lib, tmp_path):
     third.set_checkpoint(p)
     ids3, _, _ = third.exhaustive_search(*tol)
     assert ids3.tolist() == ids2.tolist()
+
+
+@pytest.mark.parametrize("dummy", [0, 1, 2, 4, 8])
+def test_assign_indicies_against_the_checkpoint(lib, tmp_path, dummy):
+    """test/src/model.cpp:448-551: 10.fasta has 2n-3 = 17 rootings; with `dummy` finished roots in the
+    checkpoint file, the search assignment hands out max(k - dummy, 0) of k requested start roots (or
+    throws when the file holds more than were asked for) and the exhaustive assignment the 17 - dummy
+    remaining ones, never a finished one -- for every start-root strategy, and split over ranks"""
+    import fixtures
+    rng = np.random.default_rng(dummy)
+    done = rng.permutation(17)[:dummy].tolist()
+    p = new_prefix(tmp_path)
+    ckp = capi.Checkpoint(p, lib)
+    ckp.save_options()
+    for rid in done:
+        ckp.write(int(rid), 0.0, 0.0, [])
+    fx = fixtures.load("10.fasta")
+    tree = capi.RootedTree(path=str(fx["tree_path"]), lib=lib)
+    m = capi.Model(tree, fx["alignment"], rate_cats=1, compress=True, seed=99)
+    m.initialize_partitions(uniform_freqs=True)
+    m.set_checkpoint(p)
+    assert m.root_count == 17
+    for strategy in ("random", "midpoint", "modified_mad"):
+        for k in (1, 2, 3, 4, 5):
+            if k - dummy >= 0:
+                got = m.assign_indicies("search", min_roots=k, root_ratio=0.0, strategy=strategy)
+                assert len(got) == k - dummy and not set(got) & set(done) and len(set(got)) == len(got)
+            else:
+                with pytest.raises(RuntimeError):
+                    m.assign_indicies("search", min_roots=k, root_ratio=0.0, strategy=strategy)
+    got = m.assign_indicies("exhaustive")
+    assert sorted(got) == sorted(set(range(17)) - set(done))
+    # the same work split over 3 ranks (src/model.cpp:1899-1907): disjoint, complete, balanced
+    parts = [m.assign_indicies("exhaustive", rank=r, num_tasks=3) for r in range(3)]
+    assert sorted(sum(parts, [])) == sorted(got) and max(map(len, parts)) - min(map(len, parts)) <= 1
