@@ -89,6 +89,35 @@ def test_annotations_and_midpoint_on_10_tree():
         "(g:0.487400,(((i:0.569700,e:0.366600):0.602800,b:0.445900):0.099300,d:0.639600):0.825200):0.223050);")
 
 
+def test_annotations_survive_rerooting():
+    """test/src/tree.cpp:385-409 ("annotations, all roots") and :366-383 (the hidden "moving root"
+    case): annotate every branch -- while re-rooting on each, or from one fixed root -- then root on a
+    tip, unroot and print: the annotations stay with their branches"""
+    a = "[&&NHX:foo=bar:fizz=buzz]"
+    t = RootedTree(path=fixtures.FX / "10.tree")
+    for rid in range(t.root_count):
+        t.root_by(rid)
+        t.annotate_branch(rid, "foo", "bar")
+        t.annotate_branch(rid, "fizz", "buzz")
+    t.root_by(t.root_id("a"))
+    t.unroot()
+    assert t.newick() == (
+        f"(a:0.224900{a},((c:0.540900{a},f:0.422200{a}):0.785300{a},((g:0.487400{a},(((i:0.569700{a},"
+        f"e:0.366600{a}):0.602800{a},b:0.445900{a}):0.099300{a},d:0.639600{a}):0.825200{a}):0.446100{a},"
+        f"j:0.854700{a}):0.614100{a}):0.416200{a},h:0.983500{a});")
+    t = RootedTree(path=fixtures.FX / "10.tree")
+    t.root_by(0)
+    for rid in range(t.root_count):
+        t.annotate_branch(rid, "foo", "bar")
+        t.annotate_branch(rid, "fizz", "buzz")
+    t.root_by(t.root_id("b"))
+    t.unroot()
+    assert t.newick() == (
+        f"(b:0.445900{a},(d:0.639600{a},((j:0.854700{a},((h:0.983500{a},a:0.224900{a}):0.416200{a},"
+        f"(c:0.540900{a},f:0.422200{a}):0.785300{a}):0.614100{a}):0.446100{a},g:0.487400{a}):0.825200{a})"
+        f":0.099300{a},(i:0.569700{a},e:0.366600{a}):0.602800{a});")
+
+
 def test_sanity_check_trees():
     """test/src/tree.cpp:336-345"""
     assert not RootedTree(path=fixtures.FX / "sanity_check1.tree").sanity_check()
