@@ -118,6 +118,36 @@ def test_annotations_survive_rerooting():
         f":0.099300{a},(i:0.569700{a},e:0.366600{a}):0.602800{a});")
 
 
+@pytest.mark.parametrize("name", ["single", "10", "101"])
+def test_construction_copy_labels_and_operations_on_the_bundled_trees(name):
+    """test/src/tree.cpp:18-140, :214-223: every root location has a positive saved branch length, two
+    constructions agree root by root, a copy has the same shape, the label map covers the tips, every
+    root yields a non-empty schedule with positive branch lengths, and root_by / unroot cycles through
+    every root"""
+    path = fixtures.FX / (name + ".tree")
+    t1, t2 = RootedTree(path=path), RootedTree(path=path)
+    n = t1.tip_count
+    assert t1.root_count == 2 * n - 3 > 0 and t1.newick() == t2.newick()
+    for rid in range(t1.root_count):
+        a, b = t1.root_info(rid), t2.root_info(rid)
+        assert a[0] > 0.0 and a == b
+    c = t1.copy()
+    assert (c.tip_count, c.inner_count, c.branch_count, c.root_count) == (
+        t1.tip_count, t1.inner_count, t1.branch_count, t1.root_count)
+    assert sorted(t1.tip_index(t1.tip_label(i)) for i in range(n)) == list(range(n))
+    for rid in range(t1.root_count):
+        ops, pm, br = t1.generate_operations(rid, 0.5)
+        assert len(ops) == n - 1 and len(pm) == len(br) == 2 * n - 2 and (br > 0.0).all()
+    for rid in range(t1.root_count):
+        t1.root_by(rid)
+        assert t1.rooted
+        t1.unroot()
+        assert not t1.rooted
+    assert c.newick() == t2.newick()
+    with pytest.raises(Exception):
+        RootedTree(path="not_a_tree_file")
+
+
 def test_sanity_check_trees():
     """test/src/tree.cpp:336-345"""
     assert not RootedTree(path=fixtures.FX / "sanity_check1.tree").sanity_check()
