@@ -670,6 +670,8 @@ def _bind_model(L: C.CDLL):
     L.rdh_model_partition.argtypes = [vp, C.c_uint]
     L.rdh_model_partition.restype = vp
     L.rdh_model_set_checkpoint.argtypes = [vp, C.c_char_p]
+    L.rdh_model_last_partition_lh.argtypes = [vp, _dp, C.c_uint]
+    L.rdh_model_last_sweep_partition_lh.argtypes = [vp, C.c_uint, _dp, C.c_uint]
     L.rdh_model_assign_indicies.argtypes = [vp, C.c_int, C.c_uint, C.c_double, C.c_uint, C.c_uint, C.c_int, _up,
                                             C.c_uint, _up]
     L._rdh_model_bound = True
@@ -1015,6 +1017,22 @@ class Model:
         """log search / exhaustive_search results to "<prefix>.ckp" (the reference's on-disk format);
         a file that already holds results makes the next run resume from it"""
         self._check(self.L.rdh_model_set_checkpoint(self.h, prefix.encode() if prefix is not None else None))
+
+    def last_partition_lh(self) -> np.ndarray:
+        """the per-partition terms of the last compute_lh / compute_lh_root, in partition order"""
+        out = np.zeros(self.partition_count)
+        self._check(self.L.rdh_model_last_partition_lh(self.h, _ptr(out, _dp), len(out)))
+        return out
+
+    def last_sweep_partition_lh(self, placements: int | None = None) -> np.ndarray:
+        """[partition][placement] terms of the last sweep_root_lh"""
+        n = self.root_count if placements is None else placements
+        out = np.zeros((self.partition_count, n))
+        for p in range(self.partition_count):
+            row = np.zeros(n)
+            self._check(self.L.rdh_model_last_sweep_partition_lh(self.h, p, _ptr(row, _dp), n))
+            out[p] = row
+        return out
 
     def assign_indicies(self, mode: str = "exhaustive", min_roots: int = 1, root_ratio: float = 0.0, rank: int = 0,
                         num_tasks: int = 1, strategy: str = "modified_mad"):

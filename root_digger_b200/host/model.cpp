@@ -287,6 +287,7 @@ double model_t::compute_lh(const root_location_t &root_location) {
   }
   double lh = 0.0;
   for (double v : part_lh) lh += v;
+  _last_part_lh = part_lh;
   return lh;
 }
 
@@ -314,6 +315,7 @@ double model_t::compute_lh_root(const root_location_t &root) {
   if (failed) throw std::runtime_error(engine_error());
   double lh = 0.0;
   for (double v : part_lh) lh += v;
+  _last_part_lh = part_lh;
   if (std::isnan(lh)) throw std::runtime_error("lh at root is not a number: " + std::to_string(lh));
   return lh;
 }
@@ -536,11 +538,13 @@ std::vector<double> model_t::sweep_root_lh(size_t begin, size_t end) {
   const std::vector<root_location_t> roots(all_roots.begin() + (std::ptrdiff_t)begin,
                                            all_roots.begin() + (std::ptrdiff_t)end);
   std::vector<double> lh(roots.size(), 0.0);
+  _last_sweep_part_lh.assign(_partitions.size(), std::vector<double>(roots.size(), 0.0));
   if (roots.empty()) return lh;
   if (_sweep_mode == sweep_mode_t::sequential) {
     for (size_t r = 0; r < roots.size(); ++r) {
       move_root(roots[r]);
       lh[r] = compute_lh_root(roots[r]);
+      for (size_t i = 0; i < _partitions.size(); ++i) _last_sweep_part_lh[i][r] = _last_part_lh[i];
     }
     return lh;
   }
@@ -576,7 +580,10 @@ std::vector<double> model_t::sweep_root_lh(size_t begin, size_t end) {
                                                 sw.ops.data(), _tree.root_clv_index(), _tree.root_scaler_index(),
                                                 RDK_SWEEP_KEEP_ROOT, chunks, chunk_off.data(), part.data());
       if (rc == RDK_FAILURE) throw std::runtime_error(engine_error());
-      for (size_t q = 0; q < part.size(); ++q) lh[sw.root_pos[q] - begin] += part[q];
+      for (size_t q = 0; q < part.size(); ++q) {
+        lh[sw.root_pos[q] - begin] += part[q];
+        _last_sweep_part_lh[i][sw.root_pos[q] - begin] = part[q];
+      }
     }
     for (double v : lh)
       if (std::isnan(v)) throw std::runtime_error("lh at root is not a number: " + std::to_string(v));
@@ -604,7 +611,10 @@ std::vector<double> model_t::sweep_root_lh(size_t begin, size_t end) {
                                        op_off.data(), ops.data(), _tree.root_clv_index(),
                                        _tree.root_scaler_index(), part.data());
     if (rc == RDK_FAILURE) throw std::runtime_error(engine_error());
-    for (size_t r = 0; r < roots.size(); ++r) lh[r] += part[r];
+    for (size_t r = 0; r < roots.size(); ++r) {
+      lh[r] += part[r];
+      _last_sweep_part_lh[i][r] = part[r];
+    }
   }
   for (double v : lh)
     if (std::isnan(v)) throw std::runtime_error("lh at root is not a number: " + std::to_string(v));

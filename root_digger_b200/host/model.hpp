@@ -109,6 +109,14 @@ public:
   void assign_indicies_by_rank_exhaustive(size_t rank, size_t num_tasks, checkpoint_t &);
   std::vector<size_t> assigned_indicies() const { return _assigned_idx; }
 
+  // ---- B200-first addition: the per-partition terms of the last evaluation ------------------
+  // compute_lh / compute_lh_root add the partitions' log-likelihoods in partition order; a run
+  // that gives every GPU its own partitions (BASELINE cfg4) needs the TERMS to
+  // rebuild that same ordered sum across ranks (root_digger_b200.sharding.PartitionShardedModel).
+  const std::vector<double> &last_partition_lh() const { return _last_part_lh; }
+  // ... and of the last sweep_root_lh: [partition][placement of the swept range]
+  const std::vector<std::vector<double>> &last_sweep_partition_lh() const { return _last_sweep_part_lh; }
+
   void move_root(const root_location_t &new_root);
   // use the fused engine entry points (rdk_sweep_root_placements) where the
   // reference loops over move_root + compute_lh_root; results are identical
@@ -188,6 +196,8 @@ private:
   uint64_t                               _seed;
   bool                                   _early_stop;
   sweep_mode_t                           _sweep_mode = sweep_mode_t::directed;
+  std::vector<double>                    _last_part_lh;
+  std::vector<std::vector<double>>       _last_sweep_part_lh;
   unsigned int                           _sweep_extra = 0;   // spare directed-CLV buffers per sweep chunk
   unsigned int                           _sweep_chunks = 1;  // independent chunks of a directed sweep
   static constexpr unsigned int          _submodels = 1;

@@ -265,6 +265,25 @@ extern "C" int rdh_model_sweep_root_lh_range(void *h, unsigned begin, unsigned e
     return 1;
   })
 }
+// per-partition terms of the last compute_lh / compute_lh_root (out: partition_count doubles) and of
+// the last sweep (part: the partition; out: one double per placement of the swept range)
+extern "C" int rdh_model_last_partition_lh(void *h, double *out, unsigned cap) {
+  RDH_TRY({
+    const auto &v = H(h).model->last_partition_lh();
+    if (v.size() > cap) throw std::runtime_error("output buffer too small");
+    for (size_t i = 0; i < v.size(); ++i) out[i] = v[i];
+    return 1;
+  })
+}
+extern "C" int rdh_model_last_sweep_partition_lh(void *h, unsigned part, double *out, unsigned cap) {
+  RDH_TRY({
+    const auto &m = H(h).model->last_sweep_partition_lh();
+    if (part >= m.size()) throw std::runtime_error("no such partition in the last sweep");
+    if (m[part].size() > cap) throw std::runtime_error("output buffer too small");
+    for (size_t i = 0; i < m[part].size(); ++i) out[i] = m[part][i];
+    return 1;
+  })
+}
 extern "C" int rdh_model_compute_all_root_lh(void *h, double *out) {
   RDH_TRY({
     auto v = H(h).model->compute_all_root_lh();

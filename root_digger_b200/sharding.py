@@ -77,3 +77,61 @@ def plan_grid(nranks: int, n_taxa: int, sites: int, rate_cats: int = 4, budget_b
         if replica_bytes(n_taxa, shard_sites, rate_cats) <= budget_bytes:
             return gs, nranks // gs
     return nranks, 1
+
+
+class PartitionShardedModel:
+    """BASELINE cfg4: the partitions of a multi-partition alignment are dealt out to
+    the ranks (`plan_partition_shards`: partition p lives on rank p % nranks); every rank holds a
+    `capi.Model` of ITS partitions only.  Per-partition parameter optimisation needs no
+    communication at all (the reference's BFGS closures are per partition, src/model.cpp:1544-1547);
+    `compute_lh` / `compute_lh_root` / `sweep_root_lh` need the SUM over all partitions
+    (src/model.cpp:397,429): one all-gather of the per-partition terms per call, after which every
+    rank adds them in global partition order -- the order a single process uses -- so the result
+    has the same bits on 1, 2 or 8 ranks.
+
+    `dist` is torch.distributed (initialised; nccl with `device="cuda"` or gloo with "cpu")."""
+
+    def __init__(self, local_model, n_partitions: int, rank: int, nranks: int, dist, device="cpu"):
+        self.m, self.P, self.rank, self.nranks, self.dist, self.device = local_model, n_partitions, rank, nranks, dist, device
+        self.owned = plan_partition_shards(n_partitions, nranks)
+        if local_model.partition_count != len(self.owned[rank]):
+            raise ValueError("the local model must hold exactly this rank's partitions")
+        self.slots = max(len(o) for o in self.owned)
+
+    def _gather_terms(self, local):
+        """local: [local partitions][n] -> [all partitions][n], every rank"""
+        import numpy as np
+        import torch
+        local = np.atleast_2d(np.asarray(local, dtype=np.float64))
+        n = local.shape[1]
+        buf = torch.zeros((self.slots, n), dtype=torch.float64, device=self.device)
+        buf[:local.shape[0]] = torch.from_numpy(local).to(self.device)
+        out = torch.zeros((self.nranks, self.slots, n), dtype=torch.float64, device=self.device)
+        self.dist.all_gather_into_tensor(out.view(-1), buf.view(-1)) if self.device != "cpu" else \
+            self.dist.all_gather(list(out.unbind(0)), buf)
+        allv = out.cpu().numpy()
+        terms = np.zeros((self.P, n))
+        for r, parts in enumerate(self.owned):
+            for j, p in enumerate(parts):
+                terms[p] = allv[r, j]
+        return terms
+
+    @staticmethod
+    def _ordered_sum(terms):
+        import numpy as np
+        total = np.zeros(terms.shape[1])
+        for p in range(terms.shape[0]):  # left to right over partitions, like model_t::compute_lh
+            total = total + terms[p]
+        return total
+
+    def compute_lh(self, rid: int, ratio: float = 0.5) -> float:
+        self.m.compute_lh(rid, ratio)
+        return float(self._ordered_sum(self._gather_terms(self.m.last_partition_lh()[:, None]))[0])
+
+    def compute_lh_root(self, rid: int, ratio: float = 0.5) -> float:
+        self.m.compute_lh_root(rid, ratio)
+        return float(self._ordered_sum(self._gather_terms(self.m.last_partition_lh()[:, None]))[0])
+
+    def sweep_root_lh(self):
+        self.m.sweep_root_lh()
+        return self._ordered_sum(self._gather_terms(self.m.last_sweep_partition_lh()))

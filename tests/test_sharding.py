@@ -106,3 +106,72 @@ def test_two_rank_gloo_site_sharding_matches_single_shard(S):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert got.hex() == want.hex()   # bit-identical whatever the number of shards
+
+
+def _partition_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, str(ROOT))
+    sys.path.insert(0, str(ROOT / "tests"))
+    import torch.distributed as dist
+    import fixtures
+    import oracle_capi
+    from root_digger_b200 import _build, capi
+    oracle_capi.load_oracle().rdo_set_default_mode(oracle_capi.MODE_ENGINE)
+    lib = capi.load_tree_lib(_build.build_host_on_oracle())
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    fx = fixtures.load("10.fasta")
+    mine = [PARTS[p] for p in sharding.plan_partition_shards(len(PARTS), world)[rank]]
+    tree = capi.RootedTree(path=str(fx["tree_path"]), lib=lib)
+    m = capi.Model(tree, fx["alignment"], rate_cats=4, compress=True, seed=3, partitions=mine)
+    m.initialize_partitions(uniform_freqs=False)
+    for j, p in enumerate(sharding.plan_partition_shards(len(PARTS), world)[rank]):
+        m.set_params(rates=_rates_of(p), alpha=0.5 + p, part=j)
+    sm = sharding.PartitionShardedModel(m, len(PARTS), rank, world, dist)
+    out = [sm.compute_lh(3, 0.4), sm.compute_lh_root(3, 0.7)] + sm.sweep_root_lh().tolist()
+    if rank == 0:
+        q.put(np.array(out))
+    dist.destroy_process_group()
+
+
+PARTS = [(0, 300), (300, 520), (520, 1000)]
+
+
+def _rates_of(p):
+    """independent substitution rates per (global) partition; the initial rates of model_t are drawn
+    from the model's RNG in local partition order (quirk B-10), so the comparison sets them"""
+    base = np.array([.34, .42, .24, .74, .16, .88, .75, .54, .20, .06, .08, .41])
+    return np.roll(base, p) * (1.0 + 0.1 * p)
+
+
+def test_two_rank_gloo_partition_sharding_matches_single_process():
+    """BASELINE cfg4 in miniature: 3 partitions dealt out to 2 ranks (p % 2), independent parameters
+    per partition; compute_lh / compute_lh_root / the placement sweep equal the single-process
+    3-partition model bit for bit (terms all-gathered, added in partition order)"""
+    import torch.multiprocessing as mp
+    import fixtures
+    import oracle_capi
+    from root_digger_b200 import _build, capi
+    oracle_capi.load_oracle().rdo_set_default_mode(oracle_capi.MODE_ENGINE)
+    lib = capi.load_tree_lib(_build.build_host_on_oracle())
+    fx = fixtures.load("10.fasta")
+    tree = capi.RootedTree(path=str(fx["tree_path"]), lib=lib)
+    m = capi.Model(tree, fx["alignment"], rate_cats=4, compress=True, seed=3, partitions=PARTS)
+    m.initialize_partitions(uniform_freqs=False)
+    for p in range(len(PARTS)):
+        m.set_params(rates=_rates_of(p), alpha=0.5 + p, part=p)
+    want = np.array([m.compute_lh(3, 0.4), m.compute_lh_root(3, 0.7)] + m.sweep_root_lh().tolist())
+    terms = m.last_sweep_partition_lh()
+    assert terms.shape == (3, m.root_count) and np.array_equal((terms[0] + terms[1]) + terms[2], want[2:])
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_partition_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert np.array_equal(got.view(np.uint64), want.view(np.uint64))
