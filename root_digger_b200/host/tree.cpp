@@ -109,6 +109,7 @@ private:
 
 unode_t *new_unode(utree_t &t) {
   t.arena.emplace_back();
+  t.arena.back().uid = (unsigned int)t.arena.size() - 1;
   return &t.arena.back();
 }
 
@@ -556,8 +557,10 @@ void rooted_tree_t::add_root_space() {
   unsigned total_unodes = _tree->inner_count * 3 + _tree->tip_count;
   _tree->arena.emplace_back();
   _root_left = &_tree->arena.back();
+  _root_left->uid = (unsigned int)_tree->arena.size() - 1;
   _tree->arena.emplace_back();
   _root_right = &_tree->arena.back();
+  _root_right->uid = (unsigned int)_tree->arena.size() - 1;
   _root_left->next = _root_right;
   _root_right->next = _root_left;
   _root_left->clv_index = _root_right->clv_index = new_size;
@@ -792,29 +795,34 @@ rooted_tree_t::sweep_schedule_t rooted_tree_t::generate_sweep_operations(size_t 
   const unsigned int ML = pm0, MR = pm0 + 1, MC = pm0 + 2;
   const double       L0 = _current_rl.saved_brlen;
 
-  // position in roots() of the edge behind each unode (both end points)
-  std::unordered_map<const unode_t *, size_t> pos_of;
+  // position in roots() of the edge behind each unode (both end points), keyed by unode uid
+  const size_t        n_unodes = _tree->arena.size();
+  std::vector<size_t> pos_of(n_unodes, (size_t)-1);
   for (size_t i = 0; i < _roots.size(); ++i) {
     const unode_t *a = _roots[i].edge;
     const unode_t *b = a == lchild ? rchild : (a == rchild ? lchild : a->back);
-    pos_of[a] = i;
-    pos_of[b] = i;
+    pos_of[a->uid] = i;
+    pos_of[b->uid] = i;
   }
   auto requested = [&](const unode_t *c) {
-    size_t i = pos_of.at(c);
+    size_t i = pos_of[c->uid];
     return i >= begin && i < end;
   };
   // does the subtree below c, the edge above c included, hold a requested placement?
-  std::unordered_map<const unode_t *, bool>  needed;
-  std::function<bool(const unode_t *)> mark = [&](const unode_t *c) {
-    bool need = requested(c);
-    if (c->next) {
-      bool a = mark(c->next->back), b = mark(c->next->next->back);
-      need = need || a || b;
+  std::vector<char> needed(n_unodes, 0);
+  struct marker_t {
+    const decltype(requested) &req;
+    std::vector<char>         &needed;
+    bool operator()(const unode_t *c) const {
+      bool need = req(c);
+      if (c->next) {
+        bool a = (*this)(c->next->back), b = (*this)(c->next->next->back);
+        need = need || a || b;
+      }
+      needed[c->uid] = need ? 1 : 0;
+      return need;
     }
-    needed[c] = need;
-    return need;
-  };
+  } mark{requested, needed};
   mark(lchild);
   mark(rchild);
 
@@ -832,7 +840,7 @@ rooted_tree_t::sweep_schedule_t rooted_tree_t::generate_sweep_operations(size_t 
   // close a placement: the two root half-branches and the root operation; child1 is the
   // end point root_by would make the left child (src/tree.cpp:273-320)
   auto emit_placement = [&](const unode_t *c, ref_t below, ref_t above) {
-    const size_t           i = pos_of.at(c);
+    const size_t           i = pos_of[c->uid];
     const root_location_t &rl = _roots[i];
     out.mi.push_back(ML);
     out.bl.push_back(rl.brlen());
@@ -866,7 +874,7 @@ rooted_tree_t::sweep_schedule_t rooted_tree_t::generate_sweep_operations(size_t 
     const unode_t *k[2] = {c->next->back, c->next->next->back};
     for (int i = 0; i < 2; ++i) {
       const unode_t *child = k[i], *sib = k[1 - i];
-      if (!needed.at(child)) continue;
+      if (!needed[child->uid]) continue;
       if (depth >= extra)
         throw std::runtime_error("generate_sweep_operations: the sweep needs more directed-CLV buffers "
                                  "than were set aside (sweep_depth_bound)");

@@ -40,6 +40,7 @@ struct unode_t {
   unsigned int pmatrix_index = 0;
   unsigned int node_index = 0;
   int          mark = 0;          // traversal tag (the reference uses ->data)
+  unsigned int uid = 0;           // position in utree_t::arena (dense key for per-unode tables)
   std::string  annotation;        // NHX text appended on export
 };
 
