@@ -142,6 +142,60 @@ def test_oracle_against_independent_numpy_restatement(n, S, K, data):
         assert o.get_scaler(c.root_scaler).max() >= 1  # underflow rescaling exercised
 
 
+@pytest.mark.parametrize("n,S,K,data", [(6, 24, 4, "evolved"), (9, 16, 2, "ambiguous"), (40, 8, 4, "iid")])
+def test_oracle_against_exact_arithmetic(n, S, K, data):
+    """the whole chain -- rate matrix, matrix exponential, pruning over the schedule, weighted root
+    log-likelihood -- re-evaluated in 60-digit arithmetic (mpmath; no rescaling needed there): the
+    oracle's fp64 result, in both arithmetic modes, is within 1e-12 relative of the exact value, i.e.
+    three orders inside the north-star tolerance"""
+    mp = pytest.importorskip("mpmath")
+    mp.mp.dps = 60
+    c = Case(n, S, K, seed=17, data=data, weights="random")
+    o = OraclePartition(n, S, K)
+    c.setup(o)
+    sched = c.full_schedule(2 % c.tree.root_count, 0.35)
+    l_ref, ps = compute_lh(o, sched, c.root_clv, c.root_scaler, persite=True, mode=MODE_REFERENCE)
+    l_eng = o.root_loglikelihood(c.root_clv, c.root_scaler, mode=MODE_ENGINE)
+    ops, pm, br = sched
+    r, f = [mp.mpf(float(x)) for x in c.rates], [mp.mpf(float(x)) for x in c.freqs]
+    Q = mp.zeros(4, 4)
+    k = 0
+    for i in range(4):
+        for j in range(4):
+            if i != j:
+                Q[i, j] = r[k] * f[j]
+                k += 1
+    for i in range(4):
+        Q[i, i] = -sum(Q[i, j] for j in range(4) if j != i)
+    mu = -sum(f[i] * Q[i, i] for i in range(4))
+    Q = Q / mu
+    P = {int(i): [mp.expm(Q * (mp.mpf(float(cr)) * mp.mpf(float(t)))) for cr in c.cat_rates] for i, t in zip(pm, br)}
+    clv = {}
+    for label, seq in c.aln.items():
+        m = [np_oracle.NT[chr(ch).upper()] for ch in seq]
+        clv[c.tree.tip_index(label)] = [[[mp.mpf((mm >> i) & 1) for i in range(4)] for _ in range(K)] for mm in m]
+    for op in ops:
+        p, _, c1, m1, _, c2, m2, _ = op.astuple()
+        out = []
+        for s in range(S):
+            row = []
+            for kk in range(K):
+                x = [sum(P[m1][kk][i, j] * clv[c1][s][kk][j] for j in range(4)) for i in range(4)]
+                y = [sum(P[m2][kk][i, j] * clv[c2][s][kk][j] for j in range(4)) for i in range(4)]
+                row.append([x[i] * y[i] for i in range(4)])
+            out.append(row)
+        clv[p] = out
+    persite = []
+    for s in range(S):
+        term = sum(mp.mpf(float(c.cat_weights[kk])) * sum(f[i] * clv[c.root_clv][s][kk][i] for i in range(4))
+                   for kk in range(K))
+        persite.append(mp.log(term) * int(c.weights[s]))
+    exact = sum(persite)
+    assert abs(mp.mpf(l_ref) - exact) <= mp.mpf("1e-12") * abs(exact)
+    assert abs(mp.mpf(l_eng) - exact) <= mp.mpf("1e-12") * abs(exact)
+    assert max(abs(mp.mpf(float(a)) - b) / abs(b) for a, b in zip(ps, persite) if b != 0) <= mp.mpf("1e-12")
+
+
 def test_golden_fixture_loglikelihoods():
     """the reference's bundled fixtures (test/data): the oracle reproduces the committed vectors bit for bit"""
     for key, rec in GOLDEN["fixtures"].items():
