@@ -67,6 +67,9 @@ def parse_args():
     ap.add_argument("--seed", type=int, default=0x5EED0002)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--exhaustive-branches", type=int, default=0,
+                    help="also time exhaustive mode (one placement = one fully optimised branch, SURVEY 8d) on "
+                         "this many branches of the e2e model (0 = skip; each branch is thousands of evaluations)")
     ap.add_argument("--launch-config", default="", help="ctas_per_sm,threads,elems (0 = engine default)")
     ap.add_argument("--tail-mode", type=int, default=0, help="0 engine rule, 1 always skip idle slots, 2 never")
     ap.add_argument("--sweep", default="directed", choices=["directed", "path"],
@@ -491,6 +494,8 @@ def run_ours(args):
                       "programs H2D, log-likelihoods D2H; alignment resident as in the reference partition"
                       + ("; + all-gather of the placement log-likelihoods)" if G_r > 1 else ")"),
                "logl_root0": a, "matches_device_arm": bool(a == lh0 and np.array_equal(b, sweep_lh))}
+        if args.exhaustive_branches > 0 and world == 1:
+            e2e["exhaustive"] = exhaustive_sample(m, args.exhaustive_branches, stats=mstats)
         m.close()
     clocks = sampler.stop() if sampler else None
 
@@ -521,6 +526,26 @@ def run_ours(args):
     g.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def exhaustive_sample(m, branches: int, tol=(1e-7, 1e-7, 1e-12, 1e4), stats=None):
+    """exhaustive mode (reference src/model.cpp:1140-1235) on a bounded sample: the first `branches`
+    root ids, each optimised to convergence (BFGS over rates / frequencies / Gamma shape + Brent on the
+    root position), timed by wall clock.  stats: optional callable returning the engine's counters
+    (program launches = evaluations).  Returns branches/s and evaluations/s."""
+    branches = max(1, min(int(branches), m.root_count))
+    num_tasks = max(1, -(-m.root_count // branches))  # rank 0 of that many tasks gets <= `branches` ids
+    s0 = stats() if stats else None
+    t0 = time.perf_counter()
+    ids, llh, alpha = m.exhaustive_search(*tol, rank=0, num_tasks=num_tasks)
+    dt = time.perf_counter() - t0
+    out = {"branches": int(len(ids)), "seconds": dt, "branches_per_sec": len(ids) / dt if dt > 0 else None,
+           "best_branch": int(ids[int(np.argmax(llh))]), "best_llh": float(np.max(llh))}
+    if s0 is not None:
+        s1 = stats()
+        ev = s1["program_launches"] - s0["program_launches"]
+        out.update(evaluations=int(ev), evaluations_per_sec=ev / dt if dt > 0 else None)
+    return out
 
 
 def dram_traffic_from_profiles():

@@ -168,3 +168,18 @@ def test_exhaustive_search_runs(lib):
     assert sorted(ids.tolist()) == list(range(17)) and np.isfinite(llh).all()
     assert ((alpha >= 0) & (alpha <= 1)).all()
     assert "LWR=" in m.newick()
+
+
+def test_bench_exhaustive_sample_helper(lib):
+    """bench.py --exhaustive-branches: the bounded exhaustive-mode sample on the oracle
+    backend -- the requested number of branches is optimised, nothing else"""
+    import importlib.util
+    from pathlib import Path
+    spec = importlib.util.spec_from_file_location("bench", Path(__file__).resolve().parent.parent / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    m = make_model(lib, uniform=False)
+    m.compute_lh(0)
+    out = bench.exhaustive_sample(m, 2, tol=(1e-2, 1e-2, 1e-2, 1e13))
+    assert 1 <= out["branches"] <= 2 and out["branches_per_sec"] > 0 and math.isfinite(out["best_llh"])
+    assert out["best_branch"] in (0, 1)
