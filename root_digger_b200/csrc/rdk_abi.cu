@@ -1169,6 +1169,11 @@ extern "C" int rdk_sweep_root_placements_chunks(rdk_partition_t *p, unsigned int
   // batches bounded by the spare P-matrix slots and the partial-sum buffer
   const size_t   stride = std::max(1u, (e->S * e->K + 31) / 32);
   const unsigned max_slots = (unsigned)std::max<size_t>(1, std::min<size_t>(4096, (size_t(256) << 20) / (stride * 8)));
+  // whatever way this call ends, the chunk table does not outlive it
+  struct chunk_table_guard {
+    Engine *e;
+    ~chunk_table_guard() { e->pend_chunk_off.clear(); }
+  } chunk_guard{e};
   // the chunks run side by side only when nothing they share is written (the root CLV is:
   // RDK_SWEEP_KEEP_ROOT must be set) and the whole sweep is one launch; otherwise they run
   // in order, which the contract always allows
