@@ -1010,16 +1010,24 @@ std::vector<double> rooted_tree_t::get_backward_children_distance(unode_t *rl) c
 std::vector<std::pair<root_location_t, double>> rooted_tree_t::apply_foreach_branch_map_reduce(
     const std::function<double(double, double, double)>      &map_func,
     const std::function<double(const std::vector<double> &)> &reduce_func) const {
-  std::vector<std::pair<root_location_t, double>> ret;
-  for (const auto &rl : _roots) {
+  // O(tips^2) pairs per branch (the reference's algorithm, src/tree.cpp:826-861): the branches are
+  // independent and each keeps its own term order, so they are scored in parallel with the same
+  // bits as the serial loop
+  std::vector<double> score(_roots.size(), 0.0);
+#pragma omp parallel for schedule(dynamic, 4)
+  for (size_t r = 0; r < _roots.size(); ++r) {
+    const auto         &rl = _roots[r];
     auto                fwd = get_forward_children_distance(rl.edge);
     auto                bwd = get_backward_children_distance(rl.edge);
     std::vector<double> vals;
     vals.reserve(fwd.size() * bwd.size());
     for (double f : fwd)
       for (double b : bwd) vals.push_back(map_func(f, b, rl.saved_brlen));
-    ret.emplace_back(rl, reduce_func(vals));
+    score[r] = reduce_func(vals);
   }
+  std::vector<std::pair<root_location_t, double>> ret;
+  ret.reserve(_roots.size());
+  for (size_t r = 0; r < _roots.size(); ++r) ret.emplace_back(_roots[r], score[r]);
   return ret;
 }
 
