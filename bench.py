@@ -324,7 +324,9 @@ def run_ours(args):
 
     # reference buffer counts + the spare buffers of the directed sweep, once per independent chunk of
     # placements (a small shard fills the device only when several chunks are walked side by side)
-    n_chunks = args.chunks if args.chunks > 0 else capi.sweep_chunk_hint(cnt, K)
+    # (site-sharded: the all-reduce adds the ranks' values slot by slot, so every rank must cut the
+    # sweep the same way -- the count comes from the LARGEST shard, not from this rank's own)
+    n_chunks = args.chunks if args.chunks > 0 else capi.sweep_chunk_hint(max(c for _, c in plan_site_shards(S, G_s)), K)
     lay = case.tree.sweep_layout(n_chunks)
     g = Partition(n, cnt, K, device=local, clv_buffers=lay["clv_buffers"], scale_buffers=lay["scale_buffers"],
                   prob_matrices=lay["prob_matrices"])
@@ -521,6 +523,10 @@ def run_ours(args):
             "roofline": roofline, "full_evaluation": full_eval, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(agg[1].item()), "clocks": clocks,
             "logl_root0": lh0, "best_placement": int(np.argmax(sweep_lh)),
+            # the sweep scores root 0 at ratio 0.5 too: same bits as the full evaluation (the reference's
+            # compute_lh == compute_lh_root invariant) -- also a cross-rank check that every shard walked
+            # the placements in the same order
+            "sweep_root0_equals_full_evaluation": bool(sweep_lh[0] == lh0),
         }
         print(json.dumps(line), flush=True)
     g.close()

@@ -246,7 +246,11 @@ int rdk_sweep_root_placements_ex(rdk_partition_t *partition,
  * warps in one launch -- which is what fills the device when the shard is small (a
  * 12.5k-site shard has one warp iteration per warp: one long latency-bound chain);
  * otherwise it runs them in order.  Results are those of rdk_sweep_root_placements_ex
- * on the same arrays, bit for bit. */
+ * on the same arrays, bit for bit.
+ * Site-sharded partitions (rdk_partition_attach_comm): the ranks' values are added
+ * slot by slot, so -- as for every sweep call -- all ranks must pass the SAME
+ * placements in the SAME order: derive the chunk count from the layout (the largest
+ * shard), not from the local site count (model_t and bench.py do). */
 int rdk_sweep_root_placements_chunks(rdk_partition_t *partition,
                                      unsigned int placements,
                                      const unsigned int *params_indices,

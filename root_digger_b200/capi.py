@@ -670,6 +670,8 @@ def _bind_model(L: C.CDLL):
     L.rdh_model_partition.argtypes = [vp, C.c_uint]
     L.rdh_model_partition.restype = vp
     L.rdh_model_set_checkpoint.argtypes = [vp, C.c_char_p]
+    L.rdh_model_sweep_chunks.argtypes = [vp]
+    L.rdh_model_sweep_chunks.restype = C.c_uint
     L.rdh_model_last_partition_lh.argtypes = [vp, _dp, C.c_uint]
     L.rdh_model_last_sweep_partition_lh.argtypes = [vp, C.c_uint, _dp, C.c_uint]
     L.rdh_model_assign_indicies.argtypes = [vp, C.c_int, C.c_uint, C.c_double, C.c_uint, C.c_uint, C.c_int, _up,
@@ -1017,6 +1019,11 @@ class Model:
         """log search / exhaustive_search results to "<prefix>.ckp" (the reference's on-disk format);
         a file that already holds results makes the next run resume from it"""
         self._check(self.L.rdh_model_set_checkpoint(self.h, prefix.encode() if prefix is not None else None))
+
+    @property
+    def sweep_chunks(self) -> int:
+        """independent chunks the directed sweep is cut into (the same on every rank of a site-sharded run)"""
+        return int(self.L.rdh_model_sweep_chunks(self.h))
 
     def last_partition_lh(self) -> np.ndarray:
         """the per-partition terms of the last compute_lh / compute_lh_root, in partition order"""

@@ -65,9 +65,20 @@ model_t::model_t(rooted_tree_t tree, const std::vector<msa_t> &msas,
     _sweep_extra = _tree.sweep_depth_bound();
     if (pi == 0) {
       _sweep_chunks = 1;
-      for (size_t q = 0; q < msas.size(); ++q)
-        _sweep_chunks = std::max(_sweep_chunks, rdk_sweep_chunk_hint((unsigned int)msas[q].length(),
+      for (size_t q = 0; q < msas.size(); ++q) {
+        // Site-sharded: the all-reduce adds the ranks' log-likelihoods slot by slot, so EVERY rank
+        // must walk the placements in the same order, i.e. cut the sweep into the same chunks --
+        // the count comes from the largest shard of the layout (a function of the global site
+        // count and the number of ranks only), never from this rank's own site count.
+        unsigned long long sites = msas[q].length();
+        if (shard.global_sites && shard.nranks > 1) {
+          const unsigned long long blocks = (shard.global_sites + RDK_SHARD_ALIGN - 1) / RDK_SHARD_ALIGN;
+          const unsigned long long per = (blocks + (unsigned long long)shard.nranks - 1) / (unsigned long long)shard.nranks;
+          sites = std::min<unsigned long long>(per * RDK_SHARD_ALIGN, shard.global_sites);
+        }
+        _sweep_chunks = std::max(_sweep_chunks, rdk_sweep_chunk_hint((unsigned int)sites,
                                                                      (unsigned int)_rate_rates[q].size()));
+      }
       _sweep_chunks = std::min<unsigned int>(_sweep_chunks, RDK_SWEEP_MAX_CHUNKS);
     }
     rdk_partition_t *p = rdk_partition_create(

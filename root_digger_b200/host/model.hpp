@@ -113,6 +113,7 @@ public:
   // compute_lh / compute_lh_root add the partitions' log-likelihoods in partition order; a run
   // that gives every GPU its own partitions (BASELINE cfg4) needs the TERMS to
   // rebuild that same ordered sum across ranks (root_digger_b200.sharding.PartitionShardedModel).
+  unsigned int sweep_chunks() const { return _sweep_chunks; }  // independent chunks of a directed sweep
   const std::vector<double> &last_partition_lh() const { return _last_part_lh; }
   // ... and of the last sweep_root_lh: [partition][placement of the swept range]
   const std::vector<std::vector<double>> &last_sweep_partition_lh() const { return _last_sweep_part_lh; }

@@ -175,3 +175,31 @@ def test_two_rank_gloo_partition_sharding_matches_single_process():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert np.array_equal(got.view(np.uint64), want.view(np.uint64))
+
+
+def test_sweep_chunk_count_is_agreed_across_site_shards():
+    """site-sharded runs add the ranks' sweep values slot by slot: every rank must cut the directed
+    sweep into the same chunks.  The count therefore comes from the largest shard of the layout, not
+    from the local site count -- here the two ranks hold 4096 and 3904 patterns of 8000, and the
+    (test) hint would say 1 chunk for the first and 3 for the second"""
+    import oracle_capi
+    from cases import Case
+    from root_digger_b200 import _build, capi
+    oracle_capi.load_oracle().rdo_set_default_mode(oracle_capi.MODE_ENGINE)
+    lib = capi.load_tree_lib(_build.build_host_on_oracle())
+    S = 8000
+    case = Case(12, S, 4, seed=3, data="iid")
+    shards = sharding.plan_site_shards(S, 2)
+    assert [c for _, c in shards] == [4096, 3904]
+    got = []
+    for off, cnt in shards:
+        aln = {l: s[off:off + cnt] for l, s in case.aln.items()}
+        m = capi.Model(capi.RootedTree(case.newick, lib=lib), aln, rate_cats=4, site_offset=off, global_sites=S,
+                       nranks=2, rank=0 if off == 0 else 1)
+        got.append(m.sweep_chunks)
+        m.close()
+    assert got == [1, 1]
+    # unsharded models of those sizes do differ: the rule is what makes the ranks agree
+    solo = [capi.Model(capi.RootedTree(case.newick, lib=lib), {l: s[:n] for l, s in case.aln.items()},
+                       rate_cats=4).sweep_chunks for n in (4096, 3904)]
+    assert solo == [1, 3]
