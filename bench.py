@@ -350,7 +350,7 @@ def run_ours(args):
         pm_off, mi, bl, op_off, ops, pos, chunk_off = case.tree.generate_chunked_sweep_operations(
             roots[0], roots[-1] + 1, layout=lay)
         pos = pos - roots[0]
-        sweep_flags = capi.RDK_SWEEP_KEEP_ROOT
+        sweep_flags = capi.RDK_SWEEP_KEEP_ROOT | capi.RDK_SWEEP_DISCARD
     else:
         pm_off, mi, bl, op_off, ops = case.sweep_schedule(roots, 0.5)
         pos = np.arange(len(roots))

@@ -223,6 +223,12 @@ int rdk_sweep_root_placements(rdk_partition_t *partition,
  * placements with ~1 CLV operation + 1 root evaluation each instead of a
  * re-orientation path per placement. */
 #define RDK_SWEEP_KEEP_ROOT 1u
+/* RDK_SWEEP_DISCARD: the content, after the call, of every CLV and scale buffer that the
+ * operations of this call write is UNDEFINED (they are scratch: the spare directed-CLV
+ * buffers of the directed sweep).  The engine then keeps a value in registers instead of
+ * storing it whenever no later operation of the sweep reads it back from memory.  The
+ * log-likelihoods are unchanged. */
+#define RDK_SWEEP_DISCARD 2u
 int rdk_sweep_root_placements_ex(rdk_partition_t *partition,
                                  unsigned int placements,
                                  const unsigned int *params_indices,
@@ -318,6 +324,9 @@ typedef struct rdk_stats {
                                            CUDA events on the partition's
                                            stream; 0 unless timing is enabled */
   unsigned long long program_timed;     /* launches included in program_time_ns */
+  unsigned long long instructions;      /* program instructions launched (operations + the
+                                           register loads the lowering inserted)           */
+  unsigned long long stores_elided;     /* CLV stores dropped because nothing reads them back */
 } rdk_stats_t;
 void rdk_partition_stats(rdk_partition_t *partition, rdk_stats_t *out);
 void rdk_partition_reset_stats(rdk_partition_t *partition);
@@ -328,11 +337,20 @@ int rdk_partition_set_timing(rdk_partition_t *partition, int enabled);
 int rdk_partition_set_launch_config(rdk_partition_t *partition,
                                     int ctas_per_sm, int threads_per_cta,
                                     int elems_per_thread);
-/* program-kernel tail handling when a warp's site range is not a multiple of
- * its elements per thread: 0 = engine's rule, 1 = always skip the idle slots,
- * 2 = never (recompute).  Results are identical in every mode. */
+/* accepted and ignored (round-1 kernels had two tail rules); results never depended on it */
 int rdk_partition_set_tail_mode(rdk_partition_t *partition, int mode);
 const char *rdk_version(void);
+/* Introspection of the lowering (csrc/rdk_lower.hpp), pure host code: `n_ops` recorded
+ * operations of 10 ints each {parent clv, parent scaler, child1 clv, child2 clv, child1
+ * scaler, child2 scaler, P slot 1, P slot 2, flags (1 store, 2 evaluate, 4 evaluate the
+ * stored CLV child1), eval slot} -> instructions of 9 ints each {flags, parent, parent
+ * scaler, child1, child1 scaler, child2 tip, P slot 1, P slot 2, eval slot}.  Returns the
+ * number of instructions, -1 if out_cap is too small. */
+int rdk_debug_lower_program(unsigned int tips, unsigned int n_ops, const int *ops,
+                            unsigned int n_chunks, const unsigned int *chunk_off,
+                            int discard_writes, const unsigned char *scratch_clv,
+                            unsigned int n_scratch_clv, int *out, unsigned int out_cap,
+                            unsigned int *out_chunk_off);
 
 #ifdef __cplusplus
 }

@@ -70,8 +70,8 @@ def build_engine(force: bool = False, verbose: bool = False, out: Path | None = 
     LIBDIR.mkdir(exist_ok=True)
     out = Path(out) if out else LIBDIR / "librdk_b200.so"
     out.parent.mkdir(parents=True, exist_ok=True)
-    srcs = [CSRC / "rdk_abi.cu", CSRC / "rdk_host_math.cpp", CSRC / "rdk_program_inst.cu"]
-    deps = srcs + [CSRC / "rdk_kernels.cuh", INCLUDE / "rdk.h"]
+    srcs = [CSRC / "rdk_abi.cu", CSRC / "rdk_host_math.cpp", CSRC / "rdk_lower_debug.cpp", CSRC / "rdk_program_inst.cu"]
+    deps = srcs + [CSRC / "rdk_kernels.cuh", CSRC / "rdk_lower.hpp", INCLUDE / "rdk.h"]
     if not force and _newer(out, deps):
         return out
     objdir = out.parent / ("obj_" + out.stem)
@@ -82,7 +82,8 @@ def build_engine(force: bool = False, verbose: bool = False, out: Path | None = 
     if verbose:
         base.insert(1, "-Xptxas=-v")
     jobs = [(base + ["-c", CSRC / "rdk_abi.cu", "-o", objdir / "rdk_abi.o"]),
-            (base + ["-c", CSRC / "rdk_host_math.cpp", "-o", objdir / "rdk_host_math.o"])]
+            (base + ["-c", CSRC / "rdk_host_math.cpp", "-o", objdir / "rdk_host_math.o"]),
+            (base + ["-c", CSRC / "rdk_lower_debug.cpp", "-o", objdir / "rdk_lower_debug.o"])]
     for k in PROGRAM_KS:
         jobs.append(base + ["-DRDK_INST_K=%d" % k, "-c", CSRC / "rdk_program_inst.cu", "-o", objdir / ("rdk_program_k%d.o" % k)])
     # heaviest translation units first (K = 4 carries the optional per-kind copies)

@@ -21,6 +21,7 @@ RDK_GAMMA_RATES_MEAN = 0
 RDK_GAMMA_RATES_MEDIAN = 1
 RDK_SHARD_ALIGN = 1024
 RDK_SWEEP_KEEP_ROOT = 1
+RDK_SWEEP_DISCARD = 2
 
 
 class Operation(C.Structure):
@@ -60,7 +61,7 @@ class Stats(C.Structure):
     _fields_ = [(n, C.c_ulonglong) for n in (
         "kernel_launches", "program_launches", "pmatrix_launches", "reduce_launches", "clv_ops",
         "root_evals", "pmatrices", "algorithmic_bytes", "h2d_bytes", "d2h_bytes", "device_bytes",
-        "program_time_ns", "program_timed")]
+        "program_time_ns", "program_timed", "instructions", "stores_elided")]
 
     def asdict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}

@@ -104,7 +104,7 @@ static int load_nccl() {
   return RDK_SUCCESS;
 }
 // ncclDataType_t / ncclRedOp_t values (stable across NCCL 2.x)
-static const int kNcclFloat64 = 8, kNcclUint64 = 5, kNcclSum = 0;
+static const int kNcclFloat64 = 8, kNcclUint64 = 5, kNcclSum = 0, kNcclMax = 2;
 
 // ---------------------------------------------------------------------------
 // engine state
@@ -144,7 +144,8 @@ struct Engine {
 
   // recorded work
   std::vector<PmatEntry> pend_pm;
-  std::vector<Instr>     pend_prog;
+  std::vector<ROp>       pend_prog;
+  bool                   pend_discard = false;  // the buffers pend_prog writes are scratch (directed sweep)
   unsigned               pend_slots = 0;  // eval slots used by pend_prog
   unsigned long long     pend_bytes = 0;  // algorithmic bytes of pend_prog
   unsigned               pend_ops = 0, pend_evals = 0;
@@ -164,10 +165,10 @@ struct Engine {
   unsigned long long site_offset = 0, global_sites = 0;
   void              *comm = nullptr;
   int                nranks = 1, rank = 0;
+  unsigned long long max_shard_sites = 0;  // largest shard of the layout (agreed over the communicator)
 
   // launch config
   int ctas_per_sm = 0, threads = 0, elems = 0;
-  int tail_skip = 0;  // 0 = choose_tail_skip's rule, 1 = always, 2 = never
 
   // optional per-launch timing of the program kernel (bench / profiling)
   bool                                            timing = false;
@@ -307,19 +308,6 @@ int launch_pmatrices(rdk_partition_t *p) {
   return RDK_SUCCESS;
 }
 
-// Tail skip pays when NO warp has a full last pass: the warps' ranges differ by at most
-// one iteration, so that is when the largest range is not a multiple of E.  (Measured on
-// B200, 500 taxa, E = 2, ms per search step with / without: 12.5k sites 5.5 / 7.7,
-// 50k 14.2 / 16.5, but 25k 9.0 / 8.7 and 100k 26.0 / 25.6 where some warps run full
-// passes anyway.)  tail_skip: 0 = this rule, 1 = always, 2 = never.
-bool choose_tail_skip(unsigned n_witer, int grid, int threads, int E, int mode) {
-  if (E < 2 || mode == 2) return false;
-  if (mode == 1) return true;
-  const unsigned long long nw = (unsigned long long)grid * (unsigned)(threads / 32);
-  const unsigned long long q_hi = (n_witer + nw - 1) / nw;
-  return q_hi % (unsigned)E != 0;
-}
-
 int ensure_partials(Engine *e, unsigned slots, unsigned stride) {
   size_t need = (size_t)slots * stride;
   if (need > e->partials_cap) {
@@ -342,66 +330,67 @@ int ensure_partials(Engine *e, unsigned slots, unsigned stride) {
   return RDK_SUCCESS;
 }
 
-// pre-decode, per instruction, what the kernel would otherwise find out by comparing
-// pointers at run time: which operands are forwarded in registers from the previous
-// instruction and which scaler counts have to be loaded.  The first instruction of a
-// shared-memory window never forwards (its operands are loaded from memory).
-void finalize_program(std::vector<Instr> &prog, int table_K, const std::vector<unsigned> &chunk_off) {
-  size_t chunk = 0, chunk_begin = 0;
-  const unsigned decoded = kFwd1 | kFwd2 | kLdS1 | kLdS2 | kFwdS1 | kFwdS2 | kEvalScaler;
-  for (size_t i = 0; i < prog.size(); ++i) {
-    Instr &in = prog[i];
-    in.flags &= ~decoded;
-    // shared-memory windows restart at every chunk of a chunked program
-    while (chunk + 1 < chunk_off.size() && i >= chunk_off[chunk + 1]) chunk_begin = chunk_off[++chunk];
-    const bool   first = ((i - chunk_begin) % kProgWindow) == 0;
-    const Instr *pv = first ? nullptr : &prog[i - 1];
-    const double   *fwd_clv = (pv && (pv->flags & kWrite)) ? pv->parent : nullptr;
-    const unsigned *fwd_scale = (pv && (pv->flags & kWrite)) ? pv->pscale : nullptr;
-    const bool load_only = (in.flags & kLoadOnly) != 0;
-    if (!(in.flags & kTip1) && fwd_clv && in.c1 == fwd_clv) in.flags |= kFwd1;
-    if (!load_only && !(in.flags & kTip2) && fwd_clv && in.c2 == fwd_clv) in.flags |= kFwd2;
-    // canonical child order (the product of the two children's terms is commutative, so the
-    // result keeps its bits): a tip first, a forwarded CLV last -- fewer kinds to compile
-    if (load_only) {
-      // the stored CLV to evaluate is the one just produced: it arrives where a forwarded
-      // child always does, in the child-2 registers
-      if (in.flags & kFwd1) in.flags = (in.flags & ~kFwd1) | kFwd2;
-    } else {
-      const unsigned f = in.flags;
-      const bool     swap = ((f & kTip2) && !(f & kTip1)) || ((f & kFwd1) && !(f & (kFwd2 | kTip2)));
-      if (swap) {
-        std::swap(in.c1, in.c2);
-        std::swap(in.c1scale, in.c2scale);
-        std::swap(in.P1, in.P2);
-        unsigned g = f & ~(kTip1 | kTip2 | kFwd1 | kFwd2);
-        if (f & kTip1) g |= kTip2;
-        if (f & kTip2) g |= kTip1;
-        if (f & kFwd1) g |= kFwd2;
-        if (f & kFwd2) g |= kFwd1;
-        in.flags = g;
+// elements per thread and launch shape of the program kernel for a shard of n_witer warp
+// iterations walked by `x_ctas_cap` CTAs at most (the chunks of a chunked program share the
+// device): the smallest E whose single pass covers the shard -- every program instruction costs
+// a warp a fixed preamble whatever E is, but a second pass costs a whole walk -- else E = 4.
+struct LaunchPlan {
+  int E, threads, grid;
+};
+LaunchPlan plan_launch(const Engine *e, unsigned n_witer, unsigned n_chunks) {
+  LaunchPlan pl{};
+  int        E = e->elems;
+  if (E == 3) E = 2;
+  if (E == 0) {
+    E = 4;
+    for (int cand : {1, 2}) {
+      const LaunchShape sh = launch_shape(cand);
+      const unsigned long long ctas = std::max<unsigned long long>(1, (unsigned long long)e->sm_count * sh.ctas_per_sm / n_chunks);
+      const unsigned long long cap = ctas * (unsigned long long)(sh.threads / 32 - 1) * cand;
+      if (n_witer <= cap) {
+        E = cand;
+        break;
       }
     }
-    if (in.c1scale) in.flags |= (fwd_scale && in.c1scale == fwd_scale) ? kFwdS1 : kLdS1;
-    if (!load_only && in.c2scale) in.flags |= (fwd_scale && in.c2scale == fwd_scale) ? kFwdS2 : kLdS2;
-    if (in.flags & kEval) {
-      const bool has_scaler = load_only ? (in.c1scale != nullptr) : ((in.flags & kScale) != 0);
-      if (has_scaler) in.flags |= kEvalScaler;
-    }
-    in.kind = 2u * ((in.flags & kFwd1) ? 0u : fast_kind_of(in.flags));
-    // the table each child reads (P of an inner child, T of a tip child) and their sizes,
-    // so that the kernel's staging has nothing to decide
-    if (in.tx == 0 && !load_only) {
-      const unsigned K = (unsigned)table_K;
-      const unsigned b1 = ((in.flags & kTip1) ? kTipTabDoubles : kPTabDoubles) * K * 8u;
-      const unsigned b2 = ((in.flags & kTip2) ? kTipTabDoubles : kPTabDoubles) * K * 8u;
-      if (in.flags & kTip1) in.P1 += (size_t)kPTabDoubles * K;
-      if (in.flags & kTip2) in.P2 += (size_t)kPTabDoubles * K;
-      in.tx = b1 | (b2 << 16);
-    }
-    // the previous instruction produces its values directly in this one's child-2 registers
-    if (in.flags & kFwd2) prog[i - 1].kind |= 1u;
   }
+  const LaunchShape sh = launch_shape(E);
+  int threads = e->threads ? std::min(e->threads, sh.threads) : sh.threads;
+  threads = std::max(64, threads);
+  const int per_sm = e->ctas_per_sm ? std::min(e->ctas_per_sm, sh.ctas_per_sm) : sh.ctas_per_sm;
+  int       grid = e->sm_count * per_sm;
+  // a chunked program launches grid x chunks CTAs: keep them all resident at once (one wave)
+  if (n_chunks > 1) grid = std::max(1, grid / (int)n_chunks);
+  // never more consumer warps than warp iterations
+  const int cons = threads / 32 - 1;
+  const int max_grid = (int)((n_witer + (unsigned)cons - 1) / (unsigned)cons);
+  grid = std::max(1, std::min(grid, max_grid));
+  pl.E = E;
+  pl.threads = threads;
+  pl.grid = grid;
+  return pl;
+}
+
+// index -> device pointer translation of a lowered instruction
+void to_device_instr(Engine *e, const LInstr &li, Instr *out) {
+  Instr in;
+  memset(&in, 0, sizeof(in));
+  in.flags = li.flags;
+  in.slot = li.slot;
+  if (li.flags & fWrite) in.parent = e->clv_ptr[li.parent - e->tips];
+  if (li.flags & fWriteS) in.pscale = e->d_scalers + (size_t)li.pscale * e->S;
+  if (li.flags & fTip1)
+    in.c1 = e->d_tips + (size_t)li.c1 * e->tip_stride;
+  else if (!(li.flags & fNop))
+    in.c1 = e->clv_ptr[li.c1 - e->tips];
+  if (li.flags & fTip2) in.c2 = e->d_tips + (size_t)li.c2 * e->tip_stride;
+  if (li.flags & fCnt1) in.c1scale = e->d_scalers + (size_t)li.c1scale * e->S;
+  if (!(li.flags & (fLoadV | fNop))) {
+    // the table each child reads: P of an inner child, T of a tip child (same pool slot)
+    const size_t K = e->K;
+    in.P1 = e->d_pool + (size_t)li.pm1 * K * kSlotDoubles + ((li.flags & fTip1) ? (size_t)kPTabDoubles * K : 0);
+    in.P2 = e->d_pool + (size_t)li.pm2 * K * kSlotDoubles + ((li.flags & fTip2) ? (size_t)kPTabDoubles * K : 0);
+  }
+  *out = in;
 }
 
 // launch recorded P-matrix work and the recorded program (no host sync)
@@ -417,7 +406,6 @@ int flush(rdk_partition_t *p) {
   const unsigned n_witer = (nelem + 31) / 32;
   ProgArgs       a;
   memset(&a, 0, sizeof(a));
-  a.n_instr = (int)e->pend_prog.size();
   a.nelem = nelem;
   a.n_witer = n_witer;
   a.weights = e->d_weights;
@@ -429,64 +417,46 @@ int flush(rdk_partition_t *p) {
     a.partials = e->d_partials;
   }
   a.persite = e->want_persite ? e->d_persite : nullptr;
-  const bool chunked = e->pend_chunk_off.size() > 2 && e->pend_prog.size() > (size_t)kProgInline;
+  // recorded operations -> the instructions the kernel walks (rdk_lower.hpp)
+  const bool            chunked = e->pend_chunk_off.size() > 2;
+  std::vector<LInstr>   lowered;
+  std::vector<unsigned> lchunk;
+  LowerOptions          lopt;
+  lopt.tips = e->tips;
+  lopt.discard_writes = e->pend_discard;
+  LowerStats lst;
+  lower_program(e->pend_prog, chunked ? e->pend_chunk_off : std::vector<unsigned>(), lopt, lowered, lchunk, &lst);
+  e->stats.instructions += lowered.size();
+  e->stats.stores_elided += lst.stores_dropped;
+  a.n_instr = (int)lowered.size();
   if (chunked) {
-    a.n_chunks = (unsigned)e->pend_chunk_off.size() - 1;
-    for (size_t c = 0; c < e->pend_chunk_off.size(); ++c) a.chunk_off[c] = e->pend_chunk_off[c];
+    a.n_chunks = (unsigned)lchunk.size() - 1;
+    for (size_t c = 0; c < lchunk.size(); ++c) a.chunk_off[c] = lchunk[c];
   }
-  finalize_program(e->pend_prog, (int)e->K, chunked ? e->pend_chunk_off : std::vector<unsigned>());
-  if (a.n_instr <= kProgInline) {
-    for (int i = 0; i < a.n_instr; ++i) a.inl[i] = e->pend_prog[i];
+  if (a.n_instr <= kProgInline && !chunked) {
+    for (int i = 0; i < a.n_instr; ++i) to_device_instr(e, lowered[i], &a.inl[i]);
   } else {
     char  *h, *d;
-    size_t bytes = sizeof(Instr) * e->pend_prog.size();
+    size_t bytes = sizeof(Instr) * lowered.size();
     if (!ring_alloc(e, bytes, &h, &d)) return RDK_FAILURE;
-    memcpy(h, e->pend_prog.data(), bytes);
+    Instr *hp = reinterpret_cast<Instr *>(h);
+    for (size_t i = 0; i < lowered.size(); ++i) to_device_instr(e, lowered[i], &hp[i]);
     CUDA_TRY(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, e->stream));
     e->stats.h2d_bytes += bytes;
     a.prog = reinterpret_cast<const Instr *>(d);
   }
-  if (nelem > 0) {
-    int threads = e->threads ? e->threads : 128;
-    // elements per thread: every program instruction costs a warp a fixed preamble (table
-    // staging, flag decode, barrier wait) whatever E is, so shards that give every warp of the
-    // E = 4 grid (2 CTAs per SM, 255 registers) at least 2 iterations run E = 4.  Measured on
-    // B200, ms per cfg2 step, E = 4 / E = 2 (4 CTAs per SM): 100 k sites 12.1 / 15.0, 50 k
-    // 7.0 / 8.3, 25 k 4.2 / 5.2, 12.5 k 3.07 / 3.08 (one iteration per warp either way).
-    int E = e->elems;
-    if (E == 0) E = (n_witer >= 2u * (unsigned)(e->sm_count * 2 * 4)) ? 4 : 2;
-    int per_sm = e->ctas_per_sm ? e->ctas_per_sm : (E == 4 ? 2 : 4);
-    if (E >= 2) threads = std::min(threads, 128);
-    if (E == 3) E = 2;
-    // every warp owns a table buffer of 2 KiB * K: keep a CTA's shared memory near 64 KiB
-    // (K = 4: 4 warps; K = 16: 1-2 warps; K = 32: 1 warp)
-#if !RDK_TABLES_L1
-    {
-      const size_t per_warp = sizeof(double) * 2 * 2 * kTabDoubles * e->K + 16;
-      const size_t budget = (size_t)64 << 10;
-      int max_warps = (int)std::max<size_t>(1, (budget - std::min(budget, sizeof(Instr) * kProgWindow)) / per_warp);
-      threads = std::min(threads, 32 * max_warps);
-    }
-#endif
-    int grid = e->sm_count * per_sm;
-    // never launch more warps than warp iterations
-    int max_grid = (int)((n_witer + (threads / 32) - 1) / (threads / 32));
-    grid = std::max(1, std::min(grid, max_grid));
-    // a chunked program launches grid x chunks CTAs: keep them all resident at once (one wave) --
-    // a partial extra wave costs as much as a full one, so the warps take more iterations instead
-    if (chunked) grid = std::max(1, std::min(grid, (e->sm_count * per_sm) / (int)a.n_chunks));
+  if (nelem > 0 && a.n_instr > 0) {
+    const LaunchPlan pl = plan_launch(e, n_witer, chunked ? a.n_chunks : 1u);
     std::pair<cudaEvent_t, cudaEvent_t> *ev = e->timing ? next_event_pair(e) : nullptr;
     if (ev) CUDA_TRY(cudaEventRecord(ev->first, e->stream));
-    if (E != 1) threads = std::min(threads, 128);
-    const bool  ts = choose_tail_skip(n_witer, grid, threads, E, e->tail_skip);
     cudaError_t lerr;
     switch (e->K) {
-      case 1: lerr = launch_program<1>(a, grid, threads, E, ts, e->stream); break;
-      case 2: lerr = launch_program<2>(a, grid, threads, E, ts, e->stream); break;
-      case 4: lerr = launch_program<4>(a, grid, threads, E, ts, e->stream); break;
-      case 8: lerr = launch_program<8>(a, grid, threads, E, ts, e->stream); break;
-      case 16: lerr = launch_program<16>(a, grid, threads, E, ts, e->stream); break;
-      case 32: lerr = launch_program<32>(a, grid, threads, E, ts, e->stream); break;
+      case 1: lerr = launch_program<1>(a, pl.grid, pl.threads, pl.E, e->stream); break;
+      case 2: lerr = launch_program<2>(a, pl.grid, pl.threads, pl.E, e->stream); break;
+      case 4: lerr = launch_program<4>(a, pl.grid, pl.threads, pl.E, e->stream); break;
+      case 8: lerr = launch_program<8>(a, pl.grid, pl.threads, pl.E, e->stream); break;
+      case 16: lerr = launch_program<16>(a, pl.grid, pl.threads, pl.E, e->stream); break;
+      case 32: lerr = launch_program<32>(a, pl.grid, pl.threads, pl.E, e->stream); break;
       default: return fail(RDK_ERROR_PARAM, "rate_cats must divide 32");
     }
     if (lerr != cudaSuccess) return fail(RDK_ERROR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(lerr));
@@ -500,6 +470,7 @@ int flush(rdk_partition_t *p) {
   e->stats.algorithmic_bytes += e->pend_bytes;
   e->pend_prog.clear();
   e->pend_chunk_off.clear();
+  e->pend_discard = false;
   e->pend_ops = e->pend_evals = 0;
   e->pend_bytes = 0;
   for (unsigned s : e->pm_retired) e->pm_free.push_back(s);
@@ -568,8 +539,9 @@ int finish_evals(rdk_partition_t *p, unsigned slots) {
   return RDK_SUCCESS;
 }
 
-// translate a corax-shaped operation into a program instruction
-int make_instr(rdk_partition_t *p, const rdk_operation_t &op, unsigned flags, Instr *out) {
+// translate a corax-shaped operation into a recorded operation (buffers allocated, P-matrix
+// indices resolved to the physical pool slots they name NOW)
+int make_rop(rdk_partition_t *p, const rdk_operation_t &op, unsigned flags, ROp *out) {
   Engine *e = eng(p);
   const unsigned nclv = e->tips + e->clv_buffers;
   if (op.parent_clv_index < e->tips || op.parent_clv_index >= nclv)
@@ -582,49 +554,40 @@ int make_instr(rdk_partition_t *p, const rdk_operation_t &op, unsigned flags, In
   if (bad_scaler(op.parent_scaler_index) || bad_scaler(op.child1_scaler_index) ||
       bad_scaler(op.child2_scaler_index))
     return fail(RDK_ERROR_PARAM, "scaler index out of range");
-  Instr in;
-  memset(&in, 0, sizeof(in));
-  in.flags = flags;
-  if (flags & kWrite) {
-    if (!ensure_clv(e, op.parent_clv_index - e->tips)) return RDK_FAILURE;
-    in.parent = e->clv_ptr[op.parent_clv_index - e->tips];
-  }
-  auto child = [&](unsigned idx, unsigned tipflag, const void **ptr) -> int {
-    if (idx < e->tips) {
-      in.flags |= tipflag;
-      *ptr = e->d_tips + (size_t)idx * e->tip_stride;
-    } else {
-      if (!ensure_clv(e, idx - e->tips)) return RDK_FAILURE;  // reading an unwritten CLV: zeros
-      *ptr = e->clv_ptr[idx - e->tips];
-    }
-    return RDK_SUCCESS;
-  };
-  if (!child(op.child1_clv_index, kTip1, &in.c1)) return RDK_FAILURE;
-  if (!child(op.child2_clv_index, kTip2, &in.c2)) return RDK_FAILURE;
-  if (op.parent_scaler_index != RDK_SCALE_BUFFER_NONE) {
-    in.flags |= kScale;
-    in.pscale = e->d_scalers + (size_t)op.parent_scaler_index * e->S;
-    if (op.child1_scaler_index != RDK_SCALE_BUFFER_NONE)
-      in.c1scale = e->d_scalers + (size_t)op.child1_scaler_index * e->S;
-    if (op.child2_scaler_index != RDK_SCALE_BUFFER_NONE)
-      in.c2scale = e->d_scalers + (size_t)op.child2_scaler_index * e->S;
-  }
-  in.P1 = e->d_pool + (size_t)e->pm_map[op.child1_matrix_index] * e->K * kSlotDoubles;
-  in.P2 = e->d_pool + (size_t)e->pm_map[op.child2_matrix_index] * e->K * kSlotDoubles;
-  *out = in;
+  ROp r;
+  memset(&r, 0, sizeof(r));
+  r.flags = flags;
+  r.parent = op.parent_clv_index;
+  if (!ensure_clv(e, op.parent_clv_index - e->tips)) return RDK_FAILURE;
+  // reading an unwritten CLV: zeros
+  if (op.child1_clv_index >= e->tips && !ensure_clv(e, op.child1_clv_index - e->tips)) return RDK_FAILURE;
+  if (op.child2_clv_index >= e->tips && !ensure_clv(e, op.child2_clv_index - e->tips)) return RDK_FAILURE;
+  r.c1 = op.child1_clv_index;
+  r.c2 = op.child2_clv_index;
+  r.pscale = op.parent_scaler_index;
+  // without a parent scale buffer the children's counts are dropped (coraxlib semantics)
+  const bool scaled = op.parent_scaler_index != RDK_SCALE_BUFFER_NONE;
+  r.c1scale = scaled ? op.child1_scaler_index : -1;
+  r.c2scale = scaled ? op.child2_scaler_index : -1;
+  if (op.child1_clv_index < e->tips && op.child2_clv_index < e->tips && r.c1scale >= 0 && r.c2scale >= 0)
+    return fail(RDK_ERROR_PARAM, "two tip children with scale buffers are not supported (tips carry no scaler, "
+                                 "reference test/src/tree.cpp:157)");
+  r.pm1 = e->pm_map[op.child1_matrix_index];
+  r.pm2 = e->pm_map[op.child2_matrix_index];
+  *out = r;
   return RDK_SUCCESS;
 }
 
 // SURVEY 8d accounting for one CLV operation on this shard
-unsigned long long op_bytes(const Engine *e, const Instr &in) {
+unsigned long long op_bytes(const Engine *e, const ROp &r) {
   unsigned long long S = e->S, clv = 32ull * e->K * S, b = 0;
-  b += (in.flags & kTip1) ? S : clv;
-  b += (in.flags & kTip2) ? S : clv;
-  if (in.flags & kWrite) b += clv;
-  if (in.c1scale) b += 4 * S;
-  if (in.c2scale) b += 4 * S;
-  if ((in.flags & kWrite) && in.pscale) b += 4 * S;
-  if (in.flags & kEval) b += 4 * S;  // pattern weights
+  b += (r.c1 < e->tips) ? S : clv;
+  b += (r.c2 < e->tips) ? S : clv;
+  if (r.flags & rWrite) b += clv;
+  if (r.c1scale >= 0) b += 4 * S;
+  if (r.c2scale >= 0) b += 4 * S;
+  if ((r.flags & rWrite) && r.pscale >= 0) b += 4 * S;
+  if (r.flags & rEval) b += 4 * S;  // pattern weights
   return b;
 }
 
@@ -964,10 +927,10 @@ extern "C" void rdk_update_clvs(rdk_partition_t *p, const rdk_operation_t *ops, 
   std::lock_guard<std::mutex> lk(e->mu);
   cudaSetDevice(e->device);
   for (unsigned i = 0; i < count; ++i) {
-    Instr in;
-    if (!make_instr(p, ops[i], kWrite, &in)) return;  // error left in rdk_errno
-    e->pend_bytes += op_bytes(e, in);
-    e->pend_prog.push_back(in);
+    ROp r;
+    if (!make_rop(p, ops[i], rWrite, &r)) return;  // error left in rdk_errno
+    e->pend_bytes += op_bytes(e, r);
+    e->pend_prog.push_back(r);
     e->pend_ops++;
   }
 }
@@ -989,29 +952,31 @@ extern "C" double rdk_compute_root_loglikelihood(rdk_partition_t *p, unsigned in
     return nan;
   }
   if (!ensure_clv(e, clv_index - e->tips)) return nan;
-  double        *root = e->clv_ptr[clv_index - e->tips];
-  const unsigned *rs = scaler_index == RDK_SCALE_BUFFER_NONE ? nullptr : e->d_scalers + (size_t)scaler_index * e->S;
+  const int rs = scaler_index == RDK_SCALE_BUFFER_NONE ? -1 : scaler_index;
   // fuse with the recorded operation that produces this CLV, if it is the last one
   bool fused = false;
   if (!e->pend_prog.empty()) {
-    Instr &last = e->pend_prog.back();
-    if ((last.flags & kWrite) && !(last.flags & kEval) && last.parent == root &&
-        last.pscale == rs) {
-      last.flags |= kEval;
+    ROp &last = e->pend_prog.back();
+    if ((last.flags & rWrite) && !(last.flags & rEval) && last.parent == clv_index && last.pscale == rs) {
+      last.flags |= rEval;
       last.slot = 0;
       e->pend_bytes += 4ull * e->S;
       fused = true;
     }
   }
   if (!fused) {
-    Instr in;
-    memset(&in, 0, sizeof(in));
-    in.flags = kLoadOnly | kEval;
-    in.c1 = root;
-    in.c1scale = rs;
-    in.slot = 0;
-    e->pend_bytes += 32ull * e->K * e->S + (rs ? 4ull * e->S : 0) + 4ull * e->S;
-    e->pend_prog.push_back(in);
+    ROp r;
+    memset(&r, 0, sizeof(r));
+    r.flags = rLoadOnly | rEval;
+    r.parent = kNoClv;
+    r.pscale = -1;
+    r.c1 = clv_index;
+    r.c1scale = rs;
+    r.c2 = kNoClv;
+    r.c2scale = -1;
+    r.slot = 0;
+    e->pend_bytes += 32ull * e->K * e->S + (rs >= 0 ? 4ull * e->S : 0) + 4ull * e->S;
+    e->pend_prog.push_back(r);
   }
   e->pend_evals++;
   e->pend_slots = 1;
@@ -1053,8 +1018,8 @@ extern "C" int rdk_root_loglikelihood_multi(rdk_partition_t *p, const rdk_operat
   if (!flush(p)) return RDK_FAILURE;
   if (e->pm_free.size() < 2 * (size_t)count)
     return fail(RDK_ERROR_PARAM, "too many candidates in one call (max %zu)", e->pm_free.size() / 2);
-  Instr base;
-  if (!make_instr(p, *root_op, 0, &base)) return RDK_FAILURE;
+  ROp base;
+  if (!make_rop(p, *root_op, 0, &base)) return RDK_FAILURE;
   std::vector<unsigned> used;
   for (unsigned b = 0; b < count; ++b) {
     unsigned s1 = e->pm_free.back();
@@ -1066,15 +1031,13 @@ extern "C" int rdk_root_loglikelihood_multi(rdk_partition_t *p, const rdk_operat
     PmatEntry e1{s1, 0, branch_lengths[2 * b]}, e2{s2, 0, branch_lengths[2 * b + 1]};
     e->pend_pm.push_back(e1);
     e->pend_pm.push_back(e2);
-    Instr in = base;
-    in.flags |= kEval;  // no kWrite: partition state is left untouched
-    in.parent = nullptr;
-    in.pscale = nullptr;
-    in.P1 = e->d_pool + (size_t)s1 * e->K * kSlotDoubles;
-    in.P2 = e->d_pool + (size_t)s2 * e->K * kSlotDoubles;
-    in.slot = b;
-    e->pend_bytes += op_bytes(e, in);
-    e->pend_prog.push_back(in);
+    ROp r = base;
+    r.flags = rEval;  // no rWrite: partition state is left untouched
+    r.pm1 = s1;
+    r.pm2 = s2;
+    r.slot = b;
+    e->pend_bytes += op_bytes(e, r);
+    e->pend_prog.push_back(r);
     e->pend_evals++;
   }
   e->pend_slots = count;
@@ -1162,13 +1125,14 @@ extern "C" int rdk_sweep_root_placements_chunks(rdk_partition_t *p, unsigned int
   CUDA_TRY(cudaSetDevice(e->device));
   if (!flush(p)) return RDK_FAILURE;
   if (!ensure_clv(e, root_clv_index - e->tips)) return RDK_FAILURE;
-  double         *root = e->clv_ptr[root_clv_index - e->tips];
-  const unsigned *rs = root_scaler_index == RDK_SCALE_BUFFER_NONE
-                           ? nullptr
-                           : e->d_scalers + (size_t)root_scaler_index * e->S;
-  // batches bounded by the spare P-matrix slots and the partial-sum buffer
-  const size_t   stride = std::max(1u, (e->S * e->K + 31) / 32);
-  const unsigned max_slots = (unsigned)std::max<size_t>(1, std::min<size_t>(4096, (size_t(256) << 20) / (stride * 8)));
+  const int rs = root_scaler_index == RDK_SCALE_BUFFER_NONE ? -1 : root_scaler_index;
+  // batches bounded by the spare P-matrix slots and the partial-sum buffer.  With a communicator
+  // attached the ranks' values are added slot by slot, so every rank must cut the sweep at the
+  // same placements: the bound is derived from the LARGEST shard of the layout (agreed when the
+  // communicator was attached), never from the local site count.
+  const unsigned long long s_ref = e->comm ? e->max_shard_sites : e->S;
+  const size_t             ref_stride = (size_t)std::max<unsigned long long>(1, (s_ref * e->K + 31) / 32);
+  const unsigned max_slots = (unsigned)std::max<size_t>(1, std::min<size_t>(4096, (size_t(256) << 20) / (ref_stride * 8)));
   // whatever way this call ends, the chunk table does not outlive it
   struct chunk_table_guard {
     Engine *e;
@@ -1214,31 +1178,31 @@ extern "C" int rdk_sweep_root_placements_chunks(rdk_partition_t *p, unsigned int
         if (!record_pmatrix(p, matrix_indices[i], branch_lengths[i])) return RDK_FAILURE;
       bool fused = false;
       for (unsigned i = op_offsets[q]; i < op_offsets[q + 1]; ++i) {
-        Instr in;
-        if (!make_instr(p, operations[i], kWrite, &in)) return RDK_FAILURE;
-        if (i + 1 == op_offsets[q + 1] && in.parent == root && in.pscale == rs) {
-          in.flags |= kEval;
-          in.slot = b;
+        ROp r;
+        if (!make_rop(p, operations[i], rWrite, &r)) return RDK_FAILURE;
+        if (i + 1 == op_offsets[q + 1] && r.parent == root_clv_index && r.pscale == rs) {
+          r.flags |= rEval;
+          r.slot = b;
           fused = true;
-          if (flags & RDK_SWEEP_KEEP_ROOT) {  // evaluate in registers, store nothing
-            in.flags &= ~kWrite;
-            in.parent = nullptr;
-            in.pscale = nullptr;
-          }
+          if (flags & RDK_SWEEP_KEEP_ROOT) r.flags &= ~rWrite;  // evaluate in registers, store nothing
         }
-        e->pend_bytes += op_bytes(e, in);
-        e->pend_prog.push_back(in);
+        e->pend_bytes += op_bytes(e, r);
+        e->pend_prog.push_back(r);
         e->pend_ops++;
       }
       if (!fused) {
-        Instr in;
-        memset(&in, 0, sizeof(in));
-        in.flags = kLoadOnly | kEval;
-        in.c1 = root;
-        in.c1scale = rs;
-        in.slot = b;
-        e->pend_bytes += 32ull * e->K * e->S + (rs ? 4ull * e->S : 0) + 4ull * e->S;
-        e->pend_prog.push_back(in);
+        ROp r;
+        memset(&r, 0, sizeof(r));
+        r.flags = rLoadOnly | rEval;
+        r.parent = kNoClv;
+        r.pscale = -1;
+        r.c1 = root_clv_index;
+        r.c1scale = rs;
+        r.c2 = kNoClv;
+        r.c2scale = -1;
+        r.slot = b;
+        e->pend_bytes += 32ull * e->K * e->S + (rs >= 0 ? 4ull * e->S : 0) + 4ull * e->S;
+        e->pend_prog.push_back(r);
       }
       e->pend_evals++;
       ++b;
@@ -1246,6 +1210,9 @@ extern "C" int rdk_sweep_root_placements_chunks(rdk_partition_t *p, unsigned int
     if (b == 0) return fail(RDK_ERROR_PARAM, "a placement needs more P-matrices than the pool holds");
     if (concurrent) e->pend_chunk_off.push_back((unsigned)e->pend_prog.size());
     e->pend_slots = b;
+    // the buffers the operations write are scratch only if nothing of them is needed by a later
+    // batch of this very sweep: the whole sweep must be this one launch
+    e->pend_discard = (flags & RDK_SWEEP_DISCARD) && done == 0 && b == placements;
     int ok = flush(p);
     e->pend_slots = 0;
     if (!ok) return RDK_FAILURE;
@@ -1344,6 +1311,16 @@ extern "C" int rdk_partition_attach_comm(rdk_partition_t *p, int nranks, int ran
   e->comm = comm;
   e->nranks = nranks;
   e->rank = rank;
+  // agree on the largest shard of the layout: everything that sizes a batch of a collective
+  // evaluation is derived from it, so that all ranks cut their work at the same places
+  unsigned long long mine = e->S, agreed = 0;
+  CUDA_TRY(cudaMemcpyAsync(e->d_hist, &mine, sizeof(mine), cudaMemcpyHostToDevice, e->stream));
+  rc = g_nccl.AllReduce(e->d_hist, e->d_hist, 1, kNcclUint64, kNcclMax, e->comm, e->stream);
+  if (rc != 0)
+    return fail(RDK_ERROR_COMM, "ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+  CUDA_TRY(cudaMemcpyAsync(&agreed, e->d_hist, sizeof(agreed), cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  e->max_shard_sites = agreed;
   return RDK_SUCCESS;
 }
 
@@ -1482,17 +1459,18 @@ extern "C" int rdk_partition_set_timing(rdk_partition_t *p, int enabled) {
 }
 
 extern "C" int rdk_partition_set_tail_mode(rdk_partition_t *p, int mode) {
+  // kept for ABI compatibility: the program kernel has a single tail rule now (slots without an
+  // iteration of their own recompute the warp's last iteration)
   if (!p) return fail(RDK_ERROR_PARAM, "null partition");
-  if (mode < 0 || mode > 2) return fail(RDK_ERROR_PARAM, "tail mode must be 0 (auto), 1 (always) or 2 (never)");
-  eng(p)->tail_skip = mode;
+  if (mode < 0 || mode > 2) return fail(RDK_ERROR_PARAM, "tail mode must be 0, 1 or 2");
   return RDK_SUCCESS;
 }
 
 extern "C" int rdk_partition_set_launch_config(rdk_partition_t *p, int ctas_per_sm,
                                                int threads_per_cta, int elems_per_thread) {
   Engine *e = eng(p);
-  if (threads_per_cta != 0 && (threads_per_cta < 32 || threads_per_cta > 256 || threads_per_cta % 32))
-    return fail(RDK_ERROR_PARAM, "threads_per_cta must be a multiple of 32 in [32,256]");
+  if (threads_per_cta != 0 && (threads_per_cta < 64 || threads_per_cta > 512 || threads_per_cta % 32))
+    return fail(RDK_ERROR_PARAM, "threads_per_cta must be a multiple of 32 in [64,512] (one warp is the table producer)");
   if (elems_per_thread < 0 || elems_per_thread > 4)
     return fail(RDK_ERROR_PARAM, "elems_per_thread must be in [0,4]");
   if (ctas_per_sm < 0 || ctas_per_sm > 32) return fail(RDK_ERROR_PARAM, "ctas_per_sm out of range");

@@ -16,65 +16,12 @@
 // accesses, enough bytes in flight, and never re-reading a CLV from HBM.
 #pragma once
 #include <cuda_runtime.h>
-#ifndef RDK_KSLOW
-// 1: CLVs are stored in blocks of 32 elements (= 32/K sites) laid out [cat][site in block][state]
-//    and lane l of a warp holds category l / (32/K): global accesses stay 1 KiB-contiguous per warp
-//    while the lanes of a quarter warp share their category (one shared-memory address per
-//    quarter warp when reading P).  0: natural [site][cat][state] layout, category = l % K.
-#define RDK_KSLOW 0  // measured on B200: no gain from the blocked layout (the LSU pipe is not the limiter)
-#endif
-#ifndef RDK_MINB2
-#define RDK_MINB2 4  // resident CTAs of 128 threads the E = 2 program kernel is compiled for
-#endif
-#ifndef RDK_FAST_KINDS
-// 1: per-kind compile-time copies of the instruction body (K = 4; E = 2, 4).  Measured on B200
-// (cfg2 step): 24 % fewer warp instructions, but the same time at E = 4 (80.4 k vs 81-82 k
-// placements/s) and +4 % at E = 2 (66.4 k vs 63.8 k): the walk is bound by the latency of each
-// warp's dependent chain, not by issue slots, and the copies cost instruction-cache misses and
-// 2 more minutes of compile time.  (2: also for the short tail passes -- 64.7 k at 100 k sites,
-// no gain on a 12.5 k-site shard.)  Off by default.
-#define RDK_FAST_KINDS 0
-#endif
-#ifndef RDK_TABLES_L1
-// 1: the P / tip tables of an instruction are read straight from global memory through L1
-//    (ld.global.nc; the lines are prefetched into L1 one instruction ahead) -- no shared-memory
-//    staging, no mbarrier wait, no per-warp copy issue per instruction.
-// 0: every warp stages them in its own shared-memory double buffer with cp.async.bulk + mbarrier.
-// Measured on B200 (cfg2 step, E = 4): 63.7 k placements/s through L1 against 81-82 k with the
-// shared-memory staging -- the L1 hit latency sits on every instruction's critical path.
-#define RDK_TABLES_L1 0
-#endif
-#ifndef RDK_FWD_STATIC
-// 1: the instruction body is compiled twice, for "the next instruction forwards my values" (they
-//    are produced directly in its child-2 operand registers) and for "it does not".
-// 0: one copy; forwarded values are moved into the next instruction's operand registers under a
-//    run-time test (8 E register moves), which halves the code the warps of an SM walk through.
-#define RDK_FWD_STATIC 1
-#endif
 #ifndef RDK_L2_PREFETCH_DIST
-// > 0: while instruction i computes, the CLV operands of instruction i + DIST are pulled into
-// L2 (prefetch.global.L2, no registers), so that the register loads issued one instruction
-// ahead find them there instead of paying the DRAM latency.  Measured on B200 (cfg2 step and
-// its 12.5 k-site shard, distances 2 / 3 / 5): no change -- the walk is not waiting on DRAM.
+// > 0: while instruction j computes, the CLV operand of instruction j + DIST is pulled into L2
+// (prefetch.global.L2, no registers).  See DESIGN.md for the measurement.
 #define RDK_L2_PREFETCH_DIST 0
 #endif
-// timing experiments only (tools/build_variant.sh): each removes one piece of the instruction
-// body -- the results are WRONG when any is set
-#ifndef RDK_X_NOEVAL
-#define RDK_X_NOEVAL 0
-#endif
-#ifndef RDK_X_NOWAIT
-#define RDK_X_NOWAIT 0
-#endif
-#ifndef RDK_X_NOLOAD
-#define RDK_X_NOLOAD 0
-#endif
-#ifndef RDK_X_NOSTORE
-#define RDK_X_NOSTORE 0
-#endif
-#ifndef RDK_LD256
-#define RDK_LD256 1  // 256-bit global loads/stores of CLV elements
-#endif
+#include "rdk_lower.hpp"
 #include <stdint.h>
 #include <type_traits>
 
@@ -467,86 +414,51 @@ __global__ void __launch_bounds__(64) pmat_expm_nonrev_kernel(const __grid_const
 // (site, category) element.  Elements are independent of each other (the
 // dependency between a parent CLV and its children is per site), so each warp
 // owns a contiguous range of elements and walks the WHOLE program on it with
-// no grid synchronisation: a full post-order traversal (n-1 CLV
-// operations + the root log-likelihood), a root move, or an entire placement
-// sweep is ONE launch.  Child CLVs produced a few instructions earlier by the
-// same warp are still in L2 (or in registers), so HBM sees each CLV written
-// once and mostly not read back.
+// no grid synchronisation: a full post-order traversal (n-1 CLV operations +
+// the root log-likelihood), a root move, or an entire placement sweep is ONE
+// launch.
 //
-// Thread mapping: element e = site*K + k.  A warp iteration `it` covers the 32/K
-// sites [it*32/K, (it+1)*32/K) = 32 consecutive 32-byte (4 x fp64) vectors = 1 KiB
-// contiguous per CLV per warp access.  Lane l handles site it*32/K + l % (32/K),
-// category k = l / (32/K): the lanes of a quarter warp share k, so their 128-bit
-// shared-memory reads of P hit ONE address per quarter warp (measured on B200:
-// 2 LSU cycles per read instead of 4 for the interleaved k = l % K mapping).
+// Thread mapping: element e = site*K + k; lane l of warp iteration `it` handles
+// e = 32*it + l, so a warp access is 32 consecutive 32-byte (4 x fp64) vectors =
+// 1 KiB contiguous per CLV.  Every thread carries E elements through each
+// instruction.
+//
+// What a warp keeps between instructions is ONE CLV value per element in
+// registers, `v` (rdk_lower.hpp): an instruction computes r = A(c1) o B(v),
+// with A a mat-vec on the CLV c1 that was LOADED while the previous instruction
+// computed, or a tip-table lookup, and B a mat-vec on v or a tip lookup.  A
+// regular operation leaves r in v (and stores it if a later instruction or the
+// caller reads it from memory); a placement evaluation (fEval) consumes r in
+// registers and leaves v as it was, so that the directed CLV it was computed
+// from is still there for the descent into the subtree.
+//
+// Tables.  The last warp of a CTA is the PRODUCER: it walks the program ahead of
+// the other (consumer) warps and fills a ring of kDepth slots in shared memory,
+// one slot per instruction = the 64-byte instruction itself + the two tables it
+// reads (P: 18K doubles of an inner child's branch, T: 64K doubles of a tip
+// child's branch), moved with cp.async.bulk and completed on the slot's `full`
+// mbarrier; a consumer warp that has finished an instruction arrives on the
+// slot's `empty` mbarrier.  The consumers of a CTA therefore drift up to kDepth
+// instructions apart, no warp ever waits for a table it asked for itself, and
+// there is no CTA-wide barrier after the prologue.
 // ---------------------------------------------------------------------------
-enum : unsigned {
-  kTip1 = 1u,      // child1 is a tip: 1 byte per site (4-bit state code)
-  kTip2 = 2u,      // child2 is a tip
-  kWrite = 4u,     // store the parent CLV (and parent scaler if present)
-  kEval = 8u,      // evaluate the root log-likelihood of the parent values
-  kLoadOnly = 16u, // no CLV arithmetic: parent values := CLV at c1 (root logL of
-                   // a stored CLV, corax_compute_root_loglikelihood)
-  kScale = 32u,    // parent has a scale buffer: apply 2^256 rescaling
-  // pre-decoded by the host when the program is finalised (finalize_program):
-  kFwd1 = 64u,     // c1 is the CLV the previous instruction produced: take it from registers
-  kFwd2 = 128u,    // same for c2
-  kLdS1 = 256u,    // load child1's scaler counts from memory
-  kLdS2 = 512u,    // load child2's scaler counts from memory
-  kFwdS1 = 1024u,  // child1's scaler is the one the previous instruction produced
-  kFwdS2 = 2048u,  // same for child2
-  kEvalScaler = 4096u,  // the evaluated root has a scale buffer (adds cnt * ln 2^-256)
-};
-
-// The flags that select code in the arithmetic of an instruction (the rest only steer the
-// operand loads).  For the combinations below -- the ones a post-order traversal and the
-// directed placement sweep are made of -- the K = 4, E = 2 kernel carries copies of the
-// instruction body compiled with the flags as CONSTANTS (no flag tests), once for "the next
-// instruction takes my result as its child 2" (the values are then produced directly in the
-// registers of the next instruction's operand: forwarding costs no register move) and once
-// for "it does not".  The host stores 2 * (index + 1) + forwards-out in Instr::kind
-// (finalize_program; 0 / 1 = flags decoded at run time), after ordering the two children
-// canonically -- a tip first, a forwarded CLV last -- which the commutative product
-// (P1 c1) o (P2 c2) allows without changing a bit of the result.
-constexpr unsigned kKindMask = kTip1 | kTip2 | kWrite | kEval | kLoadOnly | kScale | kFwd1 | kEvalScaler;
-constexpr unsigned kFastKinds[] = {
-    kWrite | kScale,                         // inner x inner
-    kWrite | kScale | kTip1,                 // tip x inner
-    kWrite | kScale | kTip1 | kTip2,         // tip x tip
-    kEval | kEvalScaler | kScale,            // sweep placement: evaluated in registers, nothing stored
-    kEval | kEvalScaler | kScale | kTip1,    // sweep placement on a tip branch
-};
-constexpr int kNumFastKinds = (int)(sizeof(kFastKinds) / sizeof(kFastKinds[0]));
-inline constexpr unsigned fast_kind_of(unsigned flags) {
-  for (int i = 0; i < kNumFastKinds; ++i)
-    if ((flags & kKindMask) == kFastKinds[i]) return (unsigned)i + 1u;
-  return 0u;
-}
-
 struct alignas(16) Instr {
-  double*         parent;
-  const void*     c1;
-  const void*     c2;
-  unsigned*       pscale;
-  const unsigned* c1scale;
-  const unsigned* c2scale;
-  const double*   P1;  // child1's table in its branch's pool slot: P (inner child) or T (tip child)
-  const double*   P2;
-  unsigned        flags;
-  unsigned        slot;  // eval slot (row of the partial-sum buffer)
-  unsigned        kind;  // 2 * (index into kFastKinds + 1, or 0) + (the next instruction forwards my result)
-  unsigned        tx;    // bytes of the two tables: b1 | b2 << 16 (0: no tables, kLoadOnly)
+  double*              parent;   // fWrite: where r is stored
+  const void*          c1;       // tip row (fTip1) or the inner CLV A loads
+  const unsigned char* c2;       // tip row (fTip2)
+  unsigned*            pscale;   // fWriteS
+  const unsigned*      c1scale;  // fCnt1
+  const double*        P1;       // the table A reads (in its branch's pool slot)   -- producer only
+  const double*        P2;       // the table B reads                               -- producer only
+  unsigned             flags;
+  unsigned             slot;     // eval slot (row of the partial-sum buffer)
 };
-static_assert(sizeof(Instr) == 80, "Instr layout");
+static_assert(sizeof(Instr) == 64, "Instr layout");
 
 constexpr int kProgInline = 8;
-#ifndef RDK_PROG_WINDOW
-#define RDK_PROG_WINDOW 256
-#endif
-constexpr int kProgWindow = RDK_PROG_WINDOW;  // instructions staged in shared memory at a time
 constexpr int kMaxChunks = 16;  // independent sub-programs one launch can run side by side
 struct ProgArgs {
-  const Instr*    prog;  // used when n_instr > kProgInline
+  const Instr*    prog;  // null: the program is inl[0..n_instr)
   int             n_instr;
   unsigned        nelem;    // sites * K on this shard
   unsigned        n_witer;  // ceil(nelem / 32)
@@ -565,57 +477,41 @@ struct ProgArgs {
   Instr           inl[kProgInline];
 };
 
+// the table ring of one CTA
+template <int K>
+struct Ring {
+  static constexpr int      kDepth = K <= 8 ? 8 : (K == 16 ? 4 : 2);
+  static constexpr int      kLogDepth = kDepth == 8 ? 3 : (kDepth == 4 ? 2 : 1);
+  static constexpr unsigned kTabBytes = kTabDoubles * K * 8;      // one child's table (the larger kind)
+  static constexpr unsigned kPBytes = kPTabDoubles * K * 8;       // P of an inner child
+  static constexpr unsigned kInstrBytes = 128;                    // the instruction, padded
+  static constexpr unsigned kSlotBytes = kInstrBytes + 2 * kTabBytes;
+  static constexpr unsigned kSmemBytes = kDepth * kSlotBytes + 2 * kDepth * 8;
+};
+
 struct d4 {
   double v[4];
 };
 
-__device__ __forceinline__ d4 ld_clv(const double* base, unsigned e) {
+__device__ __forceinline__ d4 ld_clv(const void* base, unsigned e) {
   // one 256-bit load per element (sm_100 LDG.E.256): a warp access covers 1 KiB
   // contiguous with every 32-byte sector used by exactly one lane.  L2-coherent
-  // (.cg): CLVs are read and written within one launch and never re-read by the
-  // same SM soon enough for L1 to help.
+  // (.cg): a CLV is read once per instruction, by one warp.
   const char* q = reinterpret_cast<const char*>(base) + (size_t)e * 32u;
   d4          r;
-#if RDK_LD256
   asm volatile("ld.global.cg.v4.f64 {%0,%1,%2,%3}, [%4];\n"
                : "=d"(r.v[0]), "=d"(r.v[1]), "=d"(r.v[2]), "=d"(r.v[3])
                : "l"(q));
-#else
-  const double2* q2 = reinterpret_cast<const double2*>(q);
-  double2        a = __ldcg(q2), b = __ldcg(q2 + 1);
-  r.v[0] = a.x;
-  r.v[1] = a.y;
-  r.v[2] = b.x;
-  r.v[3] = b.y;
-#endif
   return r;
 }
 __device__ __forceinline__ void st_clv(double* base, unsigned e, const d4& x) {
   char* q = reinterpret_cast<char*>(base) + (size_t)e * 32u;
-#if RDK_LD256
   asm volatile("st.global.cg.v4.f64 [%0], {%1,%2,%3,%4};\n" ::"l"(q), "d"(x.v[0]), "d"(x.v[1]), "d"(x.v[2]),
                "d"(x.v[3])
                : "memory");
-#else
-  double2* q2 = reinterpret_cast<double2*>(q);
-  __stcg(q2, make_double2(x.v[0], x.v[1]));
-  __stcg(q2 + 1, make_double2(x.v[2], x.v[3]));
-#endif
-}
-
-// a 16-byte read of a P / tip table entry
-__device__ __forceinline__ double2 ld_tab(const double2* p) {
-#if RDK_TABLES_L1
-  return __ldg(p);
-#else
-  return *p;
-#endif
 }
 __device__ __forceinline__ void prefetch_l2(const void* p) {
   asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p));
-}
-__device__ __forceinline__ void prefetch_l1(const void* p) {
-  asm volatile("prefetch.global.L1 [%0];\n" ::"l"(p));
 }
 
 // ---- mbarrier + bulk async copy (one elected thread moves a whole table) ----
@@ -650,503 +546,421 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
                : "memory");
 }
 
-// operands of one instruction for the E elements of a thread
-template <int E>
-struct Operands {
-  d4       c1[E], c2[E];  // inner children: the 4 state likelihoods
-  unsigned m1[E], m2[E];  // tip children: the state code
-  unsigned cnt1[E], cnt2[E];  // the children's scaler counts (kept apart so that nothing
-                              // waits on the loads before the instruction that needs them)
-};
+// high word of a double as a signed integer: for the likelihood values (finite, >= 0, or a
+// negative rounding residue) x < 2^-256  <=>  hi(x) < hi(2^-256), exactly (the low word of
+// 2^-256 is zero) -- the underflow test then runs on the integer pipe, not the fp64 pipe
+__device__ __forceinline__ int hi_word(double x) { return __double2hiint(x); }
+constexpr int kScaleThresholdHi = (1023 - 256) << 20;
 
-// Each WARP owns a contiguous range of warp iterations and walks the whole
-// program over it, one "pass" of E iterations at a time, independently of every
-// other warp (no CTA barrier per instruction).
-//  * the program is staged in shared memory in windows (the only CTA-level
-//    synchronisation: once per kProgWindow instructions, and only when the
-//    program does not fit one window);
-//  * per instruction and child, either the transition matrices P (inner child)
-//    or the tip table T (tip child) of the child's branch is moved into the
-//    warp's own shared double buffer by lane 0 with a bulk async copy
-//    (cp.async.bulk + mbarrier) while the previous instruction computes;
-//  * the global operands of instruction i+1 are loaded into registers BEFORE
-//    the arithmetic of instruction i (software pipelining, two register sets
-//    used in ping-pong), and when a child of i+1 is the CLV instruction i is
-//    producing -- the normal case in a post-order schedule -- it is forwarded in
-//    registers and never re-read (the host pre-decodes this into kFwd*);
-//  * there are no per-lane validity predicates: a lane without a site of its
-//    own (tail of the partition) redundantly recomputes the last site and
-//    stores the identical values (same warp, same instruction: no race); only
-//    the log-likelihood reduction masks it out.  The last pass of a warp whose
-//    range is not a multiple of E runs the instruction loop instantiated for
-//    the number of iterations it has left (NV < E) when the kernel is
-//    instantiated with TS (tail skip); without TS the slots without an iteration
-//    of their own redundantly recompute the last iteration of the range.  The
-//    host picks TS when no warp has a full last pass (choose_tail_skip): there
-//    the short loop pays; otherwise the slowest warps run full passes anyway and
-//    the second copy of the loop only costs instruction-cache misses (measured).
-template <int K, int E, int MAXT, int MINB, bool TS>
+template <int K, int E, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) clv_program_kernel(const __grid_constant__ ProgArgs a) {
   static_assert(32 % K == 0, "K must divide the warp size");
-  // the configuration RootDigger runs DNA data in (4 Gamma categories) carries the
-  // per-kind copies of the instruction body; the others decode the flags at run time
-  constexpr bool FAST = (K == 4 && (E == 2 || E == 4)) && RDK_FAST_KINDS;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  constexpr unsigned kTabBytes = kTabDoubles * K * 8;  // one child's slice of a table buffer
-  Instr*              s_prog = reinterpret_cast<Instr*>(smem_raw);
-  const unsigned      wib = threadIdx.x >> 5;
-  const unsigned      wpb = blockDim.x >> 5;
-  // per warp: [buf][child][kTabBytes] tables, then (after all warps' tables) [warp][buf] barriers
-  unsigned char*      s_tab = smem_raw + sizeof(Instr) * kProgWindow + (size_t)wib * 4 * kTabBytes;
-  unsigned long long* s_bar =
-      reinterpret_cast<unsigned long long*>(smem_raw + sizeof(Instr) * kProgWindow + (size_t)wpb * 4 * kTabBytes) +
-      2 * wib;
+  using R = Ring<K>;
+  constexpr unsigned D = R::kDepth;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned long long* const s_full = reinterpret_cast<unsigned long long*>(smem_raw + D * R::kSlotBytes);
+  unsigned long long* const s_empty = s_full + D;
 
   const unsigned tid = threadIdx.x;
   const unsigned lane = tid & 31u;
-  constexpr unsigned SPW = 32 / K;  // sites per warp iteration
-#if RDK_KSLOW
-  constexpr unsigned KSTRIDE = SPW;  // lane distance between two categories of a site
-  const unsigned     k = lane / SPW;
-  const unsigned     sl = lane % SPW;  // site within the warp iteration
-#else
-  constexpr unsigned KSTRIDE = 1;
-  const unsigned     k = lane % K;
-  const unsigned     sl = lane / K;
-#endif
-  const unsigned lane0 = lane - k * KSTRIDE;  // the k == 0 lane of this lane's site
-  unsigned       gmask = 0;                   // the K lanes that hold this lane's site
-#pragma unroll
-  for (int j = 0; j < K; ++j) gmask |= 1u << (j * KSTRIDE + lane0);
+  const unsigned wib = tid >> 5;
+  const unsigned n_cons = (blockDim.x >> 5) - 1u;  // consumer warps; warp n_cons is the producer
 
-  const unsigned gw = blockIdx.x * wpb + wib, nw = gridDim.x * wpb;
-  const unsigned it_begin = (unsigned)(((unsigned long long)a.n_witer * gw) / nw);
-  const unsigned it_end = (unsigned)(((unsigned long long)a.n_witer * (gw + 1)) / nw);
-  // every warp of the grid runs the same number of passes (the window barriers below are
-  // CTA-wide); a warp whose range is exhausted idles through the remaining ones
-  const unsigned passes = ((a.n_witer + nw - 1) / nw + E - 1) / E;
-  const unsigned last_site = a.nelem / K - 1;
-  const Instr*   prog = a.prog;
-  int            n_instr = a.n_instr;
+  const Instr* prog = a.prog;
+  unsigned     n_instr = (unsigned)a.n_instr;
+  const bool   inline_prog = a.prog == nullptr;  // <= kProgInline instructions, in the launch arguments
   if (a.n_chunks > 1) {
     prog += a.chunk_off[blockIdx.y];
-    n_instr = (int)(a.chunk_off[blockIdx.y + 1] - a.chunk_off[blockIdx.y]);
+    n_instr = a.chunk_off[blockIdx.y + 1] - a.chunk_off[blockIdx.y];
   }
-  const bool     multi_window = n_instr > kProgWindow;
 
-#if !RDK_TABLES_L1
-  if (lane == 0) {
-    mbar_init(&s_bar[0], 1);
-    mbar_init(&s_bar[1], 1);
+  // the CTA's range of warp iterations, split evenly over its consumer warps; every warp of the
+  // CTA runs the same number of passes (the ring is walked in lock step, kDepth apart at most)
+  const unsigned c_begin = (unsigned)(((unsigned long long)a.n_witer * blockIdx.x) / gridDim.x);
+  const unsigned c_end = (unsigned)(((unsigned long long)a.n_witer * (blockIdx.x + 1)) / gridDim.x);
+  const unsigned c_len = c_end - c_begin;
+  const unsigned passes = ((c_len + n_cons - 1) / n_cons + E - 1) / E;
+  const unsigned total = passes * n_instr;  // instructions this CTA's ring carries
+
+  if (tid == 0) {
+#pragma unroll
+    for (unsigned s = 0; s < D; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_empty[s], n_cons);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
-  __syncwarp();
-#endif
-  unsigned phase = 0;  // bit b: parity of the next completion of s_bar[b]
+  __syncthreads();
 
-#if RDK_TABLES_L1
-  // the whole warp: pull the lines of P or T of both children of `in` into L1 (lane l
-  // takes the l-th 128-byte line of each table; a tip table is 16 lines at K = 4)
-  auto prefetch_tables = [&](const Instr& in, unsigned) {
-    const unsigned tx = in.tx;
-    if (tx == 0) return;
-    const unsigned       b1 = tx & 0xffffu, b2 = tx >> 16;
-    const unsigned char* s1 = reinterpret_cast<const unsigned char*>(in.P1);
-    const unsigned char* s2 = reinterpret_cast<const unsigned char*>(in.P2);
-    for (unsigned off = lane * 128u; off < b1 + 127u; off += 32u * 128u) prefetch_l1(s1 + min(off, b1 - 1u));
-    for (unsigned off = lane * 128u; off < b2 + 127u; off += 32u * 128u) prefetch_l1(s2 + min(off, b2 - 1u));
-  };
-#else
-  // one thread: move P or T of both children of `in` into buffer `buf`
-  auto prefetch_tables = [&](const Instr& in, unsigned buf) {
-    unsigned long long* bar = &s_bar[buf];
-    const unsigned      tx = in.tx;  // sizes and table addresses are pre-computed by the host
-    if (tx == 0) {
-      mbar_arrive(bar);
-      return;
+  if (wib == n_cons) {
+    // ------------------------------- producer warp -------------------------------------
+    // lane l takes instructions j = base + l: it reads its instruction from global memory (or
+    // the launch arguments) ahead of time, then the lanes fill their slots in order
+    for (unsigned base = 0; base < total; base += 32u) {
+      const unsigned j = base + lane;
+      int4           w0 = make_int4(0, 0, 0, 0), w1 = w0, w2 = w0, w3 = w0;
+      if (j < total) {
+        const unsigned idx = j % n_instr;
+        const int4*    src = reinterpret_cast<const int4*>(inline_prog ? &a.inl[idx] : &prog[idx]);
+        w0 = src[0];
+        w1 = src[1];
+        w2 = src[2];
+        w3 = src[3];
+      }
+      const unsigned cnt = min(32u, total - base);
+      for (unsigned t = 0; t < cnt; ++t) {
+        if (lane == t) {
+          const unsigned s = j & (D - 1u);
+          mbar_wait(&s_empty[s], ((j >> R::kLogDepth) & 1u) ^ 1u);
+          unsigned char* slot = smem_raw + s * R::kSlotBytes;
+          int4*          dst = reinterpret_cast<int4*>(slot);
+          dst[0] = w0;
+          dst[1] = w1;
+          dst[2] = w2;
+          dst[3] = w3;
+          const unsigned fl = (unsigned)w3.z;
+          unsigned       b1 = 0, b2 = 0;
+          if (!(fl & (fLoadV | fNop))) {
+            b1 = (fl & fTip1) ? R::kTabBytes : R::kPBytes;
+            b2 = (fl & fTip2) ? R::kTabBytes : R::kPBytes;
+          }
+          // the arrive releases the plain stores above to the consumers that acquire the barrier
+          mbar_expect_tx(&s_full[s], b1 + b2);
+          if (b1) {
+            const unsigned long long p1 = ((unsigned long long)(unsigned)w2.w << 32) | (unsigned)w2.z;
+            bulk_g2s(slot + R::kInstrBytes, reinterpret_cast<const void*>(p1), b1, &s_full[s]);
+          }
+          if (b2) {
+            const unsigned long long p2 = ((unsigned long long)(unsigned)w3.y << 32) | (unsigned)w3.x;
+            bulk_g2s(slot + R::kInstrBytes + R::kTabBytes, reinterpret_cast<const void*>(p2), b2, &s_full[s]);
+          }
+        }
+        __syncwarp();
+      }
     }
-    const unsigned b1 = tx & 0xffffu, b2 = tx >> 16;
-    mbar_expect_tx(bar, b1 + b2);
-    unsigned char* dst = s_tab + (size_t)buf * 2 * kTabBytes;
-    bulk_g2s(dst, in.P1, b1, bar);
-    bulk_g2s(dst + kTabBytes, in.P2, b2, bar);
-  };
-#endif
+    return;
+  }
 
+  // --------------------------------- consumer warps --------------------------------------
+  constexpr unsigned SPW = 32 / K;  // sites per warp iteration
+  const unsigned     k = lane % K;
+  const unsigned     sl = lane / K;
+  const unsigned     lane0 = lane - k;  // the k == 0 lane of this lane's site
+  unsigned           gmask = 0;         // the K lanes that hold this lane's site
+#pragma unroll
+  for (int j = 0; j < K; ++j) gmask |= 1u << (j + lane0);
+
+  const unsigned it_begin = c_begin + (unsigned)(((unsigned long long)c_len * wib) / n_cons);
+  const unsigned it_end = c_begin + (unsigned)(((unsigned long long)c_len * (wib + 1)) / n_cons);
+  const unsigned last_site = a.nelem / K - 1;
+
+  auto slot_of = [&](unsigned j) -> const unsigned char* { return smem_raw + (j & (D - 1u)) * R::kSlotBytes; };
+  auto wait_full = [&](unsigned j) { mbar_wait(&s_full[j & (D - 1u)], (j >> R::kLogDepth) & 1u); };
+  auto release = [&](unsigned j) {
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&s_empty[j & (D - 1u)]);
+  };
+
+  d4       v[E];     // the CLV value carried from instruction to instruction
+  unsigned vcnt[E];  // its scaler counts
+  d4       c1r[E];   // the loaded child-1 CLV of the instruction about to run
+  unsigned m1[E], m2n[E], cnt1[E];  // its tip codes / child-1 scaler counts
+#pragma unroll
+  for (int u = 0; u < E; ++u) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[u].v[i] = c1r[u].v[i] = 0.0;
+    vcnt[u] = cnt1[u] = 0;
+    m1[u] = m2n[u] = 15u;  // code 15: all-zero table row
+  }
+
+  unsigned jg = 0;  // position in the CTA's instruction stream (all passes)
   for (unsigned pass = 0; pass < passes; ++pass) {
-    const bool active = it_begin + pass * E < it_end;  // warp-uniform
-    unsigned   it[E], e[E], site[E];
+    if (!(it_begin + pass * E < it_end)) {
+      // no iteration of its own in this pass: keep the ring protocol going
+      for (unsigned ii = 0; ii < n_instr; ++ii, ++jg) {
+        wait_full(jg);
+        release(jg);
+      }
+      continue;
+    }
+    // slots without an iteration of their own (the warp's last pass) redundantly recompute the
+    // warp's last iteration and store the identical values (same thread: no race); lanes
+    // without a site of their own (tail of the partition) do the same with the last site
+    unsigned it[E], e[E], site[E], wgt[E];
 #pragma unroll
     for (int u = 0; u < E; ++u) {
       const unsigned i0 = it_begin + pass * E + u;
-      it[u] = (i0 < it_end || !active) ? i0 : it_end - 1;
+      it[u] = i0 < it_end ? i0 : it_end - 1;
       unsigned st = it[u] * SPW + sl;
       if (st > last_site) st = last_site;
       site[u] = st;
-#if RDK_KSLOW
-      e[u] = (st / SPW) * 32u + k * SPW + (st % SPW);  // blocked CLV layout [block][cat][site in block]
-#else
       e[u] = st * K + k;
-#endif
+      wgt[u] = __ldg(a.weights + st);
     }
 
     // issue the global loads of one instruction's operands
-    auto load_operands = [&](auto nvc, const Instr& in, unsigned fl, Operands<E>& o) __attribute__((always_inline)) {
-      constexpr int NV = decltype(nvc)::value;  // slots with an iteration of their own
-      if (fl & kTip1) {
+    auto load_operands = [&](const Instr& in) __attribute__((always_inline)) {
+      const unsigned fl = in.flags;
+      if (fl & fTip1) {
         const unsigned char* t = reinterpret_cast<const unsigned char*>(in.c1);
 #pragma unroll
-        for (int u = 0; u < NV; ++u) o.m1[u] = __ldg(t + site[u]);
-      } else if (!(fl & kFwd1) && (fl & (kLoadOnly | kFwd2)) != (kLoadOnly | kFwd2)) {
-        const double* g = reinterpret_cast<const double*>(in.c1);
+        for (int u = 0; u < E; ++u) m1[u] = __ldg(t + site[u]);
+      } else if (!(fl & fNop)) {
+        const void* g = in.c1;
 #pragma unroll
-        for (int u = 0; u < NV; ++u) o.c1[u] = ld_clv(g, e[u]);
+        for (int u = 0; u < E; ++u) c1r[u] = ld_clv(g, e[u]);
       }
-      if (fl & kTip2) {
-        const unsigned char* t = reinterpret_cast<const unsigned char*>(in.c2);
+      if (fl & fTip2) {
+        const unsigned char* t = in.c2;
 #pragma unroll
-        for (int u = 0; u < NV; ++u) o.m2[u] = __ldg(t + site[u]);
-      } else if (!(fl & (kFwd2 | kLoadOnly))) {
-        const double* g = reinterpret_cast<const double*>(in.c2);
-#pragma unroll
-        for (int u = 0; u < NV; ++u) o.c2[u] = ld_clv(g, e[u]);
+        for (int u = 0; u < E; ++u) m2n[u] = __ldg(t + site[u]);
       }
 #pragma unroll
-      for (int u = 0; u < NV; ++u) o.cnt1[u] = o.cnt2[u] = 0;
-      if (fl & kLdS1) {
+      for (int u = 0; u < E; ++u) cnt1[u] = 0;
+      if (fl & fCnt1) {
         const unsigned* s1 = in.c1scale;
 #pragma unroll
-        for (int u = 0; u < NV; ++u) o.cnt1[u] = __ldcg(s1 + site[u]);
-      }
-      if (fl & kLdS2) {
-        const unsigned* s2 = in.c2scale;
-#pragma unroll
-        for (int u = 0; u < NV; ++u) o.cnt2[u] = __ldcg(s2 + site[u]);
+        for (int u = 0; u < E; ++u) cnt1[u] = __ldcg(s1 + site[u]);
       }
     };
 
-    // pattern weights of this pass's sites (the same for every instruction of the program)
-    unsigned wgt[E];
+    // 2^256 rescaling of the values of one instruction (SURVEY A-3): a site is rescaled when all
+    // its K*4 values are below 2^-256
+    auto rescale = [&](d4(&r)[E], unsigned(&cnt)[E]) __attribute__((always_inline)) {
 #pragma unroll
-    for (int u = 0; u < E; ++u) wgt[u] = __ldg(a.weights + site[u]);
-
-    // one instruction: `cur` holds its operands, the operands of the next instruction are
-    // loaded into `nxt`.  A child forwarded from the previous instruction is always child 2
-    // (canonical order) and is already in cur.c2: the previous instruction produced its
-    // values there.  flc: the instruction's kKindMask flags as a compile-time constant (a
-    // fast kind), or < 0: read at run time.  fwdc: the next instruction takes this one's
-    // values as its child 2; `v` is then nxt.c2, otherwise a scratch array.  bufc: the
-    // parity of the instruction's position in the window = its table buffer.
-    auto step = [&](auto nvc, auto flc, auto fwdc, auto bufc, int ii, int wn, Operands<E>& cur, Operands<E>& nxt,
-                    d4(&v)[E]) __attribute__((always_inline)) {
-      constexpr int      NV = decltype(nvc)::value;
-      constexpr int      F = decltype(flc)::value;
-      constexpr int      FWDMODE = decltype(fwdc)::value;  // 0: not forwarded, 1: forwarded (v is nxt.c2), 2: run time
-      constexpr bool     FWDOUT = FWDMODE == 1;
-      constexpr unsigned buf = decltype(bufc)::value;
-      const bool more = ii + 1 < wn;
-#if RDK_TABLES_L1
-      if (more) prefetch_tables(s_prog[ii + 1], 0);
-#else
-      __syncwarp();  // every lane has finished instruction ii-1 (frees the other table buffer)
-      if (more && lane == 0) prefetch_tables(s_prog[ii + 1], buf ^ 1u);
-#endif
-      const Instr&   in = s_prog[ii];
-      const unsigned fl = F < 0 ? in.flags : (unsigned)F;
-      unsigned       nfl = 0;
-      if (FWDOUT || more) {  // FWDOUT implies a next instruction
-        const Instr& nx = s_prog[ii + 1];
-        nfl = FWDMODE == 2 ? nx.flags : (FWDOUT ? (nx.flags | kFwd2) : (nx.flags & ~kFwd2));
-        if (!RDK_X_NOLOAD) load_operands(nvc, nx, nfl, nxt);
-      }
-#if RDK_L2_PREFETCH_DIST > 0
-      if (ii + RDK_L2_PREFETCH_DIST < wn) {
-        const Instr&   fx = s_prog[ii + RDK_L2_PREFETCH_DIST];
-        const unsigned ffl = fx.flags;
-        if (!(ffl & (kTip1 | kFwd1)) && (ffl & (kLoadOnly | kFwd2)) != (kLoadOnly | kFwd2)) {
-          const char* g = reinterpret_cast<const char*>(fx.c1);
+      for (int u = 0; u < E; ++u) {
+        const int  mx = max(max(hi_word(r[u].v[0]), hi_word(r[u].v[1])), max(hi_word(r[u].v[2]), hi_word(r[u].v[3])));
+        const unsigned m = __ballot_sync(0xffffffffu, mx < kScaleThresholdHi);
+        if ((m & gmask) == gmask) {
 #pragma unroll
-          for (int u = 0; u < NV; ++u) prefetch_l2(g + (size_t)e[u] * 32u);
-        }
-        if (!(ffl & (kTip2 | kFwd2 | kLoadOnly))) {
-          const char* g = reinterpret_cast<const char*>(fx.c2);
-#pragma unroll
-          for (int u = 0; u < NV; ++u) prefetch_l2(g + (size_t)e[u] * 32u);
+          for (int i = 0; i < 4; ++i) r[u].v[i] = dmul(r[u].v[i], RDK_SCALE_FACTOR);
+          cnt[u] += 1;
         }
       }
-#endif
-#if RDK_TABLES_L1
-      const unsigned char* tab1 = reinterpret_cast<const unsigned char*>(in.P1);
-      const unsigned char* tab2 = reinterpret_cast<const unsigned char*>(in.P2);
-#else
-#if !RDK_X_NOWAIT
-      mbar_wait(&s_bar[buf], (phase >> buf) & 1u);  // tables(ii) have landed
-#endif
-      phase ^= 1u << buf;
-      const unsigned char* tab1 = s_tab + (size_t)buf * 2 * kTabBytes;
-      const unsigned char* tab2 = tab1 + kTabBytes;
-#endif
+    };
 
-      d4 a1[E], a2[E];
+    // root log-likelihood of the values r (SURVEY A-4) into eval slot in.slot
+    auto evaluate = [&](const Instr& in, const unsigned fl, const d4(&r)[E], const unsigned(&cnt)[E])
+                        __attribute__((always_inline)) {
+      // every lane of a site gathers the K category terms in category order
+      double term[E];
 #pragma unroll
-      for (int u = 0; u < NV; ++u) {
-        a2[u] = cur.c2[u];
-        a1[u] = cur.c1[u];
-        if (F < 0 && (fl & kFwd1)) a1[u] = cur.c2[u];  // both children are the forwarded CLV
+      for (int u = 0; u < E; ++u) {
+        double t = dmul(a.pi[0], r[u].v[0]);
+        t = dfma(a.pi[1], r[u].v[1], t);
+        t = dfma(a.pi[2], r[u].v[2], t);
+        t = dfma(a.pi[3], r[u].v[3], t);
+        double tm = dmul(a.w[0], __shfl_sync(0xffffffffu, t, lane0));
+#pragma unroll
+        for (int kk = 1; kk < K; ++kk) {
+          double tk = __shfl_sync(0xffffffffu, t, lane0 + kk);
+          tm = dfma(a.w[kk], tk, tm);
+        }
+        term[u] = tm;
       }
-      unsigned cnt[E];
+      const unsigned eslot = in.slot;
+      if constexpr (E <= K) {
+        // the K lanes of a site hold the same term: lane k takes the logarithm of the
+        // site of slot u = k, so that ONE pass through rd_log serves all E slots
+        double   x = term[0];
+        unsigned cn = cnt[0], st = site[0], iw = it[0], wg = wgt[0];
 #pragma unroll
-      for (int u = 0; u < NV; ++u) cnt[u] = cur.cnt1[u] + cur.cnt2[u];
-      if (fl & kLoadOnly) {
+        for (int u = 1; u < E; ++u)
+          if (k == (unsigned)u) {
+            x = term[u];
+            cn = cnt[u];
+            st = site[u];
+            iw = it[u];
+            wg = wgt[u];
+          }
+        double l = 0.0;
+        if (k < (unsigned)E && iw * SPW + sl <= last_site) {
+          l = rd_log(x);
+          if (fl & fEvalScaler) l = dadd(l, dmul((double)cn, RDK_LOG_SCALE_THRESHOLD));
+          l = dmul(l, (double)wg);
+          if (a.persite && eslot == 0) a.persite[st] = l;
+        }
+        // canonical tree over the 32/K sites of a warp iteration (the lanes of equal k)
 #pragma unroll
-        for (int u = 0; u < NV; ++u) v[u] = (fl & kFwd2) ? a2[u] : a1[u];  // kFwd2: the CLV just produced
+        for (int off2 = 1; off2 < (int)SPW; off2 <<= 1) l = dadd(l, __shfl_xor_sync(0xffffffffu, l, off2 * K));
+        if (sl == 0 && k < (unsigned)E) a.partials[(size_t)eslot * a.partial_stride + iw] = l;
       } else {
-        // child 1
-        if (fl & kTip1) {
 #pragma unroll
-          for (int u = 0; u < NV; ++u) {
-            const double2* t = reinterpret_cast<const double2*>(tab1 + (cur.m1[u] * K + k) * 32u);
-            const double2  lo = ld_tab(t), hi = ld_tab(t + 1);
-            v[u].v[0] = lo.x;
-            v[u].v[1] = lo.y;
-            v[u].v[2] = hi.x;
-            v[u].v[3] = hi.y;
+        for (int u = 0; u < E; ++u) {
+          double l = 0.0;
+          if (k == 0 && it[u] * SPW + sl <= last_site) {
+            l = rd_log(term[u]);
+            if (fl & fEvalScaler) l = dadd(l, dmul((double)cnt[u], RDK_LOG_SCALE_THRESHOLD));
+            l = dmul(l, (double)wgt[u]);
+            if (a.persite && eslot == 0) a.persite[site[u]] = l;
           }
-        } else {
-          const double2* p = reinterpret_cast<const double2*>(tab1 + k * (kPTabDoubles * 8));
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const double2 p01 = ld_tab(p + i * 2), p23 = ld_tab(p + i * 2 + 1);
-#pragma unroll
-            for (int u = 0; u < NV; ++u) {
-              double s = dmul(p01.x, a1[u].v[0]);
-              s = dfma(p01.y, a1[u].v[1], s);
-              s = dfma(p23.x, a1[u].v[2], s);
-              s = dfma(p23.y, a1[u].v[3], s);
-              v[u].v[i] = s;
-            }
-          }
+          for (int off2 = 1; off2 < (int)SPW; off2 <<= 1) l = dadd(l, __shfl_xor_sync(0xffffffffu, l, off2 * K));
+          if (lane == 0) a.partials[(size_t)eslot * a.partial_stride + it[u]] = l;
         }
-        // child 2
-        if (fl & kTip2) {
+      }
+    };
+
+    // pipeline prologue: the operands of the pass's first instruction
+    wait_full(jg);
+    load_operands(*reinterpret_cast<const Instr*>(slot_of(jg)));
+
+    for (unsigned ii = 0; ii < n_instr; ++ii, ++jg) {
+      const unsigned char* slot = slot_of(jg);
+      const Instr&         in = *reinterpret_cast<const Instr*>(slot);
+      const unsigned       fl = in.flags;
+      const unsigned char* tab1 = slot + R::kInstrBytes;
+      const unsigned char* tab2 = tab1 + R::kTabBytes;
+      const bool           main_op = !(fl & (fLoadV | fNop));
+
+      d4       y[E];     // B(child 2), then (placement evaluations) r
+      unsigned cnt[E];   // scaler counts of r
+      unsigned m2c[E];   // this instruction's child-2 tip codes (m2n is reloaded below)
 #pragma unroll
-          for (int u = 0; u < NV; ++u) {
-            const double2* t = reinterpret_cast<const double2*>(tab2 + (cur.m2[u] * K + k) * 32u);
-            const double2  lo = ld_tab(t), hi = ld_tab(t + 1);
-            v[u].v[0] = dmul(v[u].v[0], lo.x);
-            v[u].v[1] = dmul(v[u].v[1], lo.y);
-            v[u].v[2] = dmul(v[u].v[2], hi.x);
-            v[u].v[3] = dmul(v[u].v[3], hi.y);
+      for (int u = 0; u < E; ++u) {
+        m2c[u] = m2n[u];
+        cnt[u] = cnt1[u] + ((fl & fCnt2V) ? vcnt[u] : 0u);
+      }
+
+      // ---- phase 1: y = B(child 2) ------------------------------------------------------
+      if (main_op) {
+        if (fl & fTip2) {
+#pragma unroll
+          for (int u = 0; u < E; ++u) {
+            const double2* t = reinterpret_cast<const double2*>(tab2 + (m2c[u] * K + k) * 32u);
+            const double2  lo = t[0], hi = t[1];
+            y[u].v[0] = lo.x;
+            y[u].v[1] = lo.y;
+            y[u].v[2] = hi.x;
+            y[u].v[3] = hi.y;
           }
         } else {
           const double2* p = reinterpret_cast<const double2*>(tab2 + k * (kPTabDoubles * 8));
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const double2 p01 = ld_tab(p + i * 2), p23 = ld_tab(p + i * 2 + 1);
+            const double2 p01 = p[i * 2], p23 = p[i * 2 + 1];
 #pragma unroll
-            for (int u = 0; u < NV; ++u) {
-              double s = dmul(p01.x, a2[u].v[0]);
-              s = dfma(p01.y, a2[u].v[1], s);
-              s = dfma(p23.x, a2[u].v[2], s);
-              s = dfma(p23.y, a2[u].v[3], s);
-              v[u].v[i] = dmul(v[u].v[i], s);
+            for (int u = 0; u < E; ++u) {
+              double s = dmul(p01.x, v[u].v[0]);
+              s = dfma(p01.y, v[u].v[1], s);
+              s = dfma(p23.x, v[u].v[2], s);
+              s = dfma(p23.y, v[u].v[3], s);
+              y[u].v[i] = s;
             }
           }
         }
       }
-      if (fl & kScale) {
-        // (a branch-free form -- all E ballots first, then a multiplication by 2^256 or 1.0 --
-        // was measured on B200: 3 % faster on a 12.5 k-site shard, 1.5 % slower at 100 k)
+
+      // ---- phase 2: r = A(child 1) o y, into v (regular operation) or y (evaluation) -----
+      const bool keep_v = (fl & fEval) != 0;
+      if (main_op) {
+        if (fl & fTip1) {
 #pragma unroll
-        for (int u = 0; u < NV; ++u) {
-          const bool small = (v[u].v[0] < RDK_SCALE_THRESHOLD) && (v[u].v[1] < RDK_SCALE_THRESHOLD) &&
-                             (v[u].v[2] < RDK_SCALE_THRESHOLD) && (v[u].v[3] < RDK_SCALE_THRESHOLD);
-          const unsigned m = __ballot_sync(0xffffffffu, small);
-          if ((m & gmask) == gmask) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) v[u].v[i] = dmul(v[u].v[i], RDK_SCALE_FACTOR);
-            cnt[u] += 1;
-          }
-        }
-      }
-      if ((fl & kWrite) && !RDK_X_NOSTORE) {
-        double* par = in.parent;
-#pragma unroll
-        for (int u = 0; u < NV; ++u) st_clv(par, e[u], v[u]);
-        unsigned* ps = in.pscale;
-        if (ps && k == 0) {
-#pragma unroll
-          for (int u = 0; u < NV; ++u) __stcg(ps + site[u], cnt[u]);
-        }
-      }
-      if (FWDMODE == 2 && (nfl & kFwd2)) {
-#pragma unroll
-        for (int u = 0; u < NV; ++u) nxt.c2[u] = v[u];
-      }
-      // the scaler counts of a forwarded child of instruction ii+1 (its values are `v`)
-      if (nfl & kFwdS1) {
-#pragma unroll
-        for (int u = 0; u < NV; ++u) nxt.cnt1[u] = cnt[u];
-      }
-      if (nfl & kFwdS2) {
-#pragma unroll
-        for (int u = 0; u < NV; ++u) nxt.cnt2[u] = cnt[u];
-      }
-      if ((fl & kEval) && !RDK_X_NOEVAL) {
-        // every lane of a site gathers the K category terms in category order
-        double term[E];
-#pragma unroll
-        for (int u = 0; u < NV; ++u) {
-          double t = dmul(a.pi[0], v[u].v[0]);
-          t = dfma(a.pi[1], v[u].v[1], t);
-          t = dfma(a.pi[2], v[u].v[2], t);
-          t = dfma(a.pi[3], v[u].v[3], t);
-          double tm = dmul(a.w[0], __shfl_sync(0xffffffffu, t, lane0));
-#pragma unroll
-          for (int kk = 1; kk < K; ++kk) {
-            double tk = __shfl_sync(0xffffffffu, t, lane0 + kk * KSTRIDE);
-            tm = dfma(a.w[kk], tk, tm);
-          }
-          term[u] = tm;
-        }
-        if constexpr (NV <= K) {
-          // the K lanes of a site hold the same term: lane k takes the logarithm of the
-          // site of slot u = k, so that ONE pass through rd_log serves all NV slots
-          double   x = term[0];
-          unsigned cn = cnt[0], st = site[0], iw = it[0], wg = wgt[0];
-#pragma unroll
-          for (int u = 1; u < NV; ++u)
-            if (k == (unsigned)u) {
-              x = term[u];
-              cn = cnt[u];
-              st = site[u];
-              iw = it[u];
-              wg = wgt[u];
+          for (int u = 0; u < E; ++u) {
+            const double2* t = reinterpret_cast<const double2*>(tab1 + (m1[u] * K + k) * 32u);
+            const double2  lo = t[0], hi = t[1];
+            if (keep_v) {
+              y[u].v[0] = dmul(lo.x, y[u].v[0]);
+              y[u].v[1] = dmul(lo.y, y[u].v[1]);
+              y[u].v[2] = dmul(hi.x, y[u].v[2]);
+              y[u].v[3] = dmul(hi.y, y[u].v[3]);
+            } else {
+              v[u].v[0] = dmul(lo.x, y[u].v[0]);
+              v[u].v[1] = dmul(lo.y, y[u].v[1]);
+              v[u].v[2] = dmul(hi.x, y[u].v[2]);
+              v[u].v[3] = dmul(hi.y, y[u].v[3]);
             }
-          double l = 0.0;
-          if (k < (unsigned)NV && iw * SPW + sl <= last_site) {
-            l = rd_log(x);
-            if (fl & kEvalScaler) l = dadd(l, dmul((double)cn, RDK_LOG_SCALE_THRESHOLD));
-            l = dmul(l, (double)wg);
-            if (a.persite && in.slot == 0) a.persite[st] = l;
           }
-          // canonical tree over the 32/K sites of a warp iteration (the lanes of equal k)
-#pragma unroll
-          for (int off2 = 1; off2 < (int)SPW; off2 <<= 1)
-            l = dadd(l, __shfl_xor_sync(0xffffffffu, l, off2 * (KSTRIDE == 1 ? K : 1)));
-          if (sl == 0 && k < (unsigned)NV) a.partials[(size_t)in.slot * a.partial_stride + iw] = l;
         } else {
+          const double2* p = reinterpret_cast<const double2*>(tab1 + k * (kPTabDoubles * 8));
 #pragma unroll
-          for (int u = 0; u < NV; ++u) {
-            double l = 0.0;
-            if (k == 0 && it[u] * SPW + sl <= last_site) {
-              l = rd_log(term[u]);
-              if (fl & kEvalScaler) l = dadd(l, dmul((double)cnt[u], RDK_LOG_SCALE_THRESHOLD));
-              l = dmul(l, (double)wgt[u]);
-              if (a.persite && in.slot == 0) a.persite[site[u]] = l;
+          for (int i = 0; i < 4; ++i) {
+            const double2 p01 = p[i * 2], p23 = p[i * 2 + 1];
+#pragma unroll
+            for (int u = 0; u < E; ++u) {
+              double s = dmul(p01.x, c1r[u].v[0]);
+              s = dfma(p01.y, c1r[u].v[1], s);
+              s = dfma(p23.x, c1r[u].v[2], s);
+              s = dfma(p23.y, c1r[u].v[3], s);
+              if (keep_v)
+                y[u].v[i] = dmul(s, y[u].v[i]);
+              else
+                v[u].v[i] = dmul(s, y[u].v[i]);
             }
-#pragma unroll
-            for (int off2 = 1; off2 < (int)SPW; off2 <<= 1)
-              l = dadd(l, __shfl_xor_sync(0xffffffffu, l, off2 * (KSTRIDE == 1 ? K : 1)));
-            if (lane == 0) a.partials[(size_t)in.slot * a.partial_stride + it[u]] = l;
           }
         }
-      }
-    };
-
-    // run instruction ii through the copy of the body compiled for its kind
-    auto dispatch = [&](auto nvc, auto bufc, int ii, int wn, Operands<E>& cur, Operands<E>& nxt)
-                        __attribute__((always_inline)) {
-      using IC = std::integral_constant<int, -1>;
-      using std::integral_constant;
-      using no_fwd = integral_constant<int, 0>;
-      using fwd = integral_constant<int, 1>;
-      d4             scratch[E];
-      const unsigned kind = s_prog[ii].kind;
-      // (short tail passes, NV < E, run the run-time decoded body: they are rare)
-      if constexpr (FAST && (decltype(nvc)::value == E || RDK_FAST_KINDS >= 2)) {
-        switch (kind) {
-          case 2: step(nvc, integral_constant<int, (int)kFastKinds[0]>{}, no_fwd{}, bufc, ii, wn, cur, nxt, scratch); break;
-          case 3: step(nvc, integral_constant<int, (int)kFastKinds[0]>{}, fwd{}, bufc, ii, wn, cur, nxt, nxt.c2); break;
-          case 4: step(nvc, integral_constant<int, (int)kFastKinds[1]>{}, no_fwd{}, bufc, ii, wn, cur, nxt, scratch); break;
-          case 5: step(nvc, integral_constant<int, (int)kFastKinds[1]>{}, fwd{}, bufc, ii, wn, cur, nxt, nxt.c2); break;
-          case 6: step(nvc, integral_constant<int, (int)kFastKinds[2]>{}, no_fwd{}, bufc, ii, wn, cur, nxt, scratch); break;
-          case 7: step(nvc, integral_constant<int, (int)kFastKinds[2]>{}, fwd{}, bufc, ii, wn, cur, nxt, nxt.c2); break;
-          case 8: step(nvc, integral_constant<int, (int)kFastKinds[3]>{}, no_fwd{}, bufc, ii, wn, cur, nxt, scratch); break;
-          case 10: step(nvc, integral_constant<int, (int)kFastKinds[4]>{}, no_fwd{}, bufc, ii, wn, cur, nxt, scratch); break;
-          case 1: step(nvc, IC{}, fwd{}, bufc, ii, wn, cur, nxt, nxt.c2); break;
-          default: step(nvc, IC{}, no_fwd{}, bufc, ii, wn, cur, nxt, scratch); break;
+      } else if (fl & fLoadV) {
+#pragma unroll
+        for (int u = 0; u < E; ++u) {
+          v[u] = c1r[u];
+          vcnt[u] = cnt1[u];
         }
-      } else if constexpr (RDK_FWD_STATIC) {
-        if (kind & 1u)
-          step(nvc, IC{}, fwd{}, bufc, ii, wn, cur, nxt, nxt.c2);
-        else
-          step(nvc, IC{}, no_fwd{}, bufc, ii, wn, cur, nxt, scratch);
-      } else {
-        step(nvc, IC{}, integral_constant<int, 2>{}, bufc, ii, wn, cur, nxt, scratch);
       }
-    };
 
-    // the instruction loop over one staged window, for NV slots
-    auto run_window = [&](auto nvc, int wn) __attribute__((always_inline)) {
-      using std::integral_constant;
-#if RDK_TABLES_L1
-      prefetch_tables(s_prog[0], 0);
-#else
-      __syncwarp();
-      if (lane == 0) prefetch_tables(s_prog[0], 0);
+      // ---- the operands of the next instruction of this pass (c1r, m1, cnt1 are dead now) ---
+      if (ii + 1 < n_instr) {
+        wait_full(jg + 1);
+        load_operands(*reinterpret_cast<const Instr*>(slot_of(jg + 1)));
+#if RDK_L2_PREFETCH_DIST > 1
+        if (ii + RDK_L2_PREFETCH_DIST < n_instr && RDK_L2_PREFETCH_DIST < (int)D) {
+          wait_full(jg + RDK_L2_PREFETCH_DIST);
+          const Instr& fx = *reinterpret_cast<const Instr*>(slot_of(jg + RDK_L2_PREFETCH_DIST));
+          if (!(fx.flags & (fTip1 | fNop))) {
+            const char* g = reinterpret_cast<const char*>(fx.c1);
+#pragma unroll
+            for (int u = 0; u < E; ++u) prefetch_l2(g + (size_t)e[u] * 32u);
+          }
+        }
 #endif
-      Operands<E> opA, opB;
-#pragma unroll
-      for (int u = 0; u < E; ++u) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) opA.c1[u].v[i] = opA.c2[u].v[i] = opB.c1[u].v[i] = opB.c2[u].v[i] = 0.0;
-        opA.m1[u] = opA.m2[u] = opB.m1[u] = opB.m2[u] = 15u;  // code 15: all-zero table row
-        opA.cnt1[u] = opA.cnt2[u] = opB.cnt1[u] = opB.cnt2[u] = 0;
       }
-      // the first instruction of a window never carries kFwd* (finalize_program)
-      load_operands(nvc, s_prog[0], s_prog[0].flags, opA);
-      int ii = 0;
-      for (; ii + 1 < wn; ii += 2) {
-        dispatch(nvc, integral_constant<unsigned, 0>{}, ii, wn, opA, opB);
-        dispatch(nvc, integral_constant<unsigned, 1>{}, ii + 1, wn, opB, opA);
-      }
-      if (ii < wn) dispatch(nvc, integral_constant<unsigned, 0>{}, ii, wn, opA, opB);
-    };
 
-    for (int w0 = 0; w0 < n_instr; w0 += kProgWindow) {
-      const int wn = min(kProgWindow, n_instr - w0);
-      if (multi_window || pass == 0) {
-        if (multi_window) __syncthreads();  // every warp is done with the previous window
-        const int4* src = reinterpret_cast<const int4*>(a.n_instr <= kProgInline ? a.inl : prog + w0);
-        int4*       dst = reinterpret_cast<int4*>(s_prog);
-        for (unsigned c = tid; c < (unsigned)wn * (sizeof(Instr) / 16); c += blockDim.x) dst[c] = src[c];
-        __syncthreads();
+      // ---- rescale, store, evaluate -----------------------------------------------------
+      if (main_op) {
+        if (keep_v) {
+          if (fl & fScale) rescale(y, cnt);
+          evaluate(in, fl, y, cnt);
+        } else {
+          if (fl & fScale) rescale(v, cnt);
+          if (fl & fWrite) {
+            double* par = in.parent;
+#pragma unroll
+            for (int u = 0; u < E; ++u) st_clv(par, e[u], v[u]);
+          }
+          if ((fl & fWriteS) && k == 0) {
+            unsigned* ps = in.pscale;
+#pragma unroll
+            for (int u = 0; u < E; ++u) __stcg(ps + site[u], cnt[u]);
+          }
+#pragma unroll
+          for (int u = 0; u < E; ++u) vcnt[u] = cnt[u];
+        }
       }
-      if (!active) continue;
-      // iterations of its own this warp has in this pass (warp-uniform)
-      const unsigned nvalid = min((unsigned)E, it_end - (it_begin + pass * E));
-      if (TS && E >= 2 && nvalid == 1)
-        run_window(std::integral_constant<int, 1>{}, wn);
-      else if (TS && E >= 4 && nvalid == 2)
-        run_window(std::integral_constant<int, (TS && E >= 4 ? 2 : E)>{}, wn);
-      else
-        run_window(std::integral_constant<int, E>{}, wn);
+      if (fl & fEvalV) evaluate(in, fl, v, vcnt);
+      release(jg);
     }
   }
 }
 
 // Launch of the program kernel for K rate categories: one explicit specialisation per K,
-// each in its own translation unit (rdk_program_inst.cu).  Returns the CUDA status of the
-// launch configuration (the launch itself is checked by the caller with cudaGetLastError).
+// each in its own translation unit (rdk_program_inst.cu).  `threads` counts the producer warp.
+// Returns the CUDA status of the launch configuration (the launch itself is checked by the
+// caller with cudaGetLastError).
 template <int K>
-cudaError_t launch_program(const ProgArgs& a, int grid, int threads, int E, bool tail_skip, cudaStream_t st);
-template <> cudaError_t launch_program<1>(const ProgArgs&, int, int, int, bool, cudaStream_t);
-template <> cudaError_t launch_program<2>(const ProgArgs&, int, int, int, bool, cudaStream_t);
-template <> cudaError_t launch_program<4>(const ProgArgs&, int, int, int, bool, cudaStream_t);
-template <> cudaError_t launch_program<8>(const ProgArgs&, int, int, int, bool, cudaStream_t);
-template <> cudaError_t launch_program<16>(const ProgArgs&, int, int, int, bool, cudaStream_t);
-template <> cudaError_t launch_program<32>(const ProgArgs&, int, int, int, bool, cudaStream_t);
+cudaError_t launch_program(const ProgArgs& a, int grid, int threads, int E, cudaStream_t st);
+template <> cudaError_t launch_program<1>(const ProgArgs&, int, int, int, cudaStream_t);
+template <> cudaError_t launch_program<2>(const ProgArgs&, int, int, int, cudaStream_t);
+template <> cudaError_t launch_program<4>(const ProgArgs&, int, int, int, cudaStream_t);
+template <> cudaError_t launch_program<8>(const ProgArgs&, int, int, int, cudaStream_t);
+template <> cudaError_t launch_program<16>(const ProgArgs&, int, int, int, cudaStream_t);
+template <> cudaError_t launch_program<32>(const ProgArgs&, int, int, int, cudaStream_t);
+// the launch shapes the kernel is compiled for, per elements-per-thread E: threads per CTA
+// (producer warp included) and CTAs per SM
+struct LaunchShape {
+  int threads, ctas_per_sm;
+};
+constexpr LaunchShape launch_shape(int E) {
+  return E == 4 ? LaunchShape{384, 1} : (E == 2 ? LaunchShape{320, 2} : LaunchShape{512, 2});
+}
 
 #ifndef RDK_PROGRAM_KERNEL_ONLY
 // ---------------------------------------------------------------------------

@@ -1,0 +1,274 @@
+// rdk_lower.hpp -- from recorded CLV operations to the program the walk kernel executes.
+//
+// Pure host code (no CUDA): buffer indices in, device-instruction descriptions out, so that the
+// data flow of a lowered program can be checked on a CPU (tests/test_lowering.py runs it through
+// rdk_debug_lower_program and interprets the result symbolically).
+//
+// What the kernel's warps carry from one instruction to the next is ONE register-resident CLV
+// value per element, `v` (with its scaler count): every instruction computes
+//     r = A(child 1) o B(child 2)
+// where A is a mat-vec on a CLV LOADED from memory or a tip-table lookup, and B is a mat-vec on
+// `v` or a tip-table lookup.  A post-order traversal (reference src/tree.cpp:364-413) and the
+// directed placement sweep produce, almost always, the second inner child in the instruction just
+// before its parent, so B = v needs no memory access; when it does not hold the right CLV the
+// lowering inserts a pseudo-instruction "v := load(CLV)".  The product of the two children's terms
+// is commutative bit for bit, so the children are ordered canonically (tip first / `v` last).
+//
+// The second job of the lowering is liveness: a CLV (or scale buffer) store is dropped when no
+// later instruction reads the buffer from memory before it is overwritten and the buffer's
+// content after the program is not required (scratch buffers of a directed sweep; the buffers of
+// a lazily materialised evaluation).
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <utility>
+#include <vector>
+
+namespace rdk {
+
+// ---- recorded operation (what the ABI entry points append) -------------------------------------
+enum : unsigned {
+  rWrite = 1u,     // store the parent CLV and its scaler counts
+  rEval = 2u,      // evaluate the root log-likelihood of the parent values into eval slot `slot`
+  rLoadOnly = 4u,  // no CLV arithmetic: the "parent values" are the stored CLV c1 (with c1scale)
+};
+constexpr unsigned kNoClv = 0xffffffffu;
+
+struct ROp {
+  unsigned parent;  // clv index (tips first, as in corax_operation_t) or kNoClv
+  int      pscale;  // scale buffer index or -1
+  unsigned c1, c2;  // clv indices
+  int      c1scale, c2scale;
+  unsigned pm1, pm2;  // PHYSICAL P-matrix pool slots of the two child branches
+  unsigned flags;
+  unsigned slot;
+};
+
+// ---- device instruction flags (shared with the kernel) --------------------------------------------
+enum : unsigned {
+  fTip1 = 1u,         // A = tip-table lookup of tip row c1; otherwise mat-vec on the loaded CLV c1
+  fTip2 = 2u,         // B = tip-table lookup of tip row c2; otherwise mat-vec on v
+  fWrite = 4u,        // store r to `parent`
+  fWriteS = 8u,       // store the scaler counts to `pscale`
+  fEval = 16u,        // evaluate r and leave v untouched (r is not stored, not forwarded)
+  fScale = 32u,       // the parent has a scale buffer: 2^256 rescaling + count
+  fLoadV = 64u,       // pseudo-instruction: v := CLV c1 (vcnt := its scaler counts)
+  fNop = 128u,        // no main action (only fEvalV)
+  fEvalV = 256u,      // after the main action, evaluate v
+  fCnt1 = 512u,       // child 1 (or the CLV of fLoadV) has scaler counts in memory (c1scale)
+  fCnt2V = 1024u,     // child 2 = v carries scaler counts
+  fEvalScaler = 2048u,  // the evaluated values carry scaler counts (adds cnt * ln 2^-256)
+};
+
+struct LInstr {
+  unsigned flags;
+  unsigned parent;  // clv index stored when fWrite
+  int      pscale;  // scale buffer stored when fWriteS
+  unsigned c1;      // clv index: tip row (fTip1) or inner CLV loaded from memory
+  int      c1scale;
+  unsigned c2;      // tip row when fTip2
+  unsigned pm1, pm2;  // pool slots of the tables A / B read
+  unsigned slot;
+};
+
+struct LowerOptions {
+  unsigned tips = 0;
+  // content after the program is NOT required for: every written buffer (discard_writes), or the
+  // clv indices / scale buffers flagged in these per-index tables (may be null)
+  bool                     discard_writes = false;
+  const std::vector<char> *scratch_clv = nullptr;
+  const std::vector<char> *scratch_scaler = nullptr;
+};
+
+struct LowerStats {
+  unsigned loadv = 0;         // pseudo-instructions inserted
+  unsigned stores_dropped = 0;  // CLV stores removed by the liveness pass
+  unsigned forwarded = 0;     // inner children taken from v
+};
+
+// `chunk_off` (size >= 2) delimits independent sub-programs of `ops`; `out_chunk_off` receives the
+// same boundaries in instructions of `out`.
+inline void lower_program(const std::vector<ROp> &ops, const std::vector<unsigned> &chunk_off,
+                          const LowerOptions &opt, std::vector<LInstr> &out,
+                          std::vector<unsigned> &out_chunk_off, LowerStats *stats = nullptr) {
+  out.clear();
+  out_chunk_off.clear();
+  LowerStats        st;
+  const unsigned    tips = opt.tips;
+  std::vector<unsigned> bounds = chunk_off;
+  if (bounds.size() < 2) bounds = {0u, (unsigned)ops.size()};
+  auto is_tip = [&](unsigned c) { return c < tips; };
+
+  for (size_t ch = 0; ch + 1 < bounds.size(); ++ch) {
+    out_chunk_off.push_back((unsigned)out.size());
+    const size_t chunk_first = out.size();
+    unsigned     vptr = kNoClv;  // the CLV held in v
+    int          vscale = -1;
+    // The operands an instruction loads from memory are fetched while the PREVIOUS instruction
+    // computes, i.e. before that instruction's stores are issued: a buffer stored by the
+    // instruction just before must not be loaded (it normally is not: its values are in v).
+    // The degenerate cases (both children the same CLV; same CLV under another scale buffer)
+    // get a no-op in between.
+    auto guard_raw = [&](unsigned clv, int scaler) {
+      if (out.size() == chunk_first) return;
+      const LInstr &pv = out.back();
+      const bool    hazard = ((pv.flags & fWrite) && pv.parent == clv) ||
+                          ((pv.flags & fWriteS) && scaler >= 0 && pv.pscale == scaler);
+      if (!hazard) return;
+      LInstr nop{};
+      nop.flags = fNop;
+      nop.parent = kNoClv;
+      nop.pscale = -1;
+      nop.c1 = kNoClv;
+      nop.c1scale = -1;
+      nop.c2 = kNoClv;
+      out.push_back(nop);
+    };
+    auto emit_loadv = [&](unsigned clv, int scaler) {
+      guard_raw(clv, scaler);
+      LInstr li{};
+      li.flags = fLoadV | (scaler >= 0 ? fCnt1 : 0u);
+      li.parent = kNoClv;
+      li.pscale = -1;
+      li.c1 = clv;
+      li.c1scale = scaler;
+      li.c2 = kNoClv;
+      out.push_back(li);
+      vptr = clv;
+      vscale = scaler;
+      ++st.loadv;
+    };
+    for (unsigned i = bounds[ch]; i < bounds[ch + 1]; ++i) {
+      const ROp &op = ops[i];
+      LInstr     li{};
+      li.parent = kNoClv;
+      li.pscale = -1;
+      li.c2 = kNoClv;
+      li.c1scale = -1;
+      li.slot = op.slot;
+      if (op.flags & rLoadOnly) {
+        // evaluate the stored CLV c1
+        const bool in_v = vptr == op.c1 && vscale == op.c1scale;
+        if (in_v) {
+          li.flags = fNop | fEvalV;
+          li.c1 = kNoClv;
+          ++st.forwarded;
+        } else {
+          guard_raw(op.c1, op.c1scale);
+          li.flags = fLoadV | fEvalV | (op.c1scale >= 0 ? fCnt1 : 0u);
+          li.c1 = op.c1;
+          li.c1scale = op.c1scale;
+          vptr = op.c1;
+          vscale = op.c1scale;
+        }
+        if (op.c1scale >= 0) li.flags |= fEvalScaler;
+        out.push_back(li);
+        continue;
+      }
+      unsigned c1 = op.c1, c2 = op.c2, pm1 = op.pm1, pm2 = op.pm2;
+      int      s1 = op.c1scale, s2 = op.c2scale;
+      auto swap_children = [&]() {
+        std::swap(c1, c2);
+        std::swap(pm1, pm2);
+        std::swap(s1, s2);
+      };
+      unsigned fl = 0;
+      if (is_tip(c1) && is_tip(c2)) {
+        fl |= fTip1 | fTip2;
+        if (s2 >= 0 && s1 < 0) swap_children();  // only child 1's counts can come from memory
+        s2 = -1;                                 // (the ABI rejects two tips with scale buffers)
+      } else if (is_tip(c1) || is_tip(c2)) {
+        if (is_tip(c2)) swap_children();  // the tip first
+        fl |= fTip1;
+        if (!(vptr == c2 && vscale == s2)) emit_loadv(c2, s2);
+        else ++st.forwarded;
+      } else {
+        if (vptr == c2 && vscale == s2) {
+          ++st.forwarded;
+        } else if (vptr == c1 && vscale == s1) {
+          swap_children();
+          ++st.forwarded;
+        } else {
+          emit_loadv(c2, s2);
+        }
+      }
+      if (s1 >= 0) fl |= fCnt1;
+      if (!(fl & fTip2) && s2 >= 0) fl |= fCnt2V;
+      if (op.pscale >= 0) fl |= fScale;
+      li.c1 = c1;
+      li.c1scale = s1;
+      li.c2 = (fl & fTip2) ? c2 : kNoClv;
+      li.pm1 = pm1;
+      li.pm2 = pm2;
+      if ((op.flags & rEval) && !(op.flags & rWrite)) {
+        fl |= fEval;
+        if (fl & fScale) fl |= fEvalScaler;
+      } else {
+        if (op.flags & rWrite) {
+          fl |= fWrite;
+          li.parent = op.parent;
+          if (op.pscale >= 0) {
+            fl |= fWriteS;
+            li.pscale = op.pscale;
+          }
+        }
+        if (op.flags & rEval) {
+          fl |= fEvalV;
+          if (fl & fScale) fl |= fEvalScaler;
+        }
+        vptr = op.parent;
+        vscale = op.pscale;
+      }
+      li.flags = fl;
+      guard_raw((fl & fTip1) ? kNoClv : li.c1, li.c1scale);
+      out.push_back(li);
+    }
+
+    // ---- liveness: drop the stores nobody reads back -----------------------------------------
+    // walked backwards over this chunk; live[x] = "a later instruction reads x from memory before
+    // x is overwritten, or x must hold its value after the program"
+    // dense tables sized by the largest index seen in the chunk
+    unsigned max_clv = 0, max_sc = 0;
+    for (size_t j = chunk_first; j < out.size(); ++j) {
+      const LInstr &x = out[j];
+      if (x.parent != kNoClv) max_clv = std::max(max_clv, x.parent + 1);
+      if (x.c1 != kNoClv) max_clv = std::max(max_clv, x.c1 + 1);
+      if (x.pscale >= 0) max_sc = std::max(max_sc, (unsigned)x.pscale + 1);
+      if (x.c1scale >= 0) max_sc = std::max(max_sc, (unsigned)x.c1scale + 1);
+    }
+    auto out_needed_clv = [&](unsigned c) {
+      if (opt.discard_writes) return false;
+      if (opt.scratch_clv && c < opt.scratch_clv->size() && (*opt.scratch_clv)[c]) return false;
+      return true;
+    };
+    auto out_needed_sc = [&](unsigned s) {
+      if (opt.discard_writes) return false;
+      if (opt.scratch_scaler && s < opt.scratch_scaler->size() && (*opt.scratch_scaler)[s]) return false;
+      return true;
+    };
+    std::vector<char> live_clv(max_clv), live_sc(max_sc);
+    for (unsigned c = 0; c < max_clv; ++c) live_clv[c] = out_needed_clv(c) ? 1 : 0;
+    for (unsigned s = 0; s < max_sc; ++s) live_sc[s] = out_needed_sc(s) ? 1 : 0;
+    for (size_t j = out.size(); j-- > chunk_first;) {
+      LInstr &x = out[j];
+      if (x.flags & fWrite) {
+        if (!live_clv[x.parent]) {
+          x.flags &= ~fWrite;
+          ++st.stores_dropped;
+        }
+        live_clv[x.parent] = 0;
+      }
+      if (x.flags & fWriteS) {
+        if (!live_sc[x.pscale]) x.flags &= ~fWriteS;
+        live_sc[x.pscale] = 0;
+      }
+      const bool loads_c1 = !(x.flags & (fTip1 | fNop));
+      if (loads_c1 && x.c1 != kNoClv) live_clv[x.c1] = 1;
+      if ((x.flags & fCnt1) && x.c1scale >= 0) live_sc[x.c1scale] = 1;
+    }
+  }
+  out_chunk_off.push_back((unsigned)out.size());
+  if (stats) *stats = st;
+}
+
+}  // namespace rdk

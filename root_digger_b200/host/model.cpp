@@ -589,7 +589,7 @@ std::vector<double> model_t::sweep_root_lh(size_t begin, size_t end) {
                                                 _param_indicies[i].data(), _param_indicies[i].data(),
                                                 sw.pm_off.data(), sw.mi.data(), sw.bl.data(), sw.op_off.data(),
                                                 sw.ops.data(), _tree.root_clv_index(), _tree.root_scaler_index(),
-                                                RDK_SWEEP_KEEP_ROOT, chunks, chunk_off.data(), part.data());
+                                                RDK_SWEEP_KEEP_ROOT | RDK_SWEEP_DISCARD, chunks, chunk_off.data(), part.data());
       if (rc == RDK_FAILURE) throw std::runtime_error(engine_error());
       for (size_t q = 0; q < part.size(); ++q) {
         lh[sw.root_pos[q] - begin] += part[q];

@@ -63,6 +63,7 @@ static inline int rdk_sweep_root_placements(rdo_partition_t *p, unsigned int pla
 }
 /* the flags only concern what is stored, never the values returned */
 #define RDK_SWEEP_KEEP_ROOT 1u
+#define RDK_SWEEP_DISCARD 2u
 static inline int rdk_sweep_root_placements_ex(rdo_partition_t *p, unsigned int placements,
                                                const unsigned int *params_indices,
                                                const unsigned int *freqs_indices,

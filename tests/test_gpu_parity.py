@@ -264,7 +264,7 @@ def test_launch_configs_do_not_change_results():
     g, o = make(case)
     sched = case.full_schedule(3, 0.4)
     want = compute_lh(o, sched, case.root_clv, case.root_scaler, mode=MODE_ENGINE)
-    for ctas, threads, elems in [(1, 32, 1), (2, 256, 2), (4, 128, 4), (8, 64, 1), (3, 96, 2)]:
+    for ctas, threads, elems in [(1, 64, 1), (2, 256, 2), (1, 384, 4), (2, 128, 1), (2, 96, 2), (1, 160, 4), (1, 512, 1)]:
         g.set_launch_config(ctas, threads, elems)
         for tail in (1, 2, 0):
             g.set_tail_mode(tail)

@@ -1,0 +1,311 @@
+"""Data flow of the lowering (root_digger_b200/csrc/rdk_lower.hpp), checked without a GPU.
+
+The engine turns recorded CLV operations into the instructions the program kernel walks: it
+orders the two children canonically, keeps ONE CLV value in the warps' registers (`v`), inserts
+register loads where `v` does not hold the child an operation needs, and drops the stores nobody
+reads back.  Here the lowered program is interpreted SYMBOLICALLY -- a CLV value is a nested
+tuple naming how it was computed -- next to the straightforward execution of the recorded
+operations (reference semantics: corax_update_clvs executes its operations in array order,
+src/model.cpp:402,440,461,851), and every evaluated value and every buffer whose content is
+required afterwards must be the same term.  The product of the two children's terms is
+commutative (bit for bit: one rounded multiplication per state), so a term is normalised by
+sorting its two factors.
+"""
+import ctypes as C
+import random
+
+import numpy as np
+import pytest
+
+from root_digger_b200 import capi
+
+R_WRITE, R_EVAL, R_LOADONLY = 1, 2, 4
+F = dict(Tip1=1, Tip2=2, Write=4, WriteS=8, Eval=16, Scale=32, LoadV=64, Nop=128, EvalV=256, Cnt1=512,
+         Cnt2V=1024, EvalScaler=2048)
+NONE = 0xFFFFFFFF
+
+
+def lower(tips, ops, chunk_off=None, discard=False, scratch=None):
+    L = capi.load_engine()
+    L.rdk_debug_lower_program.restype = C.c_int
+    n = len(ops)
+    arr = np.ascontiguousarray(np.array(ops, dtype=np.int64).astype(np.int32).reshape(n, 10))
+    out = np.zeros((4 * n + 16, 9), dtype=np.int32)
+    nch = len(chunk_off) - 1 if chunk_off else 1
+    co = np.ascontiguousarray(np.array(chunk_off if chunk_off else [0, n], dtype=np.uint32))
+    oco = np.zeros(nch + 1, dtype=np.uint32)
+    sc = np.ascontiguousarray(np.array(scratch, dtype=np.uint8)) if scratch is not None else None
+    cnt = L.rdk_debug_lower_program(
+        C.c_uint(tips), C.c_uint(n), arr.ctypes.data_as(C.POINTER(C.c_int)), C.c_uint(nch),
+        co.ctypes.data_as(C.POINTER(C.c_uint)), C.c_int(1 if discard else 0),
+        sc.ctypes.data_as(C.POINTER(C.c_ubyte)) if sc is not None else None, C.c_uint(0 if sc is None else len(sc)),
+        out.ctypes.data_as(C.POINTER(C.c_int)), C.c_uint(out.shape[0]), oco.ctypes.data_as(C.POINTER(C.c_uint)))
+    assert cnt >= 0
+    return [tuple(int(x) & 0xFFFFFFFF if j in (1, 3, 5) else int(x) for j, x in enumerate(row)) for row in out[:cnt]], \
+        [int(x) for x in oco]
+
+
+def term(a, b):
+    return ("mul",) + tuple(sorted((a, b), key=repr))
+
+
+class Mem:
+    """CLV buffers and scale buffers holding symbolic values"""
+
+    def __init__(self, tips, n_clv, n_sc):
+        self.tips = tips
+        self.clv = {i: ("init", i) for i in range(tips, n_clv)}
+        self.sc = {i: ("sinit", i) for i in range(n_sc)}
+
+
+def run_reference(mem, ops):
+    """recorded operations executed eagerly, in order"""
+    evals = {}
+    for (parent, pscale, c1, c2, s1, s2, pm1, pm2, flags, slot) in ops:
+        if flags & R_LOADONLY:
+            evals[slot] = ("eval", mem.clv[c1], mem.sc[s1] if s1 >= 0 else 0)
+            continue
+
+        def child(c, pm):
+            return ("tip", c, pm) if c < mem.tips else ("mv", pm, mem.clv[c])
+        r = term(child(c1, pm1), child(c2, pm2))
+        cnt = ("cnt", mem.sc[s1] if s1 >= 0 else 0, mem.sc[s2] if s2 >= 0 else 0, r) if pscale >= 0 else 0
+        cnt = normalise_cnt(cnt)
+        if pscale >= 0:
+            r = ("scaled", r)
+        if flags & R_WRITE:
+            mem.clv[parent] = r
+            if pscale >= 0:
+                mem.sc[pscale] = cnt
+        if flags & R_EVAL:
+            evals[slot] = ("eval", r, cnt if pscale >= 0 else 0)
+    return evals
+
+
+def normalise_cnt(c):
+    if c == 0:
+        return 0
+    return ("cnt",) + tuple(sorted(c[1:3], key=repr)) + (c[3],)
+
+
+def run_lowered(mem, prog):
+    """the kernel's semantics: registers v / vcnt, operands loaded from memory"""
+    evals = {}
+    v, vcnt = ("garbage",), ("garbage",)
+    prev_written = (None, None)
+    for (fl, parent, pscale, c1, s1, c2, pm1, pm2, slot) in prog:
+        loads_c1 = not (fl & (F["Tip1"] | F["Nop"]))
+        # operands are fetched while the previous instruction computes: they must not be what it stores
+        if loads_c1:
+            assert c1 != prev_written[0], "operand prefetch would race with the previous store"
+        if fl & F["Cnt1"]:
+            assert s1 != prev_written[1], "scaler prefetch would race with the previous store"
+        cnt1 = mem.sc[s1] if fl & F["Cnt1"] else 0
+        prev_written = (None, None)
+        if fl & F["LoadV"]:
+            v, vcnt = mem.clv[c1], cnt1
+        elif not (fl & F["Nop"]):
+            a = ("tip", c1, pm1) if fl & F["Tip1"] else ("mv", pm1, mem.clv[c1])
+            b = ("tip", c2, pm2) if fl & F["Tip2"] else ("mv", pm2, v)
+            r = term(a, b)
+            cnt2 = vcnt if fl & F["Cnt2V"] else 0
+            cnt = 0
+            if fl & F["Scale"]:
+                cnt = normalise_cnt(("cnt", cnt1, cnt2, r))
+                r = ("scaled", r)
+            if fl & F["Eval"]:
+                assert not (fl & (F["Write"] | F["WriteS"]))
+                evals[slot] = ("eval", r, cnt if fl & F["EvalScaler"] else 0)
+            else:
+                if fl & F["Write"]:
+                    mem.clv[parent] = r
+                if fl & F["WriteS"]:
+                    mem.sc[pscale] = cnt
+                prev_written = (parent if fl & F["Write"] else None, pscale if fl & F["WriteS"] else None)
+                v, vcnt = r, cnt
+        if fl & F["EvalV"]:
+            evals[slot] = ("eval", v, vcnt if fl & F["EvalScaler"] else 0)
+    return evals
+
+
+def random_tree_ops(rng, tips, with_eval=True):
+    """a post-order traversal of a random rooted binary tree, corax-style indices"""
+    nodes = list(range(tips))
+    next_clv, next_sc, next_pm = tips, 0, 0
+    scaler_of = {}
+    ops = []
+    rng.shuffle(nodes)
+    # random sequential joining: not a post-order of one tree in general, so forwarding, register
+    # loads and plain loads all occur
+    while len(nodes) > 1:
+        i, j = rng.sample(range(len(nodes)), 2)
+        a, b = nodes[i], nodes[j]
+        for x in sorted((i, j), reverse=True):
+            nodes.pop(x)
+        p, ps = next_clv, next_sc
+        next_clv += 1
+        next_sc += 1
+        ops.append((p, ps, a, b, scaler_of.get(a, -1), scaler_of.get(b, -1), next_pm, next_pm + 1, R_WRITE, 0))
+        next_pm += 2
+        scaler_of[p] = ps
+        nodes.append(p)
+    if with_eval:
+        last = list(ops[-1])
+        last[8] |= R_EVAL
+        ops[-1] = tuple(last)
+    return ops, next_clv, next_sc
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_traversals_keep_their_data_flow(seed):
+    rng = random.Random(seed)
+    tips = rng.choice([2, 3, 5, 9, 17, 40])
+    ops, n_clv, n_sc = random_tree_ops(rng, tips)
+    prog, _ = lower(tips, ops)
+    ref, low = Mem(tips, n_clv, n_sc), Mem(tips, n_clv, n_sc)
+    assert run_reference(ref, ops) == run_lowered(low, prog)
+    assert ref.clv == low.clv and ref.sc == low.sc  # nothing is scratch: every buffer must be stored
+
+
+def test_post_order_forwards_and_discard_drops_every_store():
+    rng = random.Random(5)
+    tips = 33
+    # a caterpillar: every inner child is produced by the instruction just before its parent
+    ops, clv, sc, pm = [], tips, 0, 0
+    prev, prev_sc = 0, -1
+    for t in range(1, tips):
+        ops.append((clv, sc, prev, t, prev_sc, -1, pm, pm + 1, R_WRITE, 0))
+        prev, prev_sc = clv, sc
+        clv, sc, pm = clv + 1, sc + 1, pm + 2
+    ops[-1] = ops[-1][:8] + (R_WRITE | R_EVAL, 0)
+    prog, _ = lower(tips, ops)
+    assert len(prog) == len(ops)  # no register load needed
+    assert all(not (fl & F["LoadV"]) for fl, *_ in prog)
+    ref, low = Mem(tips, clv, sc), Mem(tips, clv, sc)
+    assert run_reference(ref, ops) == run_lowered(low, prog)
+    assert ref.clv == low.clv
+    # the same traversal as a lazily materialised evaluation: no store survives, same value
+    prog2, _ = lower(tips, ops, discard=True)
+    assert all(not (fl & (F["Write"] | F["WriteS"])) for fl, *_ in prog2)
+    low2 = Mem(tips, clv, sc)
+    assert run_lowered(low2, prog2) == run_reference(Mem(tips, clv, sc), ops)
+    del rng
+
+
+def directed_sweep_ops(rng, tips):
+    """ops of a directed-CLV sweep (host/tree.cpp generate_sweep_operations) over a random tree,
+    spare buffers per depth; returns (setup ops, sweep ops, n_clv, n_sc, spare clv range)"""
+    # build a random rooted binary tree
+    class N:
+        pass
+    leaves = []
+    for t in range(tips):
+        n = N()
+        n.clv, n.sc, n.kids, n.pm = t, -1, None, t
+        leaves.append(n)
+    pool = leaves[:]
+    clv, sc = tips, 0
+    post = []
+    while len(pool) > 1:
+        i, j = rng.sample(range(len(pool)), 2)
+        a, b = pool[i], pool[j]
+        for x in sorted((i, j), reverse=True):
+            pool.pop(x)
+        n = N()
+        n.clv, n.sc, n.kids, n.pm = clv, sc, (a, b), clv
+        clv, sc = clv + 1, sc + 1
+        pool.append(n)
+    root = pool[0]
+
+    def walk(n):
+        if n.kids:
+            walk(n.kids[0])
+            walk(n.kids[1])
+            post.append((n.clv, n.sc, n.kids[0].clv, n.kids[1].clv, n.kids[0].sc, n.kids[1].sc,
+                         n.kids[0].pm, n.kids[1].pm, R_WRITE, 0))
+    walk(root)
+    setup = post
+    spare0, spare_sc0 = clv, sc
+    root_clv, root_sc = clv + 64, sc + 64
+    ops = []
+    slot = [0]
+    pmx = [10_000]
+
+    def placement(below, above):
+        ops.append((root_clv, root_sc, below[0], above[0], below[1], above[1], pmx[0], pmx[0] + 1, R_EVAL, slot[0]))
+        pmx[0] += 2
+        slot[0] += 1
+
+    def descend(n, up, edge_pm, depth):
+        if not n.kids:
+            return
+        for i in (0, 1):
+            child, sib = n.kids[i], n.kids[1 - i]
+            U = (spare0 + depth, spare_sc0 + depth)
+            ops.append((U[0], U[1], up[0], sib.clv, up[1], sib.sc, edge_pm, sib.pm, R_WRITE, 0))
+            placement((child.clv, child.sc), U)
+            descend(child, U, child.pm, depth + 1)
+
+    l, r = root.kids
+    placement((l.clv, l.sc), (r.clv, r.sc))
+    descend(l, (r.clv, r.sc), 9_999, 0)
+    descend(r, (l.clv, l.sc), 9_999, 0)
+    return setup, ops, root_clv + 1, root_sc + 1, slot[0]
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_directed_sweep_with_scratch_buffers(seed):
+    rng = random.Random(100 + seed)
+    tips = rng.choice([4, 7, 12, 30])
+    setup, ops, n_clv, n_sc, n_eval = directed_sweep_ops(rng, tips)
+    ref = Mem(tips, n_clv, n_sc)
+    run_reference(ref, setup)
+    low = Mem(tips, n_clv, n_sc)
+    low.clv, low.sc = dict(ref.clv), dict(ref.sc)
+    before = dict(ref.clv)
+    want = run_reference(ref, ops)
+    prog, _ = lower(tips, ops, discard=True)
+    got = run_lowered(low, prog)
+    assert len(want) == n_eval and got == want
+    # the partition's own CLVs are untouched
+    for c in range(tips, tips + len(setup)):
+        assert low.clv[c] == before[c]
+    # the evaluation leaves v alone: the first child below an inner edge finds its directed CLV in
+    # registers, and the directed CLVs towards tips are never stored
+    n_ops = sum(1 for o in ops if o[8] & R_WRITE)
+    stored = sum(1 for fl, *_ in prog if fl & F["Write"])
+    loadv = sum(1 for fl, *_ in prog if fl & F["LoadV"])
+    assert stored < n_ops and (loadv < n_ops or tips < 12)
+    # in chunks: every chunk starts with unknown registers
+    half = len(ops) // 2
+    while half < len(ops) and not (ops[half - 1][8] & R_EVAL):
+        half += 1
+    if 0 < half < len(ops):
+        progc, coff = lower(tips, ops, chunk_off=[0, half, len(ops)])
+        low2 = Mem(tips, n_clv, n_sc)
+        ref2 = Mem(tips, n_clv, n_sc)
+        run_reference(ref2, setup)
+        low2.clv, low2.sc = dict(ref2.clv), dict(ref2.sc)
+        got2 = {}
+        for c in range(2):
+            got2.update(run_lowered(low2, progc[coff[c]:coff[c + 1]]))
+        assert got2 == want
+
+
+def test_degenerate_operand_patterns():
+    tips = 4
+    # both children the same inner CLV, straight after it was produced; and a stored-CLV evaluation
+    ops = [
+        (4, 0, 0, 1, -1, -1, 0, 1, R_WRITE, 0),
+        (5, 1, 4, 4, 0, 0, 2, 3, R_WRITE, 0),
+        (0xFFFFFFFF, -1, 5, 0xFFFFFFFF, 1, -1, 0, 0, R_LOADONLY | R_EVAL, 0),
+        (6, 2, 5, 4, 1, 0, 4, 5, R_WRITE | R_EVAL, 1),
+        (0xFFFFFFFF, -1, 4, 0xFFFFFFFF, 0, -1, 0, 0, R_LOADONLY | R_EVAL, 2),
+    ]
+    ops = [tuple(-1 if x == 0xFFFFFFFF else x for x in o) for o in ops]
+    prog, _ = lower(tips, ops)
+    ref, low = Mem(tips, 8, 4), Mem(tips, 8, 4)
+    want = run_reference(ref, [tuple(o) for o in ops])
+    got = run_lowered(low, prog)
+    assert got == want and ref.clv == low.clv and ref.sc == low.sc
+    assert any(fl & F["Nop"] and not fl & F["EvalV"] for fl, *_ in prog)  # the read-after-write guard
