@@ -343,8 +343,8 @@ const char *rdk_version(void);
 /* Introspection of the lowering (csrc/rdk_lower.hpp), pure host code: `n_ops` recorded
  * operations of 10 ints each {parent clv, parent scaler, child1 clv, child2 clv, child1
  * scaler, child2 scaler, P slot 1, P slot 2, flags (1 store, 2 evaluate, 4 evaluate the
- * stored CLV child1), eval slot} -> instructions of 9 ints each {flags, parent, parent
- * scaler, child1, child1 scaler, child2 tip, P slot 1, P slot 2, eval slot}.  Returns the
+ * stored CLV child1), eval slot} -> instructions of 10 ints each {flags, parent, parent
+ * scaler, child1, child1 scaler, child2, P slot 1, P slot 2, eval slot, child2 scaler}.  Returns the
  * number of instructions, -1 if out_cap is too small. */
 int rdk_debug_lower_program(unsigned int tips, unsigned int n_ops, const int *ops,
                             unsigned int n_chunks, const unsigned int *chunk_off,

@@ -382,8 +382,12 @@ void to_device_instr(Engine *e, const LInstr &li, Instr *out) {
     in.c1 = e->d_tips + (size_t)li.c1 * e->tip_stride;
   else if (!(li.flags & fNop))
     in.c1 = e->clv_ptr[li.c1 - e->tips];
-  if (li.flags & fTip2) in.c2 = e->d_tips + (size_t)li.c2 * e->tip_stride;
+  if (li.flags & fTip2)
+    in.c2 = e->d_tips + (size_t)li.c2 * e->tip_stride;
+  else if (li.flags & fLoadV2)
+    in.c2 = e->clv_ptr[li.c2 - e->tips];
   if (li.flags & fCnt1) in.c1scale = e->d_scalers + (size_t)li.c1scale * e->S;
+  if (li.flags & fCnt2M) in.c2scale = e->d_scalers + (size_t)li.c2scale * e->S;
   if (!(li.flags & (fLoadV | fNop))) {
     // the table each child reads: P of an inner child, T of a tip child (same pool slot)
     const size_t K = e->K;

@@ -21,6 +21,23 @@
 // (prefetch.global.L2, no registers).  See DESIGN.md for the measurement.
 #define RDK_L2_PREFETCH_DIST 0
 #endif
+// timing experiments only (tools/build_variant.sh): each removes one piece of the kernel -- the
+// results are WRONG when any is set
+#ifndef RDK_X_NOTABLES
+#define RDK_X_NOTABLES 0  // the producer moves no tables
+#endif
+#ifndef RDK_X_NOLOAD
+#define RDK_X_NOLOAD 0  // the consumers load no CLV
+#endif
+#ifndef RDK_A_FIRST
+// 1: an instruction starts with the child-1 term (the operand LOADED for it), so that the loads
+//    of the next instruction's operand are issued before the child-2 mat-vec and everything
+//    after it -- the longest flight time a one-instruction look-ahead can give them; the result
+//    is then moved into v (8 E register moves).
+// 0: the child-2 term first (computed from v), the product lands directly in v; the next
+//    instruction's loads are issued only after both mat-vecs.
+#define RDK_A_FIRST 1
+#endif
 #include "rdk_lower.hpp"
 #include <stdint.h>
 #include <type_traits>
@@ -55,12 +72,18 @@ __device__ __forceinline__ double dfma(double a, double b, double c) { return __
 // derivatives (difference quotients with h = 1e-8, reference
 // src/model.cpp:481-519) irreproducible.
 // ---------------------------------------------------------------------------
+// the constants live in constant memory: a DFMA / DMUL takes them as c[bank][offset] operands,
+// where a literal would cost two moves into a uniform register pair each
+static __constant__ double kLogConst[9] = {
+    6.93147180369123816490e-01, 1.90821492927058770002e-10,  // ln2_hi, ln2_lo
+    6.666666666666735130e-01,   3.999999999940941908e-01,    // Lg1, Lg2
+    2.857142874366239149e-01,   2.222219843214978396e-01,    // Lg3, Lg4
+    1.818357216161805012e-01,   1.531383769920937332e-01,    // Lg5, Lg6
+    1.479819860511658591e-01};                               // Lg7
 __device__ __forceinline__ double rd_log(double x) {
-  const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10,
-               Lg1 = 6.666666666666735130e-01, Lg2 = 3.999999999940941908e-01,
-               Lg3 = 2.857142874366239149e-01, Lg4 = 2.222219843214978396e-01,
-               Lg5 = 1.818357216161805012e-01, Lg6 = 1.531383769920937332e-01,
-               Lg7 = 1.479819860511658591e-01;
+  const double ln2_hi = kLogConst[0], ln2_lo = kLogConst[1], Lg1 = kLogConst[2], Lg2 = kLogConst[3],
+               Lg3 = kLogConst[4], Lg4 = kLogConst[5], Lg5 = kLogConst[6], Lg6 = kLogConst[7],
+               Lg7 = kLogConst[8];
   uint64_t ix = (uint64_t)__double_as_longlong(x);
   uint32_t hx = (uint32_t)(ix >> 32);
   int      k = 0;
@@ -445,15 +468,17 @@ __global__ void __launch_bounds__(64) pmat_expm_nonrev_kernel(const __grid_const
 struct alignas(16) Instr {
   double*              parent;   // fWrite: where r is stored
   const void*          c1;       // tip row (fTip1) or the inner CLV A loads
-  const unsigned char* c2;       // tip row (fTip2)
+  const void*          c2;       // tip row (fTip2); the CLV loaded into v beforehand (fLoadV2)
   unsigned*            pscale;   // fWriteS
   const unsigned*      c1scale;  // fCnt1
+  const unsigned*      c2scale;  // fCnt2M
   const double*        P1;       // the table A reads (in its branch's pool slot)   -- producer only
   const double*        P2;       // the table B reads                               -- producer only
   unsigned             flags;
   unsigned             slot;     // eval slot (row of the partial-sum buffer)
+  unsigned             pad[2];
 };
-static_assert(sizeof(Instr) == 64, "Instr layout");
+static_assert(sizeof(Instr) == 80, "Instr layout");
 
 constexpr int kProgInline = 8;
 constexpr int kMaxChunks = 16;  // independent sub-programs one launch can run side by side
@@ -480,8 +505,12 @@ struct ProgArgs {
 // the table ring of one CTA
 template <int K>
 struct Ring {
+#ifdef RDK_RING_DEPTH
+  static constexpr int      kDepth = RDK_RING_DEPTH;
+#else
   static constexpr int      kDepth = K <= 8 ? 8 : (K == 16 ? 4 : 2);
-  static constexpr int      kLogDepth = kDepth == 8 ? 3 : (kDepth == 4 ? 2 : 1);
+#endif
+  static constexpr int      kLogDepth = kDepth == 16 ? 4 : (kDepth == 8 ? 3 : (kDepth == 4 ? 2 : 1));
   static constexpr unsigned kTabBytes = kTabDoubles * K * 8;      // one child's table (the larger kind)
   static constexpr unsigned kPBytes = kPTabDoubles * K * 8;       // P of an inner child
   static constexpr unsigned kInstrBytes = 128;                    // the instruction, padded
@@ -562,7 +591,8 @@ __global__ void __launch_bounds__(MAXT, MINB) clv_program_kernel(const __grid_co
   unsigned long long* const s_empty = s_full + D;
 
   const unsigned tid = threadIdx.x;
-  const unsigned lane = tid & 31u;
+  unsigned       lane;  // (volatile: kept in a register instead of being re-read from SR_TID in the loop)
+  asm volatile("mov.u32 %0, %%laneid;\n" : "=r"(lane));
   const unsigned wib = tid >> 5;
   const unsigned n_cons = (blockDim.x >> 5) - 1u;  // consumer warps; warp n_cons is the producer
 
@@ -598,7 +628,7 @@ __global__ void __launch_bounds__(MAXT, MINB) clv_program_kernel(const __grid_co
     // the launch arguments) ahead of time, then the lanes fill their slots in order
     for (unsigned base = 0; base < total; base += 32u) {
       const unsigned j = base + lane;
-      int4           w0 = make_int4(0, 0, 0, 0), w1 = w0, w2 = w0, w3 = w0;
+      int4           w0 = make_int4(0, 0, 0, 0), w1 = w0, w2 = w0, w3 = w0, w4 = w0;
       if (j < total) {
         const unsigned idx = j % n_instr;
         const int4*    src = reinterpret_cast<const int4*>(inline_prog ? &a.inl[idx] : &prog[idx]);
@@ -606,6 +636,7 @@ __global__ void __launch_bounds__(MAXT, MINB) clv_program_kernel(const __grid_co
         w1 = src[1];
         w2 = src[2];
         w3 = src[3];
+        w4 = src[4];
       }
       const unsigned cnt = min(32u, total - base);
       for (unsigned t = 0; t < cnt; ++t) {
@@ -618,20 +649,21 @@ __global__ void __launch_bounds__(MAXT, MINB) clv_program_kernel(const __grid_co
           dst[1] = w1;
           dst[2] = w2;
           dst[3] = w3;
-          const unsigned fl = (unsigned)w3.z;
+          dst[4] = w4;
+          const unsigned fl = (unsigned)w4.x;
           unsigned       b1 = 0, b2 = 0;
-          if (!(fl & (fLoadV | fNop))) {
+          if (!(fl & (fLoadV | fNop)) && !RDK_X_NOTABLES) {
             b1 = (fl & fTip1) ? R::kTabBytes : R::kPBytes;
             b2 = (fl & fTip2) ? R::kTabBytes : R::kPBytes;
           }
           // the arrive releases the plain stores above to the consumers that acquire the barrier
           mbar_expect_tx(&s_full[s], b1 + b2);
           if (b1) {
-            const unsigned long long p1 = ((unsigned long long)(unsigned)w2.w << 32) | (unsigned)w2.z;
+            const unsigned long long p1 = ((unsigned long long)(unsigned)w3.y << 32) | (unsigned)w3.x;
             bulk_g2s(slot + R::kInstrBytes, reinterpret_cast<const void*>(p1), b1, &s_full[s]);
           }
           if (b2) {
-            const unsigned long long p2 = ((unsigned long long)(unsigned)w3.y << 32) | (unsigned)w3.x;
+            const unsigned long long p2 = ((unsigned long long)(unsigned)w3.w << 32) | (unsigned)w3.z;
             bulk_g2s(slot + R::kInstrBytes + R::kTabBytes, reinterpret_cast<const void*>(p2), b2, &s_full[s]);
           }
         }
@@ -705,13 +737,13 @@ __global__ void __launch_bounds__(MAXT, MINB) clv_program_kernel(const __grid_co
         const unsigned char* t = reinterpret_cast<const unsigned char*>(in.c1);
 #pragma unroll
         for (int u = 0; u < E; ++u) m1[u] = __ldg(t + site[u]);
-      } else if (!(fl & fNop)) {
+      } else if (!(fl & fNop) && !RDK_X_NOLOAD) {
         const void* g = in.c1;
 #pragma unroll
         for (int u = 0; u < E; ++u) c1r[u] = ld_clv(g, e[u]);
       }
       if (fl & fTip2) {
-        const unsigned char* t = in.c2;
+        const unsigned char* t = reinterpret_cast<const unsigned char*>(in.c2);
 #pragma unroll
         for (int u = 0; u < E; ++u) m2n[u] = __ldg(t + site[u]);
       }
@@ -724,17 +756,50 @@ __global__ void __launch_bounds__(MAXT, MINB) clv_program_kernel(const __grid_co
       }
     };
 
+    // fLoadV2: v := the CLV child 2 of `in` (issued at the very end of the previous instruction:
+    // v is dead by then, and the previous instruction's stores precede it in program order)
+    auto load_v = [&](const Instr& in) __attribute__((always_inline)) {
+      const unsigned fl = in.flags;
+      if (fl & fLoadV2) {
+        const void* g = in.c2;
+#pragma unroll
+        for (int u = 0; u < E; ++u) v[u] = ld_clv(g, e[u]);
+#pragma unroll
+        for (int u = 0; u < E; ++u) vcnt[u] = 0;
+        if (fl & fCnt2M) {
+          const unsigned* s2 = in.c2scale;
+#pragma unroll
+          for (int u = 0; u < E; ++u) vcnt[u] = __ldcg(s2 + site[u]);
+        }
+      }
+    };
+
     // 2^256 rescaling of the values of one instruction (SURVEY A-3): a site is rescaled when all
     // its K*4 values are below 2^-256
     auto rescale = [&](d4(&r)[E], unsigned(&cnt)[E]) __attribute__((always_inline)) {
+      // the test runs on the integer pipe (hi_word); a ballot per slot tells every lane which
+      // sites of the warp iteration are all-small.  The multiplication itself is rare: it sits
+      // behind a WARP-UNIFORM branch (any site of any slot), so the common case costs no
+      // predicated fp64 work at all.
+      unsigned m[E], any = 0;
 #pragma unroll
       for (int u = 0; u < E; ++u) {
-        const int  mx = max(max(hi_word(r[u].v[0]), hi_word(r[u].v[1])), max(hi_word(r[u].v[2]), hi_word(r[u].v[3])));
-        const unsigned m = __ballot_sync(0xffffffffu, mx < kScaleThresholdHi);
-        if ((m & gmask) == gmask) {
+        const int mx = max(max(hi_word(r[u].v[0]), hi_word(r[u].v[1])), max(hi_word(r[u].v[2]), hi_word(r[u].v[3])));
+        m[u] = __ballot_sync(0xffffffffu, mx < kScaleThresholdHi);
+        unsigned t = m[u];  // bit at a site's first lane <=> all K lanes of the site are set
 #pragma unroll
-          for (int i = 0; i < 4; ++i) r[u].v[i] = dmul(r[u].v[i], RDK_SCALE_FACTOR);
-          cnt[u] += 1;
+        for (int sft = 1; sft < K; sft <<= 1) t &= t >> sft;
+        any |= t;
+      }
+      constexpr unsigned kSiteBase = K == 1 ? 0xffffffffu : (K == 2 ? 0x55555555u : (K == 4 ? 0x11111111u : (K == 8 ? 0x01010101u : (K == 16 ? 0x00010001u : 1u))));
+      if (any & kSiteBase) {
+#pragma unroll
+        for (int u = 0; u < E; ++u) {
+          if ((m[u] & gmask) == gmask) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) r[u].v[i] = dmul(r[u].v[i], RDK_SCALE_FACTOR);
+            cnt[u] += 1;
+          }
         }
       }
     };
@@ -804,6 +869,7 @@ __global__ void __launch_bounds__(MAXT, MINB) clv_program_kernel(const __grid_co
     // pipeline prologue: the operands of the pass's first instruction
     wait_full(jg);
     load_operands(*reinterpret_cast<const Instr*>(slot_of(jg)));
+    load_v(*reinterpret_cast<const Instr*>(slot_of(jg)));
 
     for (unsigned ii = 0; ii < n_instr; ++ii, ++jg) {
       const unsigned char* slot = slot_of(jg);
@@ -822,6 +888,113 @@ __global__ void __launch_bounds__(MAXT, MINB) clv_program_kernel(const __grid_co
         cnt[u] = cnt1[u] + ((fl & fCnt2V) ? vcnt[u] : 0u);
       }
 
+#if RDK_A_FIRST
+      // ---- phase 1: y = A(child 1); c1r / m1 are dead afterwards ---------------------------
+      if (main_op) {
+        if (fl & fTip1) {
+#pragma unroll
+          for (int u = 0; u < E; ++u) {
+            const double2* t = reinterpret_cast<const double2*>(tab1 + (m1[u] * K + k) * 32u);
+            const double2  lo = t[0], hi = t[1];
+            y[u].v[0] = lo.x;
+            y[u].v[1] = lo.y;
+            y[u].v[2] = hi.x;
+            y[u].v[3] = hi.y;
+          }
+        } else {
+          const double2* p = reinterpret_cast<const double2*>(tab1 + k * (kPTabDoubles * 8));
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const double2 p01 = p[i * 2], p23 = p[i * 2 + 1];
+#pragma unroll
+            for (int u = 0; u < E; ++u) {
+              double s = dmul(p01.x, c1r[u].v[0]);
+              s = dfma(p01.y, c1r[u].v[1], s);
+              s = dfma(p23.x, c1r[u].v[2], s);
+              s = dfma(p23.y, c1r[u].v[3], s);
+              y[u].v[i] = s;
+            }
+          }
+        }
+      } else if (fl & fLoadV) {
+#pragma unroll
+        for (int u = 0; u < E; ++u) {
+          v[u] = c1r[u];
+          vcnt[u] = cnt1[u];
+        }
+      }
+
+      // ---- the operands of the next instruction of this pass (c1r, m1, cnt1 are dead now) ---
+      if (ii + 1 < n_instr) {
+        wait_full(jg + 1);
+        load_operands(*reinterpret_cast<const Instr*>(slot_of(jg + 1)));
+#if RDK_L2_PREFETCH_DIST > 1
+        if (ii + RDK_L2_PREFETCH_DIST < n_instr && RDK_L2_PREFETCH_DIST < (int)D) {
+          wait_full(jg + RDK_L2_PREFETCH_DIST);
+          const Instr& fx = *reinterpret_cast<const Instr*>(slot_of(jg + RDK_L2_PREFETCH_DIST));
+          if (!(fx.flags & (fTip1 | fNop))) {
+            const char* g = reinterpret_cast<const char*>(fx.c1);
+#pragma unroll
+            for (int u = 0; u < E; ++u) prefetch_l2(g + (size_t)e[u] * 32u);
+          }
+        }
+#endif
+      }
+
+      // ---- phase 2: r = y o B(child 2), in place ------------------------------------------
+      const bool keep_v = (fl & fEval) != 0;
+      if (main_op) {
+        if (fl & fTip2) {
+#pragma unroll
+          for (int u = 0; u < E; ++u) {
+            const double2* t = reinterpret_cast<const double2*>(tab2 + (m2c[u] * K + k) * 32u);
+            const double2  lo = t[0], hi = t[1];
+            y[u].v[0] = dmul(y[u].v[0], lo.x);
+            y[u].v[1] = dmul(y[u].v[1], lo.y);
+            y[u].v[2] = dmul(y[u].v[2], hi.x);
+            y[u].v[3] = dmul(y[u].v[3], hi.y);
+          }
+        } else {
+          const double2* p = reinterpret_cast<const double2*>(tab2 + k * (kPTabDoubles * 8));
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const double2 p01 = p[i * 2], p23 = p[i * 2 + 1];
+#pragma unroll
+            for (int u = 0; u < E; ++u) {
+              double s = dmul(p01.x, v[u].v[0]);
+              s = dfma(p01.y, v[u].v[1], s);
+              s = dfma(p23.x, v[u].v[2], s);
+              s = dfma(p23.y, v[u].v[3], s);
+              y[u].v[i] = dmul(y[u].v[i], s);
+            }
+          }
+        }
+      }
+
+      // ---- rescale, store, evaluate -----------------------------------------------------
+      if (main_op) {
+        if (fl & fScale) rescale(y, cnt);
+        if (keep_v) {
+          evaluate(in, fl, y, cnt);
+        } else {
+          if (fl & fWrite) {
+            double* par = in.parent;
+#pragma unroll
+            for (int u = 0; u < E; ++u) st_clv(par, e[u], y[u]);
+          }
+          if ((fl & fWriteS) && k == 0) {
+            unsigned* ps = in.pscale;
+#pragma unroll
+            for (int u = 0; u < E; ++u) __stcg(ps + site[u], cnt[u]);
+          }
+#pragma unroll
+          for (int u = 0; u < E; ++u) {
+            v[u] = y[u];
+            vcnt[u] = cnt[u];
+          }
+        }
+      }
+#else
       // ---- phase 1: y = B(child 2) ------------------------------------------------------
       if (main_op) {
         if (fl & fTip2) {
@@ -935,7 +1108,9 @@ __global__ void __launch_bounds__(MAXT, MINB) clv_program_kernel(const __grid_co
           for (int u = 0; u < E; ++u) vcnt[u] = cnt[u];
         }
       }
+#endif
       if (fl & fEvalV) evaluate(in, fl, v, vcnt);
+      if (ii + 1 < n_instr) load_v(*reinterpret_cast<const Instr*>(slot_of(jg + 1)));
       release(jg);
     }
   }

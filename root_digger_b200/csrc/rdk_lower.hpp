@@ -58,6 +58,9 @@ enum : unsigned {
   fCnt1 = 512u,       // child 1 (or the CLV of fLoadV) has scaler counts in memory (c1scale)
   fCnt2V = 1024u,     // child 2 = v carries scaler counts
   fEvalScaler = 2048u,  // the evaluated values carry scaler counts (adds cnt * ln 2^-256)
+  fLoadV2 = 4096u,    // before this instruction runs, v := CLV c2 (loaded after the previous
+                      // instruction's stores, while that instruction finishes)
+  fCnt2M = 8192u,     // ... and vcnt := its scaler counts from memory (c2scale)
 };
 
 struct LInstr {
@@ -66,7 +69,8 @@ struct LInstr {
   int      pscale;  // scale buffer stored when fWriteS
   unsigned c1;      // clv index: tip row (fTip1) or inner CLV loaded from memory
   int      c1scale;
-  unsigned c2;      // tip row when fTip2
+  unsigned c2;      // tip row when fTip2; the inner CLV loaded into v when fLoadV2
+  int      c2scale; // its scale buffer (fCnt2M)
   unsigned pm1, pm2;  // pool slots of the tables A / B read
   unsigned slot;
 };
@@ -122,21 +126,8 @@ inline void lower_program(const std::vector<ROp> &ops, const std::vector<unsigne
       nop.c1 = kNoClv;
       nop.c1scale = -1;
       nop.c2 = kNoClv;
+      nop.c2scale = -1;
       out.push_back(nop);
-    };
-    auto emit_loadv = [&](unsigned clv, int scaler) {
-      guard_raw(clv, scaler);
-      LInstr li{};
-      li.flags = fLoadV | (scaler >= 0 ? fCnt1 : 0u);
-      li.parent = kNoClv;
-      li.pscale = -1;
-      li.c1 = clv;
-      li.c1scale = scaler;
-      li.c2 = kNoClv;
-      out.push_back(li);
-      vptr = clv;
-      vscale = scaler;
-      ++st.loadv;
     };
     for (unsigned i = bounds[ch]; i < bounds[ch + 1]; ++i) {
       const ROp &op = ops[i];
@@ -144,7 +135,7 @@ inline void lower_program(const std::vector<ROp> &ops, const std::vector<unsigne
       li.parent = kNoClv;
       li.pscale = -1;
       li.c2 = kNoClv;
-      li.c1scale = -1;
+      li.c1scale = li.c2scale = -1;
       li.slot = op.slot;
       if (op.flags & rLoadOnly) {
         // evaluate the stored CLV c1
@@ -173,6 +164,7 @@ inline void lower_program(const std::vector<ROp> &ops, const std::vector<unsigne
         std::swap(s1, s2);
       };
       unsigned fl = 0;
+      bool     load_v = false;  // v does not hold child 2: load it (fLoadV2)
       if (is_tip(c1) && is_tip(c2)) {
         fl |= fTip1 | fTip2;
         if (s2 >= 0 && s1 < 0) swap_children();  // only child 1's counts can come from memory
@@ -180,7 +172,7 @@ inline void lower_program(const std::vector<ROp> &ops, const std::vector<unsigne
       } else if (is_tip(c1) || is_tip(c2)) {
         if (is_tip(c2)) swap_children();  // the tip first
         fl |= fTip1;
-        if (!(vptr == c2 && vscale == s2)) emit_loadv(c2, s2);
+        if (!(vptr == c2 && vscale == s2)) load_v = true;
         else ++st.forwarded;
       } else {
         if (vptr == c2 && vscale == s2) {
@@ -189,15 +181,20 @@ inline void lower_program(const std::vector<ROp> &ops, const std::vector<unsigne
           swap_children();
           ++st.forwarded;
         } else {
-          emit_loadv(c2, s2);
+          load_v = true;
         }
+      }
+      if (load_v) {
+        fl |= fLoadV2 | (s2 >= 0 ? fCnt2M : 0u);
+        ++st.loadv;
       }
       if (s1 >= 0) fl |= fCnt1;
       if (!(fl & fTip2) && s2 >= 0) fl |= fCnt2V;
       if (op.pscale >= 0) fl |= fScale;
       li.c1 = c1;
       li.c1scale = s1;
-      li.c2 = (fl & fTip2) ? c2 : kNoClv;
+      li.c2 = (fl & (fTip2 | fLoadV2)) ? c2 : kNoClv;
+      li.c2scale = (fl & fCnt2M) ? s2 : -1;
       li.pm1 = pm1;
       li.pm2 = pm2;
       if ((op.flags & rEval) && !(op.flags & rWrite)) {
@@ -233,6 +230,8 @@ inline void lower_program(const std::vector<ROp> &ops, const std::vector<unsigne
       const LInstr &x = out[j];
       if (x.parent != kNoClv) max_clv = std::max(max_clv, x.parent + 1);
       if (x.c1 != kNoClv) max_clv = std::max(max_clv, x.c1 + 1);
+      if (x.c2 != kNoClv) max_clv = std::max(max_clv, x.c2 + 1);
+      if (x.c2scale >= 0) max_sc = std::max(max_sc, (unsigned)x.c2scale + 1);
       if (x.pscale >= 0) max_sc = std::max(max_sc, (unsigned)x.pscale + 1);
       if (x.c1scale >= 0) max_sc = std::max(max_sc, (unsigned)x.c1scale + 1);
     }
@@ -265,6 +264,8 @@ inline void lower_program(const std::vector<ROp> &ops, const std::vector<unsigne
       const bool loads_c1 = !(x.flags & (fTip1 | fNop));
       if (loads_c1 && x.c1 != kNoClv) live_clv[x.c1] = 1;
       if ((x.flags & fCnt1) && x.c1scale >= 0) live_sc[x.c1scale] = 1;
+      if (x.flags & fLoadV2) live_clv[x.c2] = 1;
+      if (x.flags & fCnt2M) live_sc[x.c2scale] = 1;
     }
   }
   out_chunk_off.push_back((unsigned)out.size());

@@ -44,7 +44,7 @@ extern "C" int rdk_debug_lower_program(unsigned int tips, unsigned int n_ops, co
     return -1;
   }
   for (size_t i = 0; i < low.size(); ++i) {
-    int          *o = out + 9 * i;
+    int          *o = out + 10 * i;
     const LInstr &x = low[i];
     o[0] = (int)x.flags;
     o[1] = (int)x.parent;
@@ -55,6 +55,7 @@ extern "C" int rdk_debug_lower_program(unsigned int tips, unsigned int n_ops, co
     o[6] = (int)x.pm1;
     o[7] = (int)x.pm2;
     o[8] = (int)x.slot;
+    o[9] = x.c2scale;
   }
   if (out_chunk_off)
     for (size_t c = 0; c < lchunk.size(); ++c) out_chunk_off[c] = lchunk[c];

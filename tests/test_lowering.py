@@ -21,7 +21,7 @@ from root_digger_b200 import capi
 
 R_WRITE, R_EVAL, R_LOADONLY = 1, 2, 4
 F = dict(Tip1=1, Tip2=2, Write=4, WriteS=8, Eval=16, Scale=32, LoadV=64, Nop=128, EvalV=256, Cnt1=512,
-         Cnt2V=1024, EvalScaler=2048)
+         Cnt2V=1024, EvalScaler=2048, LoadV2=4096, Cnt2M=8192)
 NONE = 0xFFFFFFFF
 
 
@@ -30,7 +30,7 @@ def lower(tips, ops, chunk_off=None, discard=False, scratch=None):
     L.rdk_debug_lower_program.restype = C.c_int
     n = len(ops)
     arr = np.ascontiguousarray(np.array(ops, dtype=np.int64).astype(np.int32).reshape(n, 10))
-    out = np.zeros((4 * n + 16, 9), dtype=np.int32)
+    out = np.zeros((4 * n + 16, 10), dtype=np.int32)
     nch = len(chunk_off) - 1 if chunk_off else 1
     co = np.ascontiguousarray(np.array(chunk_off if chunk_off else [0, n], dtype=np.uint32))
     oco = np.zeros(nch + 1, dtype=np.uint32)
@@ -93,7 +93,7 @@ def run_lowered(mem, prog):
     evals = {}
     v, vcnt = ("garbage",), ("garbage",)
     prev_written = (None, None)
-    for (fl, parent, pscale, c1, s1, c2, pm1, pm2, slot) in prog:
+    for (fl, parent, pscale, c1, s1, c2, pm1, pm2, slot, s2) in prog:
         loads_c1 = not (fl & (F["Tip1"] | F["Nop"]))
         # operands are fetched while the previous instruction computes: they must not be what it stores
         if loads_c1:
@@ -102,6 +102,8 @@ def run_lowered(mem, prog):
             assert s1 != prev_written[1], "scaler prefetch would race with the previous store"
         cnt1 = mem.sc[s1] if fl & F["Cnt1"] else 0
         prev_written = (None, None)
+        if fl & F["LoadV2"]:  # issued after the previous instruction's stores
+            v, vcnt = mem.clv[c2], (mem.sc[s2] if fl & F["Cnt2M"] else 0)
         if fl & F["LoadV"]:
             v, vcnt = mem.clv[c1], cnt1
         elif not (fl & F["Nop"]):
@@ -180,7 +182,7 @@ def test_post_order_forwards_and_discard_drops_every_store():
     ops[-1] = ops[-1][:8] + (R_WRITE | R_EVAL, 0)
     prog, _ = lower(tips, ops)
     assert len(prog) == len(ops)  # no register load needed
-    assert all(not (fl & F["LoadV"]) for fl, *_ in prog)
+    assert all(not (fl & (F["LoadV"] | F["LoadV2"])) for fl, *_ in prog)
     ref, low = Mem(tips, clv, sc), Mem(tips, clv, sc)
     assert run_reference(ref, ops) == run_lowered(low, prog)
     assert ref.clv == low.clv
@@ -274,7 +276,7 @@ def test_directed_sweep_with_scratch_buffers(seed):
     # registers, and the directed CLVs towards tips are never stored
     n_ops = sum(1 for o in ops if o[8] & R_WRITE)
     stored = sum(1 for fl, *_ in prog if fl & F["Write"])
-    loadv = sum(1 for fl, *_ in prog if fl & F["LoadV"])
+    loadv = sum(1 for fl, *_ in prog if fl & (F["LoadV"] | F["LoadV2"]))
     assert stored < n_ops and (loadv < n_ops or tips < 12)
     # in chunks: every chunk starts with unknown registers
     half = len(ops) // 2

@@ -1,13 +1,6 @@
 #!/bin/bash
-# usage: sweepvar.sh "variants..." "sites..." "cfg..."
+# usage: sweepvar.sh "variants..." "sites..." "cfg..." [extra bench args]
 for v in $1; do for s in $2; do for cfg in $3; do
   echo "== $v sites $s cfg $cfg"
-  RDK_ENGINE_LIB=$PWD/root_digger_b200/lib/variants/$v/librdk_b200.so timeout 120 python bench.py --sites $s --steps 5 --warmup 3 --no-cpu-baseline --no-e2e --launch-config $cfg 2>&1 | python -c "
-import sys,json
-for l in sys.stdin:
-    l=l.strip()
-    if l.startswith('{'):
-        d=json.loads(l); print(round(d['value']), d['ms_per_step'], d['roofline']['frac'], d['logl_root0'])
-    elif l: print(l[:200])
-"
+  RDK_ENGINE_LIB=$PWD/root_digger_b200/lib/variants/$v/librdk_b200.so timeout 120 python bench.py --sites $s --steps 5 --warmup 3 --no-cpu-baseline --no-e2e --launch-config $cfg $4 2>&1 | python tools/benchline.py
 done; done; done
