@@ -330,44 +330,83 @@ int ensure_partials(Engine *e, unsigned slots, unsigned stride) {
   return RDK_SUCCESS;
 }
 
-// elements per thread and launch shape of the program kernel for a shard of n_witer warp
-// iterations walked by `x_ctas_cap` CTAs at most (the chunks of a chunked program share the
-// device): the smallest E whose single pass covers the shard -- every program instruction costs
-// a warp a fixed preamble whatever E is, but a second pass costs a whole walk -- else E = 4.
+// Launch shape of the program kernel.  A warp's walk is one long dependent instruction stream, so
+// a launch costs (passes) x (instructions) x (time per instruction), and the time per instruction
+// of a warp carrying E elements per thread grows with the warps that share its SM.  Measured on
+// B200 (full evaluations of cfg2-like shards, us per instruction and pass):
+//   E = 1: 0.84 at 10 warps per SM, 1.18 at 21      E = 4: 1.36 at 5 warps per SM, 1.43 at 11
+// i.e. roughly lat0 + slope x warps with (0.53, 0.031) for E = 1 and (1.31, 0.009) for E = 4
+// (E = 2: 1.5 at 10 warps -- never the best, kept for experiments).  The cheapest
+// (E, passes) wins; the chunks of a chunked program share the device (grid x chunks CTAs, all
+// resident at once).
 struct LaunchPlan {
-  int E, threads, grid;
+  int    E, threads, grid;
+  double cost;  // passes x relative time per instruction
 };
-LaunchPlan plan_launch(const Engine *e, unsigned n_witer, unsigned n_chunks) {
-  LaunchPlan pl{};
-  int        E = e->elems;
-  if (E == 3) E = 2;
-  if (E == 0) {
-    E = 4;
-    for (int cand : {1, 2}) {
-      const LaunchShape sh = launch_shape(cand);
-      const unsigned long long ctas = std::max<unsigned long long>(1, (unsigned long long)e->sm_count * sh.ctas_per_sm / n_chunks);
-      const unsigned long long cap = ctas * (unsigned long long)(sh.threads / 32 - 1) * cand;
-      if (n_witer <= cap) {
-        E = cand;
-        break;
-      }
-    }
-  }
+const double kStepLat0[5] = {0, 0.53, 1.2, 0, 1.31};
+const double kStepSlope[5] = {0, 0.031, 0.03, 0, 0.009};
+LaunchPlan plan_launch_for(int sm_count, unsigned n_witer, unsigned n_chunks, int E, int threads_cap, int per_sm_cap) {
   const LaunchShape sh = launch_shape(E);
-  int threads = e->threads ? std::min(e->threads, sh.threads) : sh.threads;
+  int               threads = threads_cap ? std::min(threads_cap, sh.threads) : sh.threads;
   threads = std::max(64, threads);
-  const int per_sm = e->ctas_per_sm ? std::min(e->ctas_per_sm, sh.ctas_per_sm) : sh.ctas_per_sm;
-  int       grid = e->sm_count * per_sm;
-  // a chunked program launches grid x chunks CTAs: keep them all resident at once (one wave)
+  const int per_sm = per_sm_cap ? std::min(per_sm_cap, sh.ctas_per_sm) : sh.ctas_per_sm;
+  int       grid = sm_count * per_sm;
   if (n_chunks > 1) grid = std::max(1, grid / (int)n_chunks);
-  // never more consumer warps than warp iterations
   const int cons = threads / 32 - 1;
+  // never more consumer warps than warp iterations
   const int max_grid = (int)((n_witer + (unsigned)cons - 1) / (unsigned)cons);
   grid = std::max(1, std::min(grid, max_grid));
+  const unsigned per_cta = (n_witer + (unsigned)grid - 1) / (unsigned)grid;
+  const unsigned per_warp = (per_cta + (unsigned)cons - 1) / (unsigned)cons;
+  const unsigned passes = std::max(1u, (per_warp + (unsigned)E - 1) / (unsigned)E);
+  LaunchPlan     pl{};
   pl.E = E;
   pl.threads = threads;
   pl.grid = grid;
+  const double warps_per_sm =
+      std::min<double>((double)cons * per_sm, (double)n_witer * n_chunks / ((double)sm_count * E * passes));
+  pl.cost = passes * (kStepLat0[E] + kStepSlope[E] * warps_per_sm);
   return pl;
+}
+LaunchPlan plan_launch(const Engine *e, unsigned n_witer, unsigned n_chunks) {
+  if (e->elems) return plan_launch_for(e->sm_count, n_witer, n_chunks, e->elems, e->threads, e->ctas_per_sm);
+  LaunchPlan best{};
+  best.cost = 1e300;
+  for (int E : {4, 1}) {
+    LaunchPlan pl = plan_launch_for(e->sm_count, n_witer, n_chunks, E, e->threads, e->ctas_per_sm);
+    if (pl.cost < best.cost) best = pl;
+  }
+  return best;
+}
+
+// A shard is walked by ONE launch, or by TWO when its iterations do not fill the last E = 4 pass:
+// whole E = 4 passes first, then the remaining iterations in the shape that suits them (a warp
+// cannot drop elements in its last pass -- the instruction loop is compiled for E elements -- so a
+// pass that is 20 % full would cost a full one).  Every element is walked by exactly one launch
+// and the two are ordered on the stream, so the results do not depend on the split.
+struct LaunchSeg {
+  LaunchPlan pl;
+  unsigned   it0, n_witer;
+};
+int plan_segments(const Engine *e, unsigned n_witer, unsigned n_chunks, int n_instr, LaunchSeg seg[2]) {
+  seg[0].pl = plan_launch(e, n_witer, n_chunks);
+  seg[0].it0 = 0;
+  seg[0].n_witer = n_witer;
+  if (e->elems || n_instr < 32 || seg[0].pl.E != 4) return 1;
+  const LaunchShape sh = launch_shape(4);
+  const unsigned    grid = (unsigned)std::max(1, e->sm_count * sh.ctas_per_sm / (int)n_chunks);
+  const unsigned    cap = grid * (unsigned)(sh.threads / 32 - 1) * 4u;  // iterations of one full pass
+  const unsigned    full = n_witer / cap, rest = n_witer - full * cap;
+  if (full == 0 || rest == 0) return 1;
+  const LaunchPlan a = plan_launch_for(e->sm_count, full * cap, n_chunks, 4, 0, 0);
+  const LaunchPlan b = plan_launch(e, rest, n_chunks);
+  if (a.cost + b.cost + 0.02 >= seg[0].pl.cost) return 1;
+  seg[0].pl = a;
+  seg[0].n_witer = full * cap;
+  seg[1].pl = b;
+  seg[1].it0 = full * cap;
+  seg[1].n_witer = rest;
+  return 2;
 }
 
 // index -> device pointer translation of a lowered instruction
@@ -450,23 +489,29 @@ int flush(rdk_partition_t *p) {
     a.prog = reinterpret_cast<const Instr *>(d);
   }
   if (nelem > 0 && a.n_instr > 0) {
-    const LaunchPlan pl = plan_launch(e, n_witer, chunked ? a.n_chunks : 1u);
+    LaunchSeg seg[2];
+    const int n_seg = plan_segments(e, n_witer, chunked ? a.n_chunks : 1u, a.n_instr, seg);
     std::pair<cudaEvent_t, cudaEvent_t> *ev = e->timing ? next_event_pair(e) : nullptr;
     if (ev) CUDA_TRY(cudaEventRecord(ev->first, e->stream));
-    cudaError_t lerr;
-    switch (e->K) {
-      case 1: lerr = launch_program<1>(a, pl.grid, pl.threads, pl.E, e->stream); break;
-      case 2: lerr = launch_program<2>(a, pl.grid, pl.threads, pl.E, e->stream); break;
-      case 4: lerr = launch_program<4>(a, pl.grid, pl.threads, pl.E, e->stream); break;
-      case 8: lerr = launch_program<8>(a, pl.grid, pl.threads, pl.E, e->stream); break;
-      case 16: lerr = launch_program<16>(a, pl.grid, pl.threads, pl.E, e->stream); break;
-      case 32: lerr = launch_program<32>(a, pl.grid, pl.threads, pl.E, e->stream); break;
-      default: return fail(RDK_ERROR_PARAM, "rate_cats must divide 32");
+    for (int g = 0; g < n_seg; ++g) {
+      const LaunchPlan &pl = seg[g].pl;
+      a.it0 = seg[g].it0;
+      a.n_witer = seg[g].n_witer;
+      cudaError_t lerr;
+      switch (e->K) {
+        case 1: lerr = launch_program<1>(a, pl.grid, pl.threads, pl.E, e->stream); break;
+        case 2: lerr = launch_program<2>(a, pl.grid, pl.threads, pl.E, e->stream); break;
+        case 4: lerr = launch_program<4>(a, pl.grid, pl.threads, pl.E, e->stream); break;
+        case 8: lerr = launch_program<8>(a, pl.grid, pl.threads, pl.E, e->stream); break;
+        case 16: lerr = launch_program<16>(a, pl.grid, pl.threads, pl.E, e->stream); break;
+        case 32: lerr = launch_program<32>(a, pl.grid, pl.threads, pl.E, e->stream); break;
+        default: return fail(RDK_ERROR_PARAM, "rate_cats must divide 32");
+      }
+      if (lerr != cudaSuccess) return fail(RDK_ERROR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(lerr));
+      CUDA_TRY(cudaGetLastError());
+      e->stats.kernel_launches++;
     }
-    if (lerr != cudaSuccess) return fail(RDK_ERROR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(lerr));
-    CUDA_TRY(cudaGetLastError());
     if (ev) CUDA_TRY(cudaEventRecord(ev->second, e->stream));
-    e->stats.kernel_launches++;
     e->stats.program_launches++;
   }
   e->stats.clv_ops += e->pend_ops;
@@ -1092,15 +1137,26 @@ extern "C" unsigned int rdk_sweep_chunk_hint(unsigned int sites, unsigned int ra
   }
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  // warps one walk of the shard occupies (one warp iteration = 32 elements each, at least)
-  // against the warps the device holds in the E = 2 configuration (4 CTAs x 4 warps per SM)
-  const unsigned long long n_witer = ((unsigned long long)sites * rate_cats + 31) / 32;
-  const unsigned long long capacity = (unsigned long long)sms * 16;
-  if (n_witer == 0 || n_witer >= capacity) return 1;
-  // the largest count that still gives every warp of a one-wave launch at most E = 2 iterations
-  // (one pass): rounding UP instead costs a second pass -- measured on B200, 13 312-site shard,
-  // 3 chunks: 2.95 ms per cfg2 step against 2.16 ms for 12 500 sites
-  return (unsigned)std::max<unsigned long long>(1, std::min<unsigned long long>(kMaxChunks, 2 * capacity / n_witer));
+  const unsigned n_witer = (unsigned)(((unsigned long long)sites * rate_cats + 31) / 32);
+  if (n_witer == 0) return 1;
+  // the cost model of plan_launch: a sweep cut into C chunks walks 1/C of the placements (plus the
+  // re-derivation of the directed CLVs on the path to a chunk's first placement, ~ the tree depth)
+  // per CTA, on 1/C of the device
+  unsigned best_c = 1;
+  double   best = 1e300;
+  for (unsigned c = 1; c <= (unsigned)kMaxChunks; ++c) {
+    Engine probe;
+    probe.sm_count = sms;
+    LaunchSeg seg[2];
+    const int n_seg = plan_segments(&probe, n_witer, c, 1 << 20, seg);
+    double    cost = seg[0].pl.cost + (n_seg > 1 ? seg[1].pl.cost : 0.0);
+    cost *= 1.0 / c + 0.02;
+    if (cost < best * 0.9) {  // a chunk more must pay for itself
+      best = cost;
+      best_c = c;
+    }
+  }
+  return best_c;
 }
 
 extern "C" int rdk_sweep_root_placements_chunks(rdk_partition_t *p, unsigned int placements,

@@ -29,6 +29,9 @@
 #ifndef RDK_X_NOLOAD
 #define RDK_X_NOLOAD 0  // the consumers load no CLV
 #endif
+#ifndef RDK_PRODUCER_SLEEP_NS
+#define RDK_PRODUCER_SLEEP_NS 200
+#endif
 #ifndef RDK_A_FIRST
 // 1: an instruction starts with the child-1 term (the operand LOADED for it), so that the loads
 //    of the next instruction's operand are issued before the child-2 mat-vec and everything
@@ -486,7 +489,8 @@ struct ProgArgs {
   const Instr*    prog;  // null: the program is inl[0..n_instr)
   int             n_instr;
   unsigned        nelem;    // sites * K on this shard
-  unsigned        n_witer;  // ceil(nelem / 32)
+  unsigned        n_witer;  // warp iterations (32 elements each) THIS launch walks ...
+  unsigned        it0;      // ... starting at this one (a shard is walked by one or two launches)
   const unsigned* weights;  // pattern weights [sites]
   double*         partials; // [slots][partial_stride], one value per warp iteration
   unsigned        partial_stride;
@@ -568,6 +572,19 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
       "r"(parity)
       : "memory");
 }
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, P1;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
                    smem_u32(dst)),
@@ -606,8 +623,8 @@ __global__ void __launch_bounds__(MAXT, MINB) clv_program_kernel(const __grid_co
 
   // the CTA's range of warp iterations, split evenly over its consumer warps; every warp of the
   // CTA runs the same number of passes (the ring is walked in lock step, kDepth apart at most)
-  const unsigned c_begin = (unsigned)(((unsigned long long)a.n_witer * blockIdx.x) / gridDim.x);
-  const unsigned c_end = (unsigned)(((unsigned long long)a.n_witer * (blockIdx.x + 1)) / gridDim.x);
+  const unsigned c_begin = a.it0 + (unsigned)(((unsigned long long)a.n_witer * blockIdx.x) / gridDim.x);
+  const unsigned c_end = a.it0 + (unsigned)(((unsigned long long)a.n_witer * (blockIdx.x + 1)) / gridDim.x);
   const unsigned c_len = c_end - c_begin;
   const unsigned passes = ((c_len + n_cons - 1) / n_cons + E - 1) / E;
   const unsigned total = passes * n_instr;  // instructions this CTA's ring carries
@@ -642,7 +659,9 @@ __global__ void __launch_bounds__(MAXT, MINB) clv_program_kernel(const __grid_co
       for (unsigned t = 0; t < cnt; ++t) {
         if (lane == t) {
           const unsigned s = j & (D - 1u);
-          mbar_wait(&s_empty[s], ((j >> R::kLogDepth) & 1u) ^ 1u);
+          // the producer runs kDepth instructions ahead: it is nearly always waiting here, and a
+          // busy wait would take issue slots from the consumer warps of its sub-partition
+          while (!mbar_try_wait(&s_empty[s], ((j >> R::kLogDepth) & 1u) ^ 1u)) __nanosleep(RDK_PRODUCER_SLEEP_NS);
           unsigned char* slot = smem_raw + s * R::kSlotBytes;
           int4*          dst = reinterpret_cast<int4*>(slot);
           dst[0] = w0;
@@ -781,11 +800,17 @@ __global__ void __launch_bounds__(MAXT, MINB) clv_program_kernel(const __grid_co
       // sites of the warp iteration are all-small.  The multiplication itself is rare: it sits
       // behind a WARP-UNIFORM branch (any site of any slot), so the common case costs no
       // predicated fp64 work at all.
+      int mx[E], mn = 0x7fffffff;
+#pragma unroll
+      for (int u = 0; u < E; ++u) {
+        mx[u] = max(max(hi_word(r[u].v[0]), hi_word(r[u].v[1])), max(hi_word(r[u].v[2]), hi_word(r[u].v[3])));
+        mn = min(mn, mx[u]);
+      }
+      if (!__any_sync(0xffffffffu, mn < kScaleThresholdHi)) return;  // no (site, category) of the warp is all-small
       unsigned m[E], any = 0;
 #pragma unroll
       for (int u = 0; u < E; ++u) {
-        const int mx = max(max(hi_word(r[u].v[0]), hi_word(r[u].v[1])), max(hi_word(r[u].v[2]), hi_word(r[u].v[3])));
-        m[u] = __ballot_sync(0xffffffffu, mx < kScaleThresholdHi);
+        m[u] = __ballot_sync(0xffffffffu, mx[u] < kScaleThresholdHi);
         unsigned t = m[u];  // bit at a site's first lane <=> all K lanes of the site are set
 #pragma unroll
         for (int sft = 1; sft < K; sft <<= 1) t &= t >> sft;
@@ -1134,7 +1159,7 @@ struct LaunchShape {
   int threads, ctas_per_sm;
 };
 constexpr LaunchShape launch_shape(int E) {
-  return E == 4 ? LaunchShape{384, 1} : (E == 2 ? LaunchShape{320, 2} : LaunchShape{512, 2});
+  return E == 4 ? LaunchShape{384, 1} : (E == 3 ? LaunchShape{512, 1} : (E == 2 ? LaunchShape{320, 2} : LaunchShape{512, 2}));
 }
 
 #ifndef RDK_PROGRAM_KERNEL_ONLY

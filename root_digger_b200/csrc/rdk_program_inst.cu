@@ -38,6 +38,7 @@ cudaError_t launch_program<RDK_INST_K>(const ProgArgs &a, int grid, int threads,
   switch (E) {
     case 1: return launch_inst<K, 1>(a, grid, threads, st);
     case 2: return launch_inst<K, 2>(a, grid, threads, st);
+    case 3: return launch_inst<K, 3>(a, grid, threads, st);
     default: return launch_inst<K, 4>(a, grid, threads, st);
   }
 }
