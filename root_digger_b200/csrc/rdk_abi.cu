@@ -122,7 +122,12 @@ struct Engine {
   bool         own_stream = true;
   int          sm_count = 148;
 
-  unsigned tips = 0, clv_buffers = 0, S = 0, K = 0, prob_matrices = 0, scale_buffers = 0;
+  unsigned tips = 0, clv_buffers = 0, S = 0, prob_matrices = 0, scale_buffers = 0;
+  // K: the rate categories the device works with = the partition's (Kreal) padded to the next
+  // divisor of the warp size.  A padding category repeats category 0's rate with weight 0: its
+  // values equal category 0's (so the all-entries-small rescaling test is unchanged) and its
+  // term enters the site likelihood as fma(0, t, sum) = sum, bit for bit.
+  unsigned K = 0, Kreal = 0;
   size_t   clv_elems = 0;   // S*K*4 doubles per CLV
   size_t   tip_stride = 0;  // bytes per tip row
 
@@ -131,7 +136,10 @@ struct Engine {
   std::vector<void *>     slabs;     // cudaMalloc'd slabs backing clv_ptr
   double                 *slab_cur = nullptr;
   unsigned                slab_left = 0;
-  unsigned               *d_scalers = nullptr;  // [scale_buffers][S]
+  std::vector<unsigned *> sc_ptr;    // per scale buffer, lazily allocated (zero-filled) in slabs:
+  std::vector<void *>     sc_slabs;  // the reference creates 2n-2 of them and uses n-1
+  unsigned               *sc_cur = nullptr;
+  unsigned                sc_left = 0;
   unsigned               *d_weights = nullptr;  // [S]
   unsigned long long     *d_hist = nullptr;     // [16]
 
@@ -145,7 +153,8 @@ struct Engine {
   // recorded work
   std::vector<PmatEntry> pend_pm;
   std::vector<ROp>       pend_prog;
-  bool                   pend_discard = false;  // the buffers pend_prog writes are scratch (directed sweep)
+  // buffers whose content after pend_prog is not required (scratch of a directed sweep), per index
+  const std::vector<char> *pend_scratch_clv = nullptr, *pend_scratch_sc = nullptr;
   unsigned               pend_slots = 0;  // eval slots used by pend_prog
   unsigned long long     pend_bytes = 0;  // algorithmic bytes of pend_prog
   unsigned               pend_ops = 0, pend_evals = 0;
@@ -247,6 +256,28 @@ int ensure_clv(Engine *e, unsigned buf) {
   return RDK_SUCCESS;
 }
 
+int ensure_scaler(Engine *e, int idx) {
+  if (idx < 0 || e->sc_ptr[idx]) return RDK_SUCCESS;
+  const size_t one = ((size_t)std::max(1u, e->S) + 63) & ~size_t(63);  // 256-byte multiples
+  if (e->sc_left == 0) {
+    unsigned missing = 0;
+    for (unsigned *q : e->sc_ptr)
+      if (!q) ++missing;
+    unsigned n = (unsigned)std::max<size_t>(1, std::min<size_t>(256, (size_t(1) << 28) / (one * 4)));
+    n = std::min(n, std::max(1u, missing));
+    void *slab = nullptr;
+    if (!dev_alloc(e, &slab, one * 4 * n)) return RDK_FAILURE;
+    CUDA_TRY(cudaMemsetAsync(slab, 0, one * 4 * n, e->stream));
+    e->sc_slabs.push_back(slab);
+    e->sc_cur = reinterpret_cast<unsigned *>(slab);
+    e->sc_left = n;
+  }
+  e->sc_ptr[idx] = e->sc_cur;
+  e->sc_cur += one;
+  e->sc_left -= 1;
+  return RDK_SUCCESS;
+}
+
 // ---- program-kernel timing ----------------------------------------------------
 // fold the recorded event pairs into the stats (waits for them to complete)
 void harvest_events(Engine *e) {
@@ -284,7 +315,7 @@ int launch_pmatrices(rdk_partition_t *p) {
   for (int i = 0; i < 12; ++i) a.r[i] = p->subst_params[0][i];
   for (int i = 0; i < 4; ++i) a.pi[i] = p->frequencies[0][i];
   a.pinv = p->prop_invar[0];
-  for (unsigned k = 0; k < e->K; ++k) a.rates[k] = p->rates[k];
+  for (unsigned k = 0; k < e->K; ++k) a.rates[k] = p->rates[k < e->Kreal ? k : 0];
   a.pool = e->d_pool;
   if (a.n <= kPmatInline) {
     for (int i = 0; i < a.n; ++i) a.inl[i] = e->pend_pm[i];
@@ -416,7 +447,7 @@ void to_device_instr(Engine *e, const LInstr &li, Instr *out) {
   in.flags = li.flags;
   in.slot = li.slot;
   if (li.flags & fWrite) in.parent = e->clv_ptr[li.parent - e->tips];
-  if (li.flags & fWriteS) in.pscale = e->d_scalers + (size_t)li.pscale * e->S;
+  if (li.flags & fWriteS) in.pscale = e->sc_ptr[li.pscale];
   if (li.flags & fTip1)
     in.c1 = e->d_tips + (size_t)li.c1 * e->tip_stride;
   else if (!(li.flags & fNop))
@@ -425,8 +456,8 @@ void to_device_instr(Engine *e, const LInstr &li, Instr *out) {
     in.c2 = e->d_tips + (size_t)li.c2 * e->tip_stride;
   else if (li.flags & fLoadV2)
     in.c2 = e->clv_ptr[li.c2 - e->tips];
-  if (li.flags & fCnt1) in.c1scale = e->d_scalers + (size_t)li.c1scale * e->S;
-  if (li.flags & fCnt2M) in.c2scale = e->d_scalers + (size_t)li.c2scale * e->S;
+  if (li.flags & fCnt1) in.c1scale = e->sc_ptr[li.c1scale];
+  if (li.flags & fCnt2M) in.c2scale = e->sc_ptr[li.c2scale];
   if (!(li.flags & (fLoadV | fNop))) {
     // the table each child reads: P of an inner child, T of a tip child (same pool slot)
     const size_t K = e->K;
@@ -454,7 +485,7 @@ int flush(rdk_partition_t *p) {
   a.weights = e->d_weights;
   a.partial_stride = n_witer ? n_witer : 1;
   for (int i = 0; i < 4; ++i) a.pi[i] = p->frequencies[0][i];
-  for (unsigned k = 0; k < e->K; ++k) a.w[k] = p->rate_weights[k];
+  for (unsigned k = 0; k < e->K; ++k) a.w[k] = k < e->Kreal ? p->rate_weights[k] : 0.0;
   if (e->pend_slots) {
     if (!ensure_partials(e, e->pend_slots, a.partial_stride)) return RDK_FAILURE;
     a.partials = e->d_partials;
@@ -466,7 +497,8 @@ int flush(rdk_partition_t *p) {
   std::vector<unsigned> lchunk;
   LowerOptions          lopt;
   lopt.tips = e->tips;
-  lopt.discard_writes = e->pend_discard;
+  lopt.scratch_clv = e->pend_scratch_clv;
+  lopt.scratch_scaler = e->pend_scratch_sc;
   LowerStats lst;
   lower_program(e->pend_prog, chunked ? e->pend_chunk_off : std::vector<unsigned>(), lopt, lowered, lchunk, &lst);
   e->stats.instructions += lowered.size();
@@ -519,7 +551,6 @@ int flush(rdk_partition_t *p) {
   e->stats.algorithmic_bytes += e->pend_bytes;
   e->pend_prog.clear();
   e->pend_chunk_off.clear();
-  e->pend_discard = false;
   e->pend_ops = e->pend_evals = 0;
   e->pend_bytes = 0;
   for (unsigned s : e->pm_retired) e->pm_free.push_back(s);
@@ -621,6 +652,7 @@ int make_rop(rdk_partition_t *p, const rdk_operation_t &op, unsigned flags, ROp 
   if (op.child1_clv_index < e->tips && op.child2_clv_index < e->tips && r.c1scale >= 0 && r.c2scale >= 0)
     return fail(RDK_ERROR_PARAM, "two tip children with scale buffers are not supported (tips carry no scaler, "
                                  "reference test/src/tree.cpp:157)");
+  if (!ensure_scaler(e, r.pscale) || !ensure_scaler(e, r.c1scale) || !ensure_scaler(e, r.c2scale)) return RDK_FAILURE;
   r.pm1 = e->pm_map[op.child1_matrix_index];
   r.pm2 = e->pm_map[op.child2_matrix_index];
   *out = r;
@@ -629,7 +661,7 @@ int make_rop(rdk_partition_t *p, const rdk_operation_t &op, unsigned flags, ROp 
 
 // SURVEY 8d accounting for one CLV operation on this shard
 unsigned long long op_bytes(const Engine *e, const ROp &r) {
-  unsigned long long S = e->S, clv = 32ull * e->K * S, b = 0;
+  unsigned long long S = e->S, clv = 32ull * e->Kreal * S, b = 0;  // the partition's categories, not the padding
   b += (r.c1 < e->tips) ? S : clv;
   b += (r.c2 < e->tips) ? S : clv;
   if (r.flags & rWrite) b += clv;
@@ -700,24 +732,19 @@ static int engine_init(rdk_partition_t *p, Engine *e) {
   e->tips = p->tips;
   e->clv_buffers = p->clv_buffers;
   e->S = p->sites;
-  e->K = p->rate_cats;
+  e->Kreal = p->rate_cats;
+  e->K = 1;
+  while (e->K < e->Kreal) e->K <<= 1;
   e->prob_matrices = p->prob_matrices;
   e->scale_buffers = p->scale_buffers;
-#if RDK_KSLOW
-  // whole blocks of 32 elements (32/K sites): the blocked layout of rdk_kernels.cuh
-  e->clv_elems = (size_t)((e->S + 32 / e->K - 1) / (32 / e->K)) * 32 * 4;
-#else
   e->clv_elems = (size_t)e->S * e->K * 4;
-#endif
   e->tip_stride = ((size_t)e->S + 127) & ~size_t(127);
   e->global_sites = 0;
   e->clv_ptr.assign(e->clv_buffers, nullptr);
 
   if (!dev_alloc(e, (void **)&e->d_tips, e->tip_stride * std::max(1u, e->tips))) return RDK_FAILURE;
   CUDA_TRY(cudaMemsetAsync(e->d_tips, 0, e->tip_stride * std::max(1u, e->tips), e->stream));
-  size_t sc_bytes = sizeof(unsigned) * (size_t)e->S * std::max(1u, e->scale_buffers);
-  if (!dev_alloc(e, (void **)&e->d_scalers, sc_bytes)) return RDK_FAILURE;
-  CUDA_TRY(cudaMemsetAsync(e->d_scalers, 0, sc_bytes, e->stream));
+  e->sc_ptr.assign(e->scale_buffers, nullptr);
   if (!dev_alloc(e, (void **)&e->d_weights, sizeof(unsigned) * std::max(1u, e->S))) return RDK_FAILURE;
   if (!dev_alloc(e, (void **)&e->d_hist, sizeof(unsigned long long) * 16)) return RDK_FAILURE;
   if (!dev_alloc(e, (void **)&e->d_persite, sizeof(double) * std::max(1u, e->S))) return RDK_FAILURE;
@@ -765,8 +792,8 @@ extern "C" rdk_partition_t *rdk_partition_create(unsigned int tips, unsigned int
     fail(RDK_ERROR_PARAM, "exactly one rate matrix per partition is supported (model_t::_submodels)");
     return nullptr;
   }
-  if (rate_cats == 0 || rate_cats > (unsigned)kMaxCats || (32 % rate_cats) != 0) {
-    fail(RDK_ERROR_PARAM, "rate_cats must be one of 1,2,4,8,16,32 (got %u)", rate_cats);
+  if (rate_cats == 0 || rate_cats > (unsigned)kMaxCats) {
+    fail(RDK_ERROR_PARAM, "rate_cats must be in [1, %d] (got %u)", kMaxCats, rate_cats);
     return nullptr;
   }
   if ((unsigned long long)sites * rate_cats >= (1ull << 31)) {
@@ -822,7 +849,7 @@ extern "C" void rdk_partition_destroy(rdk_partition_t *p) {
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
     cudaFree(e->d_tips);
     for (void *s : e->slabs) cudaFree(s);
-    cudaFree(e->d_scalers);
+    for (void *q : e->sc_slabs) cudaFree(q);
     cudaFree(e->d_weights);
     cudaFree(e->d_hist);
     cudaFree(e->d_persite);
@@ -915,7 +942,7 @@ extern "C" void rdk_set_category_rates(rdk_partition_t *p, const double *rates) 
   std::lock_guard<std::mutex> lk(e->mu);
   cudaSetDevice(e->device);
   params_about_to_change(p);
-  memcpy(p->rates, rates, sizeof(double) * e->K);
+  memcpy(p->rates, rates, sizeof(double) * e->Kreal);
 }
 
 extern "C" void rdk_set_category_weights(rdk_partition_t *p, const double *w) {
@@ -923,7 +950,7 @@ extern "C" void rdk_set_category_weights(rdk_partition_t *p, const double *w) {
   std::lock_guard<std::mutex> lk(e->mu);
   cudaSetDevice(e->device);
   flush(p);
-  memcpy(p->rate_weights, w, sizeof(double) * e->K);
+  memcpy(p->rate_weights, w, sizeof(double) * e->Kreal);
 }
 
 extern "C" int rdk_update_invariant_sites(rdk_partition_t *p) {
@@ -956,7 +983,7 @@ extern "C" int rdk_update_prob_matrices(rdk_partition_t *p, const unsigned int *
                                         const double *branch_lengths, unsigned int count) {
   Engine *e = eng(p);
   if (params_indices)
-    for (unsigned k = 0; k < e->K; ++k)
+    for (unsigned k = 0; k < e->Kreal; ++k)
       if (params_indices[k] != 0) return fail(RDK_ERROR_PARAM, "params_indices must be all 0");
   for (unsigned i = 0; i < count; ++i) {
     if (matrix_indices[i] >= e->prob_matrices)
@@ -1002,6 +1029,7 @@ extern "C" double rdk_compute_root_loglikelihood(rdk_partition_t *p, unsigned in
   }
   if (!ensure_clv(e, clv_index - e->tips)) return nan;
   const int rs = scaler_index == RDK_SCALE_BUFFER_NONE ? -1 : scaler_index;
+  if (!ensure_scaler(e, rs)) return nan;
   // fuse with the recorded operation that produces this CLV, if it is the last one
   bool fused = false;
   if (!e->pend_prog.empty()) {
@@ -1024,7 +1052,7 @@ extern "C" double rdk_compute_root_loglikelihood(rdk_partition_t *p, unsigned in
     r.c2 = kNoClv;
     r.c2scale = -1;
     r.slot = 0;
-    e->pend_bytes += 32ull * e->K * e->S + (rs >= 0 ? 4ull * e->S : 0) + 4ull * e->S;
+    e->pend_bytes += 32ull * e->Kreal * e->S + (rs >= 0 ? 4ull * e->S : 0) + 4ull * e->S;
     e->pend_prog.push_back(r);
   }
   e->pend_evals++;
@@ -1186,13 +1214,18 @@ extern "C" int rdk_sweep_root_placements_chunks(rdk_partition_t *p, unsigned int
   if (!flush(p)) return RDK_FAILURE;
   if (!ensure_clv(e, root_clv_index - e->tips)) return RDK_FAILURE;
   const int rs = root_scaler_index == RDK_SCALE_BUFFER_NONE ? -1 : root_scaler_index;
+  if (!ensure_scaler(e, rs)) return RDK_FAILURE;
   // batches bounded by the spare P-matrix slots and the partial-sum buffer.  With a communicator
   // attached the ranks' values are added slot by slot, so every rank must cut the sweep at the
   // same placements: the bound is derived from the LARGEST shard of the layout (agreed when the
   // communicator was attached), never from the local site count.
   const unsigned long long s_ref = e->comm ? e->max_shard_sites : e->S;
   const size_t             ref_stride = (size_t)std::max<unsigned long long>(1, (s_ref * e->K + 31) / 32);
-  const unsigned max_slots = (unsigned)std::max<size_t>(1, std::min<size_t>(4096, (size_t(256) << 20) / (ref_stride * 8)));
+  unsigned max_slots = (unsigned)std::max<size_t>(1, std::min<size_t>(4096, (size_t(256) << 20) / (ref_stride * 8)));
+  if (const char *env = getenv("RDK_SWEEP_MAX_SLOTS")) {  // tests: force several batches on a small case
+    const int v = atoi(env);
+    if (v >= 1) max_slots = std::min(max_slots, (unsigned)v);
+  }
   // whatever way this call ends, the chunk table does not outlive it
   struct chunk_table_guard {
     Engine *e;
@@ -1219,16 +1252,61 @@ extern "C" int rdk_sweep_root_placements_chunks(rdk_partition_t *p, unsigned int
         concurrent = false;
     }
   }
+  // ---- batches: cut where the eval slots or the spare P-matrix slots run out -----------------
+  std::vector<unsigned> cuts{0};  // batch k = placements [cuts[k], cuts[k+1])
+  {
+    const size_t budget0 = e->pm_free.size();  // restored by every flush (retired slots return)
+    unsigned     q = 0;
+    while (q < placements) {
+      size_t   budget = budget0;
+      unsigned b = 0;
+      while (q + b < placements && b < max_slots) {
+        const size_t need = pm_offsets[q + b + 1] - pm_offsets[q + b];
+        if (need > budget) break;
+        budget -= need;
+        ++b;
+      }
+      if (b == 0) return fail(RDK_ERROR_PARAM, "a placement needs more P-matrices than the pool holds");
+      q += b;
+      cuts.push_back(q);
+    }
+  }
+  // RDK_SWEEP_DISCARD with several batches: a buffer written by batch k is scratch FOR THAT BATCH
+  // unless a later batch reads it before writing it (backward pass over the whole sweep)
+  const size_t                   n_batches = cuts.size() - 1;
+  std::vector<std::vector<char>> scratch_clv(n_batches), scratch_sc(n_batches);
+  if (flags & RDK_SWEEP_DISCARD) {
+    std::vector<char> need_clv(e->tips + e->clv_buffers, 0), need_sc(e->scale_buffers, 0);
+    for (size_t k = n_batches; k-- > 0;) {
+      scratch_clv[k].resize(need_clv.size());
+      scratch_sc[k].resize(need_sc.size());
+      for (size_t x = 0; x < need_clv.size(); ++x) scratch_clv[k][x] = !need_clv[x];
+      for (size_t x = 0; x < need_sc.size(); ++x) scratch_sc[k][x] = !need_sc[x];
+      for (unsigned i = op_offsets[cuts[k + 1]]; i-- > op_offsets[cuts[k]];) {
+        const rdk_operation_t &o = operations[i];
+        if (o.parent_clv_index < need_clv.size()) need_clv[o.parent_clv_index] = 0;
+        if (o.parent_scaler_index >= 0 && (size_t)o.parent_scaler_index < need_sc.size()) need_sc[o.parent_scaler_index] = 0;
+        if (o.child1_clv_index < need_clv.size()) need_clv[o.child1_clv_index] = 1;
+        if (o.child2_clv_index < need_clv.size()) need_clv[o.child2_clv_index] = 1;
+        if (o.child1_scaler_index >= 0 && (size_t)o.child1_scaler_index < need_sc.size()) need_sc[o.child1_scaler_index] = 1;
+        if (o.child2_scaler_index >= 0 && (size_t)o.child2_scaler_index < need_sc.size()) need_sc[o.child2_scaler_index] = 1;
+      }
+    }
+  }
+  struct scratch_guard {
+    Engine *e;
+    ~scratch_guard() { e->pend_scratch_clv = e->pend_scratch_sc = nullptr; }
+  } sguard{e};
   unsigned       done = 0;
-  while (done < placements) {
+  for (size_t batch = 0; batch < n_batches; ++batch) {
     unsigned b = 0;
     size_t   pm_budget = e->pm_free.size();
     unsigned next_chunk = 0;
     if (concurrent) e->pend_chunk_off.clear();
-    while (done + b < placements && b < max_slots) {
+    while (done + b < cuts[batch + 1]) {
       unsigned q = done + b;
       size_t   need = pm_offsets[q + 1] - pm_offsets[q];
-      if (need > pm_budget) break;
+      if (need > pm_budget) return fail(RDK_ERROR_MEM, "P-matrix pool smaller than planned");
       if (concurrent && next_chunk < n_chunks && q == chunk_offsets[next_chunk]) {
         e->pend_chunk_off.push_back((unsigned)e->pend_prog.size());
         ++next_chunk;
@@ -1261,7 +1339,7 @@ extern "C" int rdk_sweep_root_placements_chunks(rdk_partition_t *p, unsigned int
         r.c2 = kNoClv;
         r.c2scale = -1;
         r.slot = b;
-        e->pend_bytes += 32ull * e->K * e->S + (rs >= 0 ? 4ull * e->S : 0) + 4ull * e->S;
+        e->pend_bytes += 32ull * e->Kreal * e->S + (rs >= 0 ? 4ull * e->S : 0) + 4ull * e->S;
         e->pend_prog.push_back(r);
       }
       e->pend_evals++;
@@ -1270,10 +1348,12 @@ extern "C" int rdk_sweep_root_placements_chunks(rdk_partition_t *p, unsigned int
     if (b == 0) return fail(RDK_ERROR_PARAM, "a placement needs more P-matrices than the pool holds");
     if (concurrent) e->pend_chunk_off.push_back((unsigned)e->pend_prog.size());
     e->pend_slots = b;
-    // the buffers the operations write are scratch only if nothing of them is needed by a later
-    // batch of this very sweep: the whole sweep must be this one launch
-    e->pend_discard = (flags & RDK_SWEEP_DISCARD) && done == 0 && b == placements;
+    if (flags & RDK_SWEEP_DISCARD) {
+      e->pend_scratch_clv = &scratch_clv[batch];
+      e->pend_scratch_sc = &scratch_sc[batch];
+    }
     int ok = flush(p);
+    e->pend_scratch_clv = e->pend_scratch_sc = nullptr;
     e->pend_slots = 0;
     if (!ok) return RDK_FAILURE;
     if (!finish_evals(p, b)) return RDK_FAILURE;
@@ -1423,15 +1503,14 @@ extern "C" int rdk_get_clv(rdk_partition_t *p, unsigned int clv_index, double *o
   CUDA_TRY(cudaSetDevice(e->device));
   if (clv_index >= e->tips + e->clv_buffers) return fail(RDK_ERROR_PARAM, "clv index out of range");
   if (!flush(p)) return RDK_FAILURE;
-  size_t bytes = e->clv_elems * sizeof(double);  // device size (whole blocks)
+  size_t bytes = (size_t)e->S * e->Kreal * 4 * sizeof(double);  // corax layout [site][cat][state]
   if (clv_index < e->tips) {
-    bytes = (size_t)e->S * e->K * 4 * sizeof(double);  // natural size
     double *tmp = nullptr;
     CUDA_TRY(cudaMalloc((void **)&tmp, bytes ? bytes : 32));
-    size_t n = (size_t)e->S * e->K;
+    size_t n = (size_t)e->S * e->Kreal;
     if (n) {
       tip_expand_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(
-          e->d_tips + (size_t)clv_index * e->tip_stride, e->S, (int)e->K, tmp);
+          e->d_tips + (size_t)clv_index * e->tip_stride, e->S, (int)e->Kreal, tmp);
       e->stats.kernel_launches++;
     }
     cudaError_t err = cudaMemcpyAsync(out, tmp, bytes, cudaMemcpyDeviceToHost, e->stream);
@@ -1440,23 +1519,15 @@ extern "C" int rdk_get_clv(rdk_partition_t *p, unsigned int clv_index, double *o
     CUDA_TRY(err);
   } else {
     if (!ensure_clv(e, clv_index - e->tips)) return RDK_FAILURE;
-#if RDK_KSLOW
-    // device layout [block][cat][site in block][state] -> corax layout [site][cat][state]
-    std::vector<double> tmp(e->clv_elems);
-    CUDA_TRY(cudaMemcpyAsync(tmp.data(), e->clv_ptr[clv_index - e->tips], bytes, cudaMemcpyDeviceToHost,
-                             e->stream));
-    CUDA_TRY(cudaStreamSynchronize(e->stream));
-    const unsigned spw = 32 / e->K;
-    for (unsigned s = 0; s < e->S; ++s)
-      for (unsigned k = 0; k < e->K; ++k) {
-        const size_t src = ((size_t)(s / spw) * 32 + k * spw + (s % spw)) * 4;
-        for (int j = 0; j < 4; ++j) out[((size_t)s * e->K + k) * 4 + j] = tmp[src + j];
-      }
-#else
-    CUDA_TRY(cudaMemcpyAsync(out, e->clv_ptr[clv_index - e->tips], bytes, cudaMemcpyDeviceToHost,
-                             e->stream));
-    CUDA_TRY(cudaStreamSynchronize(e->stream));
-#endif
+    if (e->K == e->Kreal) {
+      CUDA_TRY(cudaMemcpyAsync(out, e->clv_ptr[clv_index - e->tips], bytes, cudaMemcpyDeviceToHost, e->stream));
+      CUDA_TRY(cudaStreamSynchronize(e->stream));
+    } else {
+      // drop the padding categories: a strided copy of Kreal * 32 bytes out of every K * 32
+      CUDA_TRY(cudaMemcpy2DAsync(out, (size_t)e->Kreal * 32, e->clv_ptr[clv_index - e->tips], (size_t)e->K * 32,
+                                 (size_t)e->Kreal * 32, e->S, cudaMemcpyDeviceToHost, e->stream));
+      CUDA_TRY(cudaStreamSynchronize(e->stream));
+    }
   }
   e->stats.d2h_bytes += bytes;
   return RDK_SUCCESS;
@@ -1469,7 +1540,8 @@ extern "C" int rdk_get_scale_buffer(rdk_partition_t *p, int scaler_index, unsign
   if (scaler_index < 0 || (unsigned)scaler_index >= e->scale_buffers)
     return fail(RDK_ERROR_PARAM, "scaler index out of range");
   if (!flush(p)) return RDK_FAILURE;
-  CUDA_TRY(cudaMemcpyAsync(out, e->d_scalers + (size_t)scaler_index * e->S, sizeof(unsigned) * e->S,
+  if (!ensure_scaler(e, scaler_index)) return RDK_FAILURE;
+  CUDA_TRY(cudaMemcpyAsync(out, e->sc_ptr[scaler_index], sizeof(unsigned) * e->S,
                            cudaMemcpyDeviceToHost, e->stream));
   CUDA_TRY(cudaStreamSynchronize(e->stream));
   return RDK_SUCCESS;
@@ -1486,7 +1558,7 @@ extern "C" int rdk_get_pmatrix(rdk_partition_t *p, unsigned int matrix_index, do
                            sizeof(double) * kPTabDoubles * e->K, cudaMemcpyDeviceToHost, e->stream));
   CUDA_TRY(cudaStreamSynchronize(e->stream));
   // device layout [cat][18 (16 used)] -> corax layout [cat][i][j]
-  for (unsigned k = 0; k < e->K; ++k)
+  for (unsigned k = 0; k < e->Kreal; ++k)
     for (int ij = 0; ij < 16; ++ij) out[(size_t)k * 16 + ij] = tmp[(size_t)k * kPTabDoubles + ij];
   return RDK_SUCCESS;
 }

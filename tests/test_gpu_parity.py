@@ -42,6 +42,13 @@ CASES = [
     (300, 523, 4, "iid", "ones"),      # deep underflow: scalers fire
     (40, 300, 16, "evolved", "ones"),
     (24, 100, 32, "evolved", "ones"),
+    # any --rate-cats (reference src/model.cpp:159-168 passes K straight to corax_partition_create):
+    # the device pads to the next divisor of 32 with zero-weight copies of category 0
+    (30, 700, 3, "evolved", "random"),
+    (300, 257, 3, "iid", "ones"),      # padding must not disturb the all-entries-small rescaling test
+    (20, 400, 5, "ambiguous", "random"),
+    (16, 300, 6, "evolved", "ones"),
+    (12, 200, 11, "evolved", "ones"),
 ]
 
 
@@ -259,6 +266,39 @@ def test_chunked_sweep_equals_the_unchunked_sweep(n, S, K, data, chunks):
     assert same_bits(got2, want)
 
 
+@pytest.mark.parametrize("n,S,K,data", [(60, 900, 4, "evolved"), (150, 700, 4, "iid"), (33, 2500, 8, "ambiguous")])
+def test_discarded_sweep_buffers_do_not_change_the_values(n, S, K, data, monkeypatch):
+    """RDK_SWEEP_DISCARD lets the engine keep a directed CLV in registers instead of storing it when no
+    later operation of the sweep reads it back (csrc/rdk_lower.hpp liveness): same bits as the sweep
+    that stores everything, in one launch and -- RDK_SWEEP_MAX_SLOTS forces it -- cut into batches, where
+    a buffer is only scratch for a batch if no LATER batch reads it; stores are really dropped"""
+    from root_digger_b200.capi import RDK_SWEEP_DISCARD, RDK_SWEEP_KEEP_ROOT, Partition
+    case = Case(n, S, K, seed=91 + n, data=data, weights="random")
+    lay = case.tree.sweep_layout()
+    kw = dict(clv_buffers=lay["clv_buffers"], scale_buffers=lay["scale_buffers"], prob_matrices=lay["prob_matrices"])
+    g = Partition(case.n, case.S, case.K, **kw)
+    case.setup(g)
+    s0 = case.full_schedule(2, 0.6)
+    lh0 = compute_lh(g, s0, case.root_clv, case.root_scaler)
+    *sw, pos = case.tree.generate_sweep_operations(layout=lay)
+    want = g.sweep_root_placements(*sw, case.root_clv, case.root_scaler, flags=RDK_SWEEP_KEEP_ROOT)
+    g.reset_stats()
+    got = g.sweep_root_placements(*sw, case.root_clv, case.root_scaler, flags=RDK_SWEEP_KEEP_ROOT | RDK_SWEEP_DISCARD)
+    st = g.stats()
+    assert same_bits(got, want)
+    assert st["stores_elided"] > case.n // 2 and st["program_launches"] == 1
+    for slots in (7, 64):
+        monkeypatch.setenv("RDK_SWEEP_MAX_SLOTS", str(slots))
+        g.reset_stats()
+        got = g.sweep_root_placements(*sw, case.root_clv, case.root_scaler, flags=RDK_SWEEP_KEEP_ROOT | RDK_SWEEP_DISCARD)
+        st = g.stats()
+        assert same_bits(got, want), slots
+        assert st["program_launches"] == -(-len(pos) // slots) and st["stores_elided"] > 0
+        monkeypatch.delenv("RDK_SWEEP_MAX_SLOTS")
+    # the partition's own state is what it was: the root-only evaluation of the current root still agrees
+    assert compute_lh_root(g, case.derivative_schedule(2, 0.6), case.root_clv, case.root_scaler) == lh0
+
+
 def test_launch_configs_do_not_change_results():
     case = Case(25, 5000, 4, seed=11, data="ambiguous", weights="random")
     g, o = make(case)
@@ -276,7 +316,7 @@ def test_launch_configs_do_not_change_results():
 def test_error_paths():
     from root_digger_b200.capi import EngineError, Partition
     with pytest.raises(EngineError):
-        Partition(4, 10, 3)  # rate_cats must divide 32
+        Partition(4, 10, 33)  # more rate categories than the engine carries
     p = Partition(4, 10, 4)
     with pytest.raises(EngineError):
         p.set_tip_states(0, b"ACGTACGT!J")  # illegal state code
