@@ -67,9 +67,15 @@ def parse_args():
     ap.add_argument("--seed", type=int, default=0x5EED0002)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--exhaustive-branches", type=int, default=0,
+    ap.add_argument("--exhaustive-branches", type=int, default=1,
                     help="also time exhaustive mode (one placement = one fully optimised branch, SURVEY 8d) on "
                          "this many branches of the e2e model (0 = skip; each branch is thousands of evaluations)")
+    ap.add_argument("--north-star", default="auto",
+                    help="the BASELINE configs beyond the headline, appended to the line as `north_star`: a comma "
+                         "list of cfg3,cfg4,cfg5, `all`, `off`, or `auto` (= all when --gpus 8, else off)")
+    ap.add_argument("--ns-scale", type=float, default=1.0,
+                    help="shrink the north-star configs (taxa and sites) by this factor: functional runs on small boxes")
+    ap.add_argument("--ns-exhaustive-branches", type=int, default=2)
     ap.add_argument("--launch-config", default="", help="ctas_per_sm,threads,elems (0 = engine default)")
     ap.add_argument("--tail-mode", type=int, default=0, help="0 engine rule, 1 always skip idle slots, 2 never")
     ap.add_argument("--sweep", default="directed", choices=["directed", "path"],
@@ -496,8 +502,8 @@ def run_ours(args):
                       "programs H2D, log-likelihoods D2H; alignment resident as in the reference partition"
                       + ("; + all-gather of the placement log-likelihoods)" if G_r > 1 else ")"),
                "logl_root0": a, "matches_device_arm": bool(a == lh0 and np.array_equal(b, sweep_lh))}
-        if args.exhaustive_branches > 0 and world == 1:
-            e2e["exhaustive"] = exhaustive_sample(m, args.exhaustive_branches, stats=mstats)
+        if args.exhaustive_branches > 0:
+            e2e["exhaustive"] = exhaustive_sample(m, args.exhaustive_branches, stats=mstats, taxa=n, barrier=barrier)
         m.close()
     clocks = sampler.stop() if sampler else None
 
@@ -506,6 +512,30 @@ def run_ours(args):
         threads = os.cpu_count() or 1
         _, cpu, _ = cpu_reference_run(args, case, steps=3, warmup=1, threads=threads, target_step_s=3.0)
         cpu["single_thread"] = cpu_single_thread(args, case)
+
+    g.close()
+    north_star = None
+    ns = args.north_star
+    if ns == "auto":
+        ns = "all" if world == 8 else "off"
+    if ns != "off":
+        import bench_northstar as bn
+        names = list(bn.CONFIGS) if ns == "all" else [x for x in ns.split(",") if x]
+        north_star = {}
+        for name in names:
+            cfg = bn.scaled(bn.CONFIGS[name], args.ns_scale)
+            try:
+                res = bn.run_config(name, cfg, torch=torch, dist=dist, rank=rank, world=world, local=local,
+                                    peak_gbs=peak, exhaustive_branches=args.ns_exhaustive_branches if name == "cfg3" else 0,
+                                    log=(lambda *a: print("[north_star]", *a, file=sys.stderr, flush=True)) if rank == 0
+                                    else (lambda *a: None))
+            except Exception as exc:  # a failed extra must not take the headline line with it
+                res = {"error": "%s: %s" % (type(exc).__name__, exc)}
+                if world > 1:
+                    raise
+            torch.cuda.empty_cache()
+            if rank == 0:
+                north_star[name] = res
 
     if rank == 0:
         line = {
@@ -528,29 +558,44 @@ def run_ours(args):
             # the placements in the same order
             "sweep_root0_equals_full_evaluation": bool(sweep_lh[0] == lh0),
         }
+        if north_star is not None:
+            line["north_star"] = north_star
         print(json.dumps(line), flush=True)
-    g.close()
     if world > 1:
         dist.destroy_process_group()
 
 
-def exhaustive_sample(m, branches: int, tol=(1e-7, 1e-7, 1e-12, 1e4), stats=None):
+def exhaustive_sample(m, branches: int, tol=(1e-7, 1e-7, 1e-12, 1e4), stats=None, taxa=0, barrier=lambda: None):
     """exhaustive mode (reference src/model.cpp:1140-1235) on a bounded sample: the first `branches`
     root ids, each optimised to convergence (BFGS over rates / frequencies / Gamma shape + Brent on the
-    root position), timed by wall clock.  stats: optional callable returning the engine's counters
-    (program launches = evaluations).  Returns branches/s and evaluations/s."""
+    root position), timed by wall clock.  stats: optional callable returning the engine's counters.
+    Returns branches/s, full evaluations/s (the unit BFGS is made of: 13 per step on the 12 rates,
+    src/model.cpp:1488-1502) and the latency of compute_dlh (2 root-only evaluations, :481-519: the unit
+    of the alpha loop).  Site-sharded runs call this on every rank (each evaluation all-reduces)."""
     branches = max(1, min(int(branches), m.root_count))
     num_tasks = max(1, -(-m.root_count // branches))  # rank 0 of that many tasks gets <= `branches` ids
     s0 = stats() if stats else None
+    barrier()
     t0 = time.perf_counter()
     ids, llh, alpha = m.exhaustive_search(*tol, rank=0, num_tasks=num_tasks)
+    barrier()
     dt = time.perf_counter() - t0
     out = {"branches": int(len(ids)), "seconds": dt, "branches_per_sec": len(ids) / dt if dt > 0 else None,
-           "best_branch": int(ids[int(np.argmax(llh))]), "best_llh": float(np.max(llh))}
+           "best_branch": int(ids[int(np.argmax(llh))]), "best_llh": float(np.max(llh)),
+           "tolerances": "atol 1e-7, pgtol 1e-7, brtol 1e-12, factor 1e4"}
     if s0 is not None:
         s1 = stats()
-        ev = s1["program_launches"] - s0["program_launches"]
-        out.update(evaluations=int(ev), evaluations_per_sec=ev / dt if dt > 0 else None)
+        ev = s1["root_evals"] - s0["root_evals"]
+        full = (s1["clv_ops"] - s0["clv_ops"]) // max(1, taxa - 1) if taxa else None
+        out.update(root_evaluations=int(ev), evaluations_per_sec=ev / dt if dt > 0 else None,
+                   full_traversals=full, full_evaluations_per_sec=(full / dt if full and dt > 0 else None))
+    reps = 50
+    barrier()
+    t1 = time.perf_counter()
+    for i in range(reps):
+        m.compute_dlh(int(ids[0]), 0.25 + 0.01 * i)
+    barrier()
+    out["us_per_compute_dlh"] = (time.perf_counter() - t1) / reps * 1e6
     return out
 
 

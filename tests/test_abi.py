@@ -56,17 +56,22 @@ def test_host_math_matches_oracle_bit_for_bit():
 
 
 def test_sweep_chunk_hint_rule(monkeypatch):
-    """rdk_sweep_chunk_hint is host arithmetic (148 SMs assumed without a device): the largest chunk count
-    that leaves every warp of a one-wave launch at most 2 iterations; 1 once the shard fills the device"""
+    """rdk_sweep_chunk_hint is host arithmetic (148 SMs assumed without a device): the chunk count that
+    minimises the launch planner's cost model -- (passes) x (time per instruction at the chosen elements
+    per thread and warps per SM) x (1/chunks of the sweep) -- with a chunk more having to pay for
+    itself; 1 once the shard fills the device in whole passes"""
     import torch
     if torch.cuda.is_available() and torch.cuda.get_device_properties(0).multi_processor_count != 148:
         pytest.skip("rule values below are for 148 SMs")
     monkeypatch.delenv("RDK_SWEEP_CHUNKS", raising=False)
     h = capi.sweep_chunk_hint
-    assert h(100000, 4) == 1 and h(25000, 4) == 1 and h(18944, 4) == 1   # >= 2368 warp iterations
-    assert h(12500, 4) == 3 and h(13312, 4) == 2 and h(6250, 4) == 6
-    assert h(1630, 4) == 16 and h(10, 1) == 16 and h(0, 4) == 1          # capped at RDK_SWEEP_MAX_CHUNKS
-    assert h(50000, 1) == 3                                               # 1 category: a quarter of the elements
+    assert h(100000, 4) == 1 and h(125000, 4) == 1 and h(500000, 4) == 1 and h(50000, 4) == 1
+    assert h(62500, 4) == 2      # 1.2 passes of 4 elements per thread: two chunks waste less of the second
+    assert h(25000, 4) == 2 and h(13312, 4) == 3 and h(12500, 4) == 4 and h(6250, 4) == 8
+    assert h(0, 4) == 1
+    for sites in (1, 10, 333, 1630, 5000, 18944, 77777):
+        for k in (1, 3, 4, 16):
+            assert 1 <= h(sites, k) <= 16                                 # RDK_SWEEP_MAX_CHUNKS
     monkeypatch.setenv("RDK_SWEEP_CHUNKS", "5")
     assert h(100000, 4) == 5
 
