@@ -75,7 +75,7 @@ def parse_args():
                          "list of cfg3,cfg4,cfg5, `all`, `off`, or `auto` (= all when --gpus 8, else off)")
     ap.add_argument("--ns-scale", type=float, default=1.0,
                     help="shrink the north-star configs (taxa and sites) by this factor: functional runs on small boxes")
-    ap.add_argument("--ns-exhaustive-branches", type=int, default=2)
+    ap.add_argument("--ns-exhaustive-branches", type=int, default=1)
     ap.add_argument("--launch-config", default="", help="ctas_per_sm,threads,elems (0 = engine default)")
     ap.add_argument("--tail-mode", type=int, default=0, help="0 engine rule, 1 always skip idle slots, 2 never")
     ap.add_argument("--sweep", default="directed", choices=["directed", "path"],

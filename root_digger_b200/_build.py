@@ -7,8 +7,8 @@
                        compiled from where it lies under /root/reference when
                        that tree is present; never copied into this repo
 
-The oracle (test infrastructure) has its own recipe in oracle/Makefile and is
-built by build_oracle(); nothing in the product links it.
+The oracle (test infrastructure) has its own recipes, oracle/Makefile and
+oracle/oracle_build.py; nothing in the product builds, links or loads it.
 """
 from __future__ import annotations
 
@@ -23,7 +23,6 @@ LIBDIR = PKG / "lib"
 CSRC = PKG / "csrc"
 HOST = PKG / "host"
 INCLUDE = ROOT / "include"
-ORACLE = ROOT / "oracle"
 REFERENCE = Path("/root/reference")
 
 NVCC_ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
@@ -97,13 +96,30 @@ def build_engine(force: bool = False, verbose: bool = False, out: Path | None = 
     return out
 
 
-def build_lbfgsb(force: bool = False) -> Path | None:
-    """Compile the reference's vendored L-BFGS-B from /root/reference (if present)."""
+def lbfgsb_source_dir() -> Path | None:
+    """where the L-BFGS-B 3.0 C sources (lbfgsb.c, linesearch.c, subalgorithms.c, linpack.c, miniCBLAS.c,
+    print.c, timer.c -- the files RootDigger vendors under lib/lbfgsb) are: $RDK_LBFGSB_SRC, else the
+    reference checkout.  They are compiled from where they lie, never copied into this repository."""
+    for cand in (os.environ.get("RDK_LBFGSB_SRC"), REFERENCE / "lib" / "lbfgsb"):
+        if cand and Path(cand).is_dir() and list(Path(cand).glob("*.c")):
+            return Path(cand)
+    return None
+
+
+def build_lbfgsb(force: bool = False) -> Path:
+    """lib/liblbfgsb.so (setulb, the optimiser model_t::bfgs_params drives, reference
+    src/model.cpp:1430-1522).  Built from lbfgsb_source_dir(); a library built earlier is kept when
+    the sources are not at hand (the GPU boxes receive the built file).  With neither, the build
+    FAILS here -- not at the first parameter optimisation."""
     LIBDIR.mkdir(exist_ok=True)
     out = LIBDIR / "liblbfgsb.so"
-    src_dir = REFERENCE / "lib" / "lbfgsb"
-    if not src_dir.is_dir():
-        return out if out.exists() else None
+    src_dir = lbfgsb_source_dir()
+    if src_dir is None:
+        if out.exists():
+            return out
+        raise RuntimeError(
+            "liblbfgsb.so cannot be built: no L-BFGS-B sources found. Point RDK_LBFGSB_SRC at a directory holding "
+            "the L-BFGS-B 3.0 C sources (RootDigger's lib/lbfgsb), or provide %s" % out)
     srcs = sorted(src_dir.glob("*.c"))
     if not force and _newer(out, srcs):
         return out
@@ -131,38 +147,8 @@ def build_host(force: bool = False) -> Path:
     return out
 
 
-def build_oracle(force: bool = False) -> Path:
-    """TEST INFRASTRUCTURE: oracle/librd_oracle.so via oracle/Makefile."""
-    out = ORACLE / "librd_oracle.so"
-    deps = [ORACLE / "rd_oracle.c", ORACLE / "rd_oracle.h", ORACLE / "Makefile"]
-    if not force and _newer(out, deps):
-        return out
-    _run(["make", "-C", ORACLE, "-B" if force else "-s"])
-    return out
-
-
-def build_host_on_oracle(force: bool = False) -> Path:
-    """TEST INFRASTRUCTURE: the same host sources compiled against the oracle
-    through tests/oracle_shim/rdk.h -> tests/_build/librd_host_oracle.so."""
-    oracle = build_oracle()
-    build_lbfgsb()
-    outdir = ROOT / "tests" / "_build"
-    outdir.mkdir(exist_ok=True)
-    out = outdir / "librd_host_oracle.so"
-    srcs = [s for s in host_sources() if s.exists()]
-    shim = ROOT / "tests" / "oracle_shim"
-    deps = srcs + list(HOST.glob("*.hpp")) + [shim / "rdk.h", oracle]
-    if not force and _newer(out, deps):
-        return out
-    _run([_cxx(), "-std=c++17", "-O2", "-fPIC", "-fopenmp", "-Wall", "-ffp-contract=off", "-DRD_BACKEND_ORACLE",
-          "-I", shim, "-I", ORACLE, "-shared", "-o", out, *srcs, "-L", ORACLE, "-lrd_oracle", "-ldl",
-          "-Wl,-rpath," + str(ORACLE), "-Wl,-Bsymbolic"])
-    return out
-
-
 def build_all(verbose: bool = False):
+    """the product: engine + L-BFGS-B + host library (the oracle has its own recipe, oracle/oracle_build.py)"""
     build_engine(verbose=verbose)
     build_lbfgsb()
     build_host()
-    build_oracle()
-    build_host_on_oracle()

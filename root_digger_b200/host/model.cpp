@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <exception>
 #include <cstdlib>
 #include <limits>
 #include <numeric>
@@ -26,6 +27,31 @@ static inline size_t compute_final_size(size_t vector_size, double ratio, size_t
 }
 
 static std::string engine_error() { return std::string(rdk_errmsg); }
+
+// Partitions are driven concurrently from OpenMP threads (reference src/model.cpp:397,429,1935).
+// An exception must not leave a parallel region (that terminates the process), and the engine's
+// error message is thread-local: both are caught ON the failing thread and the first one (in
+// partition order) is rethrown after the region.
+template <typename Body>
+static void for_each_partition(size_t n, bool dynamic, Body &&body) {
+  std::vector<std::exception_ptr> errors(n);
+  auto                            guarded = [&](size_t i) {
+    try {
+      body(i);
+    } catch (...) {
+      errors[i] = std::current_exception();
+    }
+  };
+  if (dynamic) {
+#pragma omp parallel for schedule(dynamic)
+    for (size_t i = 0; i < n; ++i) guarded(i);
+  } else {
+#pragma omp parallel for
+    for (size_t i = 0; i < n; ++i) guarded(i);
+  }
+  for (auto &e : errors)
+    if (e) std::rethrow_exception(e);
+}
 
 // ---------------------------------------------------------------------------
 // construction (src/model.cpp:99-182)
@@ -290,12 +316,11 @@ double model_t::compute_lh(const root_location_t &root_location) {
   // association order depends on the thread count; here the per-partition terms are added
   // in partition order so that the result is reproducible on any host.
   std::vector<double> part_lh(_partitions.size(), 0.0);
-#pragma omp parallel for
-  for (size_t i = 0; i < _partitions.size(); ++i) {
+  for_each_partition(_partitions.size(), false, [&](size_t i) {
     if (new_root || updated[i]) rdk_update_clvs(_partitions[i], ops.data(), (unsigned)ops.size());
     part_lh[i] = rdk_compute_root_loglikelihood(_partitions[i], _tree.root_clv_index(),
                                                 _tree.root_scaler_index(), _param_indicies[i].data(), nullptr);
-  }
+  });
   double lh = 0.0;
   for (double v : part_lh) lh += v;
   _last_part_lh = part_lh;
@@ -308,22 +333,15 @@ double model_t::compute_lh_root(const root_location_t &root) {
   rdk_operation_t           op = std::get<0>(result);
   std::vector<unsigned int> matrix_indices = std::move(std::get<1>(result));
   std::vector<double>       branch_lengths = std::move(std::get<2>(result));
-  bool                      failed = false;
   std::vector<double>       part_lh(_partitions.size(), 0.0);  // summed in partition order (see compute_lh)
-#pragma omp parallel for
-  for (size_t i = 0; i < _partitions.size(); ++i) {
+  for_each_partition(_partitions.size(), false, [&](size_t i) {
     int rc = rdk_update_prob_matrices(_partitions[i], _param_indicies[i].data(), matrix_indices.data(),
                                       branch_lengths.data(), (unsigned)matrix_indices.size());
-    if (rc == RDK_FAILURE) {
-#pragma omp atomic write
-      failed = true;
-      continue;
-    }
+    if (rc == RDK_FAILURE) throw std::runtime_error(engine_error());  // the message of THIS thread
     rdk_update_clvs(_partitions[i], &op, 1);
     part_lh[i] = rdk_compute_root_loglikelihood(_partitions[i], _tree.root_clv_index(),
                                                 _tree.root_scaler_index(), _param_indicies[i].data(), nullptr);
-  }
-  if (failed) throw std::runtime_error(engine_error());
+  });
   double lh = 0.0;
   for (double v : part_lh) lh += v;
   _last_part_lh = part_lh;
@@ -1034,8 +1052,7 @@ void model_t::optimize_params(std::vector<partition_parameters_t> &params, const
   std::vector<unsigned int>    pmatrix_indices;
   std::vector<double>          branch_lengths;
   GENERATE_AND_UNPACK_OPS(_tree, rl, ops, pmatrix_indices, branch_lengths);
-#pragma omp parallel for schedule(dynamic)
-  for (size_t i = 0; i < _partitions.size(); ++i) {
+  for_each_partition(_partitions.size(), true, [&](size_t i) {
     set_subst_rates(i, params[i].subst_rates);
     set_freqs_all_free(i, params[i].freqs);
     set_gamma_rates(i, params[i].gamma_alpha);
@@ -1049,7 +1066,7 @@ void model_t::optimize_params(std::vector<partition_parameters_t> &params, const
         bfgs_gamma_weights(params[i].gamma_weights, ops, pmatrix_indices, branch_lengths, i, pgtol,
                            factor);
     }
-  }
+  });
 }
 
 // src/model.cpp:1737-1746

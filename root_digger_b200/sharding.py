@@ -93,6 +93,10 @@ class PartitionShardedModel:
 
     def __init__(self, local_model, n_partitions: int, rank: int, nranks: int, dist, device="cpu"):
         self.m, self.P, self.rank, self.nranks, self.dist, self.device = local_model, n_partitions, rank, nranks, dist, device
+        if nranks > n_partitions:
+            # a rank without a partition would have no model_t to call (and nothing to all-gather)
+            raise ValueError("partition sharding needs at most as many ranks (%d) as partitions (%d)"
+                             % (nranks, n_partitions))
         self.owned = plan_partition_shards(n_partitions, nranks)
         if local_model.partition_count != len(self.owned[rank]):
             raise ValueError("the local model must hold exactly this rank's partitions")

@@ -10,7 +10,10 @@ from pathlib import Path
 
 import numpy as np
 
-from root_digger_b200 import _build
+import sys
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "oracle"))
+import oracle_build  # noqa: E402
 from root_digger_b200.capi import Operation, ops_array
 
 MODE_REFERENCE = 0
@@ -49,9 +52,9 @@ def load_oracle() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.ORACLE / "librd_oracle.so"
+    path = oracle_build.ORACLE / "librd_oracle.so"
     if not path.exists():
-        _build.build_oracle()
+        oracle_build.build_oracle()
     L = C.CDLL(str(path))
     L.rdo_partition_create.restype = _pp
     L.rdo_partition_create.argtypes = [C.c_uint] * 9

@@ -14,7 +14,8 @@ import numpy as np
 import pytest
 
 import oracle_capi
-from root_digger_b200 import _build, capi
+import oracle_build
+from root_digger_b200 import capi
 
 MOD = 65521
 
@@ -22,7 +23,7 @@ MOD = 65521
 @pytest.fixture(scope="module")
 def lib():
     oracle_capi.load_oracle().rdo_set_default_mode(oracle_capi.MODE_ENGINE)
-    return capi.load_tree_lib(_build.build_host_on_oracle())
+    return capi.load_tree_lib(oracle_build.build_host_on_oracle())
 
 
 # ---- independent restatement of the format -------------------------------------------------

@@ -8,7 +8,8 @@ import pytest
 
 import fixtures
 import oracle_capi
-from root_digger_b200 import _build, capi, synth
+import oracle_build
+from root_digger_b200 import capi, synth
 
 pytestmark = pytest.mark.gpu
 
@@ -16,7 +17,7 @@ pytestmark = pytest.mark.gpu
 @pytest.fixture(scope="module")
 def libs():
     oracle_capi.load_oracle().rdo_set_default_mode(oracle_capi.MODE_ENGINE)
-    return capi.load_tree_lib(), capi.load_tree_lib(_build.build_host_on_oracle())
+    return capi.load_tree_lib(), capi.load_tree_lib(oracle_build.build_host_on_oracle())
 
 
 def pair(libs, name="10.fasta", K=4, uniform=True, seed=4242):

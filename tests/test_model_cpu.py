@@ -8,13 +8,14 @@ import pytest
 
 import fixtures
 import oracle_capi
-from root_digger_b200 import _build, capi
+import oracle_build
+from root_digger_b200 import capi
 
 
 @pytest.fixture(scope="module")
 def lib():
     oracle_capi.load_oracle().rdo_set_default_mode(oracle_capi.MODE_ENGINE)
-    return capi.load_tree_lib(_build.build_host_on_oracle())
+    return capi.load_tree_lib(oracle_build.build_host_on_oracle())
 
 
 def make_model(lib, name="10.fasta", K=1, seed=12345, uniform=True, **kw):

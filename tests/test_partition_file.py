@@ -8,7 +8,8 @@ import pytest
 
 import fixtures
 import oracle_capi
-from root_digger_b200 import _build, capi
+import oracle_build
+from root_digger_b200 import capi
 
 RANGES = [(123, 4123), (5122, 12411)]
 TAIL = ",PART_0=123-4123, 5122-12411"
@@ -17,7 +18,7 @@ TAIL = ",PART_0=123-4123, 5122-12411"
 @pytest.fixture(scope="module")
 def lib():
     oracle_capi.load_oracle().rdo_set_default_mode(oracle_capi.MODE_ENGINE)
-    return capi.load_tree_lib(_build.build_host_on_oracle())
+    return capi.load_tree_lib(oracle_build.build_host_on_oracle())
 
 
 def one(lib, line):

@@ -115,9 +115,10 @@ def _partition_worker(rank, world, port, q):
     import torch.distributed as dist
     import fixtures
     import oracle_capi
-    from root_digger_b200 import _build, capi
+    import oracle_build
+    from root_digger_b200 import capi
     oracle_capi.load_oracle().rdo_set_default_mode(oracle_capi.MODE_ENGINE)
-    lib = capi.load_tree_lib(_build.build_host_on_oracle())
+    lib = capi.load_tree_lib(oracle_build.build_host_on_oracle())
     dist.init_process_group("gloo", rank=rank, world_size=world)
     fx = fixtures.load("10.fasta")
     mine = [PARTS[p] for p in sharding.plan_partition_shards(len(PARTS), world)[rank]]
@@ -150,9 +151,10 @@ def test_two_rank_gloo_partition_sharding_matches_single_process():
     import torch.multiprocessing as mp
     import fixtures
     import oracle_capi
-    from root_digger_b200 import _build, capi
+    import oracle_build
+    from root_digger_b200 import capi
     oracle_capi.load_oracle().rdo_set_default_mode(oracle_capi.MODE_ENGINE)
-    lib = capi.load_tree_lib(_build.build_host_on_oracle())
+    lib = capi.load_tree_lib(oracle_build.build_host_on_oracle())
     fx = fixtures.load("10.fasta")
     tree = capi.RootedTree(path=str(fx["tree_path"]), lib=lib)
     m = capi.Model(tree, fx["alignment"], rate_cats=4, compress=True, seed=3, partitions=PARTS)
@@ -184,9 +186,10 @@ def test_sweep_chunk_count_is_agreed_across_site_shards():
     (test) hint would say 1 chunk for the first and 3 for the second"""
     import oracle_capi
     from cases import Case
-    from root_digger_b200 import _build, capi
+    import oracle_build
+    from root_digger_b200 import capi
     oracle_capi.load_oracle().rdo_set_default_mode(oracle_capi.MODE_ENGINE)
-    lib = capi.load_tree_lib(_build.build_host_on_oracle())
+    lib = capi.load_tree_lib(oracle_build.build_host_on_oracle())
     S = 8000
     case = Case(12, S, 4, seed=3, data="iid")
     shards = sharding.plan_site_shards(S, 2)
