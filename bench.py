@@ -76,6 +76,9 @@ def parse_args():
     ap.add_argument("--ns-scale", type=float, default=1.0,
                     help="shrink the north-star configs (taxa and sites) by this factor: functional runs on small boxes")
     ap.add_argument("--ns-exhaustive-branches", type=int, default=1)
+    ap.add_argument("--ns-exhaustive-iterations", type=int, default=2,
+                    help="cap on the outer iterations per branch of the cfg3 exhaustive sample (0 = to convergence: "
+                         "~9e4 full evaluations, 7 minutes per branch on 8 GPUs)")
     ap.add_argument("--launch-config", default="", help="ctas_per_sm,threads,elems (0 = engine default)")
     ap.add_argument("--tail-mode", type=int, default=0, help="0 engine rule, 1 always skip idle slots, 2 never")
     ap.add_argument("--sweep", default="directed", choices=["directed", "path"],
@@ -231,7 +234,8 @@ def cpu_reference_run(args, case, steps, warmup, threads, target_step_s=1.5, qui
             "sample": "oracle/rd_oracle.c (CPU restatement; coraxlib is an absent submodule), OpenMP site-parallel, "
                       "%d of %d sites of the same alignment, all %d placements, %d steps; scaled by sites"
                       % (sample, S, len(roots), steps),
-            "ms_per_step_full_size": ms_step_full}
+            "ms_per_step_full_size": ms_step_full, "ms_per_step_sample": ms_step_sample, "timed_seconds": dt,
+            "sample_sites": sample}
     return value, info, ms_step_full
 
 
@@ -260,14 +264,21 @@ def run_reference(args):
         "cpu_baseline": info,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "native_libraries_mapped": sorted({l.split("/")[-1].strip() for l in open("/proc/self/maps")
+                                           if "/root_digger_b200/lib/" in l or "/tests/_build/" in l or "/oracle/" in l}),
     }
     print(json.dumps(line), flush=True)
 
 
 def build_case_cpu(args):
-    """the reference arm must not need the CUDA library: gamma categories from the oracle"""
+    """the reference arm must not map the CUDA libraries: gamma categories from the oracle, traversal
+    schedules from the host sources compiled against the oracle (tests/_build/librd_host_oracle.so)"""
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import oracle_build
     from cases import Case
-    return Case(args.taxa, args.sites, args.cats, seed=args.seed, data=args.data, alpha=1.0)
+    from root_digger_b200 import capi
+    lib = capi.load_tree_lib(oracle_build.build_host_on_oracle())
+    return Case(args.taxa, args.sites, args.cats, seed=args.seed, data=args.data, alpha=1.0, tree_lib=lib)
 
 
 def workload_config(args, placements, grid=None):
@@ -426,8 +437,17 @@ def run_ours(args):
     prog_s = st["program_time_ns"] * 1e-9
     achieved = st["algorithmic_bytes"] / prog_s / 1e9 if prog_s > 0 else 0.0
     per_launch = st["algorithmic_bytes"] / max(1, st["program_timed"])
+    prof = dram_traffic_from_profiles(n, cnt, K)
+    launches_per_step = max(1, st["program_timed"]) / args.steps
+    traffic = prof["dram_bytes_per_step"] / launches_per_step if prof else None
     roofline = {"bound": "hbm", "kernel": "clv_program_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": dram_traffic_from_profiles(),
+                "frac": achieved / peak, "traffic": traffic,
+                # measured DRAM bytes / kernel time / peak: how busy HBM really is (the contract `frac` counts
+                # the algorithmic bytes, most of which the kernel forwards in registers or finds in L2)
+                "dram_frac": (traffic / (prog_s / max(1, st["program_timed"])) / 1e9 / peak) if traffic and prog_s > 0 else None,
+                "traffic_source": prof["source"] if prof else "this per-GPU configuration (%dx%dx%d) has no committed ncu "
+                                                              "capture: null, not a number from another shape" % (n, cnt, K),
+                "min_traffic": min_step_traffic(n, cnt, K) / launches_per_step,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": per_launch,
                 "avg_launch_ms": prog_s * 1e3 / max(1, st["program_timed"]),
                 "launches_timed": st["program_timed"],
@@ -527,6 +547,7 @@ def run_ours(args):
             try:
                 res = bn.run_config(name, cfg, torch=torch, dist=dist, rank=rank, world=world, local=local,
                                     peak_gbs=peak, exhaustive_branches=args.ns_exhaustive_branches if name == "cfg3" else 0,
+                                    exhaustive_iterations=args.ns_exhaustive_iterations,
                                     log=(lambda *a: print("[north_star]", *a, file=sys.stderr, flush=True)) if rank == 0
                                     else (lambda *a: None))
             except Exception as exc:  # a failed extra must not take the headline line with it
@@ -599,15 +620,23 @@ def exhaustive_sample(m, branches: int, tol=(1e-7, 1e-7, 1e-12, 1e4), stats=None
     return out
 
 
-def dram_traffic_from_profiles():
-    """dram bytes per launch of clv_program_kernel from the committed ncu --set full summary, if any"""
+def dram_traffic_from_profiles(taxa, sites_per_gpu, cats):
+    """measured DRAM bytes of the program-kernel launches of one step for THIS per-GPU configuration, from
+    the committed ncu --set full summaries (profiles/clv_program_traffic.json); None when that
+    configuration was never profiled -- a number measured on another shape is not reported"""
     p = ROOT / "profiles" / "clv_program_traffic.json"
-    if p.exists():
-        try:
-            return json.loads(p.read_text()).get("dram_bytes_per_launch")
-        except Exception:
-            return None
-    return None
+    try:
+        return json.loads(p.read_text())["entries"].get("%dx%dx%d" % (taxa, sites_per_gpu, cats))
+    except Exception:
+        return None
+
+
+def min_step_traffic(n, sites, K):
+    """bytes one step cannot avoid moving through HBM (SURVEY 8d sizes): the full evaluation writes every
+    inner CLV once and reads the tips; the directed sweep reads every inner CLV once (as the sibling of
+    the placement next to it -- the directed CLVs it derives can live in L2 / registers) and the tips"""
+    clv = 32 * K * sites
+    return (n - 1) * clv + n * sites + (n - 2) * clv + n * sites
 
 
 def main():

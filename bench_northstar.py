@@ -126,7 +126,7 @@ def oracle_window(setup: Setup, lo: int, width: int):
 
 def run_config(name: str, cfg: dict, *, torch, dist, rank: int, world: int, local: int, peak_gbs: float,
                seed: int = 0x5EED0000, window: int = 256, steps: int = 3, exhaustive_branches: int = 0,
-               log=lambda *a: None) -> dict | None:
+               exhaustive_iterations: int = 0, log=lambda *a: None) -> dict | None:
     from root_digger_b200 import capi
     from root_digger_b200.capi import Model, RootedTree
     from root_digger_b200.sharding import PartitionShardedModel, plan_partition_shards, plan_site_shards
@@ -297,6 +297,7 @@ def run_config(name: str, cfg: dict, *, torch, dist, rank: int, world: int, loca
         reset(False)
         branches = max(1, min(exhaustive_branches, placements))
         num_tasks = max(1, -(-placements // branches))
+        m.set_max_outer_iterations(exhaustive_iterations)
         s0 = stats()
         barrier()
         t0 = time.perf_counter()
@@ -317,7 +318,11 @@ def run_config(name: str, cfg: dict, *, torch, dist, rank: int, world: int, loca
         out["exhaustive"] = {
             "branches": int(len(ids)), "seconds": dt, "branches_per_sec": len(ids) / dt,
             "root_evaluations": int(evals), "full_traversals": int(full), "full_evaluations_per_sec": full / dt,
-            "us_per_compute_dlh": dlh_us, "tolerances": "atol 1e-7, pgtol 1e-7, brtol 1e-12, factor 1e4 "
+            "us_per_compute_dlh": dlh_us,
+            "outer_iterations_per_branch": ("capped at %d (a converged branch of this size is ~9e4 full evaluations: "
+                                            "426 s in profiles/r02_bench_n8_north_star.json)" % exhaustive_iterations)
+            if exhaustive_iterations else "to convergence (reference loop, <= 1000)",
+            "tolerances": "atol 1e-7, pgtol 1e-7, brtol 1e-12, factor 1e4 "
                                                         "(reference src/model.cpp:1140 defaults)",
             "best_branch": int(ids[int(np.argmax(llh))]), "best_llh": float(np.max(llh)),
             "lwr_of_sample": [float(x) for x in m.lwr(llh)], "alpha_of_sample": [float(a) for a in alpha]}

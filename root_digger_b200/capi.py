@@ -673,6 +673,8 @@ def _bind_model(L: C.CDLL):
     L.rdh_model_set_checkpoint.argtypes = [vp, C.c_char_p]
     L.rdh_model_sweep_chunks.argtypes = [vp]
     L.rdh_model_sweep_chunks.restype = C.c_uint
+    L.rdh_model_set_max_outer_iterations.argtypes = [vp, C.c_uint]
+    L.rdh_model_set_max_outer_iterations.restype = None
     L.rdh_model_last_partition_lh.argtypes = [vp, _dp, C.c_uint]
     L.rdh_model_last_sweep_partition_lh.argtypes = [vp, C.c_uint, _dp, C.c_uint]
     L.rdh_model_assign_indicies.argtypes = [vp, C.c_int, C.c_uint, C.c_double, C.c_uint, C.c_uint, C.c_int, _up,
@@ -1020,6 +1022,10 @@ class Model:
         """log search / exhaustive_search results to "<prefix>.ckp" (the reference's on-disk format);
         a file that already holds results makes the next run resume from it"""
         self._check(self.L.rdh_model_set_checkpoint(self.h, prefix.encode() if prefix is not None else None))
+
+    def set_max_outer_iterations(self, n: int):
+        """cap the outer iterations of search / exhaustive_search per root (0 = the reference's 1000)"""
+        self.L.rdh_model_set_max_outer_iterations(self.h, int(n))
 
     @property
     def sweep_chunks(self) -> int:

@@ -745,7 +745,7 @@ std::pair<root_location_t, double> model_t::search(size_t min_roots, double root
     auto   cur_best_rl = rl;
     double cur_best_lh = -std::numeric_limits<double>::infinity();
 
-    for (size_t iter = 0; iter < 1e3; ++iter) {
+    for (size_t iter = 0; iter < _max_outer_iterations; ++iter) {
       saved_params = params;
       optimize_params(params, rl, pgtol, factor, true);
       auto cur = optimize_root_location(min_roots, root_ratio);
@@ -816,7 +816,7 @@ std::pair<root_location_t, double> model_t::exhaustive_search(double atol, doubl
     root_location_t cur_best_rl = rl;
     double          cur_best_llh = -std::numeric_limits<double>::infinity();
 
-    for (size_t iter = 0; iter < 1e3; ++iter) {
+    for (size_t iter = 0; iter < _max_outer_iterations; ++iter) {
       optimize_params(params, rl, pgtol, factor, (iter % 10 == 0));  // Appendix B-7
       if (fabs(compute_lh(rl) - cur_best_llh) < atol) break;
       auto   cur_rl = optimize_alpha(rl, brtol);

@@ -114,6 +114,10 @@ public:
   // that gives every GPU its own partitions (BASELINE cfg4) needs the TERMS to
   // rebuild that same ordered sum across ranks (root_digger_b200.sharding.PartitionShardedModel).
   unsigned int sweep_chunks() const { return _sweep_chunks; }  // independent chunks of a directed sweep
+  // outer iterations of search / exhaustive_search per root (the reference's loops run to 1e3,
+  // src/model.cpp:1051,1171); a smaller cap bounds a benchmark sample, results are then not converged
+  void   set_max_outer_iterations(size_t n) { _max_outer_iterations = n ? n : 1000; }
+  size_t max_outer_iterations() const { return _max_outer_iterations; }
   const std::vector<double> &last_partition_lh() const { return _last_part_lh; }
   // ... and of the last sweep_root_lh: [partition][placement of the swept range]
   const std::vector<std::vector<double>> &last_sweep_partition_lh() const { return _last_sweep_part_lh; }
@@ -201,6 +205,7 @@ private:
   std::vector<std::vector<double>>       _last_sweep_part_lh;
   unsigned int                           _sweep_extra = 0;   // spare directed-CLV buffers per sweep chunk
   unsigned int                           _sweep_chunks = 1;  // independent chunks of a directed sweep
+  size_t                                 _max_outer_iterations = 1000;
   static constexpr unsigned int          _submodels = 1;
 };
 

@@ -168,6 +168,7 @@ extern "C" void rdh_model_destroy(void *h) { delete reinterpret_cast<holder_t *>
 extern "C" unsigned rdh_model_sites(void *h, unsigned part) { return H(h).msa[part].length(); }
 extern "C" unsigned rdh_model_root_count(void *h) { return (unsigned)H(h).model->tree().root_count(); }
 extern "C" unsigned rdh_model_sweep_chunks(void *h) { return H(h).model->sweep_chunks(); }
+extern "C" void rdh_model_set_max_outer_iterations(void *h, unsigned n) { H(h).model->set_max_outer_iterations(n); }
 
 extern "C" int rdh_model_initialize_partitions(void *h, int uniform_freqs) {
   RDH_TRY({
