@@ -327,6 +327,8 @@ typedef struct rdk_stats {
   unsigned long long instructions;      /* program instructions launched (operations + the
                                            register loads the lowering inserted)           */
   unsigned long long stores_elided;     /* CLV stores dropped because nothing reads them back */
+  unsigned long long lazy_evaluations;  /* full evaluations that kept CLVs in registers only  */
+  unsigned long long materializations;  /* kept programs replayed with all their stores       */
 } rdk_stats_t;
 void rdk_partition_stats(rdk_partition_t *partition, rdk_stats_t *out);
 void rdk_partition_reset_stats(rdk_partition_t *partition);
@@ -337,6 +339,17 @@ int rdk_partition_set_timing(rdk_partition_t *partition, int enabled);
 int rdk_partition_set_launch_config(rdk_partition_t *partition,
                                     int ctas_per_sm, int threads_per_cta,
                                     int elems_per_thread);
+/* Lazily materialised evaluations (default on; RDK_LAZY=0 in the environment turns them off for
+ * partitions created afterwards).  A full traversal whose only requested result is the root
+ * log-likelihood -- rdk_update_clvs of >= 16 operations followed by
+ * rdk_compute_root_loglikelihood(..., persite_lnl = NULL) on the CLV the last operation produces,
+ * i.e. compute_lh_partition inside the BFGS closures (src/model.cpp:455-476, 1488-1502) -- stores
+ * only the CLVs it reads back itself, from the second such traversal in a row onwards (a single
+ * compute_lh before a sweep or a root move would only have to be replayed).  The engine keeps the operations and replays them with all
+ * their stores before anything reads such a CLV (the next traversal overwriting all of them drops
+ * the kept program instead).  Results and observable partition state are those of eager
+ * execution, bit for bit. */
+int rdk_partition_set_lazy(rdk_partition_t *partition, int enabled);
 /* accepted and ignored (round-1 kernels had two tail rules); results never depended on it */
 int rdk_partition_set_tail_mode(rdk_partition_t *partition, int mode);
 const char *rdk_version(void);

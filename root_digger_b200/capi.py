@@ -61,7 +61,8 @@ class Stats(C.Structure):
     _fields_ = [(n, C.c_ulonglong) for n in (
         "kernel_launches", "program_launches", "pmatrix_launches", "reduce_launches", "clv_ops",
         "root_evals", "pmatrices", "algorithmic_bytes", "h2d_bytes", "d2h_bytes", "device_bytes",
-        "program_time_ns", "program_timed", "instructions", "stores_elided")]
+        "program_time_ns", "program_timed", "instructions", "stores_elided", "lazy_evaluations",
+        "materializations")]
 
     def asdict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
@@ -152,6 +153,7 @@ def load_engine() -> C.CDLL:
     L.rdk_partition_set_launch_config.argtypes = [_pp, C.c_int, C.c_int, C.c_int]
     L.rdk_partition_set_timing.argtypes = [_pp, C.c_int]
     L.rdk_partition_set_tail_mode.argtypes = [_pp, C.c_int]
+    L.rdk_partition_set_lazy.argtypes = [_pp, C.c_int]
     L.rdk_set_device.argtypes = [C.c_int]
     _engine_lib = L
     return L
@@ -336,6 +338,11 @@ class Partition:
 
     def set_launch_config(self, ctas_per_sm=0, threads=0, elems=0):
         if self.L.rdk_partition_set_launch_config(self.p, ctas_per_sm, threads, elems) != RDK_SUCCESS:
+            raise EngineError(_err(self.L))
+
+    def set_lazy(self, enabled: bool):
+        """rdk_partition_set_lazy: lazily materialised full evaluations on / off"""
+        if self.L.rdk_partition_set_lazy(self.p, 1 if enabled else 0) != RDK_SUCCESS:
             raise EngineError(_err(self.L))
 
     def set_tail_mode(self, mode: int = 0):

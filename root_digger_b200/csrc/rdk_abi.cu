@@ -153,6 +153,22 @@ struct Engine {
   // recorded work
   std::vector<PmatEntry> pend_pm;
   std::vector<ROp>       pend_prog;
+  // Lazily materialised evaluation.  A full evaluation whose only requested result is the root
+  // log-likelihood (the closure BFGS calls 13 times per step, reference src/model.cpp:455-476,
+  // 1488-1502) stores only the CLVs it reads back itself; the others exist in registers only.  The
+  // recorded operations (with the P-matrix slots they used, held back from recycling) are kept:
+  // the next program either rewrites every stale buffer without reading it (the next BFGS
+  // evaluation: the kept program is dropped) or makes the engine replay the kept program with
+  // all its stores first.  Semantics are those of eager execution.
+  struct Lazy {
+    bool                  active = false;
+    std::vector<ROp>      ops;
+    std::vector<char>     stale_clv, stale_sc;  // per index: the value in memory is not the current one
+    std::vector<unsigned> held;                 // P-matrix slots retired while the program is kept
+  } lazy;
+  bool     lazy_enabled = true;
+  unsigned full_streak = 0;  // consecutive flushed programs that were lazy-eligible full traversals
+  bool pend_lazy_ok = false;  // the pending program may be evaluated lazily
   // buffers whose content after pend_prog is not required (scratch of a directed sweep), per index
   const std::vector<char> *pend_scratch_clv = nullptr, *pend_scratch_sc = nullptr;
   unsigned               pend_slots = 0;  // eval slots used by pend_prog
@@ -467,6 +483,116 @@ void to_device_instr(Engine *e, const LInstr &li, Instr *out) {
   *out = in;
 }
 
+int materialize_lazy(rdk_partition_t *p);
+
+// copy a lowered program to the device and launch the program kernel over the whole shard
+int launch_lowered(rdk_partition_t *p, ProgArgs &a, const std::vector<LInstr> &lowered,
+                   const std::vector<unsigned> &lchunk, bool chunked, bool timed) {
+  Engine        *e = eng(p);
+  const unsigned n_witer = a.n_witer;
+  a.n_instr = (int)lowered.size();
+  a.n_chunks = 0;
+  a.prog = nullptr;
+  if (chunked) {
+    a.n_chunks = (unsigned)lchunk.size() - 1;
+    for (size_t c = 0; c < lchunk.size(); ++c) a.chunk_off[c] = lchunk[c];
+  }
+  if (a.n_instr <= kProgInline && !chunked) {
+    for (int i = 0; i < a.n_instr; ++i) to_device_instr(e, lowered[i], &a.inl[i]);
+  } else {
+    char  *h, *d;
+    size_t bytes = sizeof(Instr) * lowered.size();
+    if (!ring_alloc(e, bytes, &h, &d)) return RDK_FAILURE;
+    Instr *hp = reinterpret_cast<Instr *>(h);
+    for (size_t i = 0; i < lowered.size(); ++i) to_device_instr(e, lowered[i], &hp[i]);
+    CUDA_TRY(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, e->stream));
+    e->stats.h2d_bytes += bytes;
+    a.prog = reinterpret_cast<const Instr *>(d);
+  }
+  if (a.nelem == 0 || a.n_instr == 0) return RDK_SUCCESS;
+  LaunchSeg seg[2];
+  const int n_seg = plan_segments(e, n_witer, chunked ? a.n_chunks : 1u, a.n_instr, seg);
+  std::pair<cudaEvent_t, cudaEvent_t> *ev = (timed && e->timing) ? next_event_pair(e) : nullptr;
+  if (ev) CUDA_TRY(cudaEventRecord(ev->first, e->stream));
+  for (int g = 0; g < n_seg; ++g) {
+    const LaunchPlan &pl = seg[g].pl;
+    a.it0 = seg[g].it0;
+    a.n_witer = seg[g].n_witer;
+    cudaError_t lerr;
+    switch (e->K) {
+      case 1: lerr = launch_program<1>(a, pl.grid, pl.threads, pl.E, e->stream); break;
+      case 2: lerr = launch_program<2>(a, pl.grid, pl.threads, pl.E, e->stream); break;
+      case 4: lerr = launch_program<4>(a, pl.grid, pl.threads, pl.E, e->stream); break;
+      case 8: lerr = launch_program<8>(a, pl.grid, pl.threads, pl.E, e->stream); break;
+      case 16: lerr = launch_program<16>(a, pl.grid, pl.threads, pl.E, e->stream); break;
+      case 32: lerr = launch_program<32>(a, pl.grid, pl.threads, pl.E, e->stream); break;
+      default: return fail(RDK_ERROR_PARAM, "rate_cats must divide 32");
+    }
+    if (lerr != cudaSuccess) return fail(RDK_ERROR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(lerr));
+    CUDA_TRY(cudaGetLastError());
+    e->stats.kernel_launches++;
+  }
+  a.n_witer = n_witer;
+  a.it0 = 0;
+  if (ev) CUDA_TRY(cudaEventRecord(ev->second, e->stream));
+  e->stats.program_launches++;
+  return RDK_SUCCESS;
+}
+
+void release_lazy(Engine *e) {
+  for (unsigned s : e->lazy.held) e->pm_free.push_back(s);
+  e->lazy.held.clear();
+  e->lazy.ops.clear();
+  e->lazy.active = false;
+}
+
+// replay the kept program with all its stores: every buffer holds its current value afterwards
+int materialize_lazy(rdk_partition_t *p) {
+  Engine *e = eng(p);
+  if (!e->lazy.active) return RDK_SUCCESS;
+  ProgArgs a;
+  memset(&a, 0, sizeof(a));
+  a.nelem = e->S * e->K;
+  a.n_witer = (a.nelem + 31) / 32;
+  a.weights = e->d_weights;
+  a.partial_stride = a.n_witer ? a.n_witer : 1;
+  std::vector<LInstr>   lowered;
+  std::vector<unsigned> lchunk;
+  LowerOptions          lopt;
+  lopt.tips = e->tips;
+  lower_program(e->lazy.ops, std::vector<unsigned>(), lopt, lowered, lchunk, nullptr);
+  e->stats.instructions += lowered.size();
+  e->stats.materializations++;
+  if (!launch_lowered(p, a, lowered, lchunk, false, false)) return RDK_FAILURE;
+  std::fill(e->lazy.stale_clv.begin(), e->lazy.stale_clv.end(), 0);
+  std::fill(e->lazy.stale_sc.begin(), e->lazy.stale_sc.end(), 0);
+  release_lazy(e);
+  e->full_streak = 0;
+  return RDK_SUCCESS;
+}
+
+// does the pending program read a stale buffer, or leave one stale?  (every child reference counts
+// as a read from memory: the lowering may forward it in registers, the test is conservative)
+bool pending_needs_materialization(const Engine *e) {
+  const auto       &L = e->lazy;
+  std::vector<char> wc(L.stale_clv.size(), 0), ws(L.stale_sc.size(), 0);
+  auto stale_c = [&](unsigned c) { return c != kNoClv && c < L.stale_clv.size() && L.stale_clv[c] && !wc[c]; };
+  auto stale_s = [&](int s) { return s >= 0 && (size_t)s < L.stale_sc.size() && L.stale_sc[s] && !ws[s]; };
+  for (const ROp &r : e->pend_prog) {
+    if (stale_c(r.c1) || stale_s(r.c1scale)) return true;
+    if (!(r.flags & rLoadOnly) && (stale_c(r.c2) || stale_s(r.c2scale))) return true;
+    if (r.flags & rWrite) {
+      if (r.parent < wc.size()) wc[r.parent] = 1;
+      if (r.pscale >= 0 && (size_t)r.pscale < ws.size()) ws[r.pscale] = 1;
+    }
+  }
+  for (size_t c = 0; c < wc.size(); ++c)
+    if (L.stale_clv[c] && !wc[c]) return true;
+  for (size_t s = 0; s < ws.size(); ++s)
+    if (L.stale_sc[s] && !ws[s]) return true;
+  return false;
+}
+
 // launch recorded P-matrix work and the recorded program (no host sync)
 int flush(rdk_partition_t *p) {
   Engine *e = eng(p);
@@ -475,6 +601,14 @@ int flush(rdk_partition_t *p) {
     for (unsigned s : e->pm_retired) e->pm_free.push_back(s);
     e->pm_retired.clear();
     return RDK_SUCCESS;
+  }
+  // a kept (lazily evaluated) program: superseded by this one, or replayed before it
+  if (e->lazy.active) {
+    if (pending_needs_materialization(e)) {
+      if (!materialize_lazy(p)) return RDK_FAILURE;
+    } else {
+      release_lazy(e);  // every stale buffer is rewritten without being read: nothing to keep
+    }
   }
   const unsigned nelem = e->S * e->K;
   const unsigned n_witer = (nelem + 31) / 32;
@@ -493,64 +627,56 @@ int flush(rdk_partition_t *p) {
   a.persite = e->want_persite ? e->d_persite : nullptr;
   // recorded operations -> the instructions the kernel walks (rdk_lower.hpp)
   const bool            chunked = e->pend_chunk_off.size() > 2;
+  // Lazy only in a STREAK of such traversals (the second consecutive one onwards): that is the
+  // signature of a BFGS closure -- 13 evaluations per step, reference src/model.cpp:1488-1502 --
+  // whereas the single compute_lh before a sweep or a root move would only have to be replayed
+  // (measured on B200, cfg2 search step: 9.06 ms with an always-lazy compute_lh against 8.03 ms).
+  e->full_streak = e->pend_lazy_ok ? e->full_streak + 1 : 0;
+  const bool lazy = e->pend_lazy_ok && e->full_streak >= 2 && e->lazy_enabled && !chunked && !e->pend_scratch_clv;
   std::vector<LInstr>   lowered;
   std::vector<unsigned> lchunk;
   LowerOptions          lopt;
   lopt.tips = e->tips;
   lopt.scratch_clv = e->pend_scratch_clv;
   lopt.scratch_scaler = e->pend_scratch_sc;
+  lopt.discard_writes = lazy;  // keep only the stores the program reads back itself
   LowerStats lst;
   lower_program(e->pend_prog, chunked ? e->pend_chunk_off : std::vector<unsigned>(), lopt, lowered, lchunk, &lst);
   e->stats.instructions += lowered.size();
   e->stats.stores_elided += lst.stores_dropped;
-  a.n_instr = (int)lowered.size();
-  if (chunked) {
-    a.n_chunks = (unsigned)lchunk.size() - 1;
-    for (size_t c = 0; c < lchunk.size(); ++c) a.chunk_off[c] = lchunk[c];
-  }
-  if (a.n_instr <= kProgInline && !chunked) {
-    for (int i = 0; i < a.n_instr; ++i) to_device_instr(e, lowered[i], &a.inl[i]);
-  } else {
-    char  *h, *d;
-    size_t bytes = sizeof(Instr) * lowered.size();
-    if (!ring_alloc(e, bytes, &h, &d)) return RDK_FAILURE;
-    Instr *hp = reinterpret_cast<Instr *>(h);
-    for (size_t i = 0; i < lowered.size(); ++i) to_device_instr(e, lowered[i], &hp[i]);
-    CUDA_TRY(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, e->stream));
-    e->stats.h2d_bytes += bytes;
-    a.prog = reinterpret_cast<const Instr *>(d);
-  }
-  if (nelem > 0 && a.n_instr > 0) {
-    LaunchSeg seg[2];
-    const int n_seg = plan_segments(e, n_witer, chunked ? a.n_chunks : 1u, a.n_instr, seg);
-    std::pair<cudaEvent_t, cudaEvent_t> *ev = e->timing ? next_event_pair(e) : nullptr;
-    if (ev) CUDA_TRY(cudaEventRecord(ev->first, e->stream));
-    for (int g = 0; g < n_seg; ++g) {
-      const LaunchPlan &pl = seg[g].pl;
-      a.it0 = seg[g].it0;
-      a.n_witer = seg[g].n_witer;
-      cudaError_t lerr;
-      switch (e->K) {
-        case 1: lerr = launch_program<1>(a, pl.grid, pl.threads, pl.E, e->stream); break;
-        case 2: lerr = launch_program<2>(a, pl.grid, pl.threads, pl.E, e->stream); break;
-        case 4: lerr = launch_program<4>(a, pl.grid, pl.threads, pl.E, e->stream); break;
-        case 8: lerr = launch_program<8>(a, pl.grid, pl.threads, pl.E, e->stream); break;
-        case 16: lerr = launch_program<16>(a, pl.grid, pl.threads, pl.E, e->stream); break;
-        case 32: lerr = launch_program<32>(a, pl.grid, pl.threads, pl.E, e->stream); break;
-        default: return fail(RDK_ERROR_PARAM, "rate_cats must divide 32");
+  if (lazy) {
+    // which buffers hold their current value in registers only
+    auto &L = e->lazy;
+    L.stale_clv.assign(e->tips + e->clv_buffers, 0);
+    L.stale_sc.assign(e->scale_buffers, 0);
+    bool any = false;
+    for (const LInstr &li : lowered) {
+      if (li.parent != kNoClv && li.parent < L.stale_clv.size()) {
+        L.stale_clv[li.parent] = (li.flags & fWrite) ? 0 : 1;
       }
-      if (lerr != cudaSuccess) return fail(RDK_ERROR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(lerr));
-      CUDA_TRY(cudaGetLastError());
-      e->stats.kernel_launches++;
+      if (li.pscale >= 0 && (size_t)li.pscale < L.stale_sc.size()) L.stale_sc[li.pscale] = (li.flags & fWriteS) ? 0 : 1;
     }
-    if (ev) CUDA_TRY(cudaEventRecord(ev->second, e->stream));
-    e->stats.program_launches++;
+    for (char c : L.stale_clv) any = any || c;
+    for (char c : L.stale_sc) any = any || c;
+    if (any) {
+      L.ops.clear();
+      for (const ROp &r : e->pend_prog) {
+        if (r.flags & rLoadOnly) continue;
+        ROp k = r;
+        k.flags = r.flags & rWrite;
+        if (k.flags) L.ops.push_back(k);
+      }
+      L.active = true;
+      e->stats.lazy_evaluations++;
+    }
   }
+  if (!launch_lowered(p, a, lowered, lchunk, chunked, true)) return RDK_FAILURE;
   e->stats.clv_ops += e->pend_ops;
   e->stats.root_evals += e->pend_evals;
   e->stats.algorithmic_bytes += e->pend_bytes;
   e->pend_prog.clear();
   e->pend_chunk_off.clear();
+  e->pend_lazy_ok = false;
   e->pend_ops = e->pend_evals = 0;
   e->pend_bytes = 0;
   for (unsigned s : e->pm_retired) e->pm_free.push_back(s);
@@ -675,6 +801,9 @@ unsigned long long op_bytes(const Engine *e, const ROp &r) {
 // record a P-matrix update with slot renaming; caller holds the mutex
 int record_pmatrix(rdk_partition_t *p, unsigned matrix_index, double t) {
   Engine *e = eng(p);
+  if (e->pm_free.empty() && e->lazy.active) {
+    if (!materialize_lazy(p)) return RDK_FAILURE;  // releases the slots held for the kept program
+  }
   if (e->pm_free.empty()) {
     // recycle: launch what is recorded so that retired slots become free
     if (!flush(p)) return RDK_FAILURE;
@@ -682,7 +811,7 @@ int record_pmatrix(rdk_partition_t *p, unsigned matrix_index, double t) {
   }
   unsigned slot = e->pm_free.back();
   e->pm_free.pop_back();
-  e->pm_retired.push_back(e->pm_map[matrix_index]);
+  (e->lazy.active ? e->lazy.held : e->pm_retired).push_back(e->pm_map[matrix_index]);
   e->pm_map[matrix_index] = slot;
   PmatEntry ent;
   ent.slot = slot;
@@ -732,6 +861,7 @@ static int engine_init(rdk_partition_t *p, Engine *e) {
   e->tips = p->tips;
   e->clv_buffers = p->clv_buffers;
   e->S = p->sites;
+  if (const char *env = getenv("RDK_LAZY")) e->lazy_enabled = atoi(env) != 0;
   e->Kreal = p->rate_cats;
   e->K = 1;
   while (e->K < e->Kreal) e->K <<= 1;
@@ -889,6 +1019,7 @@ extern "C" int rdk_set_tip_states(rdk_partition_t *p, unsigned int tip_index, co
   if (tip_index >= e->tips) return fail(RDK_ERROR_PARAM, "tip index %u out of range", tip_index);
   CUDA_TRY(cudaSetDevice(e->device));
   if (!flush(p)) return RDK_FAILURE;
+  if (!materialize_lazy(p)) return RDK_FAILURE;  // a kept program would be replayed on the NEW tips
   char *h, *d;
   if (!ring_alloc(e, e->S ? e->S : 1, &h, &d)) return RDK_FAILURE;
   for (unsigned s = 0; s < e->S; ++s) {
@@ -1058,6 +1189,12 @@ extern "C" double rdk_compute_root_loglikelihood(rdk_partition_t *p, unsigned in
   e->pend_evals++;
   e->pend_slots = 1;
   e->want_persite = persite_lnl != nullptr;
+  // a traversal whose only requested result is this log-likelihood may keep its CLVs in registers
+  if (fused && !persite_lnl) {
+    size_t writes = 0;
+    for (const ROp &r : e->pend_prog) writes += (r.flags & rWrite) ? 1 : 0;
+    e->pend_lazy_ok = writes >= 16;
+  }
   int ok = flush(p);
   e->pend_slots = 0;
   e->want_persite = false;
@@ -1503,6 +1640,8 @@ extern "C" int rdk_get_clv(rdk_partition_t *p, unsigned int clv_index, double *o
   CUDA_TRY(cudaSetDevice(e->device));
   if (clv_index >= e->tips + e->clv_buffers) return fail(RDK_ERROR_PARAM, "clv index out of range");
   if (!flush(p)) return RDK_FAILURE;
+  if (e->lazy.active && clv_index < e->lazy.stale_clv.size() && e->lazy.stale_clv[clv_index] && !materialize_lazy(p))
+    return RDK_FAILURE;
   size_t bytes = (size_t)e->S * e->Kreal * 4 * sizeof(double);  // corax layout [site][cat][state]
   if (clv_index < e->tips) {
     double *tmp = nullptr;
@@ -1540,6 +1679,9 @@ extern "C" int rdk_get_scale_buffer(rdk_partition_t *p, int scaler_index, unsign
   if (scaler_index < 0 || (unsigned)scaler_index >= e->scale_buffers)
     return fail(RDK_ERROR_PARAM, "scaler index out of range");
   if (!flush(p)) return RDK_FAILURE;
+  if (e->lazy.active && (size_t)scaler_index < e->lazy.stale_sc.size() && e->lazy.stale_sc[scaler_index] &&
+      !materialize_lazy(p))
+    return RDK_FAILURE;
   if (!ensure_scaler(e, scaler_index)) return RDK_FAILURE;
   CUDA_TRY(cudaMemcpyAsync(out, e->sc_ptr[scaler_index], sizeof(unsigned) * e->S,
                            cudaMemcpyDeviceToHost, e->stream));
@@ -1587,6 +1729,17 @@ extern "C" int rdk_partition_set_timing(rdk_partition_t *p, int enabled) {
   CUDA_TRY(cudaSetDevice(e->device));
   harvest_events(e);
   e->timing = enabled != 0;
+  return RDK_SUCCESS;
+}
+
+extern "C" int rdk_partition_set_lazy(rdk_partition_t *p, int enabled) {
+  if (!p) return fail(RDK_ERROR_PARAM, "null partition");
+  Engine *e = eng(p);
+  std::lock_guard<std::mutex> lk(e->mu);
+  CUDA_TRY(cudaSetDevice(e->device));
+  if (!flush(p)) return RDK_FAILURE;
+  if (!enabled && !materialize_lazy(p)) return RDK_FAILURE;
+  e->lazy_enabled = enabled != 0;
   return RDK_SUCCESS;
 }
 

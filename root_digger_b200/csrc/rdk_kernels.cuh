@@ -26,6 +26,9 @@
 #ifndef RDK_X_NOTABLES
 #define RDK_X_NOTABLES 0  // the producer moves no tables
 #endif
+#ifndef RDK_X_NOSTORE
+#define RDK_X_NOSTORE 0  // no CLV is stored
+#endif
 #ifndef RDK_X_NOLOAD
 #define RDK_X_NOLOAD 0  // the consumers load no CLV
 #endif
@@ -1002,7 +1005,7 @@ __global__ void __launch_bounds__(MAXT, MINB) clv_program_kernel(const __grid_co
         if (keep_v) {
           evaluate(in, fl, y, cnt);
         } else {
-          if (fl & fWrite) {
+          if ((fl & fWrite) && !RDK_X_NOSTORE) {
             double* par = in.parent;
 #pragma unroll
             for (int u = 0; u < E; ++u) st_clv(par, e[u], y[u]);
@@ -1119,7 +1122,7 @@ __global__ void __launch_bounds__(MAXT, MINB) clv_program_kernel(const __grid_co
           evaluate(in, fl, y, cnt);
         } else {
           if (fl & fScale) rescale(v, cnt);
-          if (fl & fWrite) {
+          if ((fl & fWrite) && !RDK_X_NOSTORE) {
             double* par = in.parent;
 #pragma unroll
             for (int u = 0; u < E; ++u) st_clv(par, e[u], v[u]);

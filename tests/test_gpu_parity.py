@@ -299,6 +299,78 @@ def test_discarded_sweep_buffers_do_not_change_the_values(n, S, K, data, monkeyp
     assert compute_lh_root(g, case.derivative_schedule(2, 0.6), case.root_clv, case.root_scaler) == lh0
 
 
+@pytest.mark.parametrize("n,S,K,data", [(64, 2000, 4, "evolved"), (300, 523, 4, "iid"), (40, 900, 3, "ambiguous")])
+def test_lazily_materialised_evaluations_are_eager_semantics(n, S, K, data):
+    """rdk_partition_set_lazy (default on): a full traversal that is only asked for its root
+    log-likelihood -- compute_lh_partition inside the BFGS closures, reference src/model.cpp:455-476 --
+    keeps most CLVs in registers; whatever is called next sees exactly the state eager execution leaves:
+    repeated evaluations with new parameters (the kept program is superseded: no replay), root-only
+    evaluation, root move, CLV / scaler read-back, the placement sweep (one replay each), all bit for
+    bit against an eager partition and the oracle"""
+    from root_digger_b200.capi import RDK_SWEEP_DISCARD, RDK_SWEEP_KEEP_ROOT, Partition
+    case = Case(n, S, K, seed=300 + n, data=data, weights="random")
+    lay = case.tree.sweep_layout()
+    kw = dict(clv_buffers=lay["clv_buffers"], scale_buffers=lay["scale_buffers"], prob_matrices=lay["prob_matrices"])
+    lazy, eager = Partition(case.n, case.S, case.K, **kw), Partition(case.n, case.S, case.K, **kw)
+    o = OraclePartition(case.n, case.S, case.K, **kw)
+    for part in (lazy, eager, o):
+        case.setup(part)
+    eager.set_lazy(False)
+    sched = case.full_schedule(4, 0.3)
+    rng = np.random.default_rng(5)
+    lazy.reset_stats()
+    # a BFGS-like run: same traversal, new substitution rates every time
+    for it in range(5):
+        rates = case.rates * (1.0 + 0.1 * rng.random(12))
+        for part in (lazy, eager, o):
+            part.set_subst_params(rates)
+        a = compute_lh(lazy, sched, case.root_clv, case.root_scaler)
+        b = compute_lh(eager, sched, case.root_clv, case.root_scaler)
+        c = compute_lh(o, sched, case.root_clv, case.root_scaler, mode=MODE_ENGINE)
+        assert same_bits([a], [b]) and same_bits([a], [c]), it
+    st = lazy.stats()
+    # the first traversal of a streak is eager (a lone compute_lh would only have to be replayed)
+    assert st["lazy_evaluations"] == 4 and st["materializations"] == 0 and st["stores_elided"] >= 4 * (n // 4)
+    assert eager.stats()["lazy_evaluations"] == 0
+    # root-only evaluation at another position of the same branch: reads the two root children
+    ds = case.derivative_schedule(4, 0.7)
+    assert same_bits([compute_lh_root(lazy, ds, case.root_clv, case.root_scaler)],
+                     [compute_lh_root(eager, ds, case.root_clv, case.root_scaler)])
+    assert lazy.stats()["materializations"] == 1
+    # every CLV and scale buffer is what eager execution left (and what the oracle has)
+    for _ in range(2):  # the second one is lazy
+        compute_lh(lazy, sched, case.root_clv, case.root_scaler)
+    compute_lh(eager, sched, case.root_clv, case.root_scaler)
+    compute_lh(o, sched, case.root_clv, case.root_scaler)
+    for op in sched[0]:
+        assert same_bits(lazy.get_clv(op.parent_clv_index), o.get_clv(op.parent_clv_index))
+        assert np.array_equal(lazy.get_scaler(op.parent_scaler_index), o.get_scaler(op.parent_scaler_index))
+    assert lazy.stats()["materializations"] == 2
+    # lazy evaluation, then a root move + root-only evaluation elsewhere
+    for _ in range(2):
+        compute_lh(lazy, sched, case.root_clv, case.root_scaler)
+    assert lazy.stats()["lazy_evaluations"] == 6
+    ms = case.move_schedule(9, 0.5)
+    for part in (lazy, eager):
+        move_root(part, ms)
+    ds = case.derivative_schedule(9, 0.25)
+    assert same_bits([compute_lh_root(lazy, ds, case.root_clv, case.root_scaler)],
+                     [compute_lh_root(eager, ds, case.root_clv, case.root_scaler)])
+    # lazy evaluation, then the directed sweep (reads every CLV of the partition)
+    s1 = case.full_schedule(1, 0.5)
+    for part in (lazy, lazy, eager):
+        compute_lh(part, s1, case.root_clv, case.root_scaler)
+    *sw, pos = case.tree.generate_sweep_operations(layout=lay)
+    fl = RDK_SWEEP_KEEP_ROOT | RDK_SWEEP_DISCARD
+    assert same_bits(lazy.sweep_root_placements(*sw, case.root_clv, case.root_scaler, flags=fl),
+                     eager.sweep_root_placements(*sw, case.root_clv, case.root_scaler, flags=fl))
+    # per-site output requested: never lazy
+    before = lazy.stats()["lazy_evaluations"]
+    _, ps = compute_lh(lazy, s1, case.root_clv, case.root_scaler, persite=True)
+    _, pe = compute_lh(eager, s1, case.root_clv, case.root_scaler, persite=True)
+    assert same_bits(ps, pe) and lazy.stats()["lazy_evaluations"] == before
+
+
 def test_launch_configs_do_not_change_results():
     case = Case(25, 5000, 4, seed=11, data="ambiguous", weights="random")
     g, o = make(case)
