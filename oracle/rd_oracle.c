@@ -217,12 +217,32 @@ int rdo_update_invariant_sites_proportion(rdo_partition_t *p, unsigned int idx,
 /* Q matrix (Appendix A-2): Q_ij = r_(ij) * pi_j, 12 r's in row-major         */
 /* off-diagonal order AC,AG,AT,CA,CG,CT,GA,GC,GT,TA,TC,TG; diagonal = -row    */
 /* sum; normalised so that -sum_i pi_i Q_ii = 1.                              */
+/*                                                                            */
+/* H1: the three choices above are the UNVERIFIED reading   */
+/* of coraxlib's non-reversible builder (the library is absent).  They are     */
+/* switchable at run time -- rdo_set_q_convention -- so that the day a coraxlib*/
+/* number is available, pinning the oracle is a matter of selecting the        */
+/* variant that reproduces it.  The default (0) is the convention the CUDA     */
+/* engine implements; the engine must be changed together with the default.    */
 /* ------------------------------------------------------------------------ */
+static int g_q_convention = 0;
+void rdo_set_q_convention(int flags) { g_q_convention = flags; }
+int  rdo_get_q_convention(void) { return g_q_convention; }
+
 void rdo_build_q_nonrev(const double *r, const double *pi, double *Q) {
+  const int no_pi = g_q_convention & RDO_Q_NO_PI;         /* Q_ij = r_(ij), frequencies only at the root */
+  const int col_major = g_q_convention & RDO_Q_SLOTS_COLUMN_MAJOR; /* r's listed column by column       */
+  const int no_norm = g_q_convention & RDO_Q_NO_NORMALISATION;     /* rates taken as absolute            */
   int k = 0;
-  for (int i = 0; i < 4; ++i)
+  if (!col_major) {
+    for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 4; ++j)
+        if (i != j) Q[i * 4 + j] = no_pi ? r[k++] : r[k++] * pi[j];
+  } else {
     for (int j = 0; j < 4; ++j)
-      if (i != j) Q[i * 4 + j] = r[k++] * pi[j];
+      for (int i = 0; i < 4; ++i)
+        if (i != j) Q[i * 4 + j] = no_pi ? r[k++] : r[k++] * pi[j];
+  }
   for (int i = 0; i < 4; ++i) {
     double s = 0.0;
     int first = 1;
@@ -236,6 +256,7 @@ void rdo_build_q_nonrev(const double *r, const double *pi, double *Q) {
     }
     Q[i * 4 + i] = -s;
   }
+  if (no_norm) return;
   double mu = pi[0] * (-Q[0]);
   mu = mu + pi[1] * (-Q[5]);
   mu = mu + pi[2] * (-Q[10]);

@@ -19,6 +19,19 @@
  *   - the reference invariants test/src/model.cpp:59-75, :271-288, :367-387;
  *   - scipy.linalg.expm / mpmath (expm), scipy.stats.gamma (gamma categories).
  *
+ *
+ * ARITHMETIC SPEC v2 -- the checker followed the implementation, and says so: the 4x4 mat-vec of
+ * the CLV update and the dot products of the root log-likelihood are explicit FMA chains here
+ * (rd_oracle.c "CLV update") because that is what the CUDA kernels issue; v1 rounded every
+ * product and sum separately.  Neither order is coraxlib's (its AVX2 kernels use their own), and
+ * the choice is only legitimate because the result stays bounded by independent arithmetic:
+ * tests/test_oracle.py::test_oracle_against_exact_arithmetic re-evaluates the whole chain
+ * (Q -> expm -> pruning -> weighted root logL) in 60-digit mpmath and requires 1e-12 relative in
+ * both arithmetic modes -- three orders inside the 1e-9 parity budget of the north star.
+ * The H1 conventions of the Q builder (pi-multiplication, slot order, normalisation) are
+ * run-time switches (rdo_set_q_convention): pinning on a coraxlib number, if one ever becomes
+ * available, is a matter of selecting the variant that reproduces it.
+ *
  * Every entry point has the same shape as the corax_* function RootDigger
  * calls, with prefix rdo_.
  */
@@ -149,6 +162,14 @@ int     rdo_compute_gamma_cats(double alpha, unsigned int categories,
 double *rdo_msa_empirical_frequencies(rdo_partition_t *p);
 
 /* building blocks exposed for unit tests */
+/* H1 switches of the Q builder (rd_oracle.c, "Q matrix"): 0 = the convention of SURVEY Appendix A-2
+ * (the one the CUDA engine implements); any combination of the flags selects another reading of
+ * coraxlib's non-reversible builder.  Process-global; affects P-matrices built afterwards. */
+#define RDO_Q_NO_PI 1
+#define RDO_Q_SLOTS_COLUMN_MAJOR 2
+#define RDO_Q_NO_NORMALISATION 4
+void rdo_set_q_convention(int flags);
+int  rdo_get_q_convention(void);
 void   rdo_build_q_nonrev(const double *subst_params, const double *freqs,
                           double *Q /*16*/);
 void   rdo_expm4(const double *A /*16*/, double *E /*16*/);

@@ -80,6 +80,9 @@ def load_oracle() -> C.CDLL:
     L.rdo_msa_empirical_frequencies.restype = C.c_void_p
     L.rdo_build_q_nonrev.argtypes = [_dp, _dp, _dp]
     L.rdo_build_q_nonrev.restype = None
+    L.rdo_set_q_convention.argtypes = [C.c_int]
+    L.rdo_set_q_convention.restype = None
+    L.rdo_get_q_convention.restype = C.c_int
     L.rdo_expm4.argtypes = [_dp, _dp]
     L.rdo_expm4.restype = None
     L.rdo_log.argtypes = [C.c_double]

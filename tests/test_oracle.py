@@ -251,6 +251,46 @@ def test_root_invariance_under_reversible_parameters():
     assert np.ptp(vals) <= 1.19e-5 * abs(vals[0])
 
 
+@pytest.mark.parametrize("flags", range(8))
+def test_reference_invariants_hold_under_every_q_convention(flags):
+    """the pi-multiplication, the slot order of the 12 rates and the normalisation of the
+    non-reversible Q are unverified readings of coraxlib -- run-time switches of the oracle
+    (rdo_set_q_convention).  Every invariant the reference's own tests hold (test/src/model.cpp:59-75
+    finite / negative / reproducible, :271-288 full traversal == root-only evaluation, :367-387 root
+    invariance under JC parameters) holds under each of the 8 variants, so none of them can be ruled
+    out from the reference's tests alone; the default is the one the CUDA engine implements."""
+    from oracle_capi import load_oracle
+    L = load_oracle()
+    assert L.rdo_get_q_convention() == 0
+    L.rdo_set_q_convention(flags)
+    try:
+        case = fixtures.FixtureCase(fixtures.load("10.fasta"), 4)
+        case.freqs = np.array([0.1, 0.2, 0.3, 0.4])  # (under uniform pi the first switch is a no-op)
+        o = OraclePartition(case.n, case.S, 4)
+        case.setup(o)
+        vals = []
+        for rid in range(0, case.tree.root_count, 4):
+            a = compute_lh(o, case.full_schedule(rid), case.root_clv, case.root_scaler)
+            b = compute_lh(o, case.full_schedule(rid), case.root_clv, case.root_scaler)
+            c = compute_lh_root(o, case.derivative_schedule(rid, 0.5), case.root_clv, case.root_scaler)
+            assert math.isfinite(a) and a < 0 and a == b and a == c
+            vals.append(a)
+        if flags:
+            # a different convention is a different model: the variants are distinguishable by value
+            L.rdo_set_q_convention(0)
+            base = compute_lh(o, case.full_schedule(0), case.root_clv, case.root_scaler)
+            L.rdo_set_q_convention(flags)
+            assert abs(base - vals[0]) > 1e-6 * abs(base)
+        jc = fixtures.FixtureCase(fixtures.load("10.fasta"), 1)
+        jc.rates = np.ones(12)
+        o1 = OraclePartition(jc.n, jc.S, 1)
+        jc.setup(o1)
+        same = [compute_lh(o1, jc.full_schedule(rid), jc.root_clv, jc.root_scaler) for rid in range(0, jc.tree.root_count, 3)]
+        assert np.ptp(same) <= 1.19e-5 * abs(same[0])
+    finally:
+        L.rdo_set_q_convention(0)
+
+
 def test_empty_and_tiny_partitions():
     o = OraclePartition(4, 0, 4)
     assert o.root_loglikelihood(6, 2) == 0.0
