@@ -47,6 +47,11 @@ CONFIGS = {
                  workload="cfg5: synthetic 10000-taxon x 1000000-site DNA, UNREST+G4, exhaustive mode, "
                           "site-sharded"),
 }
+# the headline workload at constant work per GPU (100 000 sites of 500 taxa on every GPU): what the
+# strong-scaling curve of the headline cannot show -- it leaves 12.5 k sites per GPU at N = 8
+CONFIGS["cfg2_weak"] = dict(taxa=500, sites=100_000, sites_per_gpu=True, cats=4, data="evolved", partitions=1,
+                            workload="cfg2 at constant work per GPU: 500 taxa x (100000 x N) sites, UNREST+G4, "
+                                     "site-sharded (weak scaling of the headline step)")
 BLOCK = 1024  # site block of the data generator = RDK_SHARD_ALIGN
 
 
@@ -131,6 +136,8 @@ def run_config(name: str, cfg: dict, *, torch, dist, rank: int, world: int, loca
     from root_digger_b200.capi import Model, RootedTree
     from root_digger_b200.sharding import PartitionShardedModel, plan_partition_shards, plan_site_shards
 
+    if cfg.get("sites_per_gpu"):
+        cfg = dict(cfg, sites=cfg["sites"] * world)
     n, S, K, P = cfg["taxa"], cfg["sites"], cfg["cats"], cfg["partitions"]
     t_setup = time.perf_counter()
 
@@ -155,7 +162,7 @@ def run_config(name: str, cfg: dict, *, torch, dist, rank: int, world: int, loca
         # ---- site shards, one per GPU, joined by the engine's NCCL all-reduce ------------------
         shards = plan_site_shards(S, world)
         off, cnt = shards[rank]
-        setup = Setup(cfg, seed + (3 if name == "cfg3" else 5), off, cnt)
+        setup = Setup(cfg, seed + {"cfg3": 3, "cfg5": 5}.get(name, 2), off, cnt)
         comm_id = None
         if world > 1:
             ids = torch.zeros(128, dtype=torch.uint8, device="cuda")
