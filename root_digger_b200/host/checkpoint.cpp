@@ -60,13 +60,17 @@ struct out_t {
   }
 };
 
+// Positional reads (pread) on the checkpoint's OWN descriptor: opening and closing a second
+// descriptor on the file would drop every fcntl lock this process holds on it (POSIX).
 struct in_t {
-  int  fd;
-  bool short_read = false;
-  bool raw(void *p, size_t n) {
+  int   fd;
+  off_t off = 0;
+  bool  short_read = false;
+  bool  raw(void *p, size_t n) {
     char *c = static_cast<char *>(p);
     while (n > 0) {
-      ssize_t r = ::read(fd, c, n);
+      ssize_t r = ::pread(fd, c, n, off);
+      if (r > 0) off += r;
       if (r < 0) {
         if (errno == EINTR) continue;
         throw checkpoint_read_failure{"Failed to read a value"};
@@ -335,64 +339,61 @@ void checkpoint_t::save_options(const cli_options_t &options) {
 
 void checkpoint_t::load_options(cli_options_t &options) {
   if (!on_disk() || !_existing_results) return;
-  int fd = open(_checkpoint_filename.c_str(), O_RDONLY);
-  if (fd == -1) throw checkpoint_read_failure{"Failed to open the checkpoint file for reading"};
-  in_t in{fd};
-  try {
-    read_header(in, options);
-  } catch (...) {
-    close(fd);
-    throw;
-  }
-  close(fd);
+  std::lock_guard<std::mutex> lk(_mu);
+  file_lock_t                 lock(_file_descriptor);
+  load_options_unlocked(options);
+}
+
+void checkpoint_t::load_options_unlocked(cli_options_t &options) {
+  in_t in{_file_descriptor};
+  read_header(in, options);
 }
 
 // every readable record, in file order; *damaged = the log ends in a record that fails its checksum
 std::vector<checkpoint_t::record_t> checkpoint_t::scan(bool *damaged) {
+  file_lock_t lock(_file_descriptor);
+  return scan_unlocked(damaged);
+}
+
+// the caller holds _mu and the file lock
+std::vector<checkpoint_t::record_t> checkpoint_t::scan_unlocked(bool *damaged) {
   std::vector<record_t> results;
   if (damaged) *damaged = false;
-  file_lock_t lock(_file_descriptor);
-  int         fd = open(_checkpoint_filename.c_str(), O_RDONLY);
-  if (fd == -1) throw checkpoint_read_failure{"Failed to open the checkpoint file for reading"};
-  in_t in{fd};
-  try {
-    cli_options_t tmp;
-    read_header(in, tmp);
-    off_t pos = lseek(fd, 0, SEEK_CUR), end = lseek(fd, 0, SEEK_END);
-    lseek(fd, pos, SEEK_SET);
-    while (pos < end) {
-      rd_result_t r{};
-      uint64_t    id = 0;
-      uint32_t    sum = 0;
-      bool        ok = in.pod(id) && in.pod(r.llh) && in.pod(r.alpha) && in.pod(sum);
-      r.root_id = (size_t)id;
-      if (!ok || sum != checkpoint_checksum(r)) {
-        if (damaged) *damaged = true;
-        break;
-      }
-      uint64_t                            n = 0;
-      std::vector<partition_parameters_t> params;
-      const uint64_t                      limit = (uint64_t)(end - pos) / sizeof(double);
-      ok = in.pod(n) && n <= (uint64_t)(end - pos);
-      for (uint64_t i = 0; ok && i < n; ++i) {
-        partition_parameters_t pp;
-        ok = in.doubles(pp.subst_rates, limit) && in.doubles(pp.freqs, limit) &&
-             in.doubles(pp.gamma_alpha, limit) && in.doubles(pp.gamma_weights, limit);
-        if (ok) params.push_back(std::move(pp));
-      }
-      ok = ok && in.pod(sum);
-      if (!ok || sum != checkpoint_checksum(params)) {
-        if (damaged) *damaged = true;
-        break;
-      }
-      results.emplace_back(r, std::move(params));
-      pos = lseek(fd, 0, SEEK_CUR);
+  struct stat st;
+  if (fstat(_file_descriptor, &st) == -1) throw checkpoint_read_failure{"Failed to stat the checkpoint file"};
+  const off_t   end = st.st_size;
+  in_t          in{_file_descriptor};
+  cli_options_t tmp;
+  read_header(in, tmp);
+  off_t pos = in.off;
+  while (pos < end) {
+    rd_result_t r{};
+    uint64_t    id = 0;
+    uint32_t    sum = 0;
+    bool        ok = in.pod(id) && in.pod(r.llh) && in.pod(r.alpha) && in.pod(sum);
+    r.root_id = (size_t)id;
+    if (!ok || sum != checkpoint_checksum(r)) {
+      if (damaged) *damaged = true;
+      break;
     }
-  } catch (...) {
-    close(fd);
-    throw;
+    uint64_t                            n = 0;
+    std::vector<partition_parameters_t> params;
+    const uint64_t                      limit = (uint64_t)(end - pos) / sizeof(double);
+    ok = in.pod(n) && n <= (uint64_t)(end - pos);
+    for (uint64_t i = 0; ok && i < n; ++i) {
+      partition_parameters_t pp;
+      ok = in.doubles(pp.subst_rates, limit) && in.doubles(pp.freqs, limit) &&
+           in.doubles(pp.gamma_alpha, limit) && in.doubles(pp.gamma_weights, limit);
+      if (ok) params.push_back(std::move(pp));
+    }
+    ok = ok && in.pod(sum);
+    if (!ok || sum != checkpoint_checksum(params)) {
+      if (damaged) *damaged = true;
+      break;
+    }
+    results.emplace_back(r, std::move(params));
+    pos = in.off;
   }
-  close(fd);
   return results;
 }
 
@@ -424,11 +425,14 @@ bool checkpoint_t::needs_cleaning() {
 
 void checkpoint_t::clean() {
   if (!on_disk() || !_existing_results) return;
-  cli_options_t options;
-  load_options(options);
-  auto                        progress = read_results();
+  // ONE mutex and ONE file lock across read, rewrite and rename: a record appended by another
+  // rank in between would otherwise be dropped
   std::lock_guard<std::mutex> lk(_mu);
-  std::string                 backup = _checkpoint_filename + ".bak";
+  file_lock_t                 lock(_file_descriptor);
+  cli_options_t               options;
+  load_options_unlocked(options);
+  auto        progress = scan_unlocked(nullptr);
+  std::string backup = _checkpoint_filename + ".bak";
   int copy_fd = open(backup.c_str(), O_RDWR | O_CREAT | O_APPEND | O_EXCL, 0640);
   if (copy_fd == -1)
     throw std::runtime_error("Failed to open the new checkpoint when cleaning the checkpoint");

@@ -87,6 +87,8 @@ public:
 
 private:
   std::vector<record_t> scan(bool *damaged);
+  std::vector<record_t> scan_unlocked(bool *damaged);  // caller holds _mu and the file lock
+  void                  load_options_unlocked(cli_options_t &);
 
   std::string           _checkpoint_filename;
   int                   _file_descriptor = -1;
