@@ -521,7 +521,8 @@ def run_ours(args):
                "api": "librd_host.so model_t::compute_lh + model_t::suggest_roots_lh sweep (host scheduler, "
                       "programs H2D, log-likelihoods D2H; alignment resident as in the reference partition"
                       + ("; + all-gather of the placement log-likelihoods)" if G_r > 1 else ")"),
-               "logl_root0": a, "matches_device_arm": bool(a == lh0 and np.array_equal(b, sweep_lh))}
+               "logl_root0": a, "matches_device_arm": bool(a == lh0 and np.array_equal(b, sweep_lh)),
+               "placements_sha256": placements_digest(b)}
         if args.exhaustive_branches > 0:
             e2e["exhaustive"] = exhaustive_sample(m, args.exhaustive_branches, stats=mstats, taxa=n, barrier=barrier)
         m.close()
@@ -574,6 +575,9 @@ def run_ours(args):
             "roofline": roofline, "full_evaluation": full_eval, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(agg[1].item()), "clocks": clocks,
             "logl_root0": lh0, "best_placement": int(np.argmax(sweep_lh)),
+            # SHA-256 of the bit patterns of all 2n-3 placement log-likelihoods: must be the same string in the
+            # N = 1, 2, 4, 8 lines (site shards add exact zeros: DESIGN section 3) and in the e2e arm
+            "placements_sha256": placements_digest(sweep_lh),
             # the sweep scores root 0 at ratio 0.5 too: same bits as the full evaluation (the reference's
             # compute_lh == compute_lh_root invariant) -- also a cross-rank check that every shard walked
             # the placements in the same order
@@ -629,6 +633,11 @@ def dram_traffic_from_profiles(taxa, sites_per_gpu, cats):
         return json.loads(p.read_text())["entries"].get("%dx%dx%d" % (taxa, sites_per_gpu, cats))
     except Exception:
         return None
+
+
+def placements_digest(values) -> str:
+    import hashlib
+    return hashlib.sha256(np.ascontiguousarray(values, dtype="<f8").tobytes()).hexdigest()
 
 
 def min_step_traffic(n, sites, K):
