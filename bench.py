@@ -451,7 +451,11 @@ def run_ours(args):
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": per_launch,
                 "avg_launch_ms": prog_s * 1e3 / max(1, st["program_timed"]),
                 "launches_timed": st["program_timed"],
-                "kernel_share_of_step": prog_s * 1e3 / ms if ms > 0 else None}
+                "kernel_share_of_step": prog_s * 1e3 / ms if ms > 0 else None,
+                # where the rest of a step goes on the host (engine counters, ms per step, this rank)
+                "host_ms_per_step": {"recording": st["host_record_ns"] * 1e-6 / args.steps,
+                                     "lowering_and_enqueue": st["host_lower_ns"] * 1e-6 / args.steps,
+                                     "waiting_for_device": st["host_wait_ns"] * 1e-6 / args.steps}}
 
     # ---- the unit of exhaustive mode / BFGS: one full evaluation (compute_lh), timed alone
     g.set_timing(True)

@@ -329,6 +329,9 @@ typedef struct rdk_stats {
   unsigned long long stores_elided;     /* CLV stores dropped because nothing reads them back */
   unsigned long long lazy_evaluations;  /* full evaluations that kept CLVs in registers only  */
   unsigned long long materializations;  /* kept programs replayed with all their stores       */
+  unsigned long long host_record_ns;    /* host wall time: recording P-matrix updates / operations */
+  unsigned long long host_lower_ns;     /* ... lowering, pointer translation, enqueueing launches   */
+  unsigned long long host_wait_ns;      /* ... waiting for the device at the result synchronisation */
 } rdk_stats_t;
 void rdk_partition_stats(rdk_partition_t *partition, rdk_stats_t *out);
 void rdk_partition_reset_stats(rdk_partition_t *partition);

@@ -13,6 +13,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -205,6 +206,17 @@ struct Engine {
 };
 
 Engine *eng(rdk_partition_t *p) { return reinterpret_cast<Engine *>(p->engine); }
+
+// host wall time of a scope, added to one of the rdk_stats_t host_*_ns counters
+struct HostTimer {
+  unsigned long long                   *acc;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  explicit HostTimer(unsigned long long *a) : acc(a) {}
+  ~HostTimer() {
+    *acc += (unsigned long long)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0)
+                .count();
+  }
+};
 
 unsigned next_pow2(unsigned long long n) {
   unsigned long long v = 1;
@@ -626,6 +638,7 @@ int flush(rdk_partition_t *p) {
   }
   a.persite = e->want_persite ? e->d_persite : nullptr;
   // recorded operations -> the instructions the kernel walks (rdk_lower.hpp)
+  HostTimer             lower_timer(&e->stats.host_lower_ns);  // lowering, pointer translation, enqueue
   const bool            chunked = e->pend_chunk_off.size() > 2;
   // Lazy only in a STREAK of such traversals (the second consecutive one onwards): that is the
   // signature of a BFGS closure -- 13 evaluations per step, reference src/model.cpp:1488-1502 --
@@ -740,7 +753,10 @@ int finish_evals(rdk_partition_t *p, unsigned slots) {
     e->stats.kernel_launches++;
     e->stats.reduce_launches++;
   }
-  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  {
+    HostTimer wait_timer(&e->stats.host_wait_ns);
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+  }
   e->stats.d2h_bytes += sizeof(double) * slots;
   return RDK_SUCCESS;
 }
@@ -1124,6 +1140,7 @@ extern "C" int rdk_update_prob_matrices(rdk_partition_t *p, const unsigned int *
   }
   std::lock_guard<std::mutex> lk(e->mu);
   CUDA_TRY(cudaSetDevice(e->device));
+  HostTimer record_timer(&e->stats.host_record_ns);
   for (unsigned i = 0; i < count; ++i)
     if (!record_pmatrix(p, matrix_indices[i], branch_lengths[i])) return RDK_FAILURE;
   return RDK_SUCCESS;
@@ -1133,6 +1150,7 @@ extern "C" void rdk_update_clvs(rdk_partition_t *p, const rdk_operation_t *ops, 
   Engine *e = eng(p);
   std::lock_guard<std::mutex> lk(e->mu);
   cudaSetDevice(e->device);
+  HostTimer record_timer(&e->stats.host_record_ns);
   for (unsigned i = 0; i < count; ++i) {
     ROp r;
     if (!make_rop(p, ops[i], rWrite, &r)) return;  // error left in rdk_errno
@@ -1440,6 +1458,7 @@ extern "C" int rdk_sweep_root_placements_chunks(rdk_partition_t *p, unsigned int
     size_t   pm_budget = e->pm_free.size();
     unsigned next_chunk = 0;
     if (concurrent) e->pend_chunk_off.clear();
+    auto record_t0 = std::chrono::steady_clock::now();
     while (done + b < cuts[batch + 1]) {
       unsigned q = done + b;
       size_t   need = pm_offsets[q + 1] - pm_offsets[q];
@@ -1483,6 +1502,8 @@ extern "C" int rdk_sweep_root_placements_chunks(rdk_partition_t *p, unsigned int
       ++b;
     }
     if (b == 0) return fail(RDK_ERROR_PARAM, "a placement needs more P-matrices than the pool holds");
+    e->stats.host_record_ns += (unsigned long long)std::chrono::duration_cast<std::chrono::nanoseconds>(
+                                   std::chrono::steady_clock::now() - record_t0).count();
     if (concurrent) e->pend_chunk_off.push_back((unsigned)e->pend_prog.size());
     e->pend_slots = b;
     if (flags & RDK_SWEEP_DISCARD) {
