@@ -22,6 +22,15 @@ def build_case():
     return Case(N_TAXA, SITES, K, seed=SEED, data="ambiguous", weights="ones", gamma_cats=gamma_cats)
 
 
+EXHAUSTIVE_TOL = (1e-2, 1e-2, 1e-3, 1e13)
+
+
+def small_case():
+    from cases import Case
+    from root_digger_b200.capi import gamma_cats
+    return Case(9, 700, K, seed=SEED + 9, data="evolved", weights="ones", gamma_cats=gamma_cats)
+
+
 def part_rates(case, p):
     return np.roll(case.rates, p) * (1.0 + 0.07 * p)
 
@@ -113,6 +122,24 @@ def main():
     res["parts_lh_root"] = sm.compute_lh_root(4, 0.2)
     res["parts_sweep"] = sm.sweep_root_lh()
     pm.close()
+    # ---- root placements dealt to the GPUs (exhaustive mode, reference src/model.cpp:1899-1907): every
+    # ---- rank holds a replica of all sites and optimises its contiguous chunk of the root ids
+    small = small_case()
+    em = capi.Model(capi.RootedTree(small.newick), small.aln, K, seed=5)
+    em.initialize_partitions()
+    ids, llh, alpha = em.exhaustive_search(*EXHAUSTIVE_TOL, rank=rank, num_tasks=world)
+    em.close()
+    mine = torch.full((3, 64), float("nan"), dtype=torch.float64, device="cuda")
+    mine[0, :len(ids)] = torch.from_numpy(ids.astype(np.float64))
+    mine[1, :len(ids)] = torch.from_numpy(llh)
+    mine[2, :len(ids)] = torch.from_numpy(alpha)
+    allv = torch.zeros((world, 3, 64), dtype=torch.float64, device="cuda")
+    dist.all_gather_into_tensor(allv.view(-1), mine.view(-1))
+    allv = allv.cpu().numpy()
+    keep = ~np.isnan(allv[:, 0, :])
+    res["roots_ids"] = np.concatenate([allv[r, 0, keep[r]] for r in range(world)])
+    res["roots_llh"] = np.concatenate([allv[r, 1, keep[r]] for r in range(world)])
+    res["roots_alpha"] = np.concatenate([allv[r, 2, keep[r]] for r in range(world)])
     if rank == 0:
         np.savez(sys.argv[1], **{k: np.asarray(v) for k, v in res.items()})
     dist.barrier()

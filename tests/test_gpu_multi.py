@@ -5,7 +5,10 @@ rdk_partition_attach_comm) through the C ABI and through model_t, and partitions
 (sharding.PartitionShardedModel over torch.distributed nccl) must return the bits of the same
 calls on ONE GPU: full evaluation, the chunked directed sweep in one launch and cut into batches
 (one collective per batch), batched root candidates, empirical frequencies, compute_dlh and
-optimize_alpha (reference src/model.cpp:384-519, 679-794, 865-889).  Skipped below two devices."""
+optimize_alpha (reference src/model.cpp:384-519, 679-794, 865-889); and exhaustive mode with the ROOT
+PLACEMENTS dealt to the GPUs (src/model.cpp:1899-1907, a replica of all sites per GPU, no data-path
+collective) must give the per-branch log-likelihoods, root positions and LWR ranking of one process
+doing every branch.  Skipped below two devices."""
 import os
 import socket
 import subprocess
@@ -17,6 +20,16 @@ import pytest
 
 ROOT = Path(__file__).resolve().parent.parent
 pytestmark = pytest.mark.gpu
+
+
+def capi_lwr(capi, llh):
+    """model_t::lwr (reference src/model.cpp:1237-1258) through the host library"""
+    import ctypes as C
+    L = capi.load_tree_lib()
+    llh = np.ascontiguousarray(llh, dtype=np.float64)
+    out = np.zeros(len(llh))
+    L.rdh_model_lwr(llh.ctypes.data_as(C.POINTER(C.c_double)), len(llh), out.ctypes.data_as(C.POINTER(C.c_double)))
+    return out
 
 
 def _devices():
@@ -67,6 +80,21 @@ def test_two_gpu_nccl_runs_return_the_bits_of_one_gpu(tmp_path):
     want["parts_sweep"] = pm.sweep_root_lh()
     pm.close()
 
+    # exhaustive mode with the root ids dealt to the two GPUs == one process doing all of them
+    small = w.small_case()
+    em = capi.Model(capi.RootedTree(small.newick), small.aln, w.K, seed=5)
+    em.initialize_partitions()
+    ids, llh, alpha = em.exhaustive_search(*w.EXHAUSTIVE_TOL)
+    lwr_one = em.lwr(llh)
+    em.close()
+    assert sorted(got["roots_ids"].astype(int).tolist()) == sorted(ids.tolist()) == list(range(2 * small.n - 3))
+    order = np.argsort(got["roots_ids"])
+    want["roots_ids"] = ids[np.argsort(ids)].astype(np.float64)
+    want["roots_llh"], want["roots_alpha"] = llh[np.argsort(ids)], alpha[np.argsort(ids)]
+    for k in ("roots_ids", "roots_llh", "roots_alpha"):
+        got[k] = got[k][order]
+    assert np.array_equal(np.argsort(-got["roots_llh"], kind="stable"), np.argsort(-want["roots_llh"], kind="stable"))  # LWR ranking
+    assert np.array_equal(lwr_one[np.argsort(ids)].view(np.uint64), capi_lwr(capi, got["roots_llh"]).view(np.uint64))
     assert set(got) == set(want)
     for k in sorted(want):
         a = np.ascontiguousarray(np.asarray(got[k], dtype=np.float64))
