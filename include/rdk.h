@@ -332,6 +332,7 @@ typedef struct rdk_stats {
   unsigned long long host_record_ns;    /* host wall time: recording P-matrix updates / operations */
   unsigned long long host_lower_ns;     /* ... lowering, pointer translation, enqueueing launches   */
   unsigned long long host_wait_ns;      /* ... waiting for the device at the result synchronisation */
+  unsigned long long grouped_programs;  /* programs run as subtree groups + a joining program (rdk_partition_set_subtree_groups) */
 } rdk_stats_t;
 void rdk_partition_stats(rdk_partition_t *partition, rdk_stats_t *out);
 void rdk_partition_reset_stats(rdk_partition_t *partition);
@@ -353,6 +354,16 @@ int rdk_partition_set_launch_config(rdk_partition_t *partition,
  * the kept program instead).  Results and observable partition state are those of eager
  * execution, bit for bit. */
 int rdk_partition_set_lazy(rdk_partition_t *partition, int enabled);
+/* Subtree groups.  On a small shard the walk of a long traversal is bound by the latency of one
+ * instruction, so the engine runs disjoint subtrees of the recorded operations side by side
+ * (groups, one per blockIdx.y, as the chunks of a placement sweep) and then the operations that
+ * join them -- when its launch cost model says that is faster, and only for programs that are
+ * plainly forests (csrc/rdk_lower.hpp).  Every operation computes the same value from the same
+ * operands as in array order (corax_update_clvs, src/model.cpp:402): results are identical bit
+ * for bit.  groups = 0: the engine decides (default; RDK_SUBTREE_GROUPS in the environment sets
+ * the value for partitions created afterwards), 1: never, 2..16: always that many groups where
+ * the program allows it (tests, experiments). */
+int rdk_partition_set_subtree_groups(rdk_partition_t *partition, int groups);
 /* accepted and ignored (round-1 kernels had two tail rules); results never depended on it */
 int rdk_partition_set_tail_mode(rdk_partition_t *partition, int mode);
 const char *rdk_version(void);
@@ -367,6 +378,15 @@ int rdk_debug_lower_program(unsigned int tips, unsigned int n_ops, const int *op
                             int discard_writes, const unsigned char *scratch_clv,
                             unsigned int n_scratch_clv, int *out, unsigned int out_cap,
                             unsigned int *out_chunk_off);
+
+/* The subtree-group rearrangement, lowered: the instructions of the groups (out_group_off:
+ * groups + 1 offsets), then those of the joining program; *n_group_instr = instructions of all
+ * groups, *n_total_instr = all instructions written.  `cap` = largest subtree dealt as a whole.
+ * Returns the number of groups (0: the program keeps its order), -1 if out_cap is too small. */
+int rdk_debug_lower_grouped(unsigned int tips, unsigned int n_ops, const int *ops,
+                            unsigned int n_groups, unsigned int cap, int discard_writes, int *out,
+                            unsigned int out_cap, unsigned int *out_group_off,
+                            unsigned int *n_group_instr, unsigned int *n_total_instr);
 
 #ifdef __cplusplus
 }

@@ -62,7 +62,7 @@ class Stats(C.Structure):
         "kernel_launches", "program_launches", "pmatrix_launches", "reduce_launches", "clv_ops",
         "root_evals", "pmatrices", "algorithmic_bytes", "h2d_bytes", "d2h_bytes", "device_bytes",
         "program_time_ns", "program_timed", "instructions", "stores_elided", "lazy_evaluations",
-        "materializations", "host_record_ns", "host_lower_ns", "host_wait_ns")]
+        "materializations", "host_record_ns", "host_lower_ns", "host_wait_ns", "grouped_programs")]
 
     def asdict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
@@ -154,6 +154,7 @@ def load_engine() -> C.CDLL:
     L.rdk_partition_set_timing.argtypes = [_pp, C.c_int]
     L.rdk_partition_set_tail_mode.argtypes = [_pp, C.c_int]
     L.rdk_partition_set_lazy.argtypes = [_pp, C.c_int]
+    L.rdk_partition_set_subtree_groups.argtypes = [_pp, C.c_int]
     L.rdk_set_device.argtypes = [C.c_int]
     _engine_lib = L
     return L
@@ -343,6 +344,11 @@ class Partition:
     def set_lazy(self, enabled: bool):
         """rdk_partition_set_lazy: lazily materialised full evaluations on / off"""
         if self.L.rdk_partition_set_lazy(self.p, 1 if enabled else 0) != RDK_SUCCESS:
+            raise EngineError(_err(self.L))
+
+    def set_subtree_groups(self, groups: int = 0):
+        """rdk_partition_set_subtree_groups: 0 = the engine decides, 1 = never, n = always n groups"""
+        if self.L.rdk_partition_set_subtree_groups(self.p, int(groups)) != RDK_SUCCESS:
             raise EngineError(_err(self.L))
 
     def set_tail_mode(self, mode: int = 0):

@@ -195,6 +195,7 @@ struct Engine {
 
   // launch config
   int ctas_per_sm = 0, threads = 0, elems = 0;
+  int subtree_groups = 0;  // 0: by the cost model, 1: never, n: always n (rdk_partition_set_subtree_groups)
 
   // optional per-launch timing of the program kernel (bench / profiling)
   bool                                            timing = false;
@@ -499,7 +500,7 @@ int materialize_lazy(rdk_partition_t *p);
 
 // copy a lowered program to the device and launch the program kernel over the whole shard
 int launch_lowered(rdk_partition_t *p, ProgArgs &a, const std::vector<LInstr> &lowered,
-                   const std::vector<unsigned> &lchunk, bool chunked, bool timed) {
+                   const std::vector<unsigned> &lchunk, bool chunked) {
   Engine        *e = eng(p);
   const unsigned n_witer = a.n_witer;
   a.n_instr = (int)lowered.size();
@@ -524,8 +525,6 @@ int launch_lowered(rdk_partition_t *p, ProgArgs &a, const std::vector<LInstr> &l
   if (a.nelem == 0 || a.n_instr == 0) return RDK_SUCCESS;
   LaunchSeg seg[2];
   const int n_seg = plan_segments(e, n_witer, chunked ? a.n_chunks : 1u, a.n_instr, seg);
-  std::pair<cudaEvent_t, cudaEvent_t> *ev = (timed && e->timing) ? next_event_pair(e) : nullptr;
-  if (ev) CUDA_TRY(cudaEventRecord(ev->first, e->stream));
   for (int g = 0; g < n_seg; ++g) {
     const LaunchPlan &pl = seg[g].pl;
     a.it0 = seg[g].it0;
@@ -546,8 +545,6 @@ int launch_lowered(rdk_partition_t *p, ProgArgs &a, const std::vector<LInstr> &l
   }
   a.n_witer = n_witer;
   a.it0 = 0;
-  if (ev) CUDA_TRY(cudaEventRecord(ev->second, e->stream));
-  e->stats.program_launches++;
   return RDK_SUCCESS;
 }
 
@@ -575,7 +572,8 @@ int materialize_lazy(rdk_partition_t *p) {
   lower_program(e->lazy.ops, std::vector<unsigned>(), lopt, lowered, lchunk, nullptr);
   e->stats.instructions += lowered.size();
   e->stats.materializations++;
-  if (!launch_lowered(p, a, lowered, lchunk, false, false)) return RDK_FAILURE;
+  if (!launch_lowered(p, a, lowered, lchunk, false)) return RDK_FAILURE;
+  if (a.nelem && !lowered.empty()) e->stats.program_launches++;
   std::fill(e->lazy.stale_clv.begin(), e->lazy.stale_clv.end(), 0);
   std::fill(e->lazy.stale_sc.begin(), e->lazy.stale_sc.end(), 0);
   release_lazy(e);
@@ -603,6 +601,60 @@ bool pending_needs_materialization(const Engine *e) {
   for (size_t s = 0; s < ws.size(); ++s)
     if (L.stale_sc[s] && !ws[s]) return true;
   return false;
+}
+
+// Subtree groups (rdk_lower.hpp, rdk.h rdk_partition_set_subtree_groups): should the pending program
+// run as G groups of disjoint subtrees side by side + the operations that join them?  Decided by
+// the launch cost model above: the longest group at the per-instruction time of a launch shared
+// by G groups, plus the joining operations at that of a plain launch, against all operations in
+// one plain launch.  cfg2 over 8 GPUs (12.5 k sites, 499 operations): 4 groups of <= 130
+// operations at 1.41 us + ~20 joining ones, against 499 x 0.86 us.
+bool choose_subtree_groups(const Engine *e, unsigned n_witer, std::vector<ROp> &grouped, std::vector<unsigned> &goff,
+                           std::vector<ROp> &join) {
+  const std::vector<ROp> &ops = e->pend_prog;
+  const int               mode = e->subtree_groups;
+  const size_t            n = ops.size();
+  if (mode == 1 || n < 4 || n_witer == 0) return false;
+  if (mode == 0 && (n < 48 || e->elems)) return false;
+  static const unsigned kGroups[] = {2, 3, 4, 6, 8};
+  const double          flat = plan_launch(e, n_witer, 1).cost;
+  double                shared[17] = {0};
+  if (mode == 0) {
+    // a shard that keeps the device busy with one program gains nothing: skip the analysis
+    double best_possible = 1e300;
+    for (unsigned g : kGroups) {
+      shared[g] = plan_launch(e, n_witer, g).cost;
+      best_possible = std::min(best_possible, (double)n / g * shared[g]);
+    }
+    if (best_possible >= 0.85 * (double)n * flat) return false;
+  }
+  ForestInfo fi;
+  if (!analyse_forest(ops, e->tips, fi)) return false;
+  std::vector<int> group, best_group;
+  unsigned         best_used = 0;
+  if (mode >= 2) {
+    unsigned longest = 0, n_join = 0;
+    best_used = assign_subtree_groups(fi, (unsigned)mode, (unsigned)((n + mode - 1) / mode), best_group, longest, n_join);
+  } else {
+    double best_cost = 0.9 * (double)n * flat;
+    for (unsigned g : kGroups)
+      for (unsigned div : {1u, 2u}) {
+        unsigned       longest = 0, n_join = 0;
+        const unsigned cap = (unsigned)((n + g * div - 1) / (g * div));
+        const unsigned used = assign_subtree_groups(fi, g, cap, group, longest, n_join);
+        if (used < 2) continue;
+        const double per = used == g ? shared[g] : plan_launch(e, n_witer, used).cost;
+        const double cost = longest * per + n_join * flat + 5.0;  // + a launch and its tail, us
+        if (cost < best_cost) {
+          best_cost = cost;
+          best_used = used;
+          best_group.swap(group);
+        }
+      }
+  }
+  if (best_used < 2) return false;
+  split_by_group(ops, best_group, best_used, grouped, goff, join);
+  return true;
 }
 
 // launch recorded P-matrix work and the recorded program (no host sync)
@@ -646,7 +698,7 @@ int flush(rdk_partition_t *p) {
   // (measured on B200, cfg2 search step: 9.06 ms with an always-lazy compute_lh against 8.03 ms).
   e->full_streak = e->pend_lazy_ok ? e->full_streak + 1 : 0;
   const bool lazy = e->pend_lazy_ok && e->full_streak >= 2 && e->lazy_enabled && !chunked && !e->pend_scratch_clv;
-  std::vector<LInstr>   lowered;
+  std::vector<LInstr>   lowered, lowered_join;
   std::vector<unsigned> lchunk;
   LowerOptions          lopt;
   lopt.tips = e->tips;
@@ -654,8 +706,18 @@ int flush(rdk_partition_t *p) {
   lopt.scratch_scaler = e->pend_scratch_sc;
   lopt.discard_writes = lazy;  // keep only the stores the program reads back itself
   LowerStats lst;
-  lower_program(e->pend_prog, chunked ? e->pend_chunk_off : std::vector<unsigned>(), lopt, lowered, lchunk, &lst);
-  e->stats.instructions += lowered.size();
+  // a long traversal on a small shard: disjoint subtrees side by side, then what joins them
+  std::vector<ROp>      group_ops, join_ops;
+  std::vector<unsigned> group_off;
+  const bool grouped = !chunked && !e->pend_scratch_clv && !e->pend_scratch_sc && nelem != 0 &&
+                       choose_subtree_groups(e, n_witer, group_ops, group_off, join_ops);
+  if (grouped) {
+    lower_grouped(group_ops, group_off, join_ops, lopt, lowered, lchunk, lowered_join, &lst);
+    e->stats.grouped_programs++;
+  } else {
+    lower_program(e->pend_prog, chunked ? e->pend_chunk_off : std::vector<unsigned>(), lopt, lowered, lchunk, &lst);
+  }
+  e->stats.instructions += lowered.size() + lowered_join.size();
   e->stats.stores_elided += lst.stores_dropped;
   if (lazy) {
     // which buffers hold their current value in registers only
@@ -663,12 +725,14 @@ int flush(rdk_partition_t *p) {
     L.stale_clv.assign(e->tips + e->clv_buffers, 0);
     L.stale_sc.assign(e->scale_buffers, 0);
     bool any = false;
-    for (const LInstr &li : lowered) {
-      if (li.parent != kNoClv && li.parent < L.stale_clv.size()) {
-        L.stale_clv[li.parent] = (li.flags & fWrite) ? 0 : 1;
+    for (const std::vector<LInstr> *part : {&lowered, &lowered_join})
+      for (const LInstr &li : *part) {
+        if (li.parent != kNoClv && li.parent < L.stale_clv.size()) {
+          L.stale_clv[li.parent] = (li.flags & fWrite) ? 0 : 1;
+        }
+        if (li.pscale >= 0 && (size_t)li.pscale < L.stale_sc.size())
+          L.stale_sc[li.pscale] = (li.flags & fWriteS) ? 0 : 1;
       }
-      if (li.pscale >= 0 && (size_t)li.pscale < L.stale_sc.size()) L.stale_sc[li.pscale] = (li.flags & fWriteS) ? 0 : 1;
-    }
     for (char c : L.stale_clv) any = any || c;
     for (char c : L.stale_sc) any = any || c;
     if (any) {
@@ -683,7 +747,18 @@ int flush(rdk_partition_t *p) {
       e->stats.lazy_evaluations++;
     }
   }
-  if (!launch_lowered(p, a, lowered, lchunk, chunked, true)) return RDK_FAILURE;
+  const bool runs = nelem != 0 && lowered.size() + lowered_join.size() != 0;
+  std::pair<cudaEvent_t, cudaEvent_t> *ev = (runs && e->timing) ? next_event_pair(e) : nullptr;
+  if (ev) CUDA_TRY(cudaEventRecord(ev->first, e->stream));
+  if (grouped) {
+    ProgArgs ag = a;
+    if (!launch_lowered(p, ag, lowered, lchunk, true)) return RDK_FAILURE;
+    if (!lowered_join.empty() && !launch_lowered(p, a, lowered_join, std::vector<unsigned>(), false)) return RDK_FAILURE;
+  } else {
+    if (!launch_lowered(p, a, lowered, lchunk, chunked)) return RDK_FAILURE;
+  }
+  if (ev) CUDA_TRY(cudaEventRecord(ev->second, e->stream));
+  if (runs) e->stats.program_launches++;
   e->stats.clv_ops += e->pend_ops;
   e->stats.root_evals += e->pend_evals;
   e->stats.algorithmic_bytes += e->pend_bytes;
@@ -878,6 +953,7 @@ static int engine_init(rdk_partition_t *p, Engine *e) {
   e->clv_buffers = p->clv_buffers;
   e->S = p->sites;
   if (const char *env = getenv("RDK_LAZY")) e->lazy_enabled = atoi(env) != 0;
+  if (const char *env = getenv("RDK_SUBTREE_GROUPS")) e->subtree_groups = std::max(0, std::min(kMaxChunks, atoi(env)));
   e->Kreal = p->rate_cats;
   e->K = 1;
   while (e->K < e->Kreal) e->K <<= 1;
@@ -1761,6 +1837,14 @@ extern "C" int rdk_partition_set_lazy(rdk_partition_t *p, int enabled) {
   if (!flush(p)) return RDK_FAILURE;
   if (!enabled && !materialize_lazy(p)) return RDK_FAILURE;
   e->lazy_enabled = enabled != 0;
+  return RDK_SUCCESS;
+}
+
+extern "C" int rdk_partition_set_subtree_groups(rdk_partition_t *p, int groups) {
+  if (groups < 0 || groups > kMaxChunks) return fail(RDK_ERROR_PARAM, "groups must be 0 .. %d", kMaxChunks);
+  Engine                     *e = eng(p);
+  std::lock_guard<std::mutex> lk(e->mu);
+  e->subtree_groups = groups;
   return RDK_SUCCESS;
 }
 

@@ -272,4 +272,177 @@ inline void lower_program(const std::vector<ROp> &ops, const std::vector<unsigne
   if (stats) *stats = st;
 }
 
+// ---- subtree groups --------------------------------------------------------------------------------
+// A post-order traversal is a chain of dependent instructions only along each root-to-tip path:
+// disjoint subtrees are independent programs.  On a small shard (few elements per SM) the walk is
+// bound by the latency of one instruction, not by throughput, so the engine runs G groups of
+// subtrees side by side (one `blockIdx.y` each, as the chunks of a placement sweep) and then the
+// operations that join them.  Every operation computes the same value from the same operands as
+// in array order, so the results are identical bit for bit; what changes is only which operations
+// follow one another.
+//
+// The rearrangement is offered only for programs that are plainly forests: every CLV / scale
+// buffer is written at most once, never read before it is written in the same program, and read
+// by at most one later operation (with the scale buffer its producer wrote).  Anything else
+// (in-place updates, shared children, repeated evaluations) keeps its order.
+struct ForestInfo {
+  std::vector<int>      consumer;  // the operation that reads this operation's parent CLV, -1: none
+  std::vector<unsigned> weight;    // operations in the subtree below and including this one
+  std::vector<char>     joins;     // evaluations and whatever depends on them: never in a group
+};
+
+inline bool analyse_forest(const std::vector<ROp> &ops, unsigned tips, ForestInfo &f) {
+  const size_t n = ops.size();
+  unsigned     max_clv = tips;
+  int          max_sc = 0;
+  for (const ROp &r : ops) {
+    if (r.parent != kNoClv) max_clv = std::max(max_clv, r.parent + 1);
+    if (r.c1 != kNoClv) max_clv = std::max(max_clv, r.c1 + 1);
+    if (r.c2 != kNoClv) max_clv = std::max(max_clv, r.c2 + 1);
+    max_sc = std::max(max_sc, std::max(r.pscale, std::max(r.c1scale, r.c2scale)) + 1);
+  }
+  std::vector<int>  wclv(max_clv, -1), wsc((size_t)max_sc, -1);  // the operation that wrote a buffer
+  std::vector<char> xclv(max_clv, 0), xsc((size_t)max_sc, 0);    // read as it was before the program
+  f.consumer.assign(n, -1);
+  f.weight.assign(n, 1u);
+  f.joins.assign(n, 0);
+  for (size_t i = 0; i < n; ++i) {
+    const ROp &r = ops[i];
+    auto       read = [&](unsigned c, int s) -> bool {
+      int prod = -1;
+      if (c != kNoClv && c >= tips) {
+        prod = wclv[c];
+        if (prod < 0) {
+          xclv[c] = 1;
+        } else {
+          if (f.consumer[prod] != -1) return false;  // a shared child: not a forest
+          f.consumer[prod] = (int)i;
+          f.weight[i] += f.weight[prod];
+          if (f.joins[prod]) f.joins[i] = 1;
+        }
+      }
+      if (s >= 0) {
+        if (wsc[s] < 0)
+          xsc[s] = 1;
+        else if (wsc[s] != prod)
+          return false;  // counts that did not come with the CLV
+      }
+      return true;
+    };
+    if (!read(r.c1, r.c1scale)) return false;
+    if (!(r.flags & rLoadOnly) && !read(r.c2, r.c2scale)) return false;
+    if ((r.flags & (rEval | rLoadOnly)) || !(r.flags & rWrite)) f.joins[i] = 1;
+    if (r.flags & rWrite) {
+      if (r.parent == kNoClv || r.parent < tips) return false;
+      if (wclv[r.parent] >= 0 || xclv[r.parent]) return false;  // rewritten, or read before written
+      wclv[r.parent] = (int)i;
+      if (r.pscale >= 0) {
+        if (wsc[r.pscale] >= 0 || xsc[r.pscale]) return false;
+        wsc[r.pscale] = (int)i;
+      }
+    }
+  }
+  return true;
+}
+
+// Whole subtrees of at most `cap` operations are dealt to `n_groups` groups (largest first, to the
+// least loaded group); the operations above them join.  group[i] = the group of operation i, or -1.
+// Returns the number of groups in use (0: nothing to deal); `longest` = operations of the fullest
+// group, `n_join` = joining operations.
+inline unsigned assign_subtree_groups(const ForestInfo &f, unsigned n_groups, unsigned cap, std::vector<int> &group,
+                                      unsigned &longest, unsigned &n_join) {
+  const size_t n = f.consumer.size();
+  group.assign(n, -1);
+  std::vector<int>                           unit(n, -1);
+  std::vector<std::pair<unsigned, unsigned>> units;  // (operations, unit id)
+  n_join = 0;
+  for (size_t i = n; i-- > 0;) {
+    const int c = f.consumer[i];
+    if (c >= 0 && unit[c] >= 0) {
+      unit[i] = unit[c];
+    } else if (!f.joins[i] && f.weight[i] <= cap) {
+      unit[i] = (int)units.size();
+      units.emplace_back(f.weight[i], (unsigned)units.size());
+    } else {
+      ++n_join;
+    }
+  }
+  longest = 0;
+  if (units.size() < 2 || n_groups < 2) return 0;
+  std::sort(units.begin(), units.end(), [](const std::pair<unsigned, unsigned> &a, const std::pair<unsigned, unsigned> &b) {
+    return a.first != b.first ? a.first > b.first : a.second < b.second;
+  });
+  const unsigned        g_used = (unsigned)std::min<size_t>(n_groups, units.size());
+  std::vector<unsigned> load(g_used, 0u), of_unit(units.size(), 0u);
+  for (const auto &u : units) {
+    unsigned best = 0;
+    for (unsigned g = 1; g < g_used; ++g)
+      if (load[g] < load[best]) best = g;
+    load[best] += u.first;
+    of_unit[u.second] = best;
+  }
+  for (unsigned g = 0; g < g_used; ++g) longest = std::max(longest, load[g]);
+  for (size_t i = 0; i < n; ++i)
+    if (unit[i] >= 0) group[i] = (int)of_unit[unit[i]];
+  return g_used;
+}
+
+// the operations of each group (array order kept inside a group), then the joining operations
+inline void split_by_group(const std::vector<ROp> &ops, const std::vector<int> &group, unsigned g_used,
+                           std::vector<ROp> &grouped, std::vector<unsigned> &group_off, std::vector<ROp> &join) {
+  group_off.assign(g_used + 1, 0u);
+  for (size_t i = 0; i < ops.size(); ++i)
+    if (group[i] >= 0) ++group_off[(size_t)group[i] + 1];
+  for (unsigned g = 0; g < g_used; ++g) group_off[g + 1] += group_off[g];
+  grouped.resize(group_off[g_used]);
+  join.clear();
+  std::vector<unsigned> at(group_off.begin(), group_off.end() - 1);
+  for (size_t i = 0; i < ops.size(); ++i) {
+    if (group[i] >= 0)
+      grouped[at[(size_t)group[i]]++] = ops[i];
+    else
+      join.push_back(ops[i]);
+  }
+}
+
+// lower the groups (as independent chunks) and the joining operations.  With discard_writes (a
+// lazily materialised evaluation) a group keeps, besides the stores it reads back itself, the
+// buffers the joining operations read.
+inline void lower_grouped(const std::vector<ROp> &grouped, const std::vector<unsigned> &group_off,
+                          const std::vector<ROp> &join, const LowerOptions &opt, std::vector<LInstr> &out_groups,
+                          std::vector<unsigned> &out_group_off, std::vector<LInstr> &out_join, LowerStats *stats) {
+  LowerOptions      gopt = opt;
+  std::vector<char> scr_clv, scr_sc;
+  if (opt.discard_writes) {
+    unsigned max_clv = 0;
+    int      max_sc = 0;
+    for (const ROp &r : grouped) {
+      if (r.parent != kNoClv) max_clv = std::max(max_clv, r.parent + 1);
+      max_sc = std::max(max_sc, r.pscale + 1);
+    }
+    scr_clv.assign(max_clv, 1);
+    scr_sc.assign((size_t)max_sc, 1);
+    auto needed = [&](unsigned c, int sc) {
+      if (c != kNoClv && c < scr_clv.size()) scr_clv[c] = 0;
+      if (sc >= 0 && (size_t)sc < scr_sc.size()) scr_sc[(size_t)sc] = 0;
+    };
+    for (const ROp &r : join) {
+      needed(r.c1, r.c1scale);
+      if (!(r.flags & rLoadOnly)) needed(r.c2, r.c2scale);
+    }
+    gopt.discard_writes = false;
+    gopt.scratch_clv = &scr_clv;
+    gopt.scratch_scaler = &scr_sc;
+  }
+  LowerStats a, b;
+  lower_program(grouped, group_off, gopt, out_groups, out_group_off, &a);
+  std::vector<unsigned> none;
+  lower_program(join, std::vector<unsigned>(), opt, out_join, none, &b);
+  if (stats) {
+    stats->loadv = a.loadv + b.loadv;
+    stats->stores_dropped = a.stores_dropped + b.stores_dropped;
+    stats->forwarded = a.forwarded + b.forwarded;
+  }
+}
+
 }  // namespace rdk

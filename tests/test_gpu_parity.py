@@ -371,6 +371,55 @@ def test_lazily_materialised_evaluations_are_eager_semantics(n, S, K, data):
     assert same_bits(ps, pe) and lazy.stats()["lazy_evaluations"] == before
 
 
+@pytest.mark.parametrize("n,S,K,data", [(64, 2000, 4, "evolved"), (300, 523, 4, "iid"), (130, 900, 3, "ambiguous"),
+                                        (500, 12500, 4, "evolved")])
+def test_subtree_groups_are_array_order_semantics(n, S, K, data):
+    """rdk_partition_set_subtree_groups: disjoint subtrees of a traversal walked side by side (one
+    blockIdx.y each) and then the operations that join them -- every CLV, scale buffer, per-site and
+    total log-likelihood has the bits of the operations executed in array order (corax_update_clvs,
+    reference src/model.cpp:402) and of the oracle, eager and inside a lazily materialised streak;
+    the default (the engine's cost model) groups the long traversals of these small shards by itself"""
+    from root_digger_b200.capi import Partition
+    case = Case(n, S, K, seed=700 + n, data=data, weights="random")
+    o = OraclePartition(case.n, case.S, case.K)
+    case.setup(o)
+    sched = case.full_schedule(5, 0.3)
+    want, want_ps = compute_lh(o, sched, case.root_clv, case.root_scaler, mode=MODE_ENGINE, persite=True)
+    ds = case.derivative_schedule(5, 0.7)
+    want_root = compute_lh_root(o, ds, case.root_clv, case.root_scaler, mode=MODE_ENGINE)
+    compute_lh(o, sched, case.root_clv, case.root_scaler)
+    some = list(sched[0][:: max(1, len(sched[0]) // 24)]) + [sched[0][-1]]
+    want_clv = {op.parent_clv_index: o.get_clv(op.parent_clv_index).copy() for op in some}
+    want_sc = {op.parent_scaler_index: o.get_scaler(op.parent_scaler_index).copy() for op in some}
+    for groups in (1, 0, 2, 3, 4, 8, 16):
+        g = Partition(case.n, case.S, case.K)
+        case.setup(g)
+        g.set_subtree_groups(groups)
+        g.reset_stats()
+        got, ps = compute_lh(g, sched, case.root_clv, case.root_scaler, persite=True)
+        assert same_bits([got], [want]) and same_bits(ps, want_ps), groups
+        for op in some:
+            assert same_bits(g.get_clv(op.parent_clv_index), want_clv[op.parent_clv_index]), groups
+            assert np.array_equal(g.get_scaler(op.parent_scaler_index), want_sc[op.parent_scaler_index]), groups
+        st = g.stats()
+        assert st["program_launches"] == 1
+        if groups or n >= 130:  # (the 64-taxon traversal is too short for the cost model to be sure)
+            assert st["grouped_programs"] == (0 if groups == 1 else 1), (groups, st)
+        by_default = st["grouped_programs"]
+        # a streak: the second traversal onwards keeps most CLVs in registers, groups or not
+        for it in range(4):
+            assert same_bits([compute_lh(g, sched, case.root_clv, case.root_scaler)], [want]), (groups, it)
+        st = g.stats()
+        assert st["lazy_evaluations"] == 3 and st["grouped_programs"] == 5 * by_default, (groups, st)
+        # ... and the state it leaves is the eager one (one replay on the first read)
+        assert same_bits([compute_lh_root(g, ds, case.root_clv, case.root_scaler)], [want_root]), groups
+        compute_lh(g, sched, case.root_clv, case.root_scaler)
+        for op in some:
+            assert same_bits(g.get_clv(op.parent_clv_index), want_clv[op.parent_clv_index]), groups
+            assert np.array_equal(g.get_scaler(op.parent_scaler_index), want_sc[op.parent_scaler_index]), groups
+        del g
+
+
 def test_launch_configs_do_not_change_results():
     case = Case(25, 5000, 4, seed=11, data="ambiguous", weights="random")
     g, o = make(case)

@@ -311,3 +311,146 @@ def test_degenerate_operand_patterns():
     got = run_lowered(low, prog)
     assert got == want and ref.clv == low.clv and ref.sc == low.sc
     assert any(fl & F["Nop"] and not fl & F["EvalV"] for fl, *_ in prog)  # the read-after-write guard
+
+
+# ---- subtree groups (rdk_partition_set_subtree_groups) ------------------------------------------------
+def lower_grouped(tips, ops, n_groups, cap, discard=False):
+    L = capi.load_engine()
+    L.rdk_debug_lower_grouped.restype = C.c_int
+    n = len(ops)
+    arr = np.ascontiguousarray(np.array(ops, dtype=np.int64).astype(np.int32).reshape(n, 10))
+    out = np.zeros((4 * n + 16, 10), dtype=np.int32)
+    goff = np.zeros(n_groups + 1, dtype=np.uint32)
+    ng, nt = C.c_uint(0), C.c_uint(0)
+    used = L.rdk_debug_lower_grouped(
+        C.c_uint(tips), C.c_uint(n), arr.ctypes.data_as(C.POINTER(C.c_int)), C.c_uint(n_groups), C.c_uint(cap),
+        C.c_int(1 if discard else 0), out.ctypes.data_as(C.POINTER(C.c_int)), C.c_uint(out.shape[0]),
+        goff.ctypes.data_as(C.POINTER(C.c_uint)), C.byref(ng), C.byref(nt))
+    assert used >= 0
+    if used == 0:
+        return 0, [], [], []
+    rows = [tuple(int(x) & 0xFFFFFFFF if j in (1, 3, 5) else int(x) for j, x in enumerate(row)) for row in out[:nt.value]]
+    return used, rows[:ng.value], [int(x) for x in goff[:used + 1]], rows[ng.value:]
+
+
+def post_order_ops(rng, tips, shape="random"):
+    """post-order traversal of ONE rooted binary tree (what rooted_tree_t::generate_operations emits,
+    reference src/tree.cpp:364-413), root operation evaluated"""
+    class N:
+        pass
+    pool = []
+    for t in range(tips):
+        n = N()
+        n.clv, n.sc, n.kids, n.pm = t, -1, None, t
+        pool.append(n)
+    clv, sc = tips, 0
+    while len(pool) > 1:
+        if shape == "caterpillar":
+            i, j = len(pool) - 1, 0
+        else:
+            i, j = rng.sample(range(len(pool)), 2)
+        a, b = pool[i], pool[j]
+        for x in sorted((i, j), reverse=True):
+            pool.pop(x)
+        n = N()
+        n.clv, n.sc, n.kids, n.pm = clv, sc, (a, b), clv
+        clv, sc = clv + 1, sc + 1
+        pool.append(n)
+    ops = []
+
+    def walk(n):
+        if n.kids:
+            walk(n.kids[0])
+            walk(n.kids[1])
+            ops.append((n.clv, n.sc, n.kids[0].clv, n.kids[1].clv, n.kids[0].sc, n.kids[1].sc,
+                        n.kids[0].pm, n.kids[1].pm, R_WRITE, 0))
+    import sys
+    sys.setrecursionlimit(10000)
+    walk(pool[0])
+    ops[-1] = ops[-1][:8] + (R_WRITE | R_EVAL, 0)
+    return ops, clv, sc
+
+
+@pytest.mark.parametrize("seed", range(10))
+@pytest.mark.parametrize("discard", [False, True])
+def test_subtree_groups_compute_the_traversal(seed, discard):
+    rng = random.Random(300 + seed)
+    tips = rng.choice([6, 13, 40, 120, 500])
+    ops, n_clv, n_sc = post_order_ops(rng, tips)
+    n_groups = rng.choice([2, 3, 4, 8])
+    cap = -(-len(ops) // (n_groups * rng.choice([1, 2])))
+    used, groups, goff, join = lower_grouped(tips, ops, n_groups, cap, discard)
+    ref = Mem(tips, n_clv, n_sc)
+    want = run_reference(ref, ops)
+    if used == 0:
+        assert tips <= 13  # too small to have two subtrees under the cap
+        return
+    assert 2 <= used <= n_groups and goff[0] == 0 and goff[-1] == len(groups)
+    assert all(goff[g] < goff[g + 1] for g in range(used))
+    # groups are independent: run them in REVERSE order, each with unknown registers, then the join
+    low = Mem(tips, n_clv, n_sc)
+    got = {}
+    for g in reversed(range(used)):
+        got.update(run_lowered(low, groups[goff[g]:goff[g + 1]]))
+    assert got == {}  # evaluations belong to the joining program
+    got.update(run_lowered(low, join))
+    assert got == want
+    if not discard:
+        assert ref.clv == low.clv and ref.sc == low.sc
+    else:
+        # a lazily materialised evaluation keeps the stores a group's own instructions or the joining
+        # program read back; no group writes a buffer another group reads or writes
+        written = [set(r[1] for r in groups[goff[g]:goff[g + 1]] if r[0] & F["Write"]) for g in range(used)]
+        for g in range(used):
+            for h in range(g + 1, used):
+                assert not (written[g] & written[h])
+    # no group reads what another group (or the join) writes
+    produced_by = {}
+    for g in range(used):
+        for r in groups[goff[g]:goff[g + 1]]:
+            if r[1] != NONE:
+                produced_by[r[1]] = g
+    for g in range(used):
+        for (fl, parent, pscale, c1, s1, c2, pm1, pm2, slot, s2) in groups[goff[g]:goff[g + 1]]:
+            if not (fl & (F["Tip1"] | F["Nop"])) and c1 in produced_by:
+                assert produced_by[c1] == g
+            if (fl & F["LoadV2"]) and c2 in produced_by:
+                assert produced_by[c2] == g
+    # balance: the longest group is not much longer than its share (random trees)
+    longest = max(goff[g + 1] - goff[g] for g in range(used))
+    assert longest + len(join) < len(ops) or tips <= 13
+
+
+def test_subtree_groups_leave_other_programs_alone():
+    rng = random.Random(9)
+    # a caterpillar has no two disjoint subtrees worth dealing: everything joins
+    ops, n_clv, n_sc = post_order_ops(rng, 64, shape="caterpillar")
+    used, *_ = lower_grouped(64, ops, 4, len(ops) // 4)
+    assert used == 0
+    # a shared child (both parents read CLV 8) is not a forest
+    tips = 8
+    shared = [(8, 0, 0, 1, -1, -1, 0, 1, R_WRITE, 0), (9, 1, 8, 2, 0, -1, 2, 3, R_WRITE, 0),
+              (10, 2, 8, 3, 0, -1, 4, 5, R_WRITE, 0), (11, 3, 9, 10, 1, 2, 6, 7, R_WRITE | R_EVAL, 0)]
+    assert lower_grouped(tips, shared, 2, 2)[0] == 0
+    # a buffer written twice / read before it is written keeps its order
+    twice = [(8, 0, 0, 1, -1, -1, 0, 1, R_WRITE, 0), (9, 1, 2, 3, -1, -1, 2, 3, R_WRITE, 0),
+             (8, 0, 4, 5, -1, -1, 4, 5, R_WRITE, 0), (10, 2, 8, 9, 0, 1, 6, 7, R_WRITE | R_EVAL, 0)]
+    assert lower_grouped(tips, twice, 2, 2)[0] == 0
+    war = [(9, 1, 8, 0, -1, -1, 0, 1, R_WRITE, 0), (8, 0, 1, 2, -1, -1, 2, 3, R_WRITE, 0),
+           (10, 2, 8, 9, 0, 1, 6, 7, R_WRITE | R_EVAL, 0)]
+    assert lower_grouped(tips, war, 2, 2)[0] == 0
+    # the sequential random joins of the first test are forests too (not post-orders): same values
+    for seed in range(6):
+        r2 = random.Random(seed)
+        t2 = r2.choice([17, 40, 90])
+        ops2, c2, s2 = random_tree_ops(r2, t2)
+        used, groups, goff, join = lower_grouped(t2, ops2, 3, -(-len(ops2) // 3))
+        ref, low = Mem(t2, c2, s2), Mem(t2, c2, s2)
+        want = run_reference(ref, ops2)
+        if used == 0:
+            continue
+        got = {}
+        for g in range(used):
+            got.update(run_lowered(low, groups[goff[g]:goff[g + 1]]))
+        got.update(run_lowered(low, join))
+        assert got == want and ref.clv == low.clv and ref.sc == low.sc

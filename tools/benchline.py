@@ -1,6 +1,6 @@
-"""stdin: bench.py output -> one summary line per JSON line"""
-import sys, json
-for l in sys.stdin:
+"""bench.py output (files given as arguments, else stdin) -> one summary line per JSON line"""
+import sys, json, fileinput
+for l in fileinput.input():
     l = l.strip()
     if l.startswith("{"):
         d = json.loads(l)
