@@ -333,6 +333,7 @@ typedef struct rdk_stats {
   unsigned long long host_lower_ns;     /* ... lowering, pointer translation, enqueueing launches   */
   unsigned long long host_wait_ns;      /* ... waiting for the device at the result synchronisation */
   unsigned long long grouped_programs;  /* programs run as subtree groups + a joining program (rdk_partition_set_subtree_groups) */
+  unsigned long long programs_reused;   /* programs whose lowering was taken from the previous traversal of the same structure */
 } rdk_stats_t;
 void rdk_partition_stats(rdk_partition_t *partition, rdk_stats_t *out);
 void rdk_partition_reset_stats(rdk_partition_t *partition);

@@ -62,7 +62,7 @@ class Stats(C.Structure):
         "kernel_launches", "program_launches", "pmatrix_launches", "reduce_launches", "clv_ops",
         "root_evals", "pmatrices", "algorithmic_bytes", "h2d_bytes", "d2h_bytes", "device_bytes",
         "program_time_ns", "program_timed", "instructions", "stores_elided", "lazy_evaluations",
-        "materializations", "host_record_ns", "host_lower_ns", "host_wait_ns", "grouped_programs")]
+        "materializations", "host_record_ns", "host_lower_ns", "host_wait_ns", "grouped_programs", "programs_reused")]
 
     def asdict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}

@@ -193,6 +193,27 @@ struct Engine {
   int                nranks = 1, rank = 0;
   unsigned long long max_shard_sites = 0;  // largest shard of the layout (agreed over the communicator)
 
+  // Lowered programs kept for the next traversal of the same structure (a BFGS closure re-records
+  // the same operations with new P-matrices 13 times per step, a search step alternates one full
+  // traversal and one sweep): key = the recorded operations without their P slots + everything
+  // else the lowering looks at, compared exactly; value = the instructions, whose P slots are
+  // refreshed from the operations recorded now.
+  struct KeptProgram {
+    std::vector<ROp>      ops;
+    std::vector<unsigned> chunk_off;
+    std::vector<char>     scratch_clv, scratch_sc;
+    bool                  has_scratch_clv = false, has_scratch_sc = false, lazy = false;
+    // the lowering
+    bool                  grouped = false;
+    std::vector<LInstr>   lowered, lowered_join;
+    std::vector<unsigned> lchunk;
+    LowerStats            lst;
+    unsigned long long    last_use = 0;
+  };
+  std::vector<KeptProgram> kept_programs;
+  unsigned long long       kept_clock = 0;
+  bool                     keep_programs = true;
+
   // launch config
   int ctas_per_sm = 0, threads = 0, elems = 0;
   int subtree_groups = 0;  // 0: by the cost model, 1: never, n: always n (rdk_partition_set_subtree_groups)
@@ -603,6 +624,40 @@ bool pending_needs_materialization(const Engine *e) {
   return false;
 }
 
+constexpr size_t kKeptPrograms = 8;    // entries (least recently used replaced)
+constexpr size_t kKeptMinOps = 32;     // shorter programs are lowered every time
+
+// same structure?  (P slots and positions excepted)
+bool same_structure(const ROp &a, const ROp &b) {
+  return a.parent == b.parent && a.pscale == b.pscale && a.c1 == b.c1 && a.c2 == b.c2 && a.c1scale == b.c1scale &&
+         a.c2scale == b.c2scale && a.flags == b.flags && a.slot == b.slot;
+}
+
+Engine::KeptProgram *find_kept_program(Engine *e, bool lazy, bool chunked) {
+  for (Engine::KeptProgram &k : e->kept_programs) {
+    if (k.lazy != lazy || k.ops.size() != e->pend_prog.size()) continue;
+    if (chunked ? k.chunk_off != e->pend_chunk_off : !k.chunk_off.empty()) continue;
+    if (k.has_scratch_clv != (e->pend_scratch_clv != nullptr) || k.has_scratch_sc != (e->pend_scratch_sc != nullptr)) continue;
+    if (k.has_scratch_clv && k.scratch_clv != *e->pend_scratch_clv) continue;
+    if (k.has_scratch_sc && k.scratch_sc != *e->pend_scratch_sc) continue;
+    bool same = true;
+    for (size_t i = 0; same && i < k.ops.size(); ++i) same = same_structure(k.ops[i], e->pend_prog[i]);
+    if (same) return &k;
+  }
+  return nullptr;
+}
+
+Engine::KeptProgram *new_kept_program(Engine *e) {
+  if (e->kept_programs.size() < kKeptPrograms) {
+    e->kept_programs.emplace_back();
+    return &e->kept_programs.back();
+  }
+  Engine::KeptProgram *lru = &e->kept_programs[0];
+  for (Engine::KeptProgram &k : e->kept_programs)
+    if (k.last_use < lru->last_use) lru = &k;
+  return lru;
+}
+
 // Subtree groups (rdk_lower.hpp, rdk.h rdk_partition_set_subtree_groups): should the pending program
 // run as G groups of disjoint subtrees side by side + the operations that join them?  Decided by
 // the launch cost model above: the longest group at the per-instruction time of a launch shared
@@ -698,25 +753,55 @@ int flush(rdk_partition_t *p) {
   // (measured on B200, cfg2 search step: 9.06 ms with an always-lazy compute_lh against 8.03 ms).
   e->full_streak = e->pend_lazy_ok ? e->full_streak + 1 : 0;
   const bool lazy = e->pend_lazy_ok && e->full_streak >= 2 && e->lazy_enabled && !chunked && !e->pend_scratch_clv;
-  std::vector<LInstr>   lowered, lowered_join;
-  std::vector<unsigned> lchunk;
-  LowerOptions          lopt;
-  lopt.tips = e->tips;
-  lopt.scratch_clv = e->pend_scratch_clv;
-  lopt.scratch_scaler = e->pend_scratch_sc;
-  lopt.discard_writes = lazy;  // keep only the stores the program reads back itself
-  LowerStats lst;
-  // a long traversal on a small shard: disjoint subtrees side by side, then what joins them
-  std::vector<ROp>      group_ops, join_ops;
-  std::vector<unsigned> group_off;
-  const bool grouped = !chunked && !e->pend_scratch_clv && !e->pend_scratch_sc && nelem != 0 &&
-                       choose_subtree_groups(e, n_witer, group_ops, group_off, join_ops);
-  if (grouped) {
-    lower_grouped(group_ops, group_off, join_ops, lopt, lowered, lchunk, lowered_join, &lst);
-    e->stats.grouped_programs++;
+  for (size_t i = 0; i < e->pend_prog.size(); ++i) e->pend_prog[i].id = (unsigned)i;
+  Engine::KeptProgram  scratch_entry;  // programs that are not kept are lowered into this one
+  Engine::KeptProgram *kp = nullptr;
+  const bool           keepable = e->keep_programs && e->pend_prog.size() >= kKeptMinOps;
+  if (keepable) kp = find_kept_program(e, lazy, chunked);
+  if (kp) {
+    e->stats.programs_reused++;
   } else {
-    lower_program(e->pend_prog, chunked ? e->pend_chunk_off : std::vector<unsigned>(), lopt, lowered, lchunk, &lst);
+    kp = keepable ? new_kept_program(e) : &scratch_entry;
+    LowerOptions lopt;
+    lopt.tips = e->tips;
+    lopt.scratch_clv = e->pend_scratch_clv;
+    lopt.scratch_scaler = e->pend_scratch_sc;
+    lopt.discard_writes = lazy;  // keep only the stores the program reads back itself
+    // a long traversal on a small shard: disjoint subtrees side by side, then what joins them
+    std::vector<ROp>      group_ops, join_ops;
+    std::vector<unsigned> group_off;
+    kp->lowered_join.clear();
+    kp->grouped = !chunked && !e->pend_scratch_clv && !e->pend_scratch_sc && nelem != 0 &&
+                  choose_subtree_groups(e, n_witer, group_ops, group_off, join_ops);
+    if (kp->grouped)
+      lower_grouped(group_ops, group_off, join_ops, lopt, kp->lowered, kp->lchunk, kp->lowered_join, &kp->lst);
+    else
+      lower_program(e->pend_prog, chunked ? e->pend_chunk_off : std::vector<unsigned>(), lopt, kp->lowered, kp->lchunk,
+                    &kp->lst);
+    if (keepable) {
+      kp->ops = e->pend_prog;
+      kp->chunk_off = chunked ? e->pend_chunk_off : std::vector<unsigned>();
+      kp->lazy = lazy;
+      kp->has_scratch_clv = e->pend_scratch_clv != nullptr;
+      kp->has_scratch_sc = e->pend_scratch_sc != nullptr;
+      if (kp->has_scratch_clv) kp->scratch_clv = *e->pend_scratch_clv; else kp->scratch_clv.clear();
+      if (kp->has_scratch_sc) kp->scratch_sc = *e->pend_scratch_sc; else kp->scratch_sc.clear();
+    }
   }
+  kp->last_use = ++e->kept_clock;
+  // the P slots of the operations recorded NOW (a kept program carries those of its first run)
+  for (std::vector<LInstr> *part : {&kp->lowered, &kp->lowered_join})
+    for (LInstr &li : *part) {
+      if (li.src == kNoSrc) continue;
+      const ROp &r = e->pend_prog[li.src];
+      li.pm1 = li.swapped ? r.pm2 : r.pm1;
+      li.pm2 = li.swapped ? r.pm1 : r.pm2;
+    }
+  const bool                   grouped = kp->grouped;
+  const std::vector<LInstr>   &lowered = kp->lowered, &lowered_join = kp->lowered_join;
+  const std::vector<unsigned> &lchunk = kp->lchunk;
+  const LowerStats            &lst = kp->lst;
+  if (grouped) e->stats.grouped_programs++;
   e->stats.instructions += lowered.size() + lowered_join.size();
   e->stats.stores_elided += lst.stores_dropped;
   if (lazy) {
@@ -953,6 +1038,7 @@ static int engine_init(rdk_partition_t *p, Engine *e) {
   e->clv_buffers = p->clv_buffers;
   e->S = p->sites;
   if (const char *env = getenv("RDK_LAZY")) e->lazy_enabled = atoi(env) != 0;
+  if (const char *env = getenv("RDK_KEEP_PROGRAMS")) e->keep_programs = atoi(env) != 0;  // experiments
   if (const char *env = getenv("RDK_SUBTREE_GROUPS")) e->subtree_groups = std::max(0, std::min(kMaxChunks, atoi(env)));
   e->Kreal = p->rate_cats;
   e->K = 1;
@@ -1845,6 +1931,7 @@ extern "C" int rdk_partition_set_subtree_groups(rdk_partition_t *p, int groups) 
   Engine                     *e = eng(p);
   std::lock_guard<std::mutex> lk(e->mu);
   e->subtree_groups = groups;
+  e->kept_programs.clear();  // the decision is part of a kept lowering
   return RDK_SUCCESS;
 }
 
@@ -1868,5 +1955,6 @@ extern "C" int rdk_partition_set_launch_config(rdk_partition_t *p, int ctas_per_
   e->ctas_per_sm = ctas_per_sm;
   e->threads = threads_per_cta;
   e->elems = elems_per_thread;
+  e->kept_programs.clear();  // the subtree-group decision of a kept lowering depends on the launch shape
   return RDK_SUCCESS;
 }

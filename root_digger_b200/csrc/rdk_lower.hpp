@@ -42,6 +42,7 @@ struct ROp {
   unsigned pm1, pm2;  // PHYSICAL P-matrix pool slots of the two child branches
   unsigned flags;
   unsigned slot;
+  unsigned id;  // position in the recorded program (set by the engine before lowering; carried into LInstr::src)
 };
 
 // ---- device instruction flags (shared with the kernel) --------------------------------------------
@@ -73,7 +74,13 @@ struct LInstr {
   int      c2scale; // its scale buffer (fCnt2M)
   unsigned pm1, pm2;  // pool slots of the tables A / B read
   unsigned slot;
+  // where pm1 / pm2 came from: recorded operation `src` (ROp::id), children exchanged or not -- a
+  // lowered program kept for the next identical traversal only needs its P slots refreshed
+  unsigned src;
+  bool     swapped;
 };
+
+constexpr unsigned kNoSrc = 0xffffffffu;
 
 struct LowerOptions {
   unsigned tips = 0;
@@ -120,6 +127,7 @@ inline void lower_program(const std::vector<ROp> &ops, const std::vector<unsigne
                           ((pv.flags & fWriteS) && scaler >= 0 && pv.pscale == scaler);
       if (!hazard) return;
       LInstr nop{};
+      nop.src = kNoSrc;
       nop.flags = fNop;
       nop.parent = kNoClv;
       nop.pscale = -1;
@@ -137,6 +145,7 @@ inline void lower_program(const std::vector<ROp> &ops, const std::vector<unsigne
       li.c2 = kNoClv;
       li.c1scale = li.c2scale = -1;
       li.slot = op.slot;
+      li.src = kNoSrc;
       if (op.flags & rLoadOnly) {
         // evaluate the stored CLV c1
         const bool in_v = vptr == op.c1 && vscale == op.c1scale;
@@ -158,10 +167,12 @@ inline void lower_program(const std::vector<ROp> &ops, const std::vector<unsigne
       }
       unsigned c1 = op.c1, c2 = op.c2, pm1 = op.pm1, pm2 = op.pm2;
       int      s1 = op.c1scale, s2 = op.c2scale;
+      bool swapped = false;
       auto swap_children = [&]() {
         std::swap(c1, c2);
         std::swap(pm1, pm2);
         std::swap(s1, s2);
+        swapped = !swapped;
       };
       unsigned fl = 0;
       bool     load_v = false;  // v does not hold child 2: load it (fLoadV2)
@@ -197,6 +208,8 @@ inline void lower_program(const std::vector<ROp> &ops, const std::vector<unsigne
       li.c2scale = (fl & fCnt2M) ? s2 : -1;
       li.pm1 = pm1;
       li.pm2 = pm2;
+      li.src = op.id;
+      li.swapped = swapped;
       if ((op.flags & rEval) && !(op.flags & rWrite)) {
         fl |= fEval;
         if (fl & fScale) fl |= fEvalScaler;

@@ -7,6 +7,24 @@
 
 #include <vector>
 
+namespace {
+// every instruction names the recorded operation its P slots came from (what lets the engine
+// refresh the slots of a kept program): check the mapping against the slots the lowering wrote
+bool sources_consistent(const std::vector<rdk::ROp> &ops, const std::vector<rdk::LInstr> &low) {
+  using namespace rdk;
+  for (const LInstr &x : low) {
+    if (x.flags & (fLoadV | fNop)) {
+      if (x.src != kNoSrc) return false;
+      continue;
+    }
+    if (x.src >= ops.size()) return false;
+    const ROp &r = ops[x.src];
+    if (x.pm1 != (x.swapped ? r.pm2 : r.pm1) || x.pm2 != (x.swapped ? r.pm1 : r.pm2)) return false;
+  }
+  return true;
+}
+}  // namespace
+
 extern "C" int rdk_debug_lower_program(unsigned int tips, unsigned int n_ops, const int *ops,
                                        unsigned int n_chunks, const unsigned int *chunk_off,
                                        int discard_writes, const unsigned char *scratch_clv,
@@ -27,6 +45,7 @@ extern "C" int rdk_debug_lower_program(unsigned int tips, unsigned int n_ops, co
     r.pm2 = (unsigned)f[7];
     r.flags = (unsigned)f[8];
     r.slot = (unsigned)f[9];
+    r.id = i;
   }
   std::vector<unsigned> coff;
   if (n_chunks > 1 && chunk_off) coff.assign(chunk_off, chunk_off + n_chunks + 1);
@@ -39,6 +58,10 @@ extern "C" int rdk_debug_lower_program(unsigned int tips, unsigned int n_ops, co
   std::vector<LInstr>   low;
   std::vector<unsigned> lchunk;
   lower_program(rops, coff, opt, low, lchunk);
+  if (!sources_consistent(rops, low)) {
+    rdk_errno = RDK_ERROR_PARAM;
+    return -2;
+  }
   if (low.size() > out_cap) {
     rdk_errno = RDK_ERROR_PARAM;
     return -1;
@@ -85,6 +108,7 @@ extern "C" int rdk_debug_lower_grouped(unsigned int tips, unsigned int n_ops, co
     r.pm2 = (unsigned)f[7];
     r.flags = (unsigned)f[8];
     r.slot = (unsigned)f[9];
+    r.id = i;
   }
   ForestInfo fi;
   if (!analyse_forest(rops, tips, fi)) return 0;
@@ -100,6 +124,10 @@ extern "C" int rdk_debug_lower_grouped(unsigned int tips, unsigned int n_ops, co
   opt.discard_writes = discard_writes != 0;
   std::vector<LInstr> lg, lj;
   lower_grouped(grouped, goff, join, opt, lg, lgoff, lj, nullptr);
+  if (!sources_consistent(rops, lg) || !sources_consistent(rops, lj)) {
+    rdk_errno = RDK_ERROR_PARAM;
+    return -2;
+  }
   if (lg.size() + lj.size() > out_cap) {
     rdk_errno = RDK_ERROR_PARAM;
     return -1;

@@ -388,6 +388,9 @@ def test_subtree_groups_are_array_order_semantics(n, S, K, data):
     ds = case.derivative_schedule(5, 0.7)
     want_root = compute_lh_root(o, ds, case.root_clv, case.root_scaler, mode=MODE_ENGINE)
     compute_lh(o, sched, case.root_clv, case.root_scaler)
+    others = [(rid, ratio, compute_lh(o, case.full_schedule(rid, ratio), case.root_clv, case.root_scaler, mode=MODE_ENGINE))
+              for rid, ratio in ((9, 0.5), (5, 0.8), (2 * n - 4, 0.1))]
+    compute_lh(o, sched, case.root_clv, case.root_scaler)
     some = list(sched[0][:: max(1, len(sched[0]) // 24)]) + [sched[0][-1]]
     want_clv = {op.parent_clv_index: o.get_clv(op.parent_clv_index).copy() for op in some}
     want_sc = {op.parent_scaler_index: o.get_scaler(op.parent_scaler_index).copy() for op in some}
@@ -417,6 +420,13 @@ def test_subtree_groups_are_array_order_semantics(n, S, K, data):
         for op in some:
             assert same_bits(g.get_clv(op.parent_clv_index), want_clv[op.parent_clv_index]), groups
             assert np.array_equal(g.get_scaler(op.parent_scaler_index), want_sc[op.parent_scaler_index]), groups
+        # the lowering of a traversal is kept and reused while the structure stays the same (new P slots
+        # every time); another root is another program, and coming back finds the first one again
+        if n >= 32:
+            assert g.stats()["programs_reused"] >= 3, g.stats()
+        for rid, ratio, w in others:
+            assert same_bits([compute_lh(g, case.full_schedule(rid, ratio), case.root_clv, case.root_scaler)], [w]), (groups, rid)
+        assert same_bits([compute_lh(g, sched, case.root_clv, case.root_scaler)], [want]), groups
         del g
 
 
