@@ -790,6 +790,15 @@ rooted_tree_t::sweep_schedule_t rooted_tree_t::generate_sweep_operations(size_t 
   if (begin > end || end > _roots.size()) throw std::invalid_argument("generate_sweep_operations: bad root range");
   sweep_schedule_t out;
   if (begin == end) return out;
+  {
+    const size_t q = end - begin;  // one directed-CLV operation + one root operation per placement, at most
+    out.ops.reserve(2 * q + 2);
+    out.mi.reserve(4 * q + 4);
+    out.bl.reserve(4 * q + 4);
+    out.pm_off.reserve(q + 1);
+    out.op_off.reserve(q + 1);
+    out.root_pos.reserve(q);
+  }
 
   const unode_t     *lchild = _tree->vroot->back, *rchild = _tree->vroot->next->back;
   const unsigned int ML = pm0, MR = pm0 + 1, MC = pm0 + 2;
