@@ -20,7 +20,7 @@ roofline= the dominant kernel (clv_program_kernel): algorithmic bytes (SURVEY 8d
 
 N > 1 (strong scaling: the global problem is fixed), one process per GPU, N = G_s x G_r
 (root_digger_b200.sharding.plan_grid).  Default G_s = N: the alignment's sites are
-split into N contiguous, 1024-aligned shards, CLVs resident per GPU, ONE NCCL all-reduce of the
+split into N contiguous, 256-aligned shards, CLVs resident per GPU, ONE NCCL all-reduce of the
 per-shard tree nodes per evaluation batch (the north-star layout).  --shard roots keeps a replica
 per GPU and splits the 2n-3 candidate placements of the sweep into N contiguous chunks instead
 (the rule exhaustive mode uses for ranks, reference src/model.cpp:1899-1907; no data-path

@@ -52,7 +52,7 @@ CONFIGS = {
 CONFIGS["cfg2_weak"] = dict(taxa=500, sites=100_000, sites_per_gpu=True, cats=4, data="evolved", partitions=1,
                             workload="cfg2 at constant work per GPU: 500 taxa x (100000 x N) sites, UNREST+G4, "
                                      "site-sharded (weak scaling of the headline step)")
-BLOCK = 1024  # site block of the data generator = RDK_SHARD_ALIGN
+BLOCK = 1024  # site block of the data generator (a multiple of RDK_SHARD_ALIGN: a shard is a range of its sites)
 
 
 def scaled(cfg: dict, scale: float) -> dict:

@@ -282,7 +282,7 @@ unsigned int rdk_sweep_chunk_hint(unsigned int sites, unsigned int rate_cats);
  * site_offset must be a multiple of RDK_SHARD_ALIGN unless it is 0; the
  * reduction tree is defined over the GLOBAL site index, so the result does not
  * depend on the number of shards. */
-#define RDK_SHARD_ALIGN 1024u
+#define RDK_SHARD_ALIGN 256u
 #define RDK_COMM_ID_BYTES 128
 int rdk_partition_set_shard(rdk_partition_t *partition,
                             unsigned long long site_offset,

@@ -19,7 +19,7 @@ RDK_ATTRIB_SITE_REPEATS = 1 << 10
 RDK_ATTRIB_NONREV = 1 << 11
 RDK_GAMMA_RATES_MEAN = 0
 RDK_GAMMA_RATES_MEDIAN = 1
-RDK_SHARD_ALIGN = 1024
+RDK_SHARD_ALIGN = 256
 RDK_SWEEP_KEEP_ROOT = 1
 RDK_SWEEP_DISCARD = 2
 

@@ -868,7 +868,7 @@ int finish_evals(rdk_partition_t *p, unsigned slots) {
   const bool sharded = e->global_sites != 0 && (e->comm != nullptr || e->global_sites != e->S);
   if (!sharded) {
     unsigned span = next_pow2(std::max(1u, n_witer));
-    tree_reduce_kernel<<<dim3(1, slots), 256, 0, e->stream>>>(e->d_partials, stride, n_witer, span,
+    tree_reduce_kernel<<<dim3(1, slots), 256, 0, e->stream>>>(e->d_partials, stride, n_witer, span, 1u,
                                                              d_out, 1, 0);
     CUDA_TRY(cudaGetLastError());
     e->stats.kernel_launches++;
@@ -892,8 +892,9 @@ int finish_evals(rdk_partition_t *p, unsigned slots) {
     }
     CUDA_TRY(cudaMemsetAsync(e->d_nodes, 0, need * sizeof(double), e->stream));
     if (lblocks) {
-      tree_reduce_kernel<<<dim3(lblocks, slots), 256, 0, e->stream>>>(
-          e->d_partials, stride, n_witer, span1, e->d_nodes, gblocks, boff);
+      const unsigned per_block = 256u / std::min(span1, 256u);  // nodes one block reduces
+      tree_reduce_kernel<<<dim3((lblocks + per_block - 1) / per_block, slots), 256, 0, e->stream>>>(
+          e->d_partials, stride, n_witer, span1, lblocks, e->d_nodes, gblocks, boff);
       CUDA_TRY(cudaGetLastError());
       e->stats.kernel_launches++;
       e->stats.reduce_launches++;
@@ -908,7 +909,7 @@ int finish_evals(rdk_partition_t *p, unsigned slots) {
                     g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
     }
     tree_reduce_kernel<<<dim3(1, slots), 256, 0, e->stream>>>(e->d_nodes, gblocks, gblocks,
-                                                             next_pow2(gblocks), d_out, 1, 0);
+                                                             next_pow2(gblocks), 1u, d_out, 1, 0);
     CUDA_TRY(cudaGetLastError());
     e->stats.kernel_launches++;
     e->stats.reduce_launches++;

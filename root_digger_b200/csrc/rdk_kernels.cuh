@@ -1174,25 +1174,30 @@ constexpr LaunchShape launch_shape(int E) {
 // Canonical reduction: balanced binary tree over contiguous halves of the
 // zero-padded (to a power of two) GLOBAL site index space.  The program kernel
 // produced the tree nodes that cover one warp iteration (32/K sites); this
-// kernel continues the same tree.  One block per (slot, node-range).
+// kernel continues the same tree.
 //   in : [slots][in_stride], n_in valid leaves per slot, leaf index offset
 //        `leaf0` within the padded tree (sharded partitions)
 //   out: [slots][out_stride]; out[slot][b] = tree node over leaves
-//        [b*span, (b+1)*span) (span = power of two)
-// With span >= n_in and one block per slot this yields the final sum.
+//        [b*span, (b+1)*span) (span = power of two), b < n_nodes
+// A node is reduced by R = min(span, 256) threads (each folds span / R consecutive
+// leaves with the same tree first); a block holds 256 / R nodes, blockIdx.y = slot.
+// With span >= n_in and one node per slot this yields the final sum.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) tree_reduce_kernel(const double* __restrict__ in,
                                                            unsigned in_stride, unsigned n_in,
-                                                           unsigned span, double* __restrict__ out,
+                                                           unsigned span, unsigned n_nodes,
+                                                           double* __restrict__ out,
                                                            unsigned out_stride, unsigned out_offset) {
   __shared__ double sm[256];
-  const unsigned slot = blockIdx.y, b = blockIdx.x, t = threadIdx.x;
-  const double*  p = in + (size_t)slot * in_stride;
   const unsigned R = span < 256u ? span : 256u;  // power of two
   const unsigned L = span / R;                   // power of two
+  const unsigned slot = blockIdx.y, t = threadIdx.x;
+  const unsigned b = blockIdx.x * (256u / R) + t / R;  // the node this thread works on
+  const unsigned tr = t % R;
+  const double*  p = in + (size_t)slot * in_stride;
   double         res = 0.0;
-  if (t < R) {
-    const unsigned long long base = (unsigned long long)b * span + (unsigned long long)t * L;
+  if (b < n_nodes) {
+    const unsigned long long base = (unsigned long long)b * span + (unsigned long long)tr * L;
     if (base < n_in) {
       double st[32];
       int    top = 0;
@@ -1208,10 +1213,10 @@ __global__ void __launch_bounds__(256) tree_reduce_kernel(const double* __restri
   sm[t] = res;
   __syncthreads();
   for (unsigned w = 1; w < R; w <<= 1) {
-    if (t < R && (t % (2 * w)) == 0) sm[t] = dadd(sm[t], sm[t + w]);
+    if ((tr % (2 * w)) == 0) sm[t] = dadd(sm[t], sm[t + w]);
     __syncthreads();
   }
-  if (t == 0) out[(size_t)slot * out_stride + out_offset + b] = sm[0];
+  if (tr == 0 && b < n_nodes) out[(size_t)slot * out_stride + out_offset + b] = sm[0 + t];
 }
 
 // ---------------------------------------------------------------------------

@@ -1,7 +1,7 @@
 """Shard planners (host logic of SURVEY.md section 8e).
 
   * sites: contiguous ranges of site patterns, one per GPU, aligned to
-    RDK_SHARD_ALIGN (1024) so that every shard boundary is a node boundary of
+    RDK_SHARD_ALIGN (256) so that every shard boundary is a node boundary of
     the canonical reduction tree -> the log-likelihood does not depend on the
     number of GPUs;
   * root placements: contiguous chunks of the root-id list, the rule the
@@ -10,7 +10,7 @@
 """
 from __future__ import annotations
 
-ALIGN = 1024
+ALIGN = 256
 
 
 def plan_site_shards(global_sites: int, nranks: int, align: int = ALIGN):

@@ -80,7 +80,7 @@ static inline int rdk_sweep_root_placements_ex(rdo_partition_t *p, unsigned int 
 /* chunks may always run in order; the hint is > 1 for small alignments so that the CPU
  * tests walk the chunked schedules of the host mirror too */
 #define RDK_SWEEP_MAX_CHUNKS 16u
-#define RDK_SHARD_ALIGN 1024u
+#define RDK_SHARD_ALIGN 256u
 static inline unsigned int rdk_sweep_chunk_hint(unsigned int sites, unsigned int rate_cats) {
   (void)rate_cats;
   return sites < 4096u ? 3u : 1u;

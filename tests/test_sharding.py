@@ -16,16 +16,21 @@ ROOT = Path(__file__).resolve().parent.parent
 
 
 def test_site_shard_plan():
-    for S in (0, 1, 1023, 1024, 1025, 100_000, 1_000_000):
+    A = sharding.ALIGN
+    assert A == 256  # include/rdk.h RDK_SHARD_ALIGN
+    for S in (0, 1, 255, 256, 257, 1023, 1024, 1025, 100_000, 1_000_000):
         for G in (1, 2, 3, 8):
             plan = sharding.plan_site_shards(S, G)
             assert len(plan) == G and sum(c for _, c in plan) == S
             pos = 0
             for off, cnt in plan:
-                assert off == pos and (off % 1024 == 0 or cnt == 0)
+                assert off == pos and (off % A == 0 or cnt == 0)
                 pos += cnt
     counts = [c for _, c in sharding.plan_site_shards(1_000_000, 8)]
-    assert max(counts) - min(counts) <= 1024 + 576   # balanced to one alignment block (last one ragged)
+    assert max(counts) - min(counts) <= 2 * A   # balanced to one alignment block (last one ragged)
+    # cfg2 over 8 GPUs: 12 544 sites = 1 568 warp iterations per GPU fit one E = 4 pass of a sweep in
+    # 4 chunks (37 CTAs x 11 warps x 4); the 13 312 of 1024-site blocks did not
+    assert max(c for _, c in sharding.plan_site_shards(100_000, 8)) == 12_544
 
 
 def test_grid_plan_prefers_replicas_that_fit():
@@ -66,16 +71,17 @@ def _worker(rank, world, port, S, q):
     case.setup(part, site_slice=sl)
     sched = case.full_schedule(2, 0.4)
     _, persite = compute_lh(part, sched, case.root_clv, case.root_scaler, persite=True, mode=MODE_ENGINE)
-    # per-shard nodes of the canonical tree (one per 1024-site block), zeros elsewhere
+    # per-shard nodes of the canonical tree (one per block of RDK_SHARD_ALIGN sites), zeros elsewhere
     L = load_oracle()
     import ctypes as C
-    nblocks = (S + 1023) // 1024
+    A = sharding.ALIGN
+    nblocks = (S + A - 1) // A
     nodes = np.zeros(nblocks)
-    for b in range((cnt + 1023) // 1024):
-        seg = np.ascontiguousarray(persite[b * 1024:(b + 1) * 1024])
-        pad = np.zeros(1024)
+    for b in range((cnt + A - 1) // A):
+        seg = np.ascontiguousarray(persite[b * A:(b + 1) * A])
+        pad = np.zeros(A)
         pad[:len(seg)] = seg
-        nodes[off // 1024 + b] = L.rdo_pairwise_sum(pad.ctypes.data_as(C.POINTER(C.c_double)), 1024)
+        nodes[off // A + b] = L.rdo_pairwise_sum(pad.ctypes.data_as(C.POINTER(C.c_double)), A)
     t = torch.from_numpy(nodes)
     dist.all_reduce(t)
     total = L.rdo_pairwise_sum(t.numpy().ctypes.data_as(C.POINTER(C.c_double)), nblocks)
