@@ -129,6 +129,13 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def wait_first(self, timeout=3.0):
+        """block until nvidia-smi has delivered its first sample: its start-up (NVML initialisation takes
+        driver locks for 0.1-0.3 s) is then over and does not fall into a timed region of a few tens of ms"""
+        t0 = time.time()
+        while self.proc and not self.lines and time.time() - t0 < timeout and self.proc.poll() is None:
+            time.sleep(0.01)
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -403,14 +410,17 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # the clock sampler runs from before the warm-up to the end of the measurements (it covers every timed
+    # region); it is started, and past its start-up, before anything is timed
+    sampler = ClockSampler(list(range(n_gpus))) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        sampler.wait_first()
     for _ in range(max(3, args.warmup)):
         lh0, sweep_lh = step()
     g.set_timing(True)
     g.reset_stats()
-    sampler = ClockSampler(list(range(n_gpus))) if rank == 0 else None
     barrier()
-    if sampler:
-        sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
