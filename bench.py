@@ -396,13 +396,37 @@ def run_ours(args):
         allv = gather_out.cpu().numpy().reshape(world, chunk_max)
         return np.concatenate([allv[q * G_s, :len(chunks[q])] for q in range(G_r)])
 
+    # the device arm's driver: the C ABI called with pointers bound once (schedules resident on the host in
+    # the ABI's own layout; what is timed is the engine, not numpy -> ctypes marshalling)
+    import ctypes as C
+    up, dp = C.POINTER(C.c_uint), C.POINTER(C.c_double)
+    keep = [np.ascontiguousarray(full_pm, dtype=np.uint32), np.ascontiguousarray(full_br, dtype=np.float64),
+            np.ascontiguousarray(pm_off, dtype=np.uint32), np.ascontiguousarray(mi, dtype=np.uint32),
+            np.ascontiguousarray(bl, dtype=np.float64), np.ascontiguousarray(op_off, dtype=np.uint32),
+            np.ascontiguousarray(chunk_off if chunk_off is not None else [0, len(pm_off) - 1], dtype=np.uint32),
+            np.zeros(len(pm_off) - 1)]
+    p_fpm, p_fbr, p_pmo, p_mi, p_bl, p_opo, p_co = [a.ctypes.data_as(dp if a.dtype == np.float64 else up) for a in keep[:7]]
+    sw_out = keep[7]
+    p_out = sw_out.ctypes.data_as(dp)
+    n_full_pm, n_full_ops, n_pl, n_co = len(keep[0]), len(full_ops), len(pm_off) - 1, len(keep[6]) - 1
+    L, zeros = g.L, g._zeros
+    root_clv, root_scaler = case.root_clv, case.root_scaler
+
     def step():
-        g.update_prob_matrices(full_pm, full_br)
-        g.L.rdk_update_clvs(g.p, full_arr, len(full_ops))
-        lh0 = g.root_loglikelihood(case.root_clv, case.root_scaler)
+        if L.rdk_update_prob_matrices(g.p, zeros, p_fpm, p_fbr, n_full_pm) != capi.RDK_SUCCESS:
+            raise RuntimeError("rdk_update_prob_matrices failed")
+        L.rdk_update_clvs(g.p, full_arr, n_full_ops)
+        lh0 = L.rdk_compute_root_loglikelihood(g.p, root_clv, root_scaler, zeros, None)
+        if chunk_off is None:
+            rc = L.rdk_sweep_root_placements_ex(g.p, n_pl, zeros, zeros, p_pmo, p_mi, p_bl, p_opo, sw_arr, root_clv,
+                                                root_scaler, sweep_flags, p_out)
+        else:
+            rc = L.rdk_sweep_root_placements_chunks(g.p, n_pl, zeros, zeros, p_pmo, p_mi, p_bl, p_opo, sw_arr, root_clv,
+                                                    root_scaler, sweep_flags, n_co, p_co, p_out)
+        if rc != capi.RDK_SUCCESS:
+            raise RuntimeError("sweep failed: rdk_errno %d" % L.rdk_errno_location()[0])
         out = np.empty(len(pos))
-        out[pos] = g.sweep_root_placements(pm_off, mi, bl, op_off, sw_arr, case.root_clv, case.root_scaler,
-                                           flags=sweep_flags, chunk_offsets=chunk_off)
+        out[pos] = sw_out
         return lh0, gather_placements(out)
 
     def barrier():
