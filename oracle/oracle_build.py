@@ -5,6 +5,10 @@ this; the product package (root_digger_b200/) never imports it.
   oracle/librd_oracle.so             oracle/Makefile
   tests/_build/librd_host_oracle.so  root_digger_b200/host/*.cpp compiled against the oracle
                                      through tests/oracle_shim/rdk.h (-DRD_BACKEND_ORACLE)
+  oracle/_ref/librd_reference_on_{oracle,engine}.so
+                                     RootDigger's own src/*.cpp, compiled unmodified from /root/reference
+                                     against root_digger_b200/compat/corax/corax.h (built where the
+                                     reference checkout exists; the GPU boxes receive the built files)
 """
 from __future__ import annotations
 
@@ -57,11 +61,12 @@ def build_reference_sources(backend: str = "oracle", force: bool = False):
     compiled from where they lie under /root/reference, against root_digger_b200/compat/corax/corax.h
     -- i.e. against the engine's C ABI (backend "engine": include/rdk.h + librdk_b200.so) or against
     the oracle behind the same ABI (backend "oracle": tests/oracle_shim/rdk.h + librd_oracle.so) --
-    plus tests/ref_build/ref_capi.cpp (ctypes wrappers) -> tests/_build/librd_reference_on_<backend>.so.
+    plus tests/ref_build/ref_capi.cpp (ctypes wrappers) -> oracle/_ref/librd_reference_on_<backend>.so
+    (git-ignored, not gpurun-ignored: no reference source is copied, only the built library travels).
     Returns None when the reference checkout is absent and no library was built earlier (the GPU
     boxes receive the built files)."""
     from root_digger_b200._build import INCLUDE, LIBDIR, PKG
-    outdir = ROOT / "tests" / "_build"
+    outdir = ORACLE / "_ref"
     outdir.mkdir(exist_ok=True)
     out = outdir / ("librd_reference_on_%s.so" % backend)
     ref_src = REFERENCE / "src"
