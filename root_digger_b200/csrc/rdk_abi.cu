@@ -490,6 +490,14 @@ int plan_segments(const Engine *e, unsigned n_witer, unsigned n_chunks, int n_in
   return 2;
 }
 
+// relative time per instruction of a program of n_instr instructions walked over n_witer warp
+// iterations in n_chunks chunks side by side, launched the way launch_lowered launches it
+double program_cost(const Engine *e, unsigned n_witer, unsigned n_chunks, int n_instr) {
+  LaunchSeg seg[2];
+  const int n = plan_segments(e, n_witer, n_chunks, n_instr, seg);
+  return seg[0].pl.cost + (n > 1 ? seg[1].pl.cost : 0.0);
+}
+
 // index -> device pointer translation of a lowered instruction
 void to_device_instr(Engine *e, const LInstr &li, Instr *out) {
   Instr in;
@@ -672,13 +680,14 @@ bool choose_subtree_groups(const Engine *e, unsigned n_witer, std::vector<ROp> &
   if (mode == 1 || n < 4 || n_witer == 0) return false;
   if (mode == 0 && (n < 48 || e->elems)) return false;
   static const unsigned kGroups[] = {2, 3, 4, 6, 8};
-  const double          flat = plan_launch(e, n_witer, 1).cost;
+  // (costs as the programs would really be launched: whole E = 4 passes + the rest in its own shape)
+  const double          flat = program_cost(e, n_witer, 1, (int)n);
   double                shared[17] = {0};
   if (mode == 0) {
     // a shard that keeps the device busy with one program gains nothing: skip the analysis
     double best_possible = 1e300;
     for (unsigned g : kGroups) {
-      shared[g] = plan_launch(e, n_witer, g).cost;
+      shared[g] = program_cost(e, n_witer, g, (int)(n / g));
       best_possible = std::min(best_possible, (double)n / g * shared[g]);
     }
     if (best_possible >= 0.85 * (double)n * flat) return false;
@@ -698,7 +707,7 @@ bool choose_subtree_groups(const Engine *e, unsigned n_witer, std::vector<ROp> &
         const unsigned cap = (unsigned)((n + g * div - 1) / (g * div));
         const unsigned used = assign_subtree_groups(fi, g, cap, group, longest, n_join);
         if (used < 2) continue;
-        const double per = used == g ? shared[g] : plan_launch(e, n_witer, used).cost;
+        const double per = used == g ? shared[g] : program_cost(e, n_witer, used, (int)longest);
         const double cost = longest * per + n_join * flat + 5.0;  // + a launch and its tail, us
         if (cost < best_cost) {
           best_cost = cost;
