@@ -389,6 +389,14 @@ int rdk_debug_lower_grouped(unsigned int tips, unsigned int n_ops, const int *op
                             unsigned int out_cap, unsigned int *out_group_off,
                             unsigned int *n_group_instr, unsigned int *n_total_instr);
 
+/* What the engine decides for a program (operations as above) on a shard of `sites` patterns x
+ * `rate_cats` categories on a device of `sm_count` SMs (0: 148): the number of subtree groups
+ * (0: one program in array order), the operations of the longest group and of the joining program.
+ * Pure host code. */
+int rdk_debug_choose_subtree_groups(unsigned int tips, unsigned int n_ops, const int *ops,
+                                    unsigned int sites, unsigned int rate_cats, int sm_count,
+                                    unsigned int *longest, unsigned int *n_join);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1945,6 +1945,44 @@ extern "C" int rdk_partition_set_subtree_groups(rdk_partition_t *p, int groups) 
   return RDK_SUCCESS;
 }
 
+// introspection (pure host code, no CUDA call): what choose_subtree_groups decides for a program
+// on a shard of `sites` x `rate_cats` on a device of `sm_count` SMs
+extern "C" int rdk_debug_choose_subtree_groups(unsigned int tips, unsigned int n_ops, const int *ops,
+                                               unsigned int sites, unsigned int rate_cats, int sm_count,
+                                               unsigned int *longest, unsigned int *n_join) {
+  Engine e;
+  e.sm_count = sm_count > 0 ? sm_count : 148;
+  e.tips = tips;
+  e.pend_prog.resize(n_ops);
+  for (unsigned i = 0; i < n_ops; ++i) {
+    const int *f = ops + 10 * (size_t)i;
+    ROp       &r = e.pend_prog[i];
+    memset(&r, 0, sizeof(r));
+    r.parent = (unsigned)f[0];
+    r.pscale = f[1];
+    r.c1 = (unsigned)f[2];
+    r.c2 = (unsigned)f[3];
+    r.c1scale = f[4];
+    r.c2scale = f[5];
+    r.pm1 = (unsigned)f[6];
+    r.pm2 = (unsigned)f[7];
+    r.flags = (unsigned)f[8];
+    r.slot = (unsigned)f[9];
+    r.id = i;
+  }
+  unsigned K = 1;
+  while (K < rate_cats) K <<= 1;
+  const unsigned        n_witer = (unsigned)(((unsigned long long)sites * K + 31) / 32);
+  std::vector<ROp>      grouped, join;
+  std::vector<unsigned> goff;
+  if (!choose_subtree_groups(&e, n_witer, grouped, goff, join)) return 0;
+  unsigned l = 0;
+  for (size_t g = 0; g + 1 < goff.size(); ++g) l = std::max(l, goff[g + 1] - goff[g]);
+  if (longest) *longest = l;
+  if (n_join) *n_join = (unsigned)join.size();
+  return (int)goff.size() - 1;
+}
+
 extern "C" int rdk_partition_set_tail_mode(rdk_partition_t *p, int mode) {
   // kept for ABI compatibility: the program kernel has a single tail rule now (slots without an
   // iteration of their own recompute the warp's last iteration)

@@ -454,3 +454,41 @@ def test_subtree_groups_leave_other_programs_alone():
             got.update(run_lowered(low, groups[goff[g]:goff[g + 1]]))
         got.update(run_lowered(low, join))
         assert got == want and ref.clv == low.clv and ref.sc == low.sc
+
+
+def choose_groups(tips, ops, sites, cats, sm_count=148):
+    L = capi.load_engine()
+    L.rdk_debug_choose_subtree_groups.restype = C.c_int
+    n = len(ops)
+    arr = np.ascontiguousarray(np.array(ops, dtype=np.int64).astype(np.int32).reshape(n, 10))
+    longest, n_join = C.c_uint(0), C.c_uint(0)
+    g = L.rdk_debug_choose_subtree_groups(C.c_uint(tips), C.c_uint(n), arr.ctypes.data_as(C.POINTER(C.c_int)),
+                                          C.c_uint(sites), C.c_uint(cats), C.c_int(sm_count), C.byref(longest),
+                                          C.byref(n_join))
+    return g, longest.value, n_join.value
+
+
+def test_the_cost_model_groups_small_shards_only():
+    """rdk_abi.cu choose_subtree_groups on a 148-SM device: the shard one GPU holds when
+    cfg2 runs on 8 / 4 GPUs and the cfg3 shard are grouped, cfg2 on one or two GPUs and the cfg5 shard
+    (throughput bound) stay one program in array order, and so does anything short"""
+    rng = random.Random(1)
+    ops500, *_ = post_order_ops(rng, 500)
+    g, longest, n_join = choose_groups(500, ops500, 12544, 4)
+    assert g == 4 and longest <= 140 and n_join <= 24 and longest * g + n_join >= 499
+    g, longest, n_join = choose_groups(500, ops500, 25088, 4)
+    assert g in (2, 3) and longest <= 280
+    assert choose_groups(500, ops500, 50176, 4)[0] == 0
+    assert choose_groups(500, ops500, 100000, 4)[0] == 0
+    ops2000, *_ = post_order_ops(rng, 2000)
+    g, longest, n_join = choose_groups(2000, ops2000, 62464, 4)
+    assert g >= 4 and longest <= 2 * 1999 // g
+    ops10k, *_ = post_order_ops(rng, 10000)
+    assert choose_groups(10000, ops10k, 125184, 4)[0] == 0
+    # too short to be worth a second launch; a caterpillar has nothing to deal
+    ops30, *_ = post_order_ops(rng, 30)
+    assert choose_groups(30, ops30, 1000, 4)[0] == 0
+    cat, *_ = post_order_ops(rng, 400, shape="caterpillar")
+    assert choose_groups(400, cat, 12544, 4)[0] == 0
+    # any category count: the device works on the next power of two
+    assert choose_groups(500, ops500, 12544, 3)[0] == 4
