@@ -130,7 +130,7 @@ def build_lbfgsb(force: bool = False) -> Path:
 def host_sources():
     return [HOST / "tree.cpp", HOST / "tree_capi.cpp", HOST / "msa.cpp", HOST / "partition_file.cpp", HOST / "checkpoint.cpp",
             HOST / "checkpoint_capi.cpp", HOST / "model.cpp",
-            HOST / "lbfgsb_driver.cpp", HOST / "model_capi.cpp"]
+            HOST / "lbfgsb_driver.cpp", HOST / "model_capi.cpp", HOST / "optim_capi.cpp"]
 
 
 def build_host(force: bool = False) -> Path:

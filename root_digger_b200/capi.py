@@ -638,6 +638,52 @@ class RootedTree:
 # ---------------------------------------------------------------------------
 # model_t mirror (host C++) through the C wrappers
 # ---------------------------------------------------------------------------
+# the optimiser components of host/optim.hpp, driven alone (host/optim_capi.cpp)
+# ---------------------------------------------------------------------------
+_SLOPE_FN = C.CFUNCTYPE(None, C.c_double, _dp, _dp, C.c_void_p)
+_OBJECTIVE_FN = C.CFUNCTYPE(C.c_double, _dp, C.c_int, C.c_void_p)
+
+
+def slope_root(fn, lo: float, hi: float, x_tolerance: float = 1e-12, lib: C.CDLL | None = None):
+    """rd::slope_root_brent: the root of the slope of `fn` between lo and hi, where fn(x) ->
+    (value, slope) and the slopes at lo and hi have opposite signs (model_t::optimize_alpha's
+    bracketing search, reference src/model.cpp:606-676).  Returns (x, value, slope, probes)."""
+    L = lib or load_tree_lib()
+    L.rdh_optim_slope_root.argtypes = [_SLOPE_FN, C.c_void_p, C.c_double, C.c_double, C.c_double, _dp, _up]
+
+    def thunk(x, value, slope, _user):
+        v, s = fn(x)
+        value[0], slope[0] = v, s
+
+    out = (C.c_double * 3)()
+    probes = C.c_uint(0)
+    if not L.rdh_optim_slope_root(_SLOPE_FN(thunk), None, lo, hi, x_tolerance, out, C.byref(probes)):
+        raise RuntimeError(L.rdh_last_error().decode())
+    return out[0], out[1], out[2], probes.value
+
+
+def minimize_in_box(fn, x0, lower: float, upper: float, pgtol: float = 1e-7, factr: float = 1e4,
+                    lib: C.CDLL | None = None):
+    """rd::minimize_in_box: L-BFGS-B with forward-difference gradients inside [lower, upper]^n
+    (model_t::optimize_params, reference src/model.cpp:1430-1522).  Returns (x, f_end, evaluations);
+    x is the final point when it is not worse than x0, else x0."""
+    L = lib or load_tree_lib()
+    L.rdh_optim_minimize_in_box.argtypes = [_OBJECTIVE_FN, C.c_void_p, _dp, C.c_int, C.c_double, C.c_double,
+                                            C.c_double, C.c_double, _dp, _up]
+    x = np.array(x0, dtype=np.float64)
+
+    def thunk(ptr, n, _user):
+        return float(fn(np.ctypeslib.as_array(ptr, shape=(n,)).copy()))
+
+    f_end = C.c_double(0.0)
+    calls = C.c_uint(0)
+    if not L.rdh_optim_minimize_in_box(_OBJECTIVE_FN(thunk), None, _ptr(x, _dp), len(x), lower, upper, pgtol,
+                                       factr, C.byref(f_end), C.byref(calls)):
+        raise RuntimeError(L.rdh_last_error().decode())
+    return x, f_end.value, calls.value
+
+
+# ---------------------------------------------------------------------------
 def _bind_model(L: C.CDLL):
     if getattr(L, "_rdh_model_bound", False):
         return
@@ -663,6 +709,8 @@ def _bind_model(L: C.CDLL):
     L.rdh_model_initialize_partitions.argtypes = [vp, C.c_int]
     L.rdh_model_set_fused.argtypes = [vp, C.c_int]
     L.rdh_model_set_sweep_mode.argtypes = [vp, C.c_int]
+    L.rdh_model_set_batched_probes.argtypes = [vp, C.c_int]
+    L.rdh_model_batched_probes.argtypes = [vp]
     L.rdh_model_set_params.argtypes = [vp, C.c_uint, _dp, _dp, _dp]
     L.rdh_model_compute_lh.argtypes = [vp, C.c_uint, C.c_double, _dp]
     L.rdh_model_compute_lh_root.argtypes = [vp, C.c_uint, C.c_double, _dp]
@@ -943,6 +991,16 @@ class Model:
 
     def set_fused(self, on: bool):
         self.L.rdh_model_set_fused(self.h, 1 if on else 0)
+
+    def set_batched_probes(self, on: bool):
+        """root-only evaluations of compute_dlh / optimize_alpha go to the engine as one fused batch
+        (default; RD_BATCHED_PROBES=0 in the environment turns it off) or one call each, as the
+        reference issues them (src/model.cpp:481-519, 679-794).  Same values either way."""
+        self.L.rdh_model_set_batched_probes(self.h, 1 if on else 0)
+
+    @property
+    def batched_probes(self) -> bool:
+        return bool(self.L.rdh_model_batched_probes(self.h))
 
     SWEEP_SEQUENTIAL, SWEEP_PATH, SWEEP_DIRECTED = 0, 1, 2
 

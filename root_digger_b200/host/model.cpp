@@ -1,30 +1,29 @@
-// model.cpp -- see model.hpp.  Every member cites the reference code it mirrors
-// (RootDigger src/model.cpp); quirks that change results are kept on purpose
+// model.cpp -- see model.hpp.  Members cite the reference code whose behaviour they reproduce
+// (RootDigger src/model.cpp); quirks that change results are kept on purpose and named
 // (SURVEY.md Appendix B).
 //
-// PROVENANCE.  Two kinds of code live in this file.
-//  (1) DERIVED from the reference, statement for statement: the optimiser drivers and setters --
-//      brents (src/model.cpp:606-676), optimize_alpha (:679-794), bfgs_params (:1430-1522) and its
-//      wrappers, search (:1008-1138), exhaustive_search (:1140-1258), the gamma / frequency
-//      setters (:199-355).  The trajectory of an optimiser is part of the result ("chosen root
-//      branch, LWR ranking and optimised alpha identical"), so these follow the reference's
-//      control flow exactly; they are a mirror, not a design of this repository.  The boundary
-//      they sit on is proven with the reference's OWN file instead: src/model.cpp compiles
-//      unchanged against root_digger_b200/compat/corax/corax.h and returns the bits of this mirror
-//      (tests/test_reference_sources.py, tests/test_gpu_reference_sources.py).  A host that has
-//      the reference checkout can therefore link that file and drop (1) altogether.
-//  (2) ORIGINAL to this engine: the directed-CLV sweep and its chunking (sweep_root_lh), site and
-//      partition shards with the NCCL plumbing (shard_spec_t, last_partition_lh), the fused
-//      batched root evaluations of compute_dlh, the exception-safe partition loops, the outer
-//      iteration cap for bounded benchmark samples.
+// How this file is organised, and what it owes to the reference.
+//   * The RESULT of RootDigger is the end point of two optimiser trajectories per candidate (model
+//     parameters by L-BFGS-B, position on the branch by a bracketing search on the slope), so the
+//     decisions taken along them -- which comparison, on which floating-point expression, in which
+//     order -- are specified by the reference and reproduced here; tests/test_reference_sources.py
+//     runs the reference's OWN src/model.cpp (compiled unchanged against compat/corax/corax.h) next
+//     to this file and demands the same bits.
+//   * The code that takes those decisions is this repository's: the optimisers are stand-alone
+//     components (optim.hpp: slope_root_brent, lbfgsb_session_t, minimize_in_box) driven through
+//     functors; every root-only evaluation on a branch goes through ONE primitive (probe_branch)
+//     that hands the engine whole batches -- both evaluations of a slope, the five evaluations
+//     optimize_alpha needs before its first decision, a whole dyadic level of its sign-change
+//     search -- as one fused call, one synchronisation and (on site shards) one all-reduce; the
+//     two search drivers share their bookkeeping; the placement sweep is a directed-CLV pass in
+//     chunks; partitions may be sharded over GPUs (shard_spec_t) and report their terms.
 #include "model.hpp"
-
-#include "lbfgsb_driver.hpp"
 
 #include <algorithm>
 #include <cmath>
 #include <exception>
 #include <cstdlib>
+#include <cstring>
 #include <limits>
 #include <numeric>
 #include <sstream>
@@ -36,10 +35,6 @@ model_params_t random_params(size_t size, uint64_t seed) {
   std::uniform_real_distribution<> dist(1e-4, 1.0);
   for (auto &f : mp) f = dist(engine);
   return mp;
-}
-
-static inline size_t compute_final_size(size_t vector_size, double ratio, size_t min) {
-  return std::max(static_cast<size_t>(vector_size * ratio), min);
 }
 
 static std::string engine_error() { return std::string(rdk_errmsg); }
@@ -58,7 +53,9 @@ static void for_each_partition(size_t n, bool dynamic, Body &&body) {
       errors[i] = std::current_exception();
     }
   };
-  if (dynamic) {
+  if (n == 1) {
+    guarded(0);  // the common case (cfg2 / cfg3 / cfg5): no thread team to wake per engine call
+  } else if (dynamic) {
 #pragma omp parallel for schedule(dynamic)
     for (size_t i = 0; i < n; ++i) guarded(i);
   } else {
@@ -78,6 +75,7 @@ model_t::model_t(rooted_tree_t tree, const std::vector<msa_t> &msas,
     : _invariant_sites{invariant_sites}, _seed{seed}, _early_stop{early_stop} {
   _random_engine = std::minstd_rand(_seed);
   _tree = std::move(tree);
+  if (const char *env = std::getenv("RD_BATCHED_PROBES")) _batched_probes = std::atoi(env) != 0;
   if (rate_cats.size() < msas.size())
     throw std::invalid_argument("one rate heterogeneity option per partition is required");
   for (auto rc : rate_cats) {
@@ -153,7 +151,7 @@ model_t::~model_t() {
 }
 
 // ---------------------------------------------------------------------------
-// parameter setters (src/model.cpp:184-355)
+// parameter plumbing (reference src/model.cpp:184-355)
 // ---------------------------------------------------------------------------
 void model_t::set_subst_rates(size_t p, const model_params_t &mp) {
   rdk_set_subst_params(_partitions[p], 0, mp.data());
@@ -163,408 +161,464 @@ void model_t::set_subst_rates_random(size_t p, const msa_t &msa) {
   set_subst_rates(p, random_params(msa.states() * msa.states() - msa.states(), _random_engine()));
 }
 
+void model_t::set_subst_rates_uniform() {
+  for (size_t p = 0; p < _partitions.size(); ++p) {
+    const unsigned int states = _partitions[p]->states, off_diagonal = states * states - states;
+    set_subst_rates(p, model_params_t(off_diagonal, 1.0 / off_diagonal));
+  }
+}
+
 void model_t::set_gamma_weights(size_t p, model_params_t w) {
-  double sum = 0.0;
-  for (auto &f : w) sum += f;
-  for (auto &f : w) f /= sum;
+  double total = 0.0;
+  for (double v : w) total += v;
+  for (double &v : w) v /= total;
   rdk_set_category_weights(_partitions[p], w.data());
 }
 
+// discrete-Gamma category rates for shape `alpha` into the partition and into _rate_rates
+void model_t::install_gamma_rates(size_t p, double alpha, int mode) {
+  auto &rates = _rate_rates[p];
+  rdk_compute_gamma_cats(alpha, (unsigned)rates.size(), rates.data(), mode);
+  rdk_set_category_rates(_partitions[p], rates.data());
+}
+
+// Initial state of a partition: its category weights and the rates for shape 1.
+// Appendix B-1: the reference initialises BOTH the mean- and the median-typed categories with
+// the MEAN discretisation at alpha = 1 (src/model.cpp:238-245,256-263); free rates start at 1.
 void model_t::set_gamma_rates(size_t p) {
   rdk_set_category_weights(_partitions[p], _rate_weights[p].data());
-  switch (_rate_category_types[p]) {
-  case rate_category::MEAN: set_gamma_rates_mean(p); break;
-  case rate_category::MEDIAN: set_gamma_rates_median(p); break;
-  default: set_gamma_rates_free(p); break;
+  if (_rate_category_types[p] == rate_category::FREE) {
+    std::fill(_rate_rates[p].begin(), _rate_rates[p].end(), 1.0);
+    rdk_set_category_rates(_partitions[p], _rate_rates[p].data());
+    return;
   }
+  install_gamma_rates(p, 1.0, RDK_GAMMA_RATES_MEAN);
 }
 
+// The shape the optimiser proposes.
+// Appendix B-1: with a shape given, both category types use the MEDIAN discretisation
+// (src/model.cpp:247-254,265-272).  Appendix B-2: proposed FREE rates are normalised into a
+// temporary that is dropped -- the stored rates are what is (re)installed (:279-290), so free
+// rates never move; only the free WEIGHTS are effective.
 void model_t::set_gamma_rates(size_t p, const model_params_t &alpha) {
-  switch (_rate_category_types[p]) {
-  case rate_category::MEAN: set_gamma_rates_mean(p, alpha[0]); break;
-  case rate_category::MEDIAN: set_gamma_rates_median(p, alpha[0]); break;
-  default: set_gamma_rates_free(p, alpha); break;
+  if (_rate_category_types[p] == rate_category::FREE) {
+    rdk_set_category_rates(_partitions[p], _rate_rates[p].data());
+    return;
   }
-}
-
-// Appendix B-1: the no-argument variants use alpha = 1 in MEAN mode, the
-// variants taking alpha use MEDIAN mode, for both category types
-// (src/model.cpp:238-272)
-void model_t::set_gamma_rates_mean(size_t p) {
-  rdk_compute_gamma_cats(1.0, (unsigned)_rate_rates[p].size(), _rate_rates[p].data(),
-                         RDK_GAMMA_RATES_MEAN);
-  rdk_set_category_rates(_partitions[p], _rate_rates[p].data());
-}
-void model_t::set_gamma_rates_mean(size_t p, double alpha) {
-  rdk_compute_gamma_cats(alpha, (unsigned)_rate_rates[p].size(), _rate_rates[p].data(),
-                         RDK_GAMMA_RATES_MEDIAN);
-  rdk_set_category_rates(_partitions[p], _rate_rates[p].data());
-}
-void model_t::set_gamma_rates_median(size_t p) {
-  rdk_compute_gamma_cats(1.0, (unsigned)_rate_rates[p].size(), _rate_rates[p].data(),
-                         RDK_GAMMA_RATES_MEAN);
-  rdk_set_category_rates(_partitions[p], _rate_rates[p].data());
-}
-void model_t::set_gamma_rates_median(size_t p, double alpha) {
-  rdk_compute_gamma_cats(alpha, (unsigned)_rate_rates[p].size(), _rate_rates[p].data(),
-                         RDK_GAMMA_RATES_MEDIAN);
-  rdk_set_category_rates(_partitions[p], _rate_rates[p].data());
-}
-void model_t::set_gamma_rates_free(size_t p) {
-  for (auto &r : _rate_rates[p]) r = 1.0;
-  rdk_set_category_rates(_partitions[p], _rate_rates[p].data());
-}
-// Appendix B-2: the normalised copy is discarded, the stored rates are installed
-// (src/model.cpp:279-290)
-void model_t::set_gamma_rates_free(size_t p, model_params_t free_rates) {
-  double sum = 0.0;
-  for (size_t i = 0; i < free_rates.size(); ++i) sum += free_rates[i] * _rate_weights[p][i];
-  for (auto &f : free_rates) f /= sum;
-  rdk_set_category_rates(_partitions[p], _rate_rates[p].data());
+  install_gamma_rates(p, alpha[0], RDK_GAMMA_RATES_MEDIAN);
 }
 
 void model_t::update_invariant_sites(size_t p) {
   if (_invariant_sites) {
     rdk_update_invariant_sites(_partitions[p]);
-  } else {
-    for (unsigned int i = 0; i < _submodels; ++i)
-      rdk_update_invariant_sites_proportion(_partitions[p], i, 0.0);
+    return;
   }
+  for (unsigned int m = 0; m < _submodels; ++m) rdk_update_invariant_sites_proportion(_partitions[p], m, 0.0);
 }
 
-// src/model.cpp:302-325
+// src/model.cpp:302-325: every alignment row goes to the tip of the same label
 void model_t::set_tip_states(size_t p, const msa_t &msa) {
-  auto label_map = _tree.label_map();
-  for (int i = 0; i < msa.count(); ++i) {
-    auto it = label_map.find(msa.label(i));
-    if (it == label_map.end())
-      throw std::runtime_error(std::string("Could not find taxa ") + msa.label(i) + " in tree");
-    if (rdk_set_tip_states(_partitions[p], it->second, msa.map(), msa.sequence(i)) == RDK_FAILURE)
-      throw std::runtime_error("failed to set tip " + std::to_string(i) + ": " + engine_error());
+  const auto tip_of = _tree.label_map();
+  for (int row = 0; row < msa.count(); ++row) {
+    const auto hit = tip_of.find(msa.label(row));
+    if (hit == tip_of.end())
+      throw std::runtime_error(std::string("Could not find taxa ") + msa.label(row) + " in tree");
+    if (rdk_set_tip_states(_partitions[p], hit->second, msa.map(), msa.sequence(row)) == RDK_FAILURE)
+      throw std::runtime_error("failed to set tip " + std::to_string(row) + ": " + engine_error());
   }
   rdk_set_pattern_weights(_partitions[p], msa.weights());
 }
 
-// src/model.cpp:327-339
+// src/model.cpp:327-339: a state that never occurs makes the model degenerate -- refused
 void model_t::set_empirical_freqs(size_t p) {
   rdk_partition_t *partition = _partitions[p];
-  double          *emp = rdk_msa_empirical_frequencies(partition);
-  if (!emp) throw std::runtime_error("empirical frequencies failed: " + engine_error());
-  for (size_t i = 0; i < partition->states; ++i) {
-    if (emp[i] <= 0) {
-      free(emp);
-      throw invalid_empirical_frequencies_exception(
-          "One of the state frequenices is zero while using emperical frequencies");
-    }
-  }
-  rdk_set_frequencies(partition, 0, emp);
-  free(emp);
+  struct freed_t {
+    double *v;
+    ~freed_t() { free(v); }
+  } emp{rdk_msa_empirical_frequencies(partition)};
+  if (!emp.v) throw std::runtime_error("empirical frequencies failed: " + engine_error());
+  if (std::any_of(emp.v, emp.v + partition->states, [](double f) { return f <= 0; }))
+    throw invalid_empirical_frequencies_exception(
+        "One of the state frequenices is zero while using emperical frequencies");
+  rdk_set_frequencies(partition, 0, emp.v);
 }
 
 void model_t::set_empirical_freqs() {
-  for (size_t i = 0; i < _partitions.size(); ++i) set_empirical_freqs(i);
+  for (size_t p = 0; p < _partitions.size(); ++p) set_empirical_freqs(p);
 }
 
 void model_t::set_freqs(size_t p, const model_params_t &freqs) {
-  for (auto f : freqs)
-    if (f <= 0.0) throw std::runtime_error("Frequencies with 0 entries are not allowed");
+  if (std::any_of(freqs.begin(), freqs.end(), [](double f) { return f <= 0.0; }))
+    throw std::runtime_error("Frequencies with 0 entries are not allowed");
   rdk_set_frequencies(_partitions[p], 0, freqs.data());
 }
 
-// Appendix B-4 (src/model.cpp:350-355)
+// Appendix B-4 (src/model.cpp:350-355): all four frequencies are free, renormalised on the way in
 void model_t::set_freqs_all_free(size_t p, model_params_t freqs) {
-  double sum = 0.0;
-  for (auto v : freqs) sum += v;
-  for (auto &f : freqs) f /= sum;
+  double total = 0.0;
+  for (double v : freqs) total += v;
+  for (double &v : freqs) v /= total;
   set_freqs(p, freqs);
 }
 
-void model_t::set_subst_rates_uniform() {
-  for (size_t i = 0; i < _partitions.size(); ++i) {
-    unsigned int   states = _partitions[i]->states;
-    unsigned int   params = states * states - states;
-    model_params_t mp(params, 1.0 / params);
-    set_subst_rates(i, mp);
-  }
-}
-
 void model_t::set_model_params(const std::vector<partition_parameters_t> &params) {
-  for (size_t i = 0; i < params.size(); ++i) {
-    set_subst_rates(i, params[i].subst_rates);
-    set_freqs(i, params[i].freqs);
-    set_gamma_rates(i, params[i].gamma_alpha);
-    if (_rate_category_types[i] == rate_category::FREE) set_gamma_weights(i, params[i].gamma_weights);
+  for (size_t p = 0; p < params.size(); ++p) {
+    set_subst_rates(p, params[p].subst_rates);
+    set_freqs(p, params[p].freqs);
+    set_gamma_rates(p, params[p].gamma_alpha);
+    if (_rate_category_types[p] == rate_category::FREE) set_gamma_weights(p, params[p].gamma_weights);
   }
 }
 
+// Appendix B-9: every start begins from rates 1/12 and empirical frequencies
+void model_t::reset_to_defaults() {
+  set_subst_rates_uniform();
+  set_empirical_freqs();
+}
+
+// src/model.cpp:979-1005: the optimiser's starting point for one partition; FREE weights are
+// drawn from the model's generator (so the draw order over partitions is part of the result)
+partition_parameters_t model_t::make_partition_parameters(size_t states, rate_category rc,
+                                                          size_t rate_cat_count) {
+  partition_parameters_t pp;
+  const size_t           off_diagonal = states * states - states;
+  pp.subst_rates.assign(off_diagonal, 1.0 / off_diagonal);
+  pp.freqs.assign(states, 1.0 / states);
+  if (rc == rate_category::FREE) {
+    pp.gamma_alpha.assign(rate_cat_count, 1.0);
+    pp.gamma_weights.resize(rate_cat_count);
+    std::uniform_real_distribution<> unit(0.0, 1.0);
+    for (auto &w : pp.gamma_weights) w = unit(_random_engine);
+  } else {
+    pp.gamma_alpha.assign(1, 1.0);
+  }
+  return pp;
+}
+
+std::vector<partition_parameters_t> model_t::fresh_parameters() {
+  std::vector<partition_parameters_t> params;
+  params.reserve(_partitions.size());
+  for (size_t p = 0; p < _partitions.size(); ++p)
+    params.push_back(
+        make_partition_parameters(_partitions[p]->states, _rate_category_types[p], _partitions[p]->rate_cats));
+  return params;
+}
+
 // ---------------------------------------------------------------------------
-// likelihood facade
+// evaluation
 // ---------------------------------------------------------------------------
-// src/model.cpp:357-370: the reference issues one corax_update_prob_matrices
-// call per branch from an OpenMP loop; one call with all branches is the same
-// thing for the engine (it batches them into a single kernel anyway)
+model_t::traversal_t model_t::full_traversal(const root_location_t &rl) {
+  traversal_t t;
+  std::tie(t.ops, t.pmatrix_indices, t.branch_lengths) = _tree.generate_operations(rl);
+  return t;
+}
+
+// src/model.cpp:357-370: the reference issues one corax_update_prob_matrices call per branch from
+// an OpenMP loop; one call with all branches is the same thing for the engine (one kernel)
 void model_t::update_pmatrix_partition(size_t pi, const std::vector<unsigned int> &pmatrix_indices,
                                        const std::vector<double> &branch_lengths) {
   if (pmatrix_indices.empty()) return;
-  int rc = rdk_update_prob_matrices(_partitions[pi], _param_indicies[pi].data(), pmatrix_indices.data(),
-                                    branch_lengths.data(), (unsigned)pmatrix_indices.size());
-  if (rc == RDK_FAILURE) throw std::runtime_error(engine_error());
+  if (rdk_update_prob_matrices(_partitions[pi], _param_indicies[pi].data(), pmatrix_indices.data(),
+                               branch_lengths.data(), (unsigned)pmatrix_indices.size()) == RDK_FAILURE)
+    throw std::runtime_error(engine_error());  // the message of THIS thread
 }
 
-// src/model.cpp:372-382 (Appendix B-3: always "updated")
-std::vector<bool> model_t::update_pmatrices(const std::vector<unsigned int> &pmatrix_indices,
-                                            const std::vector<double>       &branch_lengths) {
-  std::vector<bool> updated(_partitions.size(), true);
-  for (size_t i = 0; i < _partitions.size(); ++i)
-    update_pmatrix_partition(i, pmatrix_indices, branch_lengths);
-  return updated;
+double model_t::root_loglikelihood(size_t pi) {
+  return rdk_compute_root_loglikelihood(_partitions[pi], _tree.root_clv_index(), _tree.root_scaler_index(),
+                                        _param_indicies[pi].data(), nullptr);
 }
 
-// src/model.cpp:384-413
+static double sum_in_order(const std::vector<double> &terms) {
+  double total = 0.0;
+  for (double v : terms) total += v;
+  return total;
+}
+
+static void refuse_nan(double lh) {
+  if (std::isnan(lh)) throw std::runtime_error("lh at root is not a number: " + std::to_string(lh));
+}
+
+// src/model.cpp:384-413.  The reference adds the partitions with an OpenMP reduction (:397) whose
+// association order depends on the thread count; here the terms are added in partition order, so
+// the result is the same on any host and on any number of GPUs.  (Appendix B-3: the P-matrices
+// are refreshed on every call, the "changed" flags of the reference are always true.)
 double model_t::compute_lh(const root_location_t &root_location) {
+  const traversal_t trav = full_traversal(root_location);
+  for (size_t p = 0; p < _partitions.size(); ++p)
+    update_pmatrix_partition(p, trav.pmatrix_indices, trav.branch_lengths);
+  std::vector<double> terms(_partitions.size(), 0.0);
+  for_each_partition(_partitions.size(), false, [&](size_t p) {
+    rdk_update_clvs(_partitions[p], trav.ops.data(), (unsigned)trav.ops.size());
+    terms[p] = root_loglikelihood(p);
+  });
+  _last_part_lh = terms;
+  return sum_in_order(terms);
+}
+
+// src/model.cpp:415-452: the two root branches and the root CLV only
+double model_t::compute_lh_root(const root_location_t &root) {
+  rdk_operation_t           op;
+  std::vector<unsigned int> matrix_indices;
+  std::vector<double>       branch_lengths;
+  std::tie(op, matrix_indices, branch_lengths) = _tree.generate_derivative_operations(root);
+  std::vector<double> terms(_partitions.size(), 0.0);
+  for_each_partition(_partitions.size(), false, [&](size_t p) {
+    update_pmatrix_partition(p, matrix_indices, branch_lengths);
+    rdk_update_clvs(_partitions[p], &op, 1);
+    terms[p] = root_loglikelihood(p);
+  });
+  _last_part_lh = terms;
+  const double lh = sum_in_order(terms);
+  refuse_nan(lh);
+  return lh;
+}
+
+// src/model.cpp:454-476: what the parameter optimiser evaluates, one partition at a time
+double model_t::compute_lh_partition(size_t pi, const traversal_t &trav) {
+  update_pmatrix_partition(pi, trav.pmatrix_indices, trav.branch_lengths);
+  rdk_update_clvs(_partitions[pi], trav.ops.data(), (unsigned)trav.ops.size());
+  const double lh = root_loglikelihood(pi);
+  refuse_nan(lh);
+  return lh;
+}
+
+// src/model.cpp:823-854: CLVs re-oriented along the path from the current root to the new one
+void model_t::move_root(const root_location_t &new_root) {
   std::vector<rdk_operation_t> ops;
   std::vector<unsigned int>    pmatrix_indices;
   std::vector<double>          branch_lengths;
-  bool new_root = root_location != _tree.root_location();
-  GENERATE_AND_UNPACK_OPS(_tree, root_location, ops, pmatrix_indices, branch_lengths);
-  auto   updated = update_pmatrices(pmatrix_indices, branch_lengths);
-  // The reference sums the partitions with an OpenMP reduction (src/model.cpp:397), whose
-  // association order depends on the thread count; here the per-partition terms are added
-  // in partition order so that the result is reproducible on any host.
-  std::vector<double> part_lh(_partitions.size(), 0.0);
-  for_each_partition(_partitions.size(), false, [&](size_t i) {
-    if (new_root || updated[i]) rdk_update_clvs(_partitions[i], ops.data(), (unsigned)ops.size());
-    part_lh[i] = rdk_compute_root_loglikelihood(_partitions[i], _tree.root_clv_index(),
-                                                _tree.root_scaler_index(), _param_indicies[i].data(), nullptr);
+  std::tie(ops, pmatrix_indices, branch_lengths) = _tree.generate_root_update_operations(new_root);
+  for (size_t p = 0; p < _partitions.size(); ++p) {
+    if (rdk_update_prob_matrices(_partitions[p], _param_indicies[p].data(), pmatrix_indices.data(),
+                                 branch_lengths.data(), (unsigned)pmatrix_indices.size()) == RDK_FAILURE)
+      throw std::runtime_error(engine_error());
+    rdk_update_clvs(_partitions[p], ops.data(), (unsigned)ops.size());
+  }
+}
+
+// src/model.cpp:1737-1746
+std::vector<double> model_t::compute_all_root_lh() {
+  const auto &roots = _tree.roots();
+  compute_lh(roots[0]);
+  std::vector<double> lh;
+  lh.reserve(roots.size());
+  for (const auto &rl : roots) {
+    move_root(rl);
+    lh.push_back(compute_lh(rl));
+  }
+  return lh;
+}
+
+// ---------------------------------------------------------------------------
+// position on the branch: slopes, the bracketing search, optimize_alpha
+// ---------------------------------------------------------------------------
+// Log-likelihood of the tree rooted on root's branch at each of `ratios`, the CLVs below the root
+// being valid.  Batched: one rdk_root_loglikelihood_multi per partition for ALL ratios (the engine
+// stages the 2 P-matrices of every candidate, evaluates them in one program and leaves the
+// partition untouched).  Sequential: the reference's call sequence, one compute_lh_root each.
+// Either way the host tree ends up rooted at the last ratio, as after the reference's calls, and
+// NaN is reported by the CONSUMER of a value (settle / optimize_alpha), in consumption order --
+// a batch may hold evaluations the decision never looks at.
+std::vector<double> model_t::root_lh_on_branch(const root_location_t &root, const std::vector<double> &ratios) {
+  std::vector<double> lh(ratios.size(), 0.0);
+  if (ratios.empty()) return lh;
+  root_location_t at{root};
+
+  bool            fused = _batched_probes;
+  rdk_operation_t root_op;
+  std::vector<double> lengths;  // (child 1, child 2) per ratio
+  if (fused) {
+    lengths.reserve(2 * ratios.size());
+    for (size_t i = 0; i < ratios.size(); ++i) {
+      at.brlen_ratio = ratios[i];
+      rdk_operation_t           op;
+      std::vector<unsigned int> mi;
+      std::vector<double>       bl;
+      std::tie(op, mi, bl) = _tree.generate_derivative_operations(at);
+      // one root operation serves the whole batch: the same branch must give the same operation
+      if (i == 0)
+        root_op = op;
+      else if (std::memcmp(&op, &root_op, sizeof(op)) != 0)
+        fused = false;
+      lengths.insert(lengths.end(), bl.begin(), bl.end());
+    }
+  }
+  if (!fused) {
+    for (size_t i = 0; i < ratios.size(); ++i) {
+      at.brlen_ratio = ratios[i];
+      rdk_operation_t           op;
+      std::vector<unsigned int> mi;
+      std::vector<double>       bl;
+      std::tie(op, mi, bl) = _tree.generate_derivative_operations(at);
+      std::vector<double> terms(_partitions.size(), 0.0);
+      for_each_partition(_partitions.size(), false, [&](size_t p) {
+        update_pmatrix_partition(p, mi, bl);
+        rdk_update_clvs(_partitions[p], &op, 1);
+        terms[p] = root_loglikelihood(p);
+      });
+      _last_part_lh = terms;
+      lh[i] = sum_in_order(terms);
+    }
+    return lh;
+  }
+
+  std::vector<std::vector<double>> terms(_partitions.size(), std::vector<double>(ratios.size(), 0.0));
+  for_each_partition(_partitions.size(), false, [&](size_t p) {
+    if (rdk_root_loglikelihood_multi(_partitions[p], &root_op, _param_indicies[p].data(), _param_indicies[p].data(),
+                                     lengths.data(), (unsigned)ratios.size(), terms[p].data()) == RDK_FAILURE)
+      throw std::runtime_error(engine_error());
   });
-  double lh = 0.0;
-  for (double v : part_lh) lh += v;
-  _last_part_lh = part_lh;
+  for (size_t i = 0; i < ratios.size(); ++i) {
+    double total = 0.0;  // partition order, as compute_lh_root adds them
+    for (size_t p = 0; p < _partitions.size(); ++p) total += terms[p][i];
+    lh[i] = total;
+  }
+  _last_part_lh.resize(_partitions.size());
+  for (size_t p = 0; p < _partitions.size(); ++p) _last_part_lh[p] = terms[p].back();
   return lh;
 }
 
-// src/model.cpp:415-452
-double model_t::compute_lh_root(const root_location_t &root) {
-  auto                      result = _tree.generate_derivative_operations(root);
-  rdk_operation_t           op = std::get<0>(result);
-  std::vector<unsigned int> matrix_indices = std::move(std::get<1>(result));
-  std::vector<double>       branch_lengths = std::move(std::get<2>(result));
-  std::vector<double>       part_lh(_partitions.size(), 0.0);  // summed in partition order (see compute_lh)
-  for_each_partition(_partitions.size(), false, [&](size_t i) {
-    int rc = rdk_update_prob_matrices(_partitions[i], _param_indicies[i].data(), matrix_indices.data(),
-                                      branch_lengths.data(), (unsigned)matrix_indices.size());
-    if (rc == RDK_FAILURE) throw std::runtime_error(engine_error());  // the message of THIS thread
-    rdk_update_clvs(_partitions[i], &op, 1);
-    part_lh[i] = rdk_compute_root_loglikelihood(_partitions[i], _tree.root_clv_index(),
-                                                _tree.root_scaler_index(), _param_indicies[i].data(), nullptr);
-  });
-  double lh = 0.0;
-  for (double v : part_lh) lh += v;
-  _last_part_lh = part_lh;
-  if (std::isnan(lh)) throw std::runtime_error("lh at root is not a number: " + std::to_string(lh));
-  return lh;
+// A slope is a forward difference of step 1e-8 in the ratio, taken backwards where the step
+// would leave the branch (src/model.cpp:481-519, Appendix B-15).
+model_t::branch_probe_t model_t::probe_branch(const root_location_t &root, const std::vector<double> &values_at,
+                                              const std::vector<double> &slopes_at) {
+  constexpr double step = 1e-8;
+  branch_probe_t   out;
+  std::vector<double> ratios(values_at);
+  out.slopes.reserve(slopes_at.size());
+  for (double x : slopes_at) {
+    slope_probe_t s{x, 0.0, 0.0, 1.0};
+    double        shifted = x + step;
+    if (shifted >= 1.0) {
+      shifted = x - step;
+      s.sign = -1.0;
+    }
+    ratios.push_back(x);
+    ratios.push_back(shifted);
+    out.slopes.push_back(s);
+  }
+  const auto lh = root_lh_on_branch(root, ratios);
+  out.values.assign(lh.begin(), lh.begin() + (std::ptrdiff_t)values_at.size());
+  for (size_t i = 0; i < out.slopes.size(); ++i) {
+    out.slopes[i].fx = lh[values_at.size() + 2 * i];
+    out.slopes[i].fxh = lh[values_at.size() + 2 * i + 1];
+  }
+  return out;
 }
 
-// src/model.cpp:454-476
-double model_t::compute_lh_partition(size_t pi, const std::vector<rdk_operation_t> &ops,
-                                     const std::vector<unsigned int> &pmatrix_indices,
-                                     const std::vector<double>       &branch_lengths) {
-  update_pmatrix_partition(pi, pmatrix_indices, branch_lengths);
-  rdk_update_clvs(_partitions[pi], ops.data(), (unsigned)ops.size());
-  double lh = rdk_compute_root_loglikelihood(_partitions[pi], _tree.root_clv_index(),
-                                             _tree.root_scaler_index(), _param_indicies[pi].data(),
-                                             nullptr);
-  if (std::isnan(lh)) throw std::runtime_error("lh at root is not a number: " + std::to_string(lh));
-  return lh;
+// what the reference's compute_dlh makes of the two evaluations: NaN is an error, a branch that
+// is impossible at both points (-inf, -inf) is flat
+rd::slope_sample_t model_t::settle(const slope_probe_t &raw) {
+  constexpr double step = 1e-8;
+  refuse_nan(raw.fx);
+  refuse_nan(raw.fxh);
+  if (std::isinf(raw.fxh) && std::isinf(raw.fx)) return {raw.x, raw.fx, 0.0};
+  const double slope = (raw.fxh - raw.fx) / step;
+  return {raw.x, raw.fx, slope * raw.sign};
 }
 
-// src/model.cpp:481-519: forward difference with h = 1e-8 in the branch ratio,
-// taken backwards at the upper end (Appendix B-15)
 dlh_t model_t::compute_dlh(const root_location_t &root) {
-  constexpr double EPSILON = 1e-8;
-  root_location_t  root_prime{root};
-  root_prime.brlen_ratio += EPSILON;
-  double sign = 1.0;
-  if (root_prime.brlen_ratio >= 1.0) {
-    root_prime.brlen_ratio = root.brlen_ratio - EPSILON;
-    sign = -1.0;
-  }
-  dlh_t  ret;
-  double fx = compute_lh_root(root);
-  ret.lh = fx;
-  if (std::isnan(fx))
-    throw std::runtime_error("fx is not finite when computing derivative: " +
-                             std::to_string(root.edge->length));
-  double fxh = compute_lh_root(root_prime);
-  if (std::isnan(fxh))
-    throw std::runtime_error("fxh is not finite when computing derivative: " +
-                             std::to_string(root_prime.edge->length));
-  if (std::isinf(fxh) && std::isinf(fx)) return {fx, 0};
-  double dlh = (fxh - fx) / EPSILON;
-  ret.dlh = dlh * sign;
-  return ret;
+  const auto s = settle(probe_branch(root, {}, {root.brlen_ratio}).slopes[0]);
+  return {s.value, s.slope};
 }
 
-// src/model.cpp:606-676
-std::pair<root_location_t, double> model_t::brents(root_location_t beg, dlh_t d_beg, root_location_t end,
-                                                   dlh_t d_end, double atol) {
-  if (!(d_beg.dlh * d_end.dlh < 0))
-    throw std::runtime_error("Brents called with endpoints which don't bracket");
-  root_location_t midpoint{end};
-  auto            d_midpoint = d_end;
-  double          e, d;
-  d = e = end.brlen_ratio - beg.brlen_ratio;
-
-  for (size_t i = 0; i < 64; ++i) {
-    if (d_end.dlh * d_midpoint.dlh > 0.0) {
-      midpoint = beg;
-      d_midpoint = d_beg;
-      d = e = end.brlen_ratio - beg.brlen_ratio;
-    }
-    if (fabs(d_end.dlh) < fabs(d_midpoint.dlh)) {
-      beg = end;
-      end = midpoint;
-      midpoint = beg;
-      d_beg = d_end;
-      d_end = d_midpoint;
-      d_midpoint = d_beg;
-    }
-    double tol = 2.0 * fabs(end.brlen_ratio) * std::numeric_limits<double>::epsilon() + 0.5 * atol;
-    double e_tol = 0.5 * (midpoint.brlen_ratio - end.brlen_ratio);
-    if (fabs(e_tol) <= tol || fabs(d_end.dlh) <= 1e-12) return {end, d_end.lh};
-    if (fabs(e) >= tol && fabs(d_beg.dlh) > fabs(d_end.dlh)) {
-      double s = d_end.dlh / d_beg.dlh;
-      double p, q;
-      if (fabs(beg.brlen_ratio - midpoint.brlen_ratio) < 1e-12) {
-        p = 2.0 * e_tol * s;
-        q = 1.0 - s;
-      } else {
-        q = d_beg.dlh / d_midpoint.dlh;
-        double r = d_end.dlh / d_midpoint.dlh;
-        p = s * (2.0 * e_tol * q * (q - r) - (end.brlen_ratio - beg.brlen_ratio) * (r - 1.0));
-        q = (q - 1.0) * (r - 1.0) * (s - 1.0);
-      }
-      if (p > 0.0) q = -q;
-      p = fabs(p);
-      double min1 = 3.0 * e_tol * q - fabs(e_tol * q);
-      double min2 = fabs(e * q);
-      if (2.0 * p < (min1 < min2 ? min1 : min2)) {
-        e = d;
-        d = p / q;
-      } else {
-        d = e_tol;
-        e = d;
-      }
-    } else {
-      d = e_tol;
-      e = d;
-    }
-    beg = end;
-    d_beg = d_end;
-    if (fabs(d) > tol)
-      end.brlen_ratio += d;
-    else
-      end.brlen_ratio += e_tol >= 0.0 ? tol : -tol;
-    d_end = compute_dlh(end);
-  }
-  throw std::runtime_error("Brents method failed to converge");
+// the root of the slope between two samples of opposite slope (reference brents, :606-676)
+rd::slope_sample_t model_t::refine_between(const root_location_t &root, const rd::slope_sample_t &lo,
+                                           const rd::slope_sample_t &hi, double atol) {
+  rd::brent_options_t opt;
+  opt.x_tolerance = atol;
+  return rd::slope_root_brent(lo, hi, opt,
+                              [&](double x) { return settle(probe_branch(root, {}, {x}).slopes[0]); });
 }
 
-// src/model.cpp:679-794
+// src/model.cpp:679-794.  Best position of the root on its branch by the sign of the slope:
+//   1. the log-likelihood where the root stands and value + slope at both ends   (one batch of 5)
+//   2. an end with a flat slope wins outright; ends of opposite slope bracket a root -> Brent
+//   3. same sign at both ends: look for a sign change on the dyadic grid 1/2; 1/4, 3/4; 1/8 ...
+//      31/32, level by level (one batch per level; the scan within a level keeps the
+//      reference's order, so a level's later points are evaluated speculatively), refine on both
+//      sides of the first change; otherwise the best flat grid point, else the end the slope
+//      points to.
 root_location_t model_t::optimize_alpha(const root_location_t &root, double atol) {
-  double lh = compute_lh_root(root);
-  if (std::isnan(lh)) throw std::runtime_error("initial likelihood calculation is not finite");
-  root_location_t beg{root};
-  beg.brlen_ratio = 0.0;
-  root_location_t end{root};
-  end.brlen_ratio = 1.0;
-  auto d_beg = compute_dlh(beg);
-  auto d_end = compute_dlh(end);
-  if (std::isnan(d_beg.dlh) || std::isnan(d_end.dlh))
+  auto placed = [&root](double x) {
+    root_location_t rl{root};
+    rl.brlen_ratio = x;
+    return rl;
+  };
+  rd::slope_sample_t lo, hi;
+  if (_batched_probes) {
+    const auto first = probe_branch(root, {root.brlen_ratio}, {0.0, 1.0});
+    refuse_nan(first.values[0]);
+    lo = settle(first.slopes[0]);
+    hi = settle(first.slopes[1]);
+  } else {
+    refuse_nan(root_lh_on_branch(root, {root.brlen_ratio})[0]);
+    lo = settle(probe_branch(root, {}, {0.0}).slopes[0]);
+    hi = settle(probe_branch(root, {}, {1.0}).slopes[0]);
+  }
+  if (std::isnan(lo.slope) || std::isnan(hi.slope))
     throw std::runtime_error("Initial derivatives failed when optimizing alpha: " +
                              std::to_string(root.edge->length));
 
-  root_location_t best_endpoint = d_beg.lh >= d_end.lh ? beg : end;
-  auto            lh_best_endpoint = d_beg.lh >= d_end.lh ? d_beg : d_end;
+  rd::slope_sample_t best_end = lo.value >= hi.value ? lo : hi;
+  if (std::fabs(lo.slope) < atol || std::fabs(hi.slope) < atol) return placed(best_end.x);
 
-  if (fabs(d_beg.dlh) < atol || fabs(d_end.dlh) < atol) return best_endpoint;
-
-  if ((d_beg.dlh < 0.0 && d_end.dlh > 0.0) || (d_beg.dlh > 0.0 && d_end.dlh < 0.0)) {
-    auto mid = brents(beg, d_beg, end, d_end, atol);
-    return lh_best_endpoint.lh > mid.second ? best_endpoint : mid.first;
+  if ((lo.slope < 0.0 && hi.slope > 0.0) || (lo.slope > 0.0 && hi.slope < 0.0)) {
+    const auto inner = refine_between(root, lo, hi, atol);
+    return placed(best_end.value > inner.value ? best_end.x : inner.x);
   }
 
-  // same sign at both ends: dyadic grid search for a sign change
-  bool            beg_end_pos = d_beg.dlh > 0.0 && d_end.dlh > 0.0;
-  dlh_t           best_midpoint_lh = {-std::numeric_limits<double>::infinity(), 0};
-  root_location_t best_midpoint;
-  bool            found_midpoint = false;
-
-  for (size_t midpoints = 2; midpoints <= 32; midpoints *= 2) {
-    for (size_t midpoint = 1; midpoint <= midpoints; ++midpoint) {
-      if (midpoint % 2 == 0) continue;
-      double          alpha = 1.0 / (double)midpoints * midpoint;
-      root_location_t midpoint_root{beg};
-      midpoint_root.brlen_ratio = alpha;
-      auto d_midpoint = compute_dlh(midpoint_root);
-      if (fabs(d_midpoint.dlh) < atol) {
-        if (best_midpoint_lh.lh < d_midpoint.lh) {
-          best_midpoint_lh = d_midpoint;
-          best_midpoint = midpoint_root;
-          found_midpoint = true;
-        }
+  const bool         rising = lo.slope > 0.0 && hi.slope > 0.0;
+  rd::slope_sample_t best_flat{0.0, -std::numeric_limits<double>::infinity(), 0.0};
+  bool               have_flat = false;
+  for (size_t cells = 2; cells <= 32; cells *= 2) {
+    std::vector<double> grid;
+    for (size_t k = 1; k <= cells; k += 2) grid.push_back(1.0 / (double)cells * k);
+    std::vector<slope_probe_t> level;
+    if (_batched_probes) level = probe_branch(root, {}, grid).slopes;
+    for (size_t j = 0; j < grid.size(); ++j) {
+      const auto here = settle(_batched_probes ? level[j] : probe_branch(root, {}, {grid[j]}).slopes[0]);
+      if (std::fabs(here.slope) < atol && best_flat.value < here.value) {
+        best_flat = here;
+        have_flat = true;
       }
-      if ((beg_end_pos && d_midpoint.dlh < 0.0) || (!beg_end_pos && d_midpoint.dlh > 0.0)) {
-        auto r1 = brents(beg, d_beg, midpoint_root, d_midpoint, atol);
-        auto r2 = brents(midpoint_root, d_midpoint, end, d_end, atol);
-        if (lh_best_endpoint.lh < best_midpoint_lh.lh) {
-          lh_best_endpoint = best_midpoint_lh;
-          best_endpoint = best_midpoint;
-        }
-        if (r1.second < r2.second) return lh_best_endpoint.lh >= r2.second ? best_endpoint : r2.first;
-        return lh_best_endpoint.lh >= r1.second ? best_endpoint : r1.first;
-      }
+      const bool turns = rising ? here.slope < 0.0 : here.slope > 0.0;
+      if (!turns) continue;
+      const auto left = refine_between(root, lo, here, atol);
+      const auto right = refine_between(root, here, hi, atol);
+      if (best_end.value < best_flat.value) best_end = best_flat;
+      const auto &inner = left.value < right.value ? right : left;
+      return placed(best_end.value >= inner.value ? best_end.x : inner.x);
     }
   }
-  if (found_midpoint) return best_midpoint;
-  return beg_end_pos ? end : beg;
+  if (have_flat) return placed(best_flat.x);
+  return placed(rising ? 1.0 : 0.0);
 }
 
-// src/model.cpp:796-821 (Appendix B-6: atol of the ratio search is hard-coded)
+// src/model.cpp:796-821: the most likely placements of the sweep, each polished on its branch
+// (Appendix B-6: the tolerance of that search is fixed at 1e-14 here)
 std::pair<root_location_t, double> model_t::optimize_root_location(size_t min_roots, double root_ratio) {
-  std::pair<root_location_t, double> best;
-  best.second = -std::numeric_limits<double>::infinity();
-  auto sorted_roots = suggest_roots_lh(min_roots, root_ratio);
-  for (auto &rl : sorted_roots) {
-    move_root(rl);
-    rl = optimize_alpha(rl, 1e-14);
-    double rl_lh = compute_lh_root(rl);
-    if (rl_lh > best.second) {
-      best.first = rl;
-      best.second = rl_lh;
-    }
+  std::pair<root_location_t, double> best{root_location_t{}, -std::numeric_limits<double>::infinity()};
+  for (auto &candidate : suggest_roots_lh(min_roots, root_ratio)) {
+    move_root(candidate);
+    candidate = optimize_alpha(candidate, 1e-14);
+    const double lh = compute_lh_root(candidate);
+    if (lh > best.second) best = {candidate, lh};
   }
   return best;
 }
 
-// src/model.cpp:823-854
-void model_t::move_root(const root_location_t &new_root) {
-  auto                         results = _tree.generate_root_update_operations(new_root);
-  std::vector<rdk_operation_t> ops = std::move(std::get<0>(results));
-  std::vector<unsigned int>    pmatrix_indices = std::move(std::get<1>(results));
-  std::vector<double>          branch_lengths = std::move(std::get<2>(results));
-  for (size_t i = 0; i < _partitions.size(); ++i) {
-    int rc = rdk_update_prob_matrices(_partitions[i], _param_indicies[i].data(), pmatrix_indices.data(),
-                                      branch_lengths.data(), (unsigned)pmatrix_indices.size());
-    if (rc == RDK_FAILURE) throw std::runtime_error(engine_error());
-    rdk_update_clvs(_partitions[i], ops.data(), (unsigned)ops.size());
-  }
+// ---------------------------------------------------------------------------
+// candidate placements
+// ---------------------------------------------------------------------------
+static inline size_t shortlist_size(size_t candidates, double ratio, size_t at_least) {
+  return std::max(static_cast<size_t>(candidates * ratio), at_least);
 }
 
 std::vector<root_location_t> model_t::suggest_roots_random(size_t min, double ratio) {
   auto roots = _tree.roots();
   std::shuffle(roots.begin(), roots.end(), _random_engine);
-  roots.resize(compute_final_size(roots.size(), ratio, min));
+  roots.resize(shortlist_size(roots.size(), ratio, min));
   return roots;
 }
 
@@ -666,236 +720,224 @@ std::vector<double> model_t::sweep_root_lh(size_t begin, size_t end) {
   return lh;
 }
 
-// src/model.cpp:865-889
+// src/model.cpp:865-889: the sweep's log-likelihoods rank the placements; the best
+// max(ratio * N, min) come back, most likely first
 std::vector<root_location_t> model_t::suggest_roots_lh(size_t min, double ratio) {
-  std::vector<std::pair<root_location_t, double>> rl_lhs;
-  auto                                            lh = sweep_root_lh();
-  const auto                                     &roots = _tree.roots();
-  rl_lhs.reserve(roots.size());
-  for (size_t r = 0; r < roots.size(); ++r) rl_lhs.push_back(std::make_pair(roots[r], lh[r]));
-  auto final_size = std::min(compute_final_size(rl_lhs.size(), ratio, min), rl_lhs.size());
-  std::partial_sort(rl_lhs.begin(), rl_lhs.begin() + (std::ptrdiff_t)final_size, rl_lhs.end(),
-                    [](const std::pair<root_location_t, double> &a,
-                       const std::pair<root_location_t, double> &b) { return a.second > b.second; });
-  rl_lhs.resize(final_size);
-  std::vector<root_location_t> ret;
-  ret.reserve(final_size);
-  for (size_t i = 0; i < final_size; i++) ret.push_back(rl_lhs[i].first);
-  return ret;
+  const auto          lh = sweep_root_lh();
+  const auto         &roots = _tree.roots();
+  const size_t        keep = std::min(shortlist_size(roots.size(), ratio, min), roots.size());
+  typedef std::pair<root_location_t, double> scored_t;
+  std::vector<scored_t> scored;
+  scored.reserve(roots.size());
+  for (size_t r = 0; r < roots.size(); ++r) scored.emplace_back(roots[r], lh[r]);
+  std::partial_sort(scored.begin(), scored.begin() + (std::ptrdiff_t)keep, scored.end(),
+                    [](const scored_t &a, const scored_t &b) { return a.second > b.second; });
+  std::vector<root_location_t> out;
+  out.reserve(keep);
+  for (size_t i = 0; i < keep; ++i) out.push_back(scored[i].first);
+  return out;
 }
 
 std::vector<root_location_t> model_t::suggest_roots_midpoint(size_t min, double ratio) {
-  auto midpoints = _tree.rank_midpoints();
-  midpoints.resize(std::min(compute_final_size(midpoints.size(), ratio, min), midpoints.size()));
-  return midpoints;
+  auto ranked = _tree.rank_midpoints();
+  ranked.resize(std::min(shortlist_size(ranked.size(), ratio, min), ranked.size()));
+  return ranked;
 }
 
 std::vector<root_location_t> model_t::suggest_roots_modified_mad(size_t min, double ratio) {
-  auto madpoints = _tree.rank_modified_mad();
-  madpoints.resize(std::min(compute_final_size(madpoints.size(), ratio, min), madpoints.size()));
-  return madpoints;
+  auto ranked = _tree.rank_modified_mad();
+  ranked.resize(std::min(shortlist_size(ranked.size(), ratio, min), ranked.size()));
+  return ranked;
+}
+
+static std::vector<size_t> ids_of(const std::vector<root_location_t> &placements) {
+  std::vector<size_t> ids;
+  ids.reserve(placements.size());
+  for (const auto &rl : placements) ids.push_back(rl.id);
+  return ids;
 }
 
 std::vector<size_t> model_t::shuffle_root_indicies() {
-  std::vector<size_t> idx(_tree.root_count());
-  std::iota(idx.begin(), idx.end(), 0);
-  std::shuffle(idx.begin(), idx.end(), _random_engine);
-  return idx;
+  std::vector<size_t> ids(_tree.root_count());
+  std::iota(ids.begin(), ids.end(), 0);
+  std::shuffle(ids.begin(), ids.end(), _random_engine);
+  return ids;
 }
 
-std::vector<size_t> model_t::suggest_root_indicies_midpoint() {
-  std::vector<size_t> ret;
-  for (auto &rl : suggest_roots_midpoint(1, 1.0)) ret.push_back(rl.id);
-  return ret;
-}
+std::vector<size_t> model_t::suggest_root_indicies_midpoint() { return ids_of(suggest_roots_midpoint(1, 1.0)); }
 
 std::vector<size_t> model_t::suggest_root_indicies_modified_mad() {
-  std::vector<size_t> ret;
-  for (auto &rl : suggest_roots_modified_mad(1, 1.0)) ret.push_back(rl.id);
-  return ret;
+  return ids_of(suggest_roots_modified_mad(1, 1.0));
 }
 
-// src/model.cpp:979-1005
-partition_parameters_t model_t::make_partition_parameters(size_t states, rate_category rc,
-                                                          size_t rate_cat_count) {
-  partition_parameters_t pp;
-  size_t                 subst_size = states * states - states;
-  pp.subst_rates.assign(subst_size, 1.0 / subst_size);
-  pp.freqs.assign(states, 1.0 / states);
-  switch (rc) {
-  case rate_category::MEAN:
-  case rate_category::MEDIAN:
-    pp.gamma_alpha.assign(1, 1.0);
-    break;
-  case rate_category::FREE: {
-    pp.gamma_alpha.assign(rate_cat_count, 1.0);
-    pp.gamma_weights.resize(rate_cat_count);
-    std::uniform_real_distribution<> dis(0.0, 1.0);
-    for (auto &v : pp.gamma_weights) v = dis(_random_engine);
-  }
-  }
-  return pp;
+// ---------------------------------------------------------------------------
+// model parameters: L-BFGS-B in a box, one parameter block at a time
+// ---------------------------------------------------------------------------
+// src/model.cpp:1925-1984 with the four wrappers :1524-1735.  Per partition (the partitions are
+// independent and run on their own threads): install the current values, then fit the 12 rates
+// in [1e-4, 1e4], the 4 frequencies in [1e-4, 1 - 3e-4] (all free, renormalised on installation),
+// and -- unless the user fixed it -- the Gamma shape in [0.2, 1e4] and, for free categories, the
+// weights in [1e-4, 1].  Every objective evaluation is one full traversal of that partition: 13
+// per gradient of the rates, which is what the lazily materialised evaluations of the engine are
+// for.
+void model_t::optimize_params(std::vector<partition_parameters_t> &params, const root_location_t &rl,
+                              double pgtol, double factor, bool optimize_gamma) {
+  const traversal_t trav = full_traversal(rl);
+  auto              box = [&](double lower, double upper) {
+    rd::box_minimizer_options_t o;
+    o.lower = lower;
+    o.upper = upper;
+    o.pgtol = pgtol;
+    o.factr = factor;
+    return o;
+  };
+  for_each_partition(_partitions.size(), true, [&](size_t p) {
+    auto &mine = params[p];
+    auto  fit = [&](model_params_t &block, const rd::box_minimizer_options_t &o, auto install) {
+      rd::minimize_in_box(block, o, [&](const std::vector<double> &x) {
+        install(x);
+        return -compute_lh_partition(p, trav);
+      });
+    };
+    const bool free_categories = _rate_category_types[p] == rate_category::FREE;
+    set_subst_rates(p, mine.subst_rates);
+    set_freqs_all_free(p, mine.freqs);
+    set_gamma_rates(p, mine.gamma_alpha);
+    if (free_categories) set_gamma_weights(p, mine.gamma_weights);
+
+    fit(mine.subst_rates, box(1e-4, 1e4), [&](const model_params_t &x) { set_subst_rates(p, x); });
+    fit(mine.freqs, box(1e-4, 1.0 - 1e-4 * 3), [&](const model_params_t &x) { set_freqs_all_free(p, x); });
+    if (!optimize_gamma || _rate_user_init[p]) return;
+    fit(mine.gamma_alpha, box(0.2, 10000.0), [&](const model_params_t &x) { set_gamma_rates(p, x); });
+    if (free_categories)
+      fit(mine.gamma_weights, box(1e-4, 1.0), [&](const model_params_t &x) { set_gamma_weights(p, x); });
+  });
 }
 
 // ---------------------------------------------------------------------------
 // search drivers
 // ---------------------------------------------------------------------------
-// src/model.cpp:1008-1137
+namespace {
+struct placement_t {  // a root placement and its log-likelihood
+  root_location_t where;
+  double          lh = -std::numeric_limits<double>::infinity();
+};
+}  // namespace
+
+// what rank 0 does once every rank is through (src/model.cpp:1119-1133, 1259-1269): the most
+// likely record of the whole checkpoint, the first one on ties; all.size() when there is none
+static size_t most_likely(const std::vector<checkpoint_t::record_t> &all) {
+  size_t top = 0;
+  for (size_t i = 1; i < all.size(); ++i)
+    if (all[top].first.llh < all[i].first.llh) top = i;
+  return top;
+}
+
+std::pair<root_location_t, double> model_t::placement_of(const rd_result_t &result) const {
+  root_location_t where = _tree.root_location(result.root_id);
+  where.brlen_ratio = result.alpha;
+  return {where, result.llh};
+}
+
+// src/model.cpp:1008-1137.  Per assigned start: alternate "fit the parameters for this root" and
+// "move the root to the best polished placement of a sweep" until the root stops moving (early
+// stop), the likelihood stops changing, or it gets worse -- in which case the parameters of the
+// previous round are put back.  One checkpoint record per start; the answer is the best record.
 std::pair<root_location_t, double> model_t::search(size_t min_roots, double root_ratio, double atol,
                                                    double pgtol, double brtol, double factor,
                                                    checkpoint_t &checkpoint) {
-  double          best_llh = -std::numeric_limits<double>::infinity();
-  root_location_t best_rl;
-  set_subst_rates_uniform();
-  set_empirical_freqs();
+  reset_to_defaults();
+  for (size_t start : _assigned_idx) {
+    root_location_t at = _tree.root_location(start);
+    reset_to_defaults();
+    auto        params = fresh_parameters();
+    placement_t kept{at};
 
-  for (auto rl_index : _assigned_idx) {
-    auto rl = _tree.root_location(rl_index);
-    set_subst_rates_uniform();  // Appendix B-9
-    set_empirical_freqs();
-
-    std::vector<partition_parameters_t> params, saved_params;
-    for (size_t p = 0; p < _partitions.size(); ++p)
-      params.push_back(make_partition_parameters(_partitions[p]->states, _rate_category_types[p],
-                                                 _partitions[p]->rate_cats));
-    auto   cur_best_rl = rl;
-    double cur_best_lh = -std::numeric_limits<double>::infinity();
-
-    for (size_t iter = 0; iter < _max_outer_iterations; ++iter) {
-      saved_params = params;
-      optimize_params(params, rl, pgtol, factor, true);
-      auto cur = optimize_root_location(min_roots, root_ratio);
-
-      if (cur.second < cur_best_lh) {
-        // no progress: restore the parameters of the previous iteration
-        for (size_t i = 0; i < _partitions.size(); ++i) {
-          set_subst_rates(i, saved_params[i].subst_rates);
-          set_freqs(i, saved_params[i].freqs);
-          set_gamma_rates(i, saved_params[i].gamma_alpha);
-          if (_rate_category_types[i] == rate_category::FREE)
-            set_gamma_weights(i, saved_params[i].gamma_weights);
-        }
-        params = saved_params;
+    for (size_t round = 0; round < _max_outer_iterations; ++round) {
+      const auto before = params;
+      optimize_params(params, at, pgtol, factor, true);
+      const auto found = optimize_root_location(min_roots, root_ratio);
+      if (found.second < kept.lh) {
+        set_model_params(before);
+        params = before;
         break;
       }
-      if (_early_stop) {
-        if (rl.edge == cur.first.edge && fabs(rl.brlen_ratio - cur.first.brlen_ratio) < brtol) {
-          cur_best_rl = cur.first;
-          cur_best_lh = cur.second;
-          break;
-        }
-      }
-      if (fabs(cur.second - cur_best_lh) < atol) {
-        cur_best_rl = cur.first;
-        cur_best_lh = cur.second;
-        break;
-      }
-      cur_best_rl = cur.first;
-      cur_best_lh = cur.second;
-      rl = cur_best_rl;
+      const bool stayed = _early_stop && at.edge == found.first.edge &&
+                          std::fabs(at.brlen_ratio - found.first.brlen_ratio) < brtol;
+      const bool converged = std::fabs(found.second - kept.lh) < atol;
+      kept = {found.first, found.second};
+      if (stayed || converged) break;
+      at = kept.where;
     }
-    checkpoint.write({cur_best_rl.id, cur_best_lh, cur_best_rl.brlen_ratio}, params);
+    checkpoint.write({kept.where.id, kept.lh, kept.where.brlen_ratio}, params);
   }
 
-  // what rank 0 does after the barrier (src/model.cpp:1119-1133)
-  auto total = checkpoint.read_results();
-  if (!total.empty()) {
-    auto best = *std::max_element(total.begin(), total.end(),
-                                  [](const checkpoint_t::record_t &a, const checkpoint_t::record_t &b) {
-                                    return a.first.llh < b.first.llh;
-                                  });
-    best_rl = _tree.root_location(best.first.root_id);
-    best_rl.brlen_ratio = best.first.alpha;
-    best_llh = best.first.llh;
-    set_model_params(best.second);
+  std::pair<root_location_t, double> best{root_location_t{}, -std::numeric_limits<double>::infinity()};
+  const auto                         all = checkpoint.read_results();
+  if (!all.empty()) {
+    const auto &top = all[most_likely(all)];
+    best = placement_of(top.first);
+    set_model_params(top.second);
   }
-  if (!_assigned_idx.empty()) move_root(best_rl);
-  return {best_rl, best_llh};
+  if (!_assigned_idx.empty()) move_root(best.first);
+  return best;
 }
 
-// src/model.cpp:1139-1272
+// src/model.cpp:1139-1272.  Every assigned branch is optimised to convergence with the root held
+// on it: fit the parameters (the Gamma shape only every 10th round, Appendix B-7), stop when a
+// full evaluation no longer moves, else polish the position on the branch.  Then every record of
+// the checkpoint is written onto the tree (LWR = softmax of the log-likelihoods, llh, ratio).
 std::pair<root_location_t, double> model_t::exhaustive_search(double atol, double pgtol, double brtol,
                                                               double factor, checkpoint_t &checkpoint) {
-  root_location_t best_rl;
-  double          best_llh = -std::numeric_limits<double>::infinity();
+  for (size_t branch : _assigned_idx) {
+    root_location_t at = _tree.root_location(branch);
+    reset_to_defaults();
+    _tree.root_by(at);
+    compute_lh(at);
+    auto        params = fresh_parameters();
+    placement_t kept{at};
 
-  for (auto rl_index : _assigned_idx) {
-    auto rl = _tree.root_location(rl_index);
-    set_subst_rates_uniform();
-    set_empirical_freqs();
-    _tree.root_by(rl);
-    compute_lh(rl);
-    std::vector<partition_parameters_t> params;
-    for (size_t p = 0; p < _partitions.size(); ++p)
-      params.push_back(make_partition_parameters(_partitions[p]->states, _rate_category_types[p],
-                                                 _partitions[p]->rate_cats));
-    root_location_t cur_best_rl = rl;
-    double          cur_best_llh = -std::numeric_limits<double>::infinity();
-
-    for (size_t iter = 0; iter < _max_outer_iterations; ++iter) {
-      optimize_params(params, rl, pgtol, factor, (iter % 10 == 0));  // Appendix B-7
-      if (fabs(compute_lh(rl) - cur_best_llh) < atol) break;
-      auto   cur_rl = optimize_alpha(rl, brtol);
-      double cur_llh = compute_lh_root(cur_rl);
-      if (_early_stop) {
-        if (fabs(rl.brlen_ratio - cur_rl.brlen_ratio) < brtol) {
-          cur_best_rl = cur_rl;
-          cur_best_llh = cur_llh;
-          break;
-        }
-      }
-      if ((cur_llh - cur_best_llh) < atol) {
-        if (cur_llh > cur_best_llh) {
-          cur_best_rl = cur_rl;
-          cur_best_llh = cur_llh;
-        }
-        break;
-      }
-      if (cur_llh > cur_best_llh) {
-        cur_best_rl = cur_rl;
-        cur_best_llh = cur_llh;
-      }
-      rl = cur_rl;
+    for (size_t round = 0; round < _max_outer_iterations; ++round) {
+      optimize_params(params, at, pgtol, factor, round % 10 == 0);
+      if (std::fabs(compute_lh(at) - kept.lh) < atol) break;
+      const root_location_t polished = optimize_alpha(at, brtol);
+      const double          lh = compute_lh_root(polished);
+      const bool            stayed = _early_stop && std::fabs(at.brlen_ratio - polished.brlen_ratio) < brtol;
+      const bool            small_gain = (lh - kept.lh) < atol;
+      if (stayed || lh > kept.lh) kept = {polished, lh};
+      if (stayed || small_gain) break;
+      at = polished;
     }
-    checkpoint.write({cur_best_rl.id, cur_best_llh, cur_best_rl.brlen_ratio}, params);
-    if (cur_best_llh > best_llh) {
-      best_rl = cur_best_rl;
-      best_llh = cur_best_llh;
-    }
+    checkpoint.write({kept.where.id, kept.lh, kept.where.brlen_ratio}, params);
   }
 
-  // LWR annotation (src/model.cpp:1237-1269)
-  auto total = checkpoint.read_results();
-  if (!total.empty()) {
+  std::pair<root_location_t, double> best{root_location_t{}, -std::numeric_limits<double>::infinity()};
+  const auto                         all = checkpoint.read_results();
+  if (!all.empty()) {
+    best = placement_of(all[most_likely(all)].first);
     std::vector<double> llh;
-    for (auto &r : total) llh.push_back(r.first.llh);
-    auto w = lwr(llh);
-    for (size_t i = 0; i < total.size(); ++i) {
-      auto rl = _tree.root_location(total[i].first.root_id);
-      rl.brlen_ratio = total[i].first.alpha;
-      _tree.annotate_branch(rl, "LWR", std::to_string(w[i]));
-      _tree.annotate_lh(rl, total[i].first.llh);
-      _tree.annotate_ratio(rl, total[i].first.alpha);
+    llh.reserve(all.size());
+    for (const auto &rec : all) llh.push_back(rec.first.llh);
+    const auto weight = lwr(llh);
+    for (size_t i = 0; i < all.size(); ++i) {
+      const root_location_t rl = placement_of(all[i].first).first;
+      _tree.annotate_branch(rl, "LWR", std::to_string(weight[i]));
+      _tree.annotate_lh(rl, all[i].first.llh);
+      _tree.annotate_ratio(rl, all[i].first.alpha);
     }
-    auto best = *std::max_element(total.begin(), total.end(),
-                                  [](const checkpoint_t::record_t &a, const checkpoint_t::record_t &b) {
-                                    return a.first.llh < b.first.llh;
-                                  });
-    best_rl = _tree.root_location(best.first.root_id);
-    best_rl.brlen_ratio = best.first.alpha;
-    best_llh = best.first.llh;
   }
-  return {best_rl, best_llh};
+  return best;
 }
 
 // LWR_i = exp(llh_i - max) / sum_j exp(llh_j - max) (src/model.cpp:1238-1253)
 std::vector<double> model_t::lwr(const std::vector<double> &llh) {
-  double max_llh = -std::numeric_limits<double>::infinity();
-  for (double v : llh) max_llh = std::max(v, max_llh);
-  double total = 0;
-  for (double v : llh) total += exp(v - max_llh);
+  double top = -std::numeric_limits<double>::infinity();
+  for (double v : llh) top = std::max(v, top);
+  double mass = 0;
+  for (double v : llh) mass += exp(v - top);
   std::vector<double> out;
-  for (double v : llh) out.push_back(exp(v - max_llh) / total);
+  out.reserve(llh.size());
+  for (double v : llh) out.push_back(exp(v - top) / mass);
   return out;
 }
 
@@ -908,8 +950,7 @@ rooted_tree_t model_t::rooted_tree(const root_location_t &root) const {
   return t;
 }
 rooted_tree_t model_t::virtual_rooted_tree(const root_location_t &root) const {
-  rooted_tree_t t(_tree);
-  t.root_by((unsigned)root.id);
+  rooted_tree_t t = rooted_tree(root);
   t.unroot();
   return t;
 }
@@ -919,13 +960,13 @@ rooted_tree_t model_t::unrooted_tree() const {
   return t;
 }
 
-// src/model.cpp:1297-1321
+// src/model.cpp:1297-1321: tips, invariant sites, frequencies, random start rates (Appendix B-10)
 void model_t::initialize_partitions(const std::vector<msa_t> &msa) {
   for (size_t p = 0; p < _partitions.size(); ++p) {
     set_tip_states(p, msa[p]);
     update_invariant_sites(p);
     set_empirical_freqs(p);
-    set_subst_rates_random(p, msa[p]);  // Appendix B-10
+    set_subst_rates_random(p, msa[p]);
   }
 }
 
@@ -933,167 +974,26 @@ void model_t::initialize_partitions_uniform_freqs(const std::vector<msa_t> &msa)
   for (size_t p = 0; p < _partitions.size(); ++p) {
     set_tip_states(p, msa[p]);
     update_invariant_sites(p);
-    std::vector<double> uni(_partitions[p]->states, 1.0 / (double)_partitions[p]->states);
-    set_freqs(p, uni);
+    const unsigned int states = _partitions[p]->states;
+    set_freqs(p, model_params_t(states, 1.0 / (double)states));
     set_subst_rates_random(p, msa[p]);
     set_gamma_rates(p);
   }
 }
 
+// "{{r0,...,r11},{...}}": the rates of every partition, six decimals
 std::string model_t::subst_string() const {
-  std::ostringstream oss;
-  oss << "{";
+  std::ostringstream text;
+  text << "{";
   for (size_t p = 0; p < _partitions.size(); ++p) {
-    auto   part = _partitions[p];
-    size_t n = part->states * part->states - part->states;
-    oss << "{";
-    for (size_t i = 0; i < n; ++i) {
-      oss << std::to_string(part->subst_params[0][i]);
-      if (i != n - 1) oss << ",";
-    }
-    oss << "}";
-    if (p != _partitions.size() - 1) oss << ",";
+    const auto  *part = _partitions[p];
+    const size_t n = part->states * part->states - part->states;
+    text << (p ? ",{" : "{");
+    for (size_t i = 0; i < n; ++i) text << (i ? "," : "") << std::to_string(part->subst_params[0][i]);
+    text << "}";
   }
-  oss << "}";
-  return oss.str();
-}
-
-// ---------------------------------------------------------------------------
-// L-BFGS-B parameter optimisation (src/model.cpp:1430-1522; Appendix B-8,B-14)
-// ---------------------------------------------------------------------------
-static double bfgs_params(model_params_t &initial_params, size_t partition_index, double p_min,
-                          double p_max, double epsilon, double pgtol, double factor,
-                          std::function<double()>                             compute_lh,
-                          std::function<void(size_t, const model_params_t &)> set_func) {
-  rd::setulb_fn setulb = rd::load_setulb();
-  int           task = rd::LBFGSB_START;
-  int           n_params = static_cast<int>(initial_params.size());
-  set_func(partition_index, initial_params);
-  double              score = compute_lh();
-  double              initial_score = score;
-  int                 csave = 0;
-  std::vector<double> gradient(static_cast<size_t>(n_params), 0.0);
-  int                 max_corrections = 20;
-  std::vector<double> wa((2 * (size_t)max_corrections + 5) * static_cast<size_t>(n_params) +
-                             12 * (size_t)max_corrections * ((size_t)max_corrections + 1),
-                         0.0);
-  std::vector<int>    iwa(3 * static_cast<size_t>(n_params), 0);
-  std::vector<double> parameters(initial_params);
-  std::vector<double> param_min(static_cast<size_t>(n_params), p_min);
-  std::vector<double> param_max(static_cast<size_t>(n_params), p_max);
-  int                 lsave[4] = {0, 0, 0, 0};
-  int                 isave[44] = {0};
-  double              dsave[29] = {0};
-  std::vector<int>    bound_type(static_cast<size_t>(n_params), 2);
-  int                 iprint = -1;
-  size_t              iters = 0;
-
-  while (iters < 500) {
-    setulb(&n_params, &max_corrections, parameters.data(), param_min.data(), param_max.data(),
-           bound_type.data(), &score, gradient.data(), &factor, &pgtol, wa.data(), iwa.data(), &task,
-           &iprint, &csave, lsave, isave, dsave);
-    // f is evaluated after every return, whatever the task (Appendix B-8)
-    set_func(partition_index, parameters);
-    score = compute_lh();
-    if (rd::lbfgsb_is_fg(task)) {
-      for (size_t i = 0; i < static_cast<size_t>(n_params); ++i) {
-        double h = epsilon * fabs(parameters[i]);
-        if (h < epsilon) h = epsilon;
-        double temp = parameters[i];
-        parameters[i] += h;
-        set_func(partition_index, parameters);
-        double dlh = compute_lh();
-        if (!std::isfinite(dlh)) throw std::runtime_error("dlh is not finite");
-        gradient[i] = (dlh - score) / h;
-        if (!std::isfinite(gradient[i])) throw std::runtime_error("gradient is not finite");
-        parameters[i] = temp;
-      }
-    } else if (task != rd::LBFGSB_NEW_X) {
-      break;
-    }
-    iters++;
-  }
-  set_func(partition_index, parameters);
-  score = compute_lh();
-  // accepted only if not worse; the partition keeps the last tried values either
-  // way (Appendix B-14)
-  if (initial_score >= score) std::swap(parameters, initial_params);
-  return score;
-}
-
-double model_t::bfgs_rates(model_params_t &initial_rates, const std::vector<rdk_operation_t> &ops,
-                           const std::vector<unsigned int> &pmatrix_indices,
-                           const std::vector<double> &branch_lengths, size_t pi, double pgtol,
-                           double factor) {
-  return bfgs_params(
-      initial_rates, pi, 1e-4, 1e4, 1e-4, pgtol, factor,
-      [&, this]() -> double { return -this->compute_lh_partition(pi, ops, pmatrix_indices, branch_lengths); },
-      [&, this](size_t p, const model_params_t &mp) { this->set_subst_rates(p, mp); });
-}
-
-double model_t::bfgs_freqs(model_params_t &initial_freqs, const std::vector<rdk_operation_t> &ops,
-                           const std::vector<unsigned int> &pmatrix_indices,
-                           const std::vector<double> &branch_lengths, size_t pi, double pgtol,
-                           double factor) {
-  return bfgs_params(
-      initial_freqs, pi, 1e-4, 1.0 - 1e-4 * 3, 1e-4, pgtol, factor,
-      [&, this]() -> double { return -this->compute_lh_partition(pi, ops, pmatrix_indices, branch_lengths); },
-      [&, this](size_t p, const model_params_t &mp) { this->set_freqs_all_free(p, mp); });
-}
-
-double model_t::bfgs_gamma_rates(model_params_t &alpha, const std::vector<rdk_operation_t> &ops,
-                                 const std::vector<unsigned int> &pmatrix_indices,
-                                 const std::vector<double> &branch_lengths, size_t pi, double pgtol,
-                                 double factor) {
-  return bfgs_params(
-      alpha, pi, 0.2, 10000.0, 1e-4, pgtol, factor,
-      [&, this]() -> double { return -this->compute_lh_partition(pi, ops, pmatrix_indices, branch_lengths); },
-      [&, this](size_t p, const model_params_t &mp) { this->set_gamma_rates(p, mp); });
-}
-
-double model_t::bfgs_gamma_weights(model_params_t &w, const std::vector<rdk_operation_t> &ops,
-                                   const std::vector<unsigned int> &pmatrix_indices,
-                                   const std::vector<double> &branch_lengths, size_t pi, double pgtol,
-                                   double factor) {
-  return bfgs_params(
-      w, pi, 1e-4, 1.0, 1e-4, pgtol, factor,
-      [&, this]() -> double { return -this->compute_lh_partition(pi, ops, pmatrix_indices, branch_lengths); },
-      [&, this](size_t p, const model_params_t &mp) { this->set_gamma_weights(p, mp); });
-}
-
-// src/model.cpp:1925-1984
-void model_t::optimize_params(std::vector<partition_parameters_t> &params, const root_location_t &rl,
-                              double pgtol, double factor, bool optimize_gamma) {
-  std::vector<rdk_operation_t> ops;
-  std::vector<unsigned int>    pmatrix_indices;
-  std::vector<double>          branch_lengths;
-  GENERATE_AND_UNPACK_OPS(_tree, rl, ops, pmatrix_indices, branch_lengths);
-  for_each_partition(_partitions.size(), true, [&](size_t i) {
-    set_subst_rates(i, params[i].subst_rates);
-    set_freqs_all_free(i, params[i].freqs);
-    set_gamma_rates(i, params[i].gamma_alpha);
-    if (_rate_category_types[i] == rate_category::FREE) set_gamma_weights(i, params[i].gamma_weights);
-
-    bfgs_rates(params[i].subst_rates, ops, pmatrix_indices, branch_lengths, i, pgtol, factor);
-    bfgs_freqs(params[i].freqs, ops, pmatrix_indices, branch_lengths, i, pgtol, factor);
-    if (optimize_gamma && !_rate_user_init[i]) {
-      bfgs_gamma_rates(params[i].gamma_alpha, ops, pmatrix_indices, branch_lengths, i, pgtol, factor);
-      if (_rate_category_types[i] == rate_category::FREE)
-        bfgs_gamma_weights(params[i].gamma_weights, ops, pmatrix_indices, branch_lengths, i, pgtol,
-                           factor);
-    }
-  });
-}
-
-// src/model.cpp:1737-1746
-std::vector<double> model_t::compute_all_root_lh() {
-  compute_lh(_tree.roots()[0]);
-  std::vector<double> root_lh;
-  for (auto rl : _tree.roots()) {
-    move_root(rl);
-    root_lh.push_back(compute_lh(rl));
-  }
-  return root_lh;
+  text << "}";
+  return text.str();
 }
 
 // ---------------------------------------------------------------------------
@@ -1106,14 +1006,19 @@ void model_t::assign_indicies(size_t begin, size_t end) {
   std::iota(_assigned_idx.begin(), _assigned_idx.end(), begin);
 }
 
-void model_t::assign_indicies() {
-  _assigned_idx.resize(_tree.root_count());
-  std::iota(_assigned_idx.begin(), _assigned_idx.end(), 0);
-}
+void model_t::assign_indicies() { assign_indicies(0, _tree.root_count()); }
 
 void model_t::assign_indicies(size_t beg, size_t end, std::vector<size_t> idx) {
-  _assigned_idx.clear();
-  for (size_t i = beg; i < end; ++i) _assigned_idx.push_back(idx[i]);
+  _assigned_idx.assign(idx.begin() + (std::ptrdiff_t)beg, idx.begin() + (std::ptrdiff_t)end);
+}
+
+// rank r of n takes the r-th of n contiguous shares of `work`, the first |work| mod n shares one
+// item longer (src/model.cpp:1843-1849,1899-1907; sharding.plan_root_shards is the same rule)
+void model_t::assign_rank_share(const std::vector<size_t> &work, size_t rank, size_t num_tasks) {
+  const size_t share = work.size() / num_tasks, longer = work.size() % num_tasks;
+  const size_t beg = share * rank + std::min(longer, rank);
+  const size_t end = share * (rank + 1) + std::min(longer, rank + 1);
+  assign_indicies(beg, end, work);
 }
 
 void model_t::assign_indicies_by_rank_search(size_t min_roots, double root_ratio, size_t rank,
@@ -1122,55 +1027,44 @@ void model_t::assign_indicies_by_rank_search(size_t min_roots, double root_ratio
                                  checkpoint);
 }
 
+// the starts of a search: the first max(ratio * N, min) roots of the chosen ranking, minus what
+// the checkpoint already holds, dealt to the ranks
 void model_t::assign_indicies_by_rank_search(size_t min_roots, double root_ratio, size_t rank,
                                              size_t num_tasks, initial_root_strategy_t init_root,
                                              checkpoint_t &checkpoint) {
-  auto                completed = checkpoint.completed_indicies();
+  auto                done = checkpoint.completed_indicies();
   std::vector<size_t> order;
-  if (init_root == initial_root_strategy_t::random)
-    order = shuffle_root_indicies();
-  else if (init_root == initial_root_strategy_t::midpoint)
-    order = suggest_root_indicies_midpoint();
-  else if (init_root == initial_root_strategy_t::modified_mad)
-    order = suggest_root_indicies_modified_mad();
-  else
-    throw std::runtime_error{"The initial root strategy was not recognized"};
-
-  size_t root_count = std::min(
-      std::max(static_cast<size_t>(_tree.root_count() * root_ratio), min_roots), _tree.root_count());
-  if (root_count < completed.size())
+  switch (init_root) {
+  case initial_root_strategy_t::random: order = shuffle_root_indicies(); break;
+  case initial_root_strategy_t::midpoint: order = suggest_root_indicies_midpoint(); break;
+  case initial_root_strategy_t::modified_mad: order = suggest_root_indicies_modified_mad(); break;
+  default: throw std::runtime_error{"The initial root strategy was not recognized"};
+  }
+  const size_t wanted = std::min(std::max(static_cast<size_t>(_tree.root_count() * root_ratio), min_roots),
+                                 _tree.root_count());
+  if (wanted < done.size())
     throw std::runtime_error{"There are too many results in the checkpoint for this search. Is the "
                              "checkpoint corrupted?"};
-  std::sort(completed.begin(), completed.end());
-  size_t              work_left = root_count - completed.size();
-  std::vector<size_t> trimmed;
-  for (auto i : order)
-    if (!std::binary_search(completed.begin(), completed.end(), i)) trimmed.push_back(i);
-  size_t chunk = work_left / num_tasks, mod = work_left % num_tasks;
-  size_t beg = chunk * rank + std::min(mod, rank);
-  size_t end = chunk * (rank + 1) + std::min(mod, (rank + 1));
-  assign_indicies(beg, end, trimmed);
+  std::sort(done.begin(), done.end());
+  std::vector<size_t> open;
+  for (size_t id : order)
+    if (!std::binary_search(done.begin(), done.end(), id)) open.push_back(id);
+  // the reference cuts the shares from `wanted - done` items of the open list, not from all of it
+  open.resize(std::min(open.size(), wanted - done.size()));
+  assign_rank_share(open, rank, num_tasks);
 }
 
-void model_t::assign_indicies_by_rank_exhaustive(size_t rank, size_t num_tasks,
-                                                 checkpoint_t &checkpoint) {
-  auto completed = checkpoint.current_progress();
-  if (_tree.root_count() < completed.size())
+// exhaustive mode: every root id the checkpoint does not hold yet, in id order, dealt to the ranks
+void model_t::assign_indicies_by_rank_exhaustive(size_t rank, size_t num_tasks, checkpoint_t &checkpoint) {
+  const auto done = checkpoint.current_progress();
+  if (_tree.root_count() < done.size())
     throw std::runtime_error{"There are too many results in the checkpoint for this tree, are you "
                              "sure the checkpoint matches?"};
-  size_t work_left = _tree.root_count() - completed.size();
-  std::sort(completed.begin(), completed.end(),
-            [](rd_result_t a, rd_result_t b) { return a.root_id < b.root_id; });
-  std::vector<size_t> todo;
-  size_t              c = 0;
-  for (size_t i = 0; i < _tree.root_count(); ++i) {
-    if (c < completed.size() && completed[c].root_id == i)
-      ++c;
-    else
-      todo.push_back(i);
-  }
-  size_t chunk = work_left / num_tasks, mod = work_left % num_tasks;
-  size_t beg = chunk * rank + std::min(mod, rank);
-  size_t end = chunk * (rank + 1) + std::min(mod, (rank + 1));
-  assign_indicies(beg, end, todo);
+  std::vector<char> seen(_tree.root_count(), 0);
+  for (const auto &r : done)
+    if (r.root_id < seen.size()) seen[r.root_id] = 1;
+  std::vector<size_t> open;
+  for (size_t id = 0; id < seen.size(); ++id)
+    if (!seen[id]) open.push_back(id);
+  assign_rank_share(open, rank, num_tasks);
 }

@@ -16,6 +16,7 @@
 #include "checkpoint.hpp"
 #include "msa.hpp"
 #include "tree.hpp"
+#include "optim.hpp"
 #include "util.hpp"
 
 #include <functional>
@@ -135,57 +136,66 @@ public:
   void         set_sweep_mode(sweep_mode_t m) { _sweep_mode = m; }
   sweep_mode_t sweep_mode() const { return _sweep_mode; }
 
+  // The root-only evaluations of compute_dlh / optimize_alpha (two per slope, src/model.cpp:481-519;
+  // five before the first decision, :679-693; one dyadic level of the sign-change search, :732-776)
+  // go to the engine as ONE batch each (rdk_root_loglikelihood_multi) instead of one call, one
+  // synchronisation -- and, on site shards, one all-reduce -- per evaluation.  Same values, same
+  // decisions; off = the reference's call sequence (RD_BATCHED_PROBES=0 in the environment).
+  void set_batched_probes(bool on) { _batched_probes = on; }
+  bool batched_probes() const { return _batched_probes; }
+
   rdk_partition_t *partition(size_t i) { return _partitions[i]; }
   size_t           partition_count() const { return _partitions.size(); }
 
 private:
-  std::pair<root_location_t, double> brents(root_location_t beg, dlh_t d_beg, root_location_t end,
-                                            dlh_t d_end, double atol);
+  // ---- root position on a branch (model.cpp "position on the branch") ------------------------
+  // one batch of root-only evaluations on the branch of `root`: log-likelihoods at `values_at`,
+  // then forward-difference slope pairs at `slopes_at`, in that order, through ONE fused engine
+  // call per partition when batched probes are on (rdk_root_loglikelihood_multi)
+  struct slope_probe_t {
+    double x, fx, fxh, sign;
+  };
+  struct branch_probe_t {
+    std::vector<double>        values;
+    std::vector<slope_probe_t> slopes;
+  };
+  branch_probe_t    probe_branch(const root_location_t &root, const std::vector<double> &values_at,
+                                 const std::vector<double> &slopes_at);
+  std::vector<double> root_lh_on_branch(const root_location_t &root, const std::vector<double> &ratios);
+  static rd::slope_sample_t settle(const slope_probe_t &raw);
+  rd::slope_sample_t        refine_between(const root_location_t &root, const rd::slope_sample_t &lo,
+                                           const rd::slope_sample_t &hi, double atol);
 
+  // ---- parameter plumbing ----------------------------------------------------------------------
   void set_subst_rates_random(size_t, const msa_t &);
   void set_subst_rates_uniform();
+  void install_gamma_rates(size_t partition, double alpha, int mode);
   void set_gamma_rates(size_t);
-  void set_gamma_rates_mean(size_t);
-  void set_gamma_rates_mean(size_t, double);
-  void set_gamma_rates_median(size_t);
-  void set_gamma_rates_median(size_t, double);
-  void set_gamma_rates_free(size_t);
-  void set_gamma_rates_free(size_t, model_params_t);
   void update_invariant_sites(size_t);
   void set_tip_states(size_t, const msa_t &);
   void set_empirical_freqs(size_t);
   void set_empirical_freqs();
   void set_freqs_all_free(size_t, model_params_t);
   void set_model_params(const std::vector<partition_parameters_t> &);
+  void reset_to_defaults();  // rates 1/12, empirical frequencies (what every start begins from)
+  std::vector<partition_parameters_t> fresh_parameters();
+  partition_parameters_t make_partition_parameters(size_t states, rate_category rc, size_t rate_cat_count);
 
-  void update_pmatrix_partition(size_t partition_index, const std::vector<unsigned int> &pmatrix_indices,
-                                const std::vector<double> &branch_lengths);
-  std::vector<bool> update_pmatrices(const std::vector<unsigned int> &pmatrix_indices,
-                                     const std::vector<double>       &branch_lengths);
-  double compute_lh_partition(size_t partition_index, const std::vector<rdk_operation_t> &ops,
-                              const std::vector<unsigned int> &pmatrix_indices,
-                              const std::vector<double>       &branch_lengths);
-
-  double bfgs_rates(model_params_t &initial_rates, const std::vector<rdk_operation_t> &ops,
-                    const std::vector<unsigned int> &pmatrix_indices,
-                    const std::vector<double> &branch_lengths, size_t partition_index, double pgtol,
-                    double factor);
-  double bfgs_freqs(model_params_t &initial_freqs, const std::vector<rdk_operation_t> &ops,
-                    const std::vector<unsigned int> &pmatrix_indices,
-                    const std::vector<double> &branch_lengths, size_t partition_index, double pgtol,
-                    double factor);
-  double bfgs_gamma_rates(model_params_t &alpha, const std::vector<rdk_operation_t> &ops,
-                          const std::vector<unsigned int> &pmatrix_indices,
-                          const std::vector<double> &branch_lengths, size_t partition_index, double pgtol,
-                          double factor);
-  double bfgs_gamma_weights(model_params_t &w, const std::vector<rdk_operation_t> &ops,
-                            const std::vector<unsigned int> &pmatrix_indices,
-                            const std::vector<double> &branch_lengths, size_t partition_index,
-                            double pgtol, double factor);
+  // ---- evaluation ------------------------------------------------------------------------------
+  struct traversal_t {  // a full post-order schedule for one root placement
+    std::vector<rdk_operation_t> ops;
+    std::vector<unsigned int>    pmatrix_indices;
+    std::vector<double>          branch_lengths;
+  };
+  traversal_t full_traversal(const root_location_t &rl);
+  void   update_pmatrix_partition(size_t partition_index, const std::vector<unsigned int> &pmatrix_indices,
+                                  const std::vector<double> &branch_lengths);
+  double root_loglikelihood(size_t partition_index);
+  double compute_lh_partition(size_t partition_index, const traversal_t &trav);
   void   optimize_params(std::vector<partition_parameters_t> &params, const root_location_t &rl,
                          double pgtol, double factor, bool optimize_gamma);
-
-  partition_parameters_t make_partition_parameters(size_t states, rate_category rc, size_t rate_cat_count);
+  std::pair<root_location_t, double> placement_of(const rd_result_t &result) const;
+  void assign_rank_share(const std::vector<size_t> &work, size_t rank, size_t num_tasks);
 
   rooted_tree_t                          _tree;
   std::vector<rdk_partition_t *>         _partitions;
@@ -206,6 +216,7 @@ private:
   unsigned int                           _sweep_extra = 0;   // spare directed-CLV buffers per sweep chunk
   unsigned int                           _sweep_chunks = 1;  // independent chunks of a directed sweep
   size_t                                 _max_outer_iterations = 1000;
+  bool                                   _batched_probes = true;  // see set_batched_probes
   static constexpr unsigned int          _submodels = 1;
 };
 

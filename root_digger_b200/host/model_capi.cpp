@@ -185,6 +185,13 @@ extern "C" int rdh_model_set_fused(void *h, int on) {
   return 1;
 }
 
+// root-only evaluations of compute_dlh / optimize_alpha as fused batches (default) or one by one
+extern "C" int rdh_model_set_batched_probes(void *h, int on) {
+  H(h).model->set_batched_probes(on != 0);
+  return 1;
+}
+extern "C" int rdh_model_batched_probes(void *h) { return H(h).model->batched_probes() ? 1 : 0; }
+
 // 0 = sequential (the reference's loop), 1 = path (same operations, one engine call),
 // 2 = directed (one pre-order pass over directed CLVs); identical values
 extern "C" int rdh_model_set_sweep_mode(void *h, int mode) {

@@ -11,6 +11,9 @@
 #define RDK_H_
 #include "rd_oracle.h"
 
+#include <stdlib.h>
+#include <string.h>
+
 #define RDK_SUCCESS RDO_SUCCESS
 #define RDK_FAILURE RDO_FAILURE
 #define RDK_SCALE_BUFFER_NONE RDO_SCALE_BUFFER_NONE
@@ -41,6 +44,43 @@ typedef rdo_partition_t rdk_partition_t;
 #define rdk_compute_root_loglikelihood rdo_compute_root_loglikelihood
 #define rdk_compute_gamma_cats rdo_compute_gamma_cats
 #define rdk_msa_empirical_frequencies rdo_msa_empirical_frequencies
+
+/* rdk_root_loglikelihood_multi restated as the call sequence it stands for (include/rdk.h:
+ * count x { update_prob_matrices(2) ; update_clvs(root_op) ; compute_root_loglikelihood }), with
+ * the root CLV, the root scaler and the two P-matrices put back afterwards -- the engine leaves
+ * partition state untouched */
+static inline int rdk_root_loglikelihood_multi(rdo_partition_t *p, const rdo_operation_t *root_op,
+                                               const unsigned int *params_indices,
+                                               const unsigned int *freqs_indices,
+                                               const double *branch_lengths, unsigned int count,
+                                               double *out_lnl) {
+  const size_t       clv_n = (size_t)p->sites * p->rate_cats * p->states;
+  const size_t       pm_n = (size_t)p->rate_cats * p->states * p->states;
+  const unsigned int mi[2] = {root_op->child1_matrix_index, root_op->child2_matrix_index};
+  const int          sc = root_op->parent_scaler_index;
+  double            *keep_clv = (double *)malloc(sizeof(double) * clv_n);
+  double            *keep_pm = (double *)malloc(sizeof(double) * 2 * pm_n);
+  unsigned int      *keep_sc = sc >= 0 ? (unsigned int *)malloc(sizeof(unsigned int) * p->sites) : 0;
+  int                rc = RDO_SUCCESS;
+  memcpy(keep_clv, p->clv[root_op->parent_clv_index], sizeof(double) * clv_n);
+  memcpy(keep_pm, p->pmatrix[mi[0]], sizeof(double) * pm_n);
+  memcpy(keep_pm + pm_n, p->pmatrix[mi[1]], sizeof(double) * pm_n);
+  if (keep_sc) memcpy(keep_sc, p->scale_buffer[sc], sizeof(unsigned int) * p->sites);
+  for (unsigned int b = 0; b < count && rc == RDO_SUCCESS; ++b) {
+    rc = rdo_update_prob_matrices(p, params_indices, mi, branch_lengths + 2 * b, 2);
+    if (rc != RDO_SUCCESS) break;
+    rdo_update_clvs(p, root_op, 1);
+    out_lnl[b] = rdo_compute_root_loglikelihood(p, root_op->parent_clv_index, sc, freqs_indices, 0);
+  }
+  memcpy(p->clv[root_op->parent_clv_index], keep_clv, sizeof(double) * clv_n);
+  memcpy(p->pmatrix[mi[0]], keep_pm, sizeof(double) * pm_n);
+  memcpy(p->pmatrix[mi[1]], keep_pm + pm_n, sizeof(double) * pm_n);
+  if (keep_sc) memcpy(p->scale_buffer[sc], keep_sc, sizeof(unsigned int) * p->sites);
+  free(keep_clv);
+  free(keep_pm);
+  free(keep_sc);
+  return rc;
+}
 
 /* rdk_sweep_root_placements restated as the call sequence it stands for */
 static inline int rdk_sweep_root_placements(rdo_partition_t *p, unsigned int placements,

@@ -1,0 +1,133 @@
+"""The optimiser components of root_digger_b200/host/optim.hpp on their own, on analytic functions
+(CPU; the host library compiled against the oracle carries the same code).  What they do inside
+model_t -- the reference's trajectories, bit for bit -- is held by tests/test_reference_sources.py
+against the reference's own src/model.cpp (brents :606-676, bfgs_params :1430-1522)."""
+import math
+
+import numpy as np
+import pytest
+
+import oracle_build
+from root_digger_b200 import capi
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return capi.load_tree_lib(oracle_build.build_host_on_oracle())
+
+
+def concave(peak, curvature=3.0):
+    """a log-likelihood-like function with its maximum at `peak`: slope changes sign there"""
+    return lambda x: (-curvature * (x - peak) ** 2 - 100.0, -2.0 * curvature * (x - peak))
+
+
+@pytest.mark.parametrize("peak", [0.5, 0.123456789, 0.9, 1e-3])
+def test_slope_root_finds_the_peak(lib, peak):
+    x, value, slope, probes = capi.slope_root(concave(peak), 0.0, 1.0, 1e-12, lib=lib)
+    assert abs(x - peak) < 1e-9
+    assert value == pytest.approx(-100.0, abs=1e-12)
+    assert abs(slope) < 1e-8
+    assert 0 < probes <= 64
+
+
+def test_slope_root_on_a_transcendental_slope(lib):
+    # slope = cos(3x) on [0, 1]: root at pi/6; value = sin(3x)/3
+    x, value, slope, probes = capi.slope_root(lambda t: (math.sin(3 * t) / 3, math.cos(3 * t)), 0.0, 1.0, 1e-14,
+                                              lib=lib)
+    assert abs(x - math.pi / 6) < 1e-10 and abs(value - 1 / 3) < 1e-12 and probes <= 64
+
+
+def test_slope_root_returns_a_sample_it_evaluated(lib):
+    seen = []
+
+    def fn(x):
+        seen.append(x)
+        return concave(0.3)(x)
+
+    x, value, slope, probes = capi.slope_root(fn, 0.0, 1.0, 1e-10, lib=lib)
+    assert x in seen and len(seen) == probes + 2
+    assert all(0.0 <= s <= 1.0 for s in seen), "the iterates stay inside the bracket"
+
+
+def test_slope_root_refuses_a_non_bracket(lib):
+    with pytest.raises(RuntimeError, match="don't bracket"):
+        capi.slope_root(concave(2.0), 0.0, 1.0, lib=lib)  # slope positive at both ends
+    with pytest.raises(RuntimeError, match="don't bracket"):
+        capi.slope_root(lambda x: (0.0, float("nan")), 0.0, 1.0, lib=lib)
+
+
+def test_slope_root_gives_up_after_64_iterations(lib):
+    # the sign change sits immediately right of 0 and the tolerance is relative to the estimate
+    # (2 |x| eps): every step halves the bracket towards 0 and 64 halvings do not get there
+    with pytest.raises(RuntimeError, match="failed to converge"):
+        capi.slope_root(lambda x: (0.0, 1.0 if x == 0.0 else -1.0), 0.0, 1.0, 0.0, lib=lib)
+
+
+def test_slope_root_keeps_the_larger_residual_as_its_estimate(lib):
+    """Q1 of optim.hpp (the reference's rank test, src/model.cpp:624-631): the current estimate is
+    the bracket end with the LARGER |slope|, so an end that is already flat (1e-13 <= the 1e-12
+    floor) does not end the search at once as it would in textbook Brent -- the bracket is walked
+    down to it"""
+    x, _, slope, probes = capi.slope_root(lambda t: (0.0, 1e-13 if t == 0.0 else -1.0), 0.0, 1.0, 1e-9, lib=lib)
+    assert probes > 10 and 0.0 < x < 1e-8 and slope == -1.0
+
+
+def test_minimize_in_box_quadratic(lib):
+    target = np.array([0.3, 0.7, 0.55])
+    x, f_end, calls = capi.minimize_in_box(lambda v: float(np.sum((v - target) ** 2)), [0.5, 0.5, 0.5], 1e-4, 1.0,
+                                           lib=lib)
+    # forward differences of step 1e-4 bias the gradient by h: the minimum is found to about h/2
+    assert np.allclose(x, target, atol=1e-4) and f_end < 1e-7 and calls > 5
+
+
+def test_minimize_in_box_respects_the_box(lib):
+    seen = []
+
+    def fn(v):
+        seen.append(v.copy())
+        return float(np.sum((v - 2.0) ** 2))  # unconstrained minimum outside the box
+
+    x, f_end, _ = capi.minimize_in_box(fn, [0.5, 0.25], 0.2, 1.0, lib=lib)
+    assert np.allclose(x, [1.0, 1.0], atol=1e-9)
+    pts = np.array(seen)
+    assert pts.min() >= 0.2 - 1e-12 and pts.max() <= 1.0 + 1e-4 + 1e-12  # + the difference step
+
+
+def test_minimize_in_box_evaluation_protocol(lib):
+    """Q3 / Q4 of optim.hpp: the start is evaluated first, the final point last (and is what stays
+    installed), every gradient costs n shifted evaluations after one at the point itself"""
+    seen = []
+
+    def fn(v):
+        seen.append(v.copy())
+        return float((v[0] - 0.4) ** 2 + 2 * (v[1] - 0.6) ** 2)
+
+    x0 = np.array([0.9, 0.1])
+    x, f_end, calls = capi.minimize_in_box(fn, x0, 1e-4, 1.0, lib=lib)
+    assert calls == len(seen) and np.array_equal(seen[0], x0)
+    assert np.array_equal(seen[-1], x) and f_end == fn(x)
+    # the first round: the point, then one coordinate shifted by max(1e-4 |x_i|, 1e-4) at a time
+    assert np.array_equal(seen[1], x0)
+    assert seen[2][0] == x0[0] + 1e-4 and seen[2][1] == x0[1]
+    assert seen[3][0] == x0[0] and seen[3][1] == x0[1] + 1e-4
+
+
+def test_minimize_in_box_keeps_the_start_when_the_end_is_worse(lib):
+    """Q4: an objective that gets WORSE wherever the optimiser goes leaves x at the start"""
+    x0 = np.array([0.5])
+    calls = {"n": 0}
+
+    def fn(v):
+        calls["n"] += 1
+        return -1.0 if calls["n"] == 1 else float(calls["n"])  # the start is the best point ever seen
+
+    x, f_end, _ = capi.minimize_in_box(fn, x0, 1e-4, 1.0, lib=lib)
+    assert np.array_equal(x, x0) and f_end > -1.0
+
+
+def test_minimize_in_box_refuses_non_finite_objectives(lib):
+    def fn(v):
+        return float("inf") if v[0] > 0.5 else float(v[0])
+
+    with pytest.raises(RuntimeError, match="not finite"):
+        capi.minimize_in_box(fn, [0.5], 1e-4, 1.0, lib=lib)
