@@ -652,13 +652,35 @@ def exhaustive_sample(m, branches: int, tol=(1e-7, 1e-7, 1e-12, 1e4), stats=None
         full = (s1["clv_ops"] - s0["clv_ops"]) // max(1, taxa - 1) if taxa else None
         out.update(root_evaluations=int(ev), evaluations_per_sec=ev / dt if dt > 0 else None,
                    full_traversals=full, full_evaluations_per_sec=(full / dt if full and dt > 0 else None))
+    # the alpha loop (H3): latency of one slope (compute_dlh = 2 root-only evaluations) and of one
+    # optimize_alpha, with the evaluations handed to the engine as fused batches (the default,
+    # DESIGN 5.5) and one by one as the reference issues them; same values either way
     reps = 50
-    barrier()
-    t1 = time.perf_counter()
-    for i in range(reps):
-        m.compute_dlh(int(ids[0]), 0.25 + 0.01 * i)
-    barrier()
-    out["us_per_compute_dlh"] = (time.perf_counter() - t1) / reps * 1e6
+    was = m.batched_probes
+    for batched, key in ((True, "us_per_compute_dlh"), (False, "us_per_compute_dlh_unbatched")):
+        m.set_batched_probes(batched)
+        barrier()
+        t1 = time.perf_counter()
+        for i in range(reps):
+            m.compute_dlh(int(ids[0]), 0.25 + 0.01 * i)
+        barrier()
+        out[key] = (time.perf_counter() - t1) / reps * 1e6
+    alphas = {}
+    for batched, key in ((True, "us_per_optimize_alpha"), (False, "us_per_optimize_alpha_unbatched")):
+        m.set_batched_probes(batched)
+        alphas[key], spent = [], 0.0
+        for r in ids[:4]:
+            m.compute_lh(int(r), 0.5)  # CLVs oriented towards this branch (not timed)
+            barrier()
+            t1 = time.perf_counter()
+            alphas[key].append(m.optimize_alpha(int(r), 0.5, 1e-12))
+            barrier()
+            spent += time.perf_counter() - t1
+        out[key] = spent / max(1, len(alphas[key])) * 1e6
+    out["optimize_alpha_same_bits"] = bool(
+        np.array_equal(np.array(alphas["us_per_optimize_alpha"]).view(np.uint64),
+                       np.array(alphas["us_per_optimize_alpha_unbatched"]).view(np.uint64)))
+    m.set_batched_probes(was)
     return out
 
 

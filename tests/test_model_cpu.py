@@ -53,6 +53,44 @@ def test_compute_dlh_and_optimize_alpha(lib):
             assert 0.0 <= r <= 1.0
 
 
+def test_batched_probes_have_the_bits_of_the_reference_call_sequence(lib):
+    """compute_dlh (1 fused call for both evaluations) and optimize_alpha (5 evaluations
+    before the first decision, one call per dyadic level, one per Brent iteration) against the same
+    model issuing every root-only evaluation on its own, the way src/model.cpp:481-519,679-794 does
+    -- every root, three start positions, loose and tight tolerances; one and several partitions"""
+    from root_digger_b200 import synth
+    top = synth.random_tree(12, 4)
+    rates, freqs = synth.random_params(9)
+    aln = synth.simulate_alignment(top, 900, 5, rates, freqs, capi.gamma_cats(1.0, 2))
+
+    def pair(**kw):
+        out = []
+        for batched in (True, False):
+            if kw:
+                m = capi.Model(capi.RootedTree(synth.to_newick(top), lib=lib), aln, rate_cats=2, compress=True, seed=3,
+                               **kw)
+                m.initialize_partitions(uniform_freqs=False)
+            else:
+                m = make_model(lib, K=2, uniform=False)
+            m.set_batched_probes(batched)
+            assert m.batched_probes is batched
+            out.append(m)
+        return out
+
+    for a, b in (pair(), pair(partitions=[(0, 300), (300, 900)])):
+        for rid in range(a.root_count):
+            for m in (a, b):
+                m.compute_lh(rid)
+            for x in (0.0, 0.37, 1.0 - 1e-9, 1.0):
+                assert [v.hex() for v in a.compute_dlh(rid, x)] == [v.hex() for v in b.compute_dlh(rid, x)]
+            for start, atol in ((0.5, 1e-7), (0.0, 1e-14), (1.0, 1e-3)):
+                assert a.optimize_alpha(rid, start, atol).hex() == b.optimize_alpha(rid, start, atol).hex()
+                # what follows an optimize_alpha in both drivers: the root-only evaluation there
+                assert a.compute_lh_root(rid, 0.3).hex() == b.compute_lh_root(rid, 0.3).hex()
+        a.close()
+        b.close()
+
+
 def test_optimize_root_location(lib):
     """test/src/model.cpp:240-252"""
     m = make_model(lib)
@@ -184,3 +222,6 @@ def test_bench_exhaustive_sample_helper(lib):
     out = bench.exhaustive_sample(m, 2, tol=(1e-2, 1e-2, 1e-2, 1e13))
     assert 1 <= out["branches"] <= 2 and out["branches_per_sec"] > 0 and math.isfinite(out["best_llh"])
     assert out["best_branch"] in (0, 1)
+    # the alpha loop is reported with batched and one-by-one root evaluations, which must agree
+    assert out["optimize_alpha_same_bits"] is True and m.batched_probes
+    assert out["us_per_compute_dlh"] > 0 and out["us_per_compute_dlh_unbatched"] > 0
