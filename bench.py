@@ -591,8 +591,14 @@ def run_ours(args):
                                     else (lambda *a: None))
             except Exception as exc:  # a failed extra must not take the headline line with it
                 res = {"error": "%s: %s" % (type(exc).__name__, exc)}
-                if world > 1:
-                    raise
+            if world > 1:
+                # every rank learns whether ANY rank failed this extra (an error raised on all ranks alike --
+                # the usual kind -- leaves the job in step, and the next extra and the headline line go on)
+                failed = isinstance(res, dict) and "error" in res
+                flag = torch.tensor([1.0 if failed else 0.0], device="cuda")
+                dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+                if flag.item() > 0 and not failed:
+                    res = {"error": "failed on another rank"}
             torch.cuda.empty_cache()
             if rank == 0:
                 north_star[name] = res

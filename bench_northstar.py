@@ -201,7 +201,11 @@ def run_config(name: str, cfg: dict, *, torch, dist, rank: int, world: int, loca
     else:
         for j, s in enumerate(setups):
             m.set_params(rates=s.rates, freqs=s.freqs, part=j)
-        wrap = PartitionShardedModel(m, P, rank, world, dist, device="cuda") if world > 1 else None
+        # the all-gather of the partitions' terms is issued from Python after the local call -- the path
+        # measured on 8 GPUs in profiles/r02_bench_final_n8_north_star.json.  (model_t can complete the sums
+        # itself, PartitionShardedModel(in_model=True): that is what search / exhaustive_search on partition
+        # shards use; it is held on gloo by tests/test_sharding.py and on NCCL by tests/test_gpu_multi.py.)
+        wrap = PartitionShardedModel(m, P, rank, world, dist, device="cuda", in_model=False) if world > 1 else None
     m.set_sweep_mode(m.SWEEP_DIRECTED)
     L = capi.load_engine()
     handles = [C.cast(m.L.rdh_model_partition(m.h, j), C.POINTER(capi.PartitionStruct)) for j in range(parts_local)]

@@ -334,6 +334,74 @@ static double sum_in_order(const std::vector<double> &terms) {
   return total;
 }
 
+// ---- partitions dealt to several processes -------------------------------------------------
+void model_t::set_partition_exchange(const std::vector<size_t> &global_index, size_t global_partitions,
+                                     partition_exchange_fn exchange, void *user) {
+  if (!exchange) {
+    _exchange = nullptr;
+    _exchange_user = nullptr;
+    _global_index.clear();
+    _global_partitions = 0;
+    return;
+  }
+  if (global_index.size() != _partitions.size())
+    throw std::invalid_argument("set_partition_exchange: one global index per local partition is required");
+  for (size_t j = 0; j < global_index.size(); ++j)
+    if (global_index[j] >= global_partitions || (j && global_index[j] <= global_index[j - 1]))
+      throw std::invalid_argument("set_partition_exchange: global indices must be increasing and below the total");
+  for (auto type : _rate_category_types)
+    if (type == rate_category::FREE)
+      throw std::invalid_argument("set_partition_exchange: free rate categories draw their start weights from the "
+                                  "model's generator partition by partition and are not supported on shards");
+  _global_index = global_index;
+  _global_partitions = global_partitions;
+  _exchange = exchange;
+  _exchange_user = user;
+}
+
+std::vector<double> model_t::sum_over_partitions(const std::vector<std::vector<double>> &terms, size_t count) {
+  std::vector<double> total(count, 0.0);
+  if (!_exchange) {
+    for (const auto &of_partition : terms)
+      for (size_t i = 0; i < count; ++i) total[i] += of_partition[i];
+    return total;
+  }
+  std::vector<double> local(terms.size() * count), all(_global_partitions * count, 0.0);
+  for (size_t p = 0; p < terms.size(); ++p) std::copy(terms[p].begin(), terms[p].begin() + (std::ptrdiff_t)count,
+                                                      local.begin() + (std::ptrdiff_t)(p * count));
+  _exchange(local.data(), terms.size(), count, all.data(), _exchange_user);
+  for (size_t g = 0; g < _global_partitions; ++g)
+    for (size_t i = 0; i < count; ++i) total[i] += all[g * count + i];
+  return total;
+}
+
+double model_t::sum_over_partitions(const std::vector<double> &terms) {
+  if (!_exchange) return sum_in_order(terms);
+  std::vector<std::vector<double>> as_rows;
+  as_rows.reserve(terms.size());
+  for (double v : terms) as_rows.push_back({v});
+  return sum_over_partitions(as_rows, 1)[0];
+}
+
+uint64_t model_t::rng_state() const {
+  std::ostringstream text;
+  text << _random_engine;
+  return std::stoull(text.str());
+}
+
+void model_t::set_rng_state(uint64_t state) { _random_engine.seed((std::minstd_rand::result_type)state); }
+
+int model_t::first_partition_without_empirical_freqs() {
+  for (size_t p = 0; p < _partitions.size(); ++p) {
+    double *emp = rdk_msa_empirical_frequencies(_partitions[p]);
+    if (!emp) throw std::runtime_error("empirical frequencies failed: " + engine_error());
+    const bool degenerate = std::any_of(emp, emp + _partitions[p]->states, [](double f) { return f <= 0; });
+    free(emp);
+    if (degenerate) return (int)p;
+  }
+  return -1;
+}
+
 static void refuse_nan(double lh) {
   if (std::isnan(lh)) throw std::runtime_error("lh at root is not a number: " + std::to_string(lh));
 }
@@ -352,7 +420,7 @@ double model_t::compute_lh(const root_location_t &root_location) {
     terms[p] = root_loglikelihood(p);
   });
   _last_part_lh = terms;
-  return sum_in_order(terms);
+  return sum_over_partitions(terms);
 }
 
 // src/model.cpp:415-452: the two root branches and the root CLV only
@@ -368,7 +436,7 @@ double model_t::compute_lh_root(const root_location_t &root) {
     terms[p] = root_loglikelihood(p);
   });
   _last_part_lh = terms;
-  const double lh = sum_in_order(terms);
+  const double lh = sum_over_partitions(terms);
   refuse_nan(lh);
   return lh;
 }
@@ -457,7 +525,7 @@ std::vector<double> model_t::root_lh_on_branch(const root_location_t &root, cons
         terms[p] = root_loglikelihood(p);
       });
       _last_part_lh = terms;
-      lh[i] = sum_in_order(terms);
+      lh[i] = sum_over_partitions(terms);
     }
     return lh;
   }
@@ -468,11 +536,7 @@ std::vector<double> model_t::root_lh_on_branch(const root_location_t &root, cons
                                      lengths.data(), (unsigned)ratios.size(), terms[p].data()) == RDK_FAILURE)
       throw std::runtime_error(engine_error());
   });
-  for (size_t i = 0; i < ratios.size(); ++i) {
-    double total = 0.0;  // partition order, as compute_lh_root adds them
-    for (size_t p = 0; p < _partitions.size(); ++p) total += terms[p][i];
-    lh[i] = total;
-  }
+  lh = sum_over_partitions(terms, ratios.size());  // partition order, as compute_lh_root adds them
   _last_part_lh.resize(_partitions.size());
   for (size_t p = 0; p < _partitions.size(); ++p) _last_part_lh[p] = terms[p].back();
   return lh;
@@ -684,6 +748,7 @@ std::vector<double> model_t::sweep_root_lh(size_t begin, size_t end) {
         _last_sweep_part_lh[i][sw.root_pos[q] - begin] = part[q];
       }
     }
+    if (_exchange) lh = sum_over_partitions(_last_sweep_part_lh, lh.size());
     for (double v : lh)
       if (std::isnan(v)) throw std::runtime_error("lh at root is not a number: " + std::to_string(v));
     return lh;
@@ -715,6 +780,7 @@ std::vector<double> model_t::sweep_root_lh(size_t begin, size_t end) {
       _last_sweep_part_lh[i][r] = part[r];
     }
   }
+  if (_exchange) lh = sum_over_partitions(_last_sweep_part_lh, lh.size());
   for (double v : lh)
     if (std::isnan(v)) throw std::runtime_error("lh at root is not a number: " + std::to_string(v));
   return lh;
@@ -960,25 +1026,43 @@ rooted_tree_t model_t::unrooted_tree() const {
   return t;
 }
 
-// src/model.cpp:1297-1321: tips, invariant sites, frequencies, random start rates (Appendix B-10)
+// src/model.cpp:1297-1321: tips, invariant sites, frequencies, random start rates (Appendix B-10:
+// one draw of the model's generator per partition, in partition order).  On partition shards the
+// draws of the partitions held elsewhere are skipped, so that every process leaves with the
+// generator a single process would have -- the random start order of a search depends on it.
+template <typename PerPartition>
+void model_t::for_each_partition_in_global_order(PerPartition &&body) {
+  if (!_exchange) {
+    for (size_t p = 0; p < _partitions.size(); ++p) body(p);
+    return;
+  }
+  size_t local = 0;
+  for (size_t g = 0; g < _global_partitions; ++g) {
+    if (local < _global_index.size() && _global_index[local] == g)
+      body(local++);
+    else
+      _random_engine.discard(1);
+  }
+}
+
 void model_t::initialize_partitions(const std::vector<msa_t> &msa) {
-  for (size_t p = 0; p < _partitions.size(); ++p) {
+  for_each_partition_in_global_order([&](size_t p) {
     set_tip_states(p, msa[p]);
     update_invariant_sites(p);
     set_empirical_freqs(p);
     set_subst_rates_random(p, msa[p]);
-  }
+  });
 }
 
 void model_t::initialize_partitions_uniform_freqs(const std::vector<msa_t> &msa) {
-  for (size_t p = 0; p < _partitions.size(); ++p) {
+  for_each_partition_in_global_order([&](size_t p) {
     set_tip_states(p, msa[p]);
     update_invariant_sites(p);
     const unsigned int states = _partitions[p]->states;
     set_freqs(p, model_params_t(states, 1.0 / (double)states));
     set_subst_rates_random(p, msa[p]);
     set_gamma_rates(p);
-  }
+  });
 }
 
 // "{{r0,...,r11},{...}}": the rates of every partition, six decimals

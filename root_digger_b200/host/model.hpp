@@ -123,6 +123,29 @@ public:
   // ... and of the last sweep_root_lh: [partition][placement of the swept range]
   const std::vector<std::vector<double>> &last_sweep_partition_lh() const { return _last_sweep_part_lh; }
 
+  // ---- partitions dealt to several processes (BASELINE cfg4) ----------------------
+  // This process holds the partitions global_index[0..local) of `global_partitions`.  Parameter
+  // optimisation needs no exchange (each closure evaluates one partition, src/model.cpp:1544-1547);
+  // every log-likelihood that the reference sums over partitions (:397,429 -- compute_lh,
+  // compute_lh_root and with it compute_dlh / optimize_alpha, the placement sweep) is completed
+  // through `exchange`: it receives this process's terms [local partition][count] and returns the
+  // terms of ALL partitions [global partition][count]; they are then added in global partition
+  // order, the order a single process uses, so search / exhaustive_search take the same decisions
+  // on every rank and return the bits of a single-process run.  The model's random generator is
+  // kept in step with a single process (one draw per GLOBAL partition in initialize_partitions*).
+  typedef void (*partition_exchange_fn)(const double *local_terms, size_t local_partitions, size_t count,
+                                        double *all_terms, void *user);
+  void set_partition_exchange(const std::vector<size_t> &global_index, size_t global_partitions,
+                              partition_exchange_fn exchange, void *user);
+  bool partition_sharded() const { return _exchange != nullptr; }
+  // state of the model's generator (std::minstd_rand: one integer), for callers that must put
+  // several processes back in step after one of them failed half way through an initialisation
+  uint64_t rng_state() const;
+  void     set_rng_state(uint64_t state);
+  void     discard_rng(unsigned long long draws) { _random_engine.discard(draws); }
+  // the first local partition whose empirical frequencies have a zero entry, or -1
+  int first_partition_without_empirical_freqs();
+
   void move_root(const root_location_t &new_root);
   // use the fused engine entry points (rdk_sweep_root_placements) where the
   // reference loops over move_root + compute_lh_root; results are identical
@@ -177,6 +200,7 @@ private:
   void set_empirical_freqs();
   void set_freqs_all_free(size_t, model_params_t);
   void set_model_params(const std::vector<partition_parameters_t> &);
+  template <typename PerPartition> void for_each_partition_in_global_order(PerPartition &&body);
   void reset_to_defaults();  // rates 1/12, empirical frequencies (what every start begins from)
   std::vector<partition_parameters_t> fresh_parameters();
   partition_parameters_t make_partition_parameters(size_t states, rate_category rc, size_t rate_cat_count);
@@ -191,6 +215,9 @@ private:
   void   update_pmatrix_partition(size_t partition_index, const std::vector<unsigned int> &pmatrix_indices,
                                   const std::vector<double> &branch_lengths);
   double root_loglikelihood(size_t partition_index);
+  // sum over ALL partitions, in global partition order, of terms[local partition][0..count)
+  std::vector<double> sum_over_partitions(const std::vector<std::vector<double>> &terms, size_t count);
+  double              sum_over_partitions(const std::vector<double> &terms);
   double compute_lh_partition(size_t partition_index, const traversal_t &trav);
   void   optimize_params(std::vector<partition_parameters_t> &params, const root_location_t &rl,
                          double pgtol, double factor, bool optimize_gamma);
@@ -217,6 +244,10 @@ private:
   unsigned int                           _sweep_chunks = 1;  // independent chunks of a directed sweep
   size_t                                 _max_outer_iterations = 1000;
   bool                                   _batched_probes = true;  // see set_batched_probes
+  partition_exchange_fn                  _exchange = nullptr;     // see set_partition_exchange
+  void                                  *_exchange_user = nullptr;
+  std::vector<size_t>                    _global_index;           // global id of each local partition
+  size_t                                 _global_partitions = 0;
   static constexpr unsigned int          _submodels = 1;
 };
 

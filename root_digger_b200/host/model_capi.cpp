@@ -192,6 +192,31 @@ extern "C" int rdh_model_set_batched_probes(void *h, int on) {
 }
 extern "C" int rdh_model_batched_probes(void *h) { return H(h).model->batched_probes() ? 1 : 0; }
 
+// partitions dealt to several processes (model_t::set_partition_exchange): this process holds the
+// partitions global_index[0..n_local) of global_partitions; `exchange` completes every sum over
+// partitions (NULL detaches)
+extern "C" int rdh_model_set_partition_exchange(void *h, const unsigned *global_index, unsigned n_local,
+                                                unsigned global_partitions,
+                                                model_t::partition_exchange_fn exchange, void *user) {
+  RDH_TRY({
+    std::vector<size_t> idx(global_index, global_index + n_local);
+    H(h).model->set_partition_exchange(idx, global_partitions, exchange, user);
+    return 1;
+  })
+}
+extern "C" unsigned long long rdh_model_rng_state(void *h) { return H(h).model->rng_state(); }
+extern "C" void rdh_model_set_rng_state(void *h, unsigned long long state) { H(h).model->set_rng_state(state); }
+extern "C" void rdh_model_discard_rng(void *h, unsigned long long draws) { H(h).model->discard_rng(draws); }
+// first local partition whose empirical frequencies have a zero entry: -1 none, -2 error
+extern "C" int rdh_model_first_partition_without_empirical_freqs(void *h) {
+  try {
+    return H(h).model->first_partition_without_empirical_freqs();
+  } catch (const std::exception &e) {
+    rdh_set_error(e.what());
+    return -2;
+  }
+}
+
 // 0 = sequential (the reference's loop), 1 = path (same operations, one engine call),
 // 2 = directed (one pre-order pass over directed CLVs); identical values
 extern "C" int rdh_model_set_sweep_mode(void *h, int mode) {

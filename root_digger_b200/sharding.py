@@ -84,14 +84,24 @@ class PartitionShardedModel:
     the ranks (`plan_partition_shards`: partition p lives on rank p % nranks); every rank holds a
     `capi.Model` of ITS partitions only.  Per-partition parameter optimisation needs no
     communication at all (the reference's BFGS closures are per partition, src/model.cpp:1544-1547);
-    `compute_lh` / `compute_lh_root` / `sweep_root_lh` need the SUM over all partitions
-    (src/model.cpp:397,429): one all-gather of the per-partition terms per call, after which every
-    rank adds them in global partition order -- the order a single process uses -- so the result
-    has the same bits on 1, 2 or 8 ranks.
+    every log-likelihood the reference sums over partitions (src/model.cpp:397,429) is completed
+    INSIDE model_t through its partition exchange (model_t::set_partition_exchange): one all-gather
+    of the per-partition terms per evaluation batch, after which every rank adds them in global
+    partition order -- the order a single process uses.  So not only `compute_lh` /
+    `compute_lh_root` / `sweep_root_lh` but `compute_dlh`, `optimize_alpha`, `search` and
+    `exhaustive_search` run on the shards, take the same decisions on every rank and return the bits
+    of a single process holding all partitions.
 
-    `dist` is torch.distributed (initialised; nccl with `device="cuda"` or gloo with "cpu")."""
+    `dist` is torch.distributed (initialised; nccl with `device="cuda"` or gloo with "cpu").
+    Every rank must make the same calls in the same order (each one is a collective)."""
 
-    def __init__(self, local_model, n_partitions: int, rank: int, nranks: int, dist, device="cpu"):
+    def __init__(self, local_model, n_partitions: int, rank: int, nranks: int, dist, device="cpu",
+                 in_model: bool = True):
+        """in_model=False keeps model_t unaware of the other ranks: only compute_lh, compute_lh_root
+        and sweep_root_lh are available, completed by an all-gather issued from Python after the
+        local call (same collective, same ordered sum, same bits)."""
+        import ctypes as C
+        self.in_model = bool(in_model)
         self.m, self.P, self.rank, self.nranks, self.dist, self.device = local_model, n_partitions, rank, nranks, dist, device
         if nranks > n_partitions:
             # a rank without a partition would have no model_t to call (and nothing to all-gather)
@@ -101,6 +111,46 @@ class PartitionShardedModel:
         if local_model.partition_count != len(self.owned[rank]):
             raise ValueError("the local model must hold exactly this rank's partitions")
         self.slots = max(len(o) for o in self.owned)
+        self.exchanges = 0
+        self._error = None
+        self._exchange = None
+        if not self.in_model:
+            return
+        fn_t = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.c_size_t, C.c_size_t, C.POINTER(C.c_double), C.c_void_p)
+
+        def exchange(local_ptr, n_local, count, all_ptr, _user):
+            import numpy as np
+            out = np.ctypeslib.as_array(all_ptr, shape=(self.P, count))
+            try:
+                local = np.ctypeslib.as_array(local_ptr, shape=(n_local, count))
+                out[:] = self._gather_terms(local)
+                self.exchanges += 1
+            except Exception as e:  # nothing may propagate through the C++ frames: poison the sums instead
+                self._error = e
+                out[:] = float("nan")
+
+        self._exchange = fn_t(exchange)  # kept alive as long as the model uses it
+        L = local_model.L
+        L.rdh_model_set_partition_exchange.argtypes = [C.c_void_p, C.POINTER(C.c_uint), C.c_uint, C.c_uint, fn_t,
+                                                       C.c_void_p]
+        L.rdh_model_rng_state.argtypes = [C.c_void_p]
+        L.rdh_model_rng_state.restype = C.c_ulonglong
+        L.rdh_model_set_rng_state.argtypes = [C.c_void_p, C.c_ulonglong]
+        L.rdh_model_set_rng_state.restype = None
+        L.rdh_model_discard_rng.argtypes = [C.c_void_p, C.c_ulonglong]
+        L.rdh_model_discard_rng.restype = None
+        L.rdh_model_first_partition_without_empirical_freqs.argtypes = [C.c_void_p]
+        mine = (C.c_uint * len(self.owned[rank]))(*self.owned[rank])
+        if not L.rdh_model_set_partition_exchange(local_model.h, mine, len(self.owned[rank]), n_partitions,
+                                                  self._exchange, None):
+            raise RuntimeError(L.rdh_last_error().decode())
+
+    def close(self):
+        import ctypes as C
+        if self.m is not None and self.m.h and self._exchange is not None:
+            self.m.L.rdh_model_set_partition_exchange(self.m.h, None, 0, 0,
+                                                      C.cast(None, type(self._exchange)), None)
+        self.m = None
 
     def _gather_terms(self, local):
         """local: [local partitions][n] -> [all partitions][n], every rank"""
@@ -109,7 +159,7 @@ class PartitionShardedModel:
         local = np.atleast_2d(np.asarray(local, dtype=np.float64))
         n = local.shape[1]
         buf = torch.zeros((self.slots, n), dtype=torch.float64, device=self.device)
-        buf[:local.shape[0]] = torch.from_numpy(local).to(self.device)
+        buf[:local.shape[0]] = torch.from_numpy(np.ascontiguousarray(local)).to(self.device)
         out = torch.zeros((self.nranks, self.slots, n), dtype=torch.float64, device=self.device)
         self.dist.all_gather_into_tensor(out.view(-1), buf.view(-1)) if self.device != "cpu" else \
             self.dist.all_gather(list(out.unbind(0)), buf)
@@ -120,6 +170,24 @@ class PartitionShardedModel:
                 terms[p] = allv[r, j]
         return terms
 
+    def _all_ranks(self, value: int):
+        """[value of rank 0, value of rank 1, ...] on every rank"""
+        import torch
+        mine = torch.tensor([int(value)], dtype=torch.int64, device=self.device)
+        out = [torch.zeros_like(mine) for _ in range(self.nranks)]
+        self.dist.all_gather(out, mine)
+        return [int(t.item()) for t in out]
+
+    def _call(self, fn, *a, **kw):
+        if not self.in_model:
+            raise RuntimeError("this call needs the sums over partitions inside model_t (in_model=True)")
+        try:
+            return fn(*a, **kw)
+        finally:
+            if self._error is not None:
+                e, self._error = self._error, None
+                raise RuntimeError("partition exchange failed: %r" % (e,))
+
     @staticmethod
     def _ordered_sum(terms):
         import numpy as np
@@ -128,14 +196,82 @@ class PartitionShardedModel:
             total = total + terms[p]
         return total
 
+    def initialize_partitions(self, uniform_freqs: bool = False):
+        if not self.in_model:
+            return self.m.initialize_partitions(uniform_freqs=uniform_freqs)
+        return self._initialize_partitions_in_step(uniform_freqs)
+
+    def _initialize_partitions_in_step(self, uniform_freqs: bool):
+        """model_t::initialize_partitions[_uniform_freqs] on every rank.  A partition whose empirical
+        frequencies have a zero entry makes a single process throw when it gets there; here every
+        rank raises (not only the one that holds it) and every generator is left where the single
+        process's would be, so that the caller can fall back to uniform frequencies on all ranks as
+        RootDigger's main does."""
+        L, h = self.m.L, self.m.h
+        if not uniform_freqs:
+            state = L.rdh_model_rng_state(h)
+            bad = L.rdh_model_first_partition_without_empirical_freqs(h)
+            if bad == -2:
+                raise RuntimeError(L.rdh_last_error().decode())
+            first = [self.owned[r][b] for r, b in enumerate(self._all_ranks(bad)) if b >= 0]
+            if first:
+                L.rdh_model_set_rng_state(h, state)
+                L.rdh_model_discard_rng(h, min(first))  # the draws of the partitions before the failing one
+                raise RuntimeError("One of the state frequenices is zero while using emperical frequencies")
+        self.m.initialize_partitions(uniform_freqs=uniform_freqs)
+
+    def set_params(self, global_partition: int, **kw):
+        """parameters of one GLOBAL partition (a no-op on the ranks that do not hold it)"""
+        if global_partition in self.owned[self.rank]:
+            self.m.set_params(part=self.owned[self.rank].index(global_partition), **kw)
+
+    # ---- everything below is the local model_t: its sums over partitions are global ----------
     def compute_lh(self, rid: int, ratio: float = 0.5) -> float:
-        self.m.compute_lh(rid, ratio)
-        return float(self._ordered_sum(self._gather_terms(self.m.last_partition_lh()[:, None]))[0])
+        if not self.in_model:
+            self.m.compute_lh(rid, ratio)
+            return float(self._ordered_sum(self._gather_terms(self.m.last_partition_lh()[:, None]))[0])
+        return self._call(self.m.compute_lh, rid, ratio)
 
     def compute_lh_root(self, rid: int, ratio: float = 0.5) -> float:
-        self.m.compute_lh_root(rid, ratio)
-        return float(self._ordered_sum(self._gather_terms(self.m.last_partition_lh()[:, None]))[0])
+        if not self.in_model:
+            self.m.compute_lh_root(rid, ratio)
+            return float(self._ordered_sum(self._gather_terms(self.m.last_partition_lh()[:, None]))[0])
+        return self._call(self.m.compute_lh_root, rid, ratio)
+
+    def compute_dlh(self, rid: int, ratio: float = 0.5):
+        return self._call(self.m.compute_dlh, rid, ratio)
+
+    def move_root(self, rid: int, ratio: float = 0.5):
+        return self.m.move_root(rid, ratio)
+
+    def optimize_alpha(self, rid: int, ratio: float = 0.5, atol: float = 1e-7) -> float:
+        return self._call(self.m.optimize_alpha, rid, ratio, atol)
+
+    def optimize_root_location(self, min_roots: int = 1, root_ratio: float = 0.05):
+        return self._call(self.m.optimize_root_location, min_roots, root_ratio)
 
     def sweep_root_lh(self):
-        self.m.sweep_root_lh()
-        return self._ordered_sum(self._gather_terms(self.m.last_sweep_partition_lh()))
+        if not self.in_model:
+            self.m.sweep_root_lh()
+            return self._ordered_sum(self._gather_terms(self.m.last_sweep_partition_lh()))
+        return self._call(self.m.sweep_root_lh)
+
+    def search(self, *a, **kw):
+        """model_t::search over ALL partitions; every rank runs every start (rank / num_tasks of the
+        local model stay 0 / 1: the partitions are what is distributed, not the starts) and logs
+        the parameters of its own partitions"""
+        return self._call(self.m.search, *a, **kw)
+
+    def exhaustive_search(self, *a, **kw):
+        return self._call(self.m.exhaustive_search, *a, **kw)
+
+    def __getattr__(self, name):
+        # settings and accessors without a sum over partitions (set_max_outer_iterations, set_checkpoint,
+        # set_batched_probes, root_count, lwr, ...) are the local model's
+        if name in ("m", "in_model"):
+            raise AttributeError(name)
+        return getattr(self.m, name)
+
+    def last_partition_lh(self):
+        """the terms of ALL partitions of the last compute_lh / compute_lh_root, every rank"""
+        return self._gather_terms(self.m.last_partition_lh()[:, None])[:, 0]

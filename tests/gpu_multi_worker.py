@@ -117,7 +117,7 @@ def main():
     pm.initialize_partitions()
     for j, p in enumerate(mine):
         pm.set_params(rates=part_rates(case, p), freqs=case.freqs, part=j)
-    sm = sharding.PartitionShardedModel(pm, len(PARTS), rank, world, dist, device="cuda")
+    sm = sharding.PartitionShardedModel(pm, len(PARTS), rank, world, dist, device="cuda", in_model=False)
     res["parts_lh"] = sm.compute_lh(4, 0.6)
     res["parts_lh_root"] = sm.compute_lh_root(4, 0.2)
     res["parts_sweep"] = sm.sweep_root_lh()

@@ -133,8 +133,11 @@ def _partition_worker(rank, world, port, q):
     m.initialize_partitions(uniform_freqs=False)
     for j, p in enumerate(sharding.plan_partition_shards(len(PARTS), world)[rank]):
         m.set_params(rates=_rates_of(p), alpha=0.5 + p, part=j)
-    sm = sharding.PartitionShardedModel(m, len(PARTS), rank, world, dist)
-    out = [sm.compute_lh(3, 0.4), sm.compute_lh_root(3, 0.7)] + sm.sweep_root_lh().tolist()
+    out = []
+    for in_model in (False, True):  # the all-gather issued from Python / from inside model_t
+        sm = sharding.PartitionShardedModel(m, len(PARTS), rank, world, dist, in_model=in_model)
+        out += [sm.compute_lh(3, 0.4), sm.compute_lh_root(3, 0.7)] + sm.sweep_root_lh().tolist()
+        sm.close()
     if rank == 0:
         q.put(np.array(out))
     dist.destroy_process_group()
@@ -182,7 +185,131 @@ def test_two_rank_gloo_partition_sharding_matches_single_process():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
+    want = np.concatenate([want, want])
     assert np.array_equal(got.view(np.uint64), want.view(np.uint64))
+
+
+SEARCH_ARGS = dict(min_roots=2, root_ratio=0.05, atol=1e-3, pgtol=1e-3, brtol=1e-4, factor=1e12)
+EXHAUSTIVE_ARGS = (1e-2, 1e-2, 1e-3, 1e13)
+
+
+def _whole_model_results(m, strategy):
+    """what a run does with a multi-partition model, in order: initialisation (draws from the model's
+    generator), slopes and a position search on a branch, a search from ranked / shuffled starts,
+    exhaustive mode on a few branches"""
+    out = []
+    m.compute_lh(0, 0.5)
+    for rid, x in ((2, 0.3), (5, 1.0), (7, 0.0)):
+        m.compute_lh(rid, 0.5)
+        out += list(m.compute_dlh(rid, x))
+        out.append(m.optimize_alpha(rid, 0.5, 1e-9))
+    rid, alpha, lh = m.search(strategy=strategy, **SEARCH_ARGS)
+    out += [float(rid), alpha, lh]
+    m.set_max_outer_iterations(2)
+    ids, llh, al = m.exhaustive_search(*EXHAUSTIVE_ARGS, rank=0, num_tasks=6)
+    out += ids.astype(np.float64).tolist() + llh.tolist() + al.tolist() + m.lwr(llh).tolist()
+    return np.array(out)
+
+
+def _partition_search_worker(rank, world, port, strategy, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      OMP_NUM_THREADS="2")  # two ranks share the test machine
+    sys.path.insert(0, str(ROOT))
+    sys.path.insert(0, str(ROOT / "tests"))
+    import torch.distributed as dist
+    import fixtures
+    import oracle_capi
+    import oracle_build
+    from root_digger_b200 import capi
+    oracle_capi.load_oracle().rdo_set_default_mode(oracle_capi.MODE_ENGINE)
+    lib = capi.load_tree_lib(oracle_build.build_host_on_oracle())
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    fx = fixtures.load("10.fasta")
+    mine = [PARTS[p] for p in sharding.plan_partition_shards(len(PARTS), world)[rank]]
+    tree = capi.RootedTree(path=str(fx["tree_path"]), lib=lib)
+    m = capi.Model(tree, fx["alignment"], rate_cats=2, compress=True, seed=11, early_stop=True, partitions=mine)
+    sm = sharding.PartitionShardedModel(m, len(PARTS), rank, world, dist)
+    sm.initialize_partitions(uniform_freqs=False)
+    got = _whole_model_results(sm, strategy)
+    q.put((rank, got, sm.exchanges))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("strategy", ["random", "modified_mad"])
+def test_two_rank_gloo_partition_sharded_search_matches_single_process(strategy):
+    """SURVEY 8e-3 for the WHOLE of model_t: with the sums over partitions completed inside model_t
+    (set_partition_exchange), compute_dlh, optimize_alpha, search (ranked and shuffled starts -- the
+    shuffle needs the ranks' generators in step with a single process's) and exhaustive mode + LWR on
+    3 partitions dealt to 2 ranks return the bits of one process holding all three; every rank
+    reports the same values"""
+    import torch.multiprocessing as mp
+    import fixtures
+    import oracle_capi
+    import oracle_build
+    from root_digger_b200 import capi
+    oracle_capi.load_oracle().rdo_set_default_mode(oracle_capi.MODE_ENGINE)
+    lib = capi.load_tree_lib(oracle_build.build_host_on_oracle())
+    fx = fixtures.load("10.fasta")
+    tree = capi.RootedTree(path=str(fx["tree_path"]), lib=lib)
+    m = capi.Model(tree, fx["alignment"], rate_cats=2, compress=True, seed=11, early_stop=True, partitions=PARTS)
+    m.initialize_partitions(uniform_freqs=False)
+    want = _whole_model_results(m, strategy)
+    m.close()
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_partition_search_worker, args=(r, 2, port, strategy, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    import queue
+    results, waited = {}, 0
+    while len(results) < 2:
+        try:
+            r, v, n = q.get(timeout=5)
+            results[r] = (v, n)
+        except queue.Empty:
+            waited += 5
+            assert waited < 900 and all(p.exitcode in (None, 0) for p in procs), "a rank died"
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r in (0, 1):
+        got, exchanges = results[r]
+        assert np.array_equal(got.view(np.uint64), want.view(np.uint64)), (r, got, want)
+        assert exchanges > 20
+    assert results[0][1] == results[1][1], "both ranks took part in the same collectives"
+
+
+def test_partition_exchange_argument_checks():
+    """model_t::set_partition_exchange refuses layouts it cannot keep in step with a single process"""
+    import ctypes as C
+    import fixtures
+    import oracle_capi
+    import oracle_build
+    from root_digger_b200 import capi
+    oracle_capi.load_oracle().rdo_set_default_mode(oracle_capi.MODE_ENGINE)
+    lib = capi.load_tree_lib(oracle_build.build_host_on_oracle())
+    fx = fixtures.load("10.fasta")
+    m = capi.Model(capi.RootedTree(path=str(fx["tree_path"]), lib=lib), fx["alignment"], rate_cats=2, partitions=PARTS[:2])
+
+    class _Dist:  # never reached: the constructor must fail first
+        pass
+
+    with pytest.raises(ValueError, match="exactly this rank"):
+        sharding.PartitionShardedModel(m, 5, 0, 2, _Dist())   # rank 0 of 2 holds 3 of 5 partitions, not 2
+    with pytest.raises(ValueError, match="at most as many ranks"):
+        sharding.PartitionShardedModel(m, 2, 0, 3, _Dist())
+    fn_t = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.c_size_t, C.c_size_t, C.POINTER(C.c_double), C.c_void_p)
+    m.L.rdh_model_set_partition_exchange.argtypes = [C.c_void_p, C.POINTER(C.c_uint), C.c_uint, C.c_uint, fn_t, C.c_void_p]
+    cb = fn_t(lambda *a: None)
+    for idx, total in (((1, 0), 4), ((0, 4), 4), ((0,), 4)):  # decreasing; out of range; wrong count
+        arr = (C.c_uint * len(idx))(*idx)
+        assert m.L.rdh_model_set_partition_exchange(m.h, arr, len(idx), total, cb, None) == 0
+        assert b"global ind" in m.L.rdh_last_error() or b"one global index" in m.L.rdh_last_error()
+    m.close()
 
 
 def test_sweep_chunk_count_is_agreed_across_site_shards():
