@@ -425,6 +425,14 @@ double model_t::compute_lh(const root_location_t &root_location) {
 
 // src/model.cpp:415-452: the two root branches and the root CLV only
 double model_t::compute_lh_root(const root_location_t &root) {
+  const double lh = root_only_evaluation(root);
+  refuse_nan(lh);
+  return lh;
+}
+
+// the tree re-rooted at `root` on the host, then, per partition: the two root P-matrices, the root
+// CLV, the log-likelihood; summed over partitions.  NaN is the caller's to judge.
+double model_t::root_only_evaluation(const root_location_t &root) {
   rdk_operation_t           op;
   std::vector<unsigned int> matrix_indices;
   std::vector<double>       branch_lengths;
@@ -436,9 +444,7 @@ double model_t::compute_lh_root(const root_location_t &root) {
     terms[p] = root_loglikelihood(p);
   });
   _last_part_lh = terms;
-  const double lh = sum_over_partitions(terms);
-  refuse_nan(lh);
-  return lh;
+  return sum_over_partitions(terms);
 }
 
 // src/model.cpp:454-476: what the parameter optimiser evaluates, one partition at a time
@@ -514,18 +520,7 @@ std::vector<double> model_t::root_lh_on_branch(const root_location_t &root, cons
   if (!fused) {
     for (size_t i = 0; i < ratios.size(); ++i) {
       at.brlen_ratio = ratios[i];
-      rdk_operation_t           op;
-      std::vector<unsigned int> mi;
-      std::vector<double>       bl;
-      std::tie(op, mi, bl) = _tree.generate_derivative_operations(at);
-      std::vector<double> terms(_partitions.size(), 0.0);
-      for_each_partition(_partitions.size(), false, [&](size_t p) {
-        update_pmatrix_partition(p, mi, bl);
-        rdk_update_clvs(_partitions[p], &op, 1);
-        terms[p] = root_loglikelihood(p);
-      });
-      _last_part_lh = terms;
-      lh[i] = sum_over_partitions(terms);
+      lh[i] = root_only_evaluation(at);
     }
     return lh;
   }

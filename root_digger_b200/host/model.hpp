@@ -215,6 +215,7 @@ private:
   void   update_pmatrix_partition(size_t partition_index, const std::vector<unsigned int> &pmatrix_indices,
                                   const std::vector<double> &branch_lengths);
   double root_loglikelihood(size_t partition_index);
+  double root_only_evaluation(const root_location_t &root);
   // sum over ALL partitions, in global partition order, of terms[local partition][0..count)
   std::vector<double> sum_over_partitions(const std::vector<std::vector<double>> &terms, size_t count);
   double              sum_over_partitions(const std::vector<double> &terms);
