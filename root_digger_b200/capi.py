@@ -662,6 +662,42 @@ def slope_root(fn, lo: float, hi: float, x_tolerance: float = 1e-12, lib: C.CDLL
     return out[0], out[1], out[2], probes.value
 
 
+_BATCH_FN = C.CFUNCTYPE(None, _dp, C.c_int, _dp, C.c_void_p)
+
+
+def _batch_thunk(fn, log):
+    def thunk(xs, n, out, _user):
+        batch = [xs[i] for i in range(n)]
+        log.append(batch)
+        for i, x in enumerate(batch):
+            out[i] = fn(x)
+    return _BATCH_FN(thunk)
+
+
+def argmax_on_segment(fn, x_now: float, atol: float, look_ahead: bool = True, lib: C.CDLL | None = None):
+    """rd::unit_segment_search_t::argmax: the best position on [0, 1] by the sign of the slope of
+    `fn` (model_t::optimize_alpha without the tree, reference src/model.cpp:679-794), evaluations
+    handed over in batches (look_ahead) or one slope at a time.  Returns (x, [batches of abscissae])."""
+    L = lib or load_tree_lib()
+    L.rdh_optim_argmax_on_segment.argtypes = [_BATCH_FN, C.c_void_p, C.c_double, C.c_double, C.c_int, _dp, _up]
+    log = []
+    best = C.c_double(0.0)
+    if not L.rdh_optim_argmax_on_segment(_batch_thunk(fn, log), None, x_now, atol, 1 if look_ahead else 0,
+                                         C.byref(best), None):
+        raise RuntimeError(L.rdh_last_error().decode())
+    return best.value, log
+
+
+def slope_on_segment(fn, x: float, lib: C.CDLL | None = None):
+    """the forward-difference slope model_t::compute_dlh takes (src/model.cpp:481-519) -> (value, slope)"""
+    L = lib or load_tree_lib()
+    L.rdh_optim_slope_on_segment.argtypes = [_BATCH_FN, C.c_void_p, C.c_double, _dp]
+    out = (C.c_double * 2)()
+    if not L.rdh_optim_slope_on_segment(_batch_thunk(fn, []), None, x, out):
+        raise RuntimeError(L.rdh_last_error().decode())
+    return out[0], out[1]
+
+
 def minimize_in_box(fn, x0, lower: float, upper: float, pgtol: float = 1e-7, factr: float = 1e4,
                     lib: C.CDLL | None = None):
     """rd::minimize_in_box: L-BFGS-B with forward-difference gradients inside [lower, upper]^n

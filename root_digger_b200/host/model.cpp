@@ -491,7 +491,7 @@ std::vector<double> model_t::compute_all_root_lh() {
 // stages the 2 P-matrices of every candidate, evaluates them in one program and leaves the
 // partition untouched).  Sequential: the reference's call sequence, one compute_lh_root each.
 // Either way the host tree ends up rooted at the last ratio, as after the reference's calls, and
-// NaN is reported by the CONSUMER of a value (settle / optimize_alpha), in consumption order --
+// NaN is reported by the CONSUMER of a value (rd::unit_segment_search_t), in consumption order --
 // a batch may hold evaluations the decision never looks at.
 std::vector<double> model_t::root_lh_on_branch(const root_location_t &root, const std::vector<double> &ratios) {
   std::vector<double> lh(ratios.size(), 0.0);
@@ -537,121 +537,21 @@ std::vector<double> model_t::root_lh_on_branch(const root_location_t &root, cons
   return lh;
 }
 
-// A slope is a forward difference of step 1e-8 in the ratio, taken backwards where the step
-// would leave the branch (src/model.cpp:481-519, Appendix B-15).
-model_t::branch_probe_t model_t::probe_branch(const root_location_t &root, const std::vector<double> &values_at,
-                                              const std::vector<double> &slopes_at) {
-  constexpr double step = 1e-8;
-  branch_probe_t   out;
-  std::vector<double> ratios(values_at);
-  out.slopes.reserve(slopes_at.size());
-  for (double x : slopes_at) {
-    slope_probe_t s{x, 0.0, 0.0, 1.0};
-    double        shifted = x + step;
-    if (shifted >= 1.0) {
-      shifted = x - step;
-      s.sign = -1.0;
-    }
-    ratios.push_back(x);
-    ratios.push_back(shifted);
-    out.slopes.push_back(s);
-  }
-  const auto lh = root_lh_on_branch(root, ratios);
-  out.values.assign(lh.begin(), lh.begin() + (std::ptrdiff_t)values_at.size());
-  for (size_t i = 0; i < out.slopes.size(); ++i) {
-    out.slopes[i].fx = lh[values_at.size() + 2 * i];
-    out.slopes[i].fxh = lh[values_at.size() + 2 * i + 1];
-  }
-  return out;
-}
-
-// what the reference's compute_dlh makes of the two evaluations: NaN is an error, a branch that
-// is impossible at both points (-inf, -inf) is flat
-rd::slope_sample_t model_t::settle(const slope_probe_t &raw) {
-  constexpr double step = 1e-8;
-  refuse_nan(raw.fx);
-  refuse_nan(raw.fxh);
-  if (std::isinf(raw.fxh) && std::isinf(raw.fx)) return {raw.x, raw.fx, 0.0};
-  const double slope = (raw.fxh - raw.fx) / step;
-  return {raw.x, raw.fx, slope * raw.sign};
-}
-
+// compute_dlh (src/model.cpp:481-519) and optimize_alpha (:679-794) are rd::unit_segment_search_t
+// (optim.hpp) on this branch: a batch of abscissae is a batch of root positions.
 dlh_t model_t::compute_dlh(const root_location_t &root) {
-  const auto s = settle(probe_branch(root, {}, {root.brlen_ratio}).slopes[0]);
+  auto on_branch = rd::make_unit_segment_search(
+      [&](const std::vector<double> &ratios) { return root_lh_on_branch(root, ratios); }, refuse_nan, _batched_probes);
+  const auto s = on_branch.slope_at(root.brlen_ratio);
   return {s.value, s.slope};
 }
 
-// the root of the slope between two samples of opposite slope (reference brents, :606-676)
-rd::slope_sample_t model_t::refine_between(const root_location_t &root, const rd::slope_sample_t &lo,
-                                           const rd::slope_sample_t &hi, double atol) {
-  rd::brent_options_t opt;
-  opt.x_tolerance = atol;
-  return rd::slope_root_brent(lo, hi, opt,
-                              [&](double x) { return settle(probe_branch(root, {}, {x}).slopes[0]); });
-}
-
-// src/model.cpp:679-794.  Best position of the root on its branch by the sign of the slope:
-//   1. the log-likelihood where the root stands and value + slope at both ends   (one batch of 5)
-//   2. an end with a flat slope wins outright; ends of opposite slope bracket a root -> Brent
-//   3. same sign at both ends: look for a sign change on the dyadic grid 1/2; 1/4, 3/4; 1/8 ...
-//      31/32, level by level (one batch per level; the scan within a level keeps the
-//      reference's order, so a level's later points are evaluated speculatively), refine on both
-//      sides of the first change; otherwise the best flat grid point, else the end the slope
-//      points to.
 root_location_t model_t::optimize_alpha(const root_location_t &root, double atol) {
-  auto placed = [&root](double x) {
-    root_location_t rl{root};
-    rl.brlen_ratio = x;
-    return rl;
-  };
-  rd::slope_sample_t lo, hi;
-  if (_batched_probes) {
-    const auto first = probe_branch(root, {root.brlen_ratio}, {0.0, 1.0});
-    refuse_nan(first.values[0]);
-    lo = settle(first.slopes[0]);
-    hi = settle(first.slopes[1]);
-  } else {
-    refuse_nan(root_lh_on_branch(root, {root.brlen_ratio})[0]);
-    lo = settle(probe_branch(root, {}, {0.0}).slopes[0]);
-    hi = settle(probe_branch(root, {}, {1.0}).slopes[0]);
-  }
-  if (std::isnan(lo.slope) || std::isnan(hi.slope))
-    throw std::runtime_error("Initial derivatives failed when optimizing alpha: " +
-                             std::to_string(root.edge->length));
-
-  rd::slope_sample_t best_end = lo.value >= hi.value ? lo : hi;
-  if (std::fabs(lo.slope) < atol || std::fabs(hi.slope) < atol) return placed(best_end.x);
-
-  if ((lo.slope < 0.0 && hi.slope > 0.0) || (lo.slope > 0.0 && hi.slope < 0.0)) {
-    const auto inner = refine_between(root, lo, hi, atol);
-    return placed(best_end.value > inner.value ? best_end.x : inner.x);
-  }
-
-  const bool         rising = lo.slope > 0.0 && hi.slope > 0.0;
-  rd::slope_sample_t best_flat{0.0, -std::numeric_limits<double>::infinity(), 0.0};
-  bool               have_flat = false;
-  for (size_t cells = 2; cells <= 32; cells *= 2) {
-    std::vector<double> grid;
-    for (size_t k = 1; k <= cells; k += 2) grid.push_back(1.0 / (double)cells * k);
-    std::vector<slope_probe_t> level;
-    if (_batched_probes) level = probe_branch(root, {}, grid).slopes;
-    for (size_t j = 0; j < grid.size(); ++j) {
-      const auto here = settle(_batched_probes ? level[j] : probe_branch(root, {}, {grid[j]}).slopes[0]);
-      if (std::fabs(here.slope) < atol && best_flat.value < here.value) {
-        best_flat = here;
-        have_flat = true;
-      }
-      const bool turns = rising ? here.slope < 0.0 : here.slope > 0.0;
-      if (!turns) continue;
-      const auto left = refine_between(root, lo, here, atol);
-      const auto right = refine_between(root, here, hi, atol);
-      if (best_end.value < best_flat.value) best_end = best_flat;
-      const auto &inner = left.value < right.value ? right : left;
-      return placed(best_end.value >= inner.value ? best_end.x : inner.x);
-    }
-  }
-  if (have_flat) return placed(best_flat.x);
-  return placed(rising ? 1.0 : 0.0);
+  auto on_branch = rd::make_unit_segment_search(
+      [&](const std::vector<double> &ratios) { return root_lh_on_branch(root, ratios); }, refuse_nan, _batched_probes);
+  root_location_t best{root};
+  best.brlen_ratio = on_branch.argmax(root.brlen_ratio, atol, std::to_string(root.edge->length));
+  return best;
 }
 
 // src/model.cpp:796-821: the most likely placements of the sweep, each polished on its branch

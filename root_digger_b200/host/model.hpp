@@ -171,23 +171,11 @@ public:
   size_t           partition_count() const { return _partitions.size(); }
 
 private:
-  // ---- root position on a branch (model.cpp "position on the branch") ------------------------
-  // one batch of root-only evaluations on the branch of `root`: log-likelihoods at `values_at`,
-  // then forward-difference slope pairs at `slopes_at`, in that order, through ONE fused engine
-  // call per partition when batched probes are on (rdk_root_loglikelihood_multi)
-  struct slope_probe_t {
-    double x, fx, fxh, sign;
-  };
-  struct branch_probe_t {
-    std::vector<double>        values;
-    std::vector<slope_probe_t> slopes;
-  };
-  branch_probe_t    probe_branch(const root_location_t &root, const std::vector<double> &values_at,
-                                 const std::vector<double> &slopes_at);
+  // ---- root position on a branch ------------------------------------------------------------
+  // log-likelihoods of the tree rooted at `ratios` on root's branch: ONE fused engine call per
+  // partition when batched probes are on (rdk_root_loglikelihood_multi); compute_dlh and
+  // optimize_alpha are rd::unit_segment_search_t (optim.hpp) over this
   std::vector<double> root_lh_on_branch(const root_location_t &root, const std::vector<double> &ratios);
-  static rd::slope_sample_t settle(const slope_probe_t &raw);
-  rd::slope_sample_t        refine_between(const root_location_t &root, const rd::slope_sample_t &lo,
-                                           const rd::slope_sample_t &hi, double atol);
 
   // ---- parameter plumbing ----------------------------------------------------------------------
   void set_subst_rates_random(size_t, const msa_t &);

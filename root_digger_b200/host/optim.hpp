@@ -1,10 +1,12 @@
 // optim.hpp -- the two numerical optimisers model_t drives, as stand-alone components that know
 // nothing about trees or partitions:
 //
-//   rd::slope_root_brent   root of a derivative on a bracket (Brent's method on the slope), the
-//                          engine of model_t::optimize_alpha.  A "probe" is whatever the caller
-//                          uses to evaluate (value, slope) at x -- for model_t one batched pair of
-//                          root-only likelihood evaluations on the GPU.
+//   rd::slope_root_brent   root of a derivative on a bracket (Brent's method on the slope).  A
+//                          "probe" is whatever the caller uses to evaluate (value, slope) at x.
+//   rd::unit_segment_search_t
+//                          the best position on a segment by the sign of the slope, on batched
+//                          evaluations: model_t::optimize_alpha and compute_dlh without the tree
+//                          (for model_t a batch is one fused root-only evaluation call on the GPU).
 //   rd::lbfgsb_session_t   RAII face of the reverse-communication L-BFGS-B 3.0 routine (setulb),
 //   rd::minimize_in_box    and a box-constrained minimiser with forward-difference gradients on
 //                          top of it, the engine of model_t::optimize_params.
@@ -24,6 +26,7 @@
 #include <cstddef>
 #include <limits>
 #include <stdexcept>
+#include <string>
 #include <utility>
 #include <vector>
 
@@ -105,6 +108,145 @@ slope_sample_t slope_root_brent(slope_sample_t lo, slope_sample_t hi, const bren
     b = probe(x_next);
   }
   throw std::runtime_error("Brents method failed to converge");  // Q2
+}
+
+// ---------------------------------------------------------------------------------------------
+// the best position on a segment
+// ---------------------------------------------------------------------------------------------
+// Maximum of a function on [0, 1] located by the sign of its slope -- model_t::optimize_alpha and
+// compute_dlh (reference src/model.cpp:679-794, 481-519) without the tree: `evaluate(xs)` returns
+// the function at every abscissa of a batch (for model_t one fused engine call), `refuse(value)`
+// throws for a value the caller cannot work with (NaN) and is applied to the values a decision
+// actually CONSUMES, in consumption order -- a batch may hold evaluations made ahead of need.
+//
+//   slope      forward difference of step 1e-8, taken backwards where x + step would reach 1
+//              (Appendix B-15); two evaluations that are both infinite give a flat slope
+//   argmax     1. the value at the current position (only checked) and value + slope at 0 and 1
+//                 -- one batch of five evaluations
+//              2. an end whose slope is flat (|slope| < atol) ends the search: the better END wins;
+//                 slopes of opposite sign bracket a stationary point -> Brent on the slope, and
+//                 the better of that point and the better end wins
+//              3. same sign at both ends: scan the dyadic grid 1/2; 1/4, 3/4; 1/8 ... 31/32 level
+//                 by level for a slope of the other sign (one batch per level when looking ahead:
+//                 the later points of a level are evaluated speculatively), refine on both sides
+//                 of the first such point and take the best of the two refinements, the better
+//                 end and the best flat grid point seen so far; without a turn: the best flat
+//                 grid point, else the end the slope points to
+template <typename Evaluate, typename Refuse>
+class unit_segment_search_t {
+public:
+  struct raw_slope_t {
+    double x, fx, fxh, sign;
+  };
+
+  unit_segment_search_t(Evaluate evaluate, Refuse refuse, bool look_ahead, double step = 1e-8)
+      : _evaluate(std::move(evaluate)), _refuse(std::move(refuse)), _look_ahead(look_ahead), _step(step) {}
+
+  // values at `values_at`, then the evaluation pairs of the slopes at `slopes_at`: ONE batch
+  std::vector<raw_slope_t> probe(const std::vector<double> &values_at, const std::vector<double> &slopes_at,
+                                 std::vector<double> *values = nullptr) {
+    std::vector<double>      xs(values_at);
+    std::vector<raw_slope_t> raw;
+    raw.reserve(slopes_at.size());
+    for (double x : slopes_at) {
+      raw_slope_t r{x, 0.0, 0.0, 1.0};
+      double      partner = x + _step;
+      if (partner >= 1.0) {
+        partner = x - _step;
+        r.sign = -1.0;
+      }
+      xs.push_back(x);
+      xs.push_back(partner);
+      raw.push_back(r);
+    }
+    const std::vector<double> f = _evaluate(xs);
+    if (f.size() != xs.size()) throw std::logic_error("unit_segment_search_t: evaluate() returned a batch of another size");
+    if (values) values->assign(f.begin(), f.begin() + (std::ptrdiff_t)values_at.size());
+    for (size_t i = 0; i < raw.size(); ++i) {
+      raw[i].fx = f[values_at.size() + 2 * i];
+      raw[i].fxh = f[values_at.size() + 2 * i + 1];
+    }
+    return raw;
+  }
+
+  slope_sample_t settle(const raw_slope_t &raw) const {
+    _refuse(raw.fx);
+    _refuse(raw.fxh);
+    if (std::isinf(raw.fxh) && std::isinf(raw.fx)) return {raw.x, raw.fx, 0.0};
+    const double slope = (raw.fxh - raw.fx) / _step;
+    return {raw.x, raw.fx, slope * raw.sign};
+  }
+
+  slope_sample_t slope_at(double x) { return settle(probe({}, {x})[0]); }
+
+  slope_sample_t refine_between(const slope_sample_t &lo, const slope_sample_t &hi, double atol) {
+    brent_options_t opt;
+    opt.x_tolerance = atol;
+    return slope_root_brent(lo, hi, opt, [this](double x) { return slope_at(x); });
+  }
+
+  // `context` is appended to the message of the one failure that names the segment
+  double argmax(double x_now, double atol, const std::string &context = std::string()) {
+    slope_sample_t lo, hi;
+    if (_look_ahead) {
+      std::vector<double> now;
+      const auto          ends = probe({x_now}, {0.0, 1.0}, &now);
+      _refuse(now[0]);
+      lo = settle(ends[0]);
+      hi = settle(ends[1]);
+    } else {
+      _refuse(_evaluate(std::vector<double>{x_now})[0]);
+      lo = slope_at(0.0);
+      hi = slope_at(1.0);
+    }
+    if (std::isnan(lo.slope) || std::isnan(hi.slope))
+      throw std::runtime_error("Initial derivatives failed when optimizing alpha: " + context);
+
+    slope_sample_t best_end = lo.value >= hi.value ? lo : hi;
+    if (std::fabs(lo.slope) < atol || std::fabs(hi.slope) < atol) return best_end.x;
+
+    if ((lo.slope < 0.0 && hi.slope > 0.0) || (lo.slope > 0.0 && hi.slope < 0.0)) {
+      const auto inner = refine_between(lo, hi, atol);
+      return best_end.value > inner.value ? best_end.x : inner.x;
+    }
+
+    const bool     rising = lo.slope > 0.0 && hi.slope > 0.0;
+    slope_sample_t best_flat{0.0, -std::numeric_limits<double>::infinity(), 0.0};
+    bool           have_flat = false;
+    for (size_t cells = 2; cells <= 32; cells *= 2) {
+      std::vector<double> grid;
+      for (size_t k = 1; k <= cells; k += 2) grid.push_back(1.0 / (double)cells * k);
+      std::vector<raw_slope_t> level;
+      if (_look_ahead) level = probe({}, grid);
+      for (size_t j = 0; j < grid.size(); ++j) {
+        const auto here = _look_ahead ? settle(level[j]) : slope_at(grid[j]);
+        if (std::fabs(here.slope) < atol && best_flat.value < here.value) {
+          best_flat = here;
+          have_flat = true;
+        }
+        const bool turns = rising ? here.slope < 0.0 : here.slope > 0.0;
+        if (!turns) continue;
+        const auto left = refine_between(lo, here, atol);
+        const auto right = refine_between(here, hi, atol);
+        if (best_end.value < best_flat.value) best_end = best_flat;
+        const auto &inner = left.value < right.value ? right : left;
+        return best_end.value >= inner.value ? best_end.x : inner.x;
+      }
+    }
+    if (have_flat) return best_flat.x;
+    return rising ? 1.0 : 0.0;
+  }
+
+private:
+  Evaluate _evaluate;
+  Refuse   _refuse;
+  bool     _look_ahead;
+  double   _step;
+};
+
+template <typename Evaluate, typename Refuse>
+unit_segment_search_t<Evaluate, Refuse> make_unit_segment_search(Evaluate evaluate, Refuse refuse, bool look_ahead) {
+  return unit_segment_search_t<Evaluate, Refuse>(std::move(evaluate), std::move(refuse), look_ahead);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -43,6 +43,58 @@ int rdh_optim_slope_root(rdh_slope_fn fn, void *user, double lo, double hi, doub
   }
 }
 
+// the caller's function at xs[0..n) -> out[0..n): one batch
+typedef void (*rdh_batch_fn)(const double *xs, int n, double *out, void *user);
+
+// rd::unit_segment_search_t::argmax on [0, 1] (model_t::optimize_alpha without the tree); a NaN
+// value that a decision consumes fails with "lh at root is not a number".  *batches = calls of fn.
+int rdh_optim_argmax_on_segment(rdh_batch_fn fn, void *user, double x_now, double atol, int look_ahead,
+                                double *best_x, unsigned *batches) {
+  try {
+    unsigned calls = 0;
+    auto     search = rd::make_unit_segment_search(
+        [&](const std::vector<double> &xs) {
+          ++calls;
+          std::vector<double> out(xs.size(), 0.0);
+          fn(xs.data(), (int)xs.size(), out.data(), user);
+          return out;
+        },
+        [](double v) {
+          if (std::isnan(v)) throw std::runtime_error("lh at root is not a number: " + std::to_string(v));
+        },
+        look_ahead != 0);
+    *best_x = search.argmax(x_now, atol, "test segment");
+    if (batches) *batches = calls;
+    return 1;
+  } catch (const std::exception &e) {
+    rdh_set_error(e.what());
+    return 0;
+  }
+}
+
+// the forward-difference slope of rd::unit_segment_search_t at x; out = {value, slope}
+int rdh_optim_slope_on_segment(rdh_batch_fn fn, void *user, double x, double *out) {
+  try {
+    auto search = rd::make_unit_segment_search(
+        [&](const std::vector<double> &xs) {
+          std::vector<double> f(xs.size(), 0.0);
+          fn(xs.data(), (int)xs.size(), f.data(), user);
+          return f;
+        },
+        [](double v) {
+          if (std::isnan(v)) throw std::runtime_error("lh at root is not a number: " + std::to_string(v));
+        },
+        true);
+    const auto s = search.slope_at(x);
+    out[0] = s.value;
+    out[1] = s.slope;
+    return 1;
+  } catch (const std::exception &e) {
+    rdh_set_error(e.what());
+    return 0;
+  }
+}
+
 // box-constrained minimisation from x[0..n) (updated in place as minimize_in_box defines it);
 // *f_end = objective at the last point, *evaluations = objective calls
 int rdh_optim_minimize_in_box(rdh_objective_fn fn, void *user, double *x, int n, double lower, double upper,

@@ -131,3 +131,108 @@ def test_minimize_in_box_refuses_non_finite_objectives(lib):
 
     with pytest.raises(RuntimeError, match="not finite"):
         capi.minimize_in_box(fn, [0.5], 1e-4, 1.0, lib=lib)
+
+
+# ---------------------------------------------------------------------------------------------
+# rd::unit_segment_search_t against the restated reference (oracle/alpha_oracle.py)
+# ---------------------------------------------------------------------------------------------
+import alpha_oracle  # noqa: E402  (oracle/ is on the path through conftest)
+
+TAU = 2.0 * math.pi
+SURFACES = {
+    # name: (f, which branch of optimize_alpha it is there to reach)
+    "peak_0.3": (lambda x: -3.0 * (x - 0.3) ** 2 - 100.0, "bracket -> Brent"),
+    "peak_0.9": (lambda x: -40.0 * (x - 0.9) ** 2 - 5.0, "bracket -> Brent"),
+    "peak_tiny": (lambda x: -1e-3 * (x - 0.123456789) ** 2 - 7000.0, "bracket, small slopes"),
+    "log_like": (lambda x: 300.0 * math.log(0.2 + x) + 200.0 * math.log(1.3 - x) - 9000.0, "bracket -> Brent"),
+    "rising": (lambda x: 3.0 * x - 50.0, "same sign, no turn: upper end"),
+    "falling": (lambda x: -2.0 * x - 50.0, "same sign, no turn: lower end"),
+    "rising_turn_1/4": (lambda x: x + 0.3 * math.sin(2 * TAU * x) - 80.0, "same sign, turn at 1/4 (level 2)"),
+    "falling_turn_1/4": (lambda x: -(x + 0.3 * math.sin(2 * TAU * x)) - 80.0, "same sign, turn at 1/4 (level 2)"),
+    "rising_turn_inner_wins": (lambda x: 0.2 * x + 0.3 * math.sin(2 * TAU * x) - 80.0,
+                               "same sign, turn at 1/4, a refinement beats both ends"),
+    "rising_turn_1/16": (lambda x: x + 1.05 * math.sin(8 * TAU * x) / (8 * TAU) - 80.0,
+                         "same sign, turn only at 1/16 (level 16)"),
+    "flat": (lambda x: -123.0, "flat end"),
+    "cubic": (lambda x: (x - 0.5) ** 3 - 10.0, "same sign, flat grid point at 1/2, no turn"),
+    "impossible_below_0.3": (lambda x: -math.inf if x < 0.3 else -5.0 * (x - 0.6) ** 2 - 3.0,
+                             "-inf at both evaluations of the lower end: slope 0 there"),
+    "impossible_everywhere": (lambda x: -math.inf, "-inf everywhere"),
+    "valley": (lambda x: 4.0 * (x - 0.45) ** 2 - 20.0, "bracket around a MINIMUM: an end wins"),
+}
+
+
+def bits(x):
+    return np.float64(x).view(np.uint64)
+
+
+@pytest.mark.parametrize("name", sorted(SURFACES))
+@pytest.mark.parametrize("atol", [1e-7, 1e-14])
+def test_segment_search_is_the_reference_algorithm(lib, name, atol):
+    """one evaluation at a time (look_ahead off) the component IS the reference's call sequence: the
+    same abscissae in the same order and the same answer, bit for bit; with batches ahead of need the
+    answer is unchanged and the number of engine calls drops"""
+    f = SURFACES[name][0]
+    for x_now in (0.5, 0.0, 1.0):
+        want, xs = alpha_oracle.optimize_alpha(f, x_now, atol)
+        got, batches = capi.argmax_on_segment(f, x_now, atol, look_ahead=False, lib=lib)
+        flat = [x for b in batches for x in b]
+        assert bits(got) == bits(want), (name, got, want)
+        assert [bits(x) for x in flat] == [bits(x) for x in xs], name
+        assert all(len(b) <= 2 for b in batches)
+        ahead, batches_ahead = capi.argmax_on_segment(f, x_now, atol, look_ahead=True, lib=lib)
+        assert bits(ahead) == bits(want), (name, ahead, want)
+        assert len(batches_ahead) <= len(batches) - 2 and len(batches_ahead[0]) == 5
+        consumed = {bits(x) for x in xs}
+        assert consumed <= {bits(x) for b in batches_ahead for x in b}, "nothing the decision needs is skipped"
+
+
+def test_segment_search_reaches_every_branch(lib):
+    """the surfaces above do take the branches they are named for (read off the evaluation log)"""
+    def log_of(name, atol=1e-7):
+        return alpha_oracle.optimize_alpha(SURFACES[name][0], 0.5, atol)
+
+    assert len(log_of("flat")[1]) == 5 and log_of("flat")[0] == 0.0
+    assert log_of("impossible_everywhere") == (0.0, [0.5, 0.0, 1e-8, 1.0, 1.0 - 1e-8])
+    x, xs = log_of("rising")
+    assert x == 1.0 and len(xs) == 5 + 2 * 31          # the whole grid, then the upper end
+    x, xs = log_of("falling")
+    assert x == 0.0 and len(xs) == 5 + 2 * 31
+    x, xs = log_of("cubic")
+    assert x == 0.5 and len(xs) == 5 + 2 * 31          # the flat grid point wins
+    x, xs = log_of("rising_turn_1/4")
+    assert xs[5:9] == [0.5, 0.5 + 1e-8, 0.25, 0.25 + 1e-8] and x == 1.0 and len(xs) > 9   # the upper end wins
+    x, xs = log_of("rising_turn_inner_wins")
+    assert xs[7] == 0.25 and 0.0 < x < 1.0 and abs(0.2 + 0.6 * TAU * math.cos(2 * TAU * x)) < 1e-5
+    x, xs = log_of("rising_turn_1/16")
+    assert xs[5 + 2 * 7] == 1.0 / 16.0 and len(xs) > 5 + 2 * 8   # 1 + 2 + 4 grid points before level 16
+    x, xs = log_of("valley")
+    assert x in (0.0, 1.0) and len(xs) > 5
+    x, xs = log_of("peak_0.3", 1e-14)
+    assert abs(x - 0.3) < 1e-7 and 5 < len(xs) < 5 + 2 * 64
+
+
+@pytest.mark.parametrize("x", [0.0, 0.25, 1.0 - 1e-8, 1.0 - 0.5e-8, 1.0])
+def test_slope_is_the_reference_forward_difference(lib, x):
+    for name in ("log_like", "peak_0.9", "impossible_below_0.3", "impossible_everywhere"):
+        f = SURFACES[name][0]
+        want = alpha_oracle.compute_dlh(alpha_oracle.Trace(f), x)
+        got = capi.slope_on_segment(f, x, lib=lib)
+        assert [bits(v) for v in got] == [bits(v) for v in want], (name, x, got, want)
+
+
+def test_segment_search_reports_nan_only_where_the_reference_would(lib):
+    bad_at_end = lambda x: math.nan if x > 0.9 else -x  # noqa: E731
+    with pytest.raises(alpha_oracle.NotANumber):
+        alpha_oracle.optimize_alpha(bad_at_end, 0.5, 1e-7)
+    for ahead in (False, True):
+        with pytest.raises(RuntimeError, match="not a number"):
+            capi.argmax_on_segment(bad_at_end, 0.5, 1e-7, look_ahead=ahead, lib=lib)
+    # NaN at 3/4 only: the scan of level 2 turns at 1/4 and never gets there -- the batch that
+    # evaluated 3/4 ahead of need must not fail either
+    base = SURFACES["rising_turn_1/4"][0]
+    poisoned = lambda x: math.nan if abs(x - 0.75) < 3e-8 else base(x)  # noqa: E731
+    want, xs = alpha_oracle.optimize_alpha(poisoned, 0.5, 1e-7)
+    assert all(abs(x - 0.75) > 3e-8 for x in xs)
+    got, batches = capi.argmax_on_segment(poisoned, 0.5, 1e-7, look_ahead=True, lib=lib)
+    assert bits(got) == bits(want) and any(abs(x - 0.75) < 3e-8 for b in batches for x in b)
