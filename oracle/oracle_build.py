@@ -5,6 +5,8 @@ this; the product package (root_digger_b200/) never imports it.
   oracle/librd_oracle.so             oracle/Makefile
   oracle/alpha_oracle.py             (pure Python, nothing to build) the reference's search for the root
                                      position on a branch, restated over any function on [0, 1]
+  oracle/bfgs_oracle.py              (pure Python) the reference's L-BFGS-B driver bfgs_params, restated
+                                     around the reference's own setulb over any objective
   tests/_build/librd_host_oracle.so  root_digger_b200/host/*.cpp compiled against the oracle
                                      through tests/oracle_shim/rdk.h (-DRD_BACKEND_ORACLE)
   oracle/_ref/librd_reference_on_{oracle,engine}.so

@@ -236,3 +236,40 @@ def test_segment_search_reports_nan_only_where_the_reference_would(lib):
     assert all(abs(x - 0.75) > 3e-8 for x in xs)
     got, batches = capi.argmax_on_segment(poisoned, 0.5, 1e-7, look_ahead=True, lib=lib)
     assert bits(got) == bits(want) and any(abs(x - 0.75) < 3e-8 for b in batches for x in b)
+
+
+# ---------------------------------------------------------------------------------------------
+# rd::minimize_in_box against the restated reference driver (oracle/bfgs_oracle.py)
+# ---------------------------------------------------------------------------------------------
+import bfgs_oracle  # noqa: E402
+
+OBJECTIVES = {
+    "quadratic": (lambda v: sum((a - t) ** 2 for a, t in zip(v, (0.3, 0.7, 0.55))), [0.5, 0.5, 0.5], 1e-4, 1.0),
+    "rosenbrock": (lambda v: (1 - v[0]) ** 2 + 100.0 * (v[1] - v[0] ** 2) ** 2, [0.2, 0.9], 1e-4, 1e4),
+    "at_the_bound": (lambda v: sum((a - 2.0) ** 2 for a in v), [0.5, 0.25], 0.2, 1.0),
+    "neg_log_like": (lambda v: -(300 * math.log(v[0] / sum(v)) + 500 * math.log(v[1] / sum(v))
+                                 + 200 * math.log(v[2] / sum(v))), [1 / 3, 1 / 3, 1 / 3], 1e-4, 1.0 - 3e-4),
+    "twelve_rates": (lambda v: sum((math.log(a) - math.log(0.05 * (i + 1))) ** 2 for i, a in enumerate(v)) - 9000.0,
+                     [1.0 / 12] * 12, 1e-4, 1e4),
+    "gets_worse": (lambda v: -abs(v[0] - 0.5) * 0.0 + (0.0 if v[0] == 0.5 else 1.0 + v[0]), [0.5], 1e-4, 1.0),
+}
+
+
+@pytest.mark.parametrize("name", sorted(OBJECTIVES))
+@pytest.mark.parametrize("pgtol,factr", [(1e-7, 1e4), (1e-3, 1e12)])
+def test_minimize_in_box_is_the_reference_driver(lib, name, pgtol, factr):
+    """the same points evaluated in the same order, the same vector handed back and the same final
+    objective as the reference's bfgs_params (src/model.cpp:1430-1522) around the same setulb"""
+    from root_digger_b200 import _build
+    fn, x0, lo, hi = OBJECTIVES[name]
+    want_f, want_x, want_trace = bfgs_oracle.bfgs_params(_build.build_lbfgsb(), x0, lo, hi, 1e-4, pgtol, factr, fn)
+    seen = []
+
+    def logged(v):
+        seen.append(v.tolist())
+        return fn(v.tolist())
+
+    x, f_end, calls = capi.minimize_in_box(logged, x0, lo, hi, pgtol=pgtol, factr=factr, lib=lib)
+    as_bits = lambda rows: [[bits(a) for a in r] for r in rows]  # noqa: E731
+    assert calls == len(want_trace) and as_bits(seen) == as_bits(want_trace), name
+    assert bits(f_end) == bits(want_f) and [bits(a) for a in x] == [bits(a) for a in want_x], name
