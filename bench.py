@@ -687,6 +687,7 @@ def exhaustive_sample(m, branches: int, tol=(1e-7, 1e-7, 1e-12, 1e4), stats=None
         np.array_equal(np.array(alphas["us_per_optimize_alpha"]).view(np.uint64),
                        np.array(alphas["us_per_optimize_alpha_unbatched"]).view(np.uint64)))
     m.set_batched_probes(was)
+    out["root_only_evaluations"] = m.probe_counters()  # fused batches / evaluations in them / issued singly
     return out
 
 

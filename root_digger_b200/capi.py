@@ -1038,6 +1038,14 @@ class Model:
     def batched_probes(self) -> bool:
         return bool(self.L.rdh_model_batched_probes(self.h))
 
+    def probe_counters(self) -> dict:
+        """root-only evaluations so far: fused batches, evaluations inside them, evaluations issued singly"""
+        out = (C.c_ulonglong * 3)()
+        self.L.rdh_model_probe_counters.argtypes = [C.c_void_p, C.POINTER(C.c_ulonglong)]
+        self.L.rdh_model_probe_counters.restype = None
+        self.L.rdh_model_probe_counters(self.h, out)
+        return {"fused_batches": int(out[0]), "fused_evaluations": int(out[1]), "single_evaluations": int(out[2])}
+
     SWEEP_SEQUENTIAL, SWEEP_PATH, SWEEP_DIRECTED = 0, 1, 2
 
     def set_sweep_mode(self, mode: int):

@@ -444,6 +444,7 @@ double model_t::root_only_evaluation(const root_location_t &root) {
     terms[p] = root_loglikelihood(p);
   });
   _last_part_lh = terms;
+  _probe_counters.single_evaluations++;
   return sum_over_partitions(terms);
 }
 
@@ -531,6 +532,8 @@ std::vector<double> model_t::root_lh_on_branch(const root_location_t &root, cons
                                      lengths.data(), (unsigned)ratios.size(), terms[p].data()) == RDK_FAILURE)
       throw std::runtime_error(engine_error());
   });
+  _probe_counters.fused_batches++;
+  _probe_counters.fused_evaluations += ratios.size();
   lh = sum_over_partitions(terms, ratios.size());  // partition order, as compute_lh_root adds them
   _last_part_lh.resize(_partitions.size());
   for (size_t p = 0; p < _partitions.size(); ++p) _last_part_lh[p] = terms[p].back();

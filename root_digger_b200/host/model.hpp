@@ -166,6 +166,12 @@ public:
   // decisions; off = the reference's call sequence (RD_BATCHED_PROBES=0 in the environment).
   void set_batched_probes(bool on) { _batched_probes = on; }
   bool batched_probes() const { return _batched_probes; }
+  // what the position searches cost so far: fused batches issued, root-only evaluations inside
+  // them, and root-only evaluations issued one by one (compute_lh_root included)
+  struct probe_counters_t {
+    unsigned long long fused_batches = 0, fused_evaluations = 0, single_evaluations = 0;
+  };
+  const probe_counters_t &probe_counters() const { return _probe_counters; }
 
   rdk_partition_t *partition(size_t i) { return _partitions[i]; }
   size_t           partition_count() const { return _partitions.size(); }
@@ -233,6 +239,7 @@ private:
   unsigned int                           _sweep_chunks = 1;  // independent chunks of a directed sweep
   size_t                                 _max_outer_iterations = 1000;
   bool                                   _batched_probes = true;  // see set_batched_probes
+  probe_counters_t                       _probe_counters;
   partition_exchange_fn                  _exchange = nullptr;     // see set_partition_exchange
   void                                  *_exchange_user = nullptr;
   std::vector<size_t>                    _global_index;           // global id of each local partition

@@ -191,6 +191,13 @@ extern "C" int rdh_model_set_batched_probes(void *h, int on) {
   return 1;
 }
 extern "C" int rdh_model_batched_probes(void *h) { return H(h).model->batched_probes() ? 1 : 0; }
+// out[0..3) = fused batches, root-only evaluations inside them, root-only evaluations issued singly
+extern "C" void rdh_model_probe_counters(void *h, unsigned long long *out) {
+  const auto &c = H(h).model->probe_counters();
+  out[0] = c.fused_batches;
+  out[1] = c.fused_evaluations;
+  out[2] = c.single_evaluations;
+}
 
 // partitions dealt to several processes (model_t::set_partition_exchange): this process holds the
 // partitions global_index[0..n_local) of global_partitions; `exchange` completes every sum over

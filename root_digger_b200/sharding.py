@@ -265,6 +265,14 @@ class PartitionShardedModel:
     def exhaustive_search(self, *a, **kw):
         return self._call(self.m.exhaustive_search, *a, **kw)
 
+    def set_checkpoint(self, prefix):
+        """every rank logs the results with the parameters of ITS partitions: one file per rank
+        ("<prefix>.part<rank>of<nranks>.ckp"), never a shared one -- a record read back by another
+        rank would carry the wrong partitions' parameters"""
+        if prefix is not None:
+            prefix = "%s.part%dof%d" % (prefix, self.rank, self.nranks)
+        return self.m.set_checkpoint(prefix)
+
     def __getattr__(self, name):
         # settings and accessors without a sum over partitions (set_max_outer_iterations, set_checkpoint,
         # set_batched_probes, root_count, lwr, ...) are the local model's

@@ -87,6 +87,12 @@ def test_batched_probes_have_the_bits_of_the_reference_call_sequence(lib):
                 assert a.optimize_alpha(rid, start, atol).hex() == b.optimize_alpha(rid, start, atol).hex()
                 # what follows an optimize_alpha in both drivers: the root-only evaluation there
                 assert a.compute_lh_root(rid, 0.3).hex() == b.compute_lh_root(rid, 0.3).hex()
+        # the batched model did batch (a slope is one call of 2, the first decision of optimize_alpha
+        # one call of 5); the other issued every evaluation on its own
+        ca, cb = a.probe_counters(), b.probe_counters()
+        assert ca["fused_batches"] > 0 and ca["fused_evaluations"] >= 2 * ca["fused_batches"]
+        # (evaluations made ahead of need can only add to the batched count)
+        assert cb["fused_batches"] == 0 and cb["single_evaluations"] <= ca["single_evaluations"] + ca["fused_evaluations"]
         a.close()
         b.close()
 
