@@ -7,16 +7,15 @@
 
 void rdh_set_error(const std::string &s);
 
-extern "C" {
 // value and slope of the caller's function at x
-typedef void (*rdh_slope_fn)(double x, double *value, double *slope, void *user);
+extern "C" typedef void (*rdh_slope_fn)(double x, double *value, double *slope, void *user);
 // the caller's objective at x[0..n)
-typedef double (*rdh_objective_fn)(const double *x, int n, void *user);
+extern "C" typedef double (*rdh_objective_fn)(const double *x, int n, void *user);
 
 // root of the slope between lo and hi (slopes of opposite sign there); out = {x, value, slope},
 // *probes = evaluations spent after the two end points
-int rdh_optim_slope_root(rdh_slope_fn fn, void *user, double lo, double hi, double x_tolerance, double *out,
-                         unsigned *probes) {
+extern "C" int rdh_optim_slope_root(rdh_slope_fn fn, void *user, double lo, double hi, double x_tolerance,
+                                    double *out, unsigned *probes) {
   try {
     unsigned spent = 0;
     auto     sample = [&](double x) {
@@ -44,12 +43,12 @@ int rdh_optim_slope_root(rdh_slope_fn fn, void *user, double lo, double hi, doub
 }
 
 // the caller's function at xs[0..n) -> out[0..n): one batch
-typedef void (*rdh_batch_fn)(const double *xs, int n, double *out, void *user);
+extern "C" typedef void (*rdh_batch_fn)(const double *xs, int n, double *out, void *user);
 
 // rd::unit_segment_search_t::argmax on [0, 1] (model_t::optimize_alpha without the tree); a NaN
 // value that a decision consumes fails with "lh at root is not a number".  *batches = calls of fn.
-int rdh_optim_argmax_on_segment(rdh_batch_fn fn, void *user, double x_now, double atol, int look_ahead,
-                                double *best_x, unsigned *batches) {
+extern "C" int rdh_optim_argmax_on_segment(rdh_batch_fn fn, void *user, double x_now, double atol,
+                                           int look_ahead, double *best_x, unsigned *batches) {
   try {
     unsigned calls = 0;
     auto     search = rd::make_unit_segment_search(
@@ -73,7 +72,7 @@ int rdh_optim_argmax_on_segment(rdh_batch_fn fn, void *user, double x_now, doubl
 }
 
 // the forward-difference slope of rd::unit_segment_search_t at x; out = {value, slope}
-int rdh_optim_slope_on_segment(rdh_batch_fn fn, void *user, double x, double *out) {
+extern "C" int rdh_optim_slope_on_segment(rdh_batch_fn fn, void *user, double x, double *out) {
   try {
     auto search = rd::make_unit_segment_search(
         [&](const std::vector<double> &xs) {
@@ -97,8 +96,9 @@ int rdh_optim_slope_on_segment(rdh_batch_fn fn, void *user, double x, double *ou
 
 // box-constrained minimisation from x[0..n) (updated in place as minimize_in_box defines it);
 // *f_end = objective at the last point, *evaluations = objective calls
-int rdh_optim_minimize_in_box(rdh_objective_fn fn, void *user, double *x, int n, double lower, double upper,
-                              double pgtol, double factr, double *f_end, unsigned *evaluations) {
+extern "C" int rdh_optim_minimize_in_box(rdh_objective_fn fn, void *user, double *x, int n, double lower,
+                                         double upper, double pgtol, double factr, double *f_end,
+                                         unsigned *evaluations) {
   try {
     unsigned                    calls = 0;
     std::vector<double>         v(x, x + n);
@@ -119,5 +119,4 @@ int rdh_optim_minimize_in_box(rdh_objective_fn fn, void *user, double *x, int n,
     rdh_set_error(e.what());
     return 0;
   }
-}
 }

@@ -26,6 +26,35 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
     assert b"sm_100a" in L.rdk_version()
 
 
+def test_host_library_header_is_current_and_every_declared_symbol_is_exported():
+    """include/rdh.h (the host-side operator interface: rooted_tree_t, checkpoint_t, model_t, the
+    optimiser components behind opaque handles) is generated from the extern "C" definitions; the
+    committed text must be what the generator writes now, and both builds of the host library --
+    on the CUDA engine and on the oracle -- must export every function it declares"""
+    import subprocess
+    import sys
+    import oracle_build
+    from root_digger_b200 import _build
+    root = Path(__file__).resolve().parent.parent
+    assert subprocess.run([sys.executable, str(root / "tools" / "gen_rdh_header.py"), "--check"]).returncode == 0, \
+        "include/rdh.h is stale: run python tools/gen_rdh_header.py"
+    text = re.sub(r"/\*.*?\*/", "", (root / "include" / "rdh.h").read_text(), flags=re.S)
+    names = sorted(set(re.findall(r"\b(rdh_[a-z0-9_]+)\s*\(", text)))
+    assert len(names) >= 85
+    for path in (_build.build_host(), oracle_build.build_host_on_oracle()):
+        out = subprocess.run(["nm", "-D", "--defined-only", str(path)], capture_output=True, text=True, check=True).stdout
+        exported = set(line.split()[-1] for line in out.splitlines() if line.strip())
+        missing = [n for n in names if n not in exported]
+        assert not missing, (path, missing)
+        undeclared = sorted(e for e in exported if e.startswith("rdh_") and e not in names)
+        assert not undeclared, (path, undeclared)
+    # the header is plain C
+    for compiler, lang in (("gcc", "c"), ("g++", "c++")):
+        r = subprocess.run([compiler, "-fsyntax-only", "-I", str(root / "include"), "-x", lang, str(root / "include" / "rdh.h")],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+
+
 def test_struct_layouts_match_the_header():
     assert C.sizeof(capi.Operation) == 32                      # 8 x 4-byte fields, corax_operation_t
     assert [f[0] for f in capi.Operation._fields_] == re.findall(
