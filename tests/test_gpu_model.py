@@ -137,3 +137,25 @@ def test_multi_partition_model(libs):
     for rid in (0, 5, 11):
         assert g.compute_lh(rid).hex() == o.compute_lh(rid).hex()
         assert g.compute_lh_root(rid, 0.25).hex() == o.compute_lh_root(rid, 0.25).hex()
+
+
+def test_batched_root_only_evaluations_on_the_engine(libs):
+    """DESIGN 5.5 on the CUDA engine: compute_dlh / optimize_alpha with their root-only evaluations
+    handed over as fused batches (rdk_root_loglikelihood_multi: 2 per slope, 5 before the first
+    decision of optimize_alpha, a whole dyadic level) and issued one by one (the reference's call
+    sequence, src/model.cpp:481-519,679-794) return the same bits, and the batched model did batch"""
+    g, _ = synthetic_pair(libs, n=20, S=2500, K=4, seed=21)
+    g.compute_lh(0)
+    assert g.batched_probes
+    for rid in range(0, g.root_count, 3):
+        got = {}
+        for batched in (True, False):
+            g.set_batched_probes(batched)
+            g.compute_lh(rid)
+            got[batched] = [v for x in (0.0, 0.37, 1.0) for v in g.compute_dlh(rid, x)]
+            got[batched] += [g.optimize_alpha(rid, 0.5, atol) for atol in (1e-7, 1e-14)]
+            got[batched].append(g.compute_lh_root(rid, 0.3))
+        assert np.array_equal(bits(got[True]), bits(got[False])), rid
+    c = g.probe_counters()
+    assert c["fused_batches"] > 0 and c["fused_evaluations"] >= 2 * c["fused_batches"]
+    g.close()
