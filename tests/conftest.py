@@ -23,7 +23,21 @@ def _has_gpu() -> bool:
         return False
 
 
+# GPU tests run from the bottom of the stack up: the kernels against the oracle through the C ABI
+# first (the parity tests proper), then the full-size properties, then model_t on the engine, the
+# reference's own sources on the engine, and the multi-GPU runs last -- a run stopped at its first
+# failure (-x) has then covered everything below the layer that failed.
+GPU_ORDER = ["test_gpu_parity", "test_gpu_fullsize", "test_gpu_model", "test_gpu_reference_sources",
+             "test_gpu_multi", "test_gpu_zz_partition_exchange"]
+
+
+def _gpu_rank(item) -> int:
+    name = Path(str(item.fspath)).stem
+    return GPU_ORDER.index(name) if name in GPU_ORDER else -1  # everything else keeps its place in front
+
+
 def pytest_collection_modifyitems(config, items):
+    items.sort(key=_gpu_rank)  # stable: the order inside a file is kept
     if _has_gpu():
         return
     skip = pytest.mark.skip(reason="no CUDA device in this container")
