@@ -313,6 +313,38 @@ def test_degenerate_operand_patterns():
     assert any(fl & F["Nop"] and not fl & F["EvalV"] for fl, *_ in prog)  # the read-after-write guard
 
 
+@pytest.mark.parametrize("count", [1, 2, 5, 32])
+@pytest.mark.parametrize("tip_children", [0, 1, 2])
+def test_batched_root_evaluations_touch_nothing(count, tip_children):
+    """the program rdk_root_loglikelihood_multi records (model_t::probe batches, DESIGN 5.5): `count`
+    evaluations of ONE root operation, each with its own pair of P slots and its own result slot, no
+    store at all -- every evaluation is the root term of its candidate and memory is left as it was,
+    whether the root's children are inner CLVs, a tip and an inner CLV, or two tips"""
+    rng = random.Random(100 + count)
+    tips = 6
+    ops, n_clv, n_sc = random_tree_ops(rng, tips, with_eval=False)
+    inner = [o[0] for o in ops]
+    if tip_children == 0:
+        c1, c2 = inner[-1], inner[-2]
+    elif tip_children == 1:
+        c1, c2 = 2, inner[-1]
+    else:
+        c1, c2 = 0, 3
+    sc_of = {o[0]: o[1] for o in ops}
+    root, root_sc = n_clv, n_sc
+    batch = [(root, root_sc, c1, c2, sc_of.get(c1, -1), sc_of.get(c2, -1), 100 + 2 * b, 101 + 2 * b, R_EVAL, b)
+             for b in range(count)]
+    ref, low = Mem(tips, n_clv + 1, n_sc + 1), Mem(tips, n_clv + 1, n_sc + 1)
+    for mem in (ref, low):  # the traversal ran earlier: its CLVs are resident
+        run_reference(mem, ops)
+    before = (dict(low.clv), dict(low.sc))
+    prog, _ = lower(tips, batch)
+    want, got = run_reference(ref, batch), run_lowered(low, prog)
+    assert got == want and len(got) == count
+    assert (low.clv, low.sc) == before, "a batch of evaluations stores nothing"
+    assert not any(fl & (F["Write"] | F["WriteS"]) for fl, *_ in prog)
+
+
 # ---- subtree groups (rdk_partition_set_subtree_groups) ------------------------------------------------
 def lower_grouped(tips, ops, n_groups, cap, discard=False):
     L = capi.load_engine()
