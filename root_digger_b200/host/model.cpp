@@ -304,6 +304,52 @@ std::vector<partition_parameters_t> model_t::fresh_parameters() {
   return params;
 }
 
+// The parameters of ALL partitions, in global order, for the checkpoint record of a start: on
+// partition shards every rank contributes the blocks it fitted (12 rates, 4 frequencies, the Gamma
+// shape) through the same exchange that completes the log-likelihood sums, so every rank's log
+// holds complete records in the reference's format.
+std::vector<partition_parameters_t> model_t::parameters_of_all_partitions(
+    const std::vector<partition_parameters_t> &mine) {
+  if (!_exchange) return mine;
+  size_t rates = 0, freqs = 0, shape = 0;
+  if (!mine.empty()) {
+    rates = mine[0].subst_rates.size();
+    freqs = mine[0].freqs.size();
+    shape = mine[0].gamma_alpha.size();
+  }
+  const size_t                     width = rates + freqs + shape;
+  std::vector<std::vector<double>> rows;
+  for (const auto &pp : mine) {
+    if (pp.subst_rates.size() != rates || pp.freqs.size() != freqs || pp.gamma_alpha.size() != shape ||
+        !pp.gamma_weights.empty())
+      throw std::logic_error("partition shards: parameter blocks of one shape per partition are expected");
+    std::vector<double> row(pp.subst_rates);
+    row.insert(row.end(), pp.freqs.begin(), pp.freqs.end());
+    row.insert(row.end(), pp.gamma_alpha.begin(), pp.gamma_alpha.end());
+    rows.push_back(std::move(row));
+  }
+  std::vector<double> local(rows.size() * width), all(_global_partitions * width, 0.0);
+  for (size_t p = 0; p < rows.size(); ++p) std::copy(rows[p].begin(), rows[p].end(), local.begin() + (std::ptrdiff_t)(p * width));
+  _exchange(local.data(), rows.size(), width, all.data(), _exchange_user);
+  std::vector<partition_parameters_t> out(_global_partitions);
+  for (size_t g = 0; g < _global_partitions; ++g) {
+    const double *row = all.data() + g * width;
+    out[g].subst_rates.assign(row, row + rates);
+    out[g].freqs.assign(row + rates, row + rates + freqs);
+    out[g].gamma_alpha.assign(row + rates + freqs, row + width);
+  }
+  return out;
+}
+
+// ... and back: the blocks of the partitions held here, out of a complete record
+std::vector<partition_parameters_t> model_t::parameters_held_here(const std::vector<partition_parameters_t> &all) const {
+  if (!_exchange || all.size() != _global_partitions) return all;
+  std::vector<partition_parameters_t> mine;
+  mine.reserve(_global_index.size());
+  for (size_t g : _global_index) mine.push_back(all[g]);
+  return mine;
+}
+
 // ---------------------------------------------------------------------------
 // evaluation
 // ---------------------------------------------------------------------------
@@ -833,7 +879,7 @@ std::pair<root_location_t, double> model_t::search(size_t min_roots, double root
       if (stayed || converged) break;
       at = kept.where;
     }
-    checkpoint.write({kept.where.id, kept.lh, kept.where.brlen_ratio}, params);
+    checkpoint.write({kept.where.id, kept.lh, kept.where.brlen_ratio}, parameters_of_all_partitions(params));
   }
 
   std::pair<root_location_t, double> best{root_location_t{}, -std::numeric_limits<double>::infinity()};
@@ -841,7 +887,7 @@ std::pair<root_location_t, double> model_t::search(size_t min_roots, double root
   if (!all.empty()) {
     const auto &top = all[most_likely(all)];
     best = placement_of(top.first);
-    set_model_params(top.second);
+    set_model_params(parameters_held_here(top.second));
   }
   if (!_assigned_idx.empty()) move_root(best.first);
   return best;
@@ -872,7 +918,7 @@ std::pair<root_location_t, double> model_t::exhaustive_search(double atol, doubl
       if (stayed || small_gain) break;
       at = polished;
     }
-    checkpoint.write({kept.where.id, kept.lh, kept.where.brlen_ratio}, params);
+    checkpoint.write({kept.where.id, kept.lh, kept.where.brlen_ratio}, parameters_of_all_partitions(params));
   }
 
   std::pair<root_location_t, double> best{root_location_t{}, -std::numeric_limits<double>::infinity()};

@@ -132,7 +132,8 @@ public:
   // terms of ALL partitions [global partition][count]; they are then added in global partition
   // order, the order a single process uses, so search / exhaustive_search take the same decisions
   // on every rank and return the bits of a single-process run.  The model's random generator is
-  // kept in step with a single process (one draw per GLOBAL partition in initialize_partitions*).
+  // kept in step with a single process (one draw per GLOBAL partition in initialize_partitions*),
+  // and the checkpoint records carry the parameters of ALL partitions (gathered the same way).
   typedef void (*partition_exchange_fn)(const double *local_terms, size_t local_partitions, size_t count,
                                         double *all_terms, void *user);
   void set_partition_exchange(const std::vector<size_t> &global_index, size_t global_partitions,
@@ -197,6 +198,8 @@ private:
   template <typename PerPartition> void for_each_partition_in_global_order(PerPartition &&body);
   void reset_to_defaults();  // rates 1/12, empirical frequencies (what every start begins from)
   std::vector<partition_parameters_t> fresh_parameters();
+  std::vector<partition_parameters_t> parameters_of_all_partitions(const std::vector<partition_parameters_t> &mine);
+  std::vector<partition_parameters_t> parameters_held_here(const std::vector<partition_parameters_t> &all) const;
   partition_parameters_t make_partition_parameters(size_t states, rate_category rc, size_t rate_cat_count);
 
   // ---- evaluation ------------------------------------------------------------------------------

@@ -259,16 +259,17 @@ class PartitionShardedModel:
     def search(self, *a, **kw):
         """model_t::search over ALL partitions; every rank runs every start (rank / num_tasks of the
         local model stay 0 / 1: the partitions are what is distributed, not the starts) and logs
-        the parameters of its own partitions"""
+        complete records (the parameters of all partitions)"""
         return self._call(self.m.search, *a, **kw)
 
     def exhaustive_search(self, *a, **kw):
         return self._call(self.m.exhaustive_search, *a, **kw)
 
     def set_checkpoint(self, prefix):
-        """every rank logs the results with the parameters of ITS partitions: one file per rank
-        ("<prefix>.part<rank>of<nranks>.ckp"), never a shared one -- a record read back by another
-        rank would carry the wrong partitions' parameters"""
+        """one log per rank ("<prefix>.part<rank>of<nranks>.ckp"), never a shared file (two ranks
+        would both append every record).  Each holds COMPLETE records -- model_t gathers the fitted
+        parameters of all partitions through the exchange -- so any of them is a checkpoint of the
+        whole run in the reference's format."""
         if prefix is not None:
             prefix = "%s.part%dof%d" % (prefix, self.rank, self.nranks)
         return self.m.set_checkpoint(prefix)

@@ -189,8 +189,22 @@ def test_two_rank_gloo_partition_sharding_matches_single_process():
     assert np.array_equal(got.view(np.uint64), want.view(np.uint64))
 
 
-SEARCH_ARGS = dict(min_roots=2, root_ratio=0.05, atol=1e-3, pgtol=1e-3, brtol=1e-4, factor=1e12)
+SEARCH_ARGS = dict(min_roots=1, root_ratio=0.05, atol=1e-3, pgtol=1e-3, brtol=1e-4, factor=1e12)
 EXHAUSTIVE_ARGS = (1e-2, 1e-2, 1e-3, 1e13)
+
+
+def _checkpoint_records(prefix, lib):
+    """every record of "<prefix>.ckp" with the parameters of all of its partitions, as one flat array"""
+    from root_digger_b200 import capi
+    ck = capi.Checkpoint(prefix, lib=lib)
+    rows = []
+    for i, (rid, llh, alpha, nparts) in enumerate(ck.read_results()):
+        rows += [float(rid), llh, alpha, float(nparts)]
+        for part in range(nparts):
+            pr = ck.read_params(i, part, K=2)
+            rows += pr["rates"].tolist() + pr["freqs"].tolist() + [pr["alpha"]]
+    ck.close()
+    return np.array(rows)
 
 
 def _whole_model_results(m, strategy):
@@ -205,13 +219,14 @@ def _whole_model_results(m, strategy):
         out.append(m.optimize_alpha(rid, 0.5, 1e-9))
     rid, alpha, lh = m.search(strategy=strategy, **SEARCH_ARGS)
     out += [float(rid), alpha, lh]
+    out += [m.compute_lh(rid, alpha)]  # with the parameters the best record put back
     m.set_max_outer_iterations(2)
-    ids, llh, al = m.exhaustive_search(*EXHAUSTIVE_ARGS, rank=0, num_tasks=6)
+    ids, llh, al = m.exhaustive_search(*EXHAUSTIVE_ARGS, rank=0, num_tasks=9)
     out += ids.astype(np.float64).tolist() + llh.tolist() + al.tolist() + m.lwr(llh).tolist()
     return np.array(out)
 
 
-def _partition_search_worker(rank, world, port, strategy, q):
+def _partition_search_worker(rank, world, port, strategy, q, ckp_prefix=None):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
                       OMP_NUM_THREADS="2")  # two ranks share the test machine
     sys.path.insert(0, str(ROOT))
@@ -230,6 +245,8 @@ def _partition_search_worker(rank, world, port, strategy, q):
     m = capi.Model(tree, fx["alignment"], rate_cats=2, compress=True, seed=11, early_stop=True, partitions=mine)
     sm = sharding.PartitionShardedModel(m, len(PARTS), rank, world, dist)
     sm.initialize_partitions(uniform_freqs=False)
+    if ckp_prefix:
+        sm.set_checkpoint(ckp_prefix)  # one file per rank: "<prefix>.part<rank>of<world>.ckp"
     got = _whole_model_results(sm, strategy)
     q.put((rank, got, sm.exchanges))
     dist.barrier()
@@ -237,7 +254,7 @@ def _partition_search_worker(rank, world, port, strategy, q):
 
 
 @pytest.mark.parametrize("strategy", ["random", "modified_mad"])
-def test_two_rank_gloo_partition_sharded_search_matches_single_process(strategy):
+def test_two_rank_gloo_partition_sharded_search_matches_single_process(strategy, tmp_path):
     """SURVEY 8e-3 for the WHOLE of model_t: with the sums over partitions completed inside model_t
     (set_partition_exchange), compute_dlh, optimize_alpha, search (ranked and shuffled starts -- the
     shuffle needs the ranks' generators in step with a single process's) and exhaustive mode + LWR on
@@ -254,14 +271,18 @@ def test_two_rank_gloo_partition_sharded_search_matches_single_process(strategy)
     tree = capi.RootedTree(path=str(fx["tree_path"]), lib=lib)
     m = capi.Model(tree, fx["alignment"], rate_cats=2, compress=True, seed=11, early_stop=True, partitions=PARTS)
     m.initialize_partitions(uniform_freqs=False)
+    m.set_checkpoint(str(tmp_path / "one"))
     want = _whole_model_results(m, strategy)
     m.close()
+    want_log = _checkpoint_records(str(tmp_path / "one"), lib)
+    assert len(want_log) > 4 + 3 * 17  # at least one record carrying the parameters of the three partitions
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_partition_search_worker, args=(r, 2, port, strategy, q)) for r in range(2)]
+    procs = [ctx.Process(target=_partition_search_worker, args=(r, 2, port, strategy, q, str(tmp_path / "two")))
+             for r in range(2)]
     for p in procs:
         p.start()
     import queue
@@ -281,6 +302,11 @@ def test_two_rank_gloo_partition_sharded_search_matches_single_process(strategy)
         assert np.array_equal(got.view(np.uint64), want.view(np.uint64)), (r, got, want)
         assert exchanges > 20
     assert results[0][1] == results[1][1], "both ranks took part in the same collectives"
+    # every rank's log holds COMPLETE records -- the parameters of all three partitions, gathered
+    # through the same exchange -- equal to the single process's log, byte for byte in content
+    for r in (0, 1):
+        got_log = _checkpoint_records(str(tmp_path / ("two.part%dof2" % r)), lib)
+        assert np.array_equal(got_log.view(np.uint64), want_log.view(np.uint64)), r
 
 
 def test_partition_exchange_argument_checks():
