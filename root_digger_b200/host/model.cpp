@@ -437,8 +437,9 @@ uint64_t model_t::rng_state() const {
 
 void model_t::set_rng_state(uint64_t state) { _random_engine.seed((std::minstd_rand::result_type)state); }
 
-int model_t::first_partition_without_empirical_freqs() {
+int model_t::first_partition_without_empirical_freqs(const std::vector<msa_t> &msa) {
   for (size_t p = 0; p < _partitions.size(); ++p) {
+    set_tip_states(p, msa[p]);  // the frequencies are counted over the tips; setting them twice is harmless
     double *emp = rdk_msa_empirical_frequencies(_partitions[p]);
     if (!emp) throw std::runtime_error("empirical frequencies failed: " + engine_error());
     const bool degenerate = std::any_of(emp, emp + _partitions[p]->states, [](double f) { return f <= 0; });

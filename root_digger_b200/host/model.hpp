@@ -144,8 +144,9 @@ public:
   uint64_t rng_state() const;
   void     set_rng_state(uint64_t state);
   void     discard_rng(unsigned long long draws) { _random_engine.discard(draws); }
-  // the first local partition whose empirical frequencies have a zero entry, or -1
-  int first_partition_without_empirical_freqs();
+  // the first local partition whose empirical frequencies have a zero entry, or -1 (loads the tips
+  // of `msa`, the alignments initialize_partitions* will be given; draws nothing)
+  int first_partition_without_empirical_freqs(const std::vector<msa_t> &msa);
 
   void move_root(const root_location_t &new_root);
   // use the fused engine entry points (rdk_sweep_root_placements) where the

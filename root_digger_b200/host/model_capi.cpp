@@ -217,7 +217,7 @@ extern "C" void rdh_model_discard_rng(void *h, unsigned long long draws) { H(h).
 // first local partition whose empirical frequencies have a zero entry: -1 none, -2 error
 extern "C" int rdh_model_first_partition_without_empirical_freqs(void *h) {
   try {
-    return H(h).model->first_partition_without_empirical_freqs();
+    return H(h).model->first_partition_without_empirical_freqs(H(h).msa);
   } catch (const std::exception &e) {
     rdh_set_error(e.what());
     return -2;

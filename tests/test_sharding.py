@@ -365,3 +365,147 @@ def test_sweep_chunk_count_is_agreed_across_site_shards():
     solo = [capi.Model(capi.RootedTree(case.newick, lib=lib), {l: s[:n] for l, s in case.aln.items()},
                        rate_cats=4).sweep_chunks for n in (4096, 3904)]
     assert solo == [1, 3]
+
+
+def test_generator_state_round_trip_and_failed_initialisation_keeps_ranks_in_step():
+    """what PartitionShardedModel.initialize_partitions relies on when a partition has no empirical
+    frequencies: the model's generator can be read, put back and advanced (std::minstd_rand is one
+    integer), and an initialisation that throws half way leaves it as many draws further as the
+    partitions it got through -- so the ranks that did NOT fail can be put where the failing one is"""
+    import ctypes as C
+    import fixtures
+    import oracle_capi
+    import oracle_build
+    from root_digger_b200 import capi
+    oracle_capi.load_oracle().rdo_set_default_mode(oracle_capi.MODE_ENGINE)
+    lib = capi.load_tree_lib(oracle_build.build_host_on_oracle())
+    fx = fixtures.load("10.fasta")
+
+    def model(aln, parts):
+        m = capi.Model(capi.RootedTree(path=str(fx["tree_path"]), lib=lib), aln, rate_cats=1, seed=99, partitions=parts)
+        m.L.rdh_model_rng_state.argtypes = [C.c_void_p]
+        m.L.rdh_model_rng_state.restype = C.c_ulonglong
+        m.L.rdh_model_set_rng_state.argtypes = [C.c_void_p, C.c_ulonglong]
+        m.L.rdh_model_set_rng_state.restype = None
+        m.L.rdh_model_discard_rng.argtypes = [C.c_void_p, C.c_ulonglong]
+        m.L.rdh_model_discard_rng.restype = None
+        m.L.rdh_model_first_partition_without_empirical_freqs.argtypes = [C.c_void_p]
+        return m
+
+    m = model(fx["alignment"], PARTS)
+    L, h = m.L, m.h
+    s0 = L.rdh_model_rng_state(h)
+    first = m.assign_indicies("search", 5, 0.0, 0, 1, strategy="random")
+    assert L.rdh_model_rng_state(h) != s0
+    L.rdh_model_set_rng_state(h, s0)
+    assert m.assign_indicies("search", 5, 0.0, 0, 1, strategy="random") == first        # same state, same shuffle
+    L.rdh_model_set_rng_state(h, s0)
+    L.rdh_model_discard_rng(h, 1)
+    assert m.assign_indicies("search", 5, 0.0, 0, 1, strategy="random") != first
+    # one draw per partition: initialize_partitions advances the generator by exactly len(PARTS) draws
+    L.rdh_model_set_rng_state(h, s0)
+    m.initialize_partitions(uniform_freqs=False)
+    after_init = L.rdh_model_rng_state(h)
+    L.rdh_model_set_rng_state(h, s0)
+    L.rdh_model_discard_rng(h, len(PARTS))
+    assert L.rdh_model_rng_state(h) == after_init
+    assert L.rdh_model_first_partition_without_empirical_freqs(h) == -1
+    m.close()
+
+    # no G in the columns of the middle partition: its empirical frequency of G is zero
+    aln = {}
+    for label, seq in fx["alignment"].items():
+        seq = seq if isinstance(seq, str) else seq.decode()
+        b, e = PARTS[1]
+        aln[label] = seq[:b] + seq[b:e].replace("G", "A").replace("g", "a") + seq[e:]
+    bad = model(aln, PARTS)
+    L, h = bad.L, bad.h
+    assert L.rdh_model_first_partition_without_empirical_freqs(h) == 1
+    s0 = L.rdh_model_rng_state(h)
+    with pytest.raises(RuntimeError, match="frequen"):
+        bad.initialize_partitions(uniform_freqs=False)
+    failed_at = L.rdh_model_rng_state(h)
+    L.rdh_model_set_rng_state(h, s0)
+    L.rdh_model_discard_rng(h, 1)            # partition 0 drew, partition 1 threw before its draw
+    assert L.rdh_model_rng_state(h) == failed_at
+    bad.initialize_partitions(uniform_freqs=True)   # what RootDigger's main falls back to
+    bad.close()
+
+
+def _no_g_in_partition(aln, part):
+    out = {}
+    for label, seq in aln.items():
+        seq = seq if isinstance(seq, str) else seq.decode()
+        b, e = part
+        out[label] = seq[:b] + seq[b:e].replace("G", "A").replace("g", "a") + seq[e:]
+    return out
+
+
+def _starts_after_fallback(m):
+    """RootDigger's main (src/main.cpp:560-589): empirical frequencies, uniform ones if they are invalid;
+    then the shuffled starts of a search and one evaluation"""
+    try:
+        m.initialize_partitions(uniform_freqs=False)
+        fell_back = 0.0
+    except RuntimeError:
+        m.initialize_partitions(uniform_freqs=True)
+        fell_back = 1.0
+    starts = m.assign_indicies("search", 6, 0.0, 0, 1, strategy="random")
+    return np.array([fell_back] + [float(s) for s in starts] + [m.compute_lh(int(starts[0]), 0.5)])
+
+
+def _fallback_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      OMP_NUM_THREADS="2")
+    sys.path.insert(0, str(ROOT))
+    sys.path.insert(0, str(ROOT / "tests"))
+    import torch.distributed as dist
+    import fixtures
+    import oracle_capi
+    import oracle_build
+    from root_digger_b200 import capi
+    oracle_capi.load_oracle().rdo_set_default_mode(oracle_capi.MODE_ENGINE)
+    lib = capi.load_tree_lib(oracle_build.build_host_on_oracle())
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    fx = fixtures.load("10.fasta")
+    aln = _no_g_in_partition(fx["alignment"], PARTS[1])
+    mine = [PARTS[p] for p in sharding.plan_partition_shards(len(PARTS), world)[rank]]
+    m = capi.Model(capi.RootedTree(path=str(fx["tree_path"]), lib=lib), aln, rate_cats=1, seed=99, partitions=mine)
+    sm = sharding.PartitionShardedModel(m, len(PARTS), rank, world, dist)
+    q.put((rank, _starts_after_fallback(sm)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_failed_empirical_frequencies_fail_on_every_rank_and_keep_them_in_step():
+    """partition 1 (held by rank 1) has no G: a single process throws when its initialisation gets
+    there, falls back to uniform frequencies and shuffles its starts with a generator that is one
+    draw (partition 0's) + three draws further.  On shards BOTH ranks must raise -- rank 0 holds only
+    healthy partitions -- and end up with the same starts and the same likelihood as that process"""
+    import torch.multiprocessing as mp
+    import fixtures
+    import oracle_capi
+    import oracle_build
+    from root_digger_b200 import capi
+    oracle_capi.load_oracle().rdo_set_default_mode(oracle_capi.MODE_ENGINE)
+    lib = capi.load_tree_lib(oracle_build.build_host_on_oracle())
+    fx = fixtures.load("10.fasta")
+    aln = _no_g_in_partition(fx["alignment"], PARTS[1])
+    m = capi.Model(capi.RootedTree(path=str(fx["tree_path"]), lib=lib), aln, rate_cats=1, seed=99, partitions=PARTS)
+    want = _starts_after_fallback(m)
+    m.close()
+    assert want[0] == 1.0
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_fallback_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = dict(q.get(timeout=240) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r in (0, 1):
+        assert np.array_equal(results[r].view(np.uint64), want.view(np.uint64)), (r, results[r], want)
