@@ -509,3 +509,54 @@ def test_two_rank_gloo_failed_empirical_frequencies_fail_on_every_rank_and_keep_
         assert p.exitcode == 0
     for r in (0, 1):
         assert np.array_equal(results[r].view(np.uint64), want.view(np.uint64)), (r, results[r], want)
+
+
+def test_partition_exchange_failures_surface_and_detach_restores_the_local_model():
+    """a failing all-gather cannot raise through the C++ frames: the sums are poisoned, model_t refuses
+    the NaN and the wrapper reports the cause; close() detaches the exchange; without the in-model
+    exchange the calls that need global sums inside model_t are refused"""
+    import fixtures
+    import oracle_capi
+    import oracle_build
+    from root_digger_b200 import capi
+    oracle_capi.load_oracle().rdo_set_default_mode(oracle_capi.MODE_ENGINE)
+    lib = capi.load_tree_lib(oracle_build.build_host_on_oracle())
+    fx = fixtures.load("10.fasta")
+    m = capi.Model(capi.RootedTree(path=str(fx["tree_path"]), lib=lib), fx["alignment"], rate_cats=1, seed=3,
+                   partitions=PARTS[:2])
+    m.initialize_partitions(uniform_freqs=False)
+    alone = m.compute_lh(2, 0.5)
+
+    class Broken:
+        def all_gather(self, out, buf):
+            raise OSError("the network is down")
+
+    class Loopback:  # one rank: the gathered terms are the local ones
+        def all_gather(self, out, buf):
+            out[0].copy_(buf)
+
+    sm = sharding.PartitionShardedModel(m, 2, 0, 1, Broken())
+    with pytest.raises(RuntimeError, match="partition exchange failed.*network is down"):
+        sm.compute_lh(2, 0.5)
+    sm.close()
+    m2 = capi.Model(capi.RootedTree(path=str(fx["tree_path"]), lib=lib), fx["alignment"], rate_cats=1, seed=3,
+                    partitions=PARTS[:2])
+    m2.initialize_partitions(uniform_freqs=False)
+    ok = sharding.PartitionShardedModel(m2, 2, 0, 1, Loopback())
+    assert ok.compute_lh(2, 0.5).hex() == alone.hex() and ok.exchanges == 1
+    ok.set_params(1, rates=_rates_of(1))   # a GLOBAL partition index
+    ok.set_params(5, rates=_rates_of(2))   # not held here: ignored
+    changed = ok.compute_lh(2, 0.5)
+    assert changed != alone and ok.exchanges == 2
+    ok.close()
+    assert m2.compute_lh(2, 0.5).hex() == changed.hex() and ok.exchanges == 2   # detached: no further exchange
+    m2.close()
+
+    m3 = capi.Model(capi.RootedTree(path=str(fx["tree_path"]), lib=lib), fx["alignment"], rate_cats=1, seed=3,
+                    partitions=PARTS[:2])
+    m3.initialize_partitions(uniform_freqs=False)
+    outside = sharding.PartitionShardedModel(m3, 2, 0, 1, Loopback(), in_model=False)
+    assert outside.compute_lh(2, 0.5).hex() == alone.hex()
+    with pytest.raises(RuntimeError, match="in_model=True"):
+        outside.optimize_alpha(2, 0.5, 1e-7)
+    m3.close()
