@@ -79,6 +79,19 @@ def plan_grid(nranks: int, n_taxa: int, sites: int, rate_cats: int = 4, budget_b
     return nranks, 1
 
 
+def _exchange_fn_type():
+    """the C type of model_t::partition_exchange_fn, created once: every instance must hand ctypes the
+    same class it declared in argtypes"""
+    import ctypes as C
+    global _EXCHANGE_FN
+    try:
+        return _EXCHANGE_FN
+    except NameError:
+        _EXCHANGE_FN = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.c_size_t, C.c_size_t, C.POINTER(C.c_double),
+                                   C.c_void_p)
+        return _EXCHANGE_FN
+
+
 class PartitionShardedModel:
     """BASELINE cfg4: the partitions of a multi-partition alignment are dealt out to
     the ranks (`plan_partition_shards`: partition p lives on rank p % nranks); every rank holds a
@@ -116,7 +129,7 @@ class PartitionShardedModel:
         self._exchange = None
         if not self.in_model:
             return
-        fn_t = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.c_size_t, C.c_size_t, C.POINTER(C.c_double), C.c_void_p)
+        fn_t = _exchange_fn_type()
 
         def exchange(local_ptr, n_local, count, all_ptr, _user):
             import numpy as np
@@ -148,8 +161,7 @@ class PartitionShardedModel:
     def close(self):
         import ctypes as C
         if self.m is not None and self.m.h and self._exchange is not None:
-            self.m.L.rdh_model_set_partition_exchange(self.m.h, None, 0, 0,
-                                                      C.cast(None, type(self._exchange)), None)
+            self.m.L.rdh_model_set_partition_exchange(self.m.h, None, 0, 0, C.cast(None, _exchange_fn_type()), None)
         self.m = None
 
     def _gather_terms(self, local):

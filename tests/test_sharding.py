@@ -538,7 +538,6 @@ def test_partition_exchange_failures_surface_and_detach_restores_the_local_model
     sm = sharding.PartitionShardedModel(m, 2, 0, 1, Broken())
     with pytest.raises(RuntimeError, match="partition exchange failed.*network is down"):
         sm.compute_lh(2, 0.5)
-    sm.close()
     m2 = capi.Model(capi.RootedTree(path=str(fx["tree_path"]), lib=lib), fx["alignment"], rate_cats=1, seed=3,
                     partitions=PARTS[:2])
     m2.initialize_partitions(uniform_freqs=False)
@@ -551,6 +550,9 @@ def test_partition_exchange_failures_surface_and_detach_restores_the_local_model
     ok.close()
     assert m2.compute_lh(2, 0.5).hex() == changed.hex() and ok.exchanges == 2   # detached: no further exchange
     m2.close()
+    sm.close()   # several wrappers alive at once, closed in any order
+    assert m.compute_lh(2, 0.5).hex() == alone.hex()
+    m.close()
 
     m3 = capi.Model(capi.RootedTree(path=str(fx["tree_path"]), lib=lib), fx["alignment"], rate_cats=1, seed=3,
                     partitions=PARTS[:2])
